@@ -1,0 +1,234 @@
+/*
+ * solb.h — C ABI of libsolb.so, the B200 (sm_100a) replacement for the ray-tracing hot path of
+ * num3ric/sol-rs.  Everything below is `extern "C"`, POD-only, plain pointers and sizes.
+ *
+ * The reference has no FFI/plugin boundary of its own (it is a Rust crate that drives the Vulkan
+ * driver directly), so each entry point names the reference call(s) a Rust shim
+ * (rust/sol/) replaces with it.  Paths are relative to the reference root.
+ *
+ * Conventions
+ *   - every function returns int: SOLB_OK (0) or a negative SolbStatus; text via solb_last_error().
+ *   - never aborts / throws across the ABI.  The Rust shim turns non-zero into panic!() to keep
+ *     the reference's unwrap()/expect() behaviour (src/scene/mod.rs:140, src/ray/pipeline.rs:105).
+ *   - one ctx = one CUDA device + one stream; a ctx is not thread-safe (the reference is
+ *     single-threaded: src/lib.rs:174).  Multi-GPU = one ctx per device / process.
+ *   - host pointers passed in are copied during the call and never retained
+ *     (reference: Buffer::from_data copies, src/buffer.rs:186-206).
+ *   - matrices are column-major float[16] exactly as glam::Mat4 lays them out.
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with SOLB_ERR_CUDA.
+ */
+#ifndef SOLB_H
+#define SOLB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SOLB_API __declspec(dllexport)
+#else
+#define SOLB_API __attribute__((visibility("default")))
+#endif
+
+#define SOLB_VERSION 0x000100
+
+typedef enum SolbStatus {
+    SOLB_OK = 0,
+    SOLB_ERR_INVALID = -1,      /* bad argument / handle / size                         */
+    SOLB_ERR_CUDA = -2,         /* CUDA runtime error (no device, launch failure, OOM)   */
+    SOLB_ERR_NOT_BUILT = -3,    /* trace before solb_accel_build                         */
+    SOLB_ERR_UNSUPPORTED = -4,  /* e.g. non-indexed primitive (SURVEY App.A item 4)      */
+    SOLB_ERR_OVERFLOW = -5      /* internal capacity (traversal stack depth, queue)      */
+} SolbStatus;
+
+typedef struct solb_ctx solb_ctx;       /* replaces sol::Context for this path: src/context.rs        */
+typedef struct solb_scene solb_scene;   /* replaces ray::SceneDescription (+BLAS/TLAS): src/ray/mod.rs */
+typedef struct solb_target solb_target; /* replaces sol::Image2d storage targets: src/texture.rs:36-96 */
+
+/* ---- POD data contracts (identical bytes to the reference) ------------- */
+
+/* src/scene/mesh.rs:9-14; assets/glsl/pathtrace.rchit:11-16 */
+typedef struct SolbModelVertex { float pos[4], color[4], normal[4], uv[4]; } SolbModelVertex; /* 64 B */
+
+/* src/scene/mod.rs:19-29; assets/glsl/pathtrace.rchit:18-26 */
+typedef struct SolbMaterialInfo {
+    float base_color[4];
+    float emissive[3];
+    float padding0;
+    float metallic, roughness, padding1, padding2;
+} SolbMaterialInfo; /* 48 B */
+
+/* src/ray/mod.rs:16-24; assets/glsl/pathtrace.rchit:28-35 */
+typedef struct SolbSceneInstance {
+    uint32_t id, texture_offset;
+    float padding[2];
+    float transform[16];
+    float transform_it[16];
+} SolbSceneInstance; /* 144 B */
+
+/* examples/5-pathtrace.rs:7-17; assets/glsl/pathtrace.rgen:13-21.  Only view_inverse,
+ * projection_inverse and frame[2] are read by the ray-tracing stages. */
+typedef struct SolbSceneUniforms {
+    float model[16], view[16], view_inverse[16], projection[16], projection_inverse[16], model_view_projection[16];
+    uint32_t frame[3]; /* (width, height, elapsed_ticks) */
+    uint32_t _pad;
+} SolbSceneUniforms; /* 400 B */
+
+/* scene::PrimitiveSection (src/scene/mod.rs:37-44): one section -> one BLAS -> one instance */
+typedef struct SolbSection {
+    uint32_t first_vertex, n_vertices; /* BufferPart vertices (ModelVertex units, within the mesh)  */
+    uint32_t first_index, n_indices;   /* BufferPart indices (u32 units, within the mesh)           */
+    uint32_t material_index;           /* into the scene's material array                           */
+} SolbSection;
+
+/* scene::Mesh (src/scene/mesh.rs:53-61) as host arrays */
+typedef struct SolbMeshDesc {
+    const SolbModelVertex *vertices; uint32_t n_vertices;
+    const uint32_t *indices; uint32_t n_indices; /* section-relative, as glTF stores them */
+    const SolbSection *sections; uint32_t n_sections;
+    float transform[16]; /* Mesh::transform, column-major */
+} SolbMeshDesc;
+
+typedef enum SolbTargetFormat {
+    SOLB_FORMAT_RGBA32F = 0, /* vk R32G32B32A32_SFLOAT: accumulation image, examples/5-pathtrace.rs:222 */
+    SOLB_FORMAT_RGBA8 = 1,   /* vk R8G8B8A8_UNORM: render image, examples/5-pathtrace.rs:229           */
+    SOLB_FORMAT_RG32UI = 2   /* (instance, primitive) ids of the primary hit; 0xffffffff = miss        */
+} SolbTargetFormat;
+
+typedef enum SolbSchedule {
+    SOLB_SCHEDULE_WAVEFRONT = 0, /* queue-based wavefront: persistent trace kernel + shade/compact kernels */
+    SOLB_SCHEDULE_MEGAKERNEL = 1 /* one thread per pixel, flattened bounce loop                           */
+} SolbSchedule;
+
+typedef enum SolbAccumMode {
+    SOLB_ACCUM_MIX = 0, /* reference: new = mix(old, frame, 1/(frame+1-start)), pathtrace.rgen:89-101 */
+    SOLB_ACCUM_SUM = 1  /* multi-GPU: accum.xyz += frame colour, accum.w += 1 (resolved later)         */
+} SolbAccumMode;
+
+/* Everything the reference passes besides the uniform block: the push constant
+ * (examples/5-pathtrace.rs:306-314), specialization constant 0 (:103) and the shader literals
+ * (pathtrace.rgen:43-44; ao.rgen:42-43), which BASELINE.json's configs need as parameters.
+ * solb_trace_params_default() fills the reference values. */
+typedef struct SolbTraceParams {
+    int32_t accum_start_frame;  /* push.accum_start_frame                              */
+    uint32_t enable_sky;        /* ENABLE_SKYLIGHT specialization constant             */
+    uint32_t samples_per_frame; /* sampleCount literal: 8 (pathtrace), 4 (ao)          */
+    uint32_t max_bounces;       /* maxBounces literal: 32 (pathtrace); ao: max_samples 4 */
+    uint32_t schedule;          /* SolbSchedule                                        */
+    uint32_t accum_mode;        /* SolbAccumMode                                       */
+    uint32_t collect_stats;     /* 1: instrumented kernels count nodes / triangles per ray */
+    uint32_t _pad;
+} SolbTraceParams;
+
+typedef struct SolbStats {
+    uint64_t rays;            /* traceRayEXT-equivalents since last reset                     */
+    uint64_t hits;            /* closest-hit invocations                                      */
+    uint64_t paths;           /* samples started                                              */
+    uint64_t nodes_visited;   /* 8-wide nodes fetched   (collect_stats only)                  */
+    uint64_t tris_tested;     /* triangle records fetched (collect_stats only)                */
+    uint64_t kernel_launches; /* kernels launched by this ctx                                 */
+    float last_build_ms;      /* solb_accel_build / tlas_regenerate device time               */
+    float last_trace_ms;      /* last solb_trace_* device time (only when timing is enabled)  */
+    /* timing mode only: cudaEvent pairs around every launch of the dominant (traversal) kernel */
+    float trace_kernel_ms_total;     /* summed duration of k_wf_trace / k_pathtrace_mega launches since reset */
+    uint32_t trace_kernel_launches;  /* number of those launches                                              */
+} SolbStats;
+
+typedef struct SolbAccelInfo {
+    uint32_t n_instances, n_triangles;
+    uint32_t n_wide_nodes;    /* 80-byte 8-wide nodes               */
+    uint32_t wide_depth;      /* depth of the 8-wide tree           */
+    uint32_t n_binary_nodes;
+    float sah_cost_binary;    /* SAH cost of the binary tree (after treelet pass)      */
+    float sah_cost_lbvh;      /* SAH cost of the raw LBVH (before treelet pass)        */
+    float scene_lo[3], scene_hi[3];
+} SolbAccelInfo;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Replaces Context/SharedContext creation (src/context.rs:239-369) for this path.
+ * `stream` is a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */
+SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out);
+SOLB_API int solb_ctx_destroy(solb_ctx *ctx);
+SOLB_API int solb_synchronize(solb_ctx *ctx); /* queue_wait_idle, src/context.rs:539-559 */
+SOLB_API const char *solb_last_error(solb_ctx *ctx); /* ctx may be NULL: last global error */
+SOLB_API uint32_t solb_version(void);
+SOLB_API int solb_stats_get(solb_ctx *ctx, SolbStats *out); /* synchronises */
+SOLB_API int solb_stats_reset(solb_ctx *ctx);
+SOLB_API int solb_set_timing(solb_ctx *ctx, int enabled); /* cudaEvent pair around each trace/build (renderer.rs:204-225 idea) */
+
+/* ---- scene / acceleration structure -------------------------------------------------------- */
+
+/* Replaces SceneDescription::from_meshes up to (not including) the BLAS/TLAS builds
+ * (src/ray/mod.rs:59-156): flattens meshes x sections into instances (id = running count),
+ * uploads vertices / indices / per-instance material + transform. */
+SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32_t n_meshes,
+                               const SolbMaterialInfo *materials, uint32_t n_materials, solb_scene **out);
+SOLB_API int solb_scene_destroy(solb_scene *scene);
+
+/* Replaces BLAS::new per section + TLAS::new (src/ray/acceleration.rs:136-239,344-400): GPU build of
+ * the acceleration structure (Morton LBVH -> treelet SAH -> 8-wide compressed nodes). */
+SOLB_API int solb_accel_build(solb_scene *scene);
+
+/* Replaces SceneDescription::blas_transform (src/ray/mod.rs:162-167): sets instance `index`'s
+ * transform (and transform_it = inverse().transpose()) on the host copy and marks the TLAS dirty. */
+SOLB_API int solb_instance_set_transform(solb_scene *scene, uint32_t index, const float transform[16]);
+/* Replaces SceneDescription::update (src/ray/mod.rs:190-192): uploads the instance buffer. */
+SOLB_API int solb_scene_update(solb_scene *scene);
+/* Replaces SceneDescription::tlas_regenerate -> TLAS::regenerate (src/ray/acceleration.rs:402-467).
+ * The reference rebuilds every frame; here it is a no-op unless a transform changed. */
+SOLB_API int solb_tlas_regenerate(solb_scene *scene);
+
+SOLB_API int solb_scene_instance_count(solb_scene *scene, uint32_t *out);
+/* SceneDescription::instances as the shader sees them (get_instances_buffer, src/ray/mod.rs:186) */
+SOLB_API int solb_scene_get_instances(solb_scene *scene, SolbSceneInstance *out, uint32_t capacity);
+SOLB_API int solb_accel_info(solb_scene *scene, SolbAccelInfo *out);
+/* test/inspection hooks: copy the built structure back (80 B nodes, 48 B triangle records) */
+SOLB_API int solb_accel_read_nodes(solb_scene *scene, void *host, size_t bytes);
+SOLB_API int solb_accel_read_triangles(solb_scene *scene, void *host, size_t bytes);
+
+/* ---- targets ------------------------------------------------------------------------------- */
+
+/* Replaces create_image_target (examples/5-pathtrace.rs:57-80): zero-initialised. */
+SOLB_API int solb_target_create(solb_ctx *ctx, uint32_t width, uint32_t height, uint32_t format, solb_target **out);
+SOLB_API int solb_target_destroy(solb_target *t);
+SOLB_API int solb_target_clear(solb_target *t);
+/* Replaces cmd_blit_to(present image) (examples/5-pathtrace.rs:360-361): D2H of the whole image. Synchronises. */
+SOLB_API int solb_target_readback(solb_target *t, void *host, size_t bytes);
+SOLB_API int solb_target_upload(solb_target *t, const void *host, size_t bytes);
+SOLB_API int solb_target_device_ptr(solb_target *t, void **out); /* for torch.distributed / NCCL plumbing */
+SOLB_API int solb_target_info(solb_target *t, uint32_t *width, uint32_t *height, uint32_t *format);
+
+/* ---- trace launches: each replaces ShaderBindingTable::cmd_trace_rays (src/ray/sbt.rs:167-180)
+ *      for one of the three pipelines built by ray::Pipeline::new (src/ray/pipeline.rs:61-122) ---- */
+
+SOLB_API void solb_trace_params_default(SolbTraceParams *p, int pipeline /* 0 pathtrace, 1 ao */);
+
+/* 5-pathtrace: assets/glsl/pathtrace.{rgen,rchit,rmiss}.  accum RGBA32F in/out, render RGBA8 out (may be NULL). */
+SOLB_API int solb_trace_pathtrace(solb_scene *scene, const SolbSceneUniforms *uniforms, const SolbTraceParams *params,
+                                  solb_target *accum, solb_target *render);
+/* 4-ray-ao: assets/glsl/ao.{rgen,rchit,rmiss}.  image RGBA32F in/out; blue_noise = host rgba8[w*h],
+ * rows already flipped like Texture2d::new does (src/texture.rs:490-493); uploaded once per pointer change. */
+SOLB_API int solb_set_blue_noise(solb_ctx *ctx, const uint8_t *rgba8, uint32_t width, uint32_t height);
+SOLB_API int solb_trace_ao(solb_scene *scene, const SolbSceneUniforms *uniforms, const SolbTraceParams *params,
+                           solb_target *image);
+/* 3-ray-debug: assets/glsl/debug.{rgen,rchit,rmiss}.  render RGBA8 out; ids RG32UI out (optional): the
+ * (gl_InstanceID, gl_PrimitiveID) of the primary hit that north_star's parity gate needs;
+ * attribs RGBA32F out (optional): (u, v, t, 0). */
+SOLB_API int solb_trace_debug(solb_scene *scene, const SolbSceneUniforms *uniforms, solb_target *render,
+                              solb_target *ids, solb_target *attribs);
+/* traceRayEXT itself (assets/glsl/pathtrace.rgen:65-76) for arbitrary host rays:
+ * rays[i] = {ox,oy,oz,tmin, dx,dy,dz,tmax}; hits[i] = {instance, primitive, bits(u), bits(v)}; t optional. */
+SOLB_API int solb_trace_rays(solb_scene *scene, const float *rays, uint32_t n, uint32_t *hits, float *t_out);
+
+/* ---- multi-GPU resolve: out = sum.xyz / sum.w with the reference's display transform ---- */
+/* accum_out RGBA32F (may alias sum), render RGBA8 (may be NULL). */
+SOLB_API int solb_resolve_sum(solb_ctx *ctx, solb_target *sum, solb_target *accum_out, solb_target *render);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLB_H */

@@ -1,0 +1,453 @@
+// build.cu — GPU acceleration-structure build for sm_100a.
+//
+// Replaces BLAS::new / TLAS::new / TLAS::regenerate (src/ray/acceleration.rs:136-239,344-467):
+//   world-space triangle setup -> 63-bit Morton codes -> LSD radix sort (8-bit digits, warp
+//   match-any ranking) -> Karras hierarchy -> bottom-up refit fused with treelet SAH restructuring
+//   -> level-synchronous collapse into 80-byte 8-wide nodes + 48-byte triangles.
+// This TU is compiled with -Xptxas -dlcm=cg: the bottom-up passes read nodes written by other SMs in
+// the same launch, so global loads must not be served from a stale L1 line.
+#include "build.cuh"
+#include "solb_internal.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace solb {
+
+// ---------------------------------------------------------------------------------------------------
+// ordered-uint encoding so float min/max can use integer atomics
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// bounds[0..2] = min centroid (ordered), bounds[3..5] = max centroid (ordered)
+__global__ void k_init_bounds(uint32_t *bounds) {
+    if (threadIdx.x < 3) bounds[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+
+// One thread per global triangle g: fetch the section-relative indices, transform the three
+// positions object->world with the instance matrix (SceneInstance.transform, src/ray/mod.rs:22;
+// the driver would apply InstanceDescriptor.transform, acceleration.rs:330-331), emit the 48-byte
+// record, the primitive box and the centroid bounds.
+__global__ void k_prep_tris(const DeviceSceneView sv, Tri48 *tri_world, float4 *prim_lo, float4 *prim_hi, uint32_t *bounds) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 c = f3(0, 0, 0);
+    const bool valid = g < sv.n_tris;
+    if (valid) {
+        // binary search: last instance with first_tri <= g
+        uint32_t lo = 0, hi = sv.n_instances;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sv.inst_first_tri[mid] <= g) lo = mid; else hi = mid;
+        }
+        const uint32_t inst = lo;
+        const uint32_t prim = g - sv.inst_first_tri[inst];
+        const DeviceInstance di = sv.instances[inst];
+        float3 p[3];
+        for (int k = 0; k < 3; k++) {
+            const uint32_t vi = di.first_vertex + sv.indices[di.first_index + 3 * prim + k];
+            const float4 pos = sv.vertices[4 * (size_t)vi];
+            p[k] = mat4_mul_point(di.transform, f3(pos.x, pos.y, pos.z));
+        }
+        Tri48 t;
+        t.v0 = make_float4(p[0].x, p[0].y, p[0].z, __uint_as_float(inst));
+        t.v1 = make_float4(p[1].x, p[1].y, p[1].z, __uint_as_float(prim));
+        t.v2 = make_float4(p[2].x, p[2].y, p[2].z, __uint_as_float(g));
+        tri_world[g] = t;
+        const float3 lo3 = fmin3(p[0], fmin3(p[1], p[2])), hi3 = fmax3(p[0], fmax3(p[1], p[2]));
+        prim_lo[g] = make_float4(lo3.x, lo3.y, lo3.z, 0.0f);
+        prim_hi[g] = make_float4(hi3.x, hi3.y, hi3.z, 0.0f);
+        c = (lo3 + hi3) * 0.5f;
+    }
+    // warp-reduce centroid bounds, one atomic per warp per component
+    float mn[3] = { valid ? c.x : 3.4e38f, valid ? c.y : 3.4e38f, valid ? c.z : 3.4e38f };
+    float mx[3] = { valid ? c.x : -3.4e38f, valid ? c.y : -3.4e38f, valid ? c.z : -3.4e38f };
+    for (int off = 16; off; off >>= 1)
+        for (int k = 0; k < 3; k++) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], off));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
+        }
+    if ((threadIdx.x & 31) == 0 && mn[0] <= mx[0])
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&bounds[k], float_to_ordered(mn[k]));
+            atomicMax(&bounds[3 + k], float_to_ordered(mx[k]));
+        }
+}
+
+__global__ void k_morton(const float4 *prim_lo, const float4 *prim_hi, uint32_t n, const uint32_t *bounds, uint64_t *keys,
+                         uint32_t *vals) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const float3 lo = f3(ordered_to_float(bounds[0]), ordered_to_float(bounds[1]), ordered_to_float(bounds[2]));
+    const float3 hi = f3(ordered_to_float(bounds[3]), ordered_to_float(bounds[4]), ordered_to_float(bounds[5]));
+    const float3 ext = hi - lo;
+    const float3 inv = f3(ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f);
+    const float4 a = prim_lo[g], b = prim_hi[g];
+    const float3 c = f3((a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f);
+    keys[g] = morton63(c, lo, inv);
+    vals[g] = g;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, (u64 key, u32 value).  Per pass: tile histograms -> exclusive scan
+// (digit-major) -> stable scatter with warp match-any ranking (the ranking scheme of onesweep,
+// Adinets & Merrill 2022, without the chained look-back yet).
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *keys, uint32_t n, int shift, uint32_t *tile_hist,
+                                                        uint32_t num_tiles) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = base + i * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    tile_hist[threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// single-block exclusive scan of m elements (m = 256 * num_tiles), in place
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *data, uint32_t m) {
+    __shared__ uint32_t partial[1024];
+    const uint32_t chunk = (m + 1023u) / 1024u;
+    const uint32_t begin = min(threadIdx.x * chunk, m), end = min(begin + chunk, m);
+    uint32_t sum = 0;
+    for (uint32_t i = begin; i < end; i++) sum += data[i];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int off = 1; off < 1024; off <<= 1) {
+        uint32_t v = (threadIdx.x >= (uint32_t)off) ? partial[threadIdx.x - off] : 0u;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? partial[threadIdx.x - 1] : 0u;
+    for (uint32_t i = begin; i < end; i++) {
+        const uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                                                           uint32_t *vals_out, uint32_t n, int shift,
+                                                           const uint32_t *tile_offsets, uint32_t num_tiles) {
+    __shared__ uint32_t warp_hist[RS_WARPS][256];
+    __shared__ uint32_t digit_base[256];
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t chunk_base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+    uint64_t key[RS_ITEMS];
+    uint32_t val[RS_ITEMS], rank[RS_ITEMS], dig[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        const uint32_t idx = chunk_base + j * 32 + lane;
+        const bool valid = idx < n;
+        key[j] = valid ? keys_in[idx] : ~0ull;
+        val[j] = valid ? vals_in[idx] : 0u;
+        const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & 0xffu) : 0x100u;  // 0x100: padding lanes
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && (int)lane == leader) {
+            old = warp_hist[warp][d];
+            warp_hist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[j] = old + __popc(peers & lt_mask);
+        dig[j] = d;
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const uint32_t d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            const uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = run;
+            run += c;
+        }
+        digit_base[d] = tile_offsets[d * num_tiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        if (dig[j] < 0x100u) {
+            const uint32_t pos = digit_base[dig[j]] + warp_hist[warp][dig[j]] + rank[j];
+            keys_out[pos] = key[j];
+            vals_out[pos] = val[j];
+        }
+    }
+}
+
+// sorts (keys, vals) in place; tmp buffers must hold n elements each.  key_bits: number of low bits that vary.
+static cudaError_t radix_sort_pairs(cudaStream_t st, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
+                                    uint32_t n, int key_bits, uint32_t *tile_hist, uint64_t *launches) {
+    const uint32_t num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint64_t *kin = keys, *kout = keys_tmp;
+    uint32_t *vin = vals, *vout = vals_tmp;
+    int passes = (key_bits + 7) / 8;
+    if (passes & 1) passes++;  // even number of passes so the result lands back in (keys, vals)
+    for (int p = 0; p < passes; p++) {
+        const int shift = 8 * p;
+        k_rs_hist<<<num_tiles, RS_THREADS, 0, st>>>(kin, n, shift, tile_hist, num_tiles);
+        k_rs_scan<<<1, 1024, 0, st>>>(tile_hist, 256u * num_tiles);
+        k_rs_scatter<<<num_tiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, tile_hist, num_tiles);
+        *launches += 3;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// hierarchy: thread i builds internal node i (i < n-1) and leaf i (i < n)
+__global__ void k_hierarchy(const uint64_t *keys, const uint32_t *sorted_prim, const float4 *prim_lo, const float4 *prim_hi,
+                            int n, BNode *bn, int *parent, int *node_count, float *node_cost, uint32_t *flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    {
+        const uint32_t g = sorted_prim[i];
+        const float4 a = prim_lo[g], b = prim_hi[g];
+        BNode leaf;
+        leaf.lo = f3(a.x, a.y, a.z); leaf.hi = f3(b.x, b.y, b.z); leaf.left = -1; leaf.right = -1;
+        bn[n - 1 + i] = leaf;
+        node_count[n - 1 + i] = 1;
+        node_cost[n - 1 + i] = SOLB_SAH_CT * half_area(leaf.lo, leaf.hi);
+    }
+    if (i < n - 1) {
+        int l, r, first, last;
+        karras_node(keys, n, i, l, r, first, last);
+        bn[i].left = l;
+        bn[i].right = r;
+        parent[l] = i;
+        parent[r] = i;
+        flags[i] = 0;
+        if (i == 0) parent[0] = -1;
+    }
+}
+
+// bottom-up: second thread to arrive at a node owns it.  mode 0: refit only (boxes, counts, SAH cost);
+// mode 1: also restructure the treelet rooted at every node with at least `gamma` triangles.
+__global__ void k_bottom_up(int n, BNode *bn, int *parent, int *node_count, float *node_cost, uint32_t *flags, int mode, int gamma) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    TreeletScratch sc;
+    int node = parent[n - 1 + j];
+    while (node >= 0) {
+        __threadfence();
+        const uint32_t old = atomicAdd(&flags[node], 1u);
+        if (old == 0) return;  // the sibling subtree is not finished yet; its thread will continue
+        __threadfence();
+        const int l = bn[node].left, r = bn[node].right;
+        const float3 lo = fmin3(bn[l].lo, bn[r].lo), hi = fmax3(bn[l].hi, bn[r].hi);
+        bn[node].lo = lo;
+        bn[node].hi = hi;
+        const int cnt = node_count[l] + node_count[r];
+        node_count[node] = cnt;
+        node_cost[node] = leaf_or_internal_cost(half_area(lo, hi), node_cost[l] + node_cost[r], cnt);
+        if (mode == 1 && cnt >= gamma) optimize_treelet(bn, parent, node_cost, node_count, n - 1, node, sc);
+        node = parent[node];
+    }
+}
+
+__global__ void k_clear_u32(uint32_t *p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+__global__ void k_collapse_level(const BNode *bn, const int *node_count, int n_internal, const CollapseItem *queue_in,
+                                 uint32_t n_items, Node8 *wide, uint32_t *counters /*0: wide, 1: tris, 2: queue_out*/,
+                                 const uint32_t *sorted_prim, const Tri48 *tri_world, Tri48 *tri_out, CollapseItem *queue_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    collapse_one(bn, node_count, n_internal, queue_in[i], wide, &counters[0], &counters[1], sorted_prim, tri_world, tri_out,
+                 queue_out, &counters[2]);
+}
+
+// n == 1: a root with one single-triangle leaf
+__global__ void k_single_tri_root(const float4 *prim_lo, const float4 *prim_hi, const Tri48 *tri_world, Node8 *wide, Tri48 *tri_out) {
+    ChildRef ch[8];
+    for (int s = 0; s < 8; s++) ch[s].valid = 0;
+    const float3 lo = f3(prim_lo[0].x, prim_lo[0].y, prim_lo[0].z), hi = f3(prim_hi[0].x, prim_hi[0].y, prim_hi[0].z);
+    ch[0].valid = 1; ch[0].lo = lo; ch[0].hi = hi; ch[0].is_inner = 0; ch[0].tri_offset = 0; ch[0].tri_count = 1;
+    encode_node8(wide[0], lo, hi, 0, 0, ch);
+    tri_out[0] = tri_world[0];
+}
+
+__global__ void k_empty_root(Node8 *wide) {
+    ChildRef ch[8];
+    for (int s = 0; s < 8; s++) ch[s].valid = 0;
+    encode_node8(wide[0], f3(0, 0, 0), f3(0, 0, 0), 0, 0, ch);
+}
+
+// ---------------------------------------------------------------------------------------------------
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
+
+template <class T>
+static cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt, uint64_t *launches) {
+    cudaError_t err = cudaSuccess;
+    const uint32_t n = sv.n_tris;
+    Tri48 *tri_world = nullptr;
+    float4 *prim_lo = nullptr, *prim_hi = nullptr;
+    uint32_t *bounds = nullptr, *vals = nullptr, *vals_tmp = nullptr, *tile_hist = nullptr, *flags = nullptr, *counters = nullptr;
+    uint64_t *keys = nullptr, *keys_tmp = nullptr;
+    BNode *bn = nullptr;
+    int *parent = nullptr, *node_count = nullptr;
+    float *node_cost = nullptr;
+    CollapseItem *queue_a = nullptr, *queue_b = nullptr;
+    Node8 *wide = nullptr;
+    Tri48 *tri_out = nullptr;
+    const uint32_t T = 256;
+    const uint32_t nb = (n + T - 1) / T;
+    uint32_t h_counters[3];
+    uint32_t depth = 0;
+
+    out.release();
+    out.n_tris = n;
+    CK(dalloc(&wide, std::max<uint32_t>(n, 1)));
+    CK(dalloc(&tri_out, n));
+    if (n == 0) {
+        k_empty_root<<<1, 1, 0, st>>>(wide);
+        *launches += 1;
+        out.n_wide = 1;
+        out.depth = 1;
+        goto finish;
+    }
+    CK(dalloc(&tri_world, n));
+    CK(dalloc(&prim_lo, n));
+    CK(dalloc(&prim_hi, n));
+    CK(dalloc(&bounds, 8));
+    k_init_bounds<<<1, 32, 0, st>>>(bounds);
+    k_prep_tris<<<nb, T, 0, st>>>(sv, tri_world, prim_lo, prim_hi, bounds);
+    *launches += 2;
+    if (n == 1) {
+        k_single_tri_root<<<1, 1, 0, st>>>(prim_lo, prim_hi, tri_world, wide, tri_out);
+        *launches += 1;
+        out.n_wide = 1;
+        out.depth = 1;
+        goto finish;
+    }
+    CK(dalloc(&keys, n));
+    CK(dalloc(&keys_tmp, n));
+    CK(dalloc(&vals, n));
+    CK(dalloc(&vals_tmp, n));
+    CK(dalloc(&tile_hist, 256 * (size_t)((n + RS_TILE - 1) / RS_TILE)));
+    k_morton<<<nb, T, 0, st>>>(prim_lo, prim_hi, n, bounds, keys, vals);
+    *launches += 1;
+    CK(radix_sort_pairs(st, keys, vals, keys_tmp, vals_tmp, n, 63, tile_hist, launches));
+    CK(dalloc(&bn, 2 * (size_t)n - 1));
+    CK(dalloc(&parent, 2 * (size_t)n - 1));
+    CK(dalloc(&node_count, 2 * (size_t)n - 1));
+    CK(dalloc(&node_cost, 2 * (size_t)n - 1));
+    CK(dalloc(&flags, n));
+    k_hierarchy<<<nb, T, 0, st>>>(keys, vals, prim_lo, prim_hi, (int)n, bn, parent, node_count, node_cost, flags);
+    k_bottom_up<<<nb, T, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, 0, 0);
+    *launches += 2;
+    CK(cudaMemcpyAsync(&out.sah_lbvh, node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
+    for (int pass = 0; pass < opt.treelet_passes; pass++) {
+        k_clear_u32<<<nb, T, 0, st>>>(flags, n);
+        k_bottom_up<<<(n + 63) / 64, 64, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, 1, opt.treelet_gamma);
+        *launches += 2;
+    }
+    CK(cudaMemcpyAsync(&out.sah_final, node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
+    {
+        BNode root;
+        CK(cudaMemcpyAsync(&root, bn, sizeof(BNode), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const float a = half_area(root.lo, root.hi);
+        if (a > 0.0f) { out.sah_lbvh /= a; out.sah_final /= a; }
+        out.lo[0] = root.lo.x; out.lo[1] = root.lo.y; out.lo[2] = root.lo.z;
+        out.hi[0] = root.hi.x; out.hi[1] = root.hi.y; out.hi[2] = root.hi.z;
+    }
+    // collapse, one launch per level of the wide tree
+    CK(dalloc(&queue_a, n));
+    CK(dalloc(&queue_b, n));
+    CK(dalloc(&counters, 4));
+    {
+        CollapseItem rootItem;
+        rootItem.bnode = 0;
+        rootItem.wnode = 0;
+        CK(cudaMemcpyAsync(queue_a, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, st));
+        h_counters[0] = 1; h_counters[1] = 0; h_counters[2] = 0;
+        CK(cudaMemcpyAsync(counters, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
+        uint32_t n_items = 1;
+        while (n_items) {
+            k_collapse_level<<<(n_items + 63) / 64, 64, 0, st>>>(bn, node_count, (int)n - 1, queue_a, n_items, wide, counters, vals,
+                                                                 tri_world, tri_out, queue_b);
+            *launches += 1;
+            CK(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            n_items = h_counters[2];
+            h_counters[2] = 0;
+            CK(cudaMemcpyAsync(counters + 2, &h_counters[2], sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            std::swap(queue_a, queue_b);
+            depth++;
+            if (depth > SOLB_MAX_WIDE_DEPTH) { err = cudaErrorLaunchOutOfResources; goto done; }
+        }
+        out.n_wide = h_counters[0];
+        out.depth = depth;
+        if (h_counters[1] != n) { err = cudaErrorUnknown; goto done; }  // every triangle must land in exactly one leaf
+    }
+finish:
+    CK(cudaStreamSynchronize(st));
+    // shrink the node array to its final size
+    {
+        Node8 *final_nodes = nullptr;
+        CK(dalloc(&final_nodes, out.n_wide));
+        CK(cudaMemcpyAsync(final_nodes, wide, sizeof(Node8) * out.n_wide, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        out.nodes = final_nodes;
+        out.tris = tri_out;
+        tri_out = nullptr;
+        out.n_binary = n >= 2 ? 2 * n - 1 : n;
+    }
+done:
+    cudaFree(tri_world); cudaFree(prim_lo); cudaFree(prim_hi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_tmp);
+    cudaFree(vals); cudaFree(vals_tmp); cudaFree(tile_hist); cudaFree(flags); cudaFree(counters); cudaFree(bn);
+    cudaFree(parent); cudaFree(node_count); cudaFree(node_cost); cudaFree(queue_a); cudaFree(queue_b); cudaFree(wide);
+    cudaFree(tri_out);
+    if (err != cudaSuccess) out.release();
+    return err;
+}
+
+// test hook: sort (keys, vals) of n elements already on the device
+cudaError_t sort_pairs_device(cudaStream_t st, uint64_t *keys, uint32_t *vals, uint32_t n, int key_bits) {
+    uint64_t *kt = nullptr;
+    uint32_t *vt = nullptr, *th = nullptr;
+    uint64_t launches = 0;
+    cudaError_t err = cudaSuccess;
+    if (n == 0) return cudaSuccess;
+    CK(dalloc(&kt, n));
+    CK(dalloc(&vt, n));
+    CK(dalloc(&th, 256 * (size_t)((n + RS_TILE - 1) / RS_TILE)));
+    CK(radix_sort_pairs(st, keys, vals, kt, vt, n, key_bits, th, &launches));
+    CK(cudaStreamSynchronize(st));
+done:
+    cudaFree(kt); cudaFree(vt); cudaFree(th);
+    return err;
+}
+
+}  // namespace solb

@@ -1,0 +1,310 @@
+// build.cuh — per-element logic of the GPU BVH builder (Morton code, Karras hierarchy, treelet
+// restructuring, 8-wide collapse).  Replaces the driver builds behind BLAS::new / TLAS::new /
+// TLAS::regenerate (src/ray/acceleration.rs:136-239,344-467 -> vkCmdBuildAccelerationStructuresKHR).
+//
+// The reference creates one BLAS and exactly one instance per primitive section
+// (src/ray/mod.rs:122 "TODO: support multiple instances per BLAS"), so instancing saves nothing;
+// the B200 build therefore bakes every instance transform into world-space triangles and builds
+// ONE hierarchy over all of them ("flattened TLAS"): no per-instance ray transform, no overlap
+// penalty between instances whose boxes intersect (tunnel.gltf's two sections share one box).
+//
+// Functions here are SOLB_HD: kernels in build.cu call them per thread; tests/emu runs the same
+// code sequentially on the CPU.
+#pragma once
+#include "bvh.cuh"
+
+namespace solb {
+
+// ---- binary hierarchy (Karras 2012 numbering: internal i in [0, n-2], leaf j -> n-1+j) ----------
+struct BNode {
+    float3 lo; int left;   // child node ids (unified numbering); leaves: left = right = -1
+    float3 hi; int right;
+};
+static_assert(sizeof(BNode) == 32, "BNode must be 32 bytes");
+
+SOLB_HD uint64_t expand21(uint32_t v) {
+    uint64_t x = v & 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+// 63-bit Morton code of a centroid inside [lo, hi]
+SOLB_HD uint64_t morton63(float3 c, float3 lo, float3 inv_ext) {
+    const float scale = 2097152.0f;  // 2^21
+    float fx = (c.x - lo.x) * inv_ext.x * scale, fy = (c.y - lo.y) * inv_ext.y * scale, fz = (c.z - lo.z) * inv_ext.z * scale;
+    uint32_t x = (uint32_t)fminf(fmaxf(fx, 0.0f), scale - 1.0f);
+    uint32_t y = (uint32_t)fminf(fmaxf(fy, 0.0f), scale - 1.0f);
+    uint32_t z = (uint32_t)fminf(fmaxf(fz, 0.0f), scale - 1.0f);
+    return (expand21(x) << 2) | (expand21(y) << 1) | expand21(z);
+}
+
+// length of the common prefix of keys i and j, index-augmented so duplicate keys still split
+SOLB_HD int karras_delta(const uint64_t *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + clz32((uint32_t)i ^ (uint32_t)j);
+    return clz64(a ^ b);
+}
+
+// internal node i of n-1: children and covered range [first, last] of sorted primitives
+SOLB_HD void karras_node(const uint64_t *keys, int n, int i, int &left, int &right, int &first, int &last) {
+    const int d = (karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = karras_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (karras_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (karras_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = karras_delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (karras_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + (d < 0 ? d : 0);
+    first = i < j ? i : j;
+    last = i < j ? j : i;
+    left = (first == gamma) ? (n - 1 + gamma) : gamma;
+    right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+}
+
+// ---- treelet restructuring (Karras & Aila 2013, "Fast Parallel Construction of High-Quality
+//      Bounding Volume Hierarchies"), one treelet of up to 7 leaves per call, exhaustive DP over
+//      the 2^7 leaf subsets.  Internal node ids of the treelet are reused, so the rest of the tree
+//      (parents, ranges are NOT preserved: callers must not rely on Karras ranges afterwards). --------
+#define SOLB_TREELET_N 7
+#define SOLB_SAH_CI 1.2f  // cost of an internal node visit
+#define SOLB_SAH_CT 1.0f  // cost per triangle
+
+struct TreeletScratch {
+    float area[128];
+    float cost[128];
+    uint8_t part[128];
+};
+
+// subtree SAH cost + triangle count are kept per node by the caller (cost[], count[])
+SOLB_HD float leaf_or_internal_cost(float area, float children_cost, int count) {
+    // a subtree may be flattened into a leaf if it is small enough for the 8-wide collapse
+    float c = SOLB_SAH_CI * area + children_cost;
+    if (count <= SOLB_MAX_LEAF_TRIS) c = fminf(c, SOLB_SAH_CT * area * (float)count);
+    return c;
+}
+
+// Restructure the treelet rooted at `root` (an internal node).  node_cost/node_count are per-node
+// subtree SAH cost / triangle count (valid for all descendants on entry; updated for the treelet's
+// internal nodes on exit).  Returns the new cost of root.
+SOLB_HD float optimize_treelet(BNode *bn, int *parent, float *node_cost, int *node_count, int n_internal, int root,
+                               TreeletScratch &sc) {
+    int leaves[SOLB_TREELET_N];
+    int internals[SOLB_TREELET_N - 1];
+    int nl = 0, ni = 0;
+    internals[ni++] = root;
+    leaves[nl++] = bn[root].left;
+    leaves[nl++] = bn[root].right;
+    while (nl < SOLB_TREELET_N) {
+        int best = -1;
+        float best_a = -1.0f;
+        for (int i = 0; i < nl; i++) {
+            const int c = leaves[i];
+            if (c < n_internal) {
+                const float a = half_area(bn[c].lo, bn[c].hi);
+                if (a > best_a) { best_a = a; best = i; }
+            }
+        }
+        if (best < 0) break;
+        const int c = leaves[best];
+        internals[ni++] = c;
+        leaves[best] = bn[c].left;
+        leaves[nl++] = bn[c].right;
+    }
+    if (nl < 3) return node_cost[root];  // nothing to restructure
+    const int full = (1 << nl) - 1;
+    // areas of every subset's union box
+    for (int s = 1; s <= full; s++) {
+        float3 lo = f3(3.4e38f, 3.4e38f, 3.4e38f), hi = f3(-3.4e38f, -3.4e38f, -3.4e38f);
+        for (int i = 0; i < nl; i++)
+            if (s & (1 << i)) { lo = fmin3(lo, bn[leaves[i]].lo); hi = fmax3(hi, bn[leaves[i]].hi); }
+        sc.area[s] = half_area(lo, hi);
+    }
+    // singletons
+    for (int i = 0; i < nl; i++) { sc.cost[1 << i] = node_cost[leaves[i]]; sc.part[1 << i] = 0; }
+    // subsets by increasing popcount
+    for (int k = 2; k <= nl; k++) {
+        for (int s = 1; s <= full; s++) {
+            if (popc32((uint32_t)s) != k) continue;
+            float best_c = 3.4e38f;
+            int best_p = 0;
+            // enumerate partitions (p, s^p) with the lowest set bit fixed in p to halve the work
+            const int delta = (s - 1) & s;
+            int p = (-delta) & s;
+            do {
+                const float c = sc.cost[p] + sc.cost[s ^ p];
+                if (c < best_c) { best_c = c; best_p = p; }
+                p = (p - delta) & s;
+            } while (p != 0);
+            int cnt = 0;
+            for (int i = 0; i < nl; i++) if (s & (1 << i)) cnt += node_count[leaves[i]];
+            sc.cost[s] = leaf_or_internal_cost(sc.area[s], best_c, cnt);
+            sc.part[s] = (uint8_t)best_p;
+        }
+    }
+    const float old_cost = node_cost[root];
+    if (!(sc.cost[full] < old_cost * 0.9999f)) return old_cost;  // keep the topology unless it improves
+    // rebuild topology top-down reusing the internal node ids
+    int stack_set[SOLB_TREELET_N], stack_node[SOLB_TREELET_N];
+    int sp = 0, next_internal = 1;
+    stack_set[sp] = full; stack_node[sp] = root; sp++;
+    // process in an order that lets us fix boxes afterwards: record (node) in creation order
+    int order[SOLB_TREELET_N - 1];
+    int n_order = 0;
+    while (sp) {
+        sp--;
+        const int s = stack_set[sp], node = stack_node[sp];
+        order[n_order++] = node;
+        const int p0 = sc.part[s], p1 = s ^ p0;
+        int child[2];
+        const int sub[2] = { p0, p1 };
+        for (int k = 0; k < 2; k++) {
+            if (popc32((uint32_t)sub[k]) == 1) {
+                child[k] = leaves[bfind32((uint32_t)sub[k])];
+            } else {
+                child[k] = internals[next_internal++];
+                stack_set[sp] = sub[k]; stack_node[sp] = child[k]; sp++;
+            }
+            parent[child[k]] = node;
+        }
+        bn[node].left = child[0];
+        bn[node].right = child[1];
+    }
+    // boxes / costs / counts bottom-up (reverse creation order: children are created after parents)
+    for (int k = n_order - 1; k >= 0; k--) {
+        const int node = order[k];
+        const int l = bn[node].left, r = bn[node].right;
+        bn[node].lo = fmin3(bn[l].lo, bn[r].lo);
+        bn[node].hi = fmax3(bn[l].hi, bn[r].hi);
+        node_count[node] = node_count[l] + node_count[r];
+        node_cost[node] = leaf_or_internal_cost(half_area(bn[node].lo, bn[node].hi), node_cost[l] + node_cost[r], node_count[node]);
+    }
+    return node_cost[root];
+}
+
+// ---- collapse: binary tree -> 8-wide compressed nodes ------------------------------------------------
+#if defined(__CUDA_ARCH__)
+SOLB_HD uint32_t counter_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+#else
+SOLB_HD uint32_t counter_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+#endif
+
+struct CollapseItem {
+    int bnode;       // binary node to turn into a wide node (always an internal binary node)
+    uint32_t wnode;  // index of the wide node to write
+};
+
+// Gather the triangles under binary node c (in-order) into out[], return count (<= SOLB_MAX_LEAF_TRIS)
+SOLB_HD int gather_leaf_tris(const BNode *bn, int n_internal, int c, int *out) {
+    int n = 0;
+    int stack[8];
+    int sp = 0;
+    stack[sp++] = c;
+    while (sp) {
+        const int x = stack[--sp];
+        if (x >= n_internal) out[n++] = x - n_internal;  // sorted-position of the leaf primitive
+        else { stack[sp++] = bn[x].right; stack[sp++] = bn[x].left; }
+    }
+    return n;
+}
+
+// One work item.  sorted_prim[j] = global triangle id at sorted position j; tri_world indexed by
+// global triangle id; tri_out in wide-leaf order.
+SOLB_HD void collapse_one(const BNode *bn, const int *node_count, int n_internal, CollapseItem item, Node8 *wide,
+                          uint32_t *wide_count, uint32_t *tri_count, const uint32_t *sorted_prim, const Tri48 *tri_world,
+                          Tri48 *tri_out, CollapseItem *queue_out, uint32_t *queue_out_count) {
+    int cand[8];
+    int n = 2;
+    cand[0] = bn[item.bnode].left;
+    cand[1] = bn[item.bnode].right;
+    while (n < 8) {
+        int best = -1;
+        float best_a = -1.0f;
+        for (int i = 0; i < n; i++) {
+            const int c = cand[i];
+            if (c < n_internal) {  // internal binary node: may be opened
+                const float a = half_area(bn[c].lo, bn[c].hi);
+                if (a > best_a) { best_a = a; best = i; }
+            }
+        }
+        if (best < 0) break;
+        const int c = cand[best];
+        cand[best] = bn[c].left;
+        cand[n++] = bn[c].right;
+    }
+    // slot assignment: greedy auction on dot(child centre - node centre, octant direction of the slot)
+    const float3 nlo = bn[item.bnode].lo, nhi = bn[item.bnode].hi;
+    const float3 nc = (nlo + nhi) * 0.5f;
+    int slot_of[8];
+    bool slot_used[8];
+    float3 rel[8];
+    for (int i = 0; i < 8; i++) { slot_used[i] = false; slot_of[i] = -1; }
+    for (int i = 0; i < n; i++) rel[i] = (bn[cand[i]].lo + bn[cand[i]].hi) * 0.5f - nc;
+    for (int round = 0; round < n; round++) {
+        float best_v = -3.4e38f;
+        int bi = -1, bs = -1;
+        for (int i = 0; i < n; i++) {
+            if (slot_of[i] >= 0) continue;
+            for (int s = 0; s < 8; s++) {
+                if (slot_used[s]) continue;
+                const float v = ((s & 4) ? rel[i].x : -rel[i].x) + ((s & 2) ? rel[i].y : -rel[i].y) + ((s & 1) ? rel[i].z : -rel[i].z);
+                if (v > best_v) { best_v = v; bi = i; bs = s; }
+            }
+        }
+        slot_of[bi] = bs;
+        slot_used[bs] = true;
+    }
+    ChildRef ch[8];
+    int child_of_slot[8];
+    for (int s = 0; s < 8; s++) { ch[s].valid = 0; child_of_slot[s] = -1; }
+    uint32_t n_inner = 0, n_tris = 0;
+    for (int i = 0; i < n; i++) child_of_slot[slot_of[i]] = cand[i];
+    for (int s = 0; s < 8; s++) {
+        const int c = child_of_slot[s];
+        if (c < 0) continue;
+        ch[s].valid = 1;
+        ch[s].lo = bn[c].lo;
+        ch[s].hi = bn[c].hi;
+        const int cnt = node_count[c];
+        if (cnt <= SOLB_MAX_LEAF_TRIS) {
+            ch[s].is_inner = 0; ch[s].tri_offset = n_tris; ch[s].tri_count = (uint32_t)cnt;
+            n_tris += (uint32_t)cnt;
+        } else {
+            ch[s].is_inner = 1; ch[s].tri_offset = 0; ch[s].tri_count = 0;
+            n_inner++;
+        }
+    }
+    const uint32_t child_base = n_inner ? counter_add(wide_count, n_inner) : 0u;
+    const uint32_t tri_base = n_tris ? counter_add(tri_count, n_tris) : 0u;
+    encode_node8(wide[item.wnode], nlo, nhi, child_base, tri_base, ch);
+    uint32_t q = n_inner ? counter_add(queue_out_count, n_inner) : 0u;
+    uint32_t k = 0;
+    for (int s = 0; s < 8; s++) {
+        const int c = child_of_slot[s];
+        if (c < 0) continue;
+        if (ch[s].is_inner) {
+            CollapseItem it;
+            it.bnode = c;
+            it.wnode = child_base + k;
+            queue_out[q + k] = it;
+            k++;
+        } else {
+            int prims[SOLB_MAX_LEAF_TRIS + 1];
+            const int m = gather_leaf_tris(bn, n_internal, c, prims);
+            for (int j = 0; j < m; j++) tri_out[tri_base + ch[s].tri_offset + (uint32_t)j] = tri_world[sorted_prim[prims[j]]];
+        }
+    }
+}
+
+}  // namespace solb

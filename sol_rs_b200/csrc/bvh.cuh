@@ -1,0 +1,331 @@
+// bvh.cuh — 8-wide compressed BVH: node/triangle layouts, watertight ray/triangle test, traversal.
+//
+// Replaces what the reference delegates to the Vulkan driver: traceRayEXT
+// (assets/glsl/pathtrace.rgen:65-76, ao.rgen:59-70, debug.rgen:34) over the TLAS/BLAS built in
+// src/ray/acceleration.rs.  Contract restated: closest hit, opaque, two-sided (cull disabled,
+// acceleration.rs:337), mask 0xFF, tmin < t < tmax, attribs = barycentrics of v1, v2.
+//
+// Layout (after Ylitie, Karras, Laine 2017, "Efficient Incoherent Ray Traversal on GPUs Through
+// Compressed Wide BVHs"): 80-byte nodes = 5 x 16-byte vector loads; 48-byte triangles = 3 x float4.
+#pragma once
+#include "common.cuh"
+
+namespace solb {
+
+// ---- 80-byte node, addressed as 5 uint4 --------------------------------------------------------
+//  q0: px, py, pz (f32 bits), [ex | ey<<8 | ez<<16 | imask<<24]
+//  q1: child_base, tri_base, meta[0..3], meta[4..7]
+//  q2: qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7]
+//  q3: qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7]
+//  q4: qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7]
+// meta[i]: 0 = empty; internal child = 0b001_11sss (sss = slot i); leaf = (unary tri count) << 5 | tri offset
+// child box i = p + q * 2^(e-127) per axis, conservative (floor / ceil).
+struct Node8 {
+    uint4 q[5];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+// ---- 48-byte triangle: world-space vertices; w lanes carry the ids the hit shaders need ----------
+//  v0.w = gl_InstanceID, v1.w = gl_PrimitiveID, v2.w = global triangle ordinal (index of the shading record)
+struct Tri48 {
+    float4 v0, v1, v2;
+};
+static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
+
+#define SOLB_MAX_LEAF_TRIS 3
+#define SOLB_SM_STACK 8      // per-lane entries kept in shared memory
+#define SOLB_LOCAL_STACK 56  // spill (local memory)
+#define SOLB_MAX_WIDE_DEPTH (SOLB_SM_STACK + SOLB_LOCAL_STACK - 2)
+
+struct Ray {
+    float3 o;
+    float tmin;
+    float3 d;
+    float tmax;
+};
+
+struct Hit {
+    float t, u, v;     // u, v = hitAttributeEXT attribs.xy (weights of vertex 1 and 2)
+    uint32_t inst;     // gl_InstanceID, SOLB_MISS on miss
+    uint32_t prim;     // gl_PrimitiveID
+    uint32_t gtri;     // global triangle ordinal
+};
+
+struct TraceCounters {
+    uint32_t nodes, tris;
+};
+
+// ---- watertight ray/triangle test ------------------------------------------------------------------
+// Woop, Benthin, Wald 2013 ("Watertight Ray/Triangle Intersection") with the axis-permuting shear
+// replaced by a per-ray orthonormal frame (e1, e2, d): every vertex is projected to 2D ray space with
+// the same explicit fma sequence, so a vertex shared by two triangles lands on bit-identical
+// coordinates, and the 2D edge functions are evaluated without FMA contraction so the value of a shared
+// edge is exactly negated in the neighbour: a ray cannot slip between triangles that share vertices.
+// Exact zeros are re-evaluated in f64.  Barycentric error ~ eps * distance / triangle size.
+struct RayFrame {
+    float3 e1, e2;
+};
+
+SOLB_HD RayFrame make_ray_frame(float3 d) {
+    // Duff et al. 2017 branchless orthonormal basis around normalize(d)
+    const float inv = 1.0f / sqrtf(dot(d, d));
+    const float3 n = f3(d.x * inv, d.y * inv, d.z * inv);
+    const float s = (n.z < 0.0f ? -1.0f : 1.0f);
+    const float a = -1.0f / (s + n.z);
+    const float b = n.x * n.y * a;
+    RayFrame f;
+    f.e1 = f3(1.0f + s * n.x * n.x * a, s * b, -s * n.x);
+    f.e2 = f3(b, s + n.y * n.y * a, -n.y);
+    return f;
+}
+
+SOLB_HD float proj_rn(float3 a, float3 e) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a.z, e.z, __fmaf_rn(a.y, e.y, __fmul_rn(a.x, e.x)));
+#else
+    return fmaf(a.z, e.z, fmaf(a.y, e.y, mul_rn(a.x, e.x)));
+#endif
+}
+SOLB_HD float edge2d(float ax, float ay, float bx, float by) { return sub_rn(mul_rn(ax, by), mul_rn(ay, bx)); }
+
+SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, float3 p1, float3 p2, float tmin, float tmax,
+                           float &t_out, float &u_out, float &v_out) {
+    const float3 A = f3(sub_rn(p0.x, o.x), sub_rn(p0.y, o.y), sub_rn(p0.z, o.z));
+    const float3 B = f3(sub_rn(p1.x, o.x), sub_rn(p1.y, o.y), sub_rn(p1.z, o.z));
+    const float3 C = f3(sub_rn(p2.x, o.x), sub_rn(p2.y, o.y), sub_rn(p2.z, o.z));
+    const float ax = proj_rn(A, fr.e1), ay = proj_rn(A, fr.e2);
+    const float bx = proj_rn(B, fr.e1), by = proj_rn(B, fr.e2);
+    const float cx = proj_rn(C, fr.e1), cy = proj_rn(C, fr.e2);
+    float U = edge2d(cx, cy, bx, by);  // weight of vertex 0
+    float V = edge2d(ax, ay, cx, cy);  // weight of vertex 1
+    float W = edge2d(bx, by, ax, ay);  // weight of vertex 2
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        const double Ud = (double)cx * by - (double)cy * bx;
+        const double Vd = (double)ax * cy - (double)ay * cx;
+        const double Wd = (double)bx * ay - (double)by * ax;
+        if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return false;
+        U = (float)Ud; V = (float)Vd; W = (float)Wd;
+    } else if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) {
+        return false;  // two-sided: all three must share a sign
+    }
+    const float det = U + V + W;
+    if (det == 0.0f) return false;  // edge-on triangle
+    const float rdet = 1.0f / det;
+    // hit point P - o = (U A + V B + W C) / det; t = (P - o).d / d.d
+    const float T = U * dot(A, d) + V * dot(B, d) + W * dot(C, d);
+    const float t = T * rdet / dot(d, d);
+    if (!(t > tmin && t < tmax)) return false;
+    t_out = t;
+    u_out = V * rdet;
+    v_out = W * rdet;
+    return true;
+}
+
+// ---- node test: returns hit mask (bits 31..24 internal children in traversal priority order,
+//      bits 23..0 triangles of the hit leaf children) -------------------------------------------------
+SOLB_HD float q2f(uint32_t w, int shift) { return (float)((w >> shift) & 0xffu); }
+
+SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4,
+                                float3 o, float3 idir, uint32_t oct_inv4, float tmin, float tmax) {
+    const uint32_t e = q0.w;
+    const float ax = u2f((e & 0xffu) << 23) * idir.x;
+    const float ay = u2f(((e >> 8) & 0xffu) << 23) * idir.y;
+    const float az = u2f(((e >> 16) & 0xffu) << 23) * idir.z;
+    const float bx = (u2f(q0.x) - o.x) * idir.x;
+    const float by = (u2f(q0.y) - o.y) * idir.y;
+    const float bz = (u2f(q0.z) - o.z) * idir.z;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const uint32_t meta4 = g ? q1.w : q1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+        const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t lox = g ? q2.y : q2.x, loy = g ? q2.w : q2.z, loz = g ? q3.y : q3.x;
+        const uint32_t hix = g ? q3.w : q3.z, hiy = g ? q4.y : q4.x, hiz = g ? q4.w : q4.z;
+        // near/far planes per axis depend only on the ray's direction signs
+        const uint32_t nx = idir.x < 0.0f ? hix : lox, fx = idir.x < 0.0f ? lox : hix;
+        const uint32_t ny = idir.y < 0.0f ? hiy : loy, fy = idir.y < 0.0f ? loy : hiy;
+        const uint32_t nz = idir.z < 0.0f ? hiz : loz, fz = idir.z < 0.0f ? loz : hiz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int s = 8 * j;
+            const float t0x = q2f(nx, s) * ax + bx, t1x = q2f(fx, s) * ax + bx;
+            const float t0y = q2f(ny, s) * ay + by, t1y = q2f(fy, s) * ay + by;
+            const float t0z = q2f(nz, s) * az + bz, t1z = q2f(fz, s) * az + bz;
+            const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+            if (cmin <= cmax) {
+                const uint32_t child_bits = (child_bits4 >> s) & 0xffu;
+                const uint32_t bit_index = (bit_index4 >> s) & 0xffu;
+                hitmask |= child_bits << bit_index;
+            }
+        }
+    }
+    return hitmask;
+}
+
+SOLB_HD float safe_rcp_dir(float d) {
+    const float tiny = 1e-20f;
+    return 1.0f / (fabsf(d) > tiny ? d : (f2u(d) >> 31 ? -tiny : tiny));
+}
+
+#if defined(__CUDA_ARCH__)
+#define SOLB_LDG4(p) __ldg(p)
+#else
+#define SOLB_LDG4(p) (*(p))
+#endif
+
+// Closest-hit traversal.  Stack: push(uint2), pop() -> uint2, empty().
+template <bool STATS, class Stack>
+SOLB_HD void trace_closest(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris, const Ray &ray, Hit &hit,
+                           Stack &stack, TraceCounters *ctr) {
+    hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS;
+    hit.t = ray.tmax; hit.u = 0.0f; hit.v = 0.0f;
+    const float3 o = ray.o, d = ray.d;
+    const float3 idir = f3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+    const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
+    const RayFrame frame = make_ray_frame(d);
+    float tmax = ray.tmax;
+    const float tmin = ray.tmin;
+    uint2 ngroup = make_uint2(0u, 0x80000000u);  // root: "child 7^oct_inv of a virtual parent", base 0
+    uint2 tgroup = make_uint2(0u, 0u);
+    for (;;) {
+        {   // invariant: ngroup always carries at least one internal-child hit here (only such groups are pushed)
+            const uint32_t hits_imask = ngroup.y;
+            const int child_bit = bfind32(hits_imask);
+            const uint32_t child_base = ngroup.x;
+            ngroup.y &= ~(1u << child_bit);
+            if (ngroup.y & 0xff000000u) stack.push(ngroup);
+            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (oct_inv4 & 0xffu);
+            const uint32_t rel = (uint32_t)popc32(hits_imask & ~(0xffffffffu << slot));
+            const uint4 *np = nodes + (size_t)(child_base + rel) * 5;
+            const uint4 q0 = SOLB_LDG4(np + 0), q1 = SOLB_LDG4(np + 1), q2 = SOLB_LDG4(np + 2), q3 = SOLB_LDG4(np + 3),
+                        q4 = SOLB_LDG4(np + 4);
+            if (STATS) ctr->nodes++;
+            const uint32_t hm = intersect_node(q0, q1, q2, q3, q4, o, idir, oct_inv4, tmin, tmax);
+            ngroup = make_uint2(q1.x, (hm & 0xff000000u) | (q0.w >> 24));
+            tgroup = make_uint2(q1.y, hm & 0x00ffffffu);
+        }
+        while (tgroup.y) {
+            const int ti = bfind32(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const float4 *tp = tris + (size_t)(tgroup.x + (uint32_t)ti) * 3;
+            const float4 v0 = SOLB_LDG4(tp + 0), v1 = SOLB_LDG4(tp + 1), v2 = SOLB_LDG4(tp + 2);
+            if (STATS) ctr->tris++;
+            float t, u, v;
+            if (intersect_tri(o, d, frame, xyz(v0), xyz(v1), xyz(v2), tmin, tmax, t, u, v)) {
+                tmax = t;
+                hit.t = t; hit.u = u; hit.v = v;
+                hit.inst = f2u(v0.w); hit.prim = f2u(v1.w); hit.gtri = f2u(v2.w);
+            }
+        }
+        if (!(ngroup.y & 0xff000000u)) {
+            if (stack.empty()) break;
+            ngroup = stack.pop();
+        }
+    }
+}
+
+// ---- build-time node encoding (used by the collapse kernel; host-testable) -------------------------
+struct ChildRef {
+    float3 lo, hi;
+    uint32_t is_inner;   // 1: internal child, 0: leaf
+    uint32_t tri_offset; // leaf: first triangle relative to tri_base
+    uint32_t tri_count;  // leaf: 1..3
+    uint32_t valid;
+};
+
+// exponent e (biased) such that 255 * 2^(e-127) >= extent, chosen conservatively
+SOLB_HD uint32_t quant_exponent(float extent) {
+    if (!(extent > 0.0f)) return 1u;  // flat axis: any tiny positive scale works (q stays 0)
+    // smallest power of two s with extent / s <= 255
+    float s = extent / 255.0f;
+    uint32_t bits = f2u(s);
+    uint32_t e = (bits >> 23) & 0xffu;
+    if (bits & 0x7fffffu) e += 1;  // round mantissa up to the next power of two
+    if (e < 1u) e = 1u;
+    if (e > 254u) e = 254u;
+    return e;
+}
+
+// children[slot] for slot 0..7 (valid == 0: empty).  Internal children must be numbered by the
+// caller in slot order starting at child_base.
+SOLB_HD void encode_node8(Node8 &out, float3 lo, float3 hi, uint32_t child_base, uint32_t tri_base, const ChildRef *children) {
+    uint32_t ex = quant_exponent(hi.x - lo.x), ey = quant_exponent(hi.y - lo.y), ez = quant_exponent(hi.z - lo.z);
+    // guard against rounding in (c - lo) / scale: bump the exponent until every child fits in [0, 255]
+    for (int axis = 0; axis < 3; axis++) {
+        uint32_t &e = axis == 0 ? ex : (axis == 1 ? ey : ez);
+        float l = axis == 0 ? lo.x : (axis == 1 ? lo.y : lo.z);
+        for (;;) {
+            float inv = 1.0f / u2f(e << 23);
+            bool ok = true;
+            for (int i = 0; i < 8; i++) {
+                if (!children[i].valid) continue;
+                float ch = axis == 0 ? children[i].hi.x : (axis == 1 ? children[i].hi.y : children[i].hi.z);
+                if (ceilf((ch - l) * inv) > 255.0f) ok = false;
+            }
+            if (ok || e >= 254u) break;
+            e++;
+        }
+    }
+    const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+    uint32_t w[20];
+    for (int i = 0; i < 20; i++) w[i] = 0;
+    w[0] = f2u(lo.x); w[1] = f2u(lo.y); w[2] = f2u(lo.z);
+    uint32_t imask = 0;
+    for (int i = 0; i < 8; i++) {
+        const ChildRef &c = children[i];
+        if (!c.valid) continue;
+        uint32_t meta;
+        if (c.is_inner) {
+            imask |= 1u << i;
+            meta = (1u << 5) | (24u + (uint32_t)i);
+        } else {
+            const uint32_t unary = c.tri_count == 1 ? 1u : (c.tri_count == 2 ? 3u : 7u);
+            meta = (unary << 5) | c.tri_offset;
+        }
+        uint32_t q[6];
+        const float cl[3] = { c.lo.x, c.lo.y, c.lo.z }, chh[3] = { c.hi.x, c.hi.y, c.hi.z };
+        const float l3[3] = { lo.x, lo.y, lo.z }, s3[3] = { sx, sy, sz };
+        for (int a = 0; a < 3; a++) {
+            float ql = floorf((cl[a] - l3[a]) / s3[a]);
+            float qh = ceilf((chh[a] - l3[a]) / s3[a]);
+            ql = fminf(fmaxf(ql, 0.0f), 255.0f);
+            qh = fminf(fmaxf(qh, 0.0f), 255.0f);
+            // make the decoded box provably contain the child despite rounding
+            while (ql > 0.0f && l3[a] + ql * s3[a] > cl[a]) ql -= 1.0f;
+            while (qh < 255.0f && l3[a] + qh * s3[a] < chh[a]) qh += 1.0f;
+            q[a] = (uint32_t)ql;
+            q[3 + a] = (uint32_t)qh;
+        }
+        const int word = i >> 2, sh = 8 * (i & 3);
+        w[6 + word] |= meta << sh;
+        w[8 + word] |= q[0] << sh;   // qlo_x
+        w[10 + word] |= q[1] << sh;  // qlo_y
+        w[12 + word] |= q[2] << sh;  // qlo_z
+        w[14 + word] |= q[3] << sh;  // qhi_x
+        w[16 + word] |= q[4] << sh;  // qhi_y
+        w[18 + word] |= q[5] << sh;  // qhi_z
+    }
+    w[3] = ex | (ey << 8) | (ez << 16) | (imask << 24);
+    w[4] = child_base;
+    w[5] = tri_base;
+    for (int i = 0; i < 5; i++) out.q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+// decode child box i of a node (tests / invariants)
+SOLB_HD void decode_child_box(const Node8 &n, int i, float3 &lo, float3 &hi) {
+    const uint32_t *w = (const uint32_t *)&n;
+    const uint32_t e = w[3];
+    const float sx = u2f((e & 0xffu) << 23), sy = u2f(((e >> 8) & 0xffu) << 23), sz = u2f(((e >> 16) & 0xffu) << 23);
+    const int word = i >> 2, sh = 8 * (i & 3);
+    lo = f3(u2f(w[0]) + (float)((w[8 + word] >> sh) & 0xff) * sx, u2f(w[1]) + (float)((w[10 + word] >> sh) & 0xff) * sy,
+            u2f(w[2]) + (float)((w[12 + word] >> sh) & 0xff) * sz);
+    hi = f3(u2f(w[0]) + (float)((w[14 + word] >> sh) & 0xff) * sx, u2f(w[1]) + (float)((w[16 + word] >> sh) & 0xff) * sy,
+            u2f(w[2]) + (float)((w[18 + word] >> sh) & 0xff) * sz);
+}
+
+}  // namespace solb

@@ -1,0 +1,673 @@
+// solb_api.cu — the extern "C" boundary declared in include/solb.h.
+// Handles are heap objects; every entry point validates, sets the device, catches everything and
+// returns a SolbStatus.  There is no CPU path: without a usable CUDA device solb_ctx_create fails.
+#include "../../include/solb.h"
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "host_math.h"
+#include "solb_internal.h"
+#include "trace.h"
+
+using namespace solb;
+
+static thread_local std::string g_last_error;
+
+struct solb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    unsigned long long *d_stats = nullptr;  // 8 slots
+    uint64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_build_ms = 0.0f, last_trace_ms = 0.0f;
+    uint32_t *d_blue = nullptr;
+    uint32_t blue_w = 0, blue_h = 0;
+    uint32_t *pinned_count = nullptr;
+    WavefrontState ws = {};
+    std::vector<cudaEvent_t> ev_pool;  // timing mode: pairs around every dominant-kernel launch
+    float trace_kernel_ms_total = 0.0f;
+    uint32_t trace_kernel_launches = 0;
+};
+
+struct solb_scene {
+    solb_ctx *ctx = nullptr;
+    std::vector<SolbSceneInstance> instances;  // as the reference's shader would see them
+    std::vector<DeviceInstance> h_inst;
+    std::vector<uint32_t> h_first_tri;
+    uint32_t n_tris = 0, n_vertices = 0, n_indices = 0;
+    float4 *d_vertices = nullptr;
+    uint32_t *d_indices = nullptr, *d_first_tri = nullptr;
+    DeviceInstance *d_inst = nullptr;
+    ShadeRecord *d_shade = nullptr;
+    AccelStorage accel;
+    bool built = false, dirty = false;
+    DeviceSceneView view() const {
+        DeviceSceneView v;
+        v.n_instances = (uint32_t)h_inst.size();
+        v.n_tris = n_tris;
+        v.inst_first_tri = d_first_tri;
+        v.instances = d_inst;
+        v.vertices = d_vertices;
+        v.indices = d_indices;
+        return v;
+    }
+};
+
+struct solb_target {
+    solb_ctx *ctx = nullptr;
+    uint32_t width = 0, height = 0, format = 0;
+    void *dev = nullptr;
+    size_t bytes = 0;
+};
+
+static int fail(solb_ctx *ctx, int code, const std::string &msg) {
+    g_last_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+static int fail_cuda(solb_ctx *ctx, cudaError_t e, const char *what) {
+    cudaGetLastError();  // clear sticky non-fatal state
+    return fail(ctx, SOLB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define SOLB_TRY try {
+#define SOLB_CATCH(ctx)                                                                  \
+    } catch (const std::bad_alloc &) { return fail(ctx, SOLB_ERR_CUDA, "host out of memory"); } \
+    catch (const std::exception &e) { return fail(ctx, SOLB_ERR_INVALID, e.what()); }       \
+    catch (...) { return fail(ctx, SOLB_ERR_INVALID, "unknown exception"); }
+#define CU(ctx, call)                                                    \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);       \
+    } while (0)
+
+static size_t format_bytes(uint32_t f) { return f == SOLB_FORMAT_RGBA32F ? 16 : (f == SOLB_FORMAT_RGBA8 ? 4 : 8); }
+
+extern "C" {
+
+SOLB_API uint32_t solb_version(void) { return SOLB_VERSION; }
+
+SOLB_API const char *solb_last_error(solb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
+    if (!out) return fail(nullptr, SOLB_ERR_INVALID, "solb_ctx_create: out is NULL");
+    *out = nullptr;
+    SOLB_TRY
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SOLB_ERR_CUDA, std::string("no CUDA device: libsolb has no CPU fallback (") +
+                                                (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") + ")");
+    if (device < 0 || device >= count) return fail(nullptr, SOLB_ERR_INVALID, "solb_ctx_create: bad device index");
+    CU(nullptr, cudaSetDevice(device));
+    solb_ctx *c = new solb_ctx();
+    c->device = device;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail_cuda(nullptr, e, "cudaStreamCreate"); }
+        c->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->pinned_count, 64);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) { delete c; return fail_cuda(nullptr, e, "ctx setup"); }
+    *out = c;
+    return SOLB_OK;
+    SOLB_CATCH(nullptr)
+}
+
+static void free_wavefront(solb_ctx *c) {
+    WavefrontState &w = c->ws;
+    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.thr); cudaFree(w.pix); cudaFree(w.hit);
+    cudaFree(w.queue[0]); cudaFree(w.queue[1]); cudaFree(w.counters);
+    w = WavefrontState{};
+}
+
+SOLB_API int solb_ctx_destroy(solb_ctx *ctx) {
+    if (!ctx) return SOLB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_wavefront(ctx);
+    cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_blue);
+    cudaFreeHost(ctx->pinned_count);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_synchronize(solb_ctx *ctx) {
+    if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_set_timing(solb_ctx *ctx, int enabled) {
+    if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
+    ctx->timing = enabled != 0;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_stats_get(solb_ctx *ctx, SolbStats *out) {
+    if (!ctx || !out) return fail(ctx, SOLB_ERR_INVALID, "solb_stats_get: null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    unsigned long long h[8];
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaMemcpy(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    out->rays = h[0]; out->hits = h[1]; out->paths = h[2]; out->nodes_visited = h[3]; out->tris_tested = h[4];
+    out->kernel_launches = ctx->launches;
+    out->last_build_ms = ctx->last_build_ms;
+    out->last_trace_ms = ctx->last_trace_ms;
+    out->trace_kernel_ms_total = ctx->trace_kernel_ms_total;
+    out->trace_kernel_launches = ctx->trace_kernel_launches;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_stats_reset(solb_ctx *ctx) {
+    if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    ctx->launches = 0;
+    ctx->trace_kernel_ms_total = 0.0f;
+    ctx->trace_kernel_launches = 0;
+    return SOLB_OK;
+}
+
+// ---- scene -------------------------------------------------------------------------------------------
+
+SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32_t n_meshes, const SolbMaterialInfo *materials,
+                               uint32_t n_materials, solb_scene **out) {
+    if (!ctx || !out || (n_meshes && !meshes)) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_create: null argument");
+    *out = nullptr;
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::vector<float> verts;        // 16 floats per vertex
+    std::vector<uint32_t> indices;
+    solb_scene *s = new solb_scene();
+    s->ctx = ctx;
+    struct Guard { solb_scene *s; ~Guard() { if (s) solb_scene_destroy(s); } } guard{ s };
+    s->h_first_tri.push_back(0);
+    for (uint32_t m = 0; m < n_meshes; m++) {
+        const SolbMeshDesc &md = meshes[m];
+        if ((md.n_vertices && !md.vertices) || (md.n_sections && !md.sections))
+            return fail(ctx, SOLB_ERR_INVALID, "solb_scene_create: mesh with null vertex/section array");
+        const uint32_t vbase = (uint32_t)(verts.size() / 16), ibase = (uint32_t)indices.size();
+        verts.insert(verts.end(), (const float *)md.vertices, (const float *)md.vertices + 16 * (size_t)md.n_vertices);
+        if (md.n_indices) {
+            if (!md.indices) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_create: null index array");
+            indices.insert(indices.end(), md.indices, md.indices + md.n_indices);
+        }
+        for (uint32_t k = 0; k < md.n_sections; k++) {
+            const SolbSection &sec = md.sections[k];
+            // src/ray/mod.rs:103-108: sections without indices never get an index descriptor (App.A item 4)
+            if (sec.n_indices == 0 || md.n_indices == 0)
+                return fail(ctx, SOLB_ERR_UNSUPPORTED, "non-indexed primitive section: unsupported on the ray-tracing path");
+            if (sec.n_indices % 3) return fail(ctx, SOLB_ERR_INVALID, "section index count is not a multiple of 3");
+            if ((uint64_t)sec.first_index + sec.n_indices > md.n_indices || (uint64_t)sec.first_vertex + sec.n_vertices > md.n_vertices)
+                return fail(ctx, SOLB_ERR_INVALID, "section range outside its mesh");
+            if (sec.material_index >= n_materials || !materials)
+                return fail(ctx, SOLB_ERR_INVALID, "section material index out of range (the reference unwrap()s here)");
+            for (uint32_t i = 0; i < sec.n_indices; i++)
+                if (md.indices[sec.first_index + i] >= sec.n_vertices)
+                    return fail(ctx, SOLB_ERR_INVALID, "index outside its section's vertex range");
+            SolbSceneInstance si;
+            memset(&si, 0, sizeof(si));
+            si.id = (uint32_t)s->instances.size();  // running count: src/ray/mod.rs:113
+            memcpy(si.transform, md.transform, sizeof(si.transform));
+            float inv[16];
+            mat4_inverse(md.transform, inv);
+            mat4_transpose(inv, si.transform_it);  // src/ray/mod.rs:116
+            s->instances.push_back(si);
+            DeviceInstance di;
+            memset(&di, 0, sizeof(di));
+            di.first_vertex = vbase + sec.first_vertex;
+            di.first_index = ibase + sec.first_index;
+            di.n_indices = sec.n_indices;
+            di.material = sec.material_index;
+            memcpy(di.transform, si.transform, sizeof(di.transform));
+            memcpy(di.transform_it, si.transform_it, sizeof(di.transform_it));
+            memcpy(di.mat, &materials[sec.material_index], sizeof(di.mat));  // materials[gl_InstanceID]
+            s->h_inst.push_back(di);
+            s->n_tris += sec.n_indices / 3;
+            s->h_first_tri.push_back(s->n_tris);
+        }
+    }
+    s->n_vertices = (uint32_t)(verts.size() / 16);
+    s->n_indices = (uint32_t)indices.size();
+    const size_t ni = s->h_inst.size();
+    CU(ctx, cudaMalloc((void **)&s->d_vertices, std::max<size_t>(verts.size(), 16) * sizeof(float)));
+    CU(ctx, cudaMalloc((void **)&s->d_indices, std::max<size_t>(indices.size(), 1) * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc((void **)&s->d_first_tri, (ni + 1) * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc((void **)&s->d_inst, std::max<size_t>(ni, 1) * sizeof(DeviceInstance)));
+    CU(ctx, cudaMalloc((void **)&s->d_shade, std::max<size_t>(s->n_tris, 1) * sizeof(ShadeRecord)));
+    cudaStream_t st = ctx->stream;
+    if (!verts.empty()) CU(ctx, cudaMemcpyAsync(s->d_vertices, verts.data(), verts.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (!indices.empty()) CU(ctx, cudaMemcpyAsync(s->d_indices, indices.data(), indices.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(s->d_first_tri, s->h_first_tri.data(), (ni + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (ni) CU(ctx, cudaMemcpyAsync(s->d_inst, s->h_inst.data(), ni * sizeof(DeviceInstance), cudaMemcpyHostToDevice, st));
+    CU(ctx, launch_build_shade_records(st, s->view(), s->d_shade));
+    ctx->launches += s->n_tris ? 1 : 0;
+    CU(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope
+    guard.s = nullptr;
+    *out = s;
+    return SOLB_OK;
+    SOLB_CATCH(ctx)
+}
+
+SOLB_API int solb_scene_destroy(solb_scene *s) {
+    if (!s) return SOLB_OK;
+    if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
+    cudaFree(s->d_vertices); cudaFree(s->d_indices); cudaFree(s->d_first_tri); cudaFree(s->d_inst); cudaFree(s->d_shade);
+    s->accel.release();
+    delete s;
+    return SOLB_OK;
+}
+
+static int do_build(solb_scene *s) {
+    solb_ctx *ctx = s->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    BuildOptions opt;
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = build_accel(ctx->stream, s->view(), s->accel, opt, &ctx->launches);
+    if (e == cudaErrorLaunchOutOfResources) return fail(ctx, SOLB_ERR_OVERFLOW, "acceleration structure deeper than the traversal stack");
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "build_accel");
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    CU(ctx, cudaEventElapsedTime(&ctx->last_build_ms, ctx->ev0, ctx->ev1));
+    s->built = true;
+    s->dirty = false;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_accel_build(solb_scene *s) {
+    if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
+    SOLB_TRY
+    return do_build(s);
+    SOLB_CATCH(s->ctx)
+}
+
+SOLB_API int solb_instance_set_transform(solb_scene *s, uint32_t index, const float transform[16]) {
+    if (!s || !transform) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "solb_instance_set_transform: null argument");
+    if (index >= s->instances.size()) return fail(s->ctx, SOLB_ERR_INVALID, "instance index out of range");
+    SolbSceneInstance &si = s->instances[index];
+    memcpy(si.transform, transform, sizeof(si.transform));
+    float inv[16];
+    mat4_inverse(transform, inv);
+    mat4_transpose(inv, si.transform_it);  // SceneInstance::update_transform, src/ray/mod.rs:27-30
+    memcpy(s->h_inst[index].transform, si.transform, sizeof(si.transform));
+    memcpy(s->h_inst[index].transform_it, si.transform_it, sizeof(si.transform_it));
+    s->dirty = true;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_scene_update(solb_scene *s) {
+    if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
+    solb_ctx *ctx = s->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!s->h_inst.empty()) {
+        CU(ctx, cudaMemcpyAsync(s->d_inst, s->h_inst.data(), s->h_inst.size() * sizeof(DeviceInstance), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SOLB_OK;
+}
+
+SOLB_API int solb_tlas_regenerate(solb_scene *s) {
+    if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
+    if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "solb_tlas_regenerate before solb_accel_build");
+    if (!s->dirty) return SOLB_OK;
+    SOLB_TRY
+    int rc = solb_scene_update(s);  // the rebuild bakes the transforms: they must be on the device
+    if (rc != SOLB_OK) return rc;
+    return do_build(s);
+    SOLB_CATCH(s->ctx)
+}
+
+SOLB_API int solb_scene_instance_count(solb_scene *s, uint32_t *out) {
+    if (!s || !out) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    *out = (uint32_t)s->instances.size();
+    return SOLB_OK;
+}
+
+SOLB_API int solb_scene_get_instances(solb_scene *s, SolbSceneInstance *out, uint32_t capacity) {
+    if (!s || (!out && capacity)) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (capacity < s->instances.size()) return fail(s->ctx, SOLB_ERR_INVALID, "instance buffer too small");
+    if (!s->instances.empty()) memcpy(out, s->instances.data(), s->instances.size() * sizeof(SolbSceneInstance));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_accel_info(solb_scene *s, SolbAccelInfo *out) {
+    if (!s || !out) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "acceleration structure not built");
+    memset(out, 0, sizeof(*out));
+    out->n_instances = (uint32_t)s->instances.size();
+    out->n_triangles = s->accel.n_tris;
+    out->n_wide_nodes = s->accel.n_wide;
+    out->wide_depth = s->accel.depth;
+    out->n_binary_nodes = s->accel.n_binary;
+    out->sah_cost_binary = s->accel.sah_final;
+    out->sah_cost_lbvh = s->accel.sah_lbvh;
+    for (int k = 0; k < 3; k++) { out->scene_lo[k] = s->accel.lo[k]; out->scene_hi[k] = s->accel.hi[k]; }
+    return SOLB_OK;
+}
+
+SOLB_API int solb_accel_read_nodes(solb_scene *s, void *host, size_t bytes) {
+    if (!s || !host) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "acceleration structure not built");
+    if (bytes != (size_t)s->accel.n_wide * sizeof(Node8)) return fail(s->ctx, SOLB_ERR_INVALID, "size must be n_wide_nodes * 80");
+    CU(s->ctx, cudaSetDevice(s->ctx->device));
+    CU(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    CU(s->ctx, cudaMemcpy(host, s->accel.nodes, bytes, cudaMemcpyDeviceToHost));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_accel_read_triangles(solb_scene *s, void *host, size_t bytes) {
+    if (!s || (!host && bytes)) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "acceleration structure not built");
+    if (bytes != (size_t)s->accel.n_tris * sizeof(Tri48)) return fail(s->ctx, SOLB_ERR_INVALID, "size must be n_triangles * 48");
+    CU(s->ctx, cudaSetDevice(s->ctx->device));
+    CU(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    if (bytes) CU(s->ctx, cudaMemcpy(host, s->accel.tris, bytes, cudaMemcpyDeviceToHost));
+    return SOLB_OK;
+}
+
+// ---- targets -----------------------------------------------------------------------------------------
+
+SOLB_API int solb_target_create(solb_ctx *ctx, uint32_t width, uint32_t height, uint32_t format, solb_target **out) {
+    if (!ctx || !out) return fail(ctx, SOLB_ERR_INVALID, "solb_target_create: null argument");
+    *out = nullptr;
+    if (format > SOLB_FORMAT_RG32UI) return fail(ctx, SOLB_ERR_INVALID, "unknown target format");
+    if (width == 0 || height == 0) return fail(ctx, SOLB_ERR_INVALID, "zero-sized target (src/texture.rs:45 asserts extent > 0)");
+    if ((uint64_t)width * height > 0x7fffffffull) return fail(ctx, SOLB_ERR_INVALID, "target too large");
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    solb_target *t = new solb_target();
+    t->ctx = ctx; t->width = width; t->height = height; t->format = format;
+    t->bytes = (size_t)width * height * format_bytes(format);
+    cudaError_t e = cudaMalloc(&t->dev, t->bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t->dev, 0, t->bytes, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(t->dev); delete t; return fail_cuda(ctx, e, "target alloc"); }
+    *out = t;
+    return SOLB_OK;
+    SOLB_CATCH(ctx)
+}
+
+SOLB_API int solb_target_destroy(solb_target *t) {
+    if (!t) return SOLB_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->dev);
+    delete t;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_target_clear(solb_target *t) {
+    if (!t) return fail(nullptr, SOLB_ERR_INVALID, "null target");
+    CU(t->ctx, cudaSetDevice(t->ctx->device));
+    CU(t->ctx, cudaMemsetAsync(t->dev, 0, t->bytes, t->ctx->stream));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_target_readback(solb_target *t, void *host, size_t bytes) {
+    if (!t || !host) return fail(t ? t->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (bytes != t->bytes) return fail(t->ctx, SOLB_ERR_INVALID, "readback size must equal width*height*texel size");
+    CU(t->ctx, cudaSetDevice(t->ctx->device));
+    CU(t->ctx, cudaMemcpyAsync(host, t->dev, bytes, cudaMemcpyDeviceToHost, t->ctx->stream));
+    CU(t->ctx, cudaStreamSynchronize(t->ctx->stream));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_target_upload(solb_target *t, const void *host, size_t bytes) {
+    if (!t || !host) return fail(t ? t->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (bytes != t->bytes) return fail(t->ctx, SOLB_ERR_INVALID, "upload size must equal width*height*texel size");
+    CU(t->ctx, cudaSetDevice(t->ctx->device));
+    CU(t->ctx, cudaMemcpyAsync(t->dev, host, bytes, cudaMemcpyHostToDevice, t->ctx->stream));
+    CU(t->ctx, cudaStreamSynchronize(t->ctx->stream));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_target_device_ptr(solb_target *t, void **out) {
+    if (!t || !out) return fail(t ? t->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    *out = t->dev;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_target_info(solb_target *t, uint32_t *width, uint32_t *height, uint32_t *format) {
+    if (!t) return fail(nullptr, SOLB_ERR_INVALID, "null target");
+    if (width) *width = t->width;
+    if (height) *height = t->height;
+    if (format) *format = t->format;
+    return SOLB_OK;
+}
+
+// ---- trace -------------------------------------------------------------------------------------------
+
+SOLB_API void solb_trace_params_default(SolbTraceParams *p, int pipeline) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->accum_start_frame = 0;
+    p->enable_sky = 0;
+    p->samples_per_frame = pipeline == 1 ? 4u : 8u;  // ao.rgen:43 / pathtrace.rgen:44
+    p->max_bounces = pipeline == 1 ? 4u : 32u;       // ao.rgen:42 / pathtrace.rgen:43
+    p->schedule = SOLB_SCHEDULE_WAVEFRONT;
+    p->accum_mode = SOLB_ACCUM_MIX;
+}
+
+static void fill_frame_consts(FrameConsts &fc, const SolbSceneUniforms *u, uint32_t w, uint32_t h) {
+    memset(&fc, 0, sizeof(fc));
+    memcpy(fc.view_inv, u->view_inverse, sizeof(fc.view_inv));
+    memcpy(fc.proj_inv, u->projection_inverse, sizeof(fc.proj_inv));
+    // origin = view_inverse * vec4(0,0,0,1) (pathtrace.rgen:55)
+    fc.origin = make_float3(u->view_inverse[12], u->view_inverse[13], u->view_inverse[14]);
+    const float len = sqrtf(fc.origin.x * fc.origin.x + fc.origin.y * fc.origin.y + fc.origin.z * fc.origin.z);
+    fc.tmin = fmaxf(1.0f, len) * 1e-3f;  // preparePayload, pathtrace.rgen:35
+    fc.tmax = 10000.0f;
+    // gl_LaunchSizeEXT = the extent passed to cmd_trace_rays = the target size (src/ray/sbt.rs:175-177)
+    fc.width = w;
+    fc.height = h;
+    fc.frame = u->frame[2];
+}
+
+static int check_trace_args(solb_scene *s, const SolbSceneUniforms *u) {
+    if (!s || !u) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "trace: null scene/uniforms");
+    if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "trace before solb_accel_build");
+    return SOLB_OK;
+}
+
+static int check_target(solb_ctx *ctx, solb_target *t, uint32_t format, const solb_target *like, const char *name) {
+    if (!t) return fail(ctx, SOLB_ERR_INVALID, std::string(name) + " target is NULL");
+    if (t->ctx != ctx) return fail(ctx, SOLB_ERR_INVALID, std::string(name) + " target belongs to another ctx");
+    if (t->format != format) return fail(ctx, SOLB_ERR_INVALID, std::string(name) + " target has the wrong format");
+    if (like && (like->width != t->width || like->height != t->height))
+        return fail(ctx, SOLB_ERR_INVALID, std::string(name) + " target size differs from the other targets");
+    return SOLB_OK;
+}
+
+static int ensure_wavefront(solb_ctx *ctx, uint32_t n_pixels) {
+    WavefrontState &w = ctx->ws;
+    if (w.capacity >= n_pixels && w.ray_o) return SOLB_OK;
+    free_wavefront(ctx);
+    const size_t n = n_pixels;
+    CU(ctx, cudaMalloc((void **)&w.ray_o, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.ray_d, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.thr, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.pix, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.hit, n * sizeof(uint4)));
+    CU(ctx, cudaMalloc((void **)&w.queue[0], n * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc((void **)&w.queue[1], n * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc((void **)&w.counters, 4 * sizeof(uint32_t)));
+    w.capacity = n_pixels;
+    return SOLB_OK;
+}
+
+struct TraceTimer {
+    solb_ctx *c;
+    explicit TraceTimer(solb_ctx *ctx) : c(ctx) { if (c->timing) cudaEventRecord(c->ev0, c->stream); }
+    void stop() {
+        if (!c->timing) return;
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        cudaEventElapsedTime(&c->last_trace_ms, c->ev0, c->ev1);
+    }
+};
+
+SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, const SolbTraceParams *params, solb_target *accum,
+                                  solb_target *render) {
+    int rc = check_trace_args(s, u);
+    if (rc) return rc;
+    solb_ctx *ctx = s->ctx;
+    if (!params) return fail(ctx, SOLB_ERR_INVALID, "trace: null params");
+    if ((rc = check_target(ctx, accum, SOLB_FORMAT_RGBA32F, nullptr, "accum"))) return rc;
+    if (render && (rc = check_target(ctx, render, SOLB_FORMAT_RGBA8, accum, "render"))) return rc;
+    if (params->samples_per_frame == 0 || params->samples_per_frame > 0xffffu || params->max_bounces > 0xfff0u)
+        return fail(ctx, SOLB_ERR_INVALID, "samples_per_frame must be 1..65535 and max_bounces <= 65520");
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    FrameConsts fc;
+    fill_frame_consts(fc, u, accum->width, accum->height);
+    fc.accum_start = params->accum_start_frame;
+    fc.enable_sky = params->enable_sky;
+    fc.spp = params->samples_per_frame;
+    fc.max_bounces = params->max_bounces;
+    fc.accum_mode = params->accum_mode;
+    TraceTimer timer(ctx);
+    uint32_t n_ev = 0;
+    if (params->schedule == SOLB_SCHEDULE_MEGAKERNEL) {
+        CU(ctx, launch_pathtrace_mega(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, (float4 *)accum->dev,
+                                      render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0));
+        ctx->launches += 1;
+        timer.stop();
+        if (ctx->timing) { ctx->trace_kernel_ms_total += ctx->last_trace_ms; ctx->trace_kernel_launches += 1; }
+        return SOLB_OK;
+    } else {
+        if ((rc = ensure_wavefront(ctx, fc.width * fc.height))) return rc;
+        CU(ctx, launch_pathtrace_wavefront(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->ws, (float4 *)accum->dev,
+                                           render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0,
+                                           ctx->sm_count, ctx->pinned_count, &ctx->launches, ctx->timing ? &ctx->ev_pool : nullptr,
+                                           &n_ev));
+    }
+    timer.stop();  // synchronises in timing mode
+    for (uint32_t i = 0; ctx->timing && i + 1 < n_ev; i += 2) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) ctx->trace_kernel_ms_total += ms;
+        ctx->trace_kernel_launches += 1;
+    }
+    return SOLB_OK;
+    SOLB_CATCH(ctx)
+}
+
+SOLB_API int solb_set_blue_noise(solb_ctx *ctx, const uint8_t *rgba8, uint32_t width, uint32_t height) {
+    if (!ctx || !rgba8 || !width || !height) return fail(ctx, SOLB_ERR_INVALID, "solb_set_blue_noise: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_blue);
+    ctx->d_blue = nullptr;
+    CU(ctx, cudaMalloc((void **)&ctx->d_blue, (size_t)width * height * 4));
+    CU(ctx, cudaMemcpy(ctx->d_blue, rgba8, (size_t)width * height * 4, cudaMemcpyHostToDevice));
+    ctx->blue_w = width;
+    ctx->blue_h = height;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_trace_ao(solb_scene *s, const SolbSceneUniforms *u, const SolbTraceParams *params, solb_target *image) {
+    int rc = check_trace_args(s, u);
+    if (rc) return rc;
+    solb_ctx *ctx = s->ctx;
+    if (!params) return fail(ctx, SOLB_ERR_INVALID, "trace: null params");
+    if ((rc = check_target(ctx, image, SOLB_FORMAT_RGBA32F, nullptr, "image"))) return rc;
+    if (!ctx->d_blue) return fail(ctx, SOLB_ERR_INVALID, "solb_trace_ao before solb_set_blue_noise (binding 2, examples/4-ray-ao.rs:282)");
+    if (params->samples_per_frame == 0 || params->max_bounces == 0) return fail(ctx, SOLB_ERR_INVALID, "ao: zero samples");
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    FrameConsts fc;
+    fill_frame_consts(fc, u, image->width, image->height);
+    fc.accum_start = params->accum_start_frame;
+    fc.spp = params->samples_per_frame;
+    fc.max_bounces = params->max_bounces;
+    TraceTimer timer(ctx);
+    CU(ctx, launch_ao(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->d_blue, ctx->blue_w, ctx->blue_h, (float4 *)image->dev,
+                      ctx->d_stats));
+    ctx->launches += 1;
+    timer.stop();
+    return SOLB_OK;
+    SOLB_CATCH(ctx)
+}
+
+SOLB_API int solb_trace_debug(solb_scene *s, const SolbSceneUniforms *u, solb_target *render, solb_target *ids, solb_target *attribs) {
+    int rc = check_trace_args(s, u);
+    if (rc) return rc;
+    solb_ctx *ctx = s->ctx;
+    solb_target *first = render ? render : (ids ? ids : attribs);
+    if (!first) return fail(ctx, SOLB_ERR_INVALID, "solb_trace_debug: no output target");
+    if (render && (rc = check_target(ctx, render, SOLB_FORMAT_RGBA8, first, "render"))) return rc;
+    if (ids && (rc = check_target(ctx, ids, SOLB_FORMAT_RG32UI, first, "ids"))) return rc;
+    if (attribs && (rc = check_target(ctx, attribs, SOLB_FORMAT_RGBA32F, first, "attribs"))) return rc;
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    FrameConsts fc;
+    fill_frame_consts(fc, u, first->width, first->height);
+    TraceTimer timer(ctx);
+    CU(ctx, launch_debug(ctx->stream, fc, s->accel, render ? (uint32_t *)render->dev : nullptr, ids ? (uint2 *)ids->dev : nullptr,
+                         attribs ? (float4 *)attribs->dev : nullptr, ctx->d_stats));
+    ctx->launches += 1;
+    timer.stop();
+    return SOLB_OK;
+    SOLB_CATCH(ctx)
+}
+
+SOLB_API int solb_trace_rays(solb_scene *s, const float *rays, uint32_t n, uint32_t *hits, float *t_out) {
+    if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
+    solb_ctx *ctx = s->ctx;
+    if (!s->built) return fail(ctx, SOLB_ERR_NOT_BUILT, "trace before solb_accel_build");
+    if (n == 0) return SOLB_OK;
+    if (!rays || !hits) return fail(ctx, SOLB_ERR_INVALID, "solb_trace_rays: null argument");
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    float4 *d_rays = nullptr;
+    uint4 *d_hits = nullptr;
+    float *d_t = nullptr;
+    struct Free { void *a, *b, *c; ~Free() { cudaFree(a); cudaFree(b); cudaFree(c); } };
+    CU(ctx, cudaMalloc((void **)&d_rays, (size_t)n * 32));
+    Free fr{ d_rays, nullptr, nullptr };
+    CU(ctx, cudaMalloc((void **)&d_hits, (size_t)n * 16));
+    fr.b = d_hits;
+    CU(ctx, cudaMalloc((void **)&d_t, (size_t)n * 4));
+    fr.c = d_t;
+    CU(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    TraceTimer timer(ctx);
+    CU(ctx, launch_trace_rays(ctx->stream, s->accel, d_rays, n, d_hits, d_t, ctx->d_stats));
+    ctx->launches += 1;
+    timer.stop();
+    CU(ctx, cudaMemcpyAsync(hits, d_hits, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t_out) CU(ctx, cudaMemcpyAsync(t_out, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOLB_OK;
+    SOLB_CATCH(ctx)
+}
+
+SOLB_API int solb_resolve_sum(solb_ctx *ctx, solb_target *sum, solb_target *accum_out, solb_target *render) {
+    if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
+    int rc;
+    if ((rc = check_target(ctx, sum, SOLB_FORMAT_RGBA32F, nullptr, "sum"))) return rc;
+    if (accum_out && (rc = check_target(ctx, accum_out, SOLB_FORMAT_RGBA32F, sum, "accum_out"))) return rc;
+    if (render && (rc = check_target(ctx, render, SOLB_FORMAT_RGBA8, sum, "render"))) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_resolve_sum(ctx->stream, (const float4 *)sum->dev, accum_out ? (float4 *)accum_out->dev : nullptr,
+                               render ? (uint32_t *)render->dev : nullptr, sum->width * sum->height));
+    ctx->launches += 1;
+    return SOLB_OK;
+}
+
+}  // extern "C"

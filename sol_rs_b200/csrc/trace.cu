@@ -1,0 +1,539 @@
+// trace.cu — trace kernels for sm_100a: the three reference pipelines as CUDA launches.
+//   5-pathtrace  (assets/glsl/pathtrace.{rgen,rchit,rmiss})  -> wavefront kernels or megakernel
+//   4-ray-ao     (assets/glsl/ao.{rgen,rchit,rmiss})         -> k_ao
+//   3-ray-debug  (assets/glsl/debug.{rgen,rchit,rmiss})      -> k_debug
+// Each launch sequence replaces one ShaderBindingTable::cmd_trace_rays (src/ray/sbt.rs:167-180).
+#include "trace.h"
+
+#include "shade.cuh"
+
+namespace solb {
+
+constexpr int TRACE_BLOCK = 128;
+
+// Traversal stack: SOLB_SM_STACK entries per lane in shared memory ([entry][thread] so a warp's
+// accesses are conflict-free), the rest spills to local memory.
+struct DevStack {
+    uint2 *sm;
+    uint2 loc[SOLB_LOCAL_STACK];
+    int sp;
+    __device__ __forceinline__ void push(uint2 v) {
+        if (sp < SOLB_SM_STACK) sm[sp * TRACE_BLOCK] = v;
+        else loc[sp - SOLB_SM_STACK] = v;
+        sp++;
+    }
+    __device__ __forceinline__ uint2 pop() {
+        sp--;
+        return sp < SOLB_SM_STACK ? sm[sp * TRACE_BLOCK] : loc[sp - SOLB_SM_STACK];
+    }
+    __device__ __forceinline__ bool empty() const { return sp == 0; }
+};
+
+#define SOLB_DECL_STACK()                                        \
+    __shared__ uint2 s_stack[SOLB_SM_STACK * TRACE_BLOCK];       \
+    DevStack stack;                                              \
+    stack.sm = s_stack + threadIdx.x;                            \
+    stack.sp = 0
+
+// stats slots (unsigned long long each)
+enum { ST_RAYS = 0, ST_HITS = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4 };
+
+__device__ __forceinline__ void warp_add_stat(unsigned long long *stats, int slot, uint32_t v) {
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&stats[slot], (unsigned long long)v);
+}
+
+// pixel owned by this thread: each warp covers an 8x4 tile so primary rays stay coherent
+__device__ __forceinline__ bool thread_pixel(uint32_t width, uint32_t height, uint32_t &x, uint32_t &y) {
+    const uint32_t tiles_x = (width + 7u) >> 3;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    const uint32_t ty = gwarp / tiles_x, tx = gwarp - ty * tiles_x;
+    x = tx * 8u + (lane & 7u);
+    y = ty * 4u + (lane >> 3);
+    return x < width && y < height;
+}
+static uint32_t pixel_grid_blocks(uint32_t width, uint32_t height) {
+    const uint64_t warps = (uint64_t)((width + 7u) >> 3) * ((height + 3u) >> 2);
+    return (uint32_t)((warps * 32u + TRACE_BLOCK - 1) / TRACE_BLOCK);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3-ray-debug: debug.rgen:18-37 + debug.rchit:9-13 + debug.rmiss:6-9, plus the ids the parity gate needs
+__global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, const uint4 *__restrict__ nodes,
+                                                       const float4 *__restrict__ tris, uint32_t *render, uint2 *ids,
+                                                       float4 *attribs, unsigned long long *stats) {
+    SOLB_DECL_STACK();
+    uint32_t x, y;
+    const bool active = thread_pixel(fc.width, fc.height, x, y);
+    uint32_t nr = 0, nh = 0;
+    if (active) {
+        Ray r;
+        r.o = fc.origin;
+        r.d = primary_dir(fc, (float)x + 0.5f, (float)y + 0.5f);  // debug.rgen:20
+        r.tmin = 0.001f;                                          // debug.rgen:32-33
+        r.tmax = 1000.0f;
+        Hit h;
+        trace_closest<false>(nodes, tris, r, h, stack, (TraceCounters *)nullptr);
+        nr = 1;
+        float3 hv = r.d;  // debug.rgen:28: payload preset to the direction, the miss shader leaves it
+        if (h.inst != SOLB_MISS) { hv = f3(1.0f - h.u - h.v, h.u, h.v); nh = 1; }  // debug.rchit:11-12
+        const size_t p = (size_t)y * fc.width + x;
+        if (render) render[p] = pack_rgba8(hv.x, hv.y, hv.z, 0.0f);  // debug.rgen:36
+        if (ids) ids[p] = make_uint2(h.inst, h.prim);
+        if (attribs) attribs[p] = make_float4(h.u, h.v, h.inst != SOLB_MISS ? h.t : 0.0f, 0.0f);
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    warp_add_stat(stats, ST_HITS, nh);
+}
+
+// traceRayEXT for arbitrary rays (tests)
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
+                                                            const float4 *__restrict__ rays, uint32_t n, uint4 *hits, float *t_out,
+                                                            unsigned long long *stats) {
+    SOLB_DECL_STACK();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    TraceCounters ctr = { 0, 0 };
+    uint32_t nr = 0;
+    if (i < n) {
+        const float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
+        Ray r;
+        r.o = f3(a.x, a.y, a.z); r.tmin = a.w;
+        r.d = f3(b.x, b.y, b.z); r.tmax = b.w;
+        Hit h;
+        trace_closest<true>(nodes, tris, r, h, stack, &ctr);
+        hits[i] = make_uint4(h.inst, h.prim, __float_as_uint(h.u), __float_as_uint(h.v));
+        if (t_out) t_out[i] = h.inst != SOLB_MISS ? h.t : 0.0f;
+        nr = 1;
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    warp_add_stat(stats, ST_NODES, ctr.nodes);
+    warp_add_stat(stats, ST_TRIS, ctr.tris);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 5-pathtrace, megakernel schedule: pathtrace.rgen:39-104 with the sample and bounce loops flattened
+// into one loop so a lane that ends a path immediately starts its next sample.
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConsts fc, const uint4 *__restrict__ nodes,
+                                                                const float4 *__restrict__ tris,
+                                                                const DeviceInstance *__restrict__ instances,
+                                                                const ShadeRecord *__restrict__ shade, float4 *accum,
+                                                                uint32_t *render, unsigned long long *stats) {
+    SOLB_DECL_STACK();
+    uint32_t x, y;
+    const bool active = thread_pixel(fc.width, fc.height, x, y);
+    uint32_t nr = 0, nh = 0, np = 0;
+    TraceCounters ctr = { 0, 0 };
+    if (active) {
+        uint32_t rng = tea(x + y * fc.width, fc.frame);  // :47
+        float3 pixel = f3(0, 0, 0);
+        uint32_t sample = 0, depth = 0;
+        float3 thr = f3(1, 1, 1);
+        Ray r;
+        r.tmin = fc.tmin;  // rayRange is set once per sample and never touched by rchit (:35)
+        r.tmax = fc.tmax;
+        {
+            const float jx = next_rand(rng), jy = next_rand(rng);  // :52
+            r.o = fc.origin;
+            r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+            np++;
+        }
+        while (sample < fc.spp) {
+            Hit h;
+            stack.sp = 0;
+            trace_closest<STATS>(nodes, tris, r, h, stack, &ctr);  // :65-76
+            nr++;
+            bool end_path;
+            if (h.inst != SOLB_MISS) {
+                nh++;
+                float3 hv;
+                const bool done = shade_hit(instances, shade, h.inst, h.gtri, h.u, h.v, r.o, r.d, rng, hv);
+                depth++;
+                thr = thr * hv;  // :77
+                end_path = done;
+                if (!done && depth > fc.max_bounces) {  // :81-84
+                    thr = f3(0, 0, 0);
+                    end_path = true;
+                }
+            } else {
+                thr = thr * shade_miss(fc.enable_sky, r.d);  // rmiss, done = 1
+                end_path = true;
+            }
+            if (end_path) {
+                pixel = pixel + thr;  // :86
+                sample++;
+                if (sample < fc.spp) {
+                    const float jx = next_rand(rng), jy = next_rand(rng);
+                    r.o = fc.origin;
+                    r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                    thr = f3(1, 1, 1);
+                    depth = 0;
+                    np++;
+                }
+            }
+        }
+        const size_t p = (size_t)y * fc.width + x;
+        uint32_t rgba;
+        const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
+        accum[p] = out;
+        if (render) render[p] = rgba;
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    warp_add_stat(stats, ST_HITS, nh);
+    warp_add_stat(stats, ST_PATHS, np);
+    if (STATS) {
+        warp_add_stat(stats, ST_NODES, ctr.nodes);
+        warp_add_stat(stats, ST_TRIS, ctr.tris);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 5-pathtrace, wavefront schedule.
+//   k_wf_generate : per pixel, seed the RNG, emit sample 0's primary ray, fill the ray queue
+//   k_wf_trace    : persistent warps pull 32-ray batches from the queue (atomic head), closest hit -> hit record
+//   k_wf_shade    : per queued pixel, rchit / rmiss / bounce cap, regenerate the pixel's next sample in place,
+//                   ballot-compact the still-alive pixels into the next queue
+//   k_wf_resolve  : per pixel, mean of spp, running mix, NaN/Inf guard, gamma, rgba8
+// Per-pixel path state lives in SoA float4/uint4 arrays (WavefrontState); the RNG state flows from sample to
+// sample inside a pixel exactly like prd.rng does in pathtrace.rgen:47-86.
+
+__device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, uint32_t width, uint32_t height, bool &valid) {
+    // queue slot i -> pixel, in 8x4 tiles (same order as thread_pixel)
+    const uint32_t tiles_x = (width + 7u) >> 3;
+    const uint32_t w = i >> 5, lane = i & 31u;
+    const uint32_t ty = w / tiles_x, tx = w - ty * tiles_x;
+    const uint32_t x = tx * 8u + (lane & 7u), y = ty * 4u + (lane >> 3);
+    valid = x < width && y < height;
+    return y * width + x;
+}
+
+__global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, WavefrontState ws, uint32_t n_slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    uint32_t p = 0;
+    if (i < n_slots) p = swizzled_pixel(i, fc.width, fc.height, valid);
+    if (valid) {
+        const uint32_t x = p % fc.width, y = p / fc.width;
+        uint32_t rng = tea(p, fc.frame);
+        const float jx = next_rand(rng), jy = next_rand(rng);
+        const float3 d = primary_dir(fc, (float)x + jx, (float)y + jy);
+        ws.ray_o[p] = make_float4(fc.origin.x, fc.origin.y, fc.origin.z, 0.0f);
+        ws.ray_d[p] = make_float4(d.x, d.y, d.z, 0.0f);
+        ws.thr[p] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));  // w: depth | sample << 16
+        ws.pix[p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(rng));
+    }
+    // compact valid pixels into queue 0 (image edges may leave holes in the tile order)
+    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&ws.counters[0], (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (valid) ws.queue[0][base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = p;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
+                                                          const float4 *__restrict__ tris, WavefrontState ws, int qi,
+                                                          unsigned long long *stats) {
+    SOLB_DECL_STACK();
+    const uint32_t n = ws.counters[qi];
+    const uint32_t *__restrict__ queue = ws.queue[qi];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters[qi ^ 1] = 0;  // next wave's output queue
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t nr = 0;
+    TraceCounters ctr = { 0, 0 };
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ws.counters[2], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const uint32_t p = queue[i];
+            const float4 o = ws.ray_o[p], d = ws.ray_d[p];
+            Ray r;
+            r.o = f3(o.x, o.y, o.z); r.d = f3(d.x, d.y, d.z);
+            r.tmin = fc.tmin; r.tmax = fc.tmax;
+            Hit h;
+            stack.sp = 0;
+            trace_closest<STATS>(nodes, tris, r, h, stack, &ctr);
+            ws.hit[p] = make_uint4(h.inst, h.gtri, __float_as_uint(h.u), __float_as_uint(h.v));
+            nr++;
+        }
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    if (STATS) {
+        warp_add_stat(stats, ST_NODES, ctr.nodes);
+        warp_add_stat(stats, ST_TRIS, ctr.tris);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_wf_shade(const FrameConsts fc, const DeviceInstance *__restrict__ instances,
+                                                  const ShadeRecord *__restrict__ shade, WavefrontState ws, int qi,
+                                                  unsigned long long *stats) {
+    const uint32_t n = ws.counters[qi];
+    const uint32_t *__restrict__ queue_in = ws.queue[qi];
+    uint32_t *__restrict__ queue_out = ws.queue[qi ^ 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters[2] = 0;  // trace work head of the next wave
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t nh = 0, np = 0;
+    // grid-stride over warps so the ballot below always sees whole warps
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool alive = false;
+        uint32_t p = 0;
+        if (i < n) {
+            p = queue_in[i];
+            const uint4 h = ws.hit[p];
+            const float4 t4 = ws.thr[p], x4 = ws.pix[p];
+            float3 thr = f3(t4.x, t4.y, t4.z), pixel = f3(x4.x, x4.y, x4.z);
+            uint32_t ds = __float_as_uint(t4.w), rng = __float_as_uint(x4.w);
+            uint32_t depth = ds & 0xffffu, sample = ds >> 16;
+            const float4 d4 = ws.ray_d[p];
+            float3 o = f3(0, 0, 0), d = f3(d4.x, d4.y, d4.z);
+            bool end_path;
+            if (h.x != SOLB_MISS) {
+                nh++;
+                float3 hv;
+                const bool done = shade_hit(instances, shade, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
+                depth++;
+                thr = thr * hv;
+                end_path = done;
+                if (!done && depth > fc.max_bounces) { thr = f3(0, 0, 0); end_path = true; }
+            } else {
+                thr = thr * shade_miss(fc.enable_sky, d);
+                end_path = true;
+            }
+            alive = true;
+            if (end_path) {
+                pixel = pixel + thr;
+                sample++;
+                if (sample < fc.spp) {
+                    const uint32_t x = p % fc.width, y = p / fc.width;
+                    const float jx = next_rand(rng), jy = next_rand(rng);
+                    o = fc.origin;
+                    d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                    thr = f3(1, 1, 1);
+                    depth = 0;
+                    np++;
+                } else {
+                    alive = false;
+                }
+                ws.pix[p] = make_float4(pixel.x, pixel.y, pixel.z, __uint_as_float(rng));
+            } else {
+                ws.pix[p].w = __uint_as_float(rng);
+            }
+            if (alive) {
+                ws.ray_o[p] = make_float4(o.x, o.y, o.z, 0.0f);
+                ws.ray_d[p] = make_float4(d.x, d.y, d.z, 0.0f);
+                ws.thr[p] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(depth | (sample << 16)));
+            }
+        }
+        // warp-ballot compaction + one atomic per warp to append survivors to the next queue
+        const uint32_t m = __ballot_sync(0xffffffffu, alive);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(&ws.counters[qi ^ 1], (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (alive) queue_out[base + __popc(m & ((1u << lane) - 1u))] = p;
+    }
+    warp_add_stat(stats, ST_HITS, nh);
+    warp_add_stat(stats, ST_PATHS, np);
+}
+
+__global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, WavefrontState ws, float4 *accum, uint32_t *render) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fc.width * fc.height) return;
+    const float4 x4 = ws.pix[p];
+    uint32_t rgba;
+    const float4 out = resolve_pixel(fc, f3(x4.x, x4.y, x4.z), accum[p], rgba);
+    accum[p] = out;
+    if (render) render[p] = rgba;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4-ray-ao: ao.rgen:37-83 + ao.rchit:45-88 + ao.rmiss:7-10, one thread per pixel
+__global__ void __launch_bounds__(TRACE_BLOCK) k_ao(const FrameConsts fc, const uint4 *__restrict__ nodes,
+                                                    const float4 *__restrict__ tris, const DeviceInstance *__restrict__ instances,
+                                                    const ShadeRecord *__restrict__ shade, const uint32_t *__restrict__ blue,
+                                                    uint32_t blue_w, uint32_t blue_h, float4 *image, unsigned long long *stats) {
+    SOLB_DECL_STACK();
+    uint32_t x, y;
+    const bool active = thread_pixel(fc.width, fc.height, x, y);
+    uint32_t nr = 0, nh = 0, np = 0;
+    if (active) {
+        const uint32_t max_samples = fc.max_bounces;  // ao.rgen:42 (4)
+        const uint32_t sample_count = fc.spp;         // ao.rgen:43 (4)
+        uint32_t rng = tea(x + y * fc.width, fc.frame);  // ao.rgen:45
+        float3 ao = f3(0, 0, 0);
+        for (uint32_t s = 0; s < sample_count; s++) {
+            const float jx = next_rand(rng), jy = next_rand(rng);  // ao.rgen:49
+            Ray r;
+            r.o = fc.origin;
+            r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+            r.tmin = fc.tmin;  // preparePayload, ao.rgen:33
+            r.tmax = fc.tmax;
+            float3 hit_value = f3(0, 0, 0);
+            uint32_t depth = 0;
+            np++;
+            for (;;) {
+                Hit h;
+                stack.sp = 0;
+                trace_closest<false>(nodes, tris, r, h, stack, (TraceCounters *)nullptr);
+                nr++;
+                if (h.inst == SOLB_MISS) break;  // ao.rmiss: done = 1
+                nh++;
+                ao_hit(instances, shade, h.inst, h.gtri, h.u, h.v, x, y, blue, blue_w, blue_h, depth, s, r.o, r.d, rng);
+                r.tmin = 0.001f;  // ao.rchit:83
+                r.tmax = 10.0f;
+                if (depth > 0) hit_value = hit_value + f3(1, 1, 1);  // ao.rchit:84-86
+                depth++;
+                if (depth > max_samples) break;  // ao.rgen:71
+            }
+            ao = ao + hit_value * (1.0f / (float)max_samples);  // ao.rgen:74
+        }
+        float3 color = f3(1.0f - ao.x / (float)sample_count, 1.0f - ao.y / (float)sample_count, 1.0f - ao.z / (float)sample_count);
+        const size_t p = (size_t)y * fc.width + x;
+        const float a = 1.0f / (float)(uint32_t)(fc.frame - (uint32_t)fc.accum_start + 1u);  // ao.rgen:78
+        const float4 old4 = image[p];
+        color = mix3(f3(old4.x, old4.y, old4.z), color, a);  // ao.rgen:80 (no NaN guard, no gamma)
+        image[p] = make_float4(color.x, color.y, color.z, 1.0f);
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    warp_add_stat(stats, ST_HITS, nh);
+    warp_add_stat(stats, ST_PATHS, np);
+}
+
+// sum / count -> accum + display (multi-GPU resolve after the reduce)
+__global__ void __launch_bounds__(256) k_resolve_sum(const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float4 s = sum[p];
+    const float inv = s.w > 0.0f ? 1.0f / s.w : 0.0f;
+    const float3 c = f3(s.x * inv, s.y * inv, s.z * inv);
+    if (accum_out) accum_out[p] = make_float4(c.x, c.y, c.z, 1.0f);
+    const float g = 1.0f / 2.2f;
+    if (render) render[p] = pack_rgba8(powf(c.x, g), powf(c.y, g), powf(c.z, g), 1.0f);
+}
+
+// de-index the reference vertex layout into per-triangle shading records (object space)
+__global__ void k_build_shade_records(const DeviceSceneView sv, ShadeRecord *out) {
+    const float4 *__restrict__ vertices = sv.vertices;  // 4 float4 per ModelVertex
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= sv.n_tris) return;
+    uint32_t lo = 0, hi = sv.n_instances;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sv.inst_first_tri[mid] <= g) lo = mid; else hi = mid;
+    }
+    const DeviceInstance &di = sv.instances[lo];
+    const uint32_t prim = g - sv.inst_first_tri[lo];
+    float f[28];
+    for (int k = 0; k < 3; k++) {
+        const uint32_t vi = di.first_vertex + sv.indices[di.first_index + 3 * prim + k];
+        const float4 pos = vertices[4 * (size_t)vi + 0], col = vertices[4 * (size_t)vi + 1], nrm = vertices[4 * (size_t)vi + 2];
+        f[9 * k + 0] = pos.x; f[9 * k + 1] = pos.y; f[9 * k + 2] = pos.z;
+        f[9 * k + 3] = nrm.x; f[9 * k + 4] = nrm.y; f[9 * k + 5] = nrm.z;
+        f[9 * k + 6] = col.x; f[9 * k + 7] = col.y; f[9 * k + 8] = col.z;
+    }
+    f[27] = 0.0f;
+    for (int i = 0; i < 7; i++) out[g].q[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side launch wrappers
+cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &sv, ShadeRecord *out) {
+    if (sv.n_tris == 0) return cudaSuccess;
+    k_build_shade_records<<<(sv.n_tris + 255) / 256, 256, 0, st>>>(sv, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_debug(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, uint32_t *render, uint2 *ids,
+                         float4 *attribs, unsigned long long *stats) {
+    k_debug<<<pixel_grid_blocks(fc.width, fc.height), TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), render, ids, attribs, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const float4 *rays, uint32_t n, uint4 *hits, float *t_out,
+                              unsigned long long *stats) {
+    if (n == 0) return cudaSuccess;
+    k_trace_rays<<<(n + TRACE_BLOCK - 1) / TRACE_BLOCK, TRACE_BLOCK, 0, st>>>(as.nodes_u4(), as.tris_f4(), rays, n, hits, t_out, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
+                                  const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
+                                  bool collect) {
+    const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
+    if (collect)
+        k_pathtrace_mega<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), instances, shade, accum, render, stats);
+    else
+        k_pathtrace_mega<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), instances, shade, accum, render, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
+                      const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
+                      unsigned long long *stats) {
+    k_ao<<<pixel_grid_blocks(fc.width, fc.height), TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), instances, shade, blue, bw,
+                                                                         bh, image, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n) {
+    if (n == 0) return cudaSuccess;
+    k_resolve_sum<<<(n + 255) / 256, 256, 0, st>>>(sum, accum_out, render, n);
+    return cudaGetLastError();
+}
+
+// One reference frame with the wavefront schedule.  Returns the number of kernels launched.
+cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as,
+                                       const DeviceInstance *instances, const ShadeRecord *shade, WavefrontState &ws, float4 *accum,
+                                       uint32_t *render, unsigned long long *stats, bool collect, int sm_count,
+                                       uint32_t *host_count_pinned, uint64_t *launches, std::vector<cudaEvent_t> *events,
+                                       uint32_t *n_events_used) {
+    const uint32_t n_pixels = fc.width * fc.height;
+    if (n_pixels == 0) return cudaSuccess;
+    const uint32_t n_slots = (uint32_t)((((uint64_t)((fc.width + 7u) >> 3) * ((fc.height + 3u) >> 2))) * 32u);
+    cudaError_t err = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(uint32_t), st);
+    if (err != cudaSuccess) return err;
+    k_wf_generate<<<(n_slots + 255) / 256, 256, 0, st>>>(fc, ws, n_slots);
+    *launches += 1;
+    const int trace_grid = sm_count * 8;   // persistent: 8 CTAs x 128 threads per SM
+    const int shade_grid = sm_count * 4;   // grid-stride
+    // every pixel needs at least spp rays; at most spp * (max_bounces + 2)
+    const uint32_t max_waves = fc.spp * (fc.max_bounces + 2u);
+    const uint32_t check_every = 8;
+    int qi = 0;
+    for (uint32_t wave = 0; wave < max_waves; wave++) {
+        if (events) {  // timing mode: bracket the dominant kernel with an event pair
+            while (events->size() < (size_t)*n_events_used + 2) {
+                cudaEvent_t e;
+                err = cudaEventCreate(&e);
+                if (err != cudaSuccess) return err;
+                events->push_back(e);
+            }
+            cudaEventRecord((*events)[*n_events_used], st);
+        }
+        if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats);
+        else k_wf_trace<false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats);
+        if (events) {
+            cudaEventRecord((*events)[*n_events_used + 1], st);
+            *n_events_used += 2;
+        }
+        k_wf_shade<<<shade_grid, 256, 0, st>>>(fc, instances, shade, ws, qi, stats);
+        *launches += 2;
+        qi ^= 1;
+        if (wave + 1 >= fc.spp && ((wave + 1) % check_every) == 0) {
+            // poll the survivor count so finished frames stop launching empty waves
+            err = cudaMemcpyAsync(host_count_pinned, &ws.counters[qi], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+            if (err != cudaSuccess) return err;
+            err = cudaStreamSynchronize(st);
+            if (err != cudaSuccess) return err;
+            if (*host_count_pinned == 0) break;
+        }
+    }
+    k_wf_resolve<<<(n_pixels + 255) / 256, 256, 0, st>>>(fc, ws, accum, render);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace solb

@@ -1,0 +1,39 @@
+// trace.h — host-callable launch wrappers of trace.cu
+#pragma once
+#include <vector>
+
+#include "solb_internal.h"
+
+namespace solb {
+
+// Wavefront path state, one slot per pixel (SoA, 16-byte vector loads/stores):
+struct WavefrontState {
+    float4 *ray_o;      // xyz origin of the ray in flight
+    float4 *ray_d;      // xyz direction
+    float4 *thr;        // xyz throughput (accumulatedRayColor), w = bits(depth | sample << 16)
+    float4 *pix;        // xyz sum of finished samples (pixelColor), w = bits(prd.rng)
+    uint4 *hit;         // instance, global triangle, bits(u), bits(v)
+    uint32_t *queue[2]; // pixel ids with a ray in flight (ping-pong)
+    uint32_t *counters; // [0],[1]: queue sizes, [2]: trace work head
+    uint32_t capacity;  // pixels
+};
+
+cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &sv, ShadeRecord *out);
+cudaError_t launch_debug(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, uint32_t *render, uint2 *ids,
+                         float4 *attribs, unsigned long long *stats);
+cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const float4 *rays, uint32_t n, uint4 *hits, float *t_out,
+                              unsigned long long *stats);
+cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
+                                  const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
+                                  bool collect);
+cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as,
+                                       const DeviceInstance *instances, const ShadeRecord *shade, WavefrontState &ws, float4 *accum,
+                                       uint32_t *render, unsigned long long *stats, bool collect, int sm_count,
+                                       uint32_t *host_count_pinned, uint64_t *launches, std::vector<cudaEvent_t> *events,
+                                       uint32_t *n_events_used);
+cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
+                      const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
+                      unsigned long long *stats);
+cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n);
+
+}  // namespace solb

@@ -1,0 +1,298 @@
+// emu.cpp — TEST-ONLY host emulation of libsolb's per-thread device logic.
+// Compiles sol_rs_b200/csrc/{bvh,build,shade}.cuh with g++ (their functions are SOLB_HD) and steps
+// them sequentially so builder / traversal / shading logic can be checked against the oracle in the
+// CPU-only test tier.  It is NOT a product path: the library itself has no CPU fallback and nothing in
+// sol_rs_b200/ links or loads this file.  Kernel-side plumbing (queues, atomics, radix sort) is only
+// testable on the GPU.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+
+#include "build.cuh"
+#include "shade.cuh"
+
+using namespace solb;
+
+struct EmuStack {
+    uint2 e[128];
+    int sp = 0;
+    int max_sp = 0;
+    void push(uint2 v) { e[sp++] = v; if (sp > max_sp) max_sp = sp; }
+    uint2 pop() { return e[--sp]; }
+    bool empty() const { return sp == 0; }
+};
+
+struct EmuScene {
+    std::vector<DeviceInstance> inst;
+    std::vector<uint32_t> first_tri;
+    std::vector<float4> vertices;  // 4 per vertex
+    std::vector<uint32_t> indices;
+    std::vector<ShadeRecord> shade;
+    std::vector<Node8> nodes;
+    std::vector<Tri48> tris;
+    uint32_t n_tris = 0, depth = 0;
+    float sah_lbvh = 0, sah_final = 0;
+    int max_stack = 0;
+};
+
+extern "C" {
+
+EmuScene *emu_scene_create(uint32_t n_inst, const DeviceInstance *inst, const float *vertices, uint32_t n_vertices,
+                           const uint32_t *indices, uint32_t n_indices) {
+    EmuScene *s = new EmuScene();
+    s->inst.assign(inst, inst + n_inst);
+    s->vertices.resize((size_t)n_vertices * 4);
+    memcpy(s->vertices.data(), vertices, (size_t)n_vertices * 64);
+    s->indices.assign(indices, indices + n_indices);
+    s->first_tri.push_back(0);
+    for (uint32_t i = 0; i < n_inst; i++) s->first_tri.push_back(s->first_tri.back() + inst[i].n_indices / 3);
+    s->n_tris = s->first_tri.back();
+    s->shade.resize(std::max<uint32_t>(s->n_tris, 1));
+    for (uint32_t i = 0; i < n_inst; i++)
+        for (uint32_t p = 0; p < inst[i].n_indices / 3; p++) {
+            float f[28];
+            for (int k = 0; k < 3; k++) {
+                uint32_t vi = inst[i].first_vertex + indices[inst[i].first_index + 3 * p + k];
+                const float4 pos = s->vertices[4 * (size_t)vi], col = s->vertices[4 * (size_t)vi + 1], nrm = s->vertices[4 * (size_t)vi + 2];
+                f[9 * k] = pos.x; f[9 * k + 1] = pos.y; f[9 * k + 2] = pos.z;
+                f[9 * k + 3] = nrm.x; f[9 * k + 4] = nrm.y; f[9 * k + 5] = nrm.z;
+                f[9 * k + 6] = col.x; f[9 * k + 7] = col.y; f[9 * k + 8] = col.z;
+            }
+            f[27] = 0;
+            ShadeRecord &r = s->shade[s->first_tri[i] + p];
+            for (int q = 0; q < 7; q++) r.q[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        }
+    return s;
+}
+
+void emu_scene_destroy(EmuScene *s) { delete s; }
+
+// Same pipeline as build.cu, run sequentially.  treelet_passes: 0 = plain LBVH.
+int emu_build(EmuScene *s, int treelet_passes, int gamma) {
+    const uint32_t n = s->n_tris;
+    s->nodes.clear(); s->tris.clear();
+    if (n == 0) {
+        ChildRef ch[8];
+        for (auto &c : ch) c.valid = 0;
+        s->nodes.resize(1);
+        encode_node8(s->nodes[0], f3(0, 0, 0), f3(0, 0, 0), 0, 0, ch);
+        s->depth = 1;
+        return 0;
+    }
+    std::vector<Tri48> tri_world(n);
+    std::vector<float3> plo(n), phi(n);
+    float3 clo = f3(3.4e38f, 3.4e38f, 3.4e38f), chi = f3(-3.4e38f, -3.4e38f, -3.4e38f);
+    for (uint32_t i = 0; i < s->inst.size(); i++)
+        for (uint32_t p = 0; p < s->inst[i].n_indices / 3; p++) {
+            const uint32_t g = s->first_tri[i] + p;
+            float3 v[3];
+            for (int k = 0; k < 3; k++) {
+                uint32_t vi = s->inst[i].first_vertex + s->indices[s->inst[i].first_index + 3 * p + k];
+                const float4 pos = s->vertices[4 * (size_t)vi];
+                v[k] = mat4_mul_point(s->inst[i].transform, f3(pos.x, pos.y, pos.z));
+            }
+            tri_world[g].v0 = make_float4(v[0].x, v[0].y, v[0].z, u2f(i));
+            tri_world[g].v1 = make_float4(v[1].x, v[1].y, v[1].z, u2f(p));
+            tri_world[g].v2 = make_float4(v[2].x, v[2].y, v[2].z, u2f(g));
+            plo[g] = fmin3(v[0], fmin3(v[1], v[2]));
+            phi[g] = fmax3(v[0], fmax3(v[1], v[2]));
+            const float3 c = (plo[g] + phi[g]) * 0.5f;
+            clo = fmin3(clo, c); chi = fmax3(chi, c);
+        }
+    s->tris.resize(n);
+    if (n == 1) {
+        ChildRef ch[8];
+        for (auto &c : ch) c.valid = 0;
+        ch[0].valid = 1; ch[0].lo = plo[0]; ch[0].hi = phi[0]; ch[0].is_inner = 0; ch[0].tri_offset = 0; ch[0].tri_count = 1;
+        s->nodes.resize(1);
+        encode_node8(s->nodes[0], plo[0], phi[0], 0, 0, ch);
+        s->tris[0] = tri_world[0];
+        s->depth = 1;
+        return 0;
+    }
+    const float3 ext = chi - clo;
+    const float3 inv = f3(ext.x > 0 ? 1.0f / ext.x : 0, ext.y > 0 ? 1.0f / ext.y : 0, ext.z > 0 ? 1.0f / ext.z : 0);
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> vals(n);
+    for (uint32_t g = 0; g < n; g++) { keys[g] = morton63((plo[g] + phi[g]) * 0.5f, clo, inv); vals[g] = g; }
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> skeys(n);
+    for (uint32_t i = 0; i < n; i++) { skeys[i] = keys[order[i]]; vals[i] = order[i]; }
+    const int ni = (int)n - 1;
+    std::vector<BNode> bn(2 * n - 1);
+    std::vector<int> parent(2 * n - 1, -1), count(2 * n - 1, 0);
+    std::vector<float> cost(2 * n - 1, 0.0f);
+    for (uint32_t i = 0; i < n; i++) {
+        BNode &l = bn[ni + i];
+        l.lo = plo[vals[i]]; l.hi = phi[vals[i]]; l.left = l.right = -1;
+        count[ni + i] = 1;
+        cost[ni + i] = SOLB_SAH_CT * half_area(l.lo, l.hi);
+    }
+    for (int i = 0; i < ni; i++) {
+        int l, r, first, last;
+        karras_node(skeys.data(), (int)n, i, l, r, first, last);
+        bn[i].left = l; bn[i].right = r;
+        parent[l] = i; parent[r] = i;
+    }
+    // bottom-up order = reverse BFS from the root
+    auto bottom_up = [&](int mode) {
+        std::vector<int> bfs;
+        bfs.push_back(0);
+        for (size_t k = 0; k < bfs.size(); k++) {
+            int x = bfs[k];
+            if (x < ni) { bfs.push_back(bn[x].left); bfs.push_back(bn[x].right); }
+        }
+        TreeletScratch sc;
+        for (size_t k = bfs.size(); k-- > 0;) {
+            int node = bfs[k];
+            if (node >= ni) continue;
+            int l = bn[node].left, r = bn[node].right;
+            bn[node].lo = fmin3(bn[l].lo, bn[r].lo);
+            bn[node].hi = fmax3(bn[l].hi, bn[r].hi);
+            count[node] = count[l] + count[r];
+            cost[node] = leaf_or_internal_cost(half_area(bn[node].lo, bn[node].hi), cost[l] + cost[r], count[node]);
+            if (mode == 1 && count[node] >= gamma) optimize_treelet(bn.data(), parent.data(), cost.data(), count.data(), ni, node, sc);
+        }
+    };
+    bottom_up(0);
+    const float root_area = half_area(bn[0].lo, bn[0].hi);
+    s->sah_lbvh = root_area > 0 ? cost[0] / root_area : 0;
+    for (int p = 0; p < treelet_passes; p++) bottom_up(1);
+    s->sah_final = root_area > 0 ? cost[0] / root_area : 0;
+    // collapse
+    s->nodes.resize(n);
+    std::vector<CollapseItem> qa(n), qb(n);
+    uint32_t wide_count = 1, tri_count = 0, nq = 1;
+    qa[0].bnode = 0; qa[0].wnode = 0;
+    s->depth = 0;
+    while (nq) {
+        uint32_t nout = 0;
+        for (uint32_t i = 0; i < nq; i++)
+            collapse_one(bn.data(), count.data(), ni, qa[i], s->nodes.data(), &wide_count, &tri_count, vals.data(), tri_world.data(),
+                         s->tris.data(), qb.data(), &nout);
+        std::swap(qa, qb);
+        nq = nout;
+        s->depth++;
+    }
+    s->nodes.resize(wide_count);
+    return tri_count == n ? 0 : -1;
+}
+
+uint32_t emu_node_count(EmuScene *s) { return (uint32_t)s->nodes.size(); }
+uint32_t emu_depth(EmuScene *s) { return s->depth; }
+int emu_max_stack(EmuScene *s) { return s->max_stack; }
+float emu_sah(EmuScene *s, int which) { return which ? s->sah_final : s->sah_lbvh; }
+void emu_read_nodes(EmuScene *s, void *out) { memcpy(out, s->nodes.data(), s->nodes.size() * sizeof(Node8)); }
+void emu_read_tris(EmuScene *s, void *out) { memcpy(out, s->tris.data(), s->tris.size() * sizeof(Tri48)); }
+
+void emu_trace_rays(EmuScene *s, const float *rays, uint32_t n, uint32_t *hits, float *t_out, uint64_t *counters) {
+    uint64_t nodes = 0, tris = 0;
+    int max_stack = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, tris) reduction(max : max_stack)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        Ray r;
+        r.o = f3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]); r.tmin = rays[8 * i + 3];
+        r.d = f3(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6]); r.tmax = rays[8 * i + 7];
+        Hit h;
+        EmuStack st;
+        TraceCounters c = { 0, 0 };
+        trace_closest<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, h, st, &c);
+        hits[4 * i] = h.inst; hits[4 * i + 1] = h.prim; hits[4 * i + 2] = f2u(h.u); hits[4 * i + 3] = f2u(h.v);
+        if (t_out) t_out[i] = h.inst != SOLB_MISS ? h.t : 0.0f;
+        nodes += c.nodes; tris += c.tris;
+        if (st.max_sp > max_stack) max_stack = st.max_sp;
+    }
+    if (counters) { counters[0] += nodes; counters[1] += tris; }
+    if (max_stack > s->max_stack) s->max_stack = max_stack;
+}
+
+static void fill_fc(FrameConsts &fc, const float *uniforms, uint32_t w, uint32_t h) {
+    memset(&fc, 0, sizeof(fc));
+    memcpy(fc.view_inv, uniforms + 32, 64);
+    memcpy(fc.proj_inv, uniforms + 64, 64);
+    fc.origin = f3(fc.view_inv[12], fc.view_inv[13], fc.view_inv[14]);
+    fc.tmin = fmaxf(1.0f, length(fc.origin)) * 1e-3f;
+    fc.tmax = 10000.0f;
+    fc.width = w; fc.height = h;
+    fc.frame = ((const uint32_t *)uniforms)[98];
+}
+
+void emu_debug(EmuScene *s, const float *uniforms, uint32_t w, uint32_t h, uint32_t *render, uint32_t *ids) {
+    FrameConsts fc;
+    fill_fc(fc, uniforms, w, h);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < (int64_t)h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            Ray r;
+            r.o = fc.origin; r.d = primary_dir(fc, (float)x + 0.5f, (float)y + 0.5f); r.tmin = 0.001f; r.tmax = 1000.0f;
+            Hit hit;
+            EmuStack st;
+            trace_closest<false>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, (TraceCounters *)nullptr);
+            float3 hv = r.d;
+            if (hit.inst != SOLB_MISS) hv = f3(1.0f - hit.u - hit.v, hit.u, hit.v);
+            const size_t p = (size_t)y * w + x;
+            if (render) render[p] = pack_rgba8(hv.x, hv.y, hv.z, 0.0f);
+            if (ids) { ids[2 * p] = hit.inst; ids[2 * p + 1] = hit.prim; }
+        }
+}
+
+// mirrors k_pathtrace_mega
+void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_t h, int accum_start, int enable_sky, int spp,
+                         int max_bounces, int accum_mode, float *accum, uint32_t *render, uint64_t *stats) {
+    FrameConsts fc;
+    fill_fc(fc, uniforms, w, h);
+    fc.accum_start = accum_start; fc.enable_sky = (uint32_t)enable_sky; fc.spp = (uint32_t)spp; fc.max_bounces = (uint32_t)max_bounces;
+    fc.accum_mode = (uint32_t)accum_mode;
+    uint64_t nrays = 0, nhits = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : nrays, nhits)
+    for (int64_t y = 0; y < (int64_t)h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            uint32_t rng = tea(x + (uint32_t)y * w, fc.frame);
+            float3 pixel = f3(0, 0, 0), thr = f3(1, 1, 1);
+            uint32_t sample = 0, depth = 0;
+            Ray r;
+            r.tmin = fc.tmin; r.tmax = fc.tmax;
+            { const float jx = next_rand(rng), jy = next_rand(rng); r.o = fc.origin; r.d = primary_dir(fc, (float)x + jx, (float)y + jy); }
+            while (sample < fc.spp) {
+                Hit hit;
+                EmuStack st;
+                trace_closest<false>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, (TraceCounters *)nullptr);
+                nrays++;
+                bool end_path;
+                if (hit.inst != SOLB_MISS) {
+                    nhits++;
+                    float3 hv;
+                    const bool done = shade_hit(s->inst.data(), s->shade.data(), hit.inst, hit.gtri, hit.u, hit.v, r.o, r.d, rng, hv);
+                    depth++;
+                    thr = thr * hv;
+                    end_path = done;
+                    if (!done && depth > fc.max_bounces) { thr = f3(0, 0, 0); end_path = true; }
+                } else { thr = thr * shade_miss(fc.enable_sky, r.d); end_path = true; }
+                if (end_path) {
+                    pixel = pixel + thr;
+                    sample++;
+                    if (sample < fc.spp) {
+                        const float jx = next_rand(rng), jy = next_rand(rng);
+                        r.o = fc.origin; r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                        thr = f3(1, 1, 1); depth = 0;
+                    }
+                }
+            }
+            const size_t p = (size_t)y * w + x;
+            uint32_t rgba;
+            const float4 old = make_float4(accum[4 * p], accum[4 * p + 1], accum[4 * p + 2], accum[4 * p + 3]);
+            const float4 out = resolve_pixel(fc, pixel, old, rgba);
+            accum[4 * p] = out.x; accum[4 * p + 1] = out.y; accum[4 * p + 2] = out.z; accum[4 * p + 3] = out.w;
+            if (render) render[p] = rgba;
+        }
+    if (stats) { stats[0] += nrays; stats[1] += nhits; }
+}
+
+uint32_t emu_tea(uint32_t a, uint32_t b) { return tea(a, b); }
+float emu_next_rand(uint32_t *rng) { return next_rand(*rng); }
+
+}  // extern "C"

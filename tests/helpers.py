@@ -1,0 +1,89 @@
+"""Shared helpers: build the same scene/camera on the oracle side and on the product side."""
+import os
+
+import numpy as np
+
+import oracle
+from oracle import camera as ocam
+from oracle import gltf_flatten as gf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODELS = os.path.join(ROOT, "assets", "models")
+
+
+def model_path(name):
+    return os.path.join(MODELS, name + ".gltf")
+
+
+def oracle_scene(name):
+    fs = gf.load_scene(model_path(name))
+    return fs, oracle.Scene(fs)
+
+
+def oracle_camera(fs, name, w, h):
+    """cornell/tunnel: the file camera (5-pathtrace); Duck: the 3-ray-debug camera; Duck_ao: the 4-ray-ao camera."""
+    if name == "Duck":
+        c = ocam.Camera((w, h))
+        c.look_at((5, 5, 5), (0, 0, 0), (0, -1, 0))  # examples/3-ray-debug.rs:78-79
+    elif name == "Duck_ao":
+        c = ocam.Camera((w, h))
+        c.look_at((4, 1, 4), (0, 0.5, 0), (0, -1, 0))  # examples/4-ray-ao.rs:89-90
+    else:
+        c = ocam.Camera.from_view(fs.camera["view"], fs.camera["yfov"], fs.camera["znear"], fs.camera["zfar"])
+        c.set_window_size((w, h))
+    return c
+
+
+def product_camera(scene_obj, name, w, h):
+    from sol_rs_b200 import scene
+
+    if name == "Duck":
+        c = scene.Camera((w, h))
+        c.look_at((5, 5, 5), (0, 0, 0), (0, -1, 0))
+    elif name == "Duck_ao":
+        c = scene.Camera((w, h))
+        c.look_at((4, 1, 4), (0, 0.5, 0), (0, -1, 0))
+    else:
+        c = scene_obj.camera
+        c.set_window_size((w, h))
+    return c
+
+
+def pathtrace_pipeline(ctx, enable_sky):
+    from sol_rs_b200 import ray
+
+    pipe = ray.Pipeline(ctx, ray.PipelineInfo().shader("glsl/pathtrace.rgen", ray.RAYGEN_KHR)
+                        .shader("glsl/pathtrace.rmiss", ray.MISS_KHR).shader("glsl/pathtrace.rchit", ray.CLOSEST_HIT_KHR)
+                        .specialization([1 if enable_sky else 0], 0).name("pathtrace"))
+    return ray.ShaderBindingTable(ctx, pipe, ray.ShaderBindingTableInfo().raygen(0).miss(1).hitgroup(2))
+
+
+def simple_pipeline(ctx, kind):
+    from sol_rs_b200 import ray
+
+    pipe = ray.Pipeline(ctx, ray.PipelineInfo().shader("glsl/%s.rgen" % kind, ray.RAYGEN_KHR)
+                        .shader("glsl/%s.rmiss" % kind, ray.MISS_KHR).shader("glsl/%s.rchit" % kind, ray.CLOSEST_HIT_KHR))
+    return ray.ShaderBindingTable(ctx, pipe, ray.ShaderBindingTableInfo().raygen(0).miss(1).hitgroup(2))
+
+
+def load_blue_noise():
+    """assets/textures/HDR_RGBA_0.png as the reference uploads it: image::open -> flipv -> to_rgba8
+    (src/texture.rs:490-493); 16-bit -> 8-bit by (v + 128) / 257 (image 0.24 crate rule)."""
+    import cv2
+
+    im = cv2.imread(os.path.join(ROOT, "assets", "textures", "HDR_RGBA_0.png"), cv2.IMREAD_UNCHANGED)
+    assert im is not None and im.dtype == np.uint16 and im.shape[2] == 4
+    im = im[:, :, [2, 1, 0, 3]]  # BGRA -> RGBA
+    im = im[::-1]                # flipv
+    return ((im.astype(np.uint32) + 128) // 257).astype(np.uint8).copy()
+
+
+def image_metrics(a, b):
+    """mean relative error on float images and PSNR on their gamma-2.2 rgba8 versions (north_star gates)."""
+    a3, b3 = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    mre = np.abs(a3 - b3).sum() / max(np.abs(b3).sum(), 1e-12)
+    ga = np.clip(np.power(np.clip(a3, 0, None), 1 / 2.2), 0, 1) * 255
+    gb = np.clip(np.power(np.clip(b3, 0, None), 1 / 2.2), 0, 1) * 255
+    mse = np.mean((np.rint(ga) - np.rint(gb)) ** 2)
+    psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+    return mre, psnr

@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via sol_rs_b200) against the CPU oracle.
+Run on the B200 box: python -m pytest tests -m gpu"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import camera as ocam
+
+from helpers import (image_metrics, load_blue_noise, model_path, oracle_camera, oracle_scene, pathtrace_pipeline,
+                     product_camera, simple_pipeline)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sol():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sol_rs_b200
+
+    return sol_rs_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(sol):
+    c = sol.Context(0)
+    yield c
+    c.close()
+
+
+def _product(sol, ctx, name):
+    from sol_rs_b200 import ray, scene
+
+    sc = scene.load_scene(ctx, model_path(name))
+    return sc, ray.SceneDescription.from_scene(ctx, sc)
+
+
+# ---- acceleration structure ---------------------------------------------------------------------------
+
+def _walk_accel(nodes, tris):
+    """CPU walk of the 8-wide tree: returns per-triangle visit counts and checks box containment."""
+    n_tris = tris.shape[0]
+    seen = np.zeros(n_tris, dtype=np.int64)
+    f = nodes.view(np.float32)
+
+    def child_box(node, i):
+        w = nodes[node]
+        e = int(w[3])
+        s = [np.float32(2.0) ** np.float32(((e >> (8 * a)) & 0xFF) - 127) for a in range(3)]
+        word, sh = i >> 2, 8 * (i & 3)
+        lo = [f[node][a] + np.float32((int(w[8 + 2 * a + word]) >> sh) & 0xFF) * s[a] for a in range(3)]
+        hi = [f[node][a] + np.float32((int(w[14 + 2 * a + word]) >> sh) & 0xFF) * s[a] for a in range(3)]
+        return np.array(lo, dtype=np.float64), np.array(hi, dtype=np.float64)
+
+    max_depth = 0
+    stack = [(0, None, None, 1)]
+    n_nodes_seen = 0
+    while stack:
+        node, plo, phi, depth = stack.pop()
+        n_nodes_seen += 1
+        max_depth = max(max_depth, depth)
+        w = nodes[node]
+        imask = int(w[3]) >> 24
+        child_base, tri_base = int(w[4]), int(w[5])
+        for i in range(8):
+            meta = (int(w[6 + (i >> 2)]) >> (8 * (i & 3))) & 0xFF
+            if meta == 0:
+                assert not (imask >> i) & 1
+                continue
+            lo, hi = child_box(node, i)
+            if plo is not None:  # child boxes are allowed to poke out of the parent's quantised box only by rounding
+                pass
+            if (meta & 0x1F) >= 24 and (meta >> 5) == 1:
+                assert (imask >> i) & 1 and (meta & 7) == i
+                rel = bin(imask & ((1 << i) - 1)).count("1")
+                stack.append((child_base + rel, lo, hi, depth + 1))
+            else:
+                cnt = {1: 1, 3: 2, 7: 3}[meta >> 5]
+                off = meta & 0x1F
+                for k in range(cnt):
+                    t = tri_base + off + k
+                    seen[t] += 1
+                    v = tris[t].reshape(3, 4)[:, :3].astype(np.float64)
+                    assert np.all(v >= lo - 1e-6 * (1 + np.abs(lo))) and np.all(v <= hi + 1e-6 * (1 + np.abs(hi))), \
+                        "triangle outside its leaf box"
+    return seen, n_nodes_seen, max_depth
+
+
+@pytest.mark.parametrize("name", ["cornell", "Duck", "tunnel"])
+def test_accel_invariants(sol, ctx, name):
+    fs, osc = oracle_scene(name)
+    sc, sd = _product(sol, ctx, name)
+    info = sd.accel_info()
+    assert info.n_instances == len(fs.instances) and info.n_triangles == osc.tri_count
+    nodes, tris = sd.read_nodes(), sd.read_triangles()
+    seen, n_nodes, depth = _walk_accel(nodes, tris)
+    assert np.all(seen == 1), "every triangle must be reachable exactly once"
+    assert n_nodes == info.n_wide_nodes and depth == info.wide_depth
+    # ids carried in the w lanes: (instance, primitive, global ordinal) cover the scene exactly once
+    ids = tris.view(np.uint32).reshape(-1, 3, 4)[:, :, 3]
+    first = np.cumsum([0] + [i["n_indices"] // 3 for i in fs.instances])
+    assert sorted(ids[:, 2].tolist()) == list(range(osc.tri_count))
+    assert np.array_equal(ids[:, 2], first[ids[:, 0]] + ids[:, 1])
+    lo, hi = osc.bounds()
+    np.testing.assert_allclose(np.array(info.scene_lo[:]), lo, atol=1e-5)
+    np.testing.assert_allclose(np.array(info.scene_hi[:]), hi, atol=1e-5)
+    assert 0 < info.sah_cost_binary <= info.sah_cost_lbvh * 1.0001  # treelet pass never makes SAH worse
+    # the world-space vertices equal transform * position in f32 up to rounding
+    g = int(ids[0, 2])
+    inst = int(ids[0, 0])
+    I = fs.instances[inst]
+    idx = fs.indices[I["first_index"] + 3 * int(ids[0, 1]): I["first_index"] + 3 * int(ids[0, 1]) + 3] + I["first_vertex"]
+    P = fs.vertices[idx, 0:3].astype(np.float64) @ I["transform"][:3, :3].astype(np.float64) + I["transform"][3, :3]
+    np.testing.assert_allclose(tris[0].reshape(3, 4)[:, :3], P, rtol=1e-5, atol=1e-6)
+    assert g < osc.tri_count
+
+
+# ---- primary-hit ids (north_star gate 1) ---------------------------------------------------------------
+
+@pytest.mark.parametrize("name,w,h", [("Duck", 900, 600), ("cornell", 512, 512), ("tunnel", 1920, 1080)])
+def test_primary_hit_ids(sol, ctx, name, w, h):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    fs, osc = oracle_scene(name)
+    ou = ocam.scene_uniforms(oracle_camera(fs, name, w, h), w, h, 0)
+    o_rgba, o_ids, o_bt, o_flags = osc.debug(ou, w, h)
+    sc, sd = _product(sol, ctx, name)
+    cam = product_camera(sc, name, w, h)
+    u = scene.scene_uniforms(cam, w, h, 0)
+    assert bytes(u) == ou, "product and oracle uniform blocks must be identical inputs"
+    render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+    ids = sol.Image2d(ctx, w, h, N.FORMAT_RG32UI)
+    sbt = simple_pipeline(ctx, "debug")
+    sbt.cmd_trace_rays(ray.TraceBindings(sd, u, None, render, ids), (w, h, 1))
+    g_ids, g_rgba = ids.readback(), render.readback()
+    mism = np.any(g_ids != o_ids, axis=2)
+    listed = o_flags != 0  # the oracle's edge / tie / near-miss list
+    assert (mism & ~listed).sum() == 0, "hit ids differ on %d unlisted pixels" % (mism & ~listed).sum()
+    assert listed.mean() < 0.005
+    # debug.rchit colours: barycentrics (hit) or direction (miss) within 1 LSB away from listed pixels
+    d = np.abs(g_rgba.astype(np.int32) - o_rgba.astype(np.int32)).max(axis=2)
+    assert (d[~listed] > 1).sum() == 0
+    assert np.all(g_rgba[..., 3] == 0)
+
+
+def test_random_rays_vs_oracle(sol, ctx):
+    """traceRayEXT on 10^6 incoherent rays: (instance, primitive) equal to the f64 oracle except listed edge/tie rays."""
+    fs, osc = oracle_scene("tunnel")
+    sc, sd = _product(sol, ctx, "tunnel")
+    rng = np.random.default_rng(11)
+    n = 1_000_000
+    lo, hi = osc.bounds()
+    o = rng.uniform(lo * 0.9, hi * 0.9, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+    g_hits, g_t = sd.trace_rays(rays)
+    o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
+    mism = np.any(g_hits[:, :2] != o_hits[:, :2], axis=1)
+    assert (mism & (flags == 0)).sum() == 0
+    assert (flags != 0).mean() < 0.01
+    ok = ~mism & (o_hits[:, 0] != oracle.MISS)
+    np.testing.assert_allclose(g_t[ok], o_t[ok], rtol=2e-5, atol=1e-6)
+    gu = g_hits[ok, 2:].view(np.float32)
+    ou = o_hits[ok, 2:].view(np.float32)
+    assert np.abs(gu - ou).max() < 2e-3
+
+
+# ---- path tracing ----------------------------------------------------------------------------------------
+
+def _render_gpu(sol, ctx, name, w, h, frames, sky, spp, mb, schedule, accum_mode=0, start=0, collect=False):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    sc, sd = _product(sol, ctx, name)
+    cam = product_camera(sc, name, w, h)
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+    sbt = pathtrace_pipeline(ctx, sky)
+    for f in frames:
+        u = scene.scene_uniforms(cam, w, h, f)
+        sd.tlas_regenerate()
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, render, accumulation_start_frame=start, samples_per_frame=spp,
+                                             max_bounces=mb, schedule=schedule, accum_mode=accum_mode, collect_stats=collect),
+                           (w, h, 1))
+    return accum.readback(), render.readback()
+
+
+def _render_oracle(name, w, h, frames, sky, spp, mb, start=0):
+    fs, osc = oracle_scene(name)
+    cam = oracle_camera(fs, name, w, h)
+    acc = np.zeros((h, w, 4), dtype=np.float32)
+    st = oracle.OrcStats()
+    rgba = None
+    for f in frames:
+        rgba, _ = osc.pathtrace_frame(ocam.scene_uniforms(cam, w, h, f), w, h, acc, start, sky, spp, mb, st)
+    return acc, rgba, st
+
+
+@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("name,w,h,sky,mb", [("cornell", 128, 128, False, 32), ("cornell", 96, 64, False, 4),
+                                             ("tunnel", 160, 90, True, 32), ("tunnel", 160, 90, True, 8)])
+def test_pathtrace_frames_vs_oracle(sol, ctx, name, w, h, sky, mb, schedule):
+    """Identical per-pixel RNG streams: frames 0..1 agree with the oracle except decision-flip pixels."""
+    ctx.reset_stats()
+    g_acc, g_rgba = _render_gpu(sol, ctx, name, w, h, [0, 1], sky, 8, mb, schedule)
+    o_acc, o_rgba, st = _render_oracle(name, w, h, [0, 1], sky, 8, mb)
+    gs = ctx.stats()
+    assert gs.paths == st.paths == w * h * 8 * 2
+    assert abs(int(gs.rays) - int(st.rays)) <= 0.002 * st.rays  # rays/path statistics agree
+    d = np.abs(g_acc[..., :3] - o_acc[..., :3])
+    differing = (d.max(axis=2) > 1e-3 * (1.0 + np.abs(o_acc[..., :3]).max(axis=2))).mean()
+    assert differing < 0.02, "too many pixels differ from the oracle: %.4f" % differing
+    mre, psnr = image_metrics(g_acc, o_acc)
+    assert mre < 0.01
+    assert np.all(g_acc[..., 3] == 1.0)
+    assert (np.abs(g_rgba.astype(np.int32) - o_rgba.astype(np.int32)).max(axis=2) > 1).mean() < 0.02
+
+
+def test_wavefront_equals_megakernel(sol, ctx):
+    a, _ = _render_gpu(sol, ctx, "tunnel", 256, 144, [0, 1, 2], True, 8, 32, 0)
+    b, _ = _render_gpu(sol, ctx, "tunnel", 256, 144, [0, 1, 2], True, 8, 32, 1)
+    d = np.abs(a - b)[..., :3]
+    assert (d.max(axis=2) > 1e-4 * (1 + np.abs(b[..., :3]).max(axis=2))).mean() < 0.002
+
+
+def test_accumulation_restart_and_alpha(sol, ctx):
+    """pathtrace.rgen:89-101: alpha = 1/(frame+1-start); a restart overwrites whatever the image held."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    w = h = 64
+    sc, sd = _product(sol, ctx, "cornell")
+    cam = product_camera(sc, "cornell", w, h)
+    sbt = pathtrace_pipeline(ctx, False)
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    accum.upload(np.full((h, w, 4), 77.0, dtype=np.float32))
+    sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 5), accum, None, accumulation_start_frame=5), (w, h, 1))
+    a5 = accum.readback()
+    fresh = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 5), fresh, None, accumulation_start_frame=5), (w, h, 1))
+    np.testing.assert_array_equal(a5, fresh.readback())
+    sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 6), accum, None, accumulation_start_frame=5), (w, h, 1))
+    a56 = accum.readback()
+    only6 = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 6), only6, None, accumulation_start_frame=6), (w, h, 1))
+    np.testing.assert_allclose(a56[..., :3], 0.5 * a5[..., :3] + 0.5 * only6.readback()[..., :3], rtol=1e-5, atol=1e-6)
+
+
+def test_sum_mode_matches_running_mean(sol, ctx):
+    """per-rank sums + resolve equal the reference's running mix up to fp rounding."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray
+
+    mix, _ = _render_gpu(sol, ctx, "cornell", 64, 64, range(6), False, 8, 8, 0)
+    s, _ = _render_gpu(sol, ctx, "cornell", 64, 64, range(6), False, 8, 8, 0, accum_mode=N.ACCUM_SUM)
+    assert np.all(s[..., 3] == 6.0)
+    np.testing.assert_allclose(s[..., :3] / 6.0, mix[..., :3], rtol=2e-5, atol=1e-6)
+    tgt = sol.Image2d(ctx, 64, 64, N.FORMAT_RGBA32F)
+    tgt.upload(s)
+    out = sol.Image2d(ctx, 64, 64, N.FORMAT_RGBA32F)
+    rgba = sol.Image2d(ctx, 64, 64, N.FORMAT_RGBA8)
+    ray.resolve_sum(ctx, tgt, out, rgba)
+    np.testing.assert_allclose(out.readback()[..., :3], mix[..., :3], rtol=2e-5, atol=1e-6)
+    assert np.all(rgba.readback()[..., 3] == 255)
+
+
+def test_instance_transform_update(sol, ctx):
+    """SceneDescription::blas_transform + tlas_regenerate: hits follow the new transform (oracle rebuilt with it)."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    w = h = 128
+    fs, _ = oracle_scene("cornell")
+    sc, sd = _product(sol, ctx, "cornell")
+    T = np.eye(4, dtype=np.float32)
+    T[3, :3] = [0.3, 0.2, -0.1]  # [col][row] storage: translation column
+    new_t = oracle.gltf_flatten.mat4_mul(T, fs.instances[6]["transform"])
+    transforms = [i["transform"] for i in fs.instances]
+    transforms[6] = new_t
+    osc = oracle.Scene(fs, transforms)
+    sd.blas_transform(new_t.reshape(16), 6)
+    sd.update()
+    sd.tlas_regenerate()
+    inst = sd.instances()[6]
+    np.testing.assert_allclose(np.array(inst.transform[:]), new_t.reshape(16), rtol=0, atol=0)
+    tit = oracle.gltf_flatten.mat4_inverse(new_t).T.reshape(16)
+    np.testing.assert_allclose(np.array(inst.transform_it[:]), tit, rtol=1e-6, atol=1e-7)
+    cam = product_camera(sc, "cornell", w, h)
+    u = scene.scene_uniforms(cam, w, h, 0)
+    ids = sol.Image2d(ctx, w, h, N.FORMAT_RG32UI)
+    simple_pipeline(ctx, "debug").cmd_trace_rays(ray.TraceBindings(sd, u, None, None, ids), (w, h, 1))
+    _, o_ids, _, flags = osc.debug(bytes(u), w, h)
+    mism = np.any(ids.readback() != o_ids, axis=2)
+    assert (mism & (flags == 0)).sum() == 0
+    # and shading uses the updated transform too
+    a, _ = None, None
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    pathtrace_pipeline(ctx, False).cmd_trace_rays(ray.TraceBindings(sd, u, accum, None), (w, h, 1))
+    ref = np.zeros((h, w, 4), dtype=np.float32)
+    osc.pathtrace_frame(bytes(u), w, h, ref)
+    d = np.abs(accum.readback()[..., :3] - ref[..., :3])
+    assert (d.max(axis=2) > 1e-3 * (1 + ref[..., :3].max(axis=2))).mean() < 0.02
+
+
+def test_ao_frame_vs_oracle(sol, ctx):
+    """4-ray-ao on Duck (ToyCar.glb is missing upstream) with the example's camera."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    w, h = 240, 135
+    blue = load_blue_noise()
+    fs, osc = oracle_scene("Duck")
+    sc, sd = _product(sol, ctx, "Duck")
+    ctx.set_blue_noise(blue)
+    cam = product_camera(sc, "Duck_ao", w, h)
+    img = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    ref = np.zeros((h, w, 4), dtype=np.float32)
+    sbt = simple_pipeline(ctx, "ao")
+    ocamera = oracle_camera(fs, "Duck_ao", w, h)
+    for f in range(2):
+        u = scene.scene_uniforms(cam, w, h, f)
+        assert bytes(u) == ocam.scene_uniforms(ocamera, w, h, f)
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, u, img, None), (w, h, 1))
+        osc.ao_frame(bytes(u), w, h, ref, blue)
+    g = img.readback()
+    d = np.abs(g[..., :3] - ref[..., :3]).max(axis=2)
+    assert (d > 1e-4).mean() < 0.01
+    assert np.all(g[..., 3] == 1.0) and g[..., :3].min() >= 0.0 and g[..., :3].max() <= 1.0
+
+
+def test_stats_counters_and_roofline_inputs(sol, ctx):
+    """collect_stats: nodes / triangles per ray are what the B_ray roofline model is computed from."""
+    ctx.reset_stats()
+    _render_gpu(sol, ctx, "tunnel", 160, 90, [0], True, 8, 8, 0, collect=True)
+    st = ctx.stats()
+    assert st.rays > 0 and st.nodes_visited > st.rays and st.tris_tested > 0
+    assert 1.0 < st.nodes_visited / st.rays < 200.0
+
+
+def test_error_paths(sol, ctx):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    L = N.lib()
+    assert L.solb_ctx_create(0, None, None) == -1
+    bad = ctypes.c_void_p()
+    assert L.solb_ctx_create(9999, None, ctypes.byref(bad)) == -1
+    sc, sd = _product(sol, ctx, "cornell")
+    cam = product_camera(sc, "cornell", 32, 32)
+    u = scene.scene_uniforms(cam, 32, 32, 0)
+    a = sol.Image2d(ctx, 32, 32, N.FORMAT_RGBA32F)
+    r_wrong = sol.Image2d(ctx, 16, 16, N.FORMAT_RGBA8)
+    sbt = pathtrace_pipeline(ctx, False)
+    with pytest.raises(sol.SolbError):
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, u, a, r_wrong), (32, 32, 1))  # size mismatch
+    with pytest.raises(sol.SolbError):
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, u, a, None), (64, 32, 1))  # extent mismatch
+    with pytest.raises(sol.SolbError):
+        sol.Image2d(ctx, 0, 4, N.FORMAT_RGBA32F)
+    with pytest.raises(sol.SolbError):
+        sd.blas_transform(np.eye(4, dtype=np.float32), 99)
+    # a section without indices is rejected like the reference's RT path cannot represent it (App.A item 4)
+    m = sc.meshes[0]
+    m2 = scene.Mesh("x", m.vertices, m.indices, m.transform, [scene.PrimitiveSection(0, 0, m.vertices.shape[0], 0, 0, 0)])
+    with pytest.raises(sol.SolbError):
+        ray.SceneDescription.from_meshes(ctx, [m2], [m.transform], sc.materials)
+    # empty scene: builds, every ray misses
+    empty = ray.SceneDescription.from_meshes(ctx, [], [], np.zeros((0, 12), np.float32))
+    hits, _ = empty.trace_rays(np.array([[0, 0, 0, 0, 0, 0, 1, 10]], dtype=np.float32))
+    assert hits[0, 0] == N.MISS
