@@ -156,7 +156,10 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream, made current: libsolb launches on it, torch events time it, NCCL orders with it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = sol.Context(local_rank, stream.cuda_stream)
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)

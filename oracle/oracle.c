@@ -165,6 +165,7 @@ typedef struct {
     OrcTri *tris;         /* world space, BVH leaf order */
     OrcNode *nodes;
     uint32_t n_nodes;
+    double scale;         /* max |coordinate| of the world-space scene: sizes the interval-end tolerance */
 } OrcScene;
 
 static void bvh_bounds(const OrcTri *t, double lo[3], double hi[3])
@@ -266,6 +267,12 @@ ORC_API OrcScene *orc_scene_create(uint32_t n_inst, const OrcInstance *inst,
     }
     s->nodes = (OrcNode *)malloc(sizeof(OrcNode) * (2 * (size_t)nt + 2));
     s->n_nodes = 0;
+    s->scale = 1.0;
+    for (uint32_t i = 0; i < nt; i++)
+        for (int r = 0; r < 3; r++) {
+            const OrcTri *tr = &s->tris[i];
+            s->scale = fmax(s->scale, fmax(fabs(tr->v0[r]), fmax(fabs(tr->v0[r] + tr->e1[r]), fabs(tr->v0[r] + tr->e2[r]))));
+        }
     if (nt) bvh_build(s, 0, nt);
     return s;
 }
@@ -334,6 +341,7 @@ static void closest_hit(const OrcScene *s, const float org[3], const float dir[3
     /* classification bookkeeping */
     double second_t = DBL_MAX;      /* nearest strict hit on a different triangle */
     double loose_t = DBL_MAX;       /* nearest "almost hit" (bary in [-eps, 0)) */
+    int end_tie = 0;                /* a candidate sits at tmin / tmax within position rounding */
     uint32_t stack[128];
     int sp = 0;
     stack[sp++] = 0;
@@ -368,11 +376,18 @@ static void closest_hit(const OrcScene *s, const float org[3], const float dir[3
             double t = (tr->e2[0] * q[0] + tr->e2[1] * q[1] + tr->e2[2] * q[2]) * inv;
             double w = 1.0 - u - v;
             double mn = fmin(u, fmin(v, w));
-            if (!(t > tmin && t < tmax)) {
-                if (classify && mn >= -eps_b && (fabs(t - tmin) <= eps_t * fabs(tmin) || fabs(t - tmax) <= eps_t * fabs(tmax)))
-                    if (t < loose_t) loose_t = t; /* hit right at an interval end: ambiguous */
-                continue;
+            if (classify && mn >= -eps_b) {
+                /* Interval-end tie: the plane of this triangle passes within an f32-position tolerance of the
+                 * ray's start (o + tmin d) or end point, so whether t > tmin (t < tmax) holds is decided by
+                 * rounding.  |t - tmin| * |d . n^| is that distance. */
+                double nx = tr->e1[1] * tr->e2[2] - tr->e1[2] * tr->e2[1], ny = tr->e1[2] * tr->e2[0] - tr->e1[0] * tr->e2[2],
+                       nz = tr->e1[0] * tr->e2[1] - tr->e1[1] * tr->e2[0];
+                double nl = sqrt(nx * nx + ny * ny + nz * nz);
+                double dn = nl > 0.0 ? fabs(d[0] * nx + d[1] * ny + d[2] * nz) / nl : 0.0;
+                double tol = 2e-6 * s->scale;
+                if (fabs(t - tmin) * dn <= tol || fabs(t - tmax) * dn <= tol) end_tie = 1;
             }
+            if (!(t > tmin && t < tmax)) continue;
             if (mn >= 0.0) {
                 if (t < best_t || (t == best_t && best != ORC_MISS && i < best)) {
                     if (best != ORC_MISS && best_t < second_t) second_t = best_t;
@@ -396,6 +411,7 @@ static void closest_hit(const OrcScene *s, const float org[3], const float dir[3
     } else if (classify && loose_t < DBL_MAX) {
         out->flags |= ORC_FLAG_NEAR;
     }
+    if (classify && end_tie) out->flags |= ORC_FLAG_TIE;
 }
 
 /* Batch closest hit for arbitrary rays: rays[i] = {ox,oy,oz,tmin, dx,dy,dz,tmax}.

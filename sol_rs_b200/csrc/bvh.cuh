@@ -111,9 +111,15 @@ SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, fl
     const float det = U + V + W;
     if (det == 0.0f) return false;  // edge-on triangle
     const float rdet = 1.0f / det;
-    // hit point P - o = (U A + V B + W C) / det; t = (P - o).d / d.d
-    const float T = U * dot(A, d) + V * dot(B, d) + W * dot(C, d);
-    const float t = T * rdet / dot(d, d);
+    // Depth from the plane through the three vertices (n = e1 x e2 from exact-ish edge differences):
+    // t = (p0 - o).n / d.n.  On the long sliver triangles of tunnel.gltf (9.5 x 0.05 units) this is ~5x
+    // more accurate than interpolating vertex depths with the barycentrics, and as accurate as the f32
+    // rounding of the stored world-space vertices allows (~1e-4 there).
+    const float3 e1 = p1 - p0, e2 = p2 - p0;
+    const float3 n = cross(e1, e2);
+    const float den = dot(d, n);
+    if (den == 0.0f) return false;
+    const float t = dot(A, n) / den;
     if (!(t > tmin && t < tmax)) return false;
     t_out = t;
     u_out = V * rdet;
@@ -123,7 +129,16 @@ SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, fl
 
 // ---- node test: returns hit mask (bits 31..24 internal children in traversal priority order,
 //      bits 23..0 triangles of the hit leaf children) -------------------------------------------------
-SOLB_HD float q2f(uint32_t w, int shift) { return (float)((w >> shift) & 0xffu); }
+// byte j of w -> float without the I2F conversion (which runs on the quarter-rate XU pipe and was the
+// top pipe of the first traversal kernel, profiles/r01): PRMT builds the bit pattern of 2^23 + q, one
+// FADD removes the 2^23.  Exact for q in [0, 255].
+SOLB_HD float q2f(uint32_t w, int j) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)j)) - 8388608.0f;
+#else
+    return u2f(0x4B000000u | ((w >> (8 * j)) & 0xffu)) - 8388608.0f;
+#endif
+}
 
 SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4,
                                 float3 o, float3 idir, uint32_t oct_inv4, float tmin, float tmax) {
@@ -151,9 +166,9 @@ SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int s = 8 * j;
-            const float t0x = q2f(nx, s) * ax + bx, t1x = q2f(fx, s) * ax + bx;
-            const float t0y = q2f(ny, s) * ay + by, t1y = q2f(fy, s) * ay + by;
-            const float t0z = q2f(nz, s) * az + bz, t1z = q2f(fz, s) * az + bz;
+            const float t0x = q2f(nx, j) * ax + bx, t1x = q2f(fx, j) * ax + bx;
+            const float t0y = q2f(ny, j) * ay + by, t1y = q2f(fy, j) * ay + by;
+            const float t0z = q2f(nz, j) * az + bz, t1z = q2f(fz, j) * az + bz;
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
             if (cmin <= cmax) {
@@ -177,50 +192,77 @@ SOLB_HD float safe_rcp_dir(float d) {
 #define SOLB_LDG4(p) (*(p))
 #endif
 
-// Closest-hit traversal.  Stack: push(uint2), pop() -> uint2, empty().
+// Per-ray constants of a traversal
+struct TravRay {
+    float3 o, d, idir;
+    uint32_t oct_inv4;
+    RayFrame frame;
+    float tmin;
+};
+
+SOLB_HD TravRay make_trav_ray(float3 o, float3 d, float tmin) {
+    TravRay t;
+    t.o = o; t.d = d; t.tmin = tmin;
+    t.idir = f3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+    t.oct_inv4 = (7u - oct) * 0x01010101u;
+    t.frame = make_ray_frame(d);
+    return t;
+}
+
+#define SOLB_ROOT_GROUP make_uint2(0u, 0x80000000u)  // "child 7^oct_inv of a virtual parent", base 0
+
+// One node step.  Precondition: ngroup carries at least one internal-child hit.  Pops the nearest child,
+// pushes the remaining siblings, intersects the child's 8 boxes and returns its node group in ngroup and
+// its triangle group in tgroup.
+template <class Stack>
+SOLB_HD void trav_node_step(const uint4 *__restrict__ nodes, const TravRay &tr, float tmax, uint2 &ngroup, uint2 &tgroup, Stack &stack) {
+    const uint32_t hits_imask = ngroup.y;
+    const int child_bit = bfind32(hits_imask);
+    const uint32_t child_base = ngroup.x;
+    ngroup.y &= ~(1u << child_bit);
+    if (ngroup.y & 0xff000000u) stack.push(ngroup);
+    const uint32_t slot = (uint32_t)(child_bit - 24) ^ (tr.oct_inv4 & 0xffu);
+    const uint32_t rel = (uint32_t)popc32(hits_imask & ~(0xffffffffu << slot));
+    const uint4 *np = nodes + (size_t)(child_base + rel) * 5;
+    const uint4 q0 = SOLB_LDG4(np + 0), q1 = SOLB_LDG4(np + 1), q2 = SOLB_LDG4(np + 2), q3 = SOLB_LDG4(np + 3), q4 = SOLB_LDG4(np + 4);
+    const uint32_t hm = intersect_node(q0, q1, q2, q3, q4, tr.o, tr.idir, tr.oct_inv4, tr.tmin, tmax);
+    ngroup = make_uint2(q1.x, (hm & 0xff000000u) | (q0.w >> 24));
+    tgroup = make_uint2(q1.y, hm & 0x00ffffffu);
+}
+
+// One triangle step.  Precondition: tgroup.y != 0.  Tests the highest pending triangle of the group.
+SOLB_HD void trav_tri_step(const float4 *__restrict__ tris, const TravRay &tr, float &tmax, uint2 &tgroup, Hit &hit) {
+    const int ti = bfind32(tgroup.y);
+    tgroup.y &= ~(1u << ti);
+    const float4 *tp = tris + (size_t)(tgroup.x + (uint32_t)ti) * 3;
+    const float4 v0 = SOLB_LDG4(tp + 0), v1 = SOLB_LDG4(tp + 1), v2 = SOLB_LDG4(tp + 2);
+    float t, u, v;
+    if (intersect_tri(tr.o, tr.d, tr.frame, xyz(v0), xyz(v1), xyz(v2), tr.tmin, tmax, t, u, v)) {
+        tmax = t;
+        hit.t = t; hit.u = u; hit.v = v;
+        hit.inst = f2u(v0.w); hit.prim = f2u(v1.w); hit.gtri = f2u(v2.w);
+    }
+}
+
+// Closest-hit traversal, one thread per ray (debug / AO / megakernel / host emulation).
+// Stack: push(uint2), pop() -> uint2, empty().
 template <bool STATS, class Stack>
 SOLB_HD void trace_closest(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris, const Ray &ray, Hit &hit,
                            Stack &stack, TraceCounters *ctr) {
     hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS;
     hit.t = ray.tmax; hit.u = 0.0f; hit.v = 0.0f;
-    const float3 o = ray.o, d = ray.d;
-    const float3 idir = f3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
-    const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
-    const RayFrame frame = make_ray_frame(d);
+    const TravRay tr = make_trav_ray(ray.o, ray.d, ray.tmin);
     float tmax = ray.tmax;
-    const float tmin = ray.tmin;
-    uint2 ngroup = make_uint2(0u, 0x80000000u);  // root: "child 7^oct_inv of a virtual parent", base 0
+    uint2 ngroup = SOLB_ROOT_GROUP;
     uint2 tgroup = make_uint2(0u, 0u);
     for (;;) {
-        {   // invariant: ngroup always carries at least one internal-child hit here (only such groups are pushed)
-            const uint32_t hits_imask = ngroup.y;
-            const int child_bit = bfind32(hits_imask);
-            const uint32_t child_base = ngroup.x;
-            ngroup.y &= ~(1u << child_bit);
-            if (ngroup.y & 0xff000000u) stack.push(ngroup);
-            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (oct_inv4 & 0xffu);
-            const uint32_t rel = (uint32_t)popc32(hits_imask & ~(0xffffffffu << slot));
-            const uint4 *np = nodes + (size_t)(child_base + rel) * 5;
-            const uint4 q0 = SOLB_LDG4(np + 0), q1 = SOLB_LDG4(np + 1), q2 = SOLB_LDG4(np + 2), q3 = SOLB_LDG4(np + 3),
-                        q4 = SOLB_LDG4(np + 4);
-            if (STATS) ctr->nodes++;
-            const uint32_t hm = intersect_node(q0, q1, q2, q3, q4, o, idir, oct_inv4, tmin, tmax);
-            ngroup = make_uint2(q1.x, (hm & 0xff000000u) | (q0.w >> 24));
-            tgroup = make_uint2(q1.y, hm & 0x00ffffffu);
-        }
+        // invariant: ngroup always carries at least one internal-child hit here (only such groups are pushed)
+        trav_node_step(nodes, tr, tmax, ngroup, tgroup, stack);
+        if (STATS) ctr->nodes++;
         while (tgroup.y) {
-            const int ti = bfind32(tgroup.y);
-            tgroup.y &= ~(1u << ti);
-            const float4 *tp = tris + (size_t)(tgroup.x + (uint32_t)ti) * 3;
-            const float4 v0 = SOLB_LDG4(tp + 0), v1 = SOLB_LDG4(tp + 1), v2 = SOLB_LDG4(tp + 2);
+            trav_tri_step(tris, tr, tmax, tgroup, hit);
             if (STATS) ctr->tris++;
-            float t, u, v;
-            if (intersect_tri(o, d, frame, xyz(v0), xyz(v1), xyz(v2), tmin, tmax, t, u, v)) {
-                tmax = t;
-                hit.t = t; hit.u = u; hit.v = v;
-                hit.inst = f2u(v0.w); hit.prim = f2u(v1.w); hit.gtri = f2u(v2.w);
-            }
         }
         if (!(ngroup.y & 0xff000000u)) {
             if (stack.empty()) break;

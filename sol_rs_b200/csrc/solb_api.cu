@@ -33,6 +33,7 @@ struct solb_ctx {
     std::vector<cudaEvent_t> ev_pool;  // timing mode: pairs around every dominant-kernel launch
     float trace_kernel_ms_total = 0.0f;
     uint32_t trace_kernel_launches = 0;
+    int refs = 1;  // the ctx handle itself + every live scene / target: resources are freed when the last one goes
 };
 
 struct solb_scene {
@@ -132,8 +133,8 @@ static void free_wavefront(solb_ctx *c) {
     w = WavefrontState{};
 }
 
-SOLB_API int solb_ctx_destroy(solb_ctx *ctx) {
-    if (!ctx) return SOLB_OK;
+static void ctx_release(solb_ctx *ctx) {
+    if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_wavefront(ctx);
@@ -145,6 +146,15 @@ SOLB_API int solb_ctx_destroy(solb_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// Scenes and targets created from the ctx keep it alive (the reference's wrappers hold Arc<Context>:
+// src/buffer.rs:291-303), so destroy order does not matter.
+SOLB_API int solb_ctx_destroy(solb_ctx *ctx) {
+    if (!ctx) return SOLB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx_release(ctx);
     return SOLB_OK;
 }
 
@@ -198,6 +208,7 @@ SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32
     std::vector<uint32_t> indices;
     solb_scene *s = new solb_scene();
     s->ctx = ctx;
+    ctx->refs++;
     struct Guard { solb_scene *s; ~Guard() { if (s) solb_scene_destroy(s); } } guard{ s };
     s->h_first_tri.push_back(0);
     for (uint32_t m = 0; m < n_meshes; m++) {
@@ -272,7 +283,9 @@ SOLB_API int solb_scene_destroy(solb_scene *s) {
     if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
     cudaFree(s->d_vertices); cudaFree(s->d_indices); cudaFree(s->d_first_tri); cudaFree(s->d_inst); cudaFree(s->d_shade);
     s->accel.release();
+    solb_ctx *ctx = s->ctx;
     delete s;
+    if (ctx) ctx_release(ctx);
     return SOLB_OK;
 }
 
@@ -399,6 +412,7 @@ SOLB_API int solb_target_create(solb_ctx *ctx, uint32_t width, uint32_t height, 
     cudaError_t e = cudaMalloc(&t->dev, t->bytes);
     if (e == cudaSuccess) e = cudaMemsetAsync(t->dev, 0, t->bytes, ctx->stream);
     if (e != cudaSuccess) { cudaFree(t->dev); delete t; return fail_cuda(ctx, e, "target alloc"); }
+    ctx->refs++;
     *out = t;
     return SOLB_OK;
     SOLB_CATCH(ctx)
@@ -409,7 +423,9 @@ SOLB_API int solb_target_destroy(solb_target *t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->dev);
+    solb_ctx *ctx = t->ctx;
     delete t;
+    ctx_release(ctx);
     return SOLB_OK;
 }
 

@@ -207,7 +207,8 @@ __device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, uint32_t width, u
     return y * width + x;
 }
 
-__global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, WavefrontState ws, uint32_t n_slots) {
+__global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, WavefrontState ws, uint32_t n_slots,
+                                                     unsigned long long *stats) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     uint32_t p = 0;
@@ -228,7 +229,17 @@ __global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, Wavef
     if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(&ws.counters[0], (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (valid) ws.queue[0][base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = p;
+    warp_add_stat(stats, ST_PATHS, valid ? 1u : 0u);
 }
+
+// Persistent, warp-cooperative traversal.  Every iteration the warp votes between a NODE step (lanes with
+// an internal-child hit intersect one 8-wide node) and a TRIANGLE step (lanes with pending triangle hits
+// test one triangle), so the two phases never serialise inside an iteration; triangle groups a lane cannot
+// serve yet are postponed on its stack (after Ylitie et al. 2017).  Lanes whose ray has terminated are
+// refilled from the queue as soon as WF_FETCH_IDLE lanes are idle (dynamic fetch, Aila & Laine 2009); the
+// warp takes rays from the global queue in batches of WF_BATCH to keep the single atomic counter cold.
+constexpr uint32_t WF_FETCH_IDLE = 8;
+constexpr uint32_t WF_BATCH = 128;
 
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
@@ -236,28 +247,81 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, 
                                                           unsigned long long *stats) {
     SOLB_DECL_STACK();
     const uint32_t n = ws.counters[qi];
-    const uint32_t *__restrict__ queue = ws.queue[qi];
+    const uint32_t *__restrict__ queue = qi ? ws.queue[1] : ws.queue[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters[qi ^ 1] = 0;  // next wave's output queue
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t nr = 0;
     TraceCounters ctr = { 0, 0 };
+    // warp-uniform pool of queue slots [pool_next, pool_end)
+    uint32_t pool_next = 0, pool_end = 0;
+    bool exhausted = false;
+    // per-lane ray state
+    bool has_ray = false;
+    uint32_t pixel = 0;
+    TravRay tr = make_trav_ray(f3(0, 0, 0), f3(0, 0, 1), 0.0f);
+    float tmax = 0.0f;
+    Hit hit;
+    hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f;
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ws.counters[2], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            const uint32_t p = queue[i];
-            const float4 o = ws.ray_o[p], d = ws.ray_d[p];
-            Ray r;
-            r.o = f3(o.x, o.y, o.z); r.d = f3(d.x, d.y, d.z);
-            r.tmin = fc.tmin; r.tmax = fc.tmax;
-            Hit h;
-            stack.sp = 0;
-            trace_closest<STATS>(nodes, tris, r, h, stack, &ctr);
-            ws.hit[p] = make_uint4(h.inst, h.gtri, __float_as_uint(h.u), __float_as_uint(h.v));
-            nr++;
+        // ---- refill idle lanes ----
+        const uint32_t idle = __ballot_sync(0xffffffffu, !has_ray);
+        if (!exhausted && (__popc(idle) >= (int)WF_FETCH_IDLE)) {
+            uint32_t want = (uint32_t)__popc(idle);
+            uint32_t served = 0;  // idle lanes (in rank order) already given a slot
+            while (served < want && !exhausted) {
+                if (pool_next >= pool_end) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&ws.counters[2], WF_BATCH);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= n) { exhausted = true; break; }
+                    pool_next = base;
+                    pool_end = min(base + WF_BATCH, n);
+                }
+                const uint32_t take = min(want - served, pool_end - pool_next);
+                const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
+                if (!has_ray && rank >= served && rank < served + take) {
+                    pixel = queue[pool_next + (rank - served)];
+                    const float4 o = ws.ray_o[pixel], d = ws.ray_d[pixel];
+                    tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
+                    tmax = fc.tmax;
+                    hit.inst = SOLB_MISS; hit.gtri = SOLB_MISS; hit.u = 0.0f; hit.v = 0.0f;
+                    ngroup = SOLB_ROOT_GROUP;
+                    tgroup = make_uint2(0u, 0u);
+                    stack.sp = 0;
+                    has_ray = true;
+                    nr++;
+                }
+                pool_next += take;
+                served += take;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;  // nothing in flight and nothing left to fetch
+        // ---- vote: node step or triangle step ----
+        const bool w_node = has_ray && (ngroup.y & 0xff000000u);
+        const bool w_tri = has_ray && tgroup.y;
+        const int nn = __popc(__ballot_sync(0xffffffffu, w_node));
+        const int nt = __popc(__ballot_sync(0xffffffffu, w_tri));
+        if (nt > 0 && nt >= nn) {
+            if (w_tri) {
+                trav_tri_step(tris, tr, tmax, tgroup, hit);
+                if (STATS) ctr.tris++;
+            }
+        } else if (w_node) {
+            if (tgroup.y) stack.push(tgroup);  // postpone the pending triangles
+            trav_node_step(nodes, tr, tmax, ngroup, tgroup, stack);
+            if (STATS) ctr.nodes++;
+        }
+        // ---- lanes with nothing in hand: pop, or finish the ray ----
+        if (has_ray && !(ngroup.y & 0xff000000u) && !tgroup.y) {
+            if (stack.empty()) {
+                ws.hit[pixel] = make_uint4(hit.inst, hit.gtri, __float_as_uint(hit.u), __float_as_uint(hit.v));
+                has_ray = false;
+            } else {
+                const uint2 e = stack.pop();
+                if (e.y & 0xff000000u) ngroup = e; else tgroup = e;
+            }
         }
     }
     warp_add_stat(stats, ST_RAYS, nr);
@@ -495,7 +559,7 @@ cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, c
     const uint32_t n_slots = (uint32_t)((((uint64_t)((fc.width + 7u) >> 3) * ((fc.height + 3u) >> 2))) * 32u);
     cudaError_t err = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(uint32_t), st);
     if (err != cudaSuccess) return err;
-    k_wf_generate<<<(n_slots + 255) / 256, 256, 0, st>>>(fc, ws, n_slots);
+    k_wf_generate<<<(n_slots + 255) / 256, 256, 0, st>>>(fc, ws, n_slots, stats);
     *launches += 1;
     const int trace_grid = sm_count * 8;   // persistent: 8 CTAs x 128 threads per SM
     const int shade_grid = sm_count * 4;   // grid-stride
