@@ -143,7 +143,7 @@ def main():
 
     import sol_rs_b200 as sol
     from sol_rs_b200 import _native as N
-    from sol_rs_b200 import ray, scene
+    from sol_rs_b200 import multigpu, ray, scene
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,7 +181,7 @@ def main():
         """K steps with inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between steps."""
         accum = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA32F)
         render = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA8)
-        frames = [frame0 + rank + world * i for i in range(n_warm + n_steps)]  # frames f = r (mod R): SURVEY 8e
+        frames = multigpu.frames_for_rank(rank, world, world * (n_warm + n_steps), first=frame0)  # f = r (mod R): SURVEY 8e
         for f in frames[:n_warm]:
             sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), accum, render, schedule=schedule,
                                                  samples_per_frame=SPP, max_bounces=MAX_BOUNCES, accum_mode=mode), (WIDTH, HEIGHT, 1))
@@ -205,8 +205,7 @@ def main():
         if dist:
             # the one real exchange of the path: sum the per-rank accumulation buffers over NVLink, resolve on rank 0
             evs[n_steps][0].record(stream)
-            t = accum.as_torch()
-            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+            multigpu.reduce_accum(accum.as_torch(), dst=0)
             if rank == 0:
                 ray.resolve_sum(ctx, accum, accum, render)
             evs[n_steps][1].record(stream)

@@ -1,0 +1,66 @@
+//! Raw bindings to libsolb.so (include/solb.h).  Source only: this image has no rustc/cargo, so the shim
+//! is not compiled here; it is the reference-side binding a sol-rs maintainer would add.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] pub struct solb_ctx { _private: [u8; 0] }
+#[repr(C)] pub struct solb_scene { _private: [u8; 0] }
+#[repr(C)] pub struct solb_target { _private: [u8; 0] }
+
+/// identical bytes to sol::scene::ModelVertex (src/scene/mesh.rs:9-14)
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct SolbModelVertex { pub pos: [f32; 4], pub color: [f32; 4], pub normal: [f32; 4], pub uv: [f32; 4] }
+/// identical bytes to sol::scene::MaterialInfo (src/scene/mod.rs:19-29)
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct SolbMaterialInfo { pub base_color: [f32; 4], pub emissive: [f32; 3], pub padding0: f32,
+                              pub metallic: f32, pub roughness: f32, pub padding1: f32, pub padding2: f32 }
+/// identical bytes to sol::ray::SceneInstance (src/ray/mod.rs:16-24)
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct SolbSceneInstance { pub id: u32, pub texture_offset: u32, pub padding: [f32; 2],
+                               pub transform: [f32; 16], pub transform_it: [f32; 16] }
+/// identical bytes to SceneUniforms (examples/5-pathtrace.rs:7-17), padded to 400
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct SolbSceneUniforms { pub model: [f32; 16], pub view: [f32; 16], pub view_inverse: [f32; 16],
+                               pub projection: [f32; 16], pub projection_inverse: [f32; 16],
+                               pub model_view_projection: [f32; 16], pub frame: [u32; 3], pub _pad: u32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct SolbSection { pub first_vertex: u32, pub n_vertices: u32, pub first_index: u32, pub n_indices: u32, pub material_index: u32 }
+#[repr(C)]
+pub struct SolbMeshDesc { pub vertices: *const SolbModelVertex, pub n_vertices: u32, pub indices: *const u32, pub n_indices: u32,
+                          pub sections: *const SolbSection, pub n_sections: u32, pub transform: [f32; 16] }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct SolbTraceParams { pub accum_start_frame: i32, pub enable_sky: u32, pub samples_per_frame: u32, pub max_bounces: u32,
+                             pub schedule: u32, pub accum_mode: u32, pub collect_stats: u32, pub _pad: u32 }
+
+pub const SOLB_FORMAT_RGBA32F: u32 = 0;
+pub const SOLB_FORMAT_RGBA8: u32 = 1;
+pub const SOLB_FORMAT_RG32UI: u32 = 2;
+
+#[link(name = "solb")]
+extern "C" {
+    pub fn solb_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut solb_ctx) -> c_int;
+    pub fn solb_ctx_destroy(ctx: *mut solb_ctx) -> c_int;
+    pub fn solb_synchronize(ctx: *mut solb_ctx) -> c_int;
+    pub fn solb_last_error(ctx: *mut solb_ctx) -> *const c_char;
+    pub fn solb_scene_create(ctx: *mut solb_ctx, meshes: *const SolbMeshDesc, n_meshes: u32,
+                             materials: *const SolbMaterialInfo, n_materials: u32, out: *mut *mut solb_scene) -> c_int;
+    pub fn solb_scene_destroy(scene: *mut solb_scene) -> c_int;
+    pub fn solb_accel_build(scene: *mut solb_scene) -> c_int;
+    pub fn solb_instance_set_transform(scene: *mut solb_scene, index: u32, transform: *const f32) -> c_int;
+    pub fn solb_scene_update(scene: *mut solb_scene) -> c_int;
+    pub fn solb_tlas_regenerate(scene: *mut solb_scene) -> c_int;
+    pub fn solb_scene_instance_count(scene: *mut solb_scene, out: *mut u32) -> c_int;
+    pub fn solb_scene_get_instances(scene: *mut solb_scene, out: *mut SolbSceneInstance, capacity: u32) -> c_int;
+    pub fn solb_target_create(ctx: *mut solb_ctx, width: u32, height: u32, format: u32, out: *mut *mut solb_target) -> c_int;
+    pub fn solb_target_destroy(t: *mut solb_target) -> c_int;
+    pub fn solb_target_clear(t: *mut solb_target) -> c_int;
+    pub fn solb_target_readback(t: *mut solb_target, host: *mut c_void, bytes: usize) -> c_int;
+    pub fn solb_trace_params_default(p: *mut SolbTraceParams, pipeline: c_int);
+    pub fn solb_trace_pathtrace(scene: *mut solb_scene, uniforms: *const SolbSceneUniforms, params: *const SolbTraceParams,
+                                accum: *mut solb_target, render: *mut solb_target) -> c_int;
+    pub fn solb_set_blue_noise(ctx: *mut solb_ctx, rgba8: *const u8, width: u32, height: u32) -> c_int;
+    pub fn solb_trace_ao(scene: *mut solb_scene, uniforms: *const SolbSceneUniforms, params: *const SolbTraceParams,
+                         image: *mut solb_target) -> c_int;
+    pub fn solb_trace_debug(scene: *mut solb_scene, uniforms: *const SolbSceneUniforms, render: *mut solb_target,
+                            ids: *mut solb_target, attribs: *mut solb_target) -> c_int;
+}

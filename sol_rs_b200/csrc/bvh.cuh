@@ -129,14 +129,16 @@ SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, fl
 
 // ---- node test: returns hit mask (bits 31..24 internal children in traversal priority order,
 //      bits 23..0 triangles of the hit leaf children) -------------------------------------------------
-// byte j of w -> float without the I2F conversion (which runs on the quarter-rate XU pipe and was the
-// top pipe of the first traversal kernel, profiles/r01): PRMT builds the bit pattern of 2^23 + q, one
-// FADD removes the 2^23.  Exact for q in [0, 255].
-SOLB_HD float q2f(uint32_t w, int j) {
+// Dequantisation without I2F (quarter-rate XU pipe; it was the top pipe of the first traversal kernel,
+// profiles/r01_ncu_k_wf_trace_a.txt) and without a separate subtraction: one PRMT drops byte j of w into
+// mantissa bits [15:8] of the float 32768.0, giving m = 32768 + q exactly; the 32768 is folded into the
+// per-node offset, t = m * a + (b - 32768 a).  Folding costs at most |a| / 512 of rounding (a = one
+// quantisation cell in units of t), which the near / far offsets below absorb conservatively.
+SOLB_HD float q2m(uint32_t w, int j) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + (uint32_t)j)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7604u + ((uint32_t)j << 4)));
 #else
-    return u2f(0x4B000000u | ((w >> (8 * j)) & 0xffu)) - 8388608.0f;
+    return u2f(0x47000000u | (((w >> (8 * j)) & 0xffu) << 8));
 #endif
 }
 
@@ -149,6 +151,11 @@ SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, 
     const float bx = (u2f(q0.x) - o.x) * idir.x;
     const float by = (u2f(q0.y) - o.y) * idir.y;
     const float bz = (u2f(q0.z) - o.z) * idir.z;
+    // offsets with the 32768 bias removed; near planes pulled in, far planes pushed out by |a| / 256
+    const float cx = fmaf(-32768.0f, ax, bx), cy = fmaf(-32768.0f, ay, by), cz = fmaf(-32768.0f, az, bz);
+    const float px = fabsf(ax) * 0.00390625f, py = fabsf(ay) * 0.00390625f, pz = fabsf(az) * 0.00390625f;
+    const float nbx = cx - px, nby = cy - py, nbz = cz - pz;
+    const float fbx = cx + px, fby = cy + py, fbz = cz + pz;
     uint32_t hitmask = 0;
 #pragma unroll
     for (int g = 0; g < 2; g++) {
@@ -166,9 +173,9 @@ SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int s = 8 * j;
-            const float t0x = q2f(nx, j) * ax + bx, t1x = q2f(fx, j) * ax + bx;
-            const float t0y = q2f(ny, j) * ay + by, t1y = q2f(fy, j) * ay + by;
-            const float t0z = q2f(nz, j) * az + bz, t1z = q2f(fz, j) * az + bz;
+            const float t0x = fmaf(q2m(nx, j), ax, nbx), t1x = fmaf(q2m(fx, j), ax, fbx);
+            const float t0y = fmaf(q2m(ny, j), ay, nby), t1y = fmaf(q2m(fy, j), ay, fby);
+            const float t0z = fmaf(q2m(nz, j), az, nbz), t1z = fmaf(q2m(fz, j), az, fbz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
             if (cmin <= cmax) {

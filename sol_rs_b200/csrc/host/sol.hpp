@@ -22,6 +22,7 @@
 
 #include "../../../include/solb.h"
 
+#pragma GCC visibility push(default)  // the C++ mirror is libsol_host.so's public API
 namespace sol {
 
 struct Error : std::runtime_error {
@@ -248,3 +249,4 @@ std::optional<std::string> find_asset(const std::string &relative, const std::st
 }
 
 }  // namespace sol
+#pragma GCC visibility pop

@@ -3,6 +3,8 @@
 // returns a SolbStatus.  There is no CPU path: without a usable CUDA device solb_ctx_create fails.
 #include "../../include/solb.h"
 
+#include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -33,6 +35,7 @@ struct solb_ctx {
     std::vector<cudaEvent_t> ev_pool;  // timing mode: pairs around every dominant-kernel launch
     float trace_kernel_ms_total = 0.0f;
     uint32_t trace_kernel_launches = 0;
+    TraceTuning tune;
     int refs = 1;  // the ctx handle itself + every live scene / target: resources are freed when the last one goes
 };
 
@@ -115,6 +118,19 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+        auto env_int = [](const char *name, int dflt, int lo, int hi) {
+            const char *v = getenv(name);
+            if (!v || !*v) return dflt;
+            const int x = atoi(v);
+            return x < lo ? lo : (x > hi ? hi : x);
+        };
+        c->tune.fetch_idle = env_int("SOLB_FETCH_IDLE", c->tune.fetch_idle, 1, 32);
+        c->tune.tri_weight = env_int("SOLB_TRI_WEIGHT", c->tune.tri_weight, 1, 64);
+        c->tune.node_weight = env_int("SOLB_NODE_WEIGHT", c->tune.node_weight, 1, 64);
+        c->tune.ctas_per_sm = env_int("SOLB_CTAS_PER_SM", c->tune.ctas_per_sm, 1, 16);
+        c->tune.check_every = env_int("SOLB_CHECK_EVERY", c->tune.check_every, 1, 1024);
+    }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->pinned_count, 64);
@@ -293,6 +309,8 @@ static int do_build(solb_scene *s) {
     solb_ctx *ctx = s->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     BuildOptions opt;
+    if (const char *v = getenv("SOLB_TREELET_PASSES")) opt.treelet_passes = std::max(0, std::min(8, atoi(v)));
+    if (const char *v = getenv("SOLB_TREELET_GAMMA")) opt.treelet_gamma = std::max(3, std::min(1 << 20, atoi(v)));
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = build_accel(ctx->stream, s->view(), s->accel, opt, &ctx->launches);
     if (e == cudaErrorLaunchOutOfResources) return fail(ctx, SOLB_ERR_OVERFLOW, "acceleration structure deeper than the traversal stack");
@@ -572,7 +590,7 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
         CU(ctx, launch_pathtrace_wavefront(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->ws, (float4 *)accum->dev,
                                            render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0,
                                            ctx->sm_count, ctx->pinned_count, &ctx->launches, ctx->timing ? &ctx->ev_pool : nullptr,
-                                           &n_ev));
+                                           &n_ev, ctx->tune));
     }
     timer.stop();  // synchronises in timing mode
     for (uint32_t i = 0; ctx->timing && i + 1 < n_ev; i += 2) {

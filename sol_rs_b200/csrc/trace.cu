@@ -238,13 +238,12 @@ __global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, Wavef
 // serve yet are postponed on its stack (after Ylitie et al. 2017).  Lanes whose ray has terminated are
 // refilled from the queue as soon as WF_FETCH_IDLE lanes are idle (dynamic fetch, Aila & Laine 2009); the
 // warp takes rays from the global queue in batches of WF_BATCH to keep the single atomic counter cold.
-constexpr uint32_t WF_FETCH_IDLE = 8;
 constexpr uint32_t WF_BATCH = 128;
 
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                           const float4 *__restrict__ tris, WavefrontState ws, int qi,
-                                                          unsigned long long *stats) {
+                                                          unsigned long long *stats, const TraceTuning tune) {
     SOLB_DECL_STACK();
     const uint32_t n = ws.counters[qi];
     const uint32_t *__restrict__ queue = qi ? ws.queue[1] : ws.queue[0];
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, 
     for (;;) {
         // ---- refill idle lanes ----
         const uint32_t idle = __ballot_sync(0xffffffffu, !has_ray);
-        if (!exhausted && (__popc(idle) >= (int)WF_FETCH_IDLE)) {
+        if (!exhausted && (__popc(idle) >= tune.fetch_idle)) {
             uint32_t want = (uint32_t)__popc(idle);
             uint32_t served = 0;  // idle lanes (in rank order) already given a slot
             while (served < want && !exhausted) {
@@ -303,7 +302,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, 
         const bool w_tri = has_ray && tgroup.y;
         const int nn = __popc(__ballot_sync(0xffffffffu, w_node));
         const int nt = __popc(__ballot_sync(0xffffffffu, w_tri));
-        if (nt > 0 && nt >= nn) {
+        if (nt > 0 && nt * tune.tri_weight >= nn * tune.node_weight) {
             if (w_tri) {
                 trav_tri_step(tris, tr, tmax, tgroup, hit);
                 if (STATS) ctr.tris++;
@@ -553,7 +552,7 @@ cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, c
                                        const DeviceInstance *instances, const ShadeRecord *shade, WavefrontState &ws, float4 *accum,
                                        uint32_t *render, unsigned long long *stats, bool collect, int sm_count,
                                        uint32_t *host_count_pinned, uint64_t *launches, std::vector<cudaEvent_t> *events,
-                                       uint32_t *n_events_used) {
+                                       uint32_t *n_events_used, const TraceTuning &tune) {
     const uint32_t n_pixels = fc.width * fc.height;
     if (n_pixels == 0) return cudaSuccess;
     const uint32_t n_slots = (uint32_t)((((uint64_t)((fc.width + 7u) >> 3) * ((fc.height + 3u) >> 2))) * 32u);
@@ -561,11 +560,11 @@ cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, c
     if (err != cudaSuccess) return err;
     k_wf_generate<<<(n_slots + 255) / 256, 256, 0, st>>>(fc, ws, n_slots, stats);
     *launches += 1;
-    const int trace_grid = sm_count * 8;   // persistent: 8 CTAs x 128 threads per SM
+    const int trace_grid = sm_count * tune.ctas_per_sm;  // persistent CTAs of 128 threads
     const int shade_grid = sm_count * 4;   // grid-stride
     // every pixel needs at least spp rays; at most spp * (max_bounces + 2)
     const uint32_t max_waves = fc.spp * (fc.max_bounces + 2u);
-    const uint32_t check_every = 8;
+    const uint32_t check_every = (uint32_t)tune.check_every;
     int qi = 0;
     for (uint32_t wave = 0; wave < max_waves; wave++) {
         if (events) {  // timing mode: bracket the dominant kernel with an event pair
@@ -577,8 +576,8 @@ cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, c
             }
             cudaEventRecord((*events)[*n_events_used], st);
         }
-        if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats);
-        else k_wf_trace<false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats);
+        if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats, tune);
+        else k_wf_trace<false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats, tune);
         if (events) {
             cudaEventRecord((*events)[*n_events_used + 1], st);
             *n_events_used += 2;

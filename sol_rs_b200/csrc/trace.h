@@ -18,6 +18,16 @@ struct WavefrontState {
     uint32_t capacity;  // pixels
 };
 
+// scheduling knobs of the wavefront trace kernel (defaults chosen by measurement, profiles/; overridable through
+// SOLB_FETCH_IDLE / SOLB_TRI_WEIGHT / SOLB_NODE_WEIGHT / SOLB_CTAS_PER_SM / SOLB_CHECK_EVERY for experiments)
+struct TraceTuning {
+    int fetch_idle = 8;    // refill terminated lanes once this many are idle
+    int tri_weight = 1;    // triangle step wins the vote when n_tri * tri_weight >= n_node * node_weight
+    int node_weight = 1;
+    int ctas_per_sm = 8;   // persistent grid = SMs x this
+    int check_every = 8;   // host polls the survivor count every this many waves
+};
+
 cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &sv, ShadeRecord *out);
 cudaError_t launch_debug(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, uint32_t *render, uint2 *ids,
                          float4 *attribs, unsigned long long *stats);
@@ -30,7 +40,7 @@ cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, c
                                        const DeviceInstance *instances, const ShadeRecord *shade, WavefrontState &ws, float4 *accum,
                                        uint32_t *render, unsigned long long *stats, bool collect, int sm_count,
                                        uint32_t *host_count_pinned, uint64_t *launches, std::vector<cudaEvent_t> *events,
-                                       uint32_t *n_events_used);
+                                       uint32_t *n_events_used, const TraceTuning &tune);
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
                       unsigned long long *stats);

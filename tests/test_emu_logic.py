@@ -1,0 +1,79 @@
+"""CPU tier: the library's per-thread device logic (builder, 8-wide traversal, watertight test, shading),
+compiled for the host by tests/emu and stepped sequentially, against the oracle.  The same checks run on the
+real kernels in test_gpu_parity.py; this tier catches logic errors without GPU time."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import camera as ocam
+
+import emu_lib
+from helpers import oracle_camera, oracle_scene
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell", 192, 192), ("tunnel", 320, 180), ("Duck", 300, 200)])
+@pytest.mark.parametrize("passes", [0, 2])
+def test_emu_primary_hits(name, w, h, passes):
+    fs, osc = oracle_scene(name)
+    es = emu_lib.EmuScene(fs, passes)
+    u = ocam.scene_uniforms(oracle_camera(fs, name, w, h), w, h, 0)
+    _, ids, _, flags = osc.debug(u, w, h)
+    _, eids = es.debug(u, w, h)
+    mism = np.any(ids != eids, axis=2)
+    assert (mism & (flags == 0)).sum() == 0
+    info = es.info()
+    assert info["sah"] <= info["sah_lbvh"] * 1.0001 and info["depth"] <= 62
+
+
+def test_emu_treelet_pass_improves_sah():
+    fs, _ = oracle_scene("tunnel")
+    a, b = emu_lib.EmuScene(fs, 0).info(), emu_lib.EmuScene(fs, 2).info()
+    assert b["sah"] < 0.8 * a["sah"]
+
+
+def test_emu_random_rays_and_stack_depth():
+    fs, osc = oracle_scene("Duck")
+    es = emu_lib.EmuScene(fs, 2)
+    rng = np.random.default_rng(5)
+    n = 100_000
+    lo, hi = osc.bounds()
+    c, r = (lo + hi) / 2, np.linalg.norm(hi - lo)
+    o = c + rng.normal(size=(n, 3)) * r
+    d = (c + rng.normal(size=(n, 3)) * 0.2 * r) - o
+    rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+    hits, t, ctr = es.trace_rays(rays)
+    o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
+    mism = np.any(hits[:, :2] != o_hits[:, :2], axis=1)
+    assert (mism & (flags == 0)).sum() == 0
+    assert (o_hits[:, 0] != oracle.MISS).mean() > 0.05
+    assert es.info()["max_stack"] <= es.info()["depth"]
+
+
+@pytest.mark.parametrize("name,w,h,sky,mb", [("cornell", 64, 64, False, 32), ("tunnel", 96, 54, True, 8)])
+def test_emu_pathtrace_frame(name, w, h, sky, mb):
+    fs, osc = oracle_scene(name)
+    es = emu_lib.EmuScene(fs, 2)
+    cam = oracle_camera(fs, name, w, h)
+    a = np.zeros((h, w, 4), np.float32)
+    b = np.zeros((h, w, 4), np.float32)
+    st = oracle.OrcStats()
+    for f in range(2):
+        u = ocam.scene_uniforms(cam, w, h, f)
+        osc.pathtrace_frame(u, w, h, a, 0, sky, 8, mb, st)
+        es.pathtrace_frame(u, w, h, b, 0, sky, 8, mb)
+    d = np.abs(a - b)[..., :3]
+    assert (d.max(axis=2) > 1e-3 * (1 + a[..., :3].max(axis=2))).mean() < 0.02
+    assert d.sum() / a[..., :3].sum() < 0.01
+
+
+def test_emu_rng_bit_exact():
+    L = emu_lib.lib()
+    import ctypes
+    rng = np.random.default_rng(0)
+    for a, b in rng.integers(0, 2 ** 32, size=(500, 2)):
+        assert L.emu_tea(int(a), int(b)) == oracle.tea(int(a), int(b))
+    for seed in rng.integers(0, 2 ** 32, size=50):
+        s = ctypes.c_uint32(int(seed))
+        ref = oracle.rand_stream(int(seed), 8)
+        for w, f in ref:
+            assert L.emu_next_rand(ctypes.byref(s)) == f

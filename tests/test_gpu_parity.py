@@ -380,3 +380,90 @@ def test_error_paths(sol, ctx):
     empty = ray.SceneDescription.from_meshes(ctx, [], [], np.zeros((0, 12), np.float32))
     hits, _ = empty.trace_rays(np.array([[0, 0, 0, 0, 0, 0, 1, 10]], dtype=np.float32))
     assert hits[0, 0] == N.MISS
+
+
+# ---- north_star gate 2: converged images vs the committed 4096-spp golden fixtures ---------------------
+
+import os as _os
+
+GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name,w,h,sky,mb", [("tunnel", 160, 90, True, 8), ("cornell", 96, 96, False, 32)])
+@pytest.mark.parametrize("schedule", [0, 1])
+def test_converged_image_vs_golden(sol, ctx, name, w, h, sky, mb, schedule):
+    """512 frames x 8 spp = 4096 spp: mean relative error < 1 % and PSNR > 40 dB (BASELINE.json north_star)."""
+    g = np.load(_os.path.join(GOLDEN, "converged_%s_%dx%d_4096spp_b%d.npz" % (name, w, h, mb)))
+    ctx.reset_stats()
+    acc, rgba = _render_gpu(sol, ctx, name, w, h, range(512), sky, 8, mb, schedule)
+    st = ctx.stats()
+    mre, psnr = image_metrics(acc, g["accum"])
+    assert mre < 0.01, "mean relative error %.4f" % mre
+    assert psnr > 40.0, "PSNR %.1f dB" % psnr
+    # the display image too (gamma 2.2 rgba8 as stored by the oracle)
+    d = rgba[..., :3].astype(np.float64) - g["rgba8"][..., :3].astype(np.float64)
+    assert 10 * np.log10(255.0 ** 2 / max(np.mean(d ** 2), 1e-12)) > 40.0
+    # structural statistics: rays per path equal to the oracle's within 0.1 %
+    assert st.paths == int(g["paths"])
+    assert abs(st.rays / st.paths - int(g["rays"]) / int(g["paths"])) < 1e-3 * int(g["rays"]) / int(g["paths"])
+
+
+@pytest.mark.parametrize("name,cam_name,w,h", [("cornell", "cornell", 256, 256), ("Duck", "Duck", 450, 300), ("tunnel", "tunnel", 480, 270)])
+def test_primary_hit_ids_vs_golden(sol, ctx, name, cam_name, w, h):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    g = np.load(_os.path.join(GOLDEN, "hitids_%s_%dx%d.npz" % (name, w, h)))
+    sc, sd = _product(sol, ctx, name)
+    cam = product_camera(sc, cam_name, w, h)
+    ids = sol.Image2d(ctx, w, h, N.FORMAT_RG32UI)
+    simple_pipeline(ctx, "debug").cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 0), None, None, ids), (w, h, 1))
+    got = ids.readback()
+    inst = np.where(got[..., 0] == N.MISS, 255, got[..., 0]).astype(np.uint8)
+    prim = np.where(got[..., 1] == N.MISS, 65535, got[..., 1]).astype(np.uint16)
+    mism = (inst != g["inst"]) | (prim != g["prim"])
+    assert (mism & (g["flags"] == 0)).sum() == 0
+
+
+def test_ao_vs_golden(sol, ctx):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    g = np.load(_os.path.join(GOLDEN, "ao_duck_160x90_f0-3.npz"))
+    sc, sd = _product(sol, ctx, "Duck")
+    ctx.set_blue_noise(load_blue_noise())
+    cam = product_camera(sc, "Duck_ao", 160, 90)
+    img = sol.Image2d(ctx, 160, 90, N.FORMAT_RGBA32F)
+    sbt = simple_pipeline(ctx, "ao")
+    ctx.reset_stats()
+    for f in range(4):
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, 160, 90, f), img, None), (160, 90, 1))
+    d = np.abs(img.readback()[..., :3] - g["image"]).max(axis=2)
+    assert (d > 1e-4).mean() < 0.01
+    st = ctx.stats()
+    assert st.paths == int(g["paths"]) and abs(int(st.rays) - int(g["rays"])) <= 0.002 * int(g["rays"])
+
+
+def test_cpp_host_example_runs_the_reference_call_sequence(sol, ctx):
+    """examples/pathtrace_offscreen.cpp = examples/5-pathtrace.rs through the C++ mirror (sol::ray::*): its final
+    frame must be byte-identical to the same frames rendered through the Python wrapper (same C ABI below)."""
+    import json
+    import subprocess
+
+    from helpers import ROOT
+
+    exe = _os.path.join(ROOT, "examples", "pathtrace_offscreen")
+    assert _os.path.exists(exe), "run __graft_entry__.build()"
+    out = subprocess.run([exe, "--model", "models/cornell.gltf", "--frames", "3", "--size", "160x120"], capture_output=True,
+                         text=True, cwd=ROOT, timeout=120)
+    assert out.returncode == 0, out.stderr
+    info = json.loads(out.stdout.strip().splitlines()[-1])
+    _, rgba = _render_gpu(sol, ctx, "cornell", 160, 120, range(3), False, 8, 32, 0)
+    h = 1469598103934665603
+    for b in rgba.tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    assert info["fnv1a"] == "%016x" % h
+    assert info["rays"] > 0
+    # error behaviour: the reference panics without --model
+    bad = subprocess.run([exe], capture_output=True, text=True, cwd=ROOT, timeout=60)
+    assert bad.returncode != 0 and "no gltf file given" in bad.stderr

@@ -1,0 +1,163 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/solb.h declares; the C++ host mirror
+(glTF loader, Camera, SceneUniforms) reproduces the oracle-side restatement bit for bit; the product refuses to
+run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import camera as ocam
+from oracle import gltf_flatten as gf
+
+from helpers import ROOT, model_path
+
+import __graft_entry__ as entry
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    entry.build()
+
+
+def test_abi_exports_every_declared_symbol():
+    from sol_rs_b200 import _native as N
+
+    hdr = open(os.path.join(ROOT, "include", "solb.h")).read()
+    declared = set(re.findall(r"SOLB_API\s+[\w\s\*]+?\b(solb_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    assert declared == set(N.SYMBOLS), "bindings and header disagree: %s" % (declared ^ set(N.SYMBOLS))
+    L = ctypes.CDLL(N.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), "libsolb.so does not export %s" % name
+    assert N.lib().solb_version() == 0x000100
+
+
+def test_pod_layouts_match_reference_byte_contracts():
+    from sol_rs_b200 import _native as N
+
+    # SURVEY Appendix B
+    assert ctypes.sizeof(N.ModelVertex) == 64 and N.ModelVertex.color.offset == 16 and N.ModelVertex.normal.offset == 32
+    assert ctypes.sizeof(N.MaterialInfo) == 48 and N.MaterialInfo.emissive.offset == 16 and N.MaterialInfo.metallic.offset == 32
+    assert ctypes.sizeof(N.SceneInstance) == 144 and N.SceneInstance.transform.offset == 16 and N.SceneInstance.transform_it.offset == 80
+    assert ctypes.sizeof(N.SceneUniforms) == 400 and N.SceneUniforms.view_inverse.offset == 128
+    assert N.SceneUniforms.projection_inverse.offset == 256 and N.SceneUniforms.frame.offset == 384
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly, not compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sol_rs_b200 as sol
+
+    with pytest.raises(sol.SolbError) as e:
+        sol.Context(0)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under sol_rs_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sol_rs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
+                assert "liboracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
+
+
+@pytest.mark.parametrize("name", ["cornell", "tunnel", "Duck"])
+def test_cpp_loader_matches_oracle_loader(name):
+    from sol_rs_b200 import scene
+
+    s = scene.load_scene(None, model_path(name))
+    fs = gf.load_scene(model_path(name))
+    assert len(s.meshes) == len(fs.meshes)
+    v = np.concatenate([m.vertices for m in s.meshes])
+    i = np.concatenate([m.indices for m in s.meshes])
+    assert np.array_equal(v, fs.vertices) and np.array_equal(i, fs.indices)
+    assert np.array_equal(s.materials, fs.materials)
+    k = 0
+    for m, fm in zip(s.meshes, fs.meshes):
+        assert np.array_equal(m.transform, fm["transform"].reshape(16))
+        assert len(m.primitive_sections) == len(fm["sections"])
+        first_v = fm["sections"][0]["first_vertex"]
+        for ps, fsec in zip(m.primitive_sections, fm["sections"]):
+            assert ps.n_vertices == fsec["n_vertices"] and ps.n_indices == fsec["n_indices"]
+            assert ps.first_vertex == fsec["first_vertex"] - first_v  # mesh-relative on the product side
+            assert ps.material_index == fsec["material"]
+            k += 1
+    assert k == len(fs.instances)
+    assert (s.camera is not None) == (fs.camera is not None)
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell", 512, 512), ("tunnel", 1920, 1080), ("tunnel", 3840, 2160)])
+def test_cpp_camera_uniforms_match_oracle(name, w, h):
+    from sol_rs_b200 import scene
+
+    s = scene.load_scene(None, model_path(name))
+    fs = gf.load_scene(model_path(name))
+    s.camera.set_window_size((w, h))
+    oc = ocam.Camera.from_view(fs.camera["view"], fs.camera["yfov"], fs.camera["znear"], fs.camera["zfar"])
+    oc.set_window_size((w, h))
+    for frame in (0, 7, 511):
+        assert bytes(scene.scene_uniforms(s.camera, w, h, frame)) == ocam.scene_uniforms(oc, w, h, frame)
+
+
+def test_cpp_look_at_camera_matches_oracle():
+    from sol_rs_b200 import scene
+
+    for eye, center in (((5, 5, 5), (0, 0, 0)), ((4, 1, 4), (0, 0.5, 0))):  # 3-ray-debug / 4-ray-ao cameras
+        c = scene.Camera((900, 600))
+        c.look_at(eye, center, (0, -1, 0))
+        o = ocam.Camera((900, 600))
+        o.look_at(eye, center, (0, -1, 0))
+        assert bytes(scene.scene_uniforms(c, 900, 600, 3)) == ocam.scene_uniforms(o, 900, 600, 3)
+        c.set_vfov(50.0)
+        o.set_vfov(50.0)
+        np.testing.assert_array_equal(c.perspective_matrix(), o.persp.reshape(16))
+
+
+def test_loader_error_behaviour(tmp_path):
+    """The reference unwrap()s on a missing / malformed file (src/scene/mod.rs:140): the mirror raises."""
+    from sol_rs_b200 import scene
+    import sol_rs_b200 as sol
+
+    with pytest.raises(sol.SolbError):
+        scene.load_scene(None, str(tmp_path / "missing.gltf"))
+    bad = tmp_path / "bad.gltf"
+    bad.write_text("{ not json")
+    with pytest.raises(sol.SolbError):
+        scene.load_scene(None, str(bad))
+    # minimal valid document with no meshes / cameras
+    ok = tmp_path / "empty.gltf"
+    ok.write_text('{"asset": {"version": "2.0"}}')
+    s = scene.load_scene(None, str(ok))
+    assert s.meshes == [] and s.camera is None and s.materials.shape == (0, 12)
+
+
+def test_find_asset():
+    from sol_rs_b200 import util
+
+    assert util.find_asset("models/cornell.gltf").endswith("assets/models/cornell.gltf")
+    assert util.find_asset("models/ToyCar.glb") is None  # missing upstream too (.MISSING_LARGE_BLOBS)
+
+
+def test_pipeline_selects_kernel_family():
+    from sol_rs_b200 import ray
+    import sol_rs_b200 as sol
+
+    mk = lambda stem, spec=None: ray.Pipeline(None, (ray.PipelineInfo().shader("glsl/%s.rgen" % stem, ray.RAYGEN_KHR)
+                                                     .shader("glsl/%s.rmiss" % stem, ray.MISS_KHR)
+                                                     .shader("glsl/%s.rchit" % stem, ray.CLOSEST_HIT_KHR)
+                                                     .specialization(spec or [0], 0)))
+    assert mk("pathtrace").kind == ray.PATHTRACE and not mk("pathtrace").enable_sky
+    assert mk("pathtrace", [1]).enable_sky
+    assert mk("ao").kind == ray.AO and mk("debug").kind == ray.DEBUG
+    with pytest.raises(sol.SolbError):
+        mk("cube")
+    with pytest.raises(sol.SolbError):
+        ray.ShaderBindingTable(None, mk("debug"), ray.ShaderBindingTableInfo().raygen(0).miss(1))

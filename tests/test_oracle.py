@@ -209,3 +209,48 @@ def test_accumulation_alpha_and_restart(assets):
     f6 = np.zeros((H, W, 4), dtype=np.float32)
     sc.pathtrace_frame(ocam.scene_uniforms(cam, W, H, 6), W, H, f6, 6, False, 8, 4)
     np.testing.assert_allclose(c[..., :3], b[..., :3] * np.float32(0.5) + f6[..., :3] * np.float32(0.5), rtol=1e-6, atol=1e-7)
+
+
+# ---- committed golden fixtures (tests/golden/make_golden.py): the oracle must keep reproducing them ----------
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name,cam_name,w,h", [("cornell", "cornell", 256, 256), ("Duck", "Duck", 450, 300), ("tunnel", "tunnel", 480, 270)])
+def test_golden_hit_ids(name, cam_name, w, h):
+    from helpers import oracle_camera, oracle_scene
+
+    g = np.load(os.path.join(GOLDEN, "hitids_%s_%dx%d.npz" % (name, w, h)))
+    fs, osc = oracle_scene(name)
+    _, ids, _, flags = osc.debug(ocam.scene_uniforms(oracle_camera(fs, cam_name, w, h), w, h, 0), w, h)
+    inst = np.where(ids[..., 0] == oracle.MISS, 255, ids[..., 0]).astype(np.uint8)
+    prim = np.where(ids[..., 1] == oracle.MISS, 65535, ids[..., 1]).astype(np.uint16)
+    assert np.array_equal(inst, g["inst"]) and np.array_equal(prim, g["prim"]) and np.array_equal(flags, g["flags"])
+
+
+def test_golden_ao_frames():
+    from helpers import load_blue_noise, oracle_camera, oracle_scene
+
+    g = np.load(os.path.join(GOLDEN, "ao_duck_160x90_f0-3.npz"))
+    fs, osc = oracle_scene("Duck")
+    cam = oracle_camera(fs, "Duck_ao", 160, 90)
+    img = np.zeros((90, 160, 4), dtype=np.float32)
+    st = oracle.OrcStats()
+    blue = load_blue_noise()
+    assert blue.shape == (256, 256, 4) and blue.dtype == np.uint8
+    for f in range(4):
+        osc.ao_frame(ocam.scene_uniforms(cam, 160, 90, f), 160, 90, img, blue, 0, st)
+    np.testing.assert_allclose(img[..., :3], g["image"], rtol=0, atol=1e-6)
+    assert st.rays == int(g["rays"]) and st.paths == int(g["paths"])
+    assert 0.0 <= img[..., :3].min() and img[..., :3].max() <= 1.0
+
+
+def test_golden_converged_statistics():
+    """The 4096-spp fixtures carry the structural statistics of SURVEY 6."""
+    t = np.load(os.path.join(GOLDEN, "converged_tunnel_160x90_4096spp_b8.npz"))
+    assert t["accum"].shape == (90, 160, 3) and int(t["paths"]) == 160 * 90 * 4096
+    assert 5.9 < int(t["rays"]) / int(t["paths"]) < 6.7            # cap 8: ~6.3 rays/path
+    assert 0.45 < int(t["capped"]) / int(t["paths"]) < 0.57         # ~51 % reach the cap
+    c = np.load(os.path.join(GOLDEN, "converged_cornell_96x96_4096spp_b32.npz"))
+    assert c["accum"].shape == (96, 96, 3) and np.all(np.isfinite(c["accum"]))
+    assert 0.01 < int(c["emissive"]) / int(c["paths"]) < 0.06
