@@ -32,6 +32,11 @@ struct solb_ctx {
     uint32_t blue_w = 0, blue_h = 0;
     uint32_t *pinned_count = nullptr;
     WavefrontState ws = {};
+    // queues + counters + streams of the extra frame parts (overlap mode); index 0 unused (= ws / stream)
+    uint32_t *part_queue[WF_MAX_PARTS][2] = {};
+    uint32_t *part_counters[WF_MAX_PARTS] = {};
+    cudaStream_t part_stream[WF_MAX_PARTS] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[WF_MAX_PARTS] = {};
     std::vector<cudaEvent_t> ev_pool;  // timing mode: pairs around every dominant-kernel launch
     float trace_kernel_ms_total = 0.0f;
     uint32_t trace_kernel_launches = 0;
@@ -130,6 +135,8 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.node_weight = env_int("SOLB_NODE_WEIGHT", c->tune.node_weight, 1, 64);
         c->tune.ctas_per_sm = env_int("SOLB_CTAS_PER_SM", c->tune.ctas_per_sm, 1, 16);
         c->tune.check_every = env_int("SOLB_CHECK_EVERY", c->tune.check_every, 1, 1024);
+        c->tune.overlap = env_int("SOLB_OVERLAP", c->tune.overlap, 1, WF_MAX_PARTS);
+        c->tune.ctas_per_sm_overlap = env_int("SOLB_CTAS_PER_SM_OVERLAP", c->tune.ctas_per_sm_overlap, 1, 16);
     }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
@@ -146,6 +153,10 @@ static void free_wavefront(solb_ctx *c) {
     WavefrontState &w = c->ws;
     cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.thr); cudaFree(w.pix); cudaFree(w.hit);
     cudaFree(w.queue[0]); cudaFree(w.queue[1]); cudaFree(w.counters);
+    for (int k = 1; k < WF_MAX_PARTS; k++) {
+        cudaFree(c->part_queue[k][0]); cudaFree(c->part_queue[k][1]); cudaFree(c->part_counters[k]);
+        c->part_queue[k][0] = c->part_queue[k][1] = nullptr; c->part_counters[k] = nullptr;
+    }
     w = WavefrontState{};
 }
 
@@ -160,6 +171,11 @@ static void ctx_release(solb_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int k = 1; k < WF_MAX_PARTS; k++) {
+        if (ctx->part_stream[k]) cudaStreamDestroy(ctx->part_stream[k]);
+        if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -542,6 +558,16 @@ static int ensure_wavefront(solb_ctx *ctx, uint32_t n_pixels) {
     CU(ctx, cudaMalloc((void **)&w.queue[0], n * sizeof(uint32_t)));
     CU(ctx, cudaMalloc((void **)&w.queue[1], n * sizeof(uint32_t)));
     CU(ctx, cudaMalloc((void **)&w.counters, 4 * sizeof(uint32_t)));
+    for (int k = 1; k < WF_MAX_PARTS; k++) {
+        CU(ctx, cudaMalloc((void **)&ctx->part_queue[k][0], n * sizeof(uint32_t)));
+        CU(ctx, cudaMalloc((void **)&ctx->part_queue[k][1], n * sizeof(uint32_t)));
+        CU(ctx, cudaMalloc((void **)&ctx->part_counters[k], 4 * sizeof(uint32_t)));
+        if (!ctx->part_stream[k]) {
+            CU(ctx, cudaStreamCreateWithFlags(&ctx->part_stream[k], cudaStreamNonBlocking));
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming));
+        }
+    }
+    if (!ctx->ev_fork) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     w.capacity = n_pixels;
     return SOLB_OK;
 }
@@ -587,10 +613,23 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
         return SOLB_OK;
     } else {
         if ((rc = ensure_wavefront(ctx, fc.width * fc.height))) return rc;
-        CU(ctx, launch_pathtrace_wavefront(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->ws, (float4 *)accum->dev,
+        WavefrontLaunch L;
+        L.stream[0] = ctx->stream;
+        L.fork = ctx->ev_fork;
+        L.ws[0] = ctx->ws;
+        for (int k = 1; k < WF_MAX_PARTS; k++) {
+            L.stream[k] = ctx->part_stream[k];
+            L.join[k] = ctx->ev_join[k];
+            L.ws[k] = ctx->ws;
+            L.ws[k].queue[0] = ctx->part_queue[k][0];
+            L.ws[k].queue[1] = ctx->part_queue[k][1];
+            L.ws[k].counters = ctx->part_counters[k];
+        }
+        L.host_counts = ctx->pinned_count;
+        L.sm_count = ctx->sm_count;
+        CU(ctx, launch_pathtrace_wavefront(L, fc, s->accel, s->d_inst, s->d_shade, (float4 *)accum->dev,
                                            render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0,
-                                           ctx->sm_count, ctx->pinned_count, &ctx->launches, ctx->timing ? &ctx->ev_pool : nullptr,
-                                           &n_ev, ctx->tune));
+                                           &ctx->launches, ctx->timing ? &ctx->ev_pool : nullptr, &n_ev, ctx->tune));
     }
     timer.stop();  // synchronises in timing mode
     for (uint32_t i = 0; ctx->timing && i + 1 < n_ev; i += 2) {

@@ -207,12 +207,12 @@ __device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, uint32_t width, u
     return y * width + x;
 }
 
-__global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, WavefrontState ws, uint32_t n_slots,
+__global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, WavefrontState ws, uint32_t slot_begin, uint32_t n_slots,
                                                      unsigned long long *stats) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     uint32_t p = 0;
-    if (i < n_slots) p = swizzled_pixel(i, fc.width, fc.height, valid);
+    if (i < n_slots) p = swizzled_pixel(slot_begin + i, fc.width, fc.height, valid);
     if (valid) {
         const uint32_t x = p % fc.width, y = p / fc.width;
         uint32_t rng = tea(p, fc.frame);
@@ -402,9 +402,10 @@ __global__ void __launch_bounds__(256) k_wf_shade(const FrameConsts fc, const De
     warp_add_stat(stats, ST_PATHS, np);
 }
 
-__global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, WavefrontState ws, float4 *accum, uint32_t *render) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= fc.width * fc.height) return;
+__global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, WavefrontState ws, float4 *accum, uint32_t *render,
+                                                    uint32_t pixel_begin, uint32_t pixel_end) {
+    const uint32_t p = pixel_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pixel_end) return;
     const float4 x4 = ws.pix[p];
     uint32_t rgba;
     const float4 out = resolve_pixel(fc, f3(x4.x, x4.y, x4.z), accum[p], rgba);
@@ -547,55 +548,89 @@ cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum
     return cudaGetLastError();
 }
 
-// One reference frame with the wavefront schedule.  Returns the number of kernels launched.
-cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as,
-                                       const DeviceInstance *instances, const ShadeRecord *shade, WavefrontState &ws, float4 *accum,
-                                       uint32_t *render, unsigned long long *stats, bool collect, int sm_count,
-                                       uint32_t *host_count_pinned, uint64_t *launches, std::vector<cudaEvent_t> *events,
+// One reference frame with the wavefront schedule.
+//
+// The frame is split into 1..4 horizontal parts of whole tile rows.  Each part runs its own wave sequence (own
+// queues + counters, shared per-pixel state arrays) on its own stream, so the drain tail of one part's persistent
+// trace kernel and its memory-bound shade kernel overlap with another part's traversal.
+cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameConsts &fc, const AccelStorage &as,
+                                       const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
+                                       unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
                                        uint32_t *n_events_used, const TraceTuning &tune) {
     const uint32_t n_pixels = fc.width * fc.height;
     if (n_pixels == 0) return cudaSuccess;
-    const uint32_t n_slots = (uint32_t)((((uint64_t)((fc.width + 7u) >> 3) * ((fc.height + 3u) >> 2))) * 32u);
-    cudaError_t err = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(uint32_t), st);
-    if (err != cudaSuccess) return err;
-    k_wf_generate<<<(n_slots + 255) / 256, 256, 0, st>>>(fc, ws, n_slots, stats);
-    *launches += 1;
-    const int trace_grid = sm_count * tune.ctas_per_sm;  // persistent CTAs of 128 threads
-    const int shade_grid = sm_count * 4;   // grid-stride
+    cudaError_t err = cudaSuccess;
+    const uint32_t tiles_x = (fc.width + 7u) >> 3, tiles_y = (fc.height + 3u) >> 2;
+    int n_lanes = (events || !L.stream[1]) ? 1 : tune.overlap;
+    if (n_lanes > WF_MAX_PARTS) n_lanes = WF_MAX_PARTS;
+    if ((uint32_t)n_lanes > tiles_y) n_lanes = (int)tiles_y;
+    if (n_lanes < 1) n_lanes = 1;
+    const uint32_t rows_per_lane = (tiles_y + n_lanes - 1) / n_lanes;
+    const int trace_grid = L.sm_count * (n_lanes > 1 ? tune.ctas_per_sm_overlap : tune.ctas_per_sm);  // persistent CTAs of 128 threads
+    const int shade_grid = L.sm_count * (n_lanes > 1 ? 2 : 4);                                        // grid-stride
     // every pixel needs at least spp rays; at most spp * (max_bounces + 2)
     const uint32_t max_waves = fc.spp * (fc.max_bounces + 2u);
     const uint32_t check_every = (uint32_t)tune.check_every;
-    int qi = 0;
-    for (uint32_t wave = 0; wave < max_waves; wave++) {
-        if (events) {  // timing mode: bracket the dominant kernel with an event pair
-            while (events->size() < (size_t)*n_events_used + 2) {
-                cudaEvent_t e;
-                err = cudaEventCreate(&e);
-                if (err != cudaSuccess) return err;
-                events->push_back(e);
+    uint32_t pixel_begin[WF_MAX_PARTS], pixel_end[WF_MAX_PARTS];
+    bool live[WF_MAX_PARTS] = { false, false, false, false };
+    int qi[WF_MAX_PARTS] = { 0, 0, 0, 0 };
+    if (n_lanes > 1) {  // fork: the extra streams start after everything already queued on the ctx stream
+        if ((err = cudaEventRecord(L.fork, L.stream[0])) != cudaSuccess) return err;
+        for (int k = 1; k < n_lanes; k++)
+            if ((err = cudaStreamWaitEvent(L.stream[k], L.fork, 0)) != cudaSuccess) return err;
+    }
+    for (int k = 0; k < n_lanes; k++) {
+        const uint32_t row0 = k * rows_per_lane, row1 = (row0 + rows_per_lane < tiles_y) ? row0 + rows_per_lane : tiles_y;
+        const uint32_t slot_begin = row0 * tiles_x * 32u, n_slots = (row1 - row0) * tiles_x * 32u;
+        pixel_begin[k] = row0 * 4u * fc.width;
+        pixel_end[k] = (row1 * 4u < fc.height ? row1 * 4u : fc.height) * fc.width;
+        if ((err = cudaMemsetAsync(L.ws[k].counters, 0, 4 * sizeof(uint32_t), L.stream[k])) != cudaSuccess) return err;
+        k_wf_generate<<<(n_slots + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], slot_begin, n_slots, stats);
+        *launches += 1;
+        live[k] = true;
+    }
+    for (uint32_t wave = 0; wave < max_waves && (live[0] || live[1] || live[2] || live[3]); wave++) {
+        for (int k = 0; k < n_lanes; k++) {
+            if (!live[k]) continue;
+            cudaStream_t st = L.stream[k];
+            if (events) {  // timing mode (single lane): bracket the dominant kernel with an event pair
+                while (events->size() < (size_t)*n_events_used + 2) {
+                    cudaEvent_t e;
+                    if ((err = cudaEventCreate(&e)) != cudaSuccess) return err;
+                    events->push_back(e);
+                }
+                cudaEventRecord((*events)[*n_events_used], st);
             }
-            cudaEventRecord((*events)[*n_events_used], st);
+            if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune);
+            else k_wf_trace<false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune);
+            if (events) {
+                cudaEventRecord((*events)[*n_events_used + 1], st);
+                *n_events_used += 2;
+            }
+            k_wf_shade<<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+            *launches += 2;
+            qi[k] ^= 1;
         }
-        if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats, tune);
-        else k_wf_trace<false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), ws, qi, stats, tune);
-        if (events) {
-            cudaEventRecord((*events)[*n_events_used + 1], st);
-            *n_events_used += 2;
-        }
-        k_wf_shade<<<shade_grid, 256, 0, st>>>(fc, instances, shade, ws, qi, stats);
-        *launches += 2;
-        qi ^= 1;
         if (wave + 1 >= fc.spp && ((wave + 1) % check_every) == 0) {
-            // poll the survivor count so finished frames stop launching empty waves
-            err = cudaMemcpyAsync(host_count_pinned, &ws.counters[qi], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-            if (err != cudaSuccess) return err;
-            err = cudaStreamSynchronize(st);
-            if (err != cudaSuccess) return err;
-            if (*host_count_pinned == 0) break;
+            // poll the survivor counts so finished halves stop launching empty waves
+            for (int k = 0; k < n_lanes; k++)
+                if (live[k] && (err = cudaMemcpyAsync(&L.host_counts[k], &L.ws[k].counters[qi[k]], sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                                      L.stream[k])) != cudaSuccess) return err;
+            for (int k = 0; k < n_lanes; k++) {
+                if (!live[k]) continue;
+                if ((err = cudaStreamSynchronize(L.stream[k])) != cudaSuccess) return err;
+                if (L.host_counts[k] == 0) live[k] = false;
+            }
         }
     }
-    k_wf_resolve<<<(n_pixels + 255) / 256, 256, 0, st>>>(fc, ws, accum, render);
-    *launches += 1;
+    for (int k = 0; k < n_lanes; k++) {
+        k_wf_resolve<<<(pixel_end[k] - pixel_begin[k] + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], accum, render, pixel_begin[k], pixel_end[k]);
+        *launches += 1;
+    }
+    for (int k = 1; k < n_lanes; k++) {  // join
+        if ((err = cudaEventRecord(L.join[k], L.stream[k])) != cudaSuccess) return err;
+        if ((err = cudaStreamWaitEvent(L.stream[0], L.join[k], 0)) != cudaSuccess) return err;
+    }
     return cudaGetLastError();
 }
 

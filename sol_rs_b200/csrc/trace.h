@@ -26,6 +26,18 @@ struct TraceTuning {
     int node_weight = 1;
     int ctas_per_sm = 8;   // persistent grid = SMs x this
     int check_every = 8;   // host polls the survivor count every this many waves
+    int overlap = 3;       // frame parts (1..4) run as independent wave sequences on their own streams, so the drain tail of one
+                           // part's persistent trace kernel and its memory-bound shade kernel overlap another part's traversal
+    int ctas_per_sm_overlap = 5;  // persistent CTAs per SM and part when overlapping
+};
+
+constexpr int WF_MAX_PARTS = 4;
+struct WavefrontLaunch {
+    cudaStream_t stream[WF_MAX_PARTS];   // [0] = the ctx stream; others may be null: no overlap
+    cudaEvent_t fork, join[WF_MAX_PARTS];
+    WavefrontState ws[WF_MAX_PARTS];     // same per-pixel state arrays, separate queues + counters
+    uint32_t *host_counts;               // pinned, WF_MAX_PARTS entries
+    int sm_count;
 };
 
 cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &sv, ShadeRecord *out);
@@ -36,10 +48,9 @@ cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const flo
 cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                                   const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
                                   bool collect);
-cudaError_t launch_pathtrace_wavefront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as,
-                                       const DeviceInstance *instances, const ShadeRecord *shade, WavefrontState &ws, float4 *accum,
-                                       uint32_t *render, unsigned long long *stats, bool collect, int sm_count,
-                                       uint32_t *host_count_pinned, uint64_t *launches, std::vector<cudaEvent_t> *events,
+cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameConsts &fc, const AccelStorage &as,
+                                       const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
+                                       unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
                                        uint32_t *n_events_used, const TraceTuning &tune);
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
