@@ -271,6 +271,175 @@ __global__ void k_bottom_up(int n, BNode *bn, int *parent, int *node_count, floa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Warp-cooperative treelet restructuring (Karras & Aila 2013, section 4): threads still walk up from the
+// leaves with atomic flags, but when lanes of a warp reach treelet roots the WHOLE warp optimises those
+// treelets one after another: 32 lanes share the 2^7 subset areas and the dynamic program over subset
+// sizes, so one treelet costs ~1 us instead of the ~50 us of the per-thread version (k_bottom_up mode 1),
+// which also shortens the serial critical path up the tree by the same factor.
+struct WarpTreeletScratch {
+    float area[128];
+    float cost[128];
+    float lo[SOLB_TREELET_N][3], hi[SOLB_TREELET_N][3];
+    float lcost[SOLB_TREELET_N];
+    int lcount[SOLB_TREELET_N];
+    int leaves[SOLB_TREELET_N];
+    int internals[SOLB_TREELET_N];
+    uint8_t part[128];
+    uint8_t small[128];  // subset holds <= SOLB_MAX_LEAF_TRIS triangles (count saturated)
+    int nl;
+    int changed;
+};
+
+__device__ void coop_optimize_treelet(BNode *bn, int *parent, float *node_cost, int *node_count, int n_internal, int root,
+                                      WarpTreeletScratch &ws, int lane) {
+    if (lane == 0) {  // treelet formation: expand the largest-area internal leaf until 7 leaves
+        int nl = 0, ni = 0;
+        ws.internals[ni++] = root;
+        ws.leaves[nl++] = bn[root].left;
+        ws.leaves[nl++] = bn[root].right;
+        while (nl < SOLB_TREELET_N) {
+            int best = -1;
+            float best_a = -1.0f;
+            for (int i = 0; i < nl; i++) {
+                const int c = ws.leaves[i];
+                if (c < n_internal) {
+                    const float a = half_area(bn[c].lo, bn[c].hi);
+                    if (a > best_a) { best_a = a; best = i; }
+                }
+            }
+            if (best < 0) break;
+            const int c = ws.leaves[best];
+            ws.internals[ni++] = c;
+            ws.leaves[best] = bn[c].left;
+            ws.leaves[nl++] = bn[c].right;
+        }
+        ws.nl = nl;
+        ws.changed = 0;
+    }
+    __syncwarp();
+    const int nl = ws.nl;
+    if (nl < 3) return;
+    const int full = (1 << nl) - 1;
+    if (lane < nl) {
+        const BNode b = bn[ws.leaves[lane]];
+        ws.lo[lane][0] = b.lo.x; ws.lo[lane][1] = b.lo.y; ws.lo[lane][2] = b.lo.z;
+        ws.hi[lane][0] = b.hi.x; ws.hi[lane][1] = b.hi.y; ws.hi[lane][2] = b.hi.z;
+        ws.lcost[lane] = node_cost[ws.leaves[lane]];
+        ws.lcount[lane] = node_count[ws.leaves[lane]];
+    }
+    __syncwarp();
+    for (int s = lane + 1; s <= full; s += 32) {  // subset areas and "fits in a leaf" flags
+        float lo0 = 3.4e38f, lo1 = 3.4e38f, lo2 = 3.4e38f, hi0 = -3.4e38f, hi1 = -3.4e38f, hi2 = -3.4e38f;
+        int cnt = 0;
+        for (int i = 0; i < nl; i++)
+            if (s & (1 << i)) {
+                lo0 = fminf(lo0, ws.lo[i][0]); lo1 = fminf(lo1, ws.lo[i][1]); lo2 = fminf(lo2, ws.lo[i][2]);
+                hi0 = fmaxf(hi0, ws.hi[i][0]); hi1 = fmaxf(hi1, ws.hi[i][1]); hi2 = fmaxf(hi2, ws.hi[i][2]);
+                cnt += min(ws.lcount[i], 64);
+            }
+        ws.area[s] = half_area(f3(lo0, lo1, lo2), f3(hi0, hi1, hi2));
+        ws.small[s] = cnt <= SOLB_MAX_LEAF_TRIS ? (uint8_t)cnt : 0;
+        if (__popc(s) == 1) { ws.cost[s] = ws.lcost[31 - __clz(s)]; ws.part[s] = 0; }
+    }
+    __syncwarp();
+    for (int k = 2; k <= nl; k++) {  // dynamic program over subset sizes
+        for (int s = lane + 1; s <= full; s += 32) {
+            if (__popc(s) != k) continue;
+            float best_c = 3.4e38f;
+            int best_p = 0;
+            const int delta = (s - 1) & s;
+            int p = (-delta) & s;
+            do {
+                const float c = ws.cost[p] + ws.cost[s ^ p];
+                if (c < best_c) { best_c = c; best_p = p; }
+                p = (p - delta) & s;
+            } while (p != 0);
+            float c = SOLB_SAH_CI * ws.area[s] + best_c;
+            if (ws.small[s]) c = fminf(c, SOLB_SAH_CT * ws.area[s] * (float)ws.small[s]);
+            ws.cost[s] = c;
+            ws.part[s] = (uint8_t)best_p;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && ws.cost[full] < node_cost[root] * 0.9999f) {  // rebuild the topology, reusing the internal node ids
+        int stack_set[SOLB_TREELET_N], stack_node[SOLB_TREELET_N], order[SOLB_TREELET_N];
+        int sp = 0, next_internal = 1, n_order = 0;
+        stack_set[sp] = full; stack_node[sp] = root; sp++;
+        while (sp) {
+            sp--;
+            const int s = stack_set[sp], node = stack_node[sp];
+            order[n_order++] = node;
+            const int sub[2] = { (int)ws.part[s], s ^ (int)ws.part[s] };
+            int child[2];
+            for (int k = 0; k < 2; k++) {
+                if (__popc(sub[k]) == 1) child[k] = ws.leaves[31 - __clz(sub[k])];
+                else {
+                    child[k] = ws.internals[next_internal++];
+                    stack_set[sp] = sub[k]; stack_node[sp] = child[k]; sp++;
+                }
+                parent[child[k]] = node;
+            }
+            bn[node].left = child[0];
+            bn[node].right = child[1];
+        }
+        for (int k = n_order - 1; k >= 0; k--) {
+            const int node = order[k];
+            const int l = bn[node].left, r = bn[node].right;
+            const float3 lo = fmin3(bn[l].lo, bn[r].lo), hi = fmax3(bn[l].hi, bn[r].hi);
+            bn[node].lo = lo;
+            bn[node].hi = hi;
+            node_count[node] = node_count[l] + node_count[r];
+            node_cost[node] = leaf_or_internal_cost(half_area(lo, hi), node_cost[l] + node_cost[r], node_count[node]);
+        }
+        __threadfence();
+    }
+    __syncwarp();
+}
+
+constexpr int TL_BLOCK = 128;
+__global__ void __launch_bounds__(TL_BLOCK) k_bottom_up_coop(int n, BNode *bn, int *parent, int *node_count, float *node_cost,
+                                                             uint32_t *flags, int gamma) {
+    __shared__ WarpTreeletScratch scratch[TL_BLOCK / 32];
+    WarpTreeletScratch &ws = scratch[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int node = j < n ? parent[n - 1 + j] : -1;
+    bool active = node >= 0;
+    while (__any_sync(0xffffffffu, active)) {
+        bool ready = false;
+        if (active) {
+            __threadfence();
+            const uint32_t old = atomicAdd(&flags[node], 1u);
+            if (old == 0) {
+                active = false;  // the sibling subtree is not finished; its thread continues upward
+            } else {
+                __threadfence();
+                const int l = bn[node].left, r = bn[node].right;
+                const float3 lo = fmin3(bn[l].lo, bn[r].lo), hi = fmax3(bn[l].hi, bn[r].hi);
+                bn[node].lo = lo;
+                bn[node].hi = hi;
+                const int cnt = node_count[l] + node_count[r];
+                node_count[node] = cnt;
+                node_cost[node] = leaf_or_internal_cost(half_area(lo, hi), node_cost[l] + node_cost[r], cnt);
+                ready = cnt >= gamma;
+                __threadfence();
+            }
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, active && ready);
+        while (m) {
+            const int leader = __ffs(m) - 1;
+            const int root = __shfl_sync(0xffffffffu, node, leader);
+            coop_optimize_treelet(bn, parent, node_cost, node_count, n - 1, root, ws, lane);
+            m &= m - 1;
+        }
+        if (active) {
+            node = parent[node];
+            if (node < 0) active = false;
+        }
+    }
+}
+
 __global__ void k_clear_u32(uint32_t *p, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0;
@@ -306,6 +475,11 @@ __global__ void k_empty_root(Node8 *wide) {
 
 template <class T>
 static cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)); }
+// build scratch comes from the stream-ordered pool: no device-wide synchronisation per buffer, reused across rebuilds
+template <class T>
+static cudaError_t salloc(cudaStream_t st, T **p, size_t count) {
+    return cudaMallocAsync((void **)p, std::max<size_t>(count, 1) * sizeof(T), st);
+}
 
 cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt, uint64_t *launches) {
     cudaError_t err = cudaSuccess;
@@ -327,7 +501,7 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
 
     out.release();
     out.n_tris = n;
-    CK(dalloc(&wide, std::max<uint32_t>(n, 1)));
+    CK(salloc(st, &wide, std::max<uint32_t>(n, 1)));
     CK(dalloc(&tri_out, n));
     if (n == 0) {
         k_empty_root<<<1, 1, 0, st>>>(wide);
@@ -336,10 +510,10 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         out.depth = 1;
         goto finish;
     }
-    CK(dalloc(&tri_world, n));
-    CK(dalloc(&prim_lo, n));
-    CK(dalloc(&prim_hi, n));
-    CK(dalloc(&bounds, 8));
+    CK(salloc(st, &tri_world, n));
+    CK(salloc(st, &prim_lo, n));
+    CK(salloc(st, &prim_hi, n));
+    CK(salloc(st, &bounds, 8));
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
     k_prep_tris<<<nb, T, 0, st>>>(sv, tri_world, prim_lo, prim_hi, bounds);
     *launches += 2;
@@ -350,26 +524,29 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         out.depth = 1;
         goto finish;
     }
-    CK(dalloc(&keys, n));
-    CK(dalloc(&keys_tmp, n));
-    CK(dalloc(&vals, n));
-    CK(dalloc(&vals_tmp, n));
-    CK(dalloc(&tile_hist, 256 * (size_t)((n + RS_TILE - 1) / RS_TILE)));
+    CK(salloc(st, &keys, n));
+    CK(salloc(st, &keys_tmp, n));
+    CK(salloc(st, &vals, n));
+    CK(salloc(st, &vals_tmp, n));
+    CK(salloc(st, &tile_hist, 256 * (size_t)((n + RS_TILE - 1) / RS_TILE)));
     k_morton<<<nb, T, 0, st>>>(prim_lo, prim_hi, n, bounds, keys, vals);
     *launches += 1;
     CK(radix_sort_pairs(st, keys, vals, keys_tmp, vals_tmp, n, 63, tile_hist, launches));
-    CK(dalloc(&bn, 2 * (size_t)n - 1));
-    CK(dalloc(&parent, 2 * (size_t)n - 1));
-    CK(dalloc(&node_count, 2 * (size_t)n - 1));
-    CK(dalloc(&node_cost, 2 * (size_t)n - 1));
-    CK(dalloc(&flags, n));
+    CK(salloc(st, &bn, 2 * (size_t)n - 1));
+    CK(salloc(st, &parent, 2 * (size_t)n - 1));
+    CK(salloc(st, &node_count, 2 * (size_t)n - 1));
+    CK(salloc(st, &node_cost, 2 * (size_t)n - 1));
+    CK(salloc(st, &flags, n));
     k_hierarchy<<<nb, T, 0, st>>>(keys, vals, prim_lo, prim_hi, (int)n, bn, parent, node_count, node_cost, flags);
     k_bottom_up<<<nb, T, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, 0, 0);
     *launches += 2;
     CK(cudaMemcpyAsync(&out.sah_lbvh, node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
     for (int pass = 0; pass < opt.treelet_passes; pass++) {
         k_clear_u32<<<nb, T, 0, st>>>(flags, n);
-        k_bottom_up<<<(n + 63) / 64, 64, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, 1, opt.treelet_gamma);
+        if (opt.coop_treelet)
+            k_bottom_up_coop<<<(n + TL_BLOCK - 1) / TL_BLOCK, TL_BLOCK, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, opt.treelet_gamma);
+        else
+            k_bottom_up<<<(n + 63) / 64, 64, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, 1, opt.treelet_gamma);
         *launches += 2;
     }
     CK(cudaMemcpyAsync(&out.sah_final, node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -383,9 +560,9 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         out.hi[0] = root.hi.x; out.hi[1] = root.hi.y; out.hi[2] = root.hi.z;
     }
     // collapse, one launch per level of the wide tree
-    CK(dalloc(&queue_a, n));
-    CK(dalloc(&queue_b, n));
-    CK(dalloc(&counters, 4));
+    CK(salloc(st, &queue_a, n));
+    CK(salloc(st, &queue_b, n));
+    CK(salloc(st, &counters, 4));
     {
         CollapseItem rootItem;
         rootItem.bnode = 0;
@@ -425,9 +602,12 @@ finish:
         out.n_binary = n >= 2 ? 2 * n - 1 : n;
     }
 done:
-    cudaFree(tri_world); cudaFree(prim_lo); cudaFree(prim_hi); cudaFree(bounds); cudaFree(keys); cudaFree(keys_tmp);
-    cudaFree(vals); cudaFree(vals_tmp); cudaFree(tile_hist); cudaFree(flags); cudaFree(counters); cudaFree(bn);
-    cudaFree(parent); cudaFree(node_count); cudaFree(node_cost); cudaFree(queue_a); cudaFree(queue_b); cudaFree(wide);
+    {
+        void *scratch[] = { tri_world, prim_lo, prim_hi, bounds, keys, keys_tmp, vals, vals_tmp, tile_hist, flags, counters, bn,
+                            parent, node_count, node_cost, queue_a, queue_b, wide };
+        for (void *q : scratch)
+            if (q) cudaFreeAsync(q, st);
+    }
     cudaFree(tri_out);
     if (err != cudaSuccess) out.release();
     return err;

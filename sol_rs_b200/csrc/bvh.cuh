@@ -134,9 +134,24 @@ SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, fl
 // mantissa bits [15:8] of the float 32768.0, giving m = 32768 + q exactly; the 32768 is folded into the
 // per-node offset, t = m * a + (b - 32768 a).  Folding costs at most |a| / 512 of rounding (a = one
 // quantisation cell in units of t), which the near / far offsets below absorb conservatively.
+#if defined(__CUDACC__)
+// bit pattern of 32768.0f in (non-const) constant memory: opaque to the optimiser, so PRMT takes it as the register /
+// constant operand and the byte selector as an immediate
+__constant__ uint32_t c_q2m_bias = 0x47000000u;
+#endif
 SOLB_HD float q2m(uint32_t w, int j) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7604u + ((uint32_t)j << 4)));
+    // selector as an immediate, the 32768.0f pattern as the register operand: otherwise ptxas keeps re-materialising
+    // the four selectors in registers (one extra IMAD.U32 per PRMT in the first build)
+    uint32_t r;
+    const uint32_t k = c_q2m_bias;
+    switch (j) {
+        case 0: asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(k)); break;
+        case 1: asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(k)); break;
+        case 2: asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(w), "r"(k)); break;
+        default: asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(k)); break;
+    }
+    return __uint_as_float(r);
 #else
     return u2f(0x47000000u | (((w >> (8 * j)) & 0xffu) << 8));
 #endif

@@ -326,6 +326,7 @@ static int do_build(solb_scene *s) {
     CU(ctx, cudaSetDevice(ctx->device));
     BuildOptions opt;
     if (const char *v = getenv("SOLB_TREELET_PASSES")) opt.treelet_passes = std::max(0, std::min(8, atoi(v)));
+    if (const char *v = getenv("SOLB_TREELET_COOP")) opt.coop_treelet = atoi(v) != 0;
     if (const char *v = getenv("SOLB_TREELET_GAMMA")) opt.treelet_gamma = std::max(3, std::min(1 << 20, atoi(v)));
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = build_accel(ctx->stream, s->view(), s->accel, opt, &ctx->launches);

@@ -67,6 +67,7 @@ struct AccelStorage {
 struct BuildOptions {
     int treelet_passes = 2;
     int treelet_gamma = 7;
+    int coop_treelet = 1;  // warp-cooperative treelet kernel (0: per-thread reference version)
 };
 
 cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt, uint64_t *launches);

@@ -14,8 +14,8 @@ constexpr int TRACE_BLOCK = 128;
 // Traversal stack: SOLB_SM_STACK entries per lane in shared memory ([entry][thread] so a warp's
 // accesses are conflict-free), the rest spills to local memory.
 struct DevStack {
-    uint2 *sm;
-    uint2 loc[SOLB_LOCAL_STACK];
+    uint2 *sm;   // this lane's column in shared memory
+    uint2 *loc;  // spill array (local memory); kept OUTSIDE the struct so sp / sm stay in registers
     int sp;
     __device__ __forceinline__ void push(uint2 v) {
         if (sp < SOLB_SM_STACK) sm[sp * TRACE_BLOCK] = v;
@@ -31,8 +31,10 @@ struct DevStack {
 
 #define SOLB_DECL_STACK()                                        \
     __shared__ uint2 s_stack[SOLB_SM_STACK * TRACE_BLOCK];       \
+    uint2 stack_spill[SOLB_LOCAL_STACK];                         \
     DevStack stack;                                              \
     stack.sm = s_stack + threadIdx.x;                            \
+    stack.loc = stack_spill;                                     \
     stack.sp = 0
 
 // stats slots (unsigned long long each)
@@ -263,9 +265,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, 
     Hit hit;
     hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f;
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+    uint32_t b_ray = 0;  // lanes holding a ray (warp-uniform)
     for (;;) {
         // ---- refill idle lanes ----
-        const uint32_t idle = __ballot_sync(0xffffffffu, !has_ray);
+        const uint32_t idle = ~b_ray;
         if (!exhausted && (__popc(idle) >= tune.fetch_idle)) {
             uint32_t want = (uint32_t)__popc(idle);
             uint32_t served = 0;  // idle lanes (in rank order) already given a slot
@@ -295,8 +298,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, 
                 pool_next += take;
                 served += take;
             }
+            b_ray = __ballot_sync(0xffffffffu, has_ray);
         }
-        if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;  // nothing in flight and nothing left to fetch
+        if (b_ray == 0u) break;  // nothing in flight and nothing left to fetch
         // ---- vote: node step or triangle step ----
         const bool w_node = has_ray && (ngroup.y & 0xff000000u);
         const bool w_tri = has_ray && tgroup.y;
@@ -322,6 +326,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, 
                 if (e.y & 0xff000000u) ngroup = e; else tgroup = e;
             }
         }
+        b_ray = __ballot_sync(0xffffffffu, has_ray);
     }
     warp_add_stat(stats, ST_RAYS, nr);
     if (STATS) {
