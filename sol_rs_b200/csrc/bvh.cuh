@@ -68,10 +68,10 @@ struct RayFrame {
 
 SOLB_HD RayFrame make_ray_frame(float3 d) {
     // Duff et al. 2017 branchless orthonormal basis around normalize(d)
-    const float inv = 1.0f / sqrtf(dot(d, d));
+    const float inv = fast_rsqrt(dot(d, d));
     const float3 n = f3(d.x * inv, d.y * inv, d.z * inv);
     const float s = (n.z < 0.0f ? -1.0f : 1.0f);
-    const float a = -1.0f / (s + n.z);
+    const float a = -fast_rcp(s + n.z);
     const float b = n.x * n.y * a;
     RayFrame f;
     f.e1 = f3(1.0f + s * n.x * n.x * a, s * b, -s * n.x);
@@ -110,7 +110,7 @@ SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, fl
     }
     const float det = U + V + W;
     if (det == 0.0f) return false;  // edge-on triangle
-    const float rdet = 1.0f / det;
+    const float rdet = fast_rcp(det);
     // Depth from the plane through the three vertices (n = e1 x e2 from exact-ish edge differences):
     // t = (p0 - o).n / d.n.  On the long sliver triangles of tunnel.gltf (9.5 x 0.05 units) this is ~5x
     // more accurate than interpolating vertex depths with the barycentrics, and as accurate as the f32
@@ -119,7 +119,7 @@ SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, fl
     const float3 n = cross(e1, e2);
     const float den = dot(d, n);
     if (den == 0.0f) return false;
-    const float t = dot(A, n) / den;
+    const float t = fast_div(dot(A, n), den);
     if (!(t > tmin && t < tmax)) return false;
     t_out = t;
     u_out = V * rdet;
@@ -205,7 +205,7 @@ SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, 
 
 SOLB_HD float safe_rcp_dir(float d) {
     const float tiny = 1e-20f;
-    return 1.0f / (fabsf(d) > tiny ? d : (f2u(d) >> 31 ? -tiny : tiny));
+    return fast_rcp(fabsf(d) > tiny ? d : (f2u(d) >> 31 ? -tiny : tiny));
 }
 
 #if defined(__CUDA_ARCH__)

@@ -84,6 +84,30 @@ SOLB_HD float add_rn(float a, float b) {
 #endif
 }
 
+// fast reciprocal / division for quantities whose last ulp does not matter (slab offsets, ray-space frame,
+// hit depth, barycentrics): MUFU.RCP / MUFU.RSQ instead of the IEEE sequences
+SOLB_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
+}
+SOLB_HD float fast_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+SOLB_HD float fast_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
 // ---- float3 helpers ----
 SOLB_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
 SOLB_HD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
