@@ -37,6 +37,7 @@ struct solb_ctx {
     uint32_t *part_counters[WF_MAX_PARTS] = {};
     cudaStream_t part_stream[WF_MAX_PARTS] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[WF_MAX_PARTS] = {};
+    uint2 *part_spill[WF_MAX_PARTS] = {};  // ray-pool kernel stack spill, one per frame part
     std::vector<cudaEvent_t> ev_pool;  // timing mode: pairs around every dominant-kernel launch
     float trace_kernel_ms_total = 0.0f;
     uint32_t trace_kernel_launches = 0;
@@ -136,6 +137,9 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.ctas_per_sm = env_int("SOLB_CTAS_PER_SM", c->tune.ctas_per_sm, 1, 16);
         c->tune.check_every = env_int("SOLB_CHECK_EVERY", c->tune.check_every, 1, 1024);
         c->tune.overlap = env_int("SOLB_OVERLAP", c->tune.overlap, 1, WF_MAX_PARTS);
+        c->tune.pool = env_int("SOLB_POOL", c->tune.pool, 0, 1);
+        c->tune.pool_ctas_per_sm = env_int("SOLB_POOL_CTAS_PER_SM", c->tune.pool_ctas_per_sm, 1, 6);
+        c->tune.pool_refill = env_int("SOLB_POOL_REFILL", c->tune.pool_refill, 1, 64);
         c->tune.ctas_per_sm_overlap = env_int("SOLB_CTAS_PER_SM_OVERLAP", c->tune.ctas_per_sm_overlap, 1, 16);
     }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
@@ -157,6 +161,7 @@ static void free_wavefront(solb_ctx *c) {
         cudaFree(c->part_queue[k][0]); cudaFree(c->part_queue[k][1]); cudaFree(c->part_counters[k]);
         c->part_queue[k][0] = c->part_queue[k][1] = nullptr; c->part_counters[k] = nullptr;
     }
+    for (int k = 0; k < WF_MAX_PARTS; k++) { cudaFree(c->part_spill[k]); c->part_spill[k] = nullptr; }
     w = WavefrontState{};
 }
 
@@ -569,6 +574,8 @@ static int ensure_wavefront(solb_ctx *ctx, uint32_t n_pixels) {
         }
     }
     if (!ctx->ev_fork) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    if (ctx->tune.pool)
+        for (int k = 0; k < WF_MAX_PARTS; k++) CU(ctx, cudaMalloc((void **)&ctx->part_spill[k], pool_spill_bytes(ctx->sm_count, ctx->tune)));
     w.capacity = n_pixels;
     return SOLB_OK;
 }
@@ -617,6 +624,7 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
         WavefrontLaunch L;
         L.stream[0] = ctx->stream;
         L.fork = ctx->ev_fork;
+        for (int k = 0; k < WF_MAX_PARTS; k++) L.spill[k] = ctx->part_spill[k];
         L.ws[0] = ctx->ws;
         for (int k = 1; k < WF_MAX_PARTS; k++) {
             L.stream[k] = ctx->part_stream[k];

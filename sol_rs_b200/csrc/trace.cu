@@ -335,6 +335,177 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Ray-pool traversal kernel.  k_wf_trace binds one ray to one lane, so a lane idles whenever the warp's vote
+// picks the step type its ray does not need (measured: 20 of 32 lanes in node steps, 16.5 in triangle steps,
+// profiles/r01_ncu_k_wf_trace_c.txt).  Here every warp owns PL_SLOTS rays whose traversal state lives in
+// shared memory (SoA over slots); three warp-uniform 64-bit masks say which slots are free, need a node step,
+// or need a triangle step.  Each iteration the warp picks the fuller class and hands its slots to lanes
+// (lane i takes the i-th set bit), so node / triangle / ray-setup steps all run with (nearly) full warps.
+constexpr int PL_SLOTS = 64;   // rays per warp
+constexpr int PL_STACK = 4;    // stack entries per slot kept in shared memory
+constexpr int PL_SPILL = 60;   // further entries per slot in global memory
+constexpr int PL_WARPS = TRACE_BLOCK / 32;
+enum { PL_NODE = 1, PL_TRI = 2, PL_FREE = 4 };
+
+struct PoolWarp {
+    float ox[PL_SLOTS], oy[PL_SLOTS], oz[PL_SLOTS], dx[PL_SLOTS], dy[PL_SLOTS], dz[PL_SLOTS];
+    float tmax[PL_SLOTS];
+    uint32_t pixel[PL_SLOTS], hit_inst[PL_SLOTS], hit_gtri[PL_SLOTS];
+    float hit_u[PL_SLOTS], hit_v[PL_SLOTS];
+    uint32_t ngx[PL_SLOTS], ngy[PL_SLOTS], tgx[PL_SLOTS], tgy[PL_SLOTS];
+    uint2 stack[PL_STACK][PL_SLOTS];
+    uint8_t sp[PL_SLOTS];
+    uint8_t status[PL_SLOTS];  // PL_NODE | PL_TRI, or PL_FREE
+    uint8_t assign[32];        // slot handled by lane i in the current step
+};
+
+struct PoolStack {
+    PoolWarp *P;
+    uint2 *spill;  // this slot's global spill area
+    int slot, sp;
+    __device__ __forceinline__ void push(uint2 v) {
+        if (sp < PL_STACK) P->stack[sp][slot] = v;
+        else if (sp < PL_STACK + PL_SPILL) spill[sp - PL_STACK] = v;
+        sp++;
+    }
+    __device__ __forceinline__ uint2 pop() {
+        sp--;
+        return sp < PL_STACK ? P->stack[sp][slot] : spill[sp - PL_STACK];
+    }
+    __device__ __forceinline__ bool empty() const { return sp == 0; }
+};
+
+// Hand the first `cnt` slots of class mask (lo | hi << 32) to lanes 0..cnt-1: every lane looks at its own two slots
+// (lane, lane + 32), computes their rank inside the class with a prefix popcount and scatters them through
+// shared memory.  Returns this lane's slot or -1.
+__device__ __forceinline__ int pool_assign(PoolWarp &P, uint32_t lo, uint32_t hi, int cnt, int lane, uint32_t lt_mask) {
+    const int r0 = __popc(lo & lt_mask), r1 = __popc(lo) + __popc(hi & lt_mask);
+    if (((lo >> lane) & 1u) && r0 < cnt) P.assign[r0] = (uint8_t)lane;
+    if (((hi >> lane) & 1u) && r1 < cnt) P.assign[r1] = (uint8_t)(lane + 32);
+    __syncwarp();
+    const int slot = lane < cnt ? (int)P.assign[lane] : -1;
+    __syncwarp();
+    return slot;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace_pool(const FrameConsts fc, const uint4 *__restrict__ nodes,
+                                                               const float4 *__restrict__ tris, WavefrontState ws, int qi,
+                                                               unsigned long long *stats, const TraceTuning tune, uint2 *spill_base) {
+    __shared__ PoolWarp s_pool[PL_WARPS];
+    PoolWarp &P = s_pool[threadIdx.x >> 5];
+    const uint32_t n = ws.counters[qi];
+    const uint32_t *__restrict__ queue = qi ? ws.queue[1] : ws.queue[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters[qi ^ 1] = 0;  // next wave's output queue
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const size_t gwarp = (size_t)blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
+    uint2 *warp_spill = spill_base + gwarp * (size_t)(PL_SLOTS * PL_SPILL);
+    uint32_t nr = 0;
+    TraceCounters ctr = { 0, 0 };
+    P.status[lane] = PL_FREE;
+    P.status[lane + 32] = PL_FREE;
+    __syncwarp();
+    bool exhausted = false;
+    for (;;) {
+        // ---- slot classes from the per-slot status bytes (each lane reports its two slots) ----
+        const uint32_t st0 = P.status[lane], st1 = P.status[lane + 32];
+        const uint32_t node_lo = __ballot_sync(0xffffffffu, st0 & PL_NODE), node_hi = __ballot_sync(0xffffffffu, st1 & PL_NODE);
+        const uint32_t tri_lo = __ballot_sync(0xffffffffu, st0 & PL_TRI), tri_hi = __ballot_sync(0xffffffffu, st1 & PL_TRI);
+        const uint32_t free_lo = __ballot_sync(0xffffffffu, st0 & PL_FREE), free_hi = __ballot_sync(0xffffffffu, st1 & PL_FREE);
+        const int nn = __popc(node_lo) + __popc(node_hi), nt = __popc(tri_lo) + __popc(tri_hi);
+        const int nfree = __popc(free_lo) + __popc(free_hi);
+        // ---- ray setup step: fill free slots from the queue ----
+        if (!exhausted && (nfree >= tune.pool_refill || nn + nt == 0)) {
+            const int want = nfree < 32 ? nfree : 32;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ws.counters[2], (uint32_t)want);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int got = base >= n ? 0 : (int)min((uint32_t)want, n - base);
+            if (got < want) exhausted = true;
+            const int slot = pool_assign(P, free_lo, free_hi, got, lane, lt_mask);
+            if (slot >= 0) {
+                const uint32_t pixel = queue[base + lane];
+                const float4 o = ws.ray_o[pixel], d = ws.ray_d[pixel];
+                P.ox[slot] = o.x; P.oy[slot] = o.y; P.oz[slot] = o.z;
+                P.dx[slot] = d.x; P.dy[slot] = d.y; P.dz[slot] = d.z;
+                P.tmax[slot] = fc.tmax;
+                P.pixel[slot] = pixel;
+                P.hit_inst[slot] = SOLB_MISS; P.hit_gtri[slot] = SOLB_MISS; P.hit_u[slot] = 0.0f; P.hit_v[slot] = 0.0f;
+                P.ngx[slot] = 0u; P.ngy[slot] = 0x80000000u;  // SOLB_ROOT_GROUP
+                P.tgx[slot] = 0u; P.tgy[slot] = 0u;
+                P.sp[slot] = 0;
+                P.status[slot] = PL_NODE;
+                nr++;
+            }
+            __syncwarp();
+            if (got > 0) continue;  // re-read the classes
+        }
+        if (nn + nt == 0) break;  // nothing in flight, nothing left to fetch
+        // ---- pick the fuller class and hand its slots to lanes ----
+        const bool do_tri = nt > 0 && (nt * tune.tri_weight >= nn * tune.node_weight || nt >= 32);
+        const int cnt = do_tri ? (nt < 32 ? nt : 32) : (nn < 32 ? nn : 32);
+        const int slot = pool_assign(P, do_tri ? tri_lo : node_lo, do_tri ? tri_hi : node_hi, cnt, lane, lt_mask);
+        if (slot >= 0) {
+            PoolStack stack;
+            stack.P = &P;
+            stack.slot = slot;
+            stack.spill = warp_spill + (size_t)slot * PL_SPILL;
+            stack.sp = P.sp[slot];
+            uint2 ngroup = make_uint2(P.ngx[slot], P.ngy[slot]);
+            uint2 tgroup = make_uint2(P.tgx[slot], P.tgy[slot]);
+            TravRay tr;
+            tr.o = f3(P.ox[slot], P.oy[slot], P.oz[slot]);
+            tr.d = f3(P.dx[slot], P.dy[slot], P.dz[slot]);
+            tr.tmin = fc.tmin;
+            if (do_tri) {
+                tr.frame = make_ray_frame(tr.d);
+                float tmax = P.tmax[slot];
+                Hit hit;
+                hit.inst = SOLB_MISS;
+                trav_tri_step(tris, tr, tmax, tgroup, hit);
+                if (STATS) ctr.tris++;
+                if (hit.inst != SOLB_MISS) {
+                    P.tmax[slot] = tmax;
+                    P.hit_inst[slot] = hit.inst; P.hit_gtri[slot] = hit.gtri; P.hit_u[slot] = hit.u; P.hit_v[slot] = hit.v;
+                }
+            } else {
+                tr.idir = f3(safe_rcp_dir(tr.d.x), safe_rcp_dir(tr.d.y), safe_rcp_dir(tr.d.z));
+                const uint32_t oct = (tr.d.x < 0.0f ? 4u : 0u) | (tr.d.y < 0.0f ? 2u : 0u) | (tr.d.z < 0.0f ? 1u : 0u);
+                tr.oct_inv4 = (7u - oct) * 0x01010101u;
+                if (tgroup.y) stack.push(tgroup);  // postpone the pending triangles
+                trav_node_step(nodes, tr, P.tmax[slot], ngroup, tgroup, stack);
+                if (STATS) ctr.nodes++;
+            }
+            // nothing in hand: pop, or finish the ray
+            uint32_t status = 0;
+            if (!(ngroup.y & 0xff000000u) && !tgroup.y) {
+                if (stack.empty()) {
+                    ws.hit[P.pixel[slot]] = make_uint4(P.hit_inst[slot], P.hit_gtri[slot], __float_as_uint(P.hit_u[slot]),
+                                                       __float_as_uint(P.hit_v[slot]));
+                    status = PL_FREE;
+                } else {
+                    const uint2 e = stack.pop();
+                    if (e.y & 0xff000000u) ngroup = e; else tgroup = e;
+                }
+            }
+            if (ngroup.y & 0xff000000u) status |= PL_NODE;
+            if (tgroup.y) status |= PL_TRI;
+            P.ngx[slot] = ngroup.x; P.ngy[slot] = ngroup.y;
+            P.tgx[slot] = tgroup.x; P.tgy[slot] = tgroup.y;
+            P.sp[slot] = (uint8_t)stack.sp;
+            P.status[slot] = (uint8_t)status;
+        }
+        __syncwarp();
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    if (STATS) {
+        warp_add_stat(stats, ST_NODES, ctr.nodes);
+        warp_add_stat(stats, ST_TRIS, ctr.tris);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_wf_shade(const FrameConsts fc, const DeviceInstance *__restrict__ instances,
                                                   const ShadeRecord *__restrict__ shade, WavefrontState ws, int qi,
                                                   unsigned long long *stats) {
@@ -606,7 +777,11 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
                 }
                 cudaEventRecord((*events)[*n_events_used], st);
             }
-            if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune);
+            if (tune.pool && L.spill[k]) {
+                const int pool_grid = L.sm_count * tune.pool_ctas_per_sm;
+                if (collect) k_wf_trace_pool<true><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
+                else k_wf_trace_pool<false><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
+            } else if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune);
             else k_wf_trace<false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune);
             if (events) {
                 cudaEventRecord((*events)[*n_events_used + 1], st);
@@ -637,6 +812,10 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
         if ((err = cudaStreamWaitEvent(L.stream[0], L.join[k], 0)) != cudaSuccess) return err;
     }
     return cudaGetLastError();
+}
+
+size_t pool_spill_bytes(int sm_count, const TraceTuning &tune) {
+    return (size_t)sm_count * tune.pool_ctas_per_sm * PL_WARPS * PL_SLOTS * PL_SPILL * sizeof(uint2);
 }
 
 }  // namespace solb

@@ -29,6 +29,9 @@ struct TraceTuning {
     int overlap = 3;       // frame parts (1..4) run as independent wave sequences on their own streams, so the drain tail of one
                            // part's persistent trace kernel and its memory-bound shade kernel overlap another part's traversal
     int ctas_per_sm_overlap = 5;  // persistent CTAs per SM and part when overlapping
+    int pool = 0;              // 1: ray-pool traversal kernel (k_wf_trace_pool) instead of the lane-bound k_wf_trace
+    int pool_ctas_per_sm = 6;  // its persistent CTAs per SM (34 KB shared memory each)
+    int pool_refill = 16;      // refill free slots once this many of a warp's 64 are free
 };
 
 constexpr int WF_MAX_PARTS = 4;
@@ -36,6 +39,7 @@ struct WavefrontLaunch {
     cudaStream_t stream[WF_MAX_PARTS];   // [0] = the ctx stream; others may be null: no overlap
     cudaEvent_t fork, join[WF_MAX_PARTS];
     WavefrontState ws[WF_MAX_PARTS];     // same per-pixel state arrays, separate queues + counters
+    uint2 *spill[WF_MAX_PARTS];          // per-part global stack spill of the ray-pool kernel (null: kernel unavailable)
     uint32_t *host_counts;               // pinned, WF_MAX_PARTS entries
     int sm_count;
 };
@@ -55,6 +59,7 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
                       unsigned long long *stats);
+size_t pool_spill_bytes(int sm_count, const TraceTuning &tune);
 cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n);
 
 }  // namespace solb
