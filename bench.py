@@ -275,8 +275,14 @@ def main():
         avg_launch_ms = st2.trace_kernel_ms_total / max(st2.trace_kernel_launches, 1)
         achieved = b_ray * rays_per_launch / (avg_launch_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak_gbs()
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f)[kernel]["dram_bytes_per_launch"]  # from the committed ncu --set full capture
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
+                    "traffic": traffic, "algorithmic_bytes_per_launch": b_ray * rays_per_launch, "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
                     "p_hit": p_hit, "rays_per_path": r_path, "avg_launch_ms": avg_launch_ms,
                     "launches_timed": int(st2.trace_kernel_launches),
                     "kernel_share_of_step": st2.trace_kernel_ms_total / max(sum(main_run["step_ms"][:3]), 1e-9) if steps >= 3 else None,
