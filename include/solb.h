@@ -224,6 +224,9 @@ SOLB_API int solb_trace_debug(solb_scene *scene, const SolbSceneUniforms *unifor
  * rays[i] = {ox,oy,oz,tmin, dx,dy,dz,tmax}; hits[i] = {instance, primitive, bits(u), bits(v)}; t optional. */
 SOLB_API int solb_trace_rays(solb_scene *scene, const float *rays, uint32_t n, uint32_t *hits, float *t_out);
 
+/* test hook: the builder's onesweep radix sort on host (u64 key, u32 value) pairs, in place */
+SOLB_API int solb_test_sort_pairs(solb_ctx *ctx, uint64_t *keys, uint32_t *values, uint32_t n, int key_bits);
+
 /* ---- multi-GPU resolve: out = sum.xyz / sum.w with the reference's display transform ---- */
 /* accum_out RGBA32F (may alias sum), render RGBA8 (may be NULL). */
 SOLB_API int solb_resolve_sum(solb_ctx *ctx, solb_target *sum, solb_target *accum_out, solb_target *render);

@@ -109,6 +109,7 @@ SYMBOLS = {
     "solb_trace_debug": (_i, [_vp, ctypes.POINTER(SceneUniforms), _vp, _vp, _vp]),
     "solb_trace_rays": (_i, [_vp, _vp, _u32, _vp, _vp]),
     "solb_resolve_sum": (_i, [_vp, _vp, _vp, _vp]),
+    "solb_test_sort_pairs": (_i, [_vp, _vp, _vp, _u32, _i]),
 }
 
 _LIB = None

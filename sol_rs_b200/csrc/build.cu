@@ -99,63 +99,64 @@ __global__ void k_morton(const float4 *prim_lo, const float4 *prim_hi, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, (u64 key, u32 value).  Per pass: tile histograms -> exclusive scan
-// (digit-major) -> stable scatter with warp match-any ranking (the ranking scheme of onesweep,
-// Adinets & Merrill 2022, without the chained look-back yet).
+// Onesweep LSD radix sort (Adinets & Merrill 2022), 8-bit digits, (u64 key, u32 value).
+//   k_os_hist : ONE pass over the keys builds the digit histograms of all 8 passes
+//   k_os_scan : exclusive scan of each pass's 256 bins -> global digit bases
+//   k_os_pass : one kernel per digit pass; each tile ranks its keys (warp match-any multi-split), then resolves
+//               its per-digit exclusive prefix over all earlier tiles with a chained decoupled look-back instead
+//               of a separate scan kernel: keys are read once and written once per pass.
 constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 8;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_PASSES = 8;
+constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_INC = 2u << 30, OS_VALUE = (1u << 30) - 1u;
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t *keys, uint32_t n, int shift, uint32_t *tile_hist,
-                                                        uint32_t num_tiles) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(RS_THREADS) k_os_hist(const uint64_t *keys, uint32_t n, uint32_t *hist /*[8][256]*/) {
+    __shared__ uint32_t h[RS_PASSES][256];
+    for (int i = threadIdx.x; i < RS_PASSES * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * RS_TILE;
+    for (uint32_t i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) {
+        const uint64_t k = keys[i];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
-        const uint32_t idx = base + i * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & 0xffu], 1u);
+        for (int p = 0; p < RS_PASSES; p++) atomicAdd(&h[p][(uint32_t)(k >> (8 * p)) & 0xffu], 1u);
     }
     __syncthreads();
-    tile_hist[threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
-}
-
-// single-block exclusive scan of m elements (m = 256 * num_tiles), in place
-__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t *data, uint32_t m) {
-    __shared__ uint32_t partial[1024];
-    const uint32_t chunk = (m + 1023u) / 1024u;
-    const uint32_t begin = min(threadIdx.x * chunk, m), end = min(begin + chunk, m);
-    uint32_t sum = 0;
-    for (uint32_t i = begin; i < end; i++) sum += data[i];
-    partial[threadIdx.x] = sum;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int off = 1; off < 1024; off <<= 1) {
-        uint32_t v = (threadIdx.x >= (uint32_t)off) ? partial[threadIdx.x - off] : 0u;
-        __syncthreads();
-        partial[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t run = threadIdx.x ? partial[threadIdx.x - 1] : 0u;
-    for (uint32_t i = begin; i < end; i++) {
-        const uint32_t v = data[i];
-        data[i] = run;
-        run += v;
+    for (int i = threadIdx.x; i < RS_PASSES * 256; i += RS_THREADS) {
+        const uint32_t v = (&h[0][0])[i];
+        if (v) atomicAdd(&hist[i], v);
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
-                                                           uint32_t *vals_out, uint32_t n, int shift,
-                                                           const uint32_t *tile_offsets, uint32_t num_tiles) {
+// block p scans the 256 bins of pass p (exclusive), in place
+__global__ void __launch_bounds__(256) k_os_scan(uint32_t *hist) {
+    __shared__ uint32_t s[256];
+    uint32_t *h = hist + blockIdx.x * 256;
+    const uint32_t v = h[threadIdx.x];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        const uint32_t t = threadIdx.x >= (uint32_t)off ? s[threadIdx.x - off] : 0u;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    h[threadIdx.x] = s[threadIdx.x] - v;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                                                        uint32_t *vals_out, uint32_t n, int shift, const uint32_t *digit_base,
+                                                        uint32_t *status /*[tiles][256], zero*/, uint32_t *tile_counter) {
     __shared__ uint32_t warp_hist[RS_WARPS][256];
-    __shared__ uint32_t digit_base[256];
+    __shared__ uint32_t digit_off[256];
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);  // tile ids in start order: look-back never waits on an unstarted tile
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
     __syncthreads();
+    const uint32_t tile = s_tile;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t chunk_base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+    const uint32_t chunk_base = tile * RS_TILE + warp * (32 * RS_ITEMS);
     uint64_t key[RS_ITEMS];
     uint32_t val[RS_ITEMS], rank[RS_ITEMS], dig[RS_ITEMS];
 #pragma unroll
@@ -180,40 +181,69 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t *keys_
     __syncthreads();
     {
         const uint32_t d = threadIdx.x;
-        uint32_t run = 0;
+        uint32_t count = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             const uint32_t c = warp_hist[w][d];
-            warp_hist[w][d] = run;
-            run += c;
+            warp_hist[w][d] = count;
+            count += c;
         }
-        digit_base[d] = tile_offsets[d * num_tiles + blockIdx.x];
+        // chained scan with decoupled look-back over earlier tiles, one chain per digit
+        volatile uint32_t *st = status;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st[d] = count | OS_FLAG_INC;
+        } else {
+            st[(size_t)tile * 256 + d] = count | OS_FLAG_AGG;
+            __threadfence();
+            for (int64_t t = (int64_t)tile - 1;;) {
+                const uint32_t v = st[(size_t)t * 256 + d];
+                const uint32_t f = v & ~OS_VALUE;
+                if (f == OS_FLAG_INC) { excl += v & OS_VALUE; break; }
+                if (f == OS_FLAG_AGG) { excl += v & OS_VALUE; t--; }
+                // else: that tile has not published yet - spin
+            }
+            st[(size_t)tile * 256 + d] = ((excl + count) & OS_VALUE) | OS_FLAG_INC;
+        }
+        __threadfence();
+        digit_off[d] = digit_base[d] + excl;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         if (dig[j] < 0x100u) {
-            const uint32_t pos = digit_base[dig[j]] + warp_hist[warp][dig[j]] + rank[j];
+            const uint32_t pos = digit_off[dig[j]] + warp_hist[warp][dig[j]] + rank[j];
             keys_out[pos] = key[j];
             vals_out[pos] = val[j];
         }
     }
 }
 
-// sorts (keys, vals) in place; tmp buffers must hold n elements each.  key_bits: number of low bits that vary.
+// sorts (keys, vals) in place; tmp buffers hold n elements each; scratch holds onesweep_scratch_words(n) u32.
+static size_t onesweep_scratch_words(uint32_t n) {
+    const size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    return RS_PASSES * 256 + 8 + tiles * 256;
+}
 static cudaError_t radix_sort_pairs(cudaStream_t st, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
-                                    uint32_t n, int key_bits, uint32_t *tile_hist, uint64_t *launches) {
+                                    uint32_t n, int key_bits, uint32_t *scratch, uint64_t *launches) {
     const uint32_t num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t *hist = scratch, *tile_counter = scratch + RS_PASSES * 256, *status = scratch + RS_PASSES * 256 + 8;
+    cudaError_t err = cudaMemsetAsync(scratch, 0, (RS_PASSES * 256 + 8) * sizeof(uint32_t), st);
+    if (err != cudaSuccess) return err;
+    const uint32_t hist_blocks = std::min<uint32_t>(num_tiles, 148u * 8u);
+    k_os_hist<<<hist_blocks, RS_THREADS, 0, st>>>(keys, n, hist);
+    k_os_scan<<<RS_PASSES, 256, 0, st>>>(hist);
+    *launches += 2;
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     int passes = (key_bits + 7) / 8;
     if (passes & 1) passes++;  // even number of passes so the result lands back in (keys, vals)
+    if (passes > RS_PASSES) passes = RS_PASSES;
     for (int p = 0; p < passes; p++) {
-        const int shift = 8 * p;
-        k_rs_hist<<<num_tiles, RS_THREADS, 0, st>>>(kin, n, shift, tile_hist, num_tiles);
-        k_rs_scan<<<1, 1024, 0, st>>>(tile_hist, 256u * num_tiles);
-        k_rs_scatter<<<num_tiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, tile_hist, num_tiles);
-        *launches += 3;
+        if ((err = cudaMemsetAsync(status, 0, (size_t)num_tiles * 256 * sizeof(uint32_t), st)) != cudaSuccess) return err;
+        if ((err = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st)) != cudaSuccess) return err;
+        k_os_pass<<<num_tiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, 8 * p, hist + 256 * p, status, tile_counter);
+        *launches += 1;
         std::swap(kin, kout);
         std::swap(vin, vout);
     }
@@ -528,7 +558,7 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
     CK(salloc(st, &keys_tmp, n));
     CK(salloc(st, &vals, n));
     CK(salloc(st, &vals_tmp, n));
-    CK(salloc(st, &tile_hist, 256 * (size_t)((n + RS_TILE - 1) / RS_TILE)));
+    CK(salloc(st, &tile_hist, onesweep_scratch_words(n)));
     k_morton<<<nb, T, 0, st>>>(prim_lo, prim_hi, n, bounds, keys, vals);
     *launches += 1;
     CK(radix_sort_pairs(st, keys, vals, keys_tmp, vals_tmp, n, 63, tile_hist, launches));
@@ -622,7 +652,7 @@ cudaError_t sort_pairs_device(cudaStream_t st, uint64_t *keys, uint32_t *vals, u
     if (n == 0) return cudaSuccess;
     CK(dalloc(&kt, n));
     CK(dalloc(&vt, n));
-    CK(dalloc(&th, 256 * (size_t)((n + RS_TILE - 1) / RS_TILE)));
+    CK(dalloc(&th, onesweep_scratch_words(n)));
     CK(radix_sort_pairs(st, keys, vals, kt, vt, n, key_bits, th, &launches));
     CK(cudaStreamSynchronize(st));
 done:

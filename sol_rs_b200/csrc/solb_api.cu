@@ -739,6 +739,27 @@ SOLB_API int solb_trace_rays(solb_scene *s, const float *rays, uint32_t n, uint3
     SOLB_CATCH(ctx)
 }
 
+SOLB_API int solb_test_sort_pairs(solb_ctx *ctx, uint64_t *keys, uint32_t *values, uint32_t n, int key_bits) {
+    if (!ctx || ((!keys || !values) && n)) return fail(ctx, SOLB_ERR_INVALID, "solb_test_sort_pairs: null argument");
+    if (n == 0) return SOLB_OK;
+    if (key_bits < 1 || key_bits > 64) return fail(ctx, SOLB_ERR_INVALID, "key_bits must be 1..64");
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint64_t *dk = nullptr;
+    uint32_t *dv = nullptr;
+    struct Free { void *a, *b; ~Free() { cudaFree(a); cudaFree(b); } } fr{ nullptr, nullptr };
+    CU(ctx, cudaMalloc((void **)&dk, (size_t)n * 8));
+    fr.a = dk;
+    CU(ctx, cudaMalloc((void **)&dv, (size_t)n * 4));
+    fr.b = dv;
+    CU(ctx, cudaMemcpyAsync(dk, keys, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(dv, values, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, sort_pairs_device(ctx->stream, dk, dv, n, key_bits));
+    CU(ctx, cudaMemcpyAsync(keys, dk, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(values, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOLB_OK;
+}
+
 SOLB_API int solb_resolve_sum(solb_ctx *ctx, solb_target *sum, solb_target *accum_out, solb_target *render) {
     if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
     int rc;

@@ -467,3 +467,31 @@ def test_cpp_host_example_runs_the_reference_call_sequence(sol, ctx):
     # error behaviour: the reference panics without --model
     bad = subprocess.run([exe], capture_output=True, text=True, cwd=ROOT, timeout=60)
     assert bad.returncode != 0 and "no gltf file given" in bad.stderr
+
+
+@pytest.mark.parametrize("n,bits,kind", [(1, 63, "random"), (31, 63, "random"), (2048, 63, "random"), (2049, 63, "random"),
+                                         (100_000, 63, "random"), (1_000_003, 63, "random"), (300_000, 63, "equal"),
+                                         (300_000, 63, "sorted"), (300_000, 63, "reversed"), (300_000, 16, "fewbits"),
+                                         (5_000_000, 63, "random")])
+def test_onesweep_sort(sol, ctx, n, bits, kind):
+    """The builder's onesweep radix sort: sorted by key, stable (values of equal keys keep their input order)."""
+    from sol_rs_b200 import _native as N
+
+    rng = np.random.default_rng(n + bits)
+    if kind == "equal":
+        keys = np.full(n, 0x1234567890ABCDEF & ((1 << 63) - 1), dtype=np.uint64)
+    elif kind == "sorted":
+        keys = np.sort(rng.integers(0, 1 << 63, size=n, dtype=np.uint64))
+    elif kind == "reversed":
+        keys = np.sort(rng.integers(0, 1 << 63, size=n, dtype=np.uint64))[::-1].copy()
+    elif kind == "fewbits":
+        keys = rng.integers(0, 1 << 10, size=n, dtype=np.uint64)  # many duplicates
+    else:
+        keys = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = keys.copy(), vals.copy()
+    N.check(N.lib().solb_test_sort_pairs(ctx.handle, k.ctypes.data_as(ctypes.c_void_p), v.ctypes.data_as(ctypes.c_void_p), n, bits),
+            ctx.handle)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order])
+    assert np.array_equal(v, vals[order])
