@@ -135,6 +135,9 @@ def main():
     ap.add_argument("--schedule", default=os.environ.get("SOLB_SCHEDULE", "wavefront"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also bench cornell and the other schedule")
+    ap.add_argument("--workload", default="tunnel", choices=["tunnel", "synth"],
+                    help="tunnel = the headline config; synth = BASELINE configs[4]: synthetic instanced scene (--blas x 20000 triangles)")
+    ap.add_argument("--blas", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -153,6 +156,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its version banner on stdout, which must carry exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -167,7 +173,12 @@ def main():
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def setup(model, sky):
-        sc = scene.load_scene(ctx, os.path.join(ROOT, "assets", "models", model))
+        if model == "synth":
+            from sol_rs_b200 import synth
+
+            sc = synth.make_scene(args.blas, 100)
+        else:
+            sc = scene.load_scene(ctx, os.path.join(ROOT, "assets", "models", model))
         sd = ray.SceneDescription.from_scene(ctx, sc)
         cam = sc.camera
         cam.set_window_size((WIDTH, HEIGHT))
@@ -230,7 +241,11 @@ def main():
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
         return float(t.item()), int(r.item())
 
-    sc, sd, cam, sbt = setup("tunnel.gltf", True)
+    sc, sd, cam, sbt = setup("synth" if args.workload == "synth" else "tunnel.gltf", True)
+    build_ms = ctx.stats().last_build_ms
+    workload = WORKLOAD if args.workload == "tunnel" else (
+        "5-pathtrace synthetic %d BLAS x 20000 triangles (seed 0xB200) --sky %dx%d, %d spp/frame, max_bounces %d" % (
+            args.blas, WIDTH, HEIGHT, SPP, MAX_BOUNCES))
     mode = N.ACCUM_SUM if world > 1 else N.ACCUM_MIX
 
     clocks = ClockSampler(local_rank)
@@ -325,7 +340,7 @@ def main():
                     extra["cornell_1080p_b8_" + name] = {"Mrays_s": rc["rays"] / (rc["ms_total"] * 1e-3) / 1e6,
                                                          "ms_per_step": rc["ms_total"] / min(steps, 6),
                                                          "rays_per_path": rc["rays"] / max(rc["paths"], 1)}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "tunnel":
             cb = cpu_reference_arm(2, 0, (CPU_SAMPLE_W, CPU_SAMPLE_H))
             cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -333,7 +348,7 @@ def main():
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "schedule": "megakernel" if sched else "wavefront",
+                "config": {"workload": workload, "schedule": "megakernel" if sched else "wavefront", "bvh_build_ms": build_ms,
                            "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * world),
                            "l2": "256 MB buffer written between timed steps (outside the per-step event pairs)",
                            "multi_gpu": "frames f = rank (mod N) per rank, local sums, one NCCL reduce + resolve inside the timed region"

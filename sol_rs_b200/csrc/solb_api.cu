@@ -330,6 +330,9 @@ static int do_build(solb_scene *s) {
     solb_ctx *ctx = s->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     BuildOptions opt;
+    // Treelet passes cost ~12 ns/triangle each on big scenes (244 ms per pass at 20 M) for a few % of trace speed there:
+    // one pass above 4 M triangles, two below (profiles/r01_configs.jsonl).
+    if (s->n_tris > (4u << 20)) opt.treelet_passes = 1;
     if (const char *v = getenv("SOLB_TREELET_PASSES")) opt.treelet_passes = std::max(0, std::min(8, atoi(v)));
     if (const char *v = getenv("SOLB_TREELET_COOP")) opt.coop_treelet = atoi(v) != 0;
     if (const char *v = getenv("SOLB_TREELET_GAMMA")) opt.treelet_gamma = std::max(3, std::min(1 << 20, atoi(v)));
