@@ -7,6 +7,6 @@ CUDA, include/solb.h).  No CPU fallback: importing works anywhere, creating a Co
 from . import _native  # noqa: F401
 from ._native import SolbError  # noqa: F401
 from .context import Context, Image2d  # noqa: F401
-from . import scene, ray, util  # noqa: F401
+from . import scene, ray, util, multigpu, io  # noqa: F401
 
-__all__ = ["Context", "Image2d", "SolbError", "scene", "ray", "util"]
+__all__ = ["Context", "Image2d", "SolbError", "scene", "ray", "util", "multigpu", "io"]

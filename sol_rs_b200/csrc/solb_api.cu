@@ -137,6 +137,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.ctas_per_sm = env_int("SOLB_CTAS_PER_SM", c->tune.ctas_per_sm, 1, 16);
         c->tune.check_every = env_int("SOLB_CHECK_EVERY", c->tune.check_every, 1, 1024);
         c->tune.overlap = env_int("SOLB_OVERLAP", c->tune.overlap, 1, WF_MAX_PARTS);
+        c->tune.sort_shade = env_int("SOLB_SORT_SHADE", c->tune.sort_shade, 0, 1);
         c->tune.pool = env_int("SOLB_POOL", c->tune.pool, 0, 1);
         c->tune.pool_ctas_per_sm = env_int("SOLB_POOL_CTAS_PER_SM", c->tune.pool_ctas_per_sm, 1, 6);
         c->tune.pool_refill = env_int("SOLB_POOL_REFILL", c->tune.pool_refill, 1, 64);

@@ -242,8 +242,11 @@ __global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, Wavef
 // warp takes rays from the global queue in batches of WF_BATCH to keep the single atomic counter cold.
 constexpr uint32_t WF_BATCH = 128;
 
+#ifndef SOLB_WF_MIN_CTAS
+#define SOLB_WF_MIN_CTAS 7
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
+__global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                           const float4 *__restrict__ tris, WavefrontState ws, int qi,
                                                           unsigned long long *stats, const TraceTuning tune) {
     SOLB_DECL_STACK();
@@ -506,22 +509,54 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace_pool(const FrameConsts
     }
 }
 
+// SORT: material-sorted shading.  Each block takes 256 queue entries, classifies their hit records (miss /
+// emissive / surface material bucket) and counting-sorts the entries by class in shared memory before shading, so
+// the lanes of a warp run the same rmiss / emissive / BRDF path of pathtrace.rchit.
+template <bool SORT>
 __global__ void __launch_bounds__(256) k_wf_shade(const FrameConsts fc, const DeviceInstance *__restrict__ instances,
                                                   const ShadeRecord *__restrict__ shade, WavefrontState ws, int qi,
                                                   unsigned long long *stats) {
+    __shared__ uint32_t s_count[8], s_perm[256];
     const uint32_t n = ws.counters[qi];
     const uint32_t *__restrict__ queue_in = ws.queue[qi];
     uint32_t *__restrict__ queue_out = ws.queue[qi ^ 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters[2] = 0;  // trace work head of the next wave
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t nh = 0, np = 0;
-    // grid-stride over warps so the ballot below always sees whole warps
-    const uint32_t n_round = (n + 31u) & ~31u;
+    // grid-stride over whole 256-entry chunks so the block-wide sort and the warp ballot always see whole blocks
+    const uint32_t n_round = (n + 255u) & ~255u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool alive = false;
         uint32_t p = 0;
-        if (i < n) {
-            p = queue_in[i];
+        bool have = i < n;
+        if (have) p = queue_in[i];
+        if (SORT) {
+            if (threadIdx.x < 8) s_count[threadIdx.x] = 0;
+            __syncthreads();
+            uint32_t cls = 7, rank = 0;
+            if (have) {
+                const uint32_t inst = ws.hit[p].x;
+                if (inst == SOLB_MISS) cls = 0;
+                else {
+                    const DeviceInstance &in = instances[inst];
+                    cls = (in.mat[4] >= 1.0f || in.mat[5] >= 1.0f || in.mat[6] >= 1.0f) ? 1u : 2u + in.material % 5u;
+                }
+                rank = atomicAdd(&s_count[cls], 1u);
+            }
+            __syncthreads();
+            if (have) {
+                uint32_t off = 0;
+                for (uint32_t c = 0; c < cls; c++) off += s_count[c];
+                s_perm[off + rank] = p;
+            }
+            __syncthreads();
+            uint32_t total = 0;
+            for (int c = 0; c < 7; c++) total += s_count[c];
+            have = threadIdx.x < total;
+            if (have) p = s_perm[threadIdx.x];
+            __syncthreads();
+        }
+        if (have) {
             const uint4 h = ws.hit[p];
             const float4 t4 = ws.thr[p], x4 = ws.pix[p];
             float3 thr = f3(t4.x, t4.y, t4.z), pixel = f3(x4.x, x4.y, x4.z);
@@ -787,7 +822,8 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
                 cudaEventRecord((*events)[*n_events_used + 1], st);
                 *n_events_used += 2;
             }
-            k_wf_shade<<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+            if (tune.sort_shade) k_wf_shade<true><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+            else k_wf_shade<false><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
             *launches += 2;
             qi[k] ^= 1;
         }

@@ -495,3 +495,31 @@ def test_onesweep_sort(sol, ctx, n, bits, kind):
     order = np.argsort(keys, kind="stable")
     assert np.array_equal(k, keys[order])
     assert np.array_equal(v, vals[order])
+
+
+def test_accumulation_checkpoint_resume(sol, ctx, tmp_path):
+    """frames 0..5 in one go == frames 0..2, checkpoint, restore, frames 3..5 (bit-identical)."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import io, ray, scene
+
+    w, h = 96, 64
+    sc, sd = _product(sol, ctx, "cornell")
+    cam = product_camera(sc, "cornell", w, h)
+    sbt = pathtrace_pipeline(ctx, False)
+
+    def run(accum, frames):
+        for f in frames:
+            sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, None, max_bounces=8), (w, h, 1))
+
+    full = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    run(full, range(6))
+    part = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    run(part, range(3))
+    io.save_checkpoint(str(tmp_path / "ck"), part, 0, 3)
+    restored, start, nxt = io.load_checkpoint(str(tmp_path / "ck"), ctx)
+    assert (start, nxt) == (0, 3)
+    run(restored, range(nxt, 6))
+    np.testing.assert_array_equal(restored.readback(), full.readback())
+    render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+    sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 6), restored, render, max_bounces=8), (w, h, 1))
+    io.write_png(str(tmp_path / "frame.png"), render.readback())

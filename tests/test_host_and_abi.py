@@ -161,3 +161,20 @@ def test_pipeline_selects_kernel_family():
         mk("cube")
     with pytest.raises(sol.SolbError):
         ray.ShaderBindingTable(None, mk("debug"), ray.ShaderBindingTableInfo().raygen(0).miss(1))
+
+
+def test_png_writer_roundtrip(tmp_path):
+    """Offscreen image writer (replaces blit-to-present): decodes back to the same pixels."""
+    import cv2
+    from sol_rs_b200 import io
+
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(37, 53, 4), dtype=np.uint8)
+    p = str(tmp_path / "f.png")
+    io.write_png(p, img)
+    back = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+    assert back is not None and back.shape == (37, 53, 4)
+    assert np.array_equal(back[..., [2, 1, 0, 3]], img)
+    io.write_ppm(str(tmp_path / "f.ppm"), img)
+    raw = open(str(tmp_path / "f.ppm"), "rb").read()
+    assert raw.startswith(b"P6\n53 37\n255\n") and len(raw) == 13 + 37 * 53 * 3
