@@ -138,7 +138,12 @@ def main():
     ap.add_argument("--workload", default="tunnel", choices=["tunnel", "synth"],
                     help="tunnel = the headline config; synth = BASELINE configs[4]: synthetic instanced scene (--blas x 20000 triangles)")
     ap.add_argument("--blas", type=int, default=1000)
+    ap.add_argument("--size", default="", help="WxH override, e.g. 3840x2160 for BASELINE configs[3] (default 1920x1080)")
     args = ap.parse_args()
+    global WIDTH, HEIGHT, WORKLOAD
+    if args.size:
+        WIDTH, HEIGHT = (int(v) for v in args.size.lower().split("x"))
+        WORKLOAD = "5-pathtrace tunnel.gltf --sky %dx%d, %d spp/frame, max_bounces %d" % (WIDTH, HEIGHT, SPP, MAX_BOUNCES)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -156,9 +161,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL print its version banner on stdout, which must carry exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner (NCCL_DEBUG >= VERSION) on stdout, which must carry exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -85,6 +85,31 @@ def main():
             sd = ray.SceneDescription.from_scene(ctx, sc)
             r = pathtrace(sd, sc.camera, 3840, 2160, True, 8, args.frames)
             print(json.dumps({"config": "5-pathtrace tunnel.gltf --sky 3840x2160 cap 8, 1 GPU", **r}), flush=True)
+        elif what == "converge":
+            # configs[2] in full: 512 frames x 8 spp = 4096 spp at 1920x1080, readback of the final frame only
+            sc = scene.load_scene(ctx, os.path.join(ROOT, "assets/models/tunnel.gltf"))
+            sd = ray.SceneDescription.from_scene(ctx, sc)
+            cam = sc.camera
+            w, h = 1920, 1080
+            cam.set_window_size((w, h))
+            accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+            render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+            sbt = pt_sbt(True)
+            ctx.reset_stats()
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for f in range(512):
+                sd.tlas_regenerate()
+                sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, render, max_bounces=8), (w, h, 1))
+            img = render.readback()
+            dt = time.time() - t0
+            st = ctx.stats()
+            from sol_rs_b200 import io
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            io.write_png(os.path.join(ROOT, "gpurun_out", "tunnel_1080p_4096spp.png"), img)
+            print(json.dumps({"config": "5-pathtrace tunnel.gltf --sky 1920x1080, 512 frames = 4096 spp, cap 8 (configs[2] in full)",
+                              "seconds": dt, "ms_per_frame": 1e3 * dt / 512, "Mrays_s": st.rays / dt / 1e6, "rays": int(st.rays),
+                              "mean_rgb": [float(v) for v in accum.readback()[..., :3].mean(axis=(0, 1))]}), flush=True)
         elif what == "cornell512":
             sc = scene.load_scene(ctx, os.path.join(ROOT, "assets/models/cornell.gltf"))
             sd = ray.SceneDescription.from_scene(ctx, sc)
