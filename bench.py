@@ -330,6 +330,12 @@ def main():
         e2e = {"value": st3.rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 400 + 32,
                "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": 1e3 * dt / n_e2e, "steps": n_e2e}
 
+        if world == 1 and args.workload == "tunnel" and not args.size:
+            # the metric names cornell beside tunnel: same resolution / spp / bounce cap, default (auto) schedule
+            _, sd_c, cam_c, sbt_c = setup("cornell.gltf", False)
+            rc = device_timed(sd_c, cam_c, sbt_c, N.SCHEDULE_AUTO, 3, min(steps, 8), N.ACCUM_MIX, 0)
+            extra["cornell_1080p_cap8"] = {"Mrays_s": rc["rays"] / (rc["ms_total"] * 1e-3) / 1e6, "ms_per_frame": rc["ms_total"] / min(steps, 8),
+                                           "rays_per_path": rc["rays"] / max(rc["paths"], 1), "schedule": "auto (megakernel: 3 wide nodes)"}
         if args.extra:
             other = N.SCHEDULE_WAVEFRONT if sched == N.SCHEDULE_MEGAKERNEL else N.SCHEDULE_MEGAKERNEL
             r2 = device_timed(sd, cam, sbt, other, 2, min(steps, 6), N.ACCUM_MIX, 0) if world == 1 else None

@@ -100,7 +100,9 @@ typedef enum SolbTargetFormat {
 
 typedef enum SolbSchedule {
     SOLB_SCHEDULE_WAVEFRONT = 0, /* queue-based wavefront: persistent trace kernel + shade/compact kernels */
-    SOLB_SCHEDULE_MEGAKERNEL = 1 /* one thread per pixel, flattened bounce loop                           */
+    SOLB_SCHEDULE_MEGAKERNEL = 1,/* one thread per pixel, flattened bounce loop                           */
+    SOLB_SCHEDULE_AUTO = 2       /* megakernel for tiny hierarchies (<= 8 wide nodes: no traversal divergence to
+                                    hide, queue traffic dominates), wavefront otherwise                      */
 } SolbSchedule;
 
 typedef enum SolbAccumMode {

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libsolb.so")
 
 SOLB_OK = 0
 FORMAT_RGBA32F, FORMAT_RGBA8, FORMAT_RG32UI = 0, 1, 2
-SCHEDULE_WAVEFRONT, SCHEDULE_MEGAKERNEL = 0, 1
+SCHEDULE_WAVEFRONT, SCHEDULE_MEGAKERNEL, SCHEDULE_AUTO = 0, 1, 2
 ACCUM_MIX, ACCUM_SUM = 0, 1
 MISS = 0xFFFFFFFF
 

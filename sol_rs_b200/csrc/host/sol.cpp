@@ -287,7 +287,7 @@ void ShaderBindingTable::cmd_trace_rays(const TraceBindings &b, Extent3D extent)
     p.enable_sky = enable_sky_ ? 1u : 0u;
     if (b.overrides.samples_per_frame) p.samples_per_frame = b.overrides.samples_per_frame;
     if (b.overrides.max_bounces) p.max_bounces = b.overrides.max_bounces;
-    p.schedule = b.overrides.schedule;
+    if (b.overrides.schedule) p.schedule = b.overrides.schedule;  // 0 keeps the default (AUTO)
     p.accum_mode = b.overrides.accum_mode;
     p.collect_stats = b.overrides.collect_stats;
     solb_scene *s = b.scene_description->handle();

@@ -521,7 +521,7 @@ SOLB_API void solb_trace_params_default(SolbTraceParams *p, int pipeline) {
     p->enable_sky = 0;
     p->samples_per_frame = pipeline == 1 ? 4u : 8u;  // ao.rgen:43 / pathtrace.rgen:44
     p->max_bounces = pipeline == 1 ? 4u : 32u;       // ao.rgen:42 / pathtrace.rgen:43
-    p->schedule = SOLB_SCHEDULE_WAVEFRONT;
+    p->schedule = SOLB_SCHEDULE_AUTO;
     p->accum_mode = SOLB_ACCUM_MIX;
 }
 
@@ -616,7 +616,9 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
     fc.accum_mode = params->accum_mode;
     TraceTimer timer(ctx);
     uint32_t n_ev = 0;
-    if (params->schedule == SOLB_SCHEDULE_MEGAKERNEL) {
+    uint32_t schedule = params->schedule;
+    if (schedule == SOLB_SCHEDULE_AUTO) schedule = s->accel.n_wide <= 8 ? SOLB_SCHEDULE_MEGAKERNEL : SOLB_SCHEDULE_WAVEFRONT;
+    if (schedule == SOLB_SCHEDULE_MEGAKERNEL) {
         CU(ctx, launch_pathtrace_mega(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, (float4 *)accum->dev,
                                       render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0));
         ctx->launches += 1;

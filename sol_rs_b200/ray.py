@@ -194,7 +194,7 @@ class TraceBindings:
     TLAS + images (set 1), push constant.  Optional overrides expose the shader literals BASELINE's configs vary."""
 
     def __init__(self, scene_description, uniforms, accum_target=None, render_target=None, ids_target=None,
-                 accumulation_start_frame=0, samples_per_frame=None, max_bounces=None, schedule=N.SCHEDULE_WAVEFRONT,
+                 accumulation_start_frame=0, samples_per_frame=None, max_bounces=None, schedule=N.SCHEDULE_AUTO,
                  accum_mode=N.ACCUM_MIX, collect_stats=False):
         self.scene_description, self.uniforms = scene_description, uniforms
         self.accum_target, self.render_target, self.ids_target = accum_target, render_target, ids_target
