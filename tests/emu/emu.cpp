@@ -247,8 +247,8 @@ void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_
     fill_fc(fc, uniforms, w, h);
     fc.accum_start = accum_start; fc.enable_sky = (uint32_t)enable_sky; fc.spp = (uint32_t)spp; fc.max_bounces = (uint32_t)max_bounces;
     fc.accum_mode = (uint32_t)accum_mode;
-    uint64_t nrays = 0, nhits = 0;
-#pragma omp parallel for schedule(dynamic, 2) reduction(+ : nrays, nhits)
+    uint64_t nrays = 0, nhits = 0, nnodes = 0, ntris = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : nrays, nhits, nnodes, ntris)
     for (int64_t y = 0; y < (int64_t)h; y++)
         for (uint32_t x = 0; x < w; x++) {
             uint32_t rng = tea(x + (uint32_t)y * w, fc.frame);
@@ -260,7 +260,9 @@ void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_
             while (sample < fc.spp) {
                 Hit hit;
                 EmuStack st;
-                trace_closest<false>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, (TraceCounters *)nullptr);
+                TraceCounters ctr = { 0, 0 };
+                trace_closest<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, &ctr);
+                nnodes += ctr.nodes; ntris += ctr.tris;
                 nrays++;
                 bool end_path;
                 if (hit.inst != SOLB_MISS) {
@@ -289,7 +291,7 @@ void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_
             accum[4 * p] = out.x; accum[4 * p + 1] = out.y; accum[4 * p + 2] = out.z; accum[4 * p + 3] = out.w;
             if (render) render[p] = rgba;
         }
-    if (stats) { stats[0] += nrays; stats[1] += nhits; }
+    if (stats) { stats[0] += nrays; stats[1] += nhits; stats[2] += nnodes; stats[3] += ntris; }
 }
 
 uint32_t emu_tea(uint32_t a, uint32_t b) { return tea(a, b); }

@@ -118,7 +118,7 @@ class EmuScene:
     def pathtrace_frame(self, uniforms, w, h, accum, accum_start=0, enable_sky=False, spp=8, max_bounces=32, accum_mode=0):
         u = np.frombuffer(uniforms, dtype=np.float32).copy()
         render = np.zeros((h, w), dtype=np.uint32)
-        stats = np.zeros(2, dtype=np.uint64)
+        stats = np.zeros(4, dtype=np.uint64)  # rays, hits, wide nodes visited, triangles tested
         lib().emu_pathtrace_frame(self.h, _p(u), w, h, accum_start, int(enable_sky), spp, max_bounces, accum_mode, _p(accum),
                                   _p(render), _p(stats))
         return render.view(np.uint8).reshape(h, w, 4), stats

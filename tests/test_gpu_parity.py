@@ -451,6 +451,7 @@ def test_cpp_host_example_runs_the_reference_call_sequence(sol, ctx):
     import subprocess
 
     from helpers import ROOT
+    from sol_rs_b200 import _native as N
 
     exe = _os.path.join(ROOT, "examples", "pathtrace_offscreen")
     assert _os.path.exists(exe), "run __graft_entry__.build()"
@@ -458,7 +459,7 @@ def test_cpp_host_example_runs_the_reference_call_sequence(sol, ctx):
                          text=True, cwd=ROOT, timeout=120)
     assert out.returncode == 0, out.stderr
     info = json.loads(out.stdout.strip().splitlines()[-1])
-    _, rgba = _render_gpu(sol, ctx, "cornell", 160, 120, range(3), False, 8, 32, 0)
+    _, rgba = _render_gpu(sol, ctx, "cornell", 160, 120, range(3), False, 8, 32, N.SCHEDULE_AUTO)  # the example keeps the default schedule
     h = 1469598103934665603
     for b in rgba.tobytes():
         h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
