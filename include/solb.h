@@ -105,6 +105,13 @@ typedef enum SolbSchedule {
                                     hide, queue traffic dominates), wavefront otherwise                      */
 } SolbSchedule;
 
+typedef enum SolbAccelMode {
+    SOLB_ACCEL_FLAT = 0,     /* default: instance transforms baked into world-space triangles, ONE hierarchy (the reference has
+                                exactly one instance per BLAS, src/ray/mod.rs:122, so instancing saves nothing there)       */
+    SOLB_ACCEL_TWO_LEVEL = 1 /* TLAS of instances over shared object-space BLASes (src/ray/acceleration.rs:136-239,344-400):
+                                instances of one BLAS share its nodes / triangles, solb_tlas_regenerate rebuilds the TLAS only */
+} SolbAccelMode;
+
 typedef enum SolbAccumMode {
     SOLB_ACCUM_MIX = 0, /* reference: new = mix(old, frame, 1/(frame+1-start)), pathtrace.rgen:89-101 */
     SOLB_ACCUM_SUM = 1  /* multi-GPU: accum.xyz += frame colour, accum.w += 1 (resolved later)         */
@@ -147,6 +154,10 @@ typedef struct SolbAccelInfo {
     float sah_cost_binary;    /* SAH cost of the binary tree (after treelet pass)      */
     float sah_cost_lbvh;      /* SAH cost of the raw LBVH (before treelet pass)        */
     float scene_lo[3], scene_hi[3];
+    uint32_t mode;            /* SolbAccelMode the structure was built with                */
+    uint32_t n_blas;          /* unique geometries (primitive sections)                    */
+    uint32_t n_tlas_nodes;    /* two-level: 8-wide nodes of the TLAS (0 when flattened)    */
+    uint32_t tlas_depth;      /* two-level: depth of the TLAS part of wide_depth           */
 } SolbAccelInfo;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -184,9 +195,19 @@ SOLB_API int solb_scene_update(solb_scene *scene);
  * The reference rebuilds every frame; here it is a no-op unless a transform changed. */
 SOLB_API int solb_tlas_regenerate(solb_scene *scene);
 
+/* SURVEY 8f-3 (the reference's "TODO: support multiple instances per BLAS", src/ray/mod.rs:122): one more instance of
+ * the BLAS that `source_instance` uses, with its own transform and material.  The new instance id (= gl_InstanceID) is the
+ * running count.  Takes effect at the next solb_accel_build / solb_tlas_regenerate. */
+SOLB_API int solb_scene_add_instance(solb_scene *scene, uint32_t source_instance, const float transform[16],
+                                     uint32_t material_index, uint32_t *out_index);
+/* SolbAccelMode for the next build (default SOLB_ACCEL_FLAT). */
+SOLB_API int solb_scene_set_accel_mode(solb_scene *scene, uint32_t mode);
+
 SOLB_API int solb_scene_instance_count(solb_scene *scene, uint32_t *out);
 /* SceneDescription::instances as the shader sees them (get_instances_buffer, src/ray/mod.rs:186) */
 SOLB_API int solb_scene_get_instances(solb_scene *scene, SolbSceneInstance *out, uint32_t capacity);
+/* primitive_count of every instance's BLAS (src/ray/acceleration.rs:183), instance order */
+SOLB_API int solb_scene_instance_triangles(solb_scene *scene, uint32_t *out, uint32_t capacity);
 SOLB_API int solb_accel_info(solb_scene *scene, SolbAccelInfo *out);
 /* test/inspection hooks: copy the built structure back (80 B nodes, 48 B triangle records) */
 SOLB_API int solb_accel_read_nodes(solb_scene *scene, void *host, size_t bytes);

@@ -49,6 +49,9 @@ extern "C" {
     pub fn solb_instance_set_transform(scene: *mut solb_scene, index: u32, transform: *const f32) -> c_int;
     pub fn solb_scene_update(scene: *mut solb_scene) -> c_int;
     pub fn solb_tlas_regenerate(scene: *mut solb_scene) -> c_int;
+    pub fn solb_scene_add_instance(scene: *mut solb_scene, source_instance: u32, transform: *const f32, material_index: u32,
+                                   out_index: *mut u32) -> c_int;
+    pub fn solb_scene_set_accel_mode(scene: *mut solb_scene, mode: u32) -> c_int;
     pub fn solb_scene_instance_count(scene: *mut solb_scene, out: *mut u32) -> c_int;
     pub fn solb_scene_get_instances(scene: *mut solb_scene, out: *mut SolbSceneInstance, capacity: u32) -> c_int;
     pub fn solb_target_create(ctx: *mut solb_ctx, width: u32, height: u32, format: u32, out: *mut *mut solb_target) -> c_int;

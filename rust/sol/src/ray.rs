@@ -62,6 +62,16 @@ impl SceneDescription {
     }
     /// src/ray/mod.rs:178-181 (the command buffer argument is accepted for source compatibility)
     pub fn tlas_regenerate<C>(&mut self, _cmd: C) { check(&self.context, unsafe { solb_tlas_regenerate(self.raw) }); }
+    /// Beyond the reference (its TODO at src/ray/mod.rs:122): one more instance of the BLAS `source_instance` uses.
+    /// Returns the new gl_InstanceID; takes effect at the next `accel_build` / `tlas_regenerate`.
+    pub fn add_instance(&mut self, source_instance: usize, transform: glam::Mat4, material_index: u32) -> u32 {
+        let mut id = 0u32;
+        check(&self.context, unsafe { solb_scene_add_instance(self.raw, source_instance as u32, transform.to_cols_array().as_ptr(), material_index, &mut id) });
+        id
+    }
+    /// 0 = flattened (default), 1 = two-level: TLAS over shared BLASes, `tlas_regenerate` rebuilds the TLAS only.
+    pub fn set_accel_mode(&mut self, mode: u32) { check(&self.context, unsafe { solb_scene_set_accel_mode(self.raw, mode) }); }
+    pub fn accel_build(&mut self) { check(&self.context, unsafe { solb_accel_build(self.raw) }); }
     /// src/ray/mod.rs:190-192
     pub fn update(&mut self) { check(&self.context, unsafe { solb_scene_update(self.raw) }); }
     pub(crate) fn raw(&self) -> *mut solb_scene { self.raw }

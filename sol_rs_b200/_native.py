@@ -11,6 +11,7 @@ SOLB_OK = 0
 FORMAT_RGBA32F, FORMAT_RGBA8, FORMAT_RG32UI = 0, 1, 2
 SCHEDULE_WAVEFRONT, SCHEDULE_MEGAKERNEL, SCHEDULE_AUTO = 0, 1, 2
 ACCUM_MIX, ACCUM_SUM = 0, 1
+ACCEL_FLAT, ACCEL_TWO_LEVEL = 0, 1
 MISS = 0xFFFFFFFF
 
 
@@ -66,7 +67,8 @@ class Stats(ctypes.Structure):
 class AccelInfo(ctypes.Structure):
     _fields_ = [("n_instances", ctypes.c_uint32), ("n_triangles", ctypes.c_uint32), ("n_wide_nodes", ctypes.c_uint32),
                 ("wide_depth", ctypes.c_uint32), ("n_binary_nodes", ctypes.c_uint32), ("sah_cost_binary", ctypes.c_float),
-                ("sah_cost_lbvh", ctypes.c_float), ("scene_lo", ctypes.c_float * 3), ("scene_hi", ctypes.c_float * 3)]
+                ("sah_cost_lbvh", ctypes.c_float), ("scene_lo", ctypes.c_float * 3), ("scene_hi", ctypes.c_float * 3),
+                ("mode", ctypes.c_uint32), ("n_blas", ctypes.c_uint32), ("n_tlas_nodes", ctypes.c_uint32), ("tlas_depth", ctypes.c_uint32)]
 
 
 assert ctypes.sizeof(ModelVertex) == 64 and ctypes.sizeof(MaterialInfo) == 48
@@ -90,8 +92,11 @@ SYMBOLS = {
     "solb_instance_set_transform": (_i, [_vp, _u32, ctypes.POINTER(ctypes.c_float)]),
     "solb_scene_update": (_i, [_vp]),
     "solb_tlas_regenerate": (_i, [_vp]),
+    "solb_scene_add_instance": (_i, [_vp, _u32, ctypes.POINTER(ctypes.c_float), _u32, ctypes.POINTER(_u32)]),
+    "solb_scene_set_accel_mode": (_i, [_vp, _u32]),
     "solb_scene_instance_count": (_i, [_vp, ctypes.POINTER(_u32)]),
     "solb_scene_get_instances": (_i, [_vp, ctypes.POINTER(SceneInstance), _u32]),
+    "solb_scene_instance_triangles": (_i, [_vp, ctypes.POINTER(_u32), _u32]),
     "solb_accel_info": (_i, [_vp, ctypes.POINTER(AccelInfo)]),
     "solb_accel_read_nodes": (_i, [_vp, _vp, ctypes.c_size_t]),
     "solb_accel_read_triangles": (_i, [_vp, _vp, ctypes.c_size_t]),

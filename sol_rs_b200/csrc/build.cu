@@ -62,7 +62,7 @@ __global__ void k_prep_tris(const DeviceSceneView sv, Tri48 *tri_world, float4 *
         Tri48 t;
         t.v0 = make_float4(p[0].x, p[0].y, p[0].z, __uint_as_float(inst));
         t.v1 = make_float4(p[1].x, p[1].y, p[1].z, __uint_as_float(prim));
-        t.v2 = make_float4(p[2].x, p[2].y, p[2].z, __uint_as_float(g));
+        t.v2 = make_float4(p[2].x, p[2].y, p[2].z, __uint_as_float(di.shade_first_tri + prim));  // shading record (geometry triangle)
         tri_world[g] = t;
         const float3 lo3 = fmin3(p[0], fmin3(p[1], p[2])), hi3 = fmax3(p[0], fmax3(p[1], p[2]));
         prim_lo[g] = make_float4(lo3.x, lo3.y, lo3.z, 0.0f);
@@ -477,11 +477,12 @@ __global__ void k_clear_u32(uint32_t *p, uint32_t n) {
 
 __global__ void k_collapse_level(const BNode *bn, const int *node_count, int n_internal, const CollapseItem *queue_in,
                                  uint32_t n_items, Node8 *wide, uint32_t *counters /*0: wide, 1: tris, 2: queue_out*/,
-                                 const uint32_t *sorted_prim, const Tri48 *tri_world, Tri48 *tri_out, CollapseItem *queue_out) {
+                                 const uint32_t *sorted_prim, const Tri48 *tri_world, Tri48 *tri_out, CollapseItem *queue_out,
+                                 uint32_t *leaf_prim_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     collapse_one(bn, node_count, n_internal, queue_in[i], wide, &counters[0], &counters[1], sorted_prim, tri_world, tri_out,
-                 queue_out, &counters[2]);
+                 queue_out, &counters[2], leaf_prim_out);
 }
 
 // n == 1: a root with one single-triangle leaf
@@ -501,6 +502,177 @@ __global__ void k_empty_root(Node8 *wide) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// two-level build kernels (SOLB_ACCEL_TWO_LEVEL)
+
+// bounds[6 * b + 0..2] = min centroid (ordered), [3..5] = max centroid (ordered)
+__global__ void k_init_bounds_n(uint32_t *bounds, uint32_t n_sets) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 6 * n_sets) bounds[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+}
+
+// One thread per GEOMETRY triangle g (all BLASes back to back): object-space record, box, per-BLAS centroid bounds.
+__global__ void k_prep_tris_obj(const DeviceSceneView sv, Tri48 *tri_obj, float4 *prim_lo, float4 *prim_hi, uint32_t *blas_bounds) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g < sv.n_geom_tris;
+    uint32_t b = 0xffffffffu;
+    float3 c = f3(0, 0, 0);
+    if (valid) {
+        uint32_t lo = 0, hi = sv.n_blas;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sv.blas[mid].first_tri <= g) lo = mid; else hi = mid;
+        }
+        b = lo;
+        const DeviceBlas db = sv.blas[b];
+        const uint32_t prim = g - db.first_tri;
+        float3 p[3];
+        for (int k = 0; k < 3; k++) {
+            const uint32_t vi = db.first_vertex + sv.indices[db.first_index + 3 * prim + k];
+            const float4 pos = sv.vertices[4 * (size_t)vi];
+            p[k] = f3(pos.x, pos.y, pos.z);
+        }
+        Tri48 t;
+        t.v0 = make_float4(p[0].x, p[0].y, p[0].z, __uint_as_float(b));  // instance id comes from the TLAS leaf
+        t.v1 = make_float4(p[1].x, p[1].y, p[1].z, __uint_as_float(prim));
+        t.v2 = make_float4(p[2].x, p[2].y, p[2].z, __uint_as_float(g));
+        tri_obj[g] = t;
+        const float3 lo3 = fmin3(p[0], fmin3(p[1], p[2])), hi3 = fmax3(p[0], fmax3(p[1], p[2]));
+        prim_lo[g] = make_float4(lo3.x, lo3.y, lo3.z, __uint_as_float(b));
+        prim_hi[g] = make_float4(hi3.x, hi3.y, hi3.z, 0.0f);
+        c = (lo3 + hi3) * 0.5f;
+    }
+    // warps that sit inside one BLAS reduce first (the common case: BLASes hold thousands of triangles)
+    const uint32_t b0 = __shfl_sync(0xffffffffu, b, 0);
+    if (__all_sync(0xffffffffu, b == b0) && b0 != 0xffffffffu) {
+        float mn[3] = { c.x, c.y, c.z }, mx[3] = { c.x, c.y, c.z };
+        for (int off = 16; off; off >>= 1)
+            for (int k = 0; k < 3; k++) {
+                mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], off));
+                mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
+            }
+        if ((threadIdx.x & 31) == 0)
+            for (int k = 0; k < 3; k++) {
+                atomicMin(&blas_bounds[6 * b0 + k], float_to_ordered(mn[k]));
+                atomicMax(&blas_bounds[6 * b0 + 3 + k], float_to_ordered(mx[k]));
+            }
+    } else if (valid) {
+        const float cc[3] = { c.x, c.y, c.z };
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&blas_bounds[6 * b + k], float_to_ordered(cc[k]));
+            atomicMax(&blas_bounds[6 * b + 3 + k], float_to_ordered(cc[k]));
+        }
+    }
+}
+
+// Segmented Morton key: [BLAS id | Morton code of the centroid inside its BLAS's centroid box], so one sort and one
+// Karras hierarchy over all triangles yield every BLAS as its own subtree (keys sharing a prefix form a subtree).
+__global__ void k_morton_seg(const float4 *prim_lo, const float4 *prim_hi, uint32_t n, const uint32_t *blas_bounds, int morton_bits,
+                             uint64_t *keys, uint32_t *vals) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const float4 a = prim_lo[g], b4 = prim_hi[g];
+    const uint32_t b = __float_as_uint(a.w);
+    const uint32_t *bb = blas_bounds + 6 * (size_t)b;
+    const float3 lo = f3(ordered_to_float(bb[0]), ordered_to_float(bb[1]), ordered_to_float(bb[2]));
+    const float3 hi = f3(ordered_to_float(bb[3]), ordered_to_float(bb[4]), ordered_to_float(bb[5]));
+    const float3 ext = hi - lo;
+    const float3 inv = f3(ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f);
+    const float3 c = f3((a.x + b4.x) * 0.5f, (a.y + b4.y) * 0.5f, (a.z + b4.z) * 0.5f);
+    keys[g] = ((uint64_t)b << morton_bits) | (morton63(c, lo, inv) >> (63 - morton_bits));
+    vals[g] = g;
+}
+
+// BLAS b covers sorted positions [first, last]; its subtree root is the internal node whose Karras range is exactly
+// that (node `first` or node `last`), or the leaf itself for a single-triangle BLAS.  Detach it from the levels above.
+__global__ void k_blas_roots(const uint64_t *keys, int n, const DeviceBlas *blas, uint32_t n_blas, int *parent, int *blas_root) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blas) return;
+    const int first = (int)blas[b].first_tri, cnt = (int)(blas[b].n_indices / 3), last = first + cnt - 1;
+    int root;
+    if (cnt == 1) root = n - 1 + first;
+    else {
+        root = -1;
+        for (int k = 0; k < 2 && root < 0; k++) {
+            const int i = k ? last : first;
+            if (i > n - 2) continue;
+            int l, r, f, e;
+            karras_node(keys, n, i, l, r, f, e);
+            if (f == first && e == last) root = i;
+        }
+    }
+    blas_root[b] = root;
+    if (root >= 0) parent[root] = -1;
+}
+
+__global__ void k_blas_boxes(const BNode *bn, const int *blas_root, uint32_t n_blas, float4 *blas_box) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blas) return;
+    const BNode r = bn[blas_root[b]];
+    blas_box[2 * b] = make_float4(r.lo.x, r.lo.y, r.lo.z, 0.0f);
+    blas_box[2 * b + 1] = make_float4(r.hi.x, r.hi.y, r.hi.z, 0.0f);
+}
+
+// collapse seeds: item i turns the root of multi-triangle BLAS list[i] into wide node tlas_cap + list[i]
+__global__ void k_seed_blas_collapse(const uint32_t *list, uint32_t n_items, const int *blas_root, uint32_t tlas_cap, CollapseItem *queue) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    CollapseItem it;
+    it.bnode = blas_root[list[i]];
+    it.wnode = tlas_cap + list[i];
+    queue[i] = it;
+}
+
+// single-triangle BLAS list[i]: a root with one single-triangle leaf, triangle slot i
+__global__ void k_single_tri_blas(const uint32_t *list, uint32_t n_items, const DeviceBlas *blas, const float4 *prim_lo,
+                                  const float4 *prim_hi, const Tri48 *tri_obj, uint32_t tlas_cap, Node8 *wide, Tri48 *tri_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const uint32_t b = list[i], g = blas[b].first_tri;
+    ChildRef ch[8];
+    for (int s = 0; s < 8; s++) ch[s].valid = 0;
+    const float3 lo = f3(prim_lo[g].x, prim_lo[g].y, prim_lo[g].z), hi = f3(prim_hi[g].x, prim_hi[g].y, prim_hi[g].z);
+    ch[0].valid = 1; ch[0].lo = lo; ch[0].hi = hi; ch[0].is_inner = 0; ch[0].tri_offset = 0; ch[0].tri_count = 1;
+    encode_node8(wide[tlas_cap + b], lo, hi, 0, i, ch);
+    tri_out[i] = tri_obj[g];
+}
+
+// TLAS primitives: world box of every instance (its BLAS's root box under the instance matrix) + centroid bounds
+__global__ void k_inst_boxes(const DeviceInstance *instances, uint32_t n_inst, const float4 *blas_box, float4 *prim_lo, float4 *prim_hi,
+                             uint32_t *bounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inst) return;
+    const DeviceInstance &di = instances[i];
+    const float4 a = blas_box[2 * di.blas], b = blas_box[2 * di.blas + 1];
+    float3 lo, hi;
+    transform_box(di.transform, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), lo, hi);
+    prim_lo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    prim_hi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    const float cc[3] = { (lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f };
+    for (int k = 0; k < 3; k++) {
+        atomicMin(&bounds[k], float_to_ordered(cc[k]));
+        atomicMax(&bounds[3 + k], float_to_ordered(cc[k]));
+    }
+}
+
+// TLAS leaf slot j holds instance leaf_prim[j]
+__global__ void k_write_inst_leaves(const uint32_t *leaf_prim, uint32_t n_inst, const DeviceInstance *instances, uint32_t tlas_cap,
+                                    InstLeaf *out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_inst) return;
+    const uint32_t i = leaf_prim ? leaf_prim[j] : j;
+    out[j] = make_inst_leaf(instances[i].transform, tlas_cap + instances[i].blas, i);
+}
+
+// n_inst == 1: TLAS root with one single-instance leaf
+__global__ void k_single_inst_root(const float4 *prim_lo, const float4 *prim_hi, Node8 *wide) {
+    ChildRef ch[8];
+    for (int s = 0; s < 8; s++) ch[s].valid = 0;
+    const float3 lo = f3(prim_lo[0].x, prim_lo[0].y, prim_lo[0].z), hi = f3(prim_hi[0].x, prim_hi[0].y, prim_hi[0].z);
+    ch[0].valid = 1; ch[0].lo = lo; ch[0].hi = hi; ch[0].is_inner = 0; ch[0].tri_offset = 0; ch[0].tri_count = 1;
+    encode_node8(wide[0], lo, hi, 0, 0, ch);
+}
+
+// ---------------------------------------------------------------------------------------------------
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 
 template <class T>
@@ -511,21 +683,107 @@ static cudaError_t salloc(cudaStream_t st, T **p, size_t count) {
     return cudaMallocAsync((void **)p, std::max<size_t>(count, 1) * sizeof(T), st);
 }
 
+// Device scratch of one binary radix tree over n >= 2 primitives (Karras numbering: internal [0, n-2], leaf j -> n-1+j).
+struct BinaryTree {
+    uint32_t n = 0;
+    uint64_t *keys = nullptr, *keys_tmp = nullptr;
+    uint32_t *vals = nullptr, *vals_tmp = nullptr, *sort_scratch = nullptr, *flags = nullptr;
+    BNode *bn = nullptr;
+    int *parent = nullptr, *node_count = nullptr;
+    float *node_cost = nullptr;
+    cudaError_t alloc(cudaStream_t st, uint32_t n_) {
+        n = n_;
+        cudaError_t err = cudaSuccess;
+        CK(salloc(st, &keys, n));
+        CK(salloc(st, &keys_tmp, n));
+        CK(salloc(st, &vals, n));
+        CK(salloc(st, &vals_tmp, n));
+        CK(salloc(st, &sort_scratch, onesweep_scratch_words(n)));
+        CK(salloc(st, &bn, 2 * (size_t)n - 1));
+        CK(salloc(st, &parent, 2 * (size_t)n - 1));
+        CK(salloc(st, &node_count, 2 * (size_t)n - 1));
+        CK(salloc(st, &node_cost, 2 * (size_t)n - 1));
+        CK(salloc(st, &flags, n));
+    done:
+        return err;
+    }
+    void free(cudaStream_t st) {
+        void *q[] = { keys, keys_tmp, vals, vals_tmp, sort_scratch, flags, bn, parent, node_count, node_cost };
+        for (void *x : q)
+            if (x) cudaFreeAsync(x, st);
+        *this = BinaryTree();
+    }
+};
+
+// keys / vals filled: sort, link the radix tree, initialise the leaves
+static cudaError_t tree_sort_and_link(cudaStream_t st, BinaryTree &T, const float4 *prim_lo, const float4 *prim_hi, int key_bits,
+                                      uint64_t *launches) {
+    cudaError_t err = radix_sort_pairs(st, T.keys, T.vals, T.keys_tmp, T.vals_tmp, T.n, key_bits, T.sort_scratch, launches);
+    if (err != cudaSuccess) return err;
+    k_hierarchy<<<(T.n + 255) / 256, 256, 0, st>>>(T.keys, T.vals, prim_lo, prim_hi, (int)T.n, T.bn, T.parent, T.node_count, T.node_cost,
+                                                     T.flags);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+// refit (boxes, counts, SAH cost) and treelet restructuring; walks stop at nodes whose parent is -1
+static cudaError_t tree_refit_optimize(cudaStream_t st, BinaryTree &T, const BuildOptions &opt, int treelet_passes, float *sah_lbvh_out,
+                                       uint64_t *launches) {
+    const uint32_t n = T.n, nb = (n + 255) / 256;
+    cudaError_t err = cudaSuccess;
+    k_bottom_up<<<nb, 256, 0, st>>>((int)n, T.bn, T.parent, T.node_count, T.node_cost, T.flags, 0, 0);
+    *launches += 1;
+    if (sah_lbvh_out) CK(cudaMemcpyAsync(sah_lbvh_out, T.node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
+    for (int pass = 0; pass < treelet_passes; pass++) {
+        k_clear_u32<<<nb, 256, 0, st>>>(T.flags, n);
+        if (opt.coop_treelet)
+            k_bottom_up_coop<<<(n + TL_BLOCK - 1) / TL_BLOCK, TL_BLOCK, 0, st>>>((int)n, T.bn, T.parent, T.node_count, T.node_cost, T.flags,
+                                                                                  opt.treelet_gamma);
+        else
+            k_bottom_up<<<(n + 63) / 64, 64, 0, st>>>((int)n, T.bn, T.parent, T.node_count, T.node_cost, T.flags, 1, opt.treelet_gamma);
+        *launches += 2;
+    }
+    CK(cudaGetLastError());
+done:
+    return err;
+}
+
+// Level-synchronous collapse.  queue_a holds n_items seeds; counters = {wide nodes allocated, leaf slots allocated, 0}
+// must already be on the device.  On return h_counters holds the final counts and *levels the number of levels.
+static cudaError_t collapse_levels(cudaStream_t st, const BinaryTree &T, CollapseItem *queue_a, CollapseItem *queue_b, uint32_t n_items,
+                                   Node8 *wide, uint32_t *counters, const Tri48 *tri_src, Tri48 *tri_out, uint32_t *leaf_prim_out,
+                                   uint32_t h_counters[3], uint32_t *levels, uint64_t *launches) {
+    cudaError_t err = cudaSuccess;
+    uint32_t depth = 0;
+    while (n_items) {
+        k_collapse_level<<<(n_items + 63) / 64, 64, 0, st>>>(T.bn, T.node_count, (int)T.n - 1, queue_a, n_items, wide, counters, T.vals,
+                                                             tri_src, tri_out, queue_b, leaf_prim_out);
+        *launches += 1;
+        CK(cudaMemcpyAsync(h_counters, counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_items = h_counters[2];
+        h_counters[2] = 0;
+        CK(cudaMemcpyAsync(counters + 2, &h_counters[2], sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        std::swap(queue_a, queue_b);
+        depth++;
+        if (depth > SOLB_MAX_WIDE_DEPTH) { err = cudaErrorLaunchOutOfResources; goto done; }
+    }
+    *levels = depth;
+done:
+    return err;
+}
+
 cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt, uint64_t *launches) {
     cudaError_t err = cudaSuccess;
     const uint32_t n = sv.n_tris;
     Tri48 *tri_world = nullptr;
     float4 *prim_lo = nullptr, *prim_hi = nullptr;
-    uint32_t *bounds = nullptr, *vals = nullptr, *vals_tmp = nullptr, *tile_hist = nullptr, *flags = nullptr, *counters = nullptr;
-    uint64_t *keys = nullptr, *keys_tmp = nullptr;
-    BNode *bn = nullptr;
-    int *parent = nullptr, *node_count = nullptr;
-    float *node_cost = nullptr;
+    uint32_t *bounds = nullptr, *counters = nullptr;
+    BinaryTree T;
     CollapseItem *queue_a = nullptr, *queue_b = nullptr;
     Node8 *wide = nullptr;
     Tri48 *tri_out = nullptr;
-    const uint32_t T = 256;
-    const uint32_t nb = (n + T - 1) / T;
+    const uint32_t nb = (n + 255) / 256;
     uint32_t h_counters[3];
     uint32_t depth = 0;
 
@@ -545,7 +803,7 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
     CK(salloc(st, &prim_hi, n));
     CK(salloc(st, &bounds, 8));
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
-    k_prep_tris<<<nb, T, 0, st>>>(sv, tri_world, prim_lo, prim_hi, bounds);
+    k_prep_tris<<<nb, 256, 0, st>>>(sv, tri_world, prim_lo, prim_hi, bounds);
     *launches += 2;
     if (n == 1) {
         k_single_tri_root<<<1, 1, 0, st>>>(prim_lo, prim_hi, tri_world, wide, tri_out);
@@ -554,35 +812,15 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         out.depth = 1;
         goto finish;
     }
-    CK(salloc(st, &keys, n));
-    CK(salloc(st, &keys_tmp, n));
-    CK(salloc(st, &vals, n));
-    CK(salloc(st, &vals_tmp, n));
-    CK(salloc(st, &tile_hist, onesweep_scratch_words(n)));
-    k_morton<<<nb, T, 0, st>>>(prim_lo, prim_hi, n, bounds, keys, vals);
+    CK(T.alloc(st, n));
+    k_morton<<<nb, 256, 0, st>>>(prim_lo, prim_hi, n, bounds, T.keys, T.vals);
     *launches += 1;
-    CK(radix_sort_pairs(st, keys, vals, keys_tmp, vals_tmp, n, 63, tile_hist, launches));
-    CK(salloc(st, &bn, 2 * (size_t)n - 1));
-    CK(salloc(st, &parent, 2 * (size_t)n - 1));
-    CK(salloc(st, &node_count, 2 * (size_t)n - 1));
-    CK(salloc(st, &node_cost, 2 * (size_t)n - 1));
-    CK(salloc(st, &flags, n));
-    k_hierarchy<<<nb, T, 0, st>>>(keys, vals, prim_lo, prim_hi, (int)n, bn, parent, node_count, node_cost, flags);
-    k_bottom_up<<<nb, T, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, 0, 0);
-    *launches += 2;
-    CK(cudaMemcpyAsync(&out.sah_lbvh, node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
-    for (int pass = 0; pass < opt.treelet_passes; pass++) {
-        k_clear_u32<<<nb, T, 0, st>>>(flags, n);
-        if (opt.coop_treelet)
-            k_bottom_up_coop<<<(n + TL_BLOCK - 1) / TL_BLOCK, TL_BLOCK, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, opt.treelet_gamma);
-        else
-            k_bottom_up<<<(n + 63) / 64, 64, 0, st>>>((int)n, bn, parent, node_count, node_cost, flags, 1, opt.treelet_gamma);
-        *launches += 2;
-    }
-    CK(cudaMemcpyAsync(&out.sah_final, node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(tree_sort_and_link(st, T, prim_lo, prim_hi, 63, launches));
+    CK(tree_refit_optimize(st, T, opt, opt.treelet_passes, &out.sah_lbvh, launches));
+    CK(cudaMemcpyAsync(&out.sah_final, T.node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
     {
         BNode root;
-        CK(cudaMemcpyAsync(&root, bn, sizeof(BNode), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&root, T.bn, sizeof(BNode), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const float a = half_area(root.lo, root.hi);
         if (a > 0.0f) { out.sah_lbvh /= a; out.sah_final /= a; }
@@ -600,20 +838,7 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         CK(cudaMemcpyAsync(queue_a, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, st));
         h_counters[0] = 1; h_counters[1] = 0; h_counters[2] = 0;
         CK(cudaMemcpyAsync(counters, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
-        uint32_t n_items = 1;
-        while (n_items) {
-            k_collapse_level<<<(n_items + 63) / 64, 64, 0, st>>>(bn, node_count, (int)n - 1, queue_a, n_items, wide, counters, vals,
-                                                                 tri_world, tri_out, queue_b);
-            *launches += 1;
-            CK(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            n_items = h_counters[2];
-            h_counters[2] = 0;
-            CK(cudaMemcpyAsync(counters + 2, &h_counters[2], sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-            std::swap(queue_a, queue_b);
-            depth++;
-            if (depth > SOLB_MAX_WIDE_DEPTH) { err = cudaErrorLaunchOutOfResources; goto done; }
-        }
+        CK(collapse_levels(st, T, queue_a, queue_b, 1, wide, counters, tri_world, tri_out, nullptr, h_counters, &depth, launches));
         out.n_wide = h_counters[0];
         out.depth = depth;
         if (h_counters[1] != n) { err = cudaErrorUnknown; goto done; }  // every triangle must land in exactly one leaf
@@ -633,10 +858,208 @@ finish:
     }
 done:
     {
-        void *scratch[] = { tri_world, prim_lo, prim_hi, bounds, keys, keys_tmp, vals, vals_tmp, tile_hist, flags, counters, bn,
-                            parent, node_count, node_cost, queue_a, queue_b, wide };
+        void *scratch[] = { tri_world, prim_lo, prim_hi, bounds, counters, queue_a, queue_b, wide };
         for (void *q : scratch)
             if (q) cudaFreeAsync(q, st);
+        T.free(st);
+    }
+    cudaFree(tri_out);
+    if (err != cudaSuccess) out.release();
+    return err;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TLAS over the instances' world boxes, written into nodes[0, tlas_cap) and inst_leaves (both preallocated by
+// build_accel_two_level).  This is all TLAS::regenerate has to redo when instance transforms change.
+cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, uint64_t *launches) {
+    cudaError_t err = cudaSuccess;
+    const uint32_t n = sv.n_instances;
+    float4 *prim_lo = nullptr, *prim_hi = nullptr;
+    uint32_t *bounds = nullptr, *counters = nullptr, *leaf_prim = nullptr;
+    BinaryTree T;
+    CollapseItem *queue_a = nullptr, *queue_b = nullptr;
+    uint32_t h_counters[3];
+    uint32_t depth = 1;
+    BuildOptions opt;
+    if (!out.two_level || !out.nodes || n > out.tlas_cap) return cudaErrorInvalidValue;
+    out.sah_lbvh = out.sah_final = 0.0f;
+    if (n == 0) {
+        k_empty_root<<<1, 1, 0, st>>>(out.nodes);
+        *launches += 1;
+        out.n_tlas_wide = 1;
+        goto finish;
+    }
+    CK(salloc(st, &prim_lo, n));
+    CK(salloc(st, &prim_hi, n));
+    CK(salloc(st, &bounds, 8));
+    k_init_bounds<<<1, 32, 0, st>>>(bounds);
+    k_inst_boxes<<<(n + 127) / 128, 128, 0, st>>>(sv.instances, n, out.blas_box, prim_lo, prim_hi, bounds);
+    *launches += 2;
+    if (n == 1) {
+        k_single_inst_root<<<1, 1, 0, st>>>(prim_lo, prim_hi, out.nodes);
+        k_write_inst_leaves<<<1, 32, 0, st>>>(nullptr, 1, sv.instances, out.tlas_cap, out.inst_leaves);
+        *launches += 2;
+        out.n_tlas_wide = 1;
+        float4 h[2];
+        CK(cudaMemcpyAsync(&h[0], prim_lo, sizeof(float4), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h[1], prim_hi, sizeof(float4), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        out.lo[0] = h[0].x; out.lo[1] = h[0].y; out.lo[2] = h[0].z;
+        out.hi[0] = h[1].x; out.hi[1] = h[1].y; out.hi[2] = h[1].z;
+        goto finish;
+    }
+    CK(T.alloc(st, n));
+    k_morton<<<(n + 255) / 256, 256, 0, st>>>(prim_lo, prim_hi, n, bounds, T.keys, T.vals);
+    *launches += 1;
+    CK(tree_sort_and_link(st, T, prim_lo, prim_hi, 63, launches));
+    CK(tree_refit_optimize(st, T, opt, 2, &out.sah_lbvh, launches));
+    CK(cudaMemcpyAsync(&out.sah_final, T.node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
+    {
+        BNode root;
+        CK(cudaMemcpyAsync(&root, T.bn, sizeof(BNode), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const float a = half_area(root.lo, root.hi);
+        if (a > 0.0f) { out.sah_lbvh /= a; out.sah_final /= a; }
+        out.lo[0] = root.lo.x; out.lo[1] = root.lo.y; out.lo[2] = root.lo.z;
+        out.hi[0] = root.hi.x; out.hi[1] = root.hi.y; out.hi[2] = root.hi.z;
+    }
+    CK(salloc(st, &queue_a, n));
+    CK(salloc(st, &queue_b, n));
+    CK(salloc(st, &counters, 4));
+    CK(salloc(st, &leaf_prim, n));
+    {
+        CollapseItem rootItem;
+        rootItem.bnode = 0;
+        rootItem.wnode = 0;
+        CK(cudaMemcpyAsync(queue_a, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, st));
+        h_counters[0] = 1; h_counters[1] = 0; h_counters[2] = 0;
+        CK(cudaMemcpyAsync(counters, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
+        CK(collapse_levels(st, T, queue_a, queue_b, 1, out.nodes, counters, nullptr, nullptr, leaf_prim, h_counters, &depth, launches));
+        if (h_counters[1] != n || h_counters[0] > out.tlas_cap) { err = cudaErrorUnknown; goto done; }
+        out.n_tlas_wide = h_counters[0];
+        k_write_inst_leaves<<<(n + 127) / 128, 128, 0, st>>>(leaf_prim, n, sv.instances, out.tlas_cap, out.inst_leaves);
+        *launches += 1;
+    }
+finish:
+    out.tlas_depth = depth;
+    out.depth = out.tlas_depth + out.blas_depth;
+    if (out.depth > SOLB_MAX_WIDE_DEPTH) { err = cudaErrorLaunchOutOfResources; goto done; }
+    CK(cudaGetLastError());
+done:
+    {
+        void *scratch[] = { prim_lo, prim_hi, bounds, counters, leaf_prim, queue_a, queue_b };
+        for (void *q : scratch)
+            if (q) cudaFreeAsync(q, st);
+        T.free(st);
+    }
+    return err;
+}
+
+cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt,
+                                  uint64_t *launches) {
+    cudaError_t err = cudaSuccess;
+    const uint32_t n = sv.n_geom_tris, n_blas = sv.n_blas, n_inst = sv.n_instances;
+    const uint32_t tlas_cap = std::max<uint32_t>(n_inst, 1);
+    Tri48 *tri_obj = nullptr, *tri_out = nullptr;
+    float4 *prim_lo = nullptr, *prim_hi = nullptr;
+    uint32_t *blas_bounds = nullptr, *counters = nullptr, *d_list = nullptr;
+    int *blas_root = nullptr;
+    BinaryTree T;
+    CollapseItem *queue_a = nullptr, *queue_b = nullptr;
+    Node8 *wide = nullptr;
+    const uint32_t nb = (n + 255) / 256;
+    uint32_t h_counters[3] = { tlas_cap + n_blas, 0, 0 };
+    uint32_t depth = 1;
+    std::vector<uint32_t> h_list;  // multi-triangle BLASes first, then single-triangle ones
+    uint32_t n_multi = 0, n_single = 0;
+    std::vector<DeviceBlas> h_blas(n_blas);
+
+    out.release();
+    out.two_level = true;
+    out.n_tris = n;
+    out.n_blas = n_blas;
+    out.tlas_cap = tlas_cap;
+    // worst case wide-node count: TLAS region + one root per BLAS + (#triangles - 1) interiors
+    CK(salloc(st, &wide, (size_t)tlas_cap + n_blas + n));
+    CK(dalloc(&tri_out, n));
+    CK(dalloc(&out.inst_leaves, n_inst));
+    CK(dalloc(&out.blas_box, 2 * (size_t)n_blas));
+    if (n_blas) {
+        CK(cudaMemcpyAsync(h_blas.data(), sv.blas, n_blas * sizeof(DeviceBlas), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (uint32_t b = 0; b < n_blas; b++)
+            if (h_blas[b].n_indices / 3 >= 2) h_list.push_back(b);
+        n_multi = (uint32_t)h_list.size();
+        for (uint32_t b = 0; b < n_blas; b++)
+            if (h_blas[b].n_indices / 3 == 1) h_list.push_back(b);
+        n_single = (uint32_t)h_list.size() - n_multi;
+        if (n_multi + n_single != n_blas) { err = cudaErrorInvalidValue; goto done; }  // empty BLASes are rejected at scene creation
+        CK(salloc(st, &d_list, n_blas));
+        CK(cudaMemcpyAsync(d_list, h_list.data(), n_blas * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(salloc(st, &tri_obj, n));
+        CK(salloc(st, &prim_lo, n));
+        CK(salloc(st, &prim_hi, n));
+        CK(salloc(st, &blas_bounds, 6 * (size_t)n_blas));
+        CK(salloc(st, &blas_root, n_blas));
+        k_init_bounds_n<<<(6 * n_blas + 255) / 256, 256, 0, st>>>(blas_bounds, n_blas);
+        k_prep_tris_obj<<<nb, 256, 0, st>>>(sv, tri_obj, prim_lo, prim_hi, blas_bounds);
+        *launches += 2;
+        if (n >= 2) {
+            int id_bits = 0;
+            while ((1ull << id_bits) < n_blas) id_bits++;
+            const int morton_bits = ((63 - id_bits) / 3) * 3;
+            CK(T.alloc(st, n));
+            k_morton_seg<<<nb, 256, 0, st>>>(prim_lo, prim_hi, n, blas_bounds, morton_bits, T.keys, T.vals);
+            *launches += 1;
+            CK(tree_sort_and_link(st, T, prim_lo, prim_hi, morton_bits + id_bits, launches));
+            k_blas_roots<<<(n_blas + 127) / 128, 128, 0, st>>>(T.keys, (int)n, sv.blas, n_blas, T.parent, blas_root);
+            *launches += 1;
+            CK(tree_refit_optimize(st, T, opt, opt.treelet_passes, nullptr, launches));
+            k_blas_boxes<<<(n_blas + 127) / 128, 128, 0, st>>>(T.bn, blas_root, n_blas, out.blas_box);
+            *launches += 1;
+        } else {  // one BLAS holding one triangle
+            CK(cudaMemcpyAsync(out.blas_box, prim_lo, sizeof(float4), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(out.blas_box + 1, prim_hi, sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        }
+        CK(salloc(st, &counters, 4));
+        h_counters[1] = n_single;  // triangle slots [0, n_single) belong to the single-triangle BLASes
+        CK(cudaMemcpyAsync(counters, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
+        if (n_single) {
+            k_single_tri_blas<<<(n_single + 127) / 128, 128, 0, st>>>(d_list + n_multi, n_single, sv.blas, prim_lo, prim_hi, tri_obj, tlas_cap,
+                                                                      wide, tri_out);
+            *launches += 1;
+        }
+        if (n_multi) {
+            CK(salloc(st, &queue_a, n));
+            CK(salloc(st, &queue_b, n));
+            k_seed_blas_collapse<<<(n_multi + 127) / 128, 128, 0, st>>>(d_list, n_multi, blas_root, tlas_cap, queue_a);
+            *launches += 1;
+            CK(collapse_levels(st, T, queue_a, queue_b, n_multi, wide, counters, tri_obj, tri_out, nullptr, h_counters, &depth, launches));
+            if (h_counters[1] != n) { err = cudaErrorUnknown; goto done; }
+        }
+    }
+    out.blas_depth = depth;
+    out.n_wide = h_counters[0];
+    CK(cudaStreamSynchronize(st));
+    {
+        Node8 *final_nodes = nullptr;
+        CK(dalloc(&final_nodes, out.n_wide));
+        // the TLAS region is written by rebuild_tlas below; copy the BLAS part
+        if (out.n_wide > tlas_cap)
+            CK(cudaMemcpyAsync(final_nodes + tlas_cap, wide + tlas_cap, sizeof(Node8) * (out.n_wide - tlas_cap), cudaMemcpyDeviceToDevice, st));
+        out.nodes = final_nodes;
+        out.tris = tri_out;
+        tri_out = nullptr;
+        out.n_binary = n >= 2 ? 2 * n - 1 : n;
+    }
+    CK(rebuild_tlas(st, sv, out, launches));
+    CK(cudaStreamSynchronize(st));
+done:
+    {
+        void *scratch[] = { tri_obj, prim_lo, prim_hi, blas_bounds, counters, d_list, blas_root, queue_a, queue_b, wide };
+        for (void *q : scratch)
+            if (q) cudaFreeAsync(q, st);
+        T.free(st);
     }
     cudaFree(tri_out);
     if (err != cudaSuccess) out.release();

@@ -220,10 +220,11 @@ SOLB_HD int gather_leaf_tris(const BNode *bn, int n_internal, int c, int *out) {
 }
 
 // One work item.  sorted_prim[j] = global triangle id at sorted position j; tri_world indexed by
-// global triangle id; tri_out in wide-leaf order.
+// global triangle id; tri_out in wide-leaf order.  TLAS builds pass leaf_prim_out instead of tri_world / tri_out:
+// the primitive (instance) id of every leaf slot, from which the caller writes its own leaf records.
 SOLB_HD void collapse_one(const BNode *bn, const int *node_count, int n_internal, CollapseItem item, Node8 *wide,
                           uint32_t *wide_count, uint32_t *tri_count, const uint32_t *sorted_prim, const Tri48 *tri_world,
-                          Tri48 *tri_out, CollapseItem *queue_out, uint32_t *queue_out_count) {
+                          Tri48 *tri_out, CollapseItem *queue_out, uint32_t *queue_out_count, uint32_t *leaf_prim_out = nullptr) {
     int cand[8];
     int n = 2;
     cand[0] = bn[item.bnode].left;
@@ -302,9 +303,44 @@ SOLB_HD void collapse_one(const BNode *bn, const int *node_count, int n_internal
         } else {
             int prims[SOLB_MAX_LEAF_TRIS + 1];
             const int m = gather_leaf_tris(bn, n_internal, c, prims);
-            for (int j = 0; j < m; j++) tri_out[tri_base + ch[s].tri_offset + (uint32_t)j] = tri_world[sorted_prim[prims[j]]];
+            for (int j = 0; j < m; j++) {
+                const uint32_t dst = tri_base + ch[s].tri_offset + (uint32_t)j, prim = sorted_prim[prims[j]];
+                if (leaf_prim_out) leaf_prim_out[dst] = prim;
+                else tri_out[dst] = tri_world[prim];
+            }
         }
     }
+}
+
+// World-space box of an object-space box under a column-major 4x4 (instance AABB for the TLAS)
+SOLB_HD void transform_box(const float *m, float3 lo, float3 hi, float3 &out_lo, float3 &out_hi) {
+    out_lo = f3(3.4e38f, 3.4e38f, 3.4e38f);
+    out_hi = f3(-3.4e38f, -3.4e38f, -3.4e38f);
+    for (int c = 0; c < 8; c++) {
+        const float3 p = mat4_mul_point(m, f3((c & 1) ? hi.x : lo.x, (c & 2) ? hi.y : lo.y, (c & 4) ? hi.z : lo.z));
+        out_lo = fmin3(out_lo, p);
+        out_hi = fmax3(out_hi, p);
+    }
+}
+
+// InstLeaf of instance `id`: rows of inverse(transform) (world -> object) + BLAS root + id.
+// inverse() by cofactors of the upper 3x3 (affine instance matrices only, like VkAccelerationStructureInstanceKHR's 3x4).
+SOLB_HD InstLeaf make_inst_leaf(const float *m, uint32_t blas_root, uint32_t id) {
+    const float a = m[0], b = m[4], c = m[8], d = m[1], e = m[5], f = m[9], g = m[2], h = m[6], i = m[10];
+    const float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const float det = a * A + b * B + c * C;
+    const float r = det != 0.0f ? 1.0f / det : 0.0f;
+    // inverse 3x3, row-major
+    const float i00 = A * r, i01 = -(b * i - c * h) * r, i02 = (b * f - c * e) * r;
+    const float i10 = B * r, i11 = (a * i - c * g) * r, i12 = -(a * f - c * d) * r;
+    const float i20 = C * r, i21 = -(a * h - b * g) * r, i22 = (a * e - b * d) * r;
+    const float tx = m[12], ty = m[13], tz = m[14];
+    InstLeaf L;
+    L.r0 = make_float4(i00, i01, i02, -(i00 * tx + i01 * ty + i02 * tz));
+    L.r1 = make_float4(i10, i11, i12, -(i10 * tx + i11 * ty + i12 * tz));
+    L.r2 = make_float4(i20, i21, i22, -(i20 * tx + i21 * ty + i22 * tz));
+    L.r3 = make_float4(u2f(blas_root), u2f(id), 0.0f, 0.0f);
+    return L;
 }
 
 }  // namespace solb

@@ -35,7 +35,9 @@ static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
 #define SOLB_MAX_LEAF_TRIS 3
 #define SOLB_SM_STACK 8      // per-lane entries kept in shared memory
 #define SOLB_LOCAL_STACK 56  // spill (local memory)
-#define SOLB_MAX_WIDE_DEPTH (SOLB_SM_STACK + SOLB_LOCAL_STACK - 2)
+// The warp-cooperative kernel may park two entries per level (the siblings' node group and a postponed triangle
+// group), a two-level walk adds one sentinel: 2 * (TLAS depth + BLAS depth) + 1 <= SOLB_SM_STACK + SOLB_LOCAL_STACK.
+#define SOLB_MAX_WIDE_DEPTH ((SOLB_SM_STACK + SOLB_LOCAL_STACK - 2) / 2)
 
 struct Ray {
     float3 o;
@@ -254,7 +256,8 @@ SOLB_HD void trav_node_step(const uint4 *__restrict__ nodes, const TravRay &tr, 
 }
 
 // One triangle step.  Precondition: tgroup.y != 0.  Tests the highest pending triangle of the group.
-SOLB_HD void trav_tri_step(const float4 *__restrict__ tris, const TravRay &tr, float &tmax, uint2 &tgroup, Hit &hit) {
+// Returns true when the hit record was replaced.
+SOLB_HD bool trav_tri_step(const float4 *__restrict__ tris, const TravRay &tr, float &tmax, uint2 &tgroup, Hit &hit) {
     const int ti = bfind32(tgroup.y);
     tgroup.y &= ~(1u << ti);
     const float4 *tp = tris + (size_t)(tgroup.x + (uint32_t)ti) * 3;
@@ -264,7 +267,45 @@ SOLB_HD void trav_tri_step(const float4 *__restrict__ tris, const TravRay &tr, f
         tmax = t;
         hit.t = t; hit.u = u; hit.v = v;
         hit.inst = f2u(v0.w); hit.prim = f2u(v1.w); hit.gtri = f2u(v2.w);
+        return true;
     }
+    return false;
+}
+
+// ---- two-level traversal (TLAS of instances over shared, object-space BLASes) -------------------------
+// The reference's TLAS/BLAS split (src/ray/acceleration.rs:344-400): a TLAS leaf holds 64-byte instance
+// records instead of triangles.  Entering an instance transforms the ray into object space WITHOUT
+// renormalising the direction, so t keeps its world-space meaning (tmin / tmax / closest hit carry over),
+// saves the TLAS groups still in hand under a sentinel entry on the traversal stack and restarts at the
+// BLAS root; popping the sentinel returns to world space.
+//   r0, r1, r2 = rows of the world->object 3x4 matrix, r3 = (bits(BLAS root node), bits(instance id), 0, 0)
+struct InstLeaf {
+    float4 r0, r1, r2, r3;
+};
+static_assert(sizeof(InstLeaf) == 64, "InstLeaf must be 64 bytes");
+#define SOLB_STACK_SENTINEL make_uint2(0xffffffffu, 0u)  // .y == 0 never occurs in a pushed node / triangle group
+
+// One instance step (TLAS mode).  Precondition: tgroup.y != 0.  world_o / world_d = the ray as traced.
+template <class Stack>
+SOLB_HD void trav_enter_instance(const float4 *__restrict__ inst_leaves, float3 world_o, float3 world_d, TravRay &tr, uint2 &ngroup,
+                                 uint2 &tgroup, uint32_t &cur_inst, Stack &stack) {
+    const int ti = bfind32(tgroup.y);
+    tgroup.y &= ~(1u << ti);
+    const float4 *rp = inst_leaves + (size_t)(tgroup.x + (uint32_t)ti) * 4;
+    const float4 r0 = SOLB_LDG4(rp + 0), r1 = SOLB_LDG4(rp + 1), r2 = SOLB_LDG4(rp + 2), r3 = SOLB_LDG4(rp + 3);
+    if (tgroup.y) stack.push(tgroup);                 // the leaf's other instances
+    if (ngroup.y & 0xff000000u) stack.push(ngroup);   // TLAS siblings still to visit
+    stack.push(SOLB_STACK_SENTINEL);
+    const float3 o = f3(fmaf(r0.x, world_o.x, fmaf(r0.y, world_o.y, fmaf(r0.z, world_o.z, r0.w))),
+                        fmaf(r1.x, world_o.x, fmaf(r1.y, world_o.y, fmaf(r1.z, world_o.z, r1.w))),
+                        fmaf(r2.x, world_o.x, fmaf(r2.y, world_o.y, fmaf(r2.z, world_o.z, r2.w))));
+    const float3 d = f3(fmaf(r0.x, world_d.x, fmaf(r0.y, world_d.y, r0.z * world_d.z)),
+                        fmaf(r1.x, world_d.x, fmaf(r1.y, world_d.y, r1.z * world_d.z)),
+                        fmaf(r2.x, world_d.x, fmaf(r2.y, world_d.y, r2.z * world_d.z)));
+    tr = make_trav_ray(o, d, tr.tmin);
+    cur_inst = f2u(r3.y);
+    ngroup = make_uint2(f2u(r3.x), 0x80000000u);  // "child 7 ^ oct_inv of a virtual parent" whose child_base is the BLAS root
+    tgroup = make_uint2(0u, 0u);
 }
 
 // Closest-hit traversal, one thread per ray (debug / AO / megakernel / host emulation).
@@ -289,6 +330,43 @@ SOLB_HD void trace_closest(const uint4 *__restrict__ nodes, const float4 *__rest
         if (!(ngroup.y & 0xff000000u)) {
             if (stack.empty()) break;
             ngroup = stack.pop();
+        }
+    }
+}
+
+// Two-level closest hit, one thread per ray.  A plain state machine (triangle / instance step, node step, pop):
+// TLAS groups are postponed on the stack while a BLAS is walked.
+template <bool STATS, class Stack>
+SOLB_HD void trace_closest_2l(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
+                              const Ray &ray, Hit &hit, Stack &stack, TraceCounters *ctr) {
+    hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS;
+    hit.t = ray.tmax; hit.u = 0.0f; hit.v = 0.0f;
+    TravRay tr = make_trav_ray(ray.o, ray.d, ray.tmin);
+    float tmax = ray.tmax;
+    uint2 ngroup = SOLB_ROOT_GROUP;
+    uint2 tgroup = make_uint2(0u, 0u);
+    bool in_blas = false;
+    uint32_t cur_inst = SOLB_MISS;
+    for (;;) {
+        if (tgroup.y) {
+            if (in_blas) {
+                if (trav_tri_step(tris, tr, tmax, tgroup, hit)) hit.inst = cur_inst;
+                if (STATS) ctr->tris++;
+            } else {
+                trav_enter_instance(inst_leaves, ray.o, ray.d, tr, ngroup, tgroup, cur_inst, stack);
+                in_blas = true;
+            }
+        } else if (ngroup.y & 0xff000000u) {
+            trav_node_step(nodes, tr, tmax, ngroup, tgroup, stack);
+            if (STATS) ctr->nodes++;
+        } else {
+            if (stack.empty()) break;
+            const uint2 e = stack.pop();
+            if (e.y == 0u) {  // sentinel: leave the instance
+                tr = make_trav_ray(ray.o, ray.d, ray.tmin);
+                in_blas = false;
+            } else if (e.y & 0xff000000u) ngroup = e;
+            else tgroup = e;
         }
     }
 }

@@ -232,6 +232,13 @@ void SceneDescription::blas_transform(const Mat4 &transform, size_t index) {
 void SceneDescription::blas_transforms(const std::vector<Mat4> &transforms) {
     for (size_t i = 0; i < transforms.size(); i++) blas_transform(transforms[i], i);
 }
+uint32_t SceneDescription::add_instance(size_t source_instance, const Mat4 &transform, uint32_t material_index) {
+    uint32_t id = 0;
+    ctx_->check(solb_scene_add_instance(h_, (uint32_t)source_instance, transform.data(), material_index, &id));
+    return id;
+}
+void SceneDescription::set_accel_mode(SolbAccelMode mode) { ctx_->check(solb_scene_set_accel_mode(h_, (uint32_t)mode)); }
+void SceneDescription::accel_build() { ctx_->check(solb_accel_build(h_)); }
 void SceneDescription::tlas_regenerate() { ctx_->check(solb_tlas_regenerate(h_)); }
 void SceneDescription::update() { ctx_->check(solb_scene_update(h_)); }
 size_t SceneDescription::blas_count() const {

@@ -164,6 +164,11 @@ public:
     // BLAS == instance index, which is what the name says and what single-section meshes make identical.
     void blas_transform(const Mat4 &transform, size_t index);
     void blas_transforms(const std::vector<Mat4> &transforms);
+    // Beyond the reference (its TODO at src/ray/mod.rs:122): one more instance of the BLAS `source_instance` uses; returns the
+    // new gl_InstanceID.  accel_mode SOLB_ACCEL_TWO_LEVEL keeps BLASes shared and lets tlas_regenerate rebuild the TLAS only.
+    uint32_t add_instance(size_t source_instance, const Mat4 &transform, uint32_t material_index);
+    void set_accel_mode(SolbAccelMode mode);
+    void accel_build();
     void tlas_regenerate();  // the reference takes the command buffer; launches are stream-ordered here
     void update();
     std::vector<SceneInstance> instances() const;

@@ -49,14 +49,21 @@ struct solb_scene {
     solb_ctx *ctx = nullptr;
     std::vector<SolbSceneInstance> instances;  // as the reference's shader would see them
     std::vector<DeviceInstance> h_inst;
-    std::vector<uint32_t> h_first_tri;
-    uint32_t n_tris = 0, n_vertices = 0, n_indices = 0;
+    std::vector<uint32_t> h_first_tri;       // per-instance triangle prefix (flattened build)
+    std::vector<DeviceBlas> h_blas;          // unique geometry: one per primitive section
+    std::vector<SolbMaterialInfo> materials; // kept for solb_scene_add_instance
+    uint32_t n_tris = 0, n_geom_tris = 0, n_vertices = 0, n_indices = 0;
     float4 *d_vertices = nullptr;
     uint32_t *d_indices = nullptr, *d_first_tri = nullptr;
     DeviceInstance *d_inst = nullptr;
+    DeviceBlas *d_blas = nullptr;
     ShadeRecord *d_shade = nullptr;
+    size_t inst_capacity = 0;                // instances d_inst / d_first_tri can hold
     AccelStorage accel;
-    bool built = false, dirty = false;
+    uint32_t accel_mode = SOLB_ACCEL_FLAT;
+    bool built = false;
+    bool dirty = false;       // an instance transform changed since the last build / TLAS regenerate
+    bool needs_build = false; // instances were added or the mode changed: the whole structure must be rebuilt
     DeviceSceneView view() const {
         DeviceSceneView v;
         v.n_instances = (uint32_t)h_inst.size();
@@ -65,6 +72,9 @@ struct solb_scene {
         v.instances = d_inst;
         v.vertices = d_vertices;
         v.indices = d_indices;
+        v.n_blas = (uint32_t)h_blas.size();
+        v.n_geom_tris = n_geom_tris;
+        v.blas = d_blas;
         return v;
     }
 };
@@ -280,12 +290,21 @@ SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32
             mat4_inverse(md.transform, inv);
             mat4_transpose(inv, si.transform_it);  // src/ray/mod.rs:116
             s->instances.push_back(si);
+            DeviceBlas db;
+            db.first_vertex = vbase + sec.first_vertex;
+            db.first_index = ibase + sec.first_index;
+            db.n_indices = sec.n_indices;
+            db.first_tri = s->n_geom_tris;
             DeviceInstance di;
             memset(&di, 0, sizeof(di));
-            di.first_vertex = vbase + sec.first_vertex;
-            di.first_index = ibase + sec.first_index;
-            di.n_indices = sec.n_indices;
+            di.first_vertex = db.first_vertex;
+            di.first_index = db.first_index;
+            di.n_indices = db.n_indices;
             di.material = sec.material_index;
+            di.blas = (uint32_t)s->h_blas.size();  // one BLAS and one instance per section (src/ray/mod.rs:122)
+            di.shade_first_tri = db.first_tri;
+            s->h_blas.push_back(db);
+            s->n_geom_tris += sec.n_indices / 3;
             memcpy(di.transform, si.transform, sizeof(di.transform));
             memcpy(di.transform_it, si.transform_it, sizeof(di.transform_it));
             memcpy(di.mat, &materials[sec.material_index], sizeof(di.mat));  // materials[gl_InstanceID]
@@ -296,19 +315,23 @@ SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32
     }
     s->n_vertices = (uint32_t)(verts.size() / 16);
     s->n_indices = (uint32_t)indices.size();
+    if (materials && n_materials) s->materials.assign(materials, materials + n_materials);
     const size_t ni = s->h_inst.size();
+    s->inst_capacity = std::max<size_t>(ni, 1);
     CU(ctx, cudaMalloc((void **)&s->d_vertices, std::max<size_t>(verts.size(), 16) * sizeof(float)));
     CU(ctx, cudaMalloc((void **)&s->d_indices, std::max<size_t>(indices.size(), 1) * sizeof(uint32_t)));
-    CU(ctx, cudaMalloc((void **)&s->d_first_tri, (ni + 1) * sizeof(uint32_t)));
-    CU(ctx, cudaMalloc((void **)&s->d_inst, std::max<size_t>(ni, 1) * sizeof(DeviceInstance)));
-    CU(ctx, cudaMalloc((void **)&s->d_shade, std::max<size_t>(s->n_tris, 1) * sizeof(ShadeRecord)));
+    CU(ctx, cudaMalloc((void **)&s->d_first_tri, (s->inst_capacity + 1) * sizeof(uint32_t)));
+    CU(ctx, cudaMalloc((void **)&s->d_inst, s->inst_capacity * sizeof(DeviceInstance)));
+    CU(ctx, cudaMalloc((void **)&s->d_blas, std::max<size_t>(s->h_blas.size(), 1) * sizeof(DeviceBlas)));
+    CU(ctx, cudaMalloc((void **)&s->d_shade, std::max<size_t>(s->n_geom_tris, 1) * sizeof(ShadeRecord)));
     cudaStream_t st = ctx->stream;
     if (!verts.empty()) CU(ctx, cudaMemcpyAsync(s->d_vertices, verts.data(), verts.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     if (!indices.empty()) CU(ctx, cudaMemcpyAsync(s->d_indices, indices.data(), indices.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(s->d_first_tri, s->h_first_tri.data(), (ni + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     if (ni) CU(ctx, cudaMemcpyAsync(s->d_inst, s->h_inst.data(), ni * sizeof(DeviceInstance), cudaMemcpyHostToDevice, st));
+    if (ni) CU(ctx, cudaMemcpyAsync(s->d_blas, s->h_blas.data(), s->h_blas.size() * sizeof(DeviceBlas), cudaMemcpyHostToDevice, st));
     CU(ctx, launch_build_shade_records(st, s->view(), s->d_shade));
-    ctx->launches += s->n_tris ? 1 : 0;
+    ctx->launches += s->n_geom_tris ? 1 : 0;
     CU(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope
     guard.s = nullptr;
     *out = s;
@@ -319,11 +342,30 @@ SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32
 SOLB_API int solb_scene_destroy(solb_scene *s) {
     if (!s) return SOLB_OK;
     if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
-    cudaFree(s->d_vertices); cudaFree(s->d_indices); cudaFree(s->d_first_tri); cudaFree(s->d_inst); cudaFree(s->d_shade);
+    cudaFree(s->d_vertices); cudaFree(s->d_indices); cudaFree(s->d_first_tri); cudaFree(s->d_inst); cudaFree(s->d_blas);
+    cudaFree(s->d_shade);
     s->accel.release();
     solb_ctx *ctx = s->ctx;
     delete s;
     if (ctx) ctx_release(ctx);
+    return SOLB_OK;
+}
+
+// instance records + per-instance triangle prefix -> device (grows the arrays after solb_scene_add_instance)
+static int upload_instances(solb_scene *s) {
+    solb_ctx *ctx = s->ctx;
+    const size_t ni = s->h_inst.size();
+    if (ni > s->inst_capacity) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(s->d_inst); cudaFree(s->d_first_tri);
+        s->d_inst = nullptr; s->d_first_tri = nullptr;
+        s->inst_capacity = ni + ni / 2;
+        CU(ctx, cudaMalloc((void **)&s->d_first_tri, (s->inst_capacity + 1) * sizeof(uint32_t)));
+        CU(ctx, cudaMalloc((void **)&s->d_inst, s->inst_capacity * sizeof(DeviceInstance)));
+    }
+    CU(ctx, cudaMemcpyAsync(s->d_first_tri, s->h_first_tri.data(), (ni + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (ni) CU(ctx, cudaMemcpyAsync(s->d_inst, s->h_inst.data(), ni * sizeof(DeviceInstance), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SOLB_OK;
 }
 
@@ -337,8 +379,11 @@ static int do_build(solb_scene *s) {
     if (const char *v = getenv("SOLB_TREELET_PASSES")) opt.treelet_passes = std::max(0, std::min(8, atoi(v)));
     if (const char *v = getenv("SOLB_TREELET_COOP")) opt.coop_treelet = atoi(v) != 0;
     if (const char *v = getenv("SOLB_TREELET_GAMMA")) opt.treelet_gamma = std::max(3, std::min(1 << 20, atoi(v)));
+    int rc = upload_instances(s);
+    if (rc != SOLB_OK) return rc;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = build_accel(ctx->stream, s->view(), s->accel, opt, &ctx->launches);
+    cudaError_t e = s->accel_mode == SOLB_ACCEL_TWO_LEVEL ? build_accel_two_level(ctx->stream, s->view(), s->accel, opt, &ctx->launches)
+                                                          : build_accel(ctx->stream, s->view(), s->accel, opt, &ctx->launches);
     if (e == cudaErrorLaunchOutOfResources) return fail(ctx, SOLB_ERR_OVERFLOW, "acceleration structure deeper than the traversal stack");
     if (e != cudaSuccess) return fail_cuda(ctx, e, "build_accel");
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -346,6 +391,7 @@ static int do_build(solb_scene *s) {
     CU(ctx, cudaEventElapsedTime(&ctx->last_build_ms, ctx->ev0, ctx->ev1));
     s->built = true;
     s->dirty = false;
+    s->needs_build = false;
     return SOLB_OK;
 }
 
@@ -374,22 +420,67 @@ SOLB_API int solb_scene_update(solb_scene *s) {
     if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
     solb_ctx *ctx = s->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
-    if (!s->h_inst.empty()) {
-        CU(ctx, cudaMemcpyAsync(s->d_inst, s->h_inst.data(), s->h_inst.size() * sizeof(DeviceInstance), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    return SOLB_OK;
+    return upload_instances(s);
 }
 
 SOLB_API int solb_tlas_regenerate(solb_scene *s) {
     if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
     if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "solb_tlas_regenerate before solb_accel_build");
-    if (!s->dirty) return SOLB_OK;
+    if (!s->dirty && !s->needs_build) return SOLB_OK;
     SOLB_TRY
-    int rc = solb_scene_update(s);  // the rebuild bakes the transforms: they must be on the device
+    solb_ctx *ctx = s->ctx;
+    if (s->needs_build || s->accel_mode != SOLB_ACCEL_TWO_LEVEL || !s->accel.two_level) return do_build(s);  // flattened: the rebuild bakes the transforms
+    // two-level: the BLASes are untouched, only the TLAS over the moved instances is rebuilt
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = upload_instances(s);
     if (rc != SOLB_OK) return rc;
-    return do_build(s);
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = rebuild_tlas(ctx->stream, s->view(), s->accel, &ctx->launches);
+    if (e == cudaErrorLaunchOutOfResources) return fail(ctx, SOLB_ERR_OVERFLOW, "acceleration structure deeper than the traversal stack");
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "rebuild_tlas");
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    CU(ctx, cudaEventElapsedTime(&ctx->last_build_ms, ctx->ev0, ctx->ev1));
+    s->dirty = false;
+    return SOLB_OK;
     SOLB_CATCH(s->ctx)
+}
+
+SOLB_API int solb_scene_add_instance(solb_scene *s, uint32_t source_instance, const float transform[16], uint32_t material_index,
+                                     uint32_t *out_index) {
+    if (!s || !transform) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "solb_scene_add_instance: null argument");
+    if (source_instance >= s->h_inst.size()) return fail(s->ctx, SOLB_ERR_INVALID, "source instance out of range");
+    if (material_index >= s->materials.size()) return fail(s->ctx, SOLB_ERR_INVALID, "material index out of range");
+    SOLB_TRY
+    const DeviceInstance src = s->h_inst[source_instance];
+    if ((uint64_t)s->n_tris + src.n_indices / 3 > 0x7fffffffull) return fail(s->ctx, SOLB_ERR_INVALID, "too many triangles");
+    SolbSceneInstance si;
+    memset(&si, 0, sizeof(si));
+    si.id = (uint32_t)s->instances.size();
+    memcpy(si.transform, transform, sizeof(si.transform));
+    float inv[16];
+    mat4_inverse(transform, inv);
+    mat4_transpose(inv, si.transform_it);
+    DeviceInstance di = src;  // same BLAS: geometry range, blas, shade_first_tri
+    di.material = material_index;
+    memcpy(di.transform, si.transform, sizeof(di.transform));
+    memcpy(di.transform_it, si.transform_it, sizeof(di.transform_it));
+    memcpy(di.mat, &s->materials[material_index], sizeof(di.mat));
+    s->instances.push_back(si);
+    s->h_inst.push_back(di);
+    s->n_tris += di.n_indices / 3;
+    s->h_first_tri.push_back(s->n_tris);
+    s->needs_build = true;
+    if (out_index) *out_index = si.id;
+    return SOLB_OK;
+    SOLB_CATCH(s->ctx)
+}
+
+SOLB_API int solb_scene_set_accel_mode(solb_scene *s, uint32_t mode) {
+    if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
+    if (mode > SOLB_ACCEL_TWO_LEVEL) return fail(s->ctx, SOLB_ERR_INVALID, "unknown acceleration-structure mode");
+    if (mode != s->accel_mode) { s->accel_mode = mode; s->needs_build = true; }
+    return SOLB_OK;
 }
 
 SOLB_API int solb_scene_instance_count(solb_scene *s, uint32_t *out) {
@@ -405,12 +496,23 @@ SOLB_API int solb_scene_get_instances(solb_scene *s, SolbSceneInstance *out, uin
     return SOLB_OK;
 }
 
+SOLB_API int solb_scene_instance_triangles(solb_scene *s, uint32_t *out, uint32_t capacity) {
+    if (!s || (!out && capacity)) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (capacity < s->h_inst.size()) return fail(s->ctx, SOLB_ERR_INVALID, "buffer too small");
+    for (size_t i = 0; i < s->h_inst.size(); i++) out[i] = s->h_inst[i].n_indices / 3;
+    return SOLB_OK;
+}
+
 SOLB_API int solb_accel_info(solb_scene *s, SolbAccelInfo *out) {
     if (!s || !out) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
     if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "acceleration structure not built");
     memset(out, 0, sizeof(*out));
     out->n_instances = (uint32_t)s->instances.size();
     out->n_triangles = s->accel.n_tris;
+    out->mode = s->accel.two_level ? SOLB_ACCEL_TWO_LEVEL : SOLB_ACCEL_FLAT;
+    out->n_blas = (uint32_t)s->h_blas.size();
+    out->n_tlas_nodes = s->accel.n_tlas_wide;
+    out->tlas_depth = s->accel.tlas_depth;
     out->n_wide_nodes = s->accel.n_wide;
     out->wide_depth = s->accel.depth;
     out->n_binary_nodes = s->accel.n_binary;
@@ -543,6 +645,7 @@ static void fill_frame_consts(FrameConsts &fc, const SolbSceneUniforms *u, uint3
 static int check_trace_args(solb_scene *s, const SolbSceneUniforms *u) {
     if (!s || !u) return fail(s ? s->ctx : nullptr, SOLB_ERR_INVALID, "trace: null scene/uniforms");
     if (!s->built) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "trace before solb_accel_build");
+    if (s->needs_build) return fail(s->ctx, SOLB_ERR_NOT_BUILT, "instances were added or the mode changed: call solb_accel_build / solb_tlas_regenerate first");
     return SOLB_OK;
 }
 
@@ -718,7 +821,7 @@ SOLB_API int solb_trace_debug(solb_scene *s, const SolbSceneUniforms *u, solb_ta
 SOLB_API int solb_trace_rays(solb_scene *s, const float *rays, uint32_t n, uint32_t *hits, float *t_out) {
     if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
     solb_ctx *ctx = s->ctx;
-    if (!s->built) return fail(ctx, SOLB_ERR_NOT_BUILT, "trace before solb_accel_build");
+    if (!s->built || s->needs_build) return fail(ctx, SOLB_ERR_NOT_BUILT, "trace before solb_accel_build");
     if (n == 0) return SOLB_OK;
     if (!rays || !hits) return fail(ctx, SOLB_ERR_INVALID, "solb_trace_rays: null argument");
     SOLB_TRY

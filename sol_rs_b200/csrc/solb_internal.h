@@ -7,23 +7,37 @@
 
 namespace solb {
 
-// One reference instance == one primitive section == one BLAS (src/ray/mod.rs:78-134).
-struct DeviceInstance {
+// One primitive section == one BLAS (src/ray/mod.rs:78-134): geometry ranges in the concatenated arrays.
+struct DeviceBlas {
     uint32_t first_vertex;  // section's first vertex in the concatenated vertex array
     uint32_t first_index;   // section's first index in the concatenated index array
     uint32_t n_indices;
+    uint32_t first_tri;     // first geometry triangle (= first shading record) of this BLAS
+};
+
+// One instance.  The reference creates exactly one per BLAS (src/ray/mod.rs:122 "TODO: support multiple instances
+// per BLAS"); solb_scene_add_instance adds further instances of an existing BLAS.
+struct DeviceInstance {
+    uint32_t first_vertex;  // copy of the BLAS's geometry range
+    uint32_t first_index;
+    uint32_t n_indices;
     uint32_t material;      // section.material_index (kept for inspection)
+    uint32_t blas;          // geometry this instance places
+    uint32_t shade_first_tri;  // DeviceBlas.first_tri of that geometry
     float transform[16];    // SceneInstance.transform (column-major)
     float transform_it[16]; // SceneInstance.transform_it = inverse().transpose()
     float mat[12];          // MaterialInfo of materials[gl_InstanceID]: base @0, emissive @4, metallic @8, roughness @9
 };
+static_assert(sizeof(DeviceInstance) == 200, "DeviceInstance layout is mirrored by tests/emu_lib.py");
 
 struct DeviceSceneView {
-    uint32_t n_instances, n_tris;
-    const uint32_t *inst_first_tri;  // [n_instances + 1] exclusive prefix of triangle counts
+    uint32_t n_instances, n_tris;    // n_tris: triangles over all instances (flattened build)
+    const uint32_t *inst_first_tri;  // [n_instances + 1] exclusive prefix of per-instance triangle counts
     const DeviceInstance *instances;
     const float4 *vertices;          // reference ModelVertex array, 4 x float4 per vertex: pos, color, normal, uv
     const uint32_t *indices;         // section-relative u32 indices
+    uint32_t n_blas, n_geom_tris;    // unique geometry: BLAS count, triangles over all BLASes
+    const DeviceBlas *blas;          // [n_blas], first_tri ascending
 };
 
 // 112-byte shading record per global triangle: the three ModelVertex {pos, normal, color} triples the
@@ -51,16 +65,27 @@ struct FrameConsts {
 struct AccelStorage {
     uint4 *nodes_u4() const { return (uint4 *)nodes; }
     float4 *tris_f4() const { return (float4 *)tris; }
+    float4 *inst_leaves_f4() const { return (float4 *)inst_leaves; }
     Node8 *nodes = nullptr;
     Tri48 *tris = nullptr;
     uint32_t n_wide = 0, n_tris = 0, depth = 0, n_binary = 0;
     float sah_lbvh = 0.0f, sah_final = 0.0f;
     float lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+    // two-level mode (SOLB_ACCEL_TWO_LEVEL): nodes[0, tlas_cap) = TLAS region (root = node 0, rebuilt in place by
+    // rebuild_tlas), nodes[tlas_cap + b] = root of BLAS b, then the BLAS interiors; tris are object-space.
+    bool two_level = false;
+    InstLeaf *inst_leaves = nullptr;   // [n_instances] TLAS leaf records in TLAS leaf order
+    float4 *blas_box = nullptr;        // [2 * n_blas] object-space root boxes (lo, hi)
+    uint32_t tlas_cap = 0, n_blas = 0, n_tlas_wide = 0, tlas_depth = 0, blas_depth = 0;
     void release() {
         if (nodes) cudaFree(nodes);
         if (tris) cudaFree(tris);
-        nodes = nullptr; tris = nullptr;
+        if (inst_leaves) cudaFree(inst_leaves);
+        if (blas_box) cudaFree(blas_box);
+        nodes = nullptr; tris = nullptr; inst_leaves = nullptr; blas_box = nullptr;
         n_wide = n_tris = depth = n_binary = 0;
+        two_level = false;
+        tlas_cap = n_blas = n_tlas_wide = tlas_depth = blas_depth = 0;
     }
 };
 
@@ -71,6 +96,11 @@ struct BuildOptions {
 };
 
 cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt, uint64_t *launches);
+// Two-level build: every BLAS in object space in ONE batched pass (segmented Morton keys), then the TLAS over the
+// instances' world boxes.  rebuild_tlas redoes only the second half (TLAS::regenerate, src/ray/acceleration.rs:402-467).
+cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt,
+                                  uint64_t *launches);
+cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, uint64_t *launches);
 cudaError_t sort_pairs_device(cudaStream_t st, uint64_t *keys, uint32_t *vals, uint32_t n, int key_bits);
 
 }  // namespace solb

@@ -37,6 +37,15 @@ struct DevStack {
     stack.loc = stack_spill;                                     \
     stack.sp = 0
 
+// flattened (TL = false) or two-level (TL = true) closest hit
+template <bool STATS, bool TL, class Stack>
+__device__ __forceinline__ void trace_any(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
+                                          const float4 *__restrict__ inst_leaves, const Ray &ray, Hit &hit, Stack &stack,
+                                          TraceCounters *ctr) {
+    if (TL) trace_closest_2l<STATS>(nodes, tris, inst_leaves, ray, hit, stack, ctr);
+    else trace_closest<STATS>(nodes, tris, ray, hit, stack, ctr);
+}
+
 // stats slots (unsigned long long each)
 enum { ST_RAYS = 0, ST_HITS = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4 };
 
@@ -61,9 +70,10 @@ static uint32_t pixel_grid_blocks(uint32_t width, uint32_t height) {
 
 // ---------------------------------------------------------------------------------------------------
 // 3-ray-debug: debug.rgen:18-37 + debug.rchit:9-13 + debug.rmiss:6-9, plus the ids the parity gate needs
+template <bool TL>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, const uint4 *__restrict__ nodes,
-                                                       const float4 *__restrict__ tris, uint32_t *render, uint2 *ids,
-                                                       float4 *attribs, unsigned long long *stats) {
+                                                       const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
+                                                       uint32_t *render, uint2 *ids, float4 *attribs, unsigned long long *stats) {
     SOLB_DECL_STACK();
     uint32_t x, y;
     const bool active = thread_pixel(fc.width, fc.height, x, y);
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, con
         r.tmin = 0.001f;                                          // debug.rgen:32-33
         r.tmax = 1000.0f;
         Hit h;
-        trace_closest<false>(nodes, tris, r, h, stack, (TraceCounters *)nullptr);
+        trace_any<false, TL>(nodes, tris, inst_leaves, r, h, stack, (TraceCounters *)nullptr);
         nr = 1;
         float3 hv = r.d;  // debug.rgen:28: payload preset to the direction, the miss shader leaves it
         if (h.inst != SOLB_MISS) { hv = f3(1.0f - h.u - h.v, h.u, h.v); nh = 1; }  // debug.rchit:11-12
@@ -89,9 +99,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, con
 }
 
 // traceRayEXT for arbitrary rays (tests)
+template <bool TL>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
-                                                            const float4 *__restrict__ rays, uint32_t n, uint4 *hits, float *t_out,
-                                                            unsigned long long *stats) {
+                                                            const float4 *__restrict__ inst_leaves, const float4 *__restrict__ rays,
+                                                            uint32_t n, uint4 *hits, float *t_out, unsigned long long *stats) {
     SOLB_DECL_STACK();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     TraceCounters ctr = { 0, 0 };
@@ -102,7 +113,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restr
         r.o = f3(a.x, a.y, a.z); r.tmin = a.w;
         r.d = f3(b.x, b.y, b.z); r.tmax = b.w;
         Hit h;
-        trace_closest<true>(nodes, tris, r, h, stack, &ctr);
+        trace_any<true, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);
         hits[i] = make_uint4(h.inst, h.prim, __float_as_uint(h.u), __float_as_uint(h.v));
         if (t_out) t_out[i] = h.inst != SOLB_MISS ? h.t : 0.0f;
         nr = 1;
@@ -115,9 +126,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restr
 // ---------------------------------------------------------------------------------------------------
 // 5-pathtrace, megakernel schedule: pathtrace.rgen:39-104 with the sample and bounce loops flattened
 // into one loop so a lane that ends a path immediately starts its next sample.
-template <bool STATS>
+template <bool STATS, bool TL>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                                 const float4 *__restrict__ tris,
+                                                                const float4 *__restrict__ inst_leaves,
                                                                 const DeviceInstance *__restrict__ instances,
                                                                 const ShadeRecord *__restrict__ shade, float4 *accum,
                                                                 uint32_t *render, unsigned long long *stats) {
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConst
         while (sample < fc.spp) {
             Hit h;
             stack.sp = 0;
-            trace_closest<STATS>(nodes, tris, r, h, stack, &ctr);  // :65-76
+            trace_any<STATS, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);  // :65-76
             nr++;
             bool end_path;
             if (h.inst != SOLB_MISS) {
@@ -245,10 +257,12 @@ constexpr uint32_t WF_BATCH = 128;
 #ifndef SOLB_WF_MIN_CTAS
 #define SOLB_WF_MIN_CTAS 7
 #endif
-template <bool STATS>
+// TL: two-level scenes.  A lane is either in the TLAS (its "triangle" groups are instance leaves: the triangle step
+// enters the instance) or inside a BLAS; the sentinel popped at the end of a BLAS walk reloads the world-space ray.
+template <bool STATS, bool TL>
 __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
-                                                          const float4 *__restrict__ tris, WavefrontState ws, int qi,
-                                                          unsigned long long *stats, const TraceTuning tune) {
+                                                          const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
+                                                          WavefrontState ws, int qi, unsigned long long *stats, const TraceTuning tune) {
     SOLB_DECL_STACK();
     const uint32_t n = ws.counters[qi];
     const uint32_t *__restrict__ queue = qi ? ws.queue[1] : ws.queue[0];
@@ -268,6 +282,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(cons
     Hit hit;
     hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f;
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+    bool in_blas = false;          // TL only
+    uint32_t cur_inst = SOLB_MISS; // TL only: instance being walked
     uint32_t b_ray = 0;  // lanes holding a ray (warp-uniform)
     for (;;) {
         // ---- refill idle lanes ----
@@ -295,6 +311,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(cons
                     ngroup = SOLB_ROOT_GROUP;
                     tgroup = make_uint2(0u, 0u);
                     stack.sp = 0;
+                    in_blas = false;
                     has_ray = true;
                     nr++;
                 }
@@ -311,8 +328,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(cons
         const int nt = __popc(__ballot_sync(0xffffffffu, w_tri));
         if (nt > 0 && nt * tune.tri_weight >= nn * tune.node_weight) {
             if (w_tri) {
-                trav_tri_step(tris, tr, tmax, tgroup, hit);
-                if (STATS) ctr.tris++;
+                if (TL && !in_blas) {
+                    trav_enter_instance(inst_leaves, tr.o, tr.d, tr, ngroup, tgroup, cur_inst, stack);
+                    in_blas = true;
+                } else {
+                    if (trav_tri_step(tris, tr, tmax, tgroup, hit) && TL) hit.inst = cur_inst;
+                    if (STATS) ctr.tris++;
+                }
             }
         } else if (w_node) {
             if (tgroup.y) stack.push(tgroup);  // postpone the pending triangles
@@ -326,7 +348,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(cons
                 has_ray = false;
             } else {
                 const uint2 e = stack.pop();
-                if (e.y & 0xff000000u) ngroup = e; else tgroup = e;
+                if (TL && e.y == 0u) {  // sentinel: back to the TLAS with the world-space ray
+                    const float4 o = ws.ray_o[pixel], d = ws.ray_d[pixel];
+                    tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
+                    in_blas = false;
+                } else if (e.y & 0xff000000u) ngroup = e;
+                else tgroup = e;
             }
         }
         b_ray = __ballot_sync(0xffffffffu, has_ray);
@@ -626,8 +653,10 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, Wavefr
 
 // ---------------------------------------------------------------------------------------------------
 // 4-ray-ao: ao.rgen:37-83 + ao.rchit:45-88 + ao.rmiss:7-10, one thread per pixel
+template <bool TL>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_ao(const FrameConsts fc, const uint4 *__restrict__ nodes,
-                                                    const float4 *__restrict__ tris, const DeviceInstance *__restrict__ instances,
+                                                    const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
+                                                    const DeviceInstance *__restrict__ instances,
                                                     const ShadeRecord *__restrict__ shade, const uint32_t *__restrict__ blue,
                                                     uint32_t blue_w, uint32_t blue_h, float4 *image, unsigned long long *stats) {
     SOLB_DECL_STACK();
@@ -652,7 +681,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_ao(const FrameConsts fc, const 
             for (;;) {
                 Hit h;
                 stack.sp = 0;
-                trace_closest<false>(nodes, tris, r, h, stack, (TraceCounters *)nullptr);
+                trace_any<false, TL>(nodes, tris, inst_leaves, r, h, stack, (TraceCounters *)nullptr);
                 nr++;
                 if (h.inst == SOLB_MISS) break;  // ao.rmiss: done = 1
                 nh++;
@@ -692,15 +721,15 @@ __global__ void __launch_bounds__(256) k_resolve_sum(const float4 *sum, float4 *
 // de-index the reference vertex layout into per-triangle shading records (object space)
 __global__ void k_build_shade_records(const DeviceSceneView sv, ShadeRecord *out) {
     const float4 *__restrict__ vertices = sv.vertices;  // 4 float4 per ModelVertex
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= sv.n_tris) return;
-    uint32_t lo = 0, hi = sv.n_instances;
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;  // geometry triangle: records are shared by all instances of a BLAS
+    if (g >= sv.n_geom_tris) return;
+    uint32_t lo = 0, hi = sv.n_blas;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (sv.inst_first_tri[mid] <= g) lo = mid; else hi = mid;
+        if (sv.blas[mid].first_tri <= g) lo = mid; else hi = mid;
     }
-    const DeviceInstance &di = sv.instances[lo];
-    const uint32_t prim = g - sv.inst_first_tri[lo];
+    const DeviceBlas di = sv.blas[lo];
+    const uint32_t prim = g - di.first_tri;
     float f[28];
     for (int k = 0; k < 3; k++) {
         const uint32_t vi = di.first_vertex + sv.indices[di.first_index + 3 * prim + k];
@@ -716,21 +745,25 @@ __global__ void k_build_shade_records(const DeviceSceneView sv, ShadeRecord *out
 // ---------------------------------------------------------------------------------------------------
 // host-side launch wrappers
 cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &sv, ShadeRecord *out) {
-    if (sv.n_tris == 0) return cudaSuccess;
-    k_build_shade_records<<<(sv.n_tris + 255) / 256, 256, 0, st>>>(sv, out);
+    if (sv.n_geom_tris == 0) return cudaSuccess;
+    k_build_shade_records<<<(sv.n_geom_tris + 255) / 256, 256, 0, st>>>(sv, out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_debug(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, uint32_t *render, uint2 *ids,
                          float4 *attribs, unsigned long long *stats) {
-    k_debug<<<pixel_grid_blocks(fc.width, fc.height), TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), render, ids, attribs, stats);
+    const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
+    if (as.two_level) k_debug<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), render, ids, attribs, stats);
+    else k_debug<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, render, ids, attribs, stats);
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const float4 *rays, uint32_t n, uint4 *hits, float *t_out,
                               unsigned long long *stats) {
     if (n == 0) return cudaSuccess;
-    k_trace_rays<<<(n + TRACE_BLOCK - 1) / TRACE_BLOCK, TRACE_BLOCK, 0, st>>>(as.nodes_u4(), as.tris_f4(), rays, n, hits, t_out, stats);
+    const uint32_t blocks = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
+    if (as.two_level) k_trace_rays<true><<<blocks, TRACE_BLOCK, 0, st>>>(as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), rays, n, hits, t_out, stats);
+    else k_trace_rays<false><<<blocks, TRACE_BLOCK, 0, st>>>(as.nodes_u4(), as.tris_f4(), nullptr, rays, n, hits, t_out, stats);
     return cudaGetLastError();
 }
 
@@ -738,18 +771,23 @@ cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const 
                                   const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
                                   bool collect) {
     const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
-    if (collect)
-        k_pathtrace_mega<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), instances, shade, accum, render, stats);
+    const float4 *il = as.inst_leaves_f4();
+    if (as.two_level) {
+        if (collect) k_pathtrace_mega<true, true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, instances, shade, accum, render, stats);
+        else k_pathtrace_mega<false, true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, instances, shade, accum, render, stats);
+    } else if (collect)
+        k_pathtrace_mega<true, false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, instances, shade, accum, render, stats);
     else
-        k_pathtrace_mega<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), instances, shade, accum, render, stats);
+        k_pathtrace_mega<false, false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, instances, shade, accum, render, stats);
     return cudaGetLastError();
 }
 
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
                       unsigned long long *stats) {
-    k_ao<<<pixel_grid_blocks(fc.width, fc.height), TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), instances, shade, blue, bw,
-                                                                         bh, image, stats);
+    const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
+    if (as.two_level) k_ao<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), instances, shade, blue, bw, bh, image, stats);
+    else k_ao<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, instances, shade, blue, bw, bh, image, stats);
     return cudaGetLastError();
 }
 
@@ -812,12 +850,16 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
                 }
                 cudaEventRecord((*events)[*n_events_used], st);
             }
-            if (tune.pool && L.spill[k]) {
+            if (as.two_level) {
+                const float4 *il = as.inst_leaves_f4();
+                if (collect) k_wf_trace<true, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
+                else k_wf_trace<false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
+            } else if (tune.pool && L.spill[k]) {
                 const int pool_grid = L.sm_count * tune.pool_ctas_per_sm;
                 if (collect) k_wf_trace_pool<true><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
                 else k_wf_trace_pool<false><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
-            } else if (collect) k_wf_trace<true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune);
-            else k_wf_trace<false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune);
+            } else if (collect) k_wf_trace<true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+            else k_wf_trace<false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
             if (events) {
                 cudaEventRecord((*events)[*n_events_used + 1], st);
                 *n_events_used += 2;

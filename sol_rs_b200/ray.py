@@ -23,11 +23,13 @@ class SceneDescription:
         self._lib = N.lib()
 
     @classmethod
-    def from_scene(cls, context, scene):
-        return cls.from_meshes(context, scene.meshes, [m.transform for m in scene.meshes], scene.materials)
+    def from_scene(cls, context, scene, accel_mode=N.ACCEL_FLAT):
+        return cls.from_meshes(context, scene.meshes, [m.transform for m in scene.meshes], scene.materials, accel_mode)
 
     @classmethod
-    def from_meshes(cls, context, meshes, mesh_transforms, materials):
+    def from_meshes(cls, context, meshes, mesh_transforms, materials, accel_mode=N.ACCEL_FLAT):
+        """accel_mode: N.ACCEL_FLAT (default, transforms baked into one hierarchy) or N.ACCEL_TWO_LEVEL (TLAS over shared
+        object-space BLASes, the reference's own split: src/ray/acceleration.rs)."""
         assert len(meshes) == len(mesh_transforms)
         L = N.lib()
         descs = (N.MeshDesc * max(len(meshes), 1))()
@@ -56,6 +58,7 @@ class SceneDescription:
                                     mats.shape[0], ctypes.byref(h)), context.handle)
         sd = cls(context, h)
         try:
+            N.check(L.solb_scene_set_accel_mode(h, int(accel_mode)), context.handle)
             N.check(L.solb_accel_build(h), context.handle)  # BLAS::new x n + TLAS::new + end_single_time_cmd
         except Exception:
             sd.close()
@@ -66,6 +69,21 @@ class SceneDescription:
         t = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
         N.check(self._lib.solb_instance_set_transform(self._h, int(index), t.ctypes.data_as(ctypes.POINTER(ctypes.c_float))),
                 self.context.handle)
+
+    def add_instance(self, source_instance, transform, material_index):
+        """One more instance of the BLAS `source_instance` uses (the reference's TODO at src/ray/mod.rs:122).
+        Returns the new gl_InstanceID.  Call accel_build() / tlas_regenerate() afterwards."""
+        t = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+        out = ctypes.c_uint32()
+        N.check(self._lib.solb_scene_add_instance(self._h, int(source_instance), t.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                                  int(material_index), ctypes.byref(out)), self.context.handle)
+        return out.value
+
+    def set_accel_mode(self, mode):
+        N.check(self._lib.solb_scene_set_accel_mode(self._h, int(mode)), self.context.handle)
+
+    def accel_build(self):
+        N.check(self._lib.solb_accel_build(self._h), self.context.handle)
 
     def blas_transforms(self, transforms):
         for i, t in enumerate(transforms):
@@ -81,6 +99,16 @@ class SceneDescription:
         n = ctypes.c_uint32()
         N.check(self._lib.solb_scene_instance_count(self._h, ctypes.byref(n)), self.context.handle)
         return n.value
+
+    def instance_triangles(self):
+        """triangle count of every instance (= of the BLAS it places)"""
+        return [int(n) for n in self._instance_tris()]
+
+    def _instance_tris(self):
+        n = self.blas_count()
+        out = (ctypes.c_uint32 * max(n, 1))()
+        N.check(self._lib.solb_scene_instance_triangles(self._h, out, n), self.context.handle)
+        return out[:n]
 
     def instances(self):
         n = self.blas_count()

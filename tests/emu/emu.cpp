@@ -26,117 +26,65 @@ struct EmuStack {
 
 struct EmuScene {
     std::vector<DeviceInstance> inst;
-    std::vector<uint32_t> first_tri;
-    std::vector<float4> vertices;  // 4 per vertex
+    std::vector<DeviceBlas> blas;
+    std::vector<uint32_t> first_tri;  // per-instance triangle prefix (flattened build)
+    std::vector<float4> vertices;     // 4 per vertex
     std::vector<uint32_t> indices;
-    std::vector<ShadeRecord> shade;
+    std::vector<ShadeRecord> shade;   // per geometry triangle
     std::vector<Node8> nodes;
     std::vector<Tri48> tris;
-    uint32_t n_tris = 0, depth = 0;
+    std::vector<InstLeaf> inst_leaves;
+    bool two_level = false;
+    uint32_t n_tris = 0, n_geom_tris = 0, depth = 0, tlas_depth = 0;
     float sah_lbvh = 0, sah_final = 0;
     int max_stack = 0;
 };
 
-extern "C" {
+// binary radix tree over n >= 2 boxes: Morton sort, Karras links, refit, treelet passes (same per-element code as build.cu)
+struct EmuTree {
+    std::vector<BNode> bn;
+    std::vector<int> parent, count;
+    std::vector<float> cost;
+    std::vector<uint32_t> vals;  // sorted position -> primitive
+    int ni = 0;
+    float sah_lbvh = 0, sah_final = 0;
+};
 
-EmuScene *emu_scene_create(uint32_t n_inst, const DeviceInstance *inst, const float *vertices, uint32_t n_vertices,
-                           const uint32_t *indices, uint32_t n_indices) {
-    EmuScene *s = new EmuScene();
-    s->inst.assign(inst, inst + n_inst);
-    s->vertices.resize((size_t)n_vertices * 4);
-    memcpy(s->vertices.data(), vertices, (size_t)n_vertices * 64);
-    s->indices.assign(indices, indices + n_indices);
-    s->first_tri.push_back(0);
-    for (uint32_t i = 0; i < n_inst; i++) s->first_tri.push_back(s->first_tri.back() + inst[i].n_indices / 3);
-    s->n_tris = s->first_tri.back();
-    s->shade.resize(std::max<uint32_t>(s->n_tris, 1));
-    for (uint32_t i = 0; i < n_inst; i++)
-        for (uint32_t p = 0; p < inst[i].n_indices / 3; p++) {
-            float f[28];
-            for (int k = 0; k < 3; k++) {
-                uint32_t vi = inst[i].first_vertex + indices[inst[i].first_index + 3 * p + k];
-                const float4 pos = s->vertices[4 * (size_t)vi], col = s->vertices[4 * (size_t)vi + 1], nrm = s->vertices[4 * (size_t)vi + 2];
-                f[9 * k] = pos.x; f[9 * k + 1] = pos.y; f[9 * k + 2] = pos.z;
-                f[9 * k + 3] = nrm.x; f[9 * k + 4] = nrm.y; f[9 * k + 5] = nrm.z;
-                f[9 * k + 6] = col.x; f[9 * k + 7] = col.y; f[9 * k + 8] = col.z;
-            }
-            f[27] = 0;
-            ShadeRecord &r = s->shade[s->first_tri[i] + p];
-            for (int q = 0; q < 7; q++) r.q[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        }
-    return s;
-}
-
-void emu_scene_destroy(EmuScene *s) { delete s; }
-
-// Same pipeline as build.cu, run sequentially.  treelet_passes: 0 = plain LBVH.
-int emu_build(EmuScene *s, int treelet_passes, int gamma) {
-    const uint32_t n = s->n_tris;
-    s->nodes.clear(); s->tris.clear();
-    if (n == 0) {
-        ChildRef ch[8];
-        for (auto &c : ch) c.valid = 0;
-        s->nodes.resize(1);
-        encode_node8(s->nodes[0], f3(0, 0, 0), f3(0, 0, 0), 0, 0, ch);
-        s->depth = 1;
-        return 0;
-    }
-    std::vector<Tri48> tri_world(n);
-    std::vector<float3> plo(n), phi(n);
+static void emu_binary_tree(const std::vector<float3> &plo, const std::vector<float3> &phi, int treelet_passes, int gamma, EmuTree &T) {
+    const uint32_t n = (uint32_t)plo.size();
     float3 clo = f3(3.4e38f, 3.4e38f, 3.4e38f), chi = f3(-3.4e38f, -3.4e38f, -3.4e38f);
-    for (uint32_t i = 0; i < s->inst.size(); i++)
-        for (uint32_t p = 0; p < s->inst[i].n_indices / 3; p++) {
-            const uint32_t g = s->first_tri[i] + p;
-            float3 v[3];
-            for (int k = 0; k < 3; k++) {
-                uint32_t vi = s->inst[i].first_vertex + s->indices[s->inst[i].first_index + 3 * p + k];
-                const float4 pos = s->vertices[4 * (size_t)vi];
-                v[k] = mat4_mul_point(s->inst[i].transform, f3(pos.x, pos.y, pos.z));
-            }
-            tri_world[g].v0 = make_float4(v[0].x, v[0].y, v[0].z, u2f(i));
-            tri_world[g].v1 = make_float4(v[1].x, v[1].y, v[1].z, u2f(p));
-            tri_world[g].v2 = make_float4(v[2].x, v[2].y, v[2].z, u2f(g));
-            plo[g] = fmin3(v[0], fmin3(v[1], v[2]));
-            phi[g] = fmax3(v[0], fmax3(v[1], v[2]));
-            const float3 c = (plo[g] + phi[g]) * 0.5f;
-            clo = fmin3(clo, c); chi = fmax3(chi, c);
-        }
-    s->tris.resize(n);
-    if (n == 1) {
-        ChildRef ch[8];
-        for (auto &c : ch) c.valid = 0;
-        ch[0].valid = 1; ch[0].lo = plo[0]; ch[0].hi = phi[0]; ch[0].is_inner = 0; ch[0].tri_offset = 0; ch[0].tri_count = 1;
-        s->nodes.resize(1);
-        encode_node8(s->nodes[0], plo[0], phi[0], 0, 0, ch);
-        s->tris[0] = tri_world[0];
-        s->depth = 1;
-        return 0;
+    for (uint32_t g = 0; g < n; g++) {
+        const float3 c = (plo[g] + phi[g]) * 0.5f;
+        clo = fmin3(clo, c); chi = fmax3(chi, c);
     }
     const float3 ext = chi - clo;
     const float3 inv = f3(ext.x > 0 ? 1.0f / ext.x : 0, ext.y > 0 ? 1.0f / ext.y : 0, ext.z > 0 ? 1.0f / ext.z : 0);
     std::vector<uint64_t> keys(n);
-    std::vector<uint32_t> vals(n);
-    for (uint32_t g = 0; g < n; g++) { keys[g] = morton63((plo[g] + phi[g]) * 0.5f, clo, inv); vals[g] = g; }
+    for (uint32_t g = 0; g < n; g++) keys[g] = morton63((plo[g] + phi[g]) * 0.5f, clo, inv);
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
     std::vector<uint64_t> skeys(n);
-    for (uint32_t i = 0; i < n; i++) { skeys[i] = keys[order[i]]; vals[i] = order[i]; }
+    T.vals.resize(n);
+    for (uint32_t i = 0; i < n; i++) { skeys[i] = keys[order[i]]; T.vals[i] = order[i]; }
     const int ni = (int)n - 1;
-    std::vector<BNode> bn(2 * n - 1);
-    std::vector<int> parent(2 * n - 1, -1), count(2 * n - 1, 0);
-    std::vector<float> cost(2 * n - 1, 0.0f);
+    T.ni = ni;
+    T.bn.assign(2 * n - 1, BNode());
+    T.parent.assign(2 * n - 1, -1);
+    T.count.assign(2 * n - 1, 0);
+    T.cost.assign(2 * n - 1, 0.0f);
+    auto &bn = T.bn;
     for (uint32_t i = 0; i < n; i++) {
         BNode &l = bn[ni + i];
-        l.lo = plo[vals[i]]; l.hi = phi[vals[i]]; l.left = l.right = -1;
-        count[ni + i] = 1;
-        cost[ni + i] = SOLB_SAH_CT * half_area(l.lo, l.hi);
+        l.lo = plo[T.vals[i]]; l.hi = phi[T.vals[i]]; l.left = l.right = -1;
+        T.count[ni + i] = 1;
+        T.cost[ni + i] = SOLB_SAH_CT * half_area(l.lo, l.hi);
     }
     for (int i = 0; i < ni; i++) {
         int l, r, first, last;
         karras_node(skeys.data(), (int)n, i, l, r, first, last);
         bn[i].left = l; bn[i].right = r;
-        parent[l] = i; parent[r] = i;
+        T.parent[l] = i; T.parent[r] = i;
     }
     // bottom-up order = reverse BFS from the root
     auto bottom_up = [&](int mode) {
@@ -153,33 +101,221 @@ int emu_build(EmuScene *s, int treelet_passes, int gamma) {
             int l = bn[node].left, r = bn[node].right;
             bn[node].lo = fmin3(bn[l].lo, bn[r].lo);
             bn[node].hi = fmax3(bn[l].hi, bn[r].hi);
-            count[node] = count[l] + count[r];
-            cost[node] = leaf_or_internal_cost(half_area(bn[node].lo, bn[node].hi), cost[l] + cost[r], count[node]);
-            if (mode == 1 && count[node] >= gamma) optimize_treelet(bn.data(), parent.data(), cost.data(), count.data(), ni, node, sc);
+            T.count[node] = T.count[l] + T.count[r];
+            T.cost[node] = leaf_or_internal_cost(half_area(bn[node].lo, bn[node].hi), T.cost[l] + T.cost[r], T.count[node]);
+            if (mode == 1 && T.count[node] >= gamma) optimize_treelet(bn.data(), T.parent.data(), T.cost.data(), T.count.data(), ni, node, sc);
         }
     };
     bottom_up(0);
     const float root_area = half_area(bn[0].lo, bn[0].hi);
-    s->sah_lbvh = root_area > 0 ? cost[0] / root_area : 0;
+    T.sah_lbvh = root_area > 0 ? T.cost[0] / root_area : 0;
     for (int p = 0; p < treelet_passes; p++) bottom_up(1);
-    s->sah_final = root_area > 0 ? cost[0] / root_area : 0;
-    // collapse
-    s->nodes.resize(n);
+    T.sah_final = root_area > 0 ? T.cost[0] / root_area : 0;
+}
+
+// level-synchronous collapse of T's root into wide[root_wnode]; returns the number of levels
+static uint32_t emu_collapse(const EmuTree &T, uint32_t root_wnode, Node8 *wide, uint32_t *wide_count, uint32_t *tri_count,
+                             const Tri48 *src, Tri48 *dst, uint32_t *leaf_prim) {
+    const uint32_t n = (uint32_t)T.ni + 1;
     std::vector<CollapseItem> qa(n), qb(n);
-    uint32_t wide_count = 1, tri_count = 0, nq = 1;
-    qa[0].bnode = 0; qa[0].wnode = 0;
-    s->depth = 0;
+    uint32_t nq = 1, depth = 0;
+    qa[0].bnode = 0; qa[0].wnode = root_wnode;
     while (nq) {
         uint32_t nout = 0;
         for (uint32_t i = 0; i < nq; i++)
-            collapse_one(bn.data(), count.data(), ni, qa[i], s->nodes.data(), &wide_count, &tri_count, vals.data(), tri_world.data(),
-                         s->tris.data(), qb.data(), &nout);
+            collapse_one(T.bn.data(), T.count.data(), T.ni, qa[i], wide, wide_count, tri_count, T.vals.data(), src, dst, qb.data(), &nout,
+                         leaf_prim);
         std::swap(qa, qb);
         nq = nout;
-        s->depth++;
+        depth++;
     }
+    return depth;
+}
+
+static void single_leaf_root(Node8 &out, float3 lo, float3 hi, uint32_t tri_base) {
+    ChildRef ch[8];
+    for (auto &c : ch) c.valid = 0;
+    ch[0].valid = 1; ch[0].lo = lo; ch[0].hi = hi; ch[0].is_inner = 0; ch[0].tri_offset = 0; ch[0].tri_count = 1;
+    encode_node8(out, lo, hi, 0, tri_base, ch);
+}
+
+extern "C" {
+
+// instances carry their BLAS id in .blas (ids must appear in increasing order of first use); geometry ranges are per instance
+EmuScene *emu_scene_create(uint32_t n_inst, const DeviceInstance *inst, const float *vertices, uint32_t n_vertices,
+                           const uint32_t *indices, uint32_t n_indices) {
+    EmuScene *s = new EmuScene();
+    s->inst.assign(inst, inst + n_inst);
+    s->vertices.resize((size_t)n_vertices * 4);
+    memcpy(s->vertices.data(), vertices, (size_t)n_vertices * 64);
+    s->indices.assign(indices, indices + n_indices);
+    s->first_tri.push_back(0);
+    for (uint32_t i = 0; i < n_inst; i++) {
+        DeviceInstance &di = s->inst[i];
+        if (di.blas >= s->blas.size()) {
+            DeviceBlas db;
+            db.first_vertex = di.first_vertex; db.first_index = di.first_index; db.n_indices = di.n_indices; db.first_tri = s->n_geom_tris;
+            di.blas = (uint32_t)s->blas.size();
+            s->blas.push_back(db);
+            s->n_geom_tris += di.n_indices / 3;
+        }
+        di.shade_first_tri = s->blas[di.blas].first_tri;
+        s->first_tri.push_back(s->first_tri.back() + di.n_indices / 3);
+    }
+    s->n_tris = s->first_tri.back();
+    s->shade.resize(std::max<uint32_t>(s->n_geom_tris, 1));
+    for (const DeviceBlas &db : s->blas)
+        for (uint32_t p = 0; p < db.n_indices / 3; p++) {
+            float f[28];
+            for (int k = 0; k < 3; k++) {
+                uint32_t vi = db.first_vertex + indices[db.first_index + 3 * p + k];
+                const float4 pos = s->vertices[4 * (size_t)vi], col = s->vertices[4 * (size_t)vi + 1], nrm = s->vertices[4 * (size_t)vi + 2];
+                f[9 * k] = pos.x; f[9 * k + 1] = pos.y; f[9 * k + 2] = pos.z;
+                f[9 * k + 3] = nrm.x; f[9 * k + 4] = nrm.y; f[9 * k + 5] = nrm.z;
+                f[9 * k + 6] = col.x; f[9 * k + 7] = col.y; f[9 * k + 8] = col.z;
+            }
+            f[27] = 0;
+            ShadeRecord &r = s->shade[db.first_tri + p];
+            for (int q = 0; q < 7; q++) r.q[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        }
+    return s;
+}
+
+void emu_scene_destroy(EmuScene *s) { delete s; }
+
+void emu_set_transform(EmuScene *s, uint32_t i, const float *t, const float *t_it) {
+    memcpy(s->inst[i].transform, t, 64);
+    memcpy(s->inst[i].transform_it, t_it, 64);
+}
+
+// Same pipeline as build.cu (flattened mode), run sequentially.  treelet_passes: 0 = plain LBVH.
+int emu_build(EmuScene *s, int treelet_passes, int gamma) {
+    const uint32_t n = s->n_tris;
+    s->nodes.clear(); s->tris.clear(); s->inst_leaves.clear();
+    s->two_level = false;
+    if (n == 0) {
+        ChildRef ch[8];
+        for (auto &c : ch) c.valid = 0;
+        s->nodes.resize(1);
+        encode_node8(s->nodes[0], f3(0, 0, 0), f3(0, 0, 0), 0, 0, ch);
+        s->depth = 1;
+        return 0;
+    }
+    std::vector<Tri48> tri_world(n);
+    std::vector<float3> plo(n), phi(n);
+    for (uint32_t i = 0; i < s->inst.size(); i++)
+        for (uint32_t p = 0; p < s->inst[i].n_indices / 3; p++) {
+            const uint32_t g = s->first_tri[i] + p;
+            float3 v[3];
+            for (int k = 0; k < 3; k++) {
+                uint32_t vi = s->inst[i].first_vertex + s->indices[s->inst[i].first_index + 3 * p + k];
+                const float4 pos = s->vertices[4 * (size_t)vi];
+                v[k] = mat4_mul_point(s->inst[i].transform, f3(pos.x, pos.y, pos.z));
+            }
+            tri_world[g].v0 = make_float4(v[0].x, v[0].y, v[0].z, u2f(i));
+            tri_world[g].v1 = make_float4(v[1].x, v[1].y, v[1].z, u2f(p));
+            tri_world[g].v2 = make_float4(v[2].x, v[2].y, v[2].z, u2f(s->inst[i].shade_first_tri + p));
+            plo[g] = fmin3(v[0], fmin3(v[1], v[2]));
+            phi[g] = fmax3(v[0], fmax3(v[1], v[2]));
+        }
+    s->tris.resize(n);
+    if (n == 1) {
+        s->nodes.resize(1);
+        single_leaf_root(s->nodes[0], plo[0], phi[0], 0);
+        s->tris[0] = tri_world[0];
+        s->depth = 1;
+        return 0;
+    }
+    EmuTree T;
+    emu_binary_tree(plo, phi, treelet_passes, gamma, T);
+    s->sah_lbvh = T.sah_lbvh;
+    s->sah_final = T.sah_final;
+    s->nodes.resize(n);
+    uint32_t wide_count = 1, tri_count = 0;
+    s->depth = emu_collapse(T, 0, s->nodes.data(), &wide_count, &tri_count, tri_world.data(), s->tris.data(), nullptr);
     s->nodes.resize(wide_count);
     return tri_count == n ? 0 : -1;
+}
+
+// TLAS over the instances' world boxes (build.cu: rebuild_tlas): nodes[0, tlas_cap), inst_leaves
+static int emu_rebuild_tlas(EmuScene *s, const std::vector<float3> &blo, const std::vector<float3> &bhi) {
+    const uint32_t n = (uint32_t)s->inst.size(), tlas_cap = std::max<uint32_t>(n, 1);
+    s->inst_leaves.assign(std::max<uint32_t>(n, 1), InstLeaf());
+    if (n == 0) {
+        ChildRef ch[8];
+        for (auto &c : ch) c.valid = 0;
+        encode_node8(s->nodes[0], f3(0, 0, 0), f3(0, 0, 0), 0, 0, ch);
+        s->tlas_depth = 1;
+        return 0;
+    }
+    std::vector<float3> plo(n), phi(n);
+    for (uint32_t i = 0; i < n; i++) transform_box(s->inst[i].transform, blo[s->inst[i].blas], bhi[s->inst[i].blas], plo[i], phi[i]);
+    if (n == 1) {
+        single_leaf_root(s->nodes[0], plo[0], phi[0], 0);
+        s->inst_leaves[0] = make_inst_leaf(s->inst[0].transform, tlas_cap + s->inst[0].blas, 0);
+        s->tlas_depth = 1;
+        return 0;
+    }
+    EmuTree T;
+    emu_binary_tree(plo, phi, 2, 7, T);
+    s->sah_lbvh = T.sah_lbvh;
+    s->sah_final = T.sah_final;
+    std::vector<uint32_t> leaf_prim(n);
+    uint32_t wide_count = 1, leaf_count = 0;
+    s->tlas_depth = emu_collapse(T, 0, s->nodes.data(), &wide_count, &leaf_count, nullptr, nullptr, leaf_prim.data());
+    if (leaf_count != n || wide_count > tlas_cap) return -1;
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t i = leaf_prim[j];
+        s->inst_leaves[j] = make_inst_leaf(s->inst[i].transform, tlas_cap + s->inst[i].blas, i);
+    }
+    return 0;
+}
+
+// Two-level build (build.cu: build_accel_two_level): every BLAS in object space, then the TLAS.  BLASes are built one
+// after another here; the GPU builds them in one batched pass with segmented Morton keys.
+int emu_build_two_level(EmuScene *s, int treelet_passes, int gamma) {
+    const uint32_t n = s->n_geom_tris, n_blas = (uint32_t)s->blas.size(), n_inst = (uint32_t)s->inst.size();
+    const uint32_t tlas_cap = std::max<uint32_t>(n_inst, 1);
+    s->two_level = true;
+    s->nodes.assign((size_t)tlas_cap + n_blas + n, Node8());
+    s->tris.assign(std::max<uint32_t>(n, 1), Tri48());
+    uint32_t wide_count = tlas_cap + n_blas, tri_count = 0, blas_depth = 1;
+    std::vector<float3> blo(n_blas), bhi(n_blas);
+    for (uint32_t b = 0; b < n_blas; b++) {
+        const DeviceBlas &db = s->blas[b];
+        const uint32_t cnt = db.n_indices / 3;
+        std::vector<Tri48> tri_obj(cnt);
+        std::vector<float3> plo(cnt), phi(cnt);
+        for (uint32_t p = 0; p < cnt; p++) {
+            float3 v[3];
+            for (int k = 0; k < 3; k++) {
+                uint32_t vi = db.first_vertex + s->indices[db.first_index + 3 * p + k];
+                const float4 pos = s->vertices[4 * (size_t)vi];
+                v[k] = f3(pos.x, pos.y, pos.z);
+            }
+            tri_obj[p].v0 = make_float4(v[0].x, v[0].y, v[0].z, u2f(b));
+            tri_obj[p].v1 = make_float4(v[1].x, v[1].y, v[1].z, u2f(p));
+            tri_obj[p].v2 = make_float4(v[2].x, v[2].y, v[2].z, u2f(db.first_tri + p));
+            plo[p] = fmin3(v[0], fmin3(v[1], v[2]));
+            phi[p] = fmax3(v[0], fmax3(v[1], v[2]));
+        }
+        if (cnt == 1) {
+            single_leaf_root(s->nodes[tlas_cap + b], plo[0], phi[0], tri_count);
+            s->tris[tri_count++] = tri_obj[0];
+            blo[b] = plo[0]; bhi[b] = phi[0];
+            continue;
+        }
+        EmuTree T;
+        emu_binary_tree(plo, phi, treelet_passes, gamma, T);
+        blo[b] = T.bn[0].lo; bhi[b] = T.bn[0].hi;
+        const uint32_t d = emu_collapse(T, tlas_cap + b, s->nodes.data(), &wide_count, &tri_count, tri_obj.data(), s->tris.data(), nullptr);
+        blas_depth = std::max(blas_depth, d);
+    }
+    if (tri_count != n) return -1;
+    s->nodes.resize(wide_count);
+    const int rc = emu_rebuild_tlas(s, blo, bhi);
+    s->depth = s->tlas_depth + blas_depth;
+    return rc;
 }
 
 uint32_t emu_node_count(EmuScene *s) { return (uint32_t)s->nodes.size(); }
@@ -200,7 +336,8 @@ void emu_trace_rays(EmuScene *s, const float *rays, uint32_t n, uint32_t *hits, 
         Hit h;
         EmuStack st;
         TraceCounters c = { 0, 0 };
-        trace_closest<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, h, st, &c);
+        if (s->two_level) trace_closest_2l<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), (const float4 *)s->inst_leaves.data(), r, h, st, &c);
+        else trace_closest<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, h, st, &c);
         hits[4 * i] = h.inst; hits[4 * i + 1] = h.prim; hits[4 * i + 2] = f2u(h.u); hits[4 * i + 3] = f2u(h.v);
         if (t_out) t_out[i] = h.inst != SOLB_MISS ? h.t : 0.0f;
         nodes += c.nodes; tris += c.tris;
@@ -231,7 +368,8 @@ void emu_debug(EmuScene *s, const float *uniforms, uint32_t w, uint32_t h, uint3
             r.o = fc.origin; r.d = primary_dir(fc, (float)x + 0.5f, (float)y + 0.5f); r.tmin = 0.001f; r.tmax = 1000.0f;
             Hit hit;
             EmuStack st;
-            trace_closest<false>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, (TraceCounters *)nullptr);
+            if (s->two_level) trace_closest_2l<false>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), (const float4 *)s->inst_leaves.data(), r, hit, st, (TraceCounters *)nullptr);
+            else trace_closest<false>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, (TraceCounters *)nullptr);
             float3 hv = r.d;
             if (hit.inst != SOLB_MISS) hv = f3(1.0f - hit.u - hit.v, hit.u, hit.v);
             const size_t p = (size_t)y * w + x;
@@ -261,7 +399,8 @@ void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_
                 Hit hit;
                 EmuStack st;
                 TraceCounters ctr = { 0, 0 };
-                trace_closest<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, &ctr);
+                if (s->two_level) trace_closest_2l<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), (const float4 *)s->inst_leaves.data(), r, hit, st, &ctr);
+                else trace_closest<true>((const uint4 *)s->nodes.data(), (const float4 *)s->tris.data(), r, hit, st, &ctr);
                 nnodes += ctr.nodes; ntris += ctr.tris;
                 nrays++;
                 bool end_path;

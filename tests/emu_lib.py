@@ -16,8 +16,11 @@ _LIB = None
 
 class DeviceInstance(ctypes.Structure):
     _fields_ = [("first_vertex", ctypes.c_uint32), ("first_index", ctypes.c_uint32), ("n_indices", ctypes.c_uint32),
-                ("material", ctypes.c_uint32), ("transform", ctypes.c_float * 16), ("transform_it", ctypes.c_float * 16),
-                ("mat", ctypes.c_float * 12)]
+                ("material", ctypes.c_uint32), ("blas", ctypes.c_uint32), ("shade_first_tri", ctypes.c_uint32),
+                ("transform", ctypes.c_float * 16), ("transform_it", ctypes.c_float * 16), ("mat", ctypes.c_float * 12)]
+
+
+assert ctypes.sizeof(DeviceInstance) == 200  # solb_internal.h
 
 
 def lib():
@@ -35,6 +38,8 @@ def lib():
         L.emu_scene_create.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
         L.emu_scene_destroy.argtypes = [ctypes.c_void_p]
         L.emu_build.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.emu_build_two_level.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.emu_set_transform.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
         for f in ("emu_node_count", "emu_depth"):
             getattr(L, f).restype = ctypes.c_uint32
             getattr(L, f).argtypes = [ctypes.c_void_p]
@@ -60,24 +65,38 @@ def _p(a):
 
 
 class EmuScene:
-    def __init__(self, flat, treelet_passes=2, gamma=7):
-        n = len(flat.instances)
+    def __init__(self, flat, treelet_passes=2, gamma=7, two_level=False, extra_instances=()):
+        """extra_instances: (source_instance, 4x4 transform, material_index) tuples = solb_scene_add_instance."""
+        insts = [dict(inst, blas=i) for i, inst in enumerate(flat.instances)]
+        for src, t, mat in extra_instances:
+            insts.append(dict(insts[src], transform=np.asarray(t, dtype=np.float32), material=mat))
+        n = len(insts)
         arr = (DeviceInstance * max(n, 1))()
-        for i, inst in enumerate(flat.instances):
+        for i, inst in enumerate(insts):
             t = np.asarray(inst["transform"], dtype=np.float32)
             tit = gf.mat4_inverse(t).T.copy()
             arr[i].first_vertex = inst["first_vertex"]
             arr[i].first_index = inst["first_index"]
             arr[i].n_indices = inst["n_indices"]
             arr[i].material = inst["material"]
+            arr[i].blas = inst["blas"]
             arr[i].transform[:] = t.reshape(16).tolist()
             arr[i].transform_it[:] = tit.reshape(16).tolist()
             arr[i].mat[:] = flat.materials[inst["material"]].tolist()
         v = np.ascontiguousarray(flat.vertices, dtype=np.float32)
         idx = np.ascontiguousarray(flat.indices, dtype=np.uint32)
         self.h = lib().emu_scene_create(n, arr, _p(v), v.shape[0], _p(idx), idx.shape[0])
-        rc = lib().emu_build(self.h, treelet_passes, gamma)
-        assert rc == 0, "emu_build: triangle count mismatch"
+        self.passes, self.gamma, self.two_level = treelet_passes, gamma, two_level
+        self.build()
+
+    def build(self):
+        rc = (lib().emu_build_two_level if self.two_level else lib().emu_build)(self.h, self.passes, self.gamma)
+        assert rc == 0, "emu_build: triangle / instance count mismatch"
+
+    def set_transform(self, index, transform):
+        t = np.ascontiguousarray(transform, dtype=np.float32).reshape(4, 4)
+        tit = np.ascontiguousarray(gf.mat4_inverse(t).T, dtype=np.float32)
+        lib().emu_set_transform(self.h, index, _p(t), _p(tit))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -87,3 +87,39 @@ def image_metrics(a, b):
     mse = np.mean((np.rint(ga) - np.rint(gb)) ** 2)
     psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
     return mre, psnr
+
+
+def trs(translate=(0, 0, 0), axis=(0, 1, 0), angle=0.0, scale=(1, 1, 1)):
+    """column-major-by-convention 4x4 (stored like glam::Mat4::to_cols_array_2d, i.e. m[col][row]) of T * R * S."""
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    c, s = np.cos(angle), np.sin(angle)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) + s * K + (1 - c) * (K @ K)
+    M = np.eye(4)
+    M[:3, :3] = R @ np.diag(scale)
+    M[:3, 3] = translate
+    return np.ascontiguousarray(M.T, dtype=np.float32)  # rows of the array = columns of the matrix
+
+
+def instanced_variant(fs, extras):
+    """FlatScene copy with extra instances (source_instance, transform, material) appended, as
+    solb_scene_add_instance does: same geometry, own transform and material."""
+    import copy
+
+    fs2 = copy.copy(fs)
+    fs2.instances = list(fs.instances) + [dict(fs.instances[src], transform=np.asarray(t, dtype=np.float32), material=mat)
+                                          for src, t, mat in extras]
+    return fs2
+
+
+def duck_extras(fs):
+    """three more ducks: mirrored (det < 0), scaled + rotated, and one overlapping the original."""
+    base = np.asarray(fs.instances[0]["transform"], dtype=np.float32).reshape(4, 4)
+
+    def compose(m):
+        return np.ascontiguousarray((m.T.astype(np.float64) @ base.T.astype(np.float64)).T, dtype=np.float32)  # world = m * base
+
+    return [(0, compose(trs((2.0, 0.0, 0.5), (0, 1, 0), 0.7, (-1, 1, 1))), 0),
+            (0, compose(trs((-1.5, 0.3, 1.0), (1, 0, 1), 1.1, (0.6, 0.6, 0.6))), 0),
+            (0, compose(trs((0.2, 0.1, 0.0), (0, 0, 1), 0.2, (1, 1.3, 1))), 0)]

@@ -77,3 +77,84 @@ def test_emu_rng_bit_exact():
         ref = oracle.rand_stream(int(seed), 8)
         for w, f in ref:
             assert L.emu_next_rand(ctypes.byref(s)) == f
+
+
+# ---- two-level mode (TLAS over shared object-space BLASes) ------------------------------
+
+@pytest.mark.parametrize("name,w,h", [("cornell", 192, 192), ("tunnel", 320, 180), ("Duck", 300, 200)])
+def test_emu_two_level_primary_hits(name, w, h):
+    fs, osc = oracle_scene(name)
+    es = emu_lib.EmuScene(fs, 2, two_level=True)
+    u = ocam.scene_uniforms(oracle_camera(fs, name, w, h), w, h, 0)
+    _, ids, _, flags = osc.debug(u, w, h)
+    _, eids = es.debug(u, w, h)
+    mism = np.any(ids != eids, axis=2)
+    assert (mism & (flags == 0)).sum() == 0
+    assert (ids[..., 0] != oracle.MISS).mean() > 0.03
+
+
+def _duck_rays(osc, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = osc.bounds()
+    c, r = (lo + hi) / 2, np.linalg.norm(hi - lo)
+    o = c + rng.normal(size=(n, 3)) * r
+    d = (c + rng.normal(size=(n, 3)) * 0.2 * r) - o
+    return np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+
+
+def test_emu_two_level_shared_blas_instances():
+    """four instances of ONE BLAS (mirrored, scaled, overlapping): two-level hits = oracle hits = flattened hits."""
+    from helpers import duck_extras, instanced_variant
+
+    fs, _ = oracle_scene("Duck")
+    extras = duck_extras(fs)
+    osc = oracle.Scene(instanced_variant(fs, extras))
+    two = emu_lib.EmuScene(fs, 2, two_level=True, extra_instances=extras)
+    flat = emu_lib.EmuScene(fs, 2, two_level=False, extra_instances=extras)
+    rays = _duck_rays(osc, 60_000, 7)
+    o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
+    for es in (two, flat):
+        hits, t, _ = es.trace_rays(rays)
+        mism = np.any(hits[:, :2] != o_hits[:, :2], axis=1)
+        assert (mism & (flags == 0)).sum() == 0
+        ok = (o_hits[:, 0] != oracle.MISS) & ~mism
+        assert np.allclose(t[ok], o_t[ok], rtol=2e-4, atol=2e-5)
+    assert set(np.unique(o_hits[:, 0])) >= {0, 1, 2, 3}  # every instance is hit
+    # shared geometry: the two-level structure stores the duck once, the flattened one four times
+    assert two.tris(4212).shape[0] == 4212 and flat.info()["nodes"] > 3 * (two.info()["nodes"] - 4)
+    assert two.info()["max_stack"] <= 2 * two.info()["depth"] + 1
+
+
+def test_emu_two_level_tlas_rebuild_after_transform_update():
+    from helpers import duck_extras, instanced_variant, trs
+
+    fs, _ = oracle_scene("Duck")
+    extras = duck_extras(fs)
+    two = emu_lib.EmuScene(fs, 2, two_level=True, extra_instances=extras)
+    moved = np.ascontiguousarray((trs((0.5, 1.0, -2.0), (0, 1, 0), 2.0).T.astype(np.float64)
+                                  @ np.asarray(extras[1][1], dtype=np.float64).T).T, dtype=np.float32)
+    two.set_transform(2, moved)  # instance 2 = extras[1]
+    two.build()
+    extras2 = [extras[0], (0, moved, 0), extras[2]]
+    osc = oracle.Scene(instanced_variant(fs, extras2))
+    rays = _duck_rays(osc, 30_000, 11)
+    o_hits, _, flags = osc.trace_rays(rays, classify=True)
+    hits, _, _ = two.trace_rays(rays)
+    assert (np.any(hits[:, :2] != o_hits[:, :2], axis=1) & (flags == 0)).sum() == 0
+    assert (o_hits[:, 0] == 2).sum() > 100
+
+
+@pytest.mark.parametrize("name,w,h,sky,mb", [("cornell", 64, 64, False, 32), ("tunnel", 96, 54, True, 8)])
+def test_emu_two_level_pathtrace_frame(name, w, h, sky, mb):
+    fs, osc = oracle_scene(name)
+    es = emu_lib.EmuScene(fs, 2, two_level=True)
+    cam = oracle_camera(fs, name, w, h)
+    a = np.zeros((h, w, 4), np.float32)
+    b = np.zeros((h, w, 4), np.float32)
+    st = oracle.OrcStats()
+    u = ocam.scene_uniforms(cam, w, h, 0)
+    osc.pathtrace_frame(u, w, h, a, 0, sky, 8, mb, st)
+    es.pathtrace_frame(u, w, h, b, 0, sky, 8, mb)
+    d = np.abs(a - b)[..., :3]
+    assert (d.max(axis=2) > 1e-3 * (1 + a[..., :3].max(axis=2))).mean() < 0.02
+    assert d.sum() / a[..., :3].sum() < 0.01

@@ -524,3 +524,182 @@ def test_accumulation_checkpoint_resume(sol, ctx, tmp_path):
     render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
     sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 6), restored, render, max_bounces=8), (w, h, 1))
     io.write_png(str(tmp_path / "frame.png"), render.readback())
+
+
+# ---- two-level mode: TLAS over shared object-space BLASes -----------------------------
+
+def _product_two_level(sol, ctx, name):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    sc = scene.load_scene(ctx, model_path(name))
+    return sc, ray.SceneDescription.from_scene(ctx, sc, accel_mode=N.ACCEL_TWO_LEVEL)
+
+
+@pytest.mark.parametrize("name,w,h", [("Duck", 900, 600), ("cornell", 512, 512), ("tunnel", 960, 540)])
+def test_two_level_primary_hit_ids(sol, ctx, name, w, h):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    fs, osc = oracle_scene(name)
+    ou = ocam.scene_uniforms(oracle_camera(fs, name, w, h), w, h, 0)
+    _, o_ids, _, o_flags = osc.debug(ou, w, h)
+    sc, sd = _product_two_level(sol, ctx, name)
+    info = sd.accel_info()
+    assert info.mode == N.ACCEL_TWO_LEVEL and info.n_blas == len(fs.instances) and info.n_tlas_nodes >= 1
+    assert info.n_triangles == osc.tri_count and info.tlas_depth >= 1 and info.wide_depth > info.tlas_depth
+    u = scene.scene_uniforms(product_camera(sc, name, w, h), w, h, 0)
+    ids = sol.Image2d(ctx, w, h, N.FORMAT_RG32UI)
+    render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+    simple_pipeline(ctx, "debug").cmd_trace_rays(ray.TraceBindings(sd, u, None, render, ids), (w, h, 1))
+    mism = np.any(ids.readback() != o_ids, axis=2)
+    assert (mism & (o_flags == 0)).sum() == 0, "hit ids differ on %d unlisted pixels" % (mism & (o_flags == 0)).sum()
+    # object-space triangles: the stored vertices are the file's, bit for bit
+    tris = sd.read_triangles()
+    tid = tris.view(np.uint32).reshape(-1, 3, 4)[:, :, 3]
+    assert sorted(tid[:, 2].tolist()) == list(range(osc.tri_count))
+    k = int(np.argmin(tid[:, 2]))
+    I = fs.instances[0]
+    idx = fs.indices[I["first_index"] + 3 * int(tid[k, 1]): I["first_index"] + 3 * int(tid[k, 1]) + 3] + I["first_vertex"]
+    assert np.array_equal(tris[k].reshape(3, 4)[:, :3], fs.vertices[idx, 0:3])
+
+
+def _instanced_duck(sol, ctx, mode):
+    from helpers import duck_extras, instanced_variant
+    from sol_rs_b200 import ray, scene
+
+    fs, _ = oracle_scene("Duck")
+    extras = duck_extras(fs)
+    sc = scene.load_scene(ctx, model_path("Duck"))
+    sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=mode)
+    for src, t, mat in extras:
+        sd.add_instance(src, t, mat)
+    sd.accel_build()
+    return fs, extras, oracle.Scene(instanced_variant(fs, extras)), sc, sd
+
+
+def _sphere_rays(osc, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = osc.bounds()
+    c, r = (lo + hi) / 2, np.linalg.norm(hi - lo)
+    o = c + rng.normal(size=(n, 3)) * r
+    d = (c + rng.normal(size=(n, 3)) * 0.2 * r) - o
+    return np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+
+
+def test_two_level_shared_blas_instances(sol, ctx):
+    """four instances of ONE BLAS (mirrored, scaled, overlapping): two-level hits = oracle = flattened build, and the
+    two-level structure stores the geometry once."""
+    from sol_rs_b200 import _native as N
+
+    results = {}
+    for mode in (N.ACCEL_TWO_LEVEL, N.ACCEL_FLAT):
+        fs, extras, osc, sc, sd = _instanced_duck(sol, ctx, mode)
+        rays = _sphere_rays(osc, 400_000, 7)
+        o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
+        hits, t = sd.trace_rays(rays)
+        mism = np.any(hits[:, :2] != o_hits[:, :2], axis=1)
+        assert (mism & (flags == 0)).sum() == 0
+        ok = (o_hits[:, 0] != oracle.MISS) & ~mism
+        np.testing.assert_allclose(t[ok], o_t[ok], rtol=2e-4, atol=2e-5)
+        assert set(np.unique(o_hits[:, 0]).tolist()) >= {0, 1, 2, 3}
+        results[mode] = sd.accel_info()
+        assert [i.id for i in sd.instances()] == [0, 1, 2, 3]
+    two, flat = results[N.ACCEL_TWO_LEVEL], results[N.ACCEL_FLAT]
+    assert two.n_instances == 4 and two.n_blas == 1 and two.n_triangles == 4212
+    assert flat.n_triangles == 4 * 4212 and flat.n_wide_nodes > 3 * (two.n_wide_nodes - two.n_instances)
+
+
+@pytest.mark.parametrize("schedule", ["wavefront", "megakernel"])
+@pytest.mark.parametrize("name,w,h,sky,mb", [("cornell", 128, 128, False, 32), ("tunnel", 192, 108, True, 8)])
+def test_two_level_pathtrace_matches_oracle(sol, ctx, name, w, h, sky, mb, schedule):
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    sc, sd = _product_two_level(sol, ctx, name)
+    cam = product_camera(sc, name, w, h)
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    sbt = pathtrace_pipeline(ctx, sky)
+    ctx.reset_stats()
+    for f in range(2):
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, None, samples_per_frame=8, max_bounces=mb,
+                                             schedule=N.SCHEDULE_WAVEFRONT if schedule == "wavefront" else N.SCHEDULE_MEGAKERNEL,
+                                             collect_stats=True), (w, h, 1))
+    st = ctx.stats()
+    o_acc, _, o_st = _render_oracle(name, w, h, range(2), sky, 8, mb)
+    a, b = accum.readback()[..., :3], o_acc[..., :3]
+    d = np.abs(a - b)
+    assert (d.max(axis=2) > 1e-3 * (1 + b.max(axis=2))).mean() < 0.02
+    assert d.sum() / b.sum() < 0.01
+    assert abs(int(st.rays) - int(o_st.rays)) <= 0.002 * int(o_st.rays) and st.nodes_visited > st.rays
+
+
+def test_two_level_tlas_regenerate_moves_instances(sol, ctx):
+    """blas_transform + tlas_regenerate in two-level mode rebuilds only the TLAS (SceneDescription::tlas_regenerate,
+    src/ray/mod.rs:162-193): hits follow the moved instance, BLAS nodes and triangles stay byte-identical."""
+    from helpers import instanced_variant, trs
+    from sol_rs_b200 import _native as N
+
+    fs, extras, _, sc, sd = _instanced_duck(sol, ctx, N.ACCEL_TWO_LEVEL)
+    info0 = sd.accel_info()
+    nodes0, tris0 = sd.read_nodes(), sd.read_triangles()
+    moved = np.ascontiguousarray((trs((0.5, 1.0, -2.0), (0, 1, 0), 2.0).T.astype(np.float64)
+                                  @ np.asarray(extras[1][1], dtype=np.float64).T).T, dtype=np.float32)
+    sd.blas_transform(moved, 2)
+    sd.tlas_regenerate()
+    info1 = sd.accel_info()
+    nodes1, tris1 = sd.read_nodes(), sd.read_triangles()
+    cap = info0.n_instances
+    assert info1.n_wide_nodes == info0.n_wide_nodes and np.array_equal(nodes0[cap:], nodes1[cap:]) and np.array_equal(tris0, tris1)
+    assert not np.array_equal(nodes0[:cap], nodes1[:cap])
+    osc = oracle.Scene(instanced_variant(fs, [extras[0], (0, moved, 0), extras[2]]))
+    rays = _sphere_rays(osc, 200_000, 13)
+    o_hits, _, flags = osc.trace_rays(rays, classify=True)
+    hits, _ = sd.trace_rays(rays)
+    assert (np.any(hits[:, :2] != o_hits[:, :2], axis=1) & (flags == 0)).sum() == 0
+    assert (o_hits[:, 0] == 2).sum() > 500
+    # the reference's transform_it follows the transform (SceneInstance::update_transform, src/ray/mod.rs:27-30)
+    inst = sd.instances()[2]
+    np.testing.assert_allclose(np.array(inst.transform[:]).reshape(4, 4), moved, rtol=0, atol=0)
+    sd.tlas_regenerate()  # clean: no-op
+    assert sd.accel_info().n_wide_nodes == info1.n_wide_nodes
+
+
+def test_two_level_many_instances_tlas_rebuild_time(sol, ctx):
+    """1 000 instances of two shared BLASes (config 5's instance count): build, per-frame TLAS regenerate, hit parity
+    against the flattened build of the same instances."""
+    from helpers import trs
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    rng = np.random.default_rng(3)
+    sc = scene.load_scene(ctx, model_path("cornell"))
+    xf = [trs(rng.uniform(-20, 20, 3), rng.normal(size=3), rng.uniform(0, 6.28), (rng.uniform(0.5, 1.5),) * 3) for _ in range(992)]
+    sds = {}
+    for mode in (N.ACCEL_TWO_LEVEL, N.ACCEL_FLAT):
+        sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=mode)
+        for i, t in enumerate(xf):
+            sd.add_instance(i % 8, t, i % 8)
+        sd.accel_build()
+        sds[mode] = sd
+    two, flat = sds[N.ACCEL_TWO_LEVEL], sds[N.ACCEL_FLAT]
+    assert two.accel_info().n_instances == 1000 and two.accel_info().n_blas == 8 and two.accel_info().n_triangles == 32
+    assert flat.accel_info().n_triangles == sum(two.instance_triangles())
+    n = 300_000
+    o = rng.uniform(-25, 25, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+    h2, t2 = two.trace_rays(rays)
+    h1, t1 = flat.trace_rays(rays)
+    same = np.all(h2[:, :2] == h1[:, :2], axis=1)
+    assert same.mean() > 0.9995  # the two builds round differently only on edge / tie rays
+    assert (h1[:, 0] != N.MISS).mean() > 0.2
+    dt = np.abs(t2[same] - t1[same]) / (1e-4 + 2e-4 * np.abs(t1[same]))  # grazing hits amplify the object/world rounding difference
+    assert (dt > 1).mean() < 1e-4 and dt.max() < 100
+    times = []
+    for k in range(5):
+        two.blas_transform(trs(rng.uniform(-20, 20, 3), (0, 1, 0), 0.1 * k), 100 + k)
+        two.tlas_regenerate()
+        times.append(ctx.stats().last_build_ms)
+    print("two-level TLAS regenerate, 1000 instances: %s ms" % ", ".join("%.3f" % t for t in times))
+    assert min(times) < 5.0
