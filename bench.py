@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--workload", default="tunnel", choices=["tunnel", "synth"],
                     help="tunnel = the headline config; synth = BASELINE configs[4]: synthetic instanced scene (--blas x 20000 triangles)")
     ap.add_argument("--blas", type=int, default=1000)
+    ap.add_argument("--accel", default="flat", choices=["flat", "two_level"],
+                    help="flat = transforms baked into one hierarchy (default); two_level = TLAS over object-space BLASes")
     ap.add_argument("--size", default="", help="WxH override, e.g. 3840x2160 for BASELINE configs[3] (default 1920x1080)")
     args = ap.parse_args()
     global WIDTH, HEIGHT, WORKLOAD
@@ -183,7 +185,7 @@ def main():
             sc = synth.make_scene(args.blas, 100)
         else:
             sc = scene.load_scene(ctx, os.path.join(ROOT, "assets", "models", model))
-        sd = ray.SceneDescription.from_scene(ctx, sc)
+        sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=N.ACCEL_TWO_LEVEL if args.accel == "two_level" else N.ACCEL_FLAT)
         cam = sc.camera
         cam.set_window_size((WIDTH, HEIGHT))
         pipe = ray.Pipeline(ctx, ray.PipelineInfo().shader("glsl/pathtrace.rgen", ray.RAYGEN_KHR)
@@ -358,7 +360,7 @@ def main():
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": workload, "schedule": "megakernel" if sched else "wavefront", "bvh_build_ms": build_ms,
+                "config": {"workload": workload, "schedule": "megakernel" if sched else "wavefront", "accel": args.accel, "bvh_build_ms": build_ms,
                            "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * world),
                            "l2": "256 MB buffer written between timed steps (outside the per-step event pairs)",
                            "multi_gpu": "frames f = rank (mod N) per rank, local sums, one NCCL reduce + resolve inside the timed region"

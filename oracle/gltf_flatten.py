@@ -32,13 +32,37 @@ _NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT2": 4, "MAT3": 9, "M
 class Gltf:
     def __init__(self, path):
         self.path = path
-        with open(path, "r") as f:
-            self.doc = json.load(f)
+        with open(path, "rb") as f:
+            raw = f.read()
+        glb_bin = None
+        if raw[:4] == b"glTF":
+            # GLB container (what gltf::import also accepts; ToyCar.glb of examples/4-ray-ao.rs:76): header
+            # magic | version | length, then {u32 length, u32 type, data} chunks: JSON (0x4E4F534A), BIN (0x004E4942)
+            import struct
+
+            version, total = struct.unpack_from("<II", raw, 4)
+            assert version == 2, "GLB container version must be 2"
+            off, doc = 12, None
+            while off + 8 <= min(total, len(raw)):
+                clen, ctype = struct.unpack_from("<II", raw, off)
+                chunk = raw[off + 8: off + 8 + clen]
+                if ctype == 0x4E4F534A and doc is None:
+                    doc = json.loads(chunk.decode("utf-8"))
+                elif ctype == 0x004E4942 and glb_bin is None:
+                    glb_bin = chunk
+                off += 8 + ((clen + 3) & ~3)
+            assert doc is not None, "GLB without a JSON chunk"
+            self.doc = doc
+        else:
+            self.doc = json.loads(raw.decode("utf-8"))
         self.buffers = []
         base = os.path.dirname(os.path.abspath(path))
-        for b in self.doc.get("buffers", []):
-            uri = b["uri"]
-            if uri.startswith("data:"):
+        for bi, b in enumerate(self.doc.get("buffers", [])):
+            uri = b.get("uri")
+            if uri is None:
+                assert glb_bin is not None and bi == 0, "buffer without uri outside a GLB container"
+                data = glb_bin
+            elif uri.startswith("data:"):
                 data = base64.b64decode(uri.split(",", 1)[1])
             else:
                 with open(os.path.join(base, uri), "rb") as f:

@@ -10,6 +10,7 @@
 #include "solb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace solb {
@@ -673,6 +674,169 @@ __global__ void k_single_inst_root(const float4 *prim_lo, const float4 *prim_hi,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Single-CTA TLAS build for up to TLAS_FAST_MAX instances: TLAS::regenerate runs every frame in the reference
+// (examples/5-pathtrace.rs:316), so for the instance counts it is used with (8 ... a few thousand) the whole rebuild is ONE
+// launch working out of shared memory: instance boxes -> Morton keys -> bitonic sort -> Karras links -> atomic-flag refit ->
+// level-synchronous 8-wide collapse -> instance leaf records.  No treelet pass (a plain LBVH over instance boxes).
+constexpr uint32_t TLAS_FAST_MAX = 2048;
+constexpr int TLAS_FAST_THREADS = 1024;
+
+struct TlasFastInfo {
+    uint32_t n_wide, depth, leaf_count, pad;
+    float lo[4], hi[4];
+};
+
+__host__ __device__ inline size_t tlas_fast_smem_bytes(uint32_t n) {
+    uint32_t p2 = 2;
+    while (p2 < n) p2 <<= 1;
+    // bn[2n-1] 32 B | keys[p2] 8 B | idx[p2] 4 B | count[2n-1] 4 B | flags[n] 4 B | queues 2 x (n/2+1) x 8 B | leaf_prim[n] 4 B | parent[2n-1] 2 B
+    return (size_t)(2 * n) * 32 + (size_t)p2 * 12 + (size_t)(2 * n) * 4 + (size_t)n * 4 + (size_t)(n / 2 + 2) * 16 + (size_t)n * 4 +
+           (size_t)(2 * n) * 2 + 64;
+}
+
+__global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n,
+                                                                        const float4 *__restrict__ blas_box, uint32_t tlas_cap,
+                                                                        Node8 *wide, InstLeaf *inst_leaves, TlasFastInfo *info) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_bounds[6];
+    __shared__ uint32_t s_counters[3];  // wide nodes, leaf slots, next queue size
+    __shared__ uint32_t s_items, s_depth;
+    uint32_t p2 = 2;
+    while (p2 < n) p2 <<= 1;
+    BNode *bn = (BNode *)smem;
+    uint64_t *keys = (uint64_t *)(bn + 2 * n);
+    uint32_t *idx = (uint32_t *)(keys + p2);
+    int *count = (int *)(idx + p2);
+    uint32_t *flags = (uint32_t *)(count + 2 * n);
+    CollapseItem *queue_a = (CollapseItem *)(flags + n);
+    CollapseItem *queue_b = queue_a + (n / 2 + 2);
+    uint32_t *leaf_prim = (uint32_t *)(queue_b + (n / 2 + 2));
+    uint16_t *parent = (uint16_t *)(leaf_prim + n);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const int ni = (int)n - 1;
+
+    if (tid < 3) s_bounds[tid] = 0xffffffffu;
+    else if (tid < 6) s_bounds[tid] = 0u;
+    __syncthreads();
+    // 1. instance boxes: kept in the (not yet linked) leaf slots in INSTANCE order for the moment
+    for (uint32_t i = tid; i < n; i += nt) {
+        const DeviceInstance &di = instances[i];
+        const float4 a = blas_box[2 * di.blas], b = blas_box[2 * di.blas + 1];
+        float3 lo, hi;
+        transform_box(di.transform, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), lo, hi);
+        BNode leaf;
+        leaf.lo = lo; leaf.hi = hi; leaf.left = -1; leaf.right = -1;
+        bn[i] = leaf;  // temporary position; moved to bn[ni + sorted position] after the sort
+        const float cc[3] = { (lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f };
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&s_bounds[k], float_to_ordered(cc[k]));
+            atomicMax(&s_bounds[3 + k], float_to_ordered(cc[k]));
+        }
+    }
+    __syncthreads();
+    // 2. Morton keys + bitonic sort of (key, index) in shared memory
+    {
+        const float3 lo = f3(ordered_to_float(s_bounds[0]), ordered_to_float(s_bounds[1]), ordered_to_float(s_bounds[2]));
+        const float3 hi = f3(ordered_to_float(s_bounds[3]), ordered_to_float(s_bounds[4]), ordered_to_float(s_bounds[5]));
+        const float3 ext = hi - lo;
+        const float3 inv = f3(ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f);
+        for (uint32_t i = tid; i < p2; i += nt) {
+            if (i < n) {
+                const BNode &b = bn[i];
+                keys[i] = morton63((b.lo + b.hi) * 0.5f, lo, inv);
+            } else keys[i] = ~0ull;  // padding sorts last
+            idx[i] = i;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= p2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < p2; i += nt) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const uint64_t ka = keys[i], kb = keys[l];
+                    const uint32_t ia = idx[i], ib = idx[l];
+                    const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+                    const bool up = (i & k) == 0;
+                    if (a_gt_b == up) { keys[i] = kb; keys[l] = ka; idx[i] = ib; idx[l] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    // 3. move the boxes to their sorted leaf slots.  Source bn[idx[i]] (i < n) and destination bn[ni + i] ranges overlap:
+    //    stage through registers with a barrier in between (every thread owns at most ceil(n / nt) <= 2 leaves).
+    {
+        BNode tmp[(TLAS_FAST_MAX + TLAS_FAST_THREADS - 1) / TLAS_FAST_THREADS];
+        int c = 0;
+        for (uint32_t i = tid; i < n; i += nt) tmp[c++] = bn[idx[i]];
+        __syncthreads();
+        c = 0;
+        for (uint32_t i = tid; i < n; i += nt) {
+            bn[ni + i] = tmp[c++];
+            count[ni + i] = 1;
+            flags[i] = 0;
+        }
+    }
+    __syncthreads();
+    // 4. Karras links
+    for (int i = (int)tid; i < ni; i += (int)nt) {
+        int l, r, first, last;
+        karras_node(keys, (int)n, i, l, r, first, last);
+        bn[i].left = l;
+        bn[i].right = r;
+        parent[l] = (uint16_t)i;
+        parent[r] = (uint16_t)i;
+    }
+    if (tid == 0) parent[0] = 0xffffu;
+    __syncthreads();
+    // 5. refit: the second thread to arrive at a node owns it
+    for (uint32_t j = tid; j < n; j += nt) {
+        uint32_t node = parent[ni + j];
+        while (node != 0xffffu) {
+            __threadfence_block();
+            if (atomicAdd(&flags[node], 1u) == 0) break;
+            __threadfence_block();
+            const int l = bn[node].left, r = bn[node].right;
+            const volatile BNode *vl = bn + l, *vr = bn + r;
+            const float3 lo = fmin3(f3(vl->lo.x, vl->lo.y, vl->lo.z), f3(vr->lo.x, vr->lo.y, vr->lo.z));
+            const float3 hi = fmax3(f3(vl->hi.x, vl->hi.y, vl->hi.z), f3(vr->hi.x, vr->hi.y, vr->hi.z));
+            bn[node].lo = lo;
+            bn[node].hi = hi;
+            ((volatile int *)count)[node] = ((volatile int *)count)[l] + ((volatile int *)count)[r];
+            node = parent[node];
+        }
+    }
+    if (tid == 0) {
+        s_counters[0] = 1; s_counters[1] = 0; s_counters[2] = 0;
+        s_items = 1; s_depth = 0;
+        queue_a[0].bnode = 0; queue_a[0].wnode = 0;
+    }
+    __syncthreads();
+    // 6. level-synchronous collapse
+    for (;;) {
+        const uint32_t n_items = s_items;
+        if (n_items == 0) break;
+        for (uint32_t i = tid; i < n_items; i += nt)
+            collapse_one(bn, count, ni, queue_a[i], wide, &s_counters[0], &s_counters[1], idx, nullptr, nullptr, queue_b, &s_counters[2],
+                         leaf_prim);
+        __syncthreads();
+        if (tid == 0) { s_items = s_counters[2]; s_counters[2] = 0; s_depth++; }
+        CollapseItem *t = queue_a; queue_a = queue_b; queue_b = t;
+        __syncthreads();
+    }
+    // 7. instance leaf records in TLAS leaf order
+    for (uint32_t j = tid; j < n; j += nt) {
+        const uint32_t i = leaf_prim[j];
+        inst_leaves[j] = make_inst_leaf(instances[i].transform, tlas_cap + instances[i].blas, i);
+    }
+    if (tid == 0) {
+        info->n_wide = s_counters[0]; info->depth = s_depth; info->leaf_count = s_counters[1];
+        info->lo[0] = bn[0].lo.x; info->lo[1] = bn[0].lo.y; info->lo[2] = bn[0].lo.z;
+        info->hi[0] = bn[0].hi.x; info->hi[1] = bn[0].hi.y; info->hi[2] = bn[0].hi.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = e_; goto done; } } while (0)
 
 template <class T>
@@ -869,6 +1033,11 @@ done:
 }
 
 // ---------------------------------------------------------------------------------------------------
+static bool tlas_fast_enabled() {
+    const char *v = getenv("SOLB_TLAS_FAST");
+    return !(v && *v == '0');
+}
+
 // TLAS over the instances' world boxes, written into nodes[0, tlas_cap) and inst_leaves (both preallocated by
 // build_accel_two_level).  This is all TLAS::regenerate has to redo when instance transforms change.
 cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, uint64_t *launches) {
@@ -887,6 +1056,28 @@ cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorag
         k_empty_root<<<1, 1, 0, st>>>(out.nodes);
         *launches += 1;
         out.n_tlas_wide = 1;
+        goto finish;
+    }
+    if (n >= 2 && n <= TLAS_FAST_MAX && tlas_fast_enabled()) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CK(cudaFuncSetAttribute(k_tlas_build_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlas_fast_smem_bytes(TLAS_FAST_MAX)));
+            attr_set = true;
+        }
+        if (!out.d_tlas_info) {
+            CK(cudaMalloc(&out.d_tlas_info, sizeof(TlasFastInfo)));
+            CK(cudaMallocHost(&out.h_tlas_info, sizeof(TlasFastInfo)));
+        }
+        k_tlas_build_small<<<1, TLAS_FAST_THREADS, tlas_fast_smem_bytes(n), st>>>(sv.instances, n, out.blas_box, out.tlas_cap, out.nodes,
+                                                                                  out.inst_leaves, (TlasFastInfo *)out.d_tlas_info);
+        *launches += 1;
+        CK(cudaMemcpyAsync(out.h_tlas_info, out.d_tlas_info, sizeof(TlasFastInfo), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const TlasFastInfo h_info = *(const TlasFastInfo *)out.h_tlas_info;
+        if (h_info.leaf_count != n || h_info.n_wide > out.tlas_cap) { err = cudaErrorUnknown; goto done; }
+        out.n_tlas_wide = h_info.n_wide;
+        depth = h_info.depth;
+        for (int k = 0; k < 3; k++) { out.lo[k] = h_info.lo[k]; out.hi[k] = h_info.hi[k]; }
         goto finish;
     }
     CK(salloc(st, &prim_lo, n));

@@ -10,7 +10,8 @@
 //     matrix; yfov passed through unchanged (Camera applies to_radians()) (mod.rs:261-287)
 // The `gltf` crate (1.0.0, Cargo.lock:518-519) behaviour it relies on is restated: material
 // defaults, Node::transform().matrix() for decomposed TRS, accessor readers into_u32 / into_f32 /
-// into_rgba_f32.  Unsupported (no shipped asset uses them): sparse accessors, .glb, Draco.
+// into_rgba_f32.  .glb containers are accepted (JSON + BIN chunks).  Unsupported (no shipped asset uses them): sparse
+// accessors, Draco, textures (the reference loads none on this path: texture_offset is reserved, src/ray/mod.rs:20).
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -160,10 +161,41 @@ Mat4 calc_mesh_global_transform(const Doc &d, long mesh_index) {  // mod.rs:124-
 
 }  // namespace
 
+// GLB container (glTF 2.0 binary, the form ToyCar.glb of examples/4-ray-ao.rs:76 ships in; gltf::import of the gltf crate
+// accepts both): 12-byte header "glTF" | version 2 | total length, then chunks {u32 length, u32 type, data}: the first is
+// JSON (0x4E4F534A), the optional second is BIN (0x004E4942) = the buffer without a uri.
+static bool split_glb(const std::string &file, std::string &json_out, std::string &bin_out) {
+    auto u32 = [&](size_t off) {
+        uint32_t v;
+        std::memcpy(&v, file.data() + off, 4);
+        return v;
+    };
+    if (file.size() < 12 || std::memcmp(file.data(), "glTF", 4) != 0) return false;
+    if (u32(4) != 2) throw Error(SOLB_ERR_UNSUPPORTED, "load_scene: GLB container version must be 2");
+    const size_t total = std::min<size_t>(u32(8), file.size());
+    size_t off = 12;
+    bool have_json = false;
+    while (off + 8 <= total) {
+        const size_t len = u32(off);
+        const uint32_t type = u32(off + 4);
+        if (off + 8 + len > total) throw Error(SOLB_ERR_INVALID, "load_scene: GLB chunk runs past the end of the file");
+        if (type == 0x4E4F534Au && !have_json) { json_out.assign(file, off + 8, len); have_json = true; }
+        else if (type == 0x004E4942u && bin_out.empty()) bin_out.assign(file, off + 8, len);
+        off += 8 + ((len + 3) & ~(size_t)3);
+    }
+    if (!have_json) throw Error(SOLB_ERR_INVALID, "load_scene: GLB without a JSON chunk");
+    return true;
+}
+
 Scene load_scene(std::shared_ptr<Context>, const std::string &filepath) {
     Doc d;
+    std::string glb_bin;
+    bool is_glb = false;
     try {
-        d.root = json::parse(read_file(filepath, false));
+        const std::string file = read_file(filepath, true);
+        std::string json_text;
+        is_glb = split_glb(file, json_text, glb_bin);
+        d.root = json::parse(is_glb ? json_text : file);
     } catch (const std::runtime_error &e) {
         throw Error(SOLB_ERR_INVALID, std::string("load_scene: ") + e.what());
     }
@@ -172,9 +204,12 @@ Scene load_scene(std::shared_ptr<Context>, const std::string &filepath) {
     if (slash != std::string::npos) dir = filepath.substr(0, slash);
     const json::Value &buffers = d.root["buffers"];
     for (size_t i = 0; i < buffers.size(); i++) {
-        const std::string &uri = buffers[i]["uri"].string();
+        const std::string uri = buffers[i].has("uri") ? buffers[i]["uri"].string() : std::string();
         std::string data;
-        if (uri.compare(0, 5, "data:") == 0) {
+        if (uri.empty()) {  // GLB-stored buffer: only buffer 0 may omit its uri
+            if (!is_glb || i != 0) throw Error(SOLB_ERR_INVALID, "load_scene: buffer without uri outside a GLB container");
+            data = glb_bin;
+        } else if (uri.compare(0, 5, "data:") == 0) {
             const size_t comma = uri.find(',');
             if (comma == std::string::npos) throw Error(SOLB_ERR_INVALID, "load_scene: malformed data URI");
             data = base64_decode(uri, comma + 1);

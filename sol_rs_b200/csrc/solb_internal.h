@@ -77,7 +77,11 @@ struct AccelStorage {
     InstLeaf *inst_leaves = nullptr;   // [n_instances] TLAS leaf records in TLAS leaf order
     float4 *blas_box = nullptr;        // [2 * n_blas] object-space root boxes (lo, hi)
     uint32_t tlas_cap = 0, n_blas = 0, n_tlas_wide = 0, tlas_depth = 0, blas_depth = 0;
+    void *d_tlas_info = nullptr, *h_tlas_info = nullptr;  // single-CTA TLAS build: result block (device) + pinned mirror
     void release() {
+        if (d_tlas_info) cudaFree(d_tlas_info);
+        if (h_tlas_info) cudaFreeHost(h_tlas_info);
+        d_tlas_info = h_tlas_info = nullptr;
         if (nodes) cudaFree(nodes);
         if (tris) cudaFree(tris);
         if (inst_leaves) cudaFree(inst_leaves);

@@ -123,3 +123,34 @@ def duck_extras(fs):
     return [(0, compose(trs((2.0, 0.0, 0.5), (0, 1, 0), 0.7, (-1, 1, 1))), 0),
             (0, compose(trs((-1.5, 0.3, 1.0), (1, 0, 1), 1.1, (0.6, 0.6, 0.6))), 0),
             (0, compose(trs((0.2, 0.1, 0.0), (0, 0, 1), 0.2, (1, 1.3, 1))), 0)]
+
+
+def write_glb(gltf_path, out_path):
+    """Repack a .gltf (+ its external or data-URI buffers) as ONE .glb container: JSON chunk + a single BIN chunk
+    holding all buffers back to back, bufferViews rebased onto buffer 0 (glTF 2.0 binary file format)."""
+    import base64
+    import json
+    import struct
+
+    with open(gltf_path) as f:
+        doc = json.load(f)
+    base = os.path.dirname(os.path.abspath(gltf_path))
+    blob, offsets = b"", []
+    for b in doc.get("buffers", []):
+        uri = b["uri"]
+        data = base64.b64decode(uri.split(",", 1)[1]) if uri.startswith("data:") else open(os.path.join(base, uri), "rb").read()
+        offsets.append(len(blob))
+        blob += data[: b["byteLength"]]
+        blob += b"\0" * (-len(blob) % 4)
+    for v in doc.get("bufferViews", []):
+        v["byteOffset"] = v.get("byteOffset", 0) + offsets[v["buffer"]]
+        v["buffer"] = 0
+    doc["buffers"] = [{"byteLength": len(blob)}]
+    js = json.dumps(doc, separators=(",", ":")).encode("utf-8")
+    js += b" " * (-len(js) % 4)
+    total = 12 + 8 + len(js) + 8 + len(blob)
+    with open(out_path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, total))
+        f.write(struct.pack("<II", len(js), 0x4E4F534A) + js)
+        f.write(struct.pack("<II", len(blob), 0x004E4942) + blob)
+    return out_path

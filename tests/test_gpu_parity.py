@@ -676,13 +676,17 @@ def test_two_level_many_instances_tlas_rebuild_time(sol, ctx):
     sc = scene.load_scene(ctx, model_path("cornell"))
     xf = [trs(rng.uniform(-20, 20, 3), rng.normal(size=3), rng.uniform(0, 6.28), (rng.uniform(0.5, 1.5),) * 3) for _ in range(992)]
     sds = {}
-    for mode in (N.ACCEL_TWO_LEVEL, N.ACCEL_FLAT):
-        sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=mode)
-        for i, t in enumerate(xf):
-            sd.add_instance(i % 8, t, i % 8)
-        sd.accel_build()
-        sds[mode] = sd
-    two, flat = sds[N.ACCEL_TWO_LEVEL], sds[N.ACCEL_FLAT]
+    for key, mode, fast in (("two", N.ACCEL_TWO_LEVEL, "1"), ("two_general", N.ACCEL_TWO_LEVEL, "0"), ("flat", N.ACCEL_FLAT, "1")):
+        _os.environ["SOLB_TLAS_FAST"] = fast  # "0": the multi-kernel TLAS build (instance counts above the single-CTA limit)
+        try:
+            sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=mode)
+            for i, t in enumerate(xf):
+                sd.add_instance(i % 8, t, i % 8)
+            sd.accel_build()
+        finally:
+            _os.environ.pop("SOLB_TLAS_FAST", None)
+        sds[key] = sd
+    two, flat = sds["two"], sds["flat"]
     assert two.accel_info().n_instances == 1000 and two.accel_info().n_blas == 8 and two.accel_info().n_triangles == 32
     assert flat.accel_info().n_triangles == sum(two.instance_triangles())
     n = 300_000
@@ -691,15 +695,27 @@ def test_two_level_many_instances_tlas_rebuild_time(sol, ctx):
     rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
     h2, t2 = two.trace_rays(rays)
     h1, t1 = flat.trace_rays(rays)
+    h3, t3 = sds["two_general"].trace_rays(rays)
+    assert np.array_equal(h2, h3) and np.array_equal(t2, t3)  # same BLASes, different TLAS topology: identical hits
     same = np.all(h2[:, :2] == h1[:, :2], axis=1)
     assert same.mean() > 0.9995  # the two builds round differently only on edge / tie rays
     assert (h1[:, 0] != N.MISS).mean() > 0.2
     dt = np.abs(t2[same] - t1[same]) / (1e-4 + 2e-4 * np.abs(t1[same]))  # grazing hits amplify the object/world rounding difference
     assert (dt > 1).mean() < 1e-4 and dt.max() < 100
-    times = []
-    for k in range(5):
-        two.blas_transform(trs(rng.uniform(-20, 20, 3), (0, 1, 0), 0.1 * k), 100 + k)
-        two.tlas_regenerate()
-        times.append(ctx.stats().last_build_ms)
-    print("two-level TLAS regenerate, 1000 instances: %s ms" % ", ".join("%.3f" % t for t in times))
-    assert min(times) < 5.0
+    moves = [trs(rng.uniform(-20, 20, 3), (0, 1, 0), 0.1 * k) for k in range(5)]
+    for key in ("two", "two_general"):
+        times = []
+        _os.environ["SOLB_TLAS_FAST"] = "1" if key == "two" else "0"
+        try:
+            for k in range(5):
+                sds[key].blas_transform(moves[k], 100 + k)
+                sds[key].tlas_regenerate()
+                times.append(ctx.stats().last_build_ms)
+        finally:
+            _os.environ.pop("SOLB_TLAS_FAST", None)
+        print("TLAS regenerate, 1000 instances, %s: %s ms" % ("single-CTA kernel" if key == "two" else "multi-kernel path",
+                                                              ", ".join("%.3f" % t for t in times)))
+        assert min(times) < 5.0
+    h4, _ = two.trace_rays(rays)
+    h5, _ = sds["two_general"].trace_rays(rays)
+    assert np.array_equal(h4, h5) and not np.array_equal(h4, h2)

@@ -178,3 +178,29 @@ def test_png_writer_roundtrip(tmp_path):
     io.write_ppm(str(tmp_path / "f.ppm"), img)
     raw = open(str(tmp_path / "f.ppm"), "rb").read()
     assert raw.startswith(b"P6\n53 37\n255\n") and len(raw) == 13 + 37 * 53 * 3
+
+
+@pytest.mark.parametrize("name", ["cornell", "tunnel", "Duck"])
+def test_glb_container_loads_like_its_gltf(name, tmp_path):
+    """the .glb container (the form the reference's 4-ray-ao default asset ToyCar.glb ships in,
+    examples/4-ray-ao.rs:76) goes through both loaders and yields exactly the scene of the equivalent .gltf."""
+    from helpers import write_glb
+    from sol_rs_b200 import scene
+
+    glb = write_glb(model_path(name), str(tmp_path / (name + ".glb")))
+    a, b = gf.load_scene(model_path(name)), gf.load_scene(glb)
+    assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.indices, b.indices) and np.array_equal(a.materials, b.materials)
+    assert len(a.instances) == len(b.instances) and all(np.array_equal(x["transform"], y["transform"]) for x, y in zip(a.instances, b.instances))
+    s = scene.load_scene(None, glb)
+    assert np.array_equal(np.concatenate([m.vertices for m in s.meshes]), a.vertices)
+    assert np.array_equal(np.concatenate([m.indices for m in s.meshes]), a.indices)
+    assert np.array_equal(s.materials, a.materials) and (s.camera is not None) == (a.camera is not None)
+    # malformed containers fail like the reference's gltf::import(...).unwrap(): an error, never a crash
+    raw = open(glb, "rb").read()
+    bad = tmp_path / "bad.glb"
+    bad.write_bytes(raw[:20] + b"\xff\xff\xff\x7f" + raw[24:])  # JSON chunk type corrupted
+    with pytest.raises(Exception):
+        scene.load_scene(None, str(bad))
+    bad.write_bytes(raw[: len(raw) // 2])                        # truncated
+    with pytest.raises(Exception):
+        scene.load_scene(None, str(bad))
