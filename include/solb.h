@@ -167,6 +167,9 @@ typedef struct SolbAccelInfo {
 SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out);
 SOLB_API int solb_ctx_destroy(solb_ctx *ctx);
 SOLB_API int solb_synchronize(solb_ctx *ctx); /* queue_wait_idle, src/context.rs:539-559 */
+/* Return cached build scratch to the driver (the stream-ordered pool keeps it between builds so per-frame rebuilds do not
+ * re-map memory; cf. the reference's gpu-allocator blocks, src/context.rs:229). Synchronises. */
+SOLB_API int solb_ctx_trim(solb_ctx *ctx);
 SOLB_API const char *solb_last_error(solb_ctx *ctx); /* ctx may be NULL: last global error */
 SOLB_API uint32_t solb_version(void);
 SOLB_API int solb_stats_get(solb_ctx *ctx, SolbStats *out); /* synchronises */

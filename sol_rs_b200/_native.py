@@ -81,6 +81,7 @@ SYMBOLS = {
     "solb_ctx_create": (_i, [_i, _vp, _pp]),
     "solb_ctx_destroy": (_i, [_vp]),
     "solb_synchronize": (_i, [_vp]),
+    "solb_ctx_trim": (_i, [_vp]),
     "solb_last_error": (ctypes.c_char_p, [_vp]),
     "solb_version": (_u32, []),
     "solb_stats_get": (_i, [_vp, ctypes.POINTER(Stats)]),

@@ -24,6 +24,10 @@ class Context:
     def synchronize(self):
         N.check(self._lib.solb_synchronize(self._h), self._h)
 
+    def trim(self):
+        """hand the cached build scratch back to the driver (solb_ctx_trim)"""
+        N.check(self._lib.solb_ctx_trim(self._h), self._h)
+
     def stats(self):
         st = N.Stats()
         N.check(self._lib.solb_stats_get(self._h, ctypes.byref(st)), self._h)

@@ -10,6 +10,8 @@
 #include "solb_internal.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -471,6 +473,31 @@ __global__ void __launch_bounds__(TL_BLOCK) k_bottom_up_coop(int n, BNode *bn, i
     }
 }
 
+// bottom-up pass of the optimal-collapse dynamic program (DpEntry per binary node); same atomic-flag walk as k_bottom_up
+__global__ void k_bottom_up_dp(int n, const BNode *bn, const int *parent, const int *node_count, uint32_t *flags, DpEntry *dp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    {
+        const BNode leaf = bn[n - 1 + j];
+        DpEntry e;
+        dp_leaf_entry(e, half_area(leaf.lo, leaf.hi));
+        dp[n - 1 + j] = e;
+    }
+    int node = parent[n - 1 + j];
+    while (node >= 0) {
+        __threadfence();
+        const uint32_t old = atomicAdd(&flags[node], 1u);
+        if (old == 0) return;
+        __threadfence();
+        const BNode b = bn[node];
+        const DpEntry l = dp[b.left], r = dp[b.right];
+        DpEntry e;
+        dp_inner_entry(e, l, r, half_area(b.lo, b.hi), node_count[node]);
+        dp[node] = e;
+        node = parent[node];
+    }
+}
+
 __global__ void k_clear_u32(uint32_t *p, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0;
@@ -479,11 +506,11 @@ __global__ void k_clear_u32(uint32_t *p, uint32_t n) {
 __global__ void k_collapse_level(const BNode *bn, const int *node_count, int n_internal, const CollapseItem *queue_in,
                                  uint32_t n_items, Node8 *wide, uint32_t *counters /*0: wide, 1: tris, 2: queue_out*/,
                                  const uint32_t *sorted_prim, const Tri48 *tri_world, Tri48 *tri_out, CollapseItem *queue_out,
-                                 uint32_t *leaf_prim_out) {
+                                 uint32_t *leaf_prim_out, const DpEntry *dp) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     collapse_one(bn, node_count, n_internal, queue_in[i], wide, &counters[0], &counters[1], sorted_prim, tri_world, tri_out,
-                 queue_out, &counters[2], leaf_prim_out);
+                 queue_out, &counters[2], leaf_prim_out, dp);
 }
 
 // n == 1: a root with one single-triangle leaf
@@ -847,6 +874,25 @@ static cudaError_t salloc(cudaStream_t st, T **p, size_t count) {
     return cudaMallocAsync((void **)p, std::max<size_t>(count, 1) * sizeof(T), st);
 }
 
+// SOLB_BUILD_TRACE=1: synchronise after every build phase and print its wall-clock share to stderr (debug aid)
+struct PhaseTrace {
+    cudaStream_t st;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTrace(cudaStream_t s) : st(s) {
+        const char *v = getenv("SOLB_BUILD_TRACE");
+        on = v && *v == '1';
+        if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); }
+    }
+    void mark(const char *name) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[solb build] %-28s %9.3f ms\n", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // Device scratch of one binary radix tree over n >= 2 primitives (Karras numbering: internal [0, n-2], leaf j -> n-1+j).
 struct BinaryTree {
     uint32_t n = 0;
@@ -855,6 +901,7 @@ struct BinaryTree {
     BNode *bn = nullptr;
     int *parent = nullptr, *node_count = nullptr;
     float *node_cost = nullptr;
+    DpEntry *dp = nullptr;  // optimal-collapse table (null: greedy collapse)
     cudaError_t alloc(cudaStream_t st, uint32_t n_) {
         n = n_;
         cudaError_t err = cudaSuccess;
@@ -872,7 +919,7 @@ struct BinaryTree {
         return err;
     }
     void free(cudaStream_t st) {
-        void *q[] = { keys, keys_tmp, vals, vals_tmp, sort_scratch, flags, bn, parent, node_count, node_cost };
+        void *q[] = { keys, keys_tmp, vals, vals_tmp, sort_scratch, flags, bn, parent, node_count, node_cost, dp };
         for (void *x : q)
             if (x) cudaFreeAsync(x, st);
         *this = BinaryTree();
@@ -907,6 +954,12 @@ static cudaError_t tree_refit_optimize(cudaStream_t st, BinaryTree &T, const Bui
             k_bottom_up<<<(n + 63) / 64, 64, 0, st>>>((int)n, T.bn, T.parent, T.node_count, T.node_cost, T.flags, 1, opt.treelet_gamma);
         *launches += 2;
     }
+    if (opt.dp_collapse) {
+        CK(salloc(st, &T.dp, 2 * (size_t)n - 1));
+        k_clear_u32<<<nb, 256, 0, st>>>(T.flags, n);
+        k_bottom_up_dp<<<nb, 256, 0, st>>>((int)n, T.bn, T.parent, T.node_count, T.flags, T.dp);
+        *launches += 2;
+    }
     CK(cudaGetLastError());
 done:
     return err;
@@ -921,7 +974,7 @@ static cudaError_t collapse_levels(cudaStream_t st, const BinaryTree &T, Collaps
     uint32_t depth = 0;
     while (n_items) {
         k_collapse_level<<<(n_items + 63) / 64, 64, 0, st>>>(T.bn, T.node_count, (int)T.n - 1, queue_a, n_items, wide, counters, T.vals,
-                                                             tri_src, tri_out, queue_b, leaf_prim_out);
+                                                             tri_src, tri_out, queue_b, leaf_prim_out, T.dp);
         *launches += 1;
         CK(cudaMemcpyAsync(h_counters, counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -951,6 +1004,7 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
     uint32_t h_counters[3];
     uint32_t depth = 0;
 
+    PhaseTrace trace(st);
     out.release();
     out.n_tris = n;
     CK(salloc(st, &wide, std::max<uint32_t>(n, 1)));
@@ -976,10 +1030,13 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         out.depth = 1;
         goto finish;
     }
+    trace.mark("alloc + prep");
     CK(T.alloc(st, n));
     k_morton<<<nb, 256, 0, st>>>(prim_lo, prim_hi, n, bounds, T.keys, T.vals);
     *launches += 1;
+    trace.mark("tree alloc + morton");
     CK(tree_sort_and_link(st, T, prim_lo, prim_hi, 63, launches));
+    trace.mark("sort + hierarchy");
     CK(tree_refit_optimize(st, T, opt, opt.treelet_passes, &out.sah_lbvh, launches));
     CK(cudaMemcpyAsync(&out.sah_final, T.node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
     {
@@ -991,6 +1048,7 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         out.lo[0] = root.lo.x; out.lo[1] = root.lo.y; out.lo[2] = root.lo.z;
         out.hi[0] = root.hi.x; out.hi[1] = root.hi.y; out.hi[2] = root.hi.z;
     }
+    trace.mark("refit + treelets");
     // collapse, one launch per level of the wide tree
     CK(salloc(st, &queue_a, n));
     CK(salloc(st, &queue_b, n));
@@ -1007,6 +1065,7 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
         out.depth = depth;
         if (h_counters[1] != n) { err = cudaErrorUnknown; goto done; }  // every triangle must land in exactly one leaf
     }
+    trace.mark("collapse");
 finish:
     CK(cudaStreamSynchronize(st));
     // shrink the node array to its final size
@@ -1020,6 +1079,7 @@ finish:
         tri_out = nullptr;
         out.n_binary = n >= 2 ? 2 * n - 1 : n;
     }
+    trace.mark("final node copy");
 done:
     {
         void *scratch[] = { tri_world, prim_lo, prim_hi, bounds, counters, queue_a, queue_b, wide };
@@ -1028,6 +1088,7 @@ done:
         T.free(st);
     }
     cudaFree(tri_out);
+    trace.mark("free scratch");
     if (err != cudaSuccess) out.release();
     return err;
 }
@@ -1165,6 +1226,7 @@ cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, Ac
     uint32_t n_multi = 0, n_single = 0;
     std::vector<DeviceBlas> h_blas(n_blas);
 
+    PhaseTrace trace(st);
     out.release();
     out.two_level = true;
     out.n_tris = n;
@@ -1195,6 +1257,7 @@ cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, Ac
         k_init_bounds_n<<<(6 * n_blas + 255) / 256, 256, 0, st>>>(blas_bounds, n_blas);
         k_prep_tris_obj<<<nb, 256, 0, st>>>(sv, tri_obj, prim_lo, prim_hi, blas_bounds);
         *launches += 2;
+        trace.mark("2L alloc + prep");
         if (n >= 2) {
             int id_bits = 0;
             while ((1ull << id_bits) < n_blas) id_bits++;
@@ -1202,12 +1265,15 @@ cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, Ac
             CK(T.alloc(st, n));
             k_morton_seg<<<nb, 256, 0, st>>>(prim_lo, prim_hi, n, blas_bounds, morton_bits, T.keys, T.vals);
             *launches += 1;
+            trace.mark("2L tree alloc + morton");
             CK(tree_sort_and_link(st, T, prim_lo, prim_hi, morton_bits + id_bits, launches));
             k_blas_roots<<<(n_blas + 127) / 128, 128, 0, st>>>(T.keys, (int)n, sv.blas, n_blas, T.parent, blas_root);
             *launches += 1;
+            trace.mark("2L sort + hierarchy + roots");
             CK(tree_refit_optimize(st, T, opt, opt.treelet_passes, nullptr, launches));
             k_blas_boxes<<<(n_blas + 127) / 128, 128, 0, st>>>(T.bn, blas_root, n_blas, out.blas_box);
             *launches += 1;
+            trace.mark("2L refit + treelets");
         } else {  // one BLAS holding one triangle
             CK(cudaMemcpyAsync(out.blas_box, prim_lo, sizeof(float4), cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpyAsync(out.blas_box + 1, prim_hi, sizeof(float4), cudaMemcpyDeviceToDevice, st));
@@ -1229,6 +1295,7 @@ cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, Ac
             if (h_counters[1] != n) { err = cudaErrorUnknown; goto done; }
         }
     }
+    trace.mark("2L collapse");
     out.blas_depth = depth;
     out.n_wide = h_counters[0];
     CK(cudaStreamSynchronize(st));
@@ -1243,8 +1310,10 @@ cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, Ac
         tri_out = nullptr;
         out.n_binary = n >= 2 ? 2 * n - 1 : n;
     }
+    trace.mark("2L final node copy");
     CK(rebuild_tlas(st, sv, out, launches));
     CK(cudaStreamSynchronize(st));
+    trace.mark("2L tlas");
 done:
     {
         void *scratch[] = { tri_obj, prim_lo, prim_hi, blas_bounds, counters, d_list, blas_root, queue_a, queue_b, wide };

@@ -97,6 +97,7 @@ struct BuildOptions {
     int treelet_passes = 2;
     int treelet_gamma = 7;
     int coop_treelet = 1;  // warp-cooperative treelet kernel (0: per-thread reference version)
+    int dp_collapse = 1;   // SAH-optimal wide collapse (Ylitie et al. 2017); 0: greedy largest-area-first
 };
 
 cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt, uint64_t *launches);

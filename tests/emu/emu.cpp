@@ -46,9 +46,12 @@ struct EmuTree {
     std::vector<int> parent, count;
     std::vector<float> cost;
     std::vector<uint32_t> vals;  // sorted position -> primitive
+    std::vector<DpEntry> dp;     // optimal-collapse table (empty: greedy collapse)
     int ni = 0;
     float sah_lbvh = 0, sah_final = 0;
 };
+
+static int g_emu_dp = 1;  // mirrors BuildOptions::dp_collapse
 
 static void emu_binary_tree(const std::vector<float3> &plo, const std::vector<float3> &phi, int treelet_passes, int gamma, EmuTree &T) {
     const uint32_t n = (uint32_t)plo.size();
@@ -111,6 +114,21 @@ static void emu_binary_tree(const std::vector<float3> &plo, const std::vector<fl
     T.sah_lbvh = root_area > 0 ? T.cost[0] / root_area : 0;
     for (int p = 0; p < treelet_passes; p++) bottom_up(1);
     T.sah_final = root_area > 0 ? T.cost[0] / root_area : 0;
+    if (g_emu_dp) {  // k_bottom_up_dp
+        T.dp.assign(2 * n - 1, DpEntry());
+        std::vector<int> bfs;
+        bfs.push_back(0);
+        for (size_t k = 0; k < bfs.size(); k++) {
+            int x = bfs[k];
+            if (x < ni) { bfs.push_back(bn[x].left); bfs.push_back(bn[x].right); }
+        }
+        for (size_t k = bfs.size(); k-- > 0;) {
+            const int node = bfs[k];
+            const float a = half_area(bn[node].lo, bn[node].hi);
+            if (node >= ni) dp_leaf_entry(T.dp[node], a);
+            else dp_inner_entry(T.dp[node], T.dp[bn[node].left], T.dp[bn[node].right], a, T.count[node]);
+        }
+    }
 }
 
 // level-synchronous collapse of T's root into wide[root_wnode]; returns the number of levels
@@ -124,7 +142,7 @@ static uint32_t emu_collapse(const EmuTree &T, uint32_t root_wnode, Node8 *wide,
         uint32_t nout = 0;
         for (uint32_t i = 0; i < nq; i++)
             collapse_one(T.bn.data(), T.count.data(), T.ni, qa[i], wide, wide_count, tri_count, T.vals.data(), src, dst, qb.data(), &nout,
-                         leaf_prim);
+                         leaf_prim, T.dp.empty() ? nullptr : T.dp.data());
         std::swap(qa, qb);
         nq = nout;
         depth++;
@@ -182,6 +200,7 @@ EmuScene *emu_scene_create(uint32_t n_inst, const DeviceInstance *inst, const fl
 }
 
 void emu_scene_destroy(EmuScene *s) { delete s; }
+void emu_set_dp_collapse(int on) { g_emu_dp = on; }
 
 void emu_set_transform(EmuScene *s, uint32_t i, const float *t, const float *t_it) {
     memcpy(s->inst[i].transform, t, 64);

@@ -39,6 +39,7 @@ def lib():
         L.emu_scene_destroy.argtypes = [ctypes.c_void_p]
         L.emu_build.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.emu_build_two_level.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.emu_set_dp_collapse.argtypes = [ctypes.c_int]
         L.emu_set_transform.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
         for f in ("emu_node_count", "emu_depth"):
             getattr(L, f).restype = ctypes.c_uint32
@@ -65,7 +66,7 @@ def _p(a):
 
 
 class EmuScene:
-    def __init__(self, flat, treelet_passes=2, gamma=7, two_level=False, extra_instances=()):
+    def __init__(self, flat, treelet_passes=2, gamma=7, two_level=False, extra_instances=(), dp_collapse=True):
         """extra_instances: (source_instance, 4x4 transform, material_index) tuples = solb_scene_add_instance."""
         insts = [dict(inst, blas=i) for i, inst in enumerate(flat.instances)]
         for src, t, mat in extra_instances:
@@ -86,10 +87,11 @@ class EmuScene:
         v = np.ascontiguousarray(flat.vertices, dtype=np.float32)
         idx = np.ascontiguousarray(flat.indices, dtype=np.uint32)
         self.h = lib().emu_scene_create(n, arr, _p(v), v.shape[0], _p(idx), idx.shape[0])
-        self.passes, self.gamma, self.two_level = treelet_passes, gamma, two_level
+        self.passes, self.gamma, self.two_level, self.dp_collapse = treelet_passes, gamma, two_level, dp_collapse
         self.build()
 
     def build(self):
+        lib().emu_set_dp_collapse(int(self.dp_collapse))
         rc = (lib().emu_build_two_level if self.two_level else lib().emu_build)(self.h, self.passes, self.gamma)
         assert rc == 0, "emu_build: triangle / instance count mismatch"
 
