@@ -934,6 +934,9 @@ static cudaError_t tree_sort_and_link(cudaStream_t st, BinaryTree &T, const floa
     k_hierarchy<<<(T.n + 255) / 256, 256, 0, st>>>(T.keys, T.vals, prim_lo, prim_hi, (int)T.n, T.bn, T.parent, T.node_count, T.node_cost,
                                                      T.flags);
     *launches += 1;
+    // the sort's ping-pong buffers are dead from here on: hand them back so later scratch (collapse table, queues) reuses them
+    cudaFreeAsync(T.keys_tmp, st); cudaFreeAsync(T.vals_tmp, st); cudaFreeAsync(T.sort_scratch, st);
+    T.keys_tmp = nullptr; T.vals_tmp = nullptr; T.sort_scratch = nullptr;
     return cudaGetLastError();
 }
 
@@ -1036,6 +1039,8 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
     *launches += 1;
     trace.mark("tree alloc + morton");
     CK(tree_sort_and_link(st, T, prim_lo, prim_hi, 63, launches));
+    cudaFreeAsync(prim_lo, st); cudaFreeAsync(prim_hi, st); cudaFreeAsync(T.keys, st);  // leaf boxes live in the tree now
+    prim_lo = prim_hi = nullptr; T.keys = nullptr;
     trace.mark("sort + hierarchy");
     CK(tree_refit_optimize(st, T, opt, opt.treelet_passes, &out.sah_lbvh, launches));
     CK(cudaMemcpyAsync(&out.sah_final, T.node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1050,6 +1055,8 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
     }
     trace.mark("refit + treelets");
     // collapse, one launch per level of the wide tree
+    cudaFreeAsync(T.node_cost, st); cudaFreeAsync(T.parent, st); cudaFreeAsync(T.flags, st);
+    T.node_cost = nullptr; T.parent = nullptr; T.flags = nullptr;
     CK(salloc(st, &queue_a, n));
     CK(salloc(st, &queue_b, n));
     CK(salloc(st, &counters, 4));
