@@ -306,10 +306,10 @@ __global__ void k_bottom_up(int n, BNode *bn, int *parent, int *node_count, floa
 
 // ---------------------------------------------------------------------------------------------------
 // Warp-cooperative treelet restructuring (Karras & Aila 2013, section 4): threads still walk up from the
-// leaves with atomic flags, but when lanes of a warp reach treelet roots the WHOLE warp optimises those
-// treelets one after another: 32 lanes share the 2^7 subset areas and the dynamic program over subset
-// sizes, so one treelet costs ~1 us instead of the ~50 us of the per-thread version (k_bottom_up mode 1),
-// which also shortens the serial critical path up the tree by the same factor.
+// leaves with atomic flags, but when lanes of a warp reach treelet roots the warp optimises those treelets
+// cooperatively (lane groups share the 2^7 subset areas and the dynamic program over subset sizes), so one
+// treelet costs microseconds instead of the ~50 us of the per-thread version (k_bottom_up mode 1), which also
+// shortens the serial critical path up the tree by the same factor.
 struct WarpTreeletScratch {
     float area[128];
     float cost[128];
@@ -324,45 +324,56 @@ struct WarpTreeletScratch {
     int changed;
 };
 
+// Each warp optimises up to TL_GROUPS ready treelets at once, one per group of TL_GROUP lanes: treelet formation and the
+// topology rebuild are serial chains of dependent global loads / stores run by the group's first lane, so four of them
+// in flight per warp quadruple the memory-level parallelism of the pass; the 2^7 subset areas and the dynamic program are
+// spread over the group's lanes.  Treelets that are ready in the same iteration root disjoint subtrees (a node only
+// becomes ready after both children were finished in EARLIER iterations), so they are independent.
+constexpr int TL_GROUP = 32;  // measured at 20 M triangles: 8-lane groups (4 treelets per warp) 70 ms, whole warp per treelet 48 ms
+constexpr int TL_GROUPS = 32 / TL_GROUP;
+
+// root < 0: this group has no treelet this round (it still takes part in the warp-wide barriers)
 __device__ void coop_optimize_treelet(BNode *bn, int *parent, float *node_cost, int *node_count, int n_internal, int root,
-                                      WarpTreeletScratch &ws, int lane) {
-    if (lane == 0) {  // treelet formation: expand the largest-area internal leaf until 7 leaves
+                                      WarpTreeletScratch &ws, int glane) {
+    if (glane == 0) {  // treelet formation: expand the largest-area internal leaf until 7 leaves
         int nl = 0, ni = 0;
-        ws.internals[ni++] = root;
-        ws.leaves[nl++] = bn[root].left;
-        ws.leaves[nl++] = bn[root].right;
-        while (nl < SOLB_TREELET_N) {
-            int best = -1;
-            float best_a = -1.0f;
-            for (int i = 0; i < nl; i++) {
-                const int c = ws.leaves[i];
-                if (c < n_internal) {
-                    const float a = half_area(bn[c].lo, bn[c].hi);
-                    if (a > best_a) { best_a = a; best = i; }
+        if (root >= 0) {
+            ws.internals[ni++] = root;
+            ws.leaves[nl++] = bn[root].left;
+            ws.leaves[nl++] = bn[root].right;
+            while (nl < SOLB_TREELET_N) {
+                int best = -1;
+                float best_a = -1.0f;
+                for (int i = 0; i < nl; i++) {
+                    const int c = ws.leaves[i];
+                    if (c < n_internal) {
+                        const float a = half_area(bn[c].lo, bn[c].hi);
+                        if (a > best_a) { best_a = a; best = i; }
+                    }
                 }
+                if (best < 0) break;
+                const int c = ws.leaves[best];
+                ws.internals[ni++] = c;
+                ws.leaves[best] = bn[c].left;
+                ws.leaves[nl++] = bn[c].right;
             }
-            if (best < 0) break;
-            const int c = ws.leaves[best];
-            ws.internals[ni++] = c;
-            ws.leaves[best] = bn[c].left;
-            ws.leaves[nl++] = bn[c].right;
         }
         ws.nl = nl;
         ws.changed = 0;
     }
     __syncwarp();
     const int nl = ws.nl;
-    if (nl < 3) return;
-    const int full = (1 << nl) - 1;
-    if (lane < nl) {
-        const BNode b = bn[ws.leaves[lane]];
-        ws.lo[lane][0] = b.lo.x; ws.lo[lane][1] = b.lo.y; ws.lo[lane][2] = b.lo.z;
-        ws.hi[lane][0] = b.hi.x; ws.hi[lane][1] = b.hi.y; ws.hi[lane][2] = b.hi.z;
-        ws.lcost[lane] = node_cost[ws.leaves[lane]];
-        ws.lcount[lane] = node_count[ws.leaves[lane]];
+    const bool on = nl >= 3;
+    const int full = on ? (1 << nl) - 1 : 0;
+    if (on && glane < nl) {
+        const BNode b = bn[ws.leaves[glane]];
+        ws.lo[glane][0] = b.lo.x; ws.lo[glane][1] = b.lo.y; ws.lo[glane][2] = b.lo.z;
+        ws.hi[glane][0] = b.hi.x; ws.hi[glane][1] = b.hi.y; ws.hi[glane][2] = b.hi.z;
+        ws.lcost[glane] = node_cost[ws.leaves[glane]];
+        ws.lcount[glane] = node_count[ws.leaves[glane]];
     }
     __syncwarp();
-    for (int s = lane + 1; s <= full; s += 32) {  // subset areas and "fits in a leaf" flags
+    for (int s = glane + 1; s <= full; s += TL_GROUP) {  // subset areas and "fits in a leaf" flags
         float lo0 = 3.4e38f, lo1 = 3.4e38f, lo2 = 3.4e38f, hi0 = -3.4e38f, hi1 = -3.4e38f, hi2 = -3.4e38f;
         int cnt = 0;
         for (int i = 0; i < nl; i++)
@@ -376,26 +387,27 @@ __device__ void coop_optimize_treelet(BNode *bn, int *parent, float *node_cost, 
         if (__popc(s) == 1) { ws.cost[s] = ws.lcost[31 - __clz(s)]; ws.part[s] = 0; }
     }
     __syncwarp();
-    for (int k = 2; k <= nl; k++) {  // dynamic program over subset sizes
-        for (int s = lane + 1; s <= full; s += 32) {
-            if (__popc(s) != k) continue;
-            float best_c = 3.4e38f;
-            int best_p = 0;
-            const int delta = (s - 1) & s;
-            int p = (-delta) & s;
-            do {
-                const float c = ws.cost[p] + ws.cost[s ^ p];
-                if (c < best_c) { best_c = c; best_p = p; }
-                p = (p - delta) & s;
-            } while (p != 0);
-            float c = SOLB_SAH_CI * ws.area[s] + best_c;
-            if (ws.small[s]) c = fminf(c, SOLB_SAH_CT * ws.area[s] * (float)ws.small[s]);
-            ws.cost[s] = c;
-            ws.part[s] = (uint8_t)best_p;
-        }
+    for (int k = 2; k <= SOLB_TREELET_N; k++) {  // dynamic program over subset sizes (every group runs all 6 barriers)
+        if (k <= nl)
+            for (int s = glane + 1; s <= full; s += TL_GROUP) {
+                if (__popc(s) != k) continue;
+                float best_c = 3.4e38f;
+                int best_p = 0;
+                const int delta = (s - 1) & s;
+                int p = (-delta) & s;
+                do {
+                    const float c = ws.cost[p] + ws.cost[s ^ p];
+                    if (c < best_c) { best_c = c; best_p = p; }
+                    p = (p - delta) & s;
+                } while (p != 0);
+                float c = SOLB_SAH_CI * ws.area[s] + best_c;
+                if (ws.small[s]) c = fminf(c, SOLB_SAH_CT * ws.area[s] * (float)ws.small[s]);
+                ws.cost[s] = c;
+                ws.part[s] = (uint8_t)best_p;
+            }
         __syncwarp();
     }
-    if (lane == 0 && ws.cost[full] < node_cost[root] * 0.9999f) {  // rebuild the topology, reusing the internal node ids
+    if (on && glane == 0 && ws.cost[full] < node_cost[root] * 0.9999f) {  // rebuild the topology, reusing the internal node ids
         int stack_set[SOLB_TREELET_N], stack_node[SOLB_TREELET_N], order[SOLB_TREELET_N];
         int sp = 0, next_internal = 1, n_order = 0;
         stack_set[sp] = full; stack_node[sp] = root; sp++;
@@ -433,9 +445,9 @@ __device__ void coop_optimize_treelet(BNode *bn, int *parent, float *node_cost, 
 constexpr int TL_BLOCK = 128;
 __global__ void __launch_bounds__(TL_BLOCK) k_bottom_up_coop(int n, BNode *bn, int *parent, int *node_count, float *node_cost,
                                                              uint32_t *flags, int gamma) {
-    __shared__ WarpTreeletScratch scratch[TL_BLOCK / 32];
-    WarpTreeletScratch &ws = scratch[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
+    __shared__ WarpTreeletScratch scratch[TL_BLOCK / 32][TL_GROUPS];
+    const int lane = threadIdx.x & 31, group = lane / TL_GROUP, glane = lane % TL_GROUP;
+    WarpTreeletScratch &ws = scratch[threadIdx.x >> 5][group];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int node = j < n ? parent[n - 1 + j] : -1;
     bool active = node >= 0;
@@ -460,11 +472,16 @@ __global__ void __launch_bounds__(TL_BLOCK) k_bottom_up_coop(int n, BNode *bn, i
             }
         }
         uint32_t m = __ballot_sync(0xffffffffu, active && ready);
-        while (m) {
-            const int leader = __ffs(m) - 1;
-            const int root = __shfl_sync(0xffffffffu, node, leader);
-            coop_optimize_treelet(bn, parent, node_cost, node_count, n - 1, root, ws, lane);
-            m &= m - 1;
+        while (m) {  // hand the next TL_GROUPS ready treelets to the warp's lane groups
+            int root = -1;
+#pragma unroll
+            for (int g = 0; g < TL_GROUPS; g++) {
+                const int leader = m ? __ffs(m) - 1 : 0;
+                const int r = __shfl_sync(0xffffffffu, node, leader);
+                if (m && g == group) root = r;
+                m &= m - 1;
+            }
+            coop_optimize_treelet(bn, parent, node_cost, node_count, n - 1, root, ws, glane);
         }
         if (active) {
             node = parent[node];
@@ -706,7 +723,7 @@ __global__ void k_single_inst_root(const float4 *prim_lo, const float4 *prim_hi,
 // launch working out of shared memory: instance boxes -> Morton keys -> bitonic sort -> Karras links -> atomic-flag refit ->
 // level-synchronous 8-wide collapse -> instance leaf records.  No treelet pass (a plain LBVH over instance boxes).
 constexpr uint32_t TLAS_FAST_MAX = 2048;
-constexpr int TLAS_FAST_THREADS = 1024;
+constexpr int TLAS_FAST_THREADS = 256;  // few, fat threads: collapse_one wants registers, everything else is tiny
 
 struct TlasFastInfo {
     uint32_t n_wide, depth, leaf_count, pad;

@@ -289,6 +289,44 @@ SOLB_HD int gather_leaf_tris(const BNode *bn, int n_internal, int c, int *out) {
     return n;
 }
 
+// Slot auction of the wide node's children (after Ylitie et al. 2017): repeatedly give the (child, free slot) pair with the
+// largest dot(child centre - node centre, octant direction of the slot) its slot, so children are visited roughly front to
+// back when the slots are walked in the ray's octant order.  Written with fixed-bound loops and bit masks so the 8 x 8 scores
+// stay in registers: one thread per wide node runs this on the critical path of every collapse level.
+SOLB_HD void assign_child_slots(const float3 *rel, int n, int *slot_of) {
+    uint32_t free_child = (1u << n) - 1u, free_slot = 0xffu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; i++) slot_of[i] = -1;
+    for (int round = 0; round < n; round++) {
+        float best_v = -3.4e38f;
+        int bi = -1, bs = -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 8; i++) {
+            if (!((free_child >> i) & 1u)) continue;
+            const float rx = rel[i].x, ry = rel[i].y, rz = rel[i].z;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int sl = 0; sl < 8; sl++) {
+                if (!((free_slot >> sl) & 1u)) continue;
+                const float v = ((sl & 4) ? rx : -rx) + ((sl & 2) ? ry : -ry) + ((sl & 1) ? rz : -rz);
+                if (v > best_v) { best_v = v; bi = i; bs = sl; }
+            }
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 8; i++)
+            if (i == bi) slot_of[i] = bs;
+        free_child &= ~(1u << bi);
+        free_slot &= ~(1u << bs);
+    }
+}
+
 // One work item.  sorted_prim[j] = global triangle id at sorted position j; tri_world indexed by
 // global triangle id; tri_out in wide-leaf order.  TLAS builds pass leaf_prim_out instead of tri_world / tri_out:
 // the primitive (instance) id of every leaf slot, from which the caller writes its own leaf records.
@@ -298,64 +336,78 @@ SOLB_HD void collapse_one(const BNode *bn, const int *node_count, int n_internal
                           const DpEntry *dp = nullptr) {
     int cand[8];
     int n = 2;
-    cand[0] = bn[item.bnode].left;
-    cand[1] = bn[item.bnode].right;
+    const BNode self = bn[item.bnode];
+    cand[0] = self.left;
+    cand[1] = self.right;
     if (dp) n = dp_gather_children(bn, dp, n_internal, item.bnode, cand);
-    while (!dp && n < 8) {  // greedy: open the internal candidate with the largest box
-        int best = -1;
-        float best_a = -1.0f;
-        for (int i = 0; i < n; i++) {
-            const int c = cand[i];
-            if (c < n_internal) {  // internal binary node: may be opened
-                const float a = half_area(bn[c].lo, bn[c].hi);
-                if (a > best_a) { best_a = a; best = i; }
-            }
+    else {  // greedy: open the internal candidate with the largest box until 8 children
+        float area[8];  // < 0: a binary leaf, cannot be opened
+        for (int i = 0; i < 2; i++) area[i] = cand[i] < n_internal ? half_area(bn[cand[i]].lo, bn[cand[i]].hi) : -1.0f;
+        while (n < 8) {
+            int best = -1;
+            float best_a = -1.0f;
+            for (int i = 0; i < n; i++)
+                if (area[i] > best_a) { best_a = area[i]; best = i; }
+            if (best < 0) break;
+            const int c = cand[best], l = bn[c].left, r = bn[c].right;
+            cand[best] = l;
+            area[best] = l < n_internal ? half_area(bn[l].lo, bn[l].hi) : -1.0f;
+            cand[n] = r;
+            area[n] = r < n_internal ? half_area(bn[r].lo, bn[r].hi) : -1.0f;
+            n++;
         }
-        if (best < 0) break;
-        const int c = cand[best];
-        cand[best] = bn[c].left;
-        cand[n++] = bn[c].right;
     }
-    // slot assignment: greedy auction on dot(child centre - node centre, octant direction of the slot)
-    const float3 nlo = bn[item.bnode].lo, nhi = bn[item.bnode].hi;
+    // children: boxes, leaf / inner decision, slots
+    const float3 nlo = self.lo, nhi = self.hi;
     const float3 nc = (nlo + nhi) * 0.5f;
-    int slot_of[8];
-    bool slot_used[8];
-    float3 rel[8];
-    for (int i = 0; i < 8; i++) { slot_used[i] = false; slot_of[i] = -1; }
-    for (int i = 0; i < n; i++) rel[i] = (bn[cand[i]].lo + bn[cand[i]].hi) * 0.5f - nc;
-    for (int round = 0; round < n; round++) {
-        float best_v = -3.4e38f;
-        int bi = -1, bs = -1;
-        for (int i = 0; i < n; i++) {
-            if (slot_of[i] >= 0) continue;
-            for (int s = 0; s < 8; s++) {
-                if (slot_used[s]) continue;
-                const float v = ((s & 4) ? rel[i].x : -rel[i].x) + ((s & 2) ? rel[i].y : -rel[i].y) + ((s & 1) ? rel[i].z : -rel[i].z);
-                if (v > best_v) { best_v = v; bi = i; bs = s; }
-            }
+    float3 clo[8], chi[8], rel[8];
+    int ccount[8];
+    bool cleaf[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; i++) {
+        if (i < n) {
+            const int c = cand[i];
+            const BNode b = bn[c];
+            clo[i] = b.lo; chi[i] = b.hi;
+            rel[i] = (b.lo + b.hi) * 0.5f - nc;
+            ccount[i] = node_count[c];
+            cleaf[i] = dp ? (dp[c].k >> 31) != 0u : ccount[i] <= SOLB_MAX_LEAF_TRIS;
+        } else {
+            clo[i] = chi[i] = rel[i] = f3(0.0f, 0.0f, 0.0f);
+            ccount[i] = 0;
+            cleaf[i] = false;
         }
-        slot_of[bi] = bs;
-        slot_used[bs] = true;
     }
+    int slot_of[8];
+    assign_child_slots(rel, n, slot_of);
     ChildRef ch[8];
     int child_of_slot[8];
-    for (int s = 0; s < 8; s++) { ch[s].valid = 0; child_of_slot[s] = -1; }
     uint32_t n_inner = 0, n_tris = 0;
-    for (int i = 0; i < n; i++) child_of_slot[slot_of[i]] = cand[i];
-    for (int s = 0; s < 8; s++) {
-        const int c = child_of_slot[s];
-        if (c < 0) continue;
-        ch[s].valid = 1;
-        ch[s].lo = bn[c].lo;
-        ch[s].hi = bn[c].hi;
-        const int cnt = node_count[c];
-        if (dp ? (dp[c].k >> 31) != 0u : cnt <= SOLB_MAX_LEAF_TRIS) {
-            ch[s].is_inner = 0; ch[s].tri_offset = n_tris; ch[s].tri_count = (uint32_t)cnt;
-            n_tris += (uint32_t)cnt;
-        } else {
-            ch[s].is_inner = 1; ch[s].tri_offset = 0; ch[s].tri_count = 0;
-            n_inner++;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int sl = 0; sl < 8; sl++) {
+        ch[sl].valid = 0;
+        child_of_slot[sl] = -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 8; i++) {
+            if (i < n && slot_of[i] == sl) {
+                child_of_slot[sl] = cand[i];
+                ch[sl].valid = 1;
+                ch[sl].lo = clo[i];
+                ch[sl].hi = chi[i];
+                if (cleaf[i]) {
+                    ch[sl].is_inner = 0; ch[sl].tri_offset = n_tris; ch[sl].tri_count = (uint32_t)ccount[i];
+                    n_tris += (uint32_t)ccount[i];
+                } else {
+                    ch[sl].is_inner = 1; ch[sl].tri_offset = 0; ch[sl].tri_count = 0;
+                    n_inner++;
+                }
+            }
         }
     }
     const uint32_t child_base = n_inner ? counter_add(wide_count, n_inner) : 0u;
@@ -363,10 +415,10 @@ SOLB_HD void collapse_one(const BNode *bn, const int *node_count, int n_internal
     encode_node8(wide[item.wnode], nlo, nhi, child_base, tri_base, ch);
     uint32_t q = n_inner ? counter_add(queue_out_count, n_inner) : 0u;
     uint32_t k = 0;
-    for (int s = 0; s < 8; s++) {
-        const int c = child_of_slot[s];
+    for (int sl = 0; sl < 8; sl++) {
+        const int c = child_of_slot[sl];
         if (c < 0) continue;
-        if (ch[s].is_inner) {
+        if (ch[sl].is_inner) {
             CollapseItem it;
             it.bnode = c;
             it.wnode = child_base + k;
@@ -376,7 +428,7 @@ SOLB_HD void collapse_one(const BNode *bn, const int *node_count, int n_internal
             int prims[SOLB_MAX_LEAF_TRIS + 1];
             const int m = gather_leaf_tris(bn, n_internal, c, prims);
             for (int j = 0; j < m; j++) {
-                const uint32_t dst = tri_base + ch[s].tri_offset + (uint32_t)j, prim = sorted_prim[prims[j]];
+                const uint32_t dst = tri_base + ch[sl].tri_offset + (uint32_t)j, prim = sorted_prim[prims[j]];
                 if (leaf_prim_out) leaf_prim_out[dst] = prim;
                 else tri_out[dst] = tri_world[prim];
             }

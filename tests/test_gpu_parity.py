@@ -425,12 +425,14 @@ def test_primary_hit_ids_vs_golden(sol, ctx, name, cam_name, w, h):
     assert (mism & (g["flags"] == 0)).sum() == 0
 
 
-def test_ao_vs_golden(sol, ctx):
+@pytest.mark.parametrize("accel", ["flat", "two_level"])
+def test_ao_vs_golden(sol, ctx, accel):
     from sol_rs_b200 import _native as N
     from sol_rs_b200 import ray, scene
 
     g = np.load(_os.path.join(GOLDEN, "ao_duck_160x90_f0-3.npz"))
-    sc, sd = _product(sol, ctx, "Duck")
+    sc = scene.load_scene(ctx, model_path("Duck"))
+    sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=N.ACCEL_TWO_LEVEL if accel == "two_level" else N.ACCEL_FLAT)
     ctx.set_blue_noise(load_blue_noise())
     cam = product_camera(sc, "Duck_ao", 160, 90)
     img = sol.Image2d(ctx, 160, 90, N.FORMAT_RGBA32F)
