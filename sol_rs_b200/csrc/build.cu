@@ -324,6 +324,26 @@ struct WarpTreeletScratch {
     int changed;
 };
 
+// Partition tables of the 7-leaf treelet (the only size gamma >= 7 produces): the 63 splits of the full set and the 31
+// splits of each of its seven 6-element subsets, in the enumeration order of the serial loop (p = (p - delta) & s), so the
+// lanes of a warp can share one subset's splits and still break ties like the serial code (first in order wins).
+struct TreeletTables {
+    uint8_t part7[64];
+    uint8_t part6[7][32];
+};
+__device__ void treelet_tables_init(TreeletTables &t, int tid) {
+    if (tid < 8) {  // tid 0..6: the 6-element subsets, tid 7: the full set
+        const int s = tid < 7 ? (127 ^ (1 << tid)) : 127;
+        uint8_t *out = tid < 7 ? t.part6[tid] : t.part7;
+        const int delta = (s - 1) & s;
+        int p = (-delta) & s, r = 0;
+        do {
+            out[r++] = (uint8_t)p;
+            p = (p - delta) & s;
+        } while (p != 0);
+    }
+}
+
 // Each warp optimises up to TL_GROUPS ready treelets at once, one per group of TL_GROUP lanes: treelet formation and the
 // topology rebuild are serial chains of dependent global loads / stores run by the group's first lane, so four of them
 // in flight per warp quadruple the memory-level parallelism of the pass; the 2^7 subset areas and the dynamic program are
@@ -334,7 +354,7 @@ constexpr int TL_GROUPS = 32 / TL_GROUP;
 
 // root < 0: this group has no treelet this round (it still takes part in the warp-wide barriers)
 __device__ void coop_optimize_treelet(BNode *bn, int *parent, float *node_cost, int *node_count, int n_internal, int root,
-                                      WarpTreeletScratch &ws, int glane) {
+                                      WarpTreeletScratch &ws, const TreeletTables &tt, int glane) {
     if (glane == 0) {  // treelet formation: expand the largest-area internal leaf until 7 leaves
         int nl = 0, ni = 0;
         if (root >= 0) {
@@ -387,8 +407,40 @@ __device__ void coop_optimize_treelet(BNode *bn, int *parent, float *node_cost, 
         if (__popc(s) == 1) { ws.cost[s] = ws.lcost[31 - __clz(s)]; ws.part[s] = 0; }
     }
     __syncwarp();
-    for (int k = 2; k <= SOLB_TREELET_N; k++) {  // dynamic program over subset sizes (every group runs all 6 barriers)
-        if (k <= nl)
+    // dynamic program over subset sizes (every group runs all the barriers).  Sizes 2..5 (21 + 35 + 35 + 21 subsets with
+    // 1..15 splits each): one lane per subset.  Sizes 6 and 7 of a full 7-leaf treelet (7 subsets x 31 splits, 1 x 63) would
+    // leave all but 7 / 1 lanes idle for 31 / 63 serial steps, 45 % of the kernel's instructions in the first profile
+    // (gpurun_out/prof_treelet.ncu-rep): there the lanes split each subset's table of splits and reduce (cost, order) by shuffle.
+    const bool fast67 = TL_GROUP == 32 && nl == SOLB_TREELET_N;  // warp-uniform only with one treelet per warp (full-mask shuffles)
+    for (int k = 2; k <= SOLB_TREELET_N; k++) {
+        if (fast67 && k >= 6) {
+            constexpr int LPS = TL_GROUP / 8;              // lanes per 6-element subset (7 subsets, 8th share idles)
+            const int lanes = k == 6 ? LPS : TL_GROUP;     // lanes sharing one subset
+            const int j = k == 6 ? glane / LPS : 0, sub = k == 6 ? glane % LPS : glane;
+            const int n_parts = k == 6 ? 31 : 63;
+            const bool have = k == 7 || j < 7;
+            const int s = k == 6 ? (127 ^ (1 << (j < 7 ? j : 0))) : 127;
+            const uint8_t *table = k == 6 ? tt.part6[j < 7 ? j : 0] : tt.part7;
+            float best_c = 3.4e38f;
+            int best_r = 0x7fffffff;
+            if (have)
+                for (int r = sub; r < n_parts; r += lanes) {
+                    const int p = table[r];
+                    const float c = ws.cost[p] + ws.cost[s ^ p];
+                    if (c < best_c) { best_c = c; best_r = r; }
+                }
+            for (int off = 1; off < lanes; off <<= 1) {  // lanes of one subset are contiguous and lanes is a power of two
+                const float oc = __shfl_xor_sync(0xffffffffu, best_c, off, TL_GROUP);
+                const int orr = __shfl_xor_sync(0xffffffffu, best_r, off, TL_GROUP);
+                if (oc < best_c || (oc == best_c && orr < best_r)) { best_c = oc; best_r = orr; }
+            }
+            if (have && sub == 0) {
+                float c = SOLB_SAH_CI * ws.area[s] + best_c;
+                if (ws.small[s]) c = fminf(c, SOLB_SAH_CT * ws.area[s] * (float)ws.small[s]);
+                ws.cost[s] = c;
+                ws.part[s] = best_r < n_parts ? table[best_r] : (uint8_t)0;
+            }
+        } else if (k <= nl)
             for (int s = glane + 1; s <= full; s += TL_GROUP) {
                 if (__popc(s) != k) continue;
                 float best_c = 3.4e38f;
@@ -446,6 +498,9 @@ constexpr int TL_BLOCK = 128;
 __global__ void __launch_bounds__(TL_BLOCK) k_bottom_up_coop(int n, BNode *bn, int *parent, int *node_count, float *node_cost,
                                                              uint32_t *flags, int gamma) {
     __shared__ WarpTreeletScratch scratch[TL_BLOCK / 32][TL_GROUPS];
+    __shared__ TreeletTables tables;
+    treelet_tables_init(tables, threadIdx.x);
+    __syncthreads();
     const int lane = threadIdx.x & 31, group = lane / TL_GROUP, glane = lane % TL_GROUP;
     WarpTreeletScratch &ws = scratch[threadIdx.x >> 5][group];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -481,7 +536,7 @@ __global__ void __launch_bounds__(TL_BLOCK) k_bottom_up_coop(int n, BNode *bn, i
                 if (m && g == group) root = r;
                 m &= m - 1;
             }
-            coop_optimize_treelet(bn, parent, node_cost, node_count, n - 1, root, ws, glane);
+            coop_optimize_treelet(bn, parent, node_cost, node_count, n - 1, root, ws, tables, glane);
         }
         if (active) {
             node = parent[node];

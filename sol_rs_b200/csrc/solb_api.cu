@@ -164,6 +164,9 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.pool_ctas_per_sm = env_int("SOLB_POOL_CTAS_PER_SM", c->tune.pool_ctas_per_sm, 1, 6);
         c->tune.pool_refill = env_int("SOLB_POOL_REFILL", c->tune.pool_refill, 1, 64);
         c->tune.ctas_per_sm_overlap = env_int("SOLB_CTAS_PER_SM_OVERLAP", c->tune.ctas_per_sm_overlap, 1, 16);
+        c->tune.mega_persistent = env_int("SOLB_MEGA_PERSISTENT", c->tune.mega_persistent, 0, 1);
+        c->tune.mega_ctas_per_sm = env_int("SOLB_MEGA_CTAS_PER_SM", c->tune.mega_ctas_per_sm, 1, 16);
+        c->tune.mega_fetch_idle = env_int("SOLB_MEGA_FETCH_IDLE", c->tune.mega_fetch_idle, 1, 32);
     }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
@@ -746,7 +749,8 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
     if (schedule == SOLB_SCHEDULE_AUTO) schedule = s->accel.n_wide <= 8 ? SOLB_SCHEDULE_MEGAKERNEL : SOLB_SCHEDULE_WAVEFRONT;
     if (schedule == SOLB_SCHEDULE_MEGAKERNEL) {
         CU(ctx, launch_pathtrace_mega(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, (float4 *)accum->dev,
-                                      render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0));
+                                      render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0,
+                                      (uint32_t *)(ctx->d_stats + 7), ctx->sm_count, ctx->tune));  // stats slot 7: pixel counter
         ctx->launches += 1;
         timer.stop();
         if (ctx->timing) { ctx->trace_kernel_ms_total += ctx->last_trace_ms; ctx->trace_kernel_launches += 1; }

@@ -5,6 +5,8 @@
 // Each launch sequence replaces one ShaderBindingTable::cmd_trace_rays (src/ray/sbt.rs:167-180).
 #include "trace.h"
 
+#include <algorithm>
+
 #include "shade.cuh"
 
 namespace solb {
@@ -191,6 +193,123 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConst
         const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
         accum[p] = out;
         if (render) render[p] = rgba;
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    warp_add_stat(stats, ST_HITS, nh);
+    warp_add_stat(stats, ST_PATHS, np);
+    if (STATS) {
+        warp_add_stat(stats, ST_NODES, ctr.nodes);
+        warp_add_stat(stats, ST_TRIS, ctr.tris);
+    }
+}
+
+__device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, uint32_t width, uint32_t height, bool &valid);
+
+// Persistent variant of the megakernel: a lane that finishes its pixel's samples resolves it and takes the next pixel
+// from a global counter (8x4-tile order, warp-aggregated batches), so a warp no longer waits for its longest pixel:
+// the per-pixel ray count varies 8..72 on the shipped scenes.  Per-pixel arithmetic and RNG streams are unchanged.
+constexpr uint32_t MEGA_BATCH = 64;
+template <bool STATS, bool TL>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega_persistent(const FrameConsts fc, const uint4 *__restrict__ nodes,
+                                                                           const float4 *__restrict__ tris,
+                                                                           const float4 *__restrict__ inst_leaves,
+                                                                           const DeviceInstance *__restrict__ instances,
+                                                                           const ShadeRecord *__restrict__ shade, float4 *accum,
+                                                                           uint32_t *render, unsigned long long *stats,
+                                                                           uint32_t *pixel_counter, uint32_t n_slots, int fetch_idle) {
+    SOLB_DECL_STACK();
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    uint32_t nr = 0, nh = 0, np = 0;
+    TraceCounters ctr = { 0, 0 };
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform range of tile-order slots
+    bool exhausted = false, has_pixel = false;
+    uint32_t x = 0, y = 0, rng = 0, sample = 0, depth = 0;
+    float3 pixel = f3(0, 0, 0), thr = f3(1, 1, 1);
+    Ray r;
+    r.o = fc.origin; r.d = f3(0, 0, 1); r.tmin = fc.tmin; r.tmax = fc.tmax;
+    uint32_t b_pix = 0;
+    for (;;) {
+        const uint32_t idle = ~b_pix;
+        if (!exhausted && __popc(idle) >= fetch_idle) {
+            const uint32_t want = (uint32_t)__popc(idle);
+            uint32_t served = 0;
+            while (served < want && !exhausted) {
+                if (pool_next >= pool_end) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(pixel_counter, MEGA_BATCH);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= n_slots) { exhausted = true; break; }
+                    pool_next = base;
+                    pool_end = min(base + MEGA_BATCH, n_slots);
+                }
+                const uint32_t take = min(want - served, pool_end - pool_next);
+                const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
+                if (!has_pixel && rank >= served && rank < served + take) {
+                    bool valid;
+                    const uint32_t p = swizzled_pixel(pool_next + (rank - served), fc.width, fc.height, valid);
+                    if (valid) {  // image edges leave holes in the tile order
+                        x = p % fc.width; y = p / fc.width;
+                        rng = tea(p, fc.frame);  // pathtrace.rgen:47
+                        pixel = f3(0, 0, 0); thr = f3(1, 1, 1);
+                        sample = 0; depth = 0;
+                        const float jx = next_rand(rng), jy = next_rand(rng);  // :52
+                        r.o = fc.origin;
+                        r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                        np++;
+                        has_pixel = true;
+                    }
+                }
+                pool_next += take;
+                served += take;
+            }
+            b_pix = __ballot_sync(0xffffffffu, has_pixel);
+        }
+        if (b_pix == 0u) {
+            if (exhausted) break;
+            continue;  // every slot of this round was an edge hole: fetch again
+        }
+        if (has_pixel) {
+            Hit h;
+            stack.sp = 0;
+            trace_any<STATS, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);  // :65-76
+            nr++;
+            bool end_path;
+            if (h.inst != SOLB_MISS) {
+                nh++;
+                float3 hv;
+                const bool done = shade_hit(instances, shade, h.inst, h.gtri, h.u, h.v, r.o, r.d, rng, hv);
+                depth++;
+                thr = thr * hv;  // :77
+                end_path = done;
+                if (!done && depth > fc.max_bounces) {  // :81-84
+                    thr = f3(0, 0, 0);
+                    end_path = true;
+                }
+            } else {
+                thr = thr * shade_miss(fc.enable_sky, r.d);  // rmiss, done = 1
+                end_path = true;
+            }
+            if (end_path) {
+                pixel = pixel + thr;  // :86
+                sample++;
+                if (sample < fc.spp) {
+                    const float jx = next_rand(rng), jy = next_rand(rng);
+                    r.o = fc.origin;
+                    r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                    thr = f3(1, 1, 1);
+                    depth = 0;
+                    np++;
+                } else {
+                    const size_t p = (size_t)y * fc.width + x;
+                    uint32_t rgba;
+                    const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
+                    accum[p] = out;
+                    if (render) render[p] = rgba;
+                    has_pixel = false;
+                }
+            }
+        }
+        b_pix = __ballot_sync(0xffffffffu, has_pixel);
     }
     warp_add_stat(stats, ST_RAYS, nr);
     warp_add_stat(stats, ST_HITS, nh);
@@ -769,9 +888,20 @@ cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const flo
 
 cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                                   const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
-                                  bool collect) {
+                                  bool collect, uint32_t *pixel_counter, int sm_count, const TraceTuning &tune) {
     const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
     const float4 *il = as.inst_leaves_f4();
+    if (pixel_counter && tune.mega_persistent) {
+        const uint32_t n_slots = ((fc.width + 7u) >> 3) * ((fc.height + 3u) >> 2) * 32u;
+        const uint32_t grid = std::min<uint32_t>(blocks, (uint32_t)(sm_count * tune.mega_ctas_per_sm));
+        cudaError_t err = cudaMemsetAsync(pixel_counter, 0, sizeof(uint32_t), st);
+        if (err != cudaSuccess) return err;
+#define SOLB_MEGA_P(S, T) k_pathtrace_mega_persistent<S, T><<<grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, accum, render, stats, pixel_counter, n_slots, tune.mega_fetch_idle)
+        if (as.two_level) { if (collect) SOLB_MEGA_P(true, true); else SOLB_MEGA_P(false, true); }
+        else { if (collect) SOLB_MEGA_P(true, false); else SOLB_MEGA_P(false, false); }
+#undef SOLB_MEGA_P
+        return cudaGetLastError();
+    }
     if (as.two_level) {
         if (collect) k_pathtrace_mega<true, true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, instances, shade, accum, render, stats);
         else k_pathtrace_mega<false, true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, instances, shade, accum, render, stats);

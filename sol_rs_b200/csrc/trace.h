@@ -33,6 +33,9 @@ struct TraceTuning {
     int pool = 0;              // 1: ray-pool traversal kernel (k_wf_trace_pool) instead of the lane-bound k_wf_trace
     int pool_ctas_per_sm = 6;  // its persistent CTAs per SM (34 KB shared memory each)
     int pool_refill = 16;      // refill free slots once this many of a warp's 64 are free
+    int mega_persistent = 1;   // megakernel schedule: persistent CTAs with dynamic pixel fetch (0: one thread per pixel)
+    int mega_ctas_per_sm = 6;  // its persistent CTAs per SM (80 registers -> 6 x 128 threads)
+    int mega_fetch_idle = 8;   // refill finished lanes once this many are idle
 };
 
 constexpr int WF_MAX_PARTS = 4;
@@ -52,7 +55,7 @@ cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const flo
                               unsigned long long *stats);
 cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                                   const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
-                                  bool collect);
+                                  bool collect, uint32_t *pixel_counter, int sm_count, const TraceTuning &tune);
 cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameConsts &fc, const AccelStorage &as,
                                        const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
                                        unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
