@@ -1,7 +1,7 @@
 // pathtrace_offscreen.cpp — examples/5-pathtrace.rs of the reference without the window: the same setup() /
 // render() call sequence through the C++ host mirror (sol.hpp), frames read back instead of presented.
 //   pathtrace_offscreen --model models/cornell.gltf [--sky] [--frames 8] [--size 512x512] [--bounces 32]
-//                       [--debug] [--out frame.ppm]
+//                       [--debug] [--two-level] [--out frame.ppm]
 // Prints one line: frames, ms/frame, Mrays/s, and an FNV-1a checksum of the final rgba8 frame.
 #include <chrono>
 #include <cstdio>
@@ -16,13 +16,14 @@ using namespace sol;
 
 int main(int argc, char **argv) {
     std::string model, out;
-    bool enable_sky = false, debug = false;
+    bool enable_sky = false, debug = false, two_level = false;
     uint32_t frames = 8, w = 1280, h = 720, bounces = 0;  // 1280x720: examples/5-pathtrace.rs:374
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--model" && i + 1 < argc) model = argv[++i];       // examples/5-pathtrace.rs:120-125
         else if (a == "--sky") enable_sky = true;                     // :220
         else if (a == "--debug") debug = true;
+        else if (a == "--two-level") two_level = true;  // TLAS over object-space BLASes instead of the flattened hierarchy
         else if (a == "--frames" && i + 1 < argc) frames = (uint32_t)atoi(argv[++i]);
         else if (a == "--bounces" && i + 1 < argc) bounces = (uint32_t)atoi(argv[++i]);
         else if (a == "--out" && i + 1 < argc) out = argv[++i];
@@ -36,6 +37,10 @@ int main(int argc, char **argv) {
         if (!path) path = model;
         scene::Scene scene = scene::load_scene(context, *path);
         ray::SceneDescription scene_description = ray::SceneDescription::from_scene(context, scene);
+        if (two_level) {
+            scene_description.set_accel_mode(SOLB_ACCEL_TWO_LEVEL);
+            scene_description.accel_build();
+        }
         scene::Camera camera = scene.camera ? *scene.camera : scene::Camera(Vec2{ (float)w, (float)h });
         if (debug) { camera = scene::Camera(Vec2{ (float)w, (float)h }); camera.look_at({ 5, 5, 5 }, { 0, 0, 0 }, { 0, -1, 0 }); }
         else camera.set_window_size(Vec2{ (float)w, (float)h });

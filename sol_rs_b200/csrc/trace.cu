@@ -205,9 +205,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConst
 
 __device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, uint32_t width, uint32_t height, bool &valid);
 
-// Persistent variant of the megakernel: a lane that finishes its pixel's samples resolves it and takes the next pixel
-// from a global counter (8x4-tile order, warp-aggregated batches), so a warp no longer waits for its longest pixel:
-// the per-pixel ray count varies 8..72 on the shipped scenes.  Per-pixel arithmetic and RNG streams are unchanged.
+// Persistent variant of the megakernel (experimental, SOLB_MEGA_PERSISTENT=1): a lane that finishes its pixel's samples
+// resolves it and takes the next pixel from a global counter (8x4-tile order, warp-aggregated batches), so a warp no longer
+// waits for its longest pixel (the per-pixel ray count varies 8..72 on the shipped scenes).  Per-pixel arithmetic and RNG
+// streams are unchanged.  Measured 5 % slower than one thread per pixel (TraceTuning::mega_persistent): kept for comparison.
 constexpr uint32_t MEGA_BATCH = 64;
 template <bool STATS, bool TL>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega_persistent(const FrameConsts fc, const uint4 *__restrict__ nodes,

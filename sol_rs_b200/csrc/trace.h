@@ -33,7 +33,10 @@ struct TraceTuning {
     int pool = 0;              // 1: ray-pool traversal kernel (k_wf_trace_pool) instead of the lane-bound k_wf_trace
     int pool_ctas_per_sm = 6;  // its persistent CTAs per SM (34 KB shared memory each)
     int pool_refill = 16;      // refill free slots once this many of a warp's 64 are free
-    int mega_persistent = 1;   // megakernel schedule: persistent CTAs with dynamic pixel fetch (0: one thread per pixel)
+    int mega_persistent = 0;   // megakernel schedule: persistent CTAs with dynamic pixel fetch instead of one thread per pixel.
+                               // Measured slower (cornell 1080p 8 027 vs 8 459 Mrays/s, tunnel 2 236 vs 2 284): the hardware block
+                               // scheduler already refills finished warps, only the intra-warp imbalance is left to win and the
+                               // refill code costs more than that.  Off by default (SOLB_MEGA_PERSISTENT=1 to compare).
     int mega_ctas_per_sm = 6;  // its persistent CTAs per SM (80 registers -> 6 x 128 threads)
     int mega_fetch_idle = 8;   // refill finished lanes once this many are idle
 };

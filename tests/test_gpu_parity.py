@@ -467,6 +467,12 @@ def test_cpp_host_example_runs_the_reference_call_sequence(sol, ctx):
         h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     assert info["fnv1a"] == "%016x" % h
     assert info["rays"] > 0
+    # the same frames through the two-level structure (C++ mirror: set_accel_mode + accel_build)
+    out2 = subprocess.run([exe, "--model", "models/cornell.gltf", "--frames", "3", "--size", "160x120", "--two-level"], capture_output=True,
+                          text=True, cwd=ROOT, timeout=120)
+    assert out2.returncode == 0, out2.stderr
+    info2 = json.loads(out2.stdout.strip().splitlines()[-1])
+    assert info2["rays"] > 0 and abs(info2["rays"] - info["rays"]) <= 0.002 * info["rays"]
     # error behaviour: the reference panics without --model
     bad = subprocess.run([exe], capture_output=True, text=True, cwd=ROOT, timeout=60)
     assert bad.returncode != 0 and "no gltf file given" in bad.stderr
