@@ -410,7 +410,7 @@ __device__ void coop_optimize_treelet(BNode *bn, int *parent, float *node_cost, 
     // dynamic program over subset sizes (every group runs all the barriers).  Sizes 2..5 (21 + 35 + 35 + 21 subsets with
     // 1..15 splits each): one lane per subset.  Sizes 6 and 7 of a full 7-leaf treelet (7 subsets x 31 splits, 1 x 63) would
     // leave all but 7 / 1 lanes idle for 31 / 63 serial steps, 45 % of the kernel's instructions in the first profile
-    // (gpurun_out/prof_treelet.ncu-rep): there the lanes split each subset's table of splits and reduce (cost, order) by shuffle.
+    // (profiles/r01_ncu_k_bottom_up_coop.txt): there the lanes split each subset's table of splits and reduce (cost, order) by shuffle.
     const bool fast67 = TL_GROUP == 32 && nl == SOLB_TREELET_N;  // warp-uniform only with one treelet per warp (full-mask shuffles)
     for (int k = 2; k <= SOLB_TREELET_N; k++) {
         if (fast67 && k >= 6) {
