@@ -151,6 +151,25 @@ def _find_mesh(doc, node_idx, transforms, mesh_index):
     return False
 
 
+def mesh_first_node(doc, mesh_index):
+    """index of the node the reference's search (src/scene/mod.rs:106-136) stops at for this mesh, or -1"""
+    def walk(i):
+        node = doc["nodes"][i]
+        if node.get("mesh", None) == mesh_index:
+            return i
+        for c in node.get("children", []):
+            r = walk(c)
+            if r >= 0:
+                return r
+        return -1
+
+    for i in range(len(doc.get("nodes", []))):
+        r = walk(i)
+        if r >= 0:
+            return r
+    return -1
+
+
 def mesh_global_transform(doc, mesh_index):
     """src/scene/mod.rs:124-136: scan nodes in index order, first subtree holding the mesh wins."""
     g = np.eye(4, dtype=F32)
@@ -226,7 +245,32 @@ class FlatScene:
         self.camera = None  # dict(view=[4,4], yfov, znear, zfar) or None
 
 
-def load_scene(path):
+def _other_node_transforms(doc, mesh_index, first_node):
+    """glTF node-graph instancing (beyond the reference): the global transform root -> node of every node that
+    references the mesh except the one the reference's own search stopped at, node-index order."""
+    nodes = doc.get("nodes", [])
+    parent = [-1] * len(nodes)
+    for i, n in enumerate(nodes):
+        for c in n.get("children", []):
+            if 0 <= c < len(nodes):
+                parent[c] = i
+    out = []
+    for i, n in enumerate(nodes):
+        if i == first_node or n.get("mesh", None) != mesh_index:
+            continue
+        chain, k = [], i
+        while k >= 0 and len(chain) <= len(nodes):
+            chain.append(k)
+            k = parent[k]
+        gm = np.eye(4, dtype=F32)
+        for k in reversed(chain):
+            gm = mat4_mul(gm, node_matrix(nodes[k]))
+        out.append(gm)
+    return out
+
+
+def load_scene(path, instancing=False):
+    """instancing=True appends, after the reference's instances, one instance per (further node of a mesh) x (section)."""
     g = Gltf(path)
     doc = g.doc
     fs = FlatScene()
@@ -293,6 +337,11 @@ def load_scene(path):
             if sec["material"] is None:
                 raise ValueError("primitive without material: the reference unwrap()s (src/scene/mod.rs:65)")
             fs.instances.append(dict(mesh=mi, transform=mesh["transform"], **sec))
+    if instancing:
+        for mi, mesh in enumerate(fs.meshes):
+            for t in _other_node_transforms(doc, mi, mesh_first_node(doc, mi)):
+                for sec in mesh["sections"]:
+                    fs.instances.append(dict(mesh=mi, transform=t, **sec))
     # camera: first camera only, perspective only (src/scene/mod.rs:261-287)
     cams = doc.get("cameras", [])
     if cams and cams[0].get("type") == "perspective":

@@ -135,28 +135,53 @@ Mat4 node_matrix(const json::Value &node) {
     return math::mul(math::mul(T, R), S);
 }
 
-bool find_mesh(const json::Value &nodes, size_t node_index, std::vector<Mat4> &transforms, long mesh_index) {  // mod.rs:106-122
+bool find_mesh(const json::Value &nodes, size_t node_index, std::vector<Mat4> &transforms, long mesh_index, long *found_node) {  // mod.rs:106-122
     const json::Value &node = nodes[node_index];
     transforms.push_back(node_matrix(node));
-    if (node.has("mesh") && node["mesh"].integer(-1) == mesh_index) return true;
+    if (node.has("mesh") && node["mesh"].integer(-1) == mesh_index) { *found_node = (long)node_index; return true; }
     const json::Value &children = node["children"];
     for (size_t i = 0; i < children.size(); i++)
-        if (find_mesh(nodes, (size_t)children[i].integer(0), transforms, mesh_index)) return true;
+        if (find_mesh(nodes, (size_t)children[i].integer(0), transforms, mesh_index, found_node)) return true;
     transforms.pop_back();
     return false;
 }
 
-Mat4 calc_mesh_global_transform(const Doc &d, long mesh_index) {  // mod.rs:124-136
+Mat4 calc_mesh_global_transform(const Doc &d, long mesh_index, long *found_node) {  // mod.rs:124-136
     Mat4 g = math::identity();
     std::vector<Mat4> transforms;
     const json::Value &nodes = d.root["nodes"];
+    *found_node = -1;
     for (size_t i = 0; i < nodes.size(); i++) {
-        if (find_mesh(nodes, i, transforms, mesh_index)) {
+        if (find_mesh(nodes, i, transforms, mesh_index, found_node)) {
             for (const Mat4 &t : transforms) g = math::mul(g, t);
             break;
         }
     }
     return g;
+}
+
+// glTF node-graph instancing (beyond the reference): the true global transform (root -> node) of every node that
+// references the mesh, except the node the reference's own search stopped at
+std::vector<Mat4> other_node_transforms(const Doc &d, long mesh_index, long first_node) {
+    const json::Value &nodes = d.root["nodes"];
+    std::vector<long> parent(nodes.size(), -1);
+    for (size_t i = 0; i < nodes.size(); i++) {
+        const json::Value &children = nodes[i]["children"];
+        for (size_t k = 0; k < children.size(); k++) {
+            const long c = children[k].integer(-1);
+            if (c >= 0 && (size_t)c < nodes.size()) parent[(size_t)c] = (long)i;
+        }
+    }
+    std::vector<Mat4> out;
+    for (size_t i = 0; i < nodes.size(); i++) {
+        if ((long)i == first_node || !nodes[i].has("mesh") || nodes[i]["mesh"].integer(-1) != mesh_index) continue;
+        std::vector<long> chain;
+        for (long n = (long)i; n >= 0 && chain.size() <= nodes.size(); n = parent[(size_t)n]) chain.push_back(n);
+        Mat4 g = math::identity();
+        for (size_t k = chain.size(); k-- > 0;) g = math::mul(g, node_matrix(nodes[(size_t)chain[k]]));
+        out.push_back(g);
+    }
+    return out;
 }
 
 }  // namespace
@@ -277,7 +302,9 @@ Scene load_scene(std::shared_ptr<Context>, const std::string &filepath) {
             }
             mesh.primitive_sections.push_back(sec);
         }
-        mesh.transform = calc_mesh_global_transform(d, (long)mi);
+        long first_node = -1;
+        mesh.transform = calc_mesh_global_transform(d, (long)mi, &first_node);
+        mesh.extra_instance_transforms = other_node_transforms(d, (long)mi, first_node);
         scene.meshes.push_back(std::move(mesh));
     }
 

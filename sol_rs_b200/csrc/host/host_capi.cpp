@@ -43,6 +43,14 @@ SOLH_API int solh_mesh_info(const scene::Scene *s, uint32_t i, SolhMeshInfo *out
     std::snprintf(out->name, sizeof(out->name), "%s", m.name.c_str());
     return 0;
 }
+SOLH_API uint32_t solh_mesh_extra_instance_count(const scene::Scene *s, uint32_t i) {
+    return i < s->meshes.size() ? (uint32_t)s->meshes[i].extra_instance_transforms.size() : 0u;
+}
+SOLH_API int solh_mesh_extra_instance_transform(const scene::Scene *s, uint32_t i, uint32_t k, float *out) {
+    if (i >= s->meshes.size() || k >= s->meshes[i].extra_instance_transforms.size()) return -1;
+    std::memcpy(out, s->meshes[i].extra_instance_transforms[k].data(), 64);
+    return 0;
+}
 // material_index = 0xffffffff when the primitive has none; n_indices = 0 when it is not indexed
 SOLH_API int solh_mesh_sections(const scene::Scene *s, uint32_t i, SolbSection *out) {
     if (i >= s->meshes.size()) return -1;

@@ -179,11 +179,28 @@ SceneUniforms SceneUniforms::from(const scene::Camera &camera, UVec3 frame) {  /
 // ---- ray -------------------------------------------------------------------------------------------------
 namespace ray {
 
-SceneDescription SceneDescription::from_scene(std::shared_ptr<Context> context, const scene::Scene &scene) {  // src/ray/mod.rs:50-57
+SceneDescription SceneDescription::from_scene(std::shared_ptr<Context> context, const scene::Scene &scene, SolbAccelMode accel_mode,
+                                              bool instancing) {  // src/ray/mod.rs:50-57
     std::vector<const scene::Mesh *> meshes;
     std::vector<Mat4> transforms;
     for (const auto &m : scene.meshes) { meshes.push_back(&m); transforms.push_back(m.transform); }
-    return from_meshes(std::move(context), meshes, transforms, &scene.materials);
+    SceneDescription sd = from_meshes(std::move(context), meshes, transforms, &scene.materials);
+    bool rebuild = accel_mode != SOLB_ACCEL_FLAT;
+    if (rebuild) sd.set_accel_mode(accel_mode);
+    if (instancing) {
+        // instance ids run over meshes x sections (src/ray/mod.rs:113); further nodes of a mesh append instances of the same BLASes
+        size_t first_instance = 0;
+        for (const auto &m : scene.meshes) {
+            for (const Mat4 &t : m.extra_instance_transforms)
+                for (size_t k = 0; k < m.primitive_sections.size(); k++) {
+                    sd.add_instance(first_instance + k, t, (uint32_t)*m.primitive_sections[k].material_index);
+                    rebuild = true;
+                }
+            first_instance += m.primitive_sections.size();
+        }
+    }
+    if (rebuild) sd.accel_build();
+    return sd;
 }
 
 SceneDescription SceneDescription::from_meshes(std::shared_ptr<Context> context, const std::vector<const scene::Mesh *> &meshes,

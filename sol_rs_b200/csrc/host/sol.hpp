@@ -108,6 +108,11 @@ struct Mesh {  // src/scene/mesh.rs:53-61 (buffers kept as host arrays; SceneDes
     std::vector<uint32_t> indices;
     Mat4 transform;
     std::vector<PrimitiveSection> primitive_sections;
+    // Beyond the reference (glTF node-graph instancing): global transforms of the OTHER nodes that reference
+    // this mesh, in node-index order.  The reference gives a mesh only the first node's transform (`transform`, found by
+    // its own search, src/scene/mod.rs:106-136); SceneDescription::from_scene(..., instancing = true) turns these into
+    // additional instances of the same BLASes.
+    std::vector<Mat4> extra_instance_transforms;
 };
 
 class Camera {  // src/scene/camera.rs:34-127,264-270 (mouse manipulators are out of scope)
@@ -154,7 +159,10 @@ using SceneInstance = SolbSceneInstance;  // src/ray/mod.rs:16-24
 
 class SceneDescription {  // src/ray/mod.rs:38-206
 public:
-    static SceneDescription from_scene(std::shared_ptr<Context> context, const scene::Scene &scene);
+    // instancing: every further node referencing a mesh becomes one more instance of its BLASes (accel_mode is then best
+    // SOLB_ACCEL_TWO_LEVEL so they share geometry)
+    static SceneDescription from_scene(std::shared_ptr<Context> context, const scene::Scene &scene,
+                                       SolbAccelMode accel_mode = SOLB_ACCEL_FLAT, bool instancing = false);
     static SceneDescription from_meshes(std::shared_ptr<Context> context, const std::vector<const scene::Mesh *> &meshes,
                                         const std::vector<Mat4> &mesh_transforms, const std::vector<scene::MaterialInfo> *materials);
     SceneDescription(SceneDescription &&o) noexcept;

@@ -23,8 +23,21 @@ class SceneDescription:
         self._lib = N.lib()
 
     @classmethod
-    def from_scene(cls, context, scene, accel_mode=N.ACCEL_FLAT):
-        return cls.from_meshes(context, scene.meshes, [m.transform for m in scene.meshes], scene.materials, accel_mode)
+    def from_scene(cls, context, scene, accel_mode=N.ACCEL_FLAT, instancing=False):
+        """src/ray/mod.rs:50-57.  instancing=True (beyond the reference): every further glTF node that references
+        a mesh becomes one more instance of that mesh's BLASes (instance ids continue the running count)."""
+        sd = cls.from_meshes(context, scene.meshes, [m.transform for m in scene.meshes], scene.materials, accel_mode)
+        if instancing:
+            first, added = 0, False
+            for m in scene.meshes:
+                for t in getattr(m, "extra_instance_transforms", ()):
+                    for k, ps in enumerate(m.primitive_sections):
+                        sd.add_instance(first + k, t, ps.material_index)
+                        added = True
+                first += len(m.primitive_sections)
+            if added:
+                sd.accel_build()
+        return sd
 
     @classmethod
     def from_meshes(cls, context, meshes, mesh_transforms, materials, accel_mode=N.ACCEL_FLAT):

@@ -40,6 +40,9 @@ def hostlib():
         H.solh_scene_has_camera.argtypes = [vp]
         H.solh_mesh_info.argtypes = [vp, u32, ctypes.POINTER(_MeshInfo)]
         H.solh_mesh_sections.argtypes = [vp, u32, ctypes.POINTER(N.Section)]
+        H.solh_mesh_extra_instance_count.restype = u32
+        H.solh_mesh_extra_instance_count.argtypes = [vp, u32]
+        H.solh_mesh_extra_instance_transform.argtypes = [vp, u32, u32, vp]
         H.solh_camera_new.restype = vp
         H.solh_camera_new.argtypes = [f, f]
         H.solh_camera_from_scene.restype = vp
@@ -77,12 +80,15 @@ class Mesh:
     """src/scene/mesh.rs:53-61 with the buffers as host arrays: vertices float32 [n, 16] (ModelVertex),
     indices uint32 [m] (section-relative), transform float32 [16] column-major."""
 
-    def __init__(self, name, vertices, indices, transform, primitive_sections):
+    def __init__(self, name, vertices, indices, transform, primitive_sections, extra_instance_transforms=()):
         self.name = name
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 16)
         self.indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
         self.transform = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
         self.primitive_sections = list(primitive_sections)
+        # beyond the reference (SURVEY 8f-3): global transforms of the other nodes referencing this mesh; the reference keeps
+        # only the first node's (`transform`).  ray.SceneDescription.from_scene(..., instancing=True) instantiates them.
+        self.extra_instance_transforms = [np.ascontiguousarray(t, dtype=np.float32).reshape(16) for t in extra_instance_transforms]
 
 
 class Camera:
@@ -165,7 +171,13 @@ def load_scene(context, filepath):
             sections = [PrimitiveSection(k, s.first_vertex, s.n_vertices, s.first_index, s.n_indices,
                                          None if s.material_index == 0xFFFFFFFF else int(s.material_index))
                         for k, s in enumerate(secs[: info.n_sections])]
-            meshes.append(Mesh(info.name.decode("utf-8", "replace"), verts, inds, np.array(info.transform[:], dtype=np.float32), sections))
+            extra = []
+            for k in range(H.solh_mesh_extra_instance_count(h, i)):
+                t = np.zeros(16, dtype=np.float32)
+                H.solh_mesh_extra_instance_transform(h, i, k, t.ctypes.data_as(ctypes.c_void_p))
+                extra.append(t)
+            meshes.append(Mesh(info.name.decode("utf-8", "replace"), verts, inds, np.array(info.transform[:], dtype=np.float32), sections,
+                               extra))
         nm = H.solh_scene_material_count(h)
         mats = np.ctypeslib.as_array(ctypes.cast(H.solh_scene_materials(h), ctypes.POINTER(ctypes.c_float)),
                                      shape=(nm, 12)).copy() if nm else np.zeros((0, 12), np.float32)

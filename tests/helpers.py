@@ -154,3 +154,34 @@ def write_glb(gltf_path, out_path):
         f.write(struct.pack("<II", len(js), 0x4E4F534A) + js)
         f.write(struct.pack("<II", len(blob), 0x004E4942) + blob)
     return out_path
+
+
+def write_instanced_gltf(gltf_path, out_path):
+    """Copy of a .gltf whose mesh 0 is referenced by three more nodes: a sibling of its original node, a root node with a
+    rotation + translation, and a grandchild under a scaled parent (glTF node-graph instancing)."""
+    import json
+    import shutil
+
+    with open(gltf_path) as f:
+        doc = json.load(f)
+    base = os.path.dirname(os.path.abspath(gltf_path))
+    for b in doc.get("buffers", []):
+        if not b["uri"].startswith("data:"):
+            shutil.copy(os.path.join(base, b["uri"]), os.path.join(os.path.dirname(out_path), b["uri"]))
+    nodes = doc["nodes"]
+    n0 = len(nodes)
+    nodes.append({"mesh": 0, "translation": [150.0, 0.0, 40.0], "rotation": [0.0, 0.38268343, 0.0, 0.92387953]})   # n0: root-level
+    nodes.append({"children": [n0 + 2], "scale": [0.5, 0.5, 0.5], "translation": [-120.0, 30.0, 0.0]})              # n0+1: scaled parent
+    nodes.append({"children": [n0 + 3], "rotation": [0.70710678, 0.0, 0.0, 0.70710678]})                           # n0+2
+    nodes.append({"mesh": 0, "translation": [0.0, 0.0, 200.0]})                                                    # n0+3: grandchild
+    scene0 = doc["scenes"][doc.get("scene", 0)]
+    # hang the new roots under the same parent chain as the original mesh node so they inherit its root scale
+    first = next(i for i, n in enumerate(nodes) if n.get("mesh", None) == 0)
+    parent = next((i for i, n in enumerate(nodes) if first in n.get("children", [])), None)
+    if parent is None:
+        scene0["nodes"] += [n0, n0 + 1]
+    else:
+        nodes[parent]["children"] += [n0, n0 + 1]
+    with open(out_path, "w") as f:
+        json.dump(doc, f)
+    return out_path

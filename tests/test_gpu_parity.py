@@ -176,11 +176,11 @@ def test_random_rays_vs_oracle(sol, ctx):
 
 # ---- path tracing ----------------------------------------------------------------------------------------
 
-def _render_gpu(sol, ctx, name, w, h, frames, sky, spp, mb, schedule, accum_mode=0, start=0, collect=False):
+def _render_gpu(sol, ctx, name, w, h, frames, sky, spp, mb, schedule, accum_mode=0, start=0, collect=False, two_level=False):
     from sol_rs_b200 import _native as N
     from sol_rs_b200 import ray, scene
 
-    sc, sd = _product(sol, ctx, name)
+    sc, sd = _product_two_level(sol, ctx, name) if two_level else _product(sol, ctx, name)
     cam = product_camera(sc, name, w, h)
     accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
     render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
@@ -390,12 +390,12 @@ GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("name,w,h,sky,mb", [("tunnel", 160, 90, True, 8), ("cornell", 96, 96, False, 32)])
-@pytest.mark.parametrize("schedule", [0, 1])
-def test_converged_image_vs_golden(sol, ctx, name, w, h, sky, mb, schedule):
+@pytest.mark.parametrize("schedule,two_level", [(0, False), (1, False), (0, True)])
+def test_converged_image_vs_golden(sol, ctx, name, w, h, sky, mb, schedule, two_level):
     """512 frames x 8 spp = 4096 spp: mean relative error < 1 % and PSNR > 40 dB (BASELINE.json north_star)."""
     g = np.load(_os.path.join(GOLDEN, "converged_%s_%dx%d_4096spp_b%d.npz" % (name, w, h, mb)))
     ctx.reset_stats()
-    acc, rgba = _render_gpu(sol, ctx, name, w, h, range(512), sky, 8, mb, schedule)
+    acc, rgba = _render_gpu(sol, ctx, name, w, h, range(512), sky, 8, mb, schedule, two_level=two_level)
     st = ctx.stats()
     mre, psnr = image_metrics(acc, g["accum"])
     assert mre < 0.01, "mean relative error %.4f" % mre
@@ -727,3 +727,40 @@ def test_two_level_many_instances_tlas_rebuild_time(sol, ctx):
     h4, _ = two.trace_rays(rays)
     h5, _ = sds["two_general"].trace_rays(rays)
     assert np.array_equal(h4, h5) and not np.array_equal(h4, h2)
+
+
+@pytest.mark.parametrize("accel", ["two_level", "flat"])
+def test_node_graph_instancing_end_to_end(sol, ctx, accel, tmp_path):
+    """glTF node-graph instancing: load_scene exposes the further nodes of a mesh, from_scene(instancing=True)
+    turns them into instances of the same BLAS; hits and a path-traced frame equal the oracle over the flattened scene."""
+    from helpers import write_instanced_gltf
+    from oracle import gltf_flatten as gf
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    path = write_instanced_gltf(model_path("Duck"), str(tmp_path / "Duck_inst.gltf"))
+    fs = gf.load_scene(path, instancing=True)
+    osc = oracle.Scene(fs)
+    sc = scene.load_scene(ctx, path)
+    sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=N.ACCEL_TWO_LEVEL if accel == "two_level" else N.ACCEL_FLAT, instancing=True)
+    info = sd.accel_info()
+    assert info.n_instances == 3 and info.n_blas == 1
+    assert info.n_triangles == (4212 if accel == "two_level" else 3 * 4212)
+    rays = _sphere_rays(osc, 300_000, 21)
+    o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
+    hits, t = sd.trace_rays(rays)
+    assert (np.any(hits[:, :2] != o_hits[:, :2], axis=1) & (flags == 0)).sum() == 0
+    assert set(np.unique(o_hits[:, 0]).tolist()) >= {0, 1, 2}
+    # one path-traced frame (sky on so the ducks are lit) through the wavefront schedule
+    w, h = 160, 120
+    cam = scene.Camera((w, h))
+    cam.look_at((5, 5, 5), (0, 0, 0), (0, -1, 0))
+    ocamera = ocam.Camera((w, h))
+    ocamera.look_at((5, 5, 5), (0, 0, 0), (0, -1, 0))
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    pathtrace_pipeline(ctx, True).cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 0), accum, None, max_bounces=8,
+                                                                   schedule=N.SCHEDULE_WAVEFRONT), (w, h, 1))
+    ref = np.zeros((h, w, 4), np.float32)
+    osc.pathtrace_frame(ocam.scene_uniforms(ocamera, w, h, 0), w, h, ref, 0, True, 8, 8)
+    d = np.abs(accum.readback()[..., :3] - ref[..., :3])
+    assert (d.max(axis=2) > 1e-3 * (1 + ref[..., :3].max(axis=2))).mean() < 0.02 and d.sum() / ref[..., :3].sum() < 0.01

@@ -204,3 +204,35 @@ def test_glb_container_loads_like_its_gltf(name, tmp_path):
     bad.write_bytes(raw[: len(raw) // 2])                        # truncated
     with pytest.raises(Exception):
         scene.load_scene(None, str(bad))
+
+
+def test_node_graph_instancing_loader(tmp_path):
+    """a mesh referenced by several glTF nodes.  The reference keeps the first node's transform only
+    (src/scene/mod.rs:106-136, App.A item 5) — unchanged; the further nodes' global transforms are exposed separately and
+    agree between the C++ loader and the oracle-side flatten."""
+    from helpers import write_instanced_gltf
+    from sol_rs_b200 import scene
+
+    path = write_instanced_gltf(model_path("Duck"), str(tmp_path / "Duck_inst.gltf"))
+    ref, ref_plain = gf.load_scene(path), gf.load_scene(model_path("Duck"))
+    assert len(ref.instances) == 1 and np.array_equal(ref.instances[0]["transform"], ref_plain.instances[0]["transform"])
+    inst = gf.load_scene(path, instancing=True)
+    assert len(inst.instances) == 3 and np.array_equal(inst.instances[0]["transform"], ref.instances[0]["transform"])
+    s = scene.load_scene(None, path)
+    assert len(s.meshes) == 1 and len(s.meshes[0].extra_instance_transforms) == 2
+    assert np.array_equal(s.meshes[0].transform, ref.meshes[0]["transform"].reshape(16))
+    for t, oi in zip(s.meshes[0].extra_instance_transforms, inst.instances[1:]):
+        np.testing.assert_allclose(t, oi["transform"].reshape(16), rtol=0, atol=0)
+    # independent point check of the grandchild: origin -> T(0,0,200) -> rotX(+90 deg): (0,-200,0) -> scale .5 ->
+    # T(-120,30,0): (-120,-70,0) in the frame of the node the new roots were hung under
+    import json
+
+    doc = json.load(open(path))
+    first = next(i for i, n in enumerate(doc["nodes"]) if n.get("mesh", None) == 0)
+    par = next((i for i, n in enumerate(doc["nodes"]) if first in n.get("children", [])), None)
+    assert par is not None and not any(par in n.get("children", []) for n in doc["nodes"]), "Duck: mesh node under one root node"
+    P = gf.node_matrix(doc["nodes"][par]).astype(np.float64).T  # arrays are [col][row]
+    want = P @ np.array([-120.0, -70.0, 0.0, 1.0])
+    got = inst.instances[2]["transform"].astype(np.float64).T @ np.array([0.0, 0.0, 0.0, 1.0])
+    np.testing.assert_allclose(got[:3], want[:3], rtol=1e-5, atol=1e-5)
+    assert len(scene.load_scene(None, model_path("Duck")).meshes[0].extra_instance_transforms) == 0
