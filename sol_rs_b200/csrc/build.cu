@@ -1381,7 +1381,8 @@ cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, Ac
     {
         Node8 *final_nodes = nullptr;
         CK(dalloc(&final_nodes, out.n_wide));
-        // the TLAS region is written by rebuild_tlas below; copy the BLAS part
+        // the TLAS region is written by rebuild_tlas below (unused slots stay zero = empty nodes); copy the BLAS part
+        CK(cudaMemsetAsync(final_nodes, 0, sizeof(Node8) * std::min(out.n_wide, tlas_cap), st));
         if (out.n_wide > tlas_cap)
             CK(cudaMemcpyAsync(final_nodes + tlas_cap, wide + tlas_cap, sizeof(Node8) * (out.n_wide - tlas_cap), cudaMemcpyDeviceToDevice, st));
         out.nodes = final_nodes;

@@ -947,7 +947,7 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
     if (n_lanes < 1) n_lanes = 1;
     const uint32_t rows_per_lane = (tiles_y + n_lanes - 1) / n_lanes;
     const int trace_grid = L.sm_count * (n_lanes > 1 ? tune.ctas_per_sm_overlap : tune.ctas_per_sm);  // persistent CTAs of 128 threads
-    const int shade_grid = L.sm_count * (n_lanes > 1 ? 2 : 4);                                        // grid-stride
+    const int shade_grid = L.sm_count * (n_lanes > 1 ? tune.shade_ctas_per_sm_overlap : 4);          // grid-stride
     // every pixel needs at least spp rays; at most spp * (max_bounces + 2)
     const uint32_t max_waves = fc.spp * (fc.max_bounces + 2u);
     const uint32_t check_every = (uint32_t)tune.check_every;

@@ -29,6 +29,7 @@ struct TraceTuning {
     int overlap = 3;       // frame parts (1..4) run as independent wave sequences on their own streams, so the drain tail of one
                            // part's persistent trace kernel and its memory-bound shade kernel overlap another part's traversal
     int ctas_per_sm_overlap = 5;  // persistent CTAs per SM and part when overlapping
+    int shade_ctas_per_sm_overlap = 2;  // grid-stride shade CTAs (256 threads) per SM and part when overlapping
     int sort_shade = 0;        // 1: material-sorted shading (block-level counting sort of the shade queue by hit class)
     int pool = 0;              // 1: ray-pool traversal kernel (k_wf_trace_pool) instead of the lane-bound k_wf_trace
     int pool_ctas_per_sm = 6;  // its persistent CTAs per SM (34 KB shared memory each)

@@ -764,3 +764,77 @@ def test_node_graph_instancing_end_to_end(sol, ctx, accel, tmp_path):
     osc.pathtrace_frame(ocam.scene_uniforms(ocamera, w, h, 0), w, h, ref, 0, True, 8, 8)
     d = np.abs(accum.readback()[..., :3] - ref[..., :3])
     assert (d.max(axis=2) > 1e-3 * (1 + ref[..., :3].max(axis=2))).mean() < 0.02 and d.sum() / ref[..., :3].sum() < 0.01
+
+
+def _tiny_scene(tri_sets, transforms):
+    """meshes of hand-made triangles -> (product meshes, oracle FlatScene).  tri_sets[i] = float [k, 3, 3]."""
+    from oracle import gltf_flatten as gf
+    from sol_rs_b200 import scene
+
+    fs = gf.FlatScene()
+    fs.materials = np.array([[0.8, 0.8, 0.8, 1, 0, 0, 0, 0, 0.0, 0.9, 0, 0]], dtype=np.float32)
+    meshes, verts, inds, nv, ni = [], [], [], 0, 0
+    for tris, t in zip(tri_sets, transforms):
+        tris = np.asarray(tris, dtype=np.float32).reshape(-1, 3, 3)
+        v = np.zeros((tris.shape[0] * 3, 16), dtype=np.float32)
+        v[:, 0:3] = tris.reshape(-1, 3)
+        v[:, 3] = 1
+        v[:, 4:8] = 1
+        v[:, 8:12] = [0, 1, 0, 1]
+        idx = np.arange(v.shape[0], dtype=np.uint32)
+        t = np.asarray(t, dtype=np.float32).reshape(4, 4)
+        meshes.append(scene.Mesh("m%d" % len(meshes), v, idx, t.reshape(16), [scene.PrimitiveSection(0, 0, v.shape[0], 0, idx.shape[0], 0)]))
+        fs.instances.append(dict(mesh=len(meshes) - 1, transform=t, first_vertex=nv, n_vertices=v.shape[0], first_index=ni,
+                                 n_indices=idx.shape[0], material=0))
+        verts.append(v)
+        inds.append(idx)
+        nv += v.shape[0]
+        ni += idx.shape[0]
+    fs.vertices = np.concatenate(verts)
+    fs.indices = np.concatenate(inds)
+    return meshes, fs
+
+
+def test_two_level_edge_cases(sol, ctx):
+    """single-triangle BLASes (their own root kernel), a two-triangle BLAS, mirrored / scaled instances, an empty scene:
+    two-level == flattened == oracle; a singular instance transform is skipped cleanly."""
+    from helpers import trs
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray
+
+    rng = np.random.default_rng(5)
+    one = [[[0, 0, 0], [1, 0, 0], [0, 1, 0]]]
+    quad = [[[0, 0, 0], [1, 0, 0], [1, 1, 0]], [[0, 0, 0], [1, 1, 0], [0, 1, 0]]]
+    blob = rng.uniform(-0.5, 0.5, size=(40, 3, 3))
+    cases = {
+        "single triangle": ([one], [trs((0, 0, 0))]),
+        "two single-triangle BLASes": ([one, one], [trs((0, 0, 0)), trs((0.2, 0.1, 1.0), (0, 0, 1), 0.5)]),
+        "mixed": ([one, quad, blob, one], [trs((0, 0, 0)), trs((0, 0, -1), (1, 0, 0), 0.3, (2, 2, 2)), trs((0.3, 0.2, 2.0)),
+                                           trs((-0.4, 0, 0.5), (0, 1, 0), 1.0, (-1, 1, 1))]),
+    }
+    n = 50_000
+    o = rng.uniform(-1.5, 1.5, size=(n, 3)) + [0, 0, -4]
+    d = np.concatenate([rng.uniform(-0.4, 0.4, size=(n, 2)), np.ones((n, 1))], axis=1)
+    rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+    for name, (tri_sets, xf) in cases.items():
+        meshes, fs = _tiny_scene(tri_sets, xf)
+        osc = oracle.Scene(fs)
+        o_hits, _, flags = osc.trace_rays(rays, classify=True)
+        for mode in (N.ACCEL_TWO_LEVEL, N.ACCEL_FLAT):
+            sd = ray.SceneDescription.from_meshes(ctx, meshes, [m.transform for m in meshes], fs.materials, accel_mode=mode)
+            hits, _ = sd.trace_rays(rays)
+            bad = np.any(hits[:, :2] != o_hits[:, :2], axis=1) & (flags == 0)
+            assert bad.sum() == 0, "%s, mode %d: %d unlisted mismatches" % (name, mode, bad.sum())
+            info = sd.accel_info()
+            assert info.n_instances == len(meshes) and info.mode == mode
+        assert (o_hits[:, 0] != oracle.MISS).sum() > 100, name
+    # an instance squashed flat by a singular transform cannot be entered in object space (no inverse): the two-level walk
+    # skips it instead of producing NaNs; the other instance is unaffected
+    meshes, fs = _tiny_scene([blob, quad], [trs((0, 0, 0.5), (0, 0, 1), 0.0, (1, 1, 0)), trs((0, 0, -0.5))])
+    sd = ray.SceneDescription.from_meshes(ctx, meshes, [m.transform for m in meshes], fs.materials, accel_mode=N.ACCEL_TWO_LEVEL)
+    hits, t = sd.trace_rays(rays)
+    assert np.all(hits[:, 0] != 0) and (hits[:, 0] == 1).sum() > 100 and np.all(np.isfinite(t))
+    empty = ray.SceneDescription.from_meshes(ctx, [], [], np.zeros((0, 12), np.float32), accel_mode=N.ACCEL_TWO_LEVEL)
+    hits, _ = empty.trace_rays(rays[:100])
+    assert np.all(hits[:, 0] == N.MISS) and empty.accel_info().n_instances == 0
+    empty.tlas_regenerate()
