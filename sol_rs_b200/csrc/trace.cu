@@ -379,11 +379,20 @@ constexpr uint32_t WF_BATCH = 128;
 #endif
 // TL: two-level scenes.  A lane is either in the TLAS (its "triangle" groups are instance leaves: the triangle step
 // enters the instance) or inside a BLAS; the sentinel popped at the end of a BLAS walk reloads the world-space ray.
-template <bool STATS, bool TL>
+// COOP (experimental, SOLB_COOP_TRI=1, flattened scenes): instead of a triangle step in which every lane tests ONE of its own
+// pending triangles, the warp pools ALL pending triangle tests of its rays and deals them out to all 32 lanes (a lane fetches
+// the owner's ray by shuffle), then every owner takes the nearest of its results.  One such step empties every lane's
+// triangle group, so the rays that were waiting for a triangle step return to the node phase together: in a replay of the
+// headline workload's rays (tools/warp_policy_sim) node steps ran 25.5 instead of 20.6 lanes wide.  The dealing (prefix
+// scan, work list, 7 shuffles, ray frame, result gather) costs ~170 instructions per round though, and the replay only wins
+// below ~40: measured 3 051 vs 3 300 Mrays/s, so it stays off (profiles/r01_sweep_coop_tri.txt).
+template <bool STATS, bool TL, bool COOP>
 __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                           const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
                                                           WavefrontState ws, int qi, unsigned long long *stats, const TraceTuning tune) {
     SOLB_DECL_STACK();
+    __shared__ uint32_t s_coop_item[COOP ? TRACE_BLOCK : 1];  // per warp: 32 (owner lane << 27 | triangle index)
+    __shared__ float s_coop_t[COOP ? TRACE_BLOCK : 1];        // per warp: hit distance of each dealt test (inf: miss)
     const uint32_t n = ws.counters[qi];
     const uint32_t *__restrict__ queue = qi ? ws.queue[1] : ws.queue[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) ws.counters[qi ^ 1] = 0;  // next wave's output queue
@@ -444,9 +453,84 @@ __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(cons
         // ---- vote: node step or triangle step ----
         const bool w_node = has_ray && (ngroup.y & 0xff000000u);
         const bool w_tri = has_ray && tgroup.y;
-        const int nn = __popc(__ballot_sync(0xffffffffu, w_node));
-        const int nt = __popc(__ballot_sync(0xffffffffu, w_tri));
-        if (nt > 0 && nt * tune.tri_weight >= nn * tune.node_weight) {
+        const uint32_t b_node = __ballot_sync(0xffffffffu, w_node), b_tri = __ballot_sync(0xffffffffu, w_tri);
+        const int nn = __popc(b_node), nt = __popc(b_tri);
+        if (COOP && !TL) {
+            if (nt > 0 && (nn == 0 || __popc(b_tri & ~b_node) >= tune.coop_block)) {
+                // ---- cooperative triangle step ----
+                uint32_t *work = s_coop_item + (threadIdx.x & ~31u);
+                float *res_t = s_coop_t + (threadIdx.x & ~31u);
+                const uint32_t mine = w_tri ? tgroup.y : 0u;
+                const int cnt = __popc(mine);
+                int incl = cnt;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, dlt);
+                    if ((int)lane >= dlt) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+                for (int base = 0; base < total; base += 32) {
+                    {   // owners publish the tests that fall into this round, nearest-first order of the serial walk
+                        uint32_t mm = mine;
+                        int k = off - base;
+                        while (mm) {
+                            const int b = 31 - __clz(mm);
+                            mm &= ~(1u << b);
+                            if (k >= 0 && k < 32) work[k] = (lane << 27) | (tgroup.x + (uint32_t)b);
+                            k++;
+                        }
+                    }
+                    __syncwarp();
+                    const int n_work = min(32, total - base);
+                    const bool worker = (int)lane < n_work;
+                    const uint32_t item = worker ? work[lane] : 0u;
+                    const int owner = (int)(item >> 27);
+                    const float3 o = f3(__shfl_sync(0xffffffffu, tr.o.x, owner), __shfl_sync(0xffffffffu, tr.o.y, owner),
+                                        __shfl_sync(0xffffffffu, tr.o.z, owner));
+                    const float3 d = f3(__shfl_sync(0xffffffffu, tr.d.x, owner), __shfl_sync(0xffffffffu, tr.d.y, owner),
+                                        __shfl_sync(0xffffffffu, tr.d.z, owner));
+                    const float o_tmax = __shfl_sync(0xffffffffu, tmax, owner);
+                    float t = 3.4e38f, u = 0.0f, v = 0.0f;
+                    uint32_t h_inst = SOLB_MISS, h_gtri = SOLB_MISS;
+                    if (worker) {
+                        const float4 *tp = tris + (size_t)(item & 0x07ffffffu) * 3;
+                        const float4 v0 = SOLB_LDG4(tp + 0), v1 = SOLB_LDG4(tp + 1), v2 = SOLB_LDG4(tp + 2);
+                        const RayFrame fr = make_ray_frame(d);
+                        float tt, uu, vv;
+                        if (intersect_tri(o, d, fr, xyz(v0), xyz(v1), xyz(v2), fc.tmin, o_tmax, tt, uu, vv)) {
+                            t = tt; u = uu; v = vv;
+                            h_inst = __float_as_uint(v0.w); h_gtri = __float_as_uint(v2.w);
+                        }
+                        if (STATS) ctr.tris++;
+                    }
+                    res_t[lane] = t;
+                    __syncwarp();
+                    // owners: the nearest of their tests in this round (first wins ties, like the serial walk)
+                    int best = -1;
+                    float best_t = tmax;
+                    {
+                        const int lo = max(off - base, 0), hi = min(off - base + cnt, 32);
+                        for (int k = lo; k < hi; k++) {
+                            const float tk = res_t[k];
+                            if (tk < best_t) { best_t = tk; best = k; }
+                        }
+                    }
+                    const int src = best >= 0 ? best : (int)lane;
+                    const float bu = __shfl_sync(0xffffffffu, u, src), bv = __shfl_sync(0xffffffffu, v, src);
+                    const uint32_t bi = __shfl_sync(0xffffffffu, h_inst, src), bg = __shfl_sync(0xffffffffu, h_gtri, src);
+                    if (best >= 0) {
+                        tmax = best_t;
+                        hit.t = best_t; hit.u = bu; hit.v = bv; hit.inst = bi; hit.gtri = bg;
+                    }
+                    __syncwarp();
+                }
+                if (w_tri) tgroup.y = 0u;
+            } else if (w_node) {
+                if (tgroup.y) stack.push(tgroup);  // postpone the pending triangles
+                trav_node_step(nodes, tr, tmax, ngroup, tgroup, stack);
+                if (STATS) ctr.nodes++;
+            }
+        } else if (nt > 0 && nt * tune.tri_weight >= nn * tune.node_weight) {
             if (w_tri) {
                 if (TL && !in_blas) {
                     trav_enter_instance(inst_leaves, tr.o, tr.d, tr, ngroup, tgroup, cur_inst, stack);
@@ -983,14 +1067,17 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
             }
             if (as.two_level) {
                 const float4 *il = as.inst_leaves_f4();
-                if (collect) k_wf_trace<true, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
-                else k_wf_trace<false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
+                if (collect) k_wf_trace<true, true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
+                else k_wf_trace<false, true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
             } else if (tune.pool && L.spill[k]) {
                 const int pool_grid = L.sm_count * tune.pool_ctas_per_sm;
                 if (collect) k_wf_trace_pool<true><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
                 else k_wf_trace_pool<false><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
-            } else if (collect) k_wf_trace<true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
-            else k_wf_trace<false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+            } else if (tune.coop_tri && as.n_tris < (1u << 27)) {  // the dealt item packs the triangle index into 27 bits
+                if (collect) k_wf_trace<true, false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+                else k_wf_trace<false, false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+            } else if (collect) k_wf_trace<true, false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+            else k_wf_trace<false, false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
             if (events) {
                 cudaEventRecord((*events)[*n_events_used + 1], st);
                 *n_events_used += 2;

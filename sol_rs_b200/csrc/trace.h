@@ -29,6 +29,11 @@ struct TraceTuning {
     int overlap = 3;       // frame parts (1..4) run as independent wave sequences on their own streams, so the drain tail of one
                            // part's persistent trace kernel and its memory-bound shade kernel overlap another part's traversal
     int ctas_per_sm_overlap = 5;  // persistent CTAs per SM and part when overlapping
+    int coop_tri = 0;      // 1: cooperative triangle step of k_wf_trace (flattened scenes) instead of every lane testing its own
+                           // triangles.  Measured slower (3 051 vs 3 300 Mrays/s): dealing the tests out costs ~170 instructions per
+                           // round on top of the ~180 of the test, the policy replay only pays off below ~40
+                           // (profiles/r01_sweep_coop_tri.txt).  Off by default.
+    int coop_block = 8;    // ... taken once this many lanes hold only triangle work (or no lane has node work)
     int shade_ctas_per_sm_overlap = 2;  // grid-stride shade CTAs (256 threads) per SM and part when overlapping
     int sort_shade = 0;        // 1: material-sorted shading (block-level counting sort of the shade queue by hit class)
     int pool = 0;              // 1: ray-pool traversal kernel (k_wf_trace_pool) instead of the lane-bound k_wf_trace
