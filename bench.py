@@ -263,9 +263,34 @@ def main():
     value = rays_total / (ms_total * 1e-3) / 1e6
     ms_per_step = ms_total / steps
 
+    # ---- e2e (every rank): the call a user makes, host buffers, H2D of the step's inputs + D2H of the rendered frame each
+    #      step; whole-job value = rays of all ranks / the slowest rank's wall clock ----
+    e2e_accum = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA32F)
+    e2e_render = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA8)
+    host_frame = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True).numpy()
+    for f in range(2):
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), e2e_accum, e2e_render, schedule=sched,
+                                             samples_per_frame=SPP, max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
+    ctx.reset_stats()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_e2e = min(steps, 8)
+    for f in multigpu.frames_for_rank(rank, world, world * n_e2e, first=200):
+        u = scene.scene_uniforms(cam, WIDTH, HEIGHT, f)  # host-side camera -> 400-byte uniform block (the step's input)
+        sd.tlas_regenerate()
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, u, e2e_accum, e2e_render, schedule=sched, samples_per_frame=SPP,
+                                             max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
+        e2e_render.readback(host_frame)  # replaces blit-to-present: the step's result reaches host memory
+    dt_e2e = time.perf_counter() - t0
+    e2e_ms, e2e_rays = gather_max_sum(1e3 * dt_e2e, int(ctx.stats().rays))
+    e2e = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 400 + 32,
+           "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": e2e_ms / n_e2e, "steps": n_e2e}
+    del e2e_accum, e2e_render
+
     # ---- roofline of the dominant kernel: instrumented pass for nodes/triangles per ray + per-launch event timing ----
     roofline = None
-    e2e = None
     cpu_baseline = None
     extra = {}
     if rank == 0:
@@ -309,28 +334,6 @@ def main():
                     "kernel_share_of_step": st2.trace_kernel_ms_total / max(sum(main_run["step_ms"][:3]), 1e-9) if steps >= 3 else None,
                     "note": "algorithmic bytes are served mostly from L1/L2 (BVH + triangles = %.1f MB): frac can exceed what DRAM counters show" % (
                         (sd.accel_info().n_wide_nodes * 80 + sd.accel_info().n_triangles * 48) / 1e6)}
-
-        # ---- e2e: the call a user makes, host buffers, H2D of the step's inputs + D2H of the rendered frame each step ----
-        render = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA8)
-        host_frame = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True).numpy()
-        accum.clear()
-        for f in range(2):
-            sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), accum, render, schedule=sched,
-                                                 samples_per_frame=SPP, max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
-        ctx.reset_stats()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_e2e = min(steps, 8)
-        for f in range(n_e2e):
-            u = scene.scene_uniforms(cam, WIDTH, HEIGHT, 200 + f)  # host-side camera -> 400-byte uniform block (the step's input)
-            sd.tlas_regenerate()
-            sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, render, schedule=sched, samples_per_frame=SPP,
-                                                 max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
-            render.readback(host_frame)  # replaces blit-to-present: the step's result reaches host memory
-        dt = time.perf_counter() - t0
-        st3 = ctx.stats()
-        e2e = {"value": st3.rays / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 400 + 32,
-               "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": 1e3 * dt / n_e2e, "steps": n_e2e}
 
         if world == 1 and args.workload == "tunnel" and not args.size:
             # the metric names cornell beside tunnel: same resolution / spp / bounce cap, default (auto) schedule
