@@ -138,6 +138,9 @@ def main():
     ap.add_argument("--workload", default="tunnel", choices=["tunnel", "synth"],
                     help="tunnel = the headline config; synth = BASELINE configs[4]: synthetic instanced scene (--blas x 20000 triangles)")
     ap.add_argument("--blas", type=int, default=1000)
+    ap.add_argument("--split", default="frames", choices=["frames", "tiles"],
+                    help="multi-GPU split: frames = rank r renders frames f = r (mod N), one NCCL reduce at the end (default); tiles = "
+                         "every frame is cut into N row tiles, one all-gather of the accumulation rows per frame (single-sample mode)")
     ap.add_argument("--accel", default="flat", choices=["flat", "two_level"],
                     help="flat = transforms baked into one hierarchy (default); two_level = TLAS over object-space BLASes")
     ap.add_argument("--size", default="", help="WxH override, e.g. 3840x2160 for BASELINE configs[3] (default 1920x1080)")
@@ -198,6 +201,9 @@ def main():
         """K steps with inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between steps."""
         accum = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA32F)
         render = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA8)
+        tiled = dist is not None and args.split == "tiles"
+        if tiled:
+            return device_timed_tiles(sd, cam, sbt, schedule, n_warm, n_steps, frame0, accum, render)
         frames = multigpu.frames_for_rank(rank, world, world * (n_warm + n_steps), first=frame0)  # f = r (mod R): SURVEY 8e
         for f in frames[:n_warm]:
             sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), accum, render, schedule=schedule,
@@ -237,6 +243,44 @@ def main():
         st = ctx.stats()
         return {"ms_total": sum(step_ms) + reduce_ms, "step_ms": step_ms, "reduce_ms": reduce_ms, "rays": int(st.rays),
                 "paths": int(st.paths), "hits": int(st.hits), "launches": int(st.kernel_launches), "wall_s": wall}
+
+    def device_timed_tiles(sd, cam, sbt, schedule, n_warm, n_steps, frame0, accum, render):
+        """Tile split (single-sample interactive mode): every rank traces rows [r H/N, (r+1) H/N) of EVERY frame into
+        the full-size targets, then one all-gather of the accumulation rows makes the frame whole on every rank."""
+        assert HEIGHT % world == 0, "tile split needs HEIGHT divisible by the number of ranks"
+        rows = HEIGHT // world
+        full = accum.as_torch()
+        mine = full[rank * rows:(rank + 1) * rows]
+        parts = [full[r * rows:(r + 1) * rows] for r in range(world)]  # gather straight into the accumulation image
+
+        def one(f):
+            u = scene.scene_uniforms(cam, WIDTH, HEIGHT, f)
+            sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, render, schedule=schedule, samples_per_frame=SPP, max_bounces=MAX_BOUNCES,
+                                                 tile_rows=(rank * rows, rows)), (WIDTH, HEIGHT, 1))
+            dist.all_gather(parts, mine)
+
+        for f in range(frame0, frame0 + n_warm):
+            one(f)
+        accum.clear()
+        ctx.reset_stats()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        t_wall = time.perf_counter()
+        for i in range(n_steps):
+            l2_flush.fill_(i & 0xFF)
+            evs[i][0].record(stream)
+            one(frame0 + n_warm + i)
+            evs[i][1].record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t_wall
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        st = ctx.stats()
+        return {"ms_total": sum(step_ms), "step_ms": step_ms, "reduce_ms": 0.0, "rays": int(st.rays), "paths": int(st.paths),
+                "hits": int(st.hits), "launches": int(st.kernel_launches), "wall_s": wall}
 
     def gather_max_sum(ms_total, rays):
         if not dist:
@@ -360,13 +404,16 @@ def main():
             cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
+        tiled = world > 1 and args.split == "tiles"
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "schedule": "megakernel" if sched else "wavefront", "accel": args.accel, "bvh_build_ms": build_ms,
-                           "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * world),
+                           "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * (1 if tiled else world)),
                            "l2": "256 MB buffer written between timed steps (outside the per-step event pairs)",
-                           "multi_gpu": "frames f = rank (mod N) per rank, local sums, one NCCL reduce + resolve inside the timed region"
+                           "multi_gpu": ("every frame cut into N row tiles, one NCCL all-gather of the accumulation rows per frame inside the timed region"
+                                         if tiled else
+                                         "frames f = rank (mod N) per rank, local sums, one NCCL reduce + resolve inside the timed region")
                            if world > 1 else "single GPU"},
                 "ms_per_frame": ms_per_step, "reduce_ms": main_run["reduce_ms"],
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": main_run["launches"],

@@ -129,6 +129,10 @@ typedef struct SolbTraceParams {
     uint32_t schedule;          /* SolbSchedule                                        */
     uint32_t accum_mode;        /* SolbAccumMode                                       */
     uint32_t collect_stats;     /* 1: instrumented kernels count nodes / triangles per ray */
+    uint32_t tile_row_begin;    /* tile split of ONE frame across GPUs: trace only image rows               */
+    uint32_t tile_row_count;    /* [tile_row_begin, tile_row_begin + tile_row_count) of the full-size targets; 0 = all.
+                                   Seeds, pixel coordinates and addresses stay those of the full image, so the union of
+                                   the tiles is bit-identical to the undivided frame.                                     */
     uint32_t _pad;
 } SolbTraceParams;
 

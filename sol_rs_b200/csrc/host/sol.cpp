@@ -314,6 +314,8 @@ void ShaderBindingTable::cmd_trace_rays(const TraceBindings &b, Extent3D extent)
     if (b.overrides.schedule) p.schedule = b.overrides.schedule;  // 0 keeps the default (AUTO)
     p.accum_mode = b.overrides.accum_mode;
     p.collect_stats = b.overrides.collect_stats;
+    p.tile_row_begin = b.overrides.tile_row_begin;
+    p.tile_row_count = b.overrides.tile_row_count;
     solb_scene *s = b.scene_description->handle();
     switch (kind_) {
         case PipelineKind::PATHTRACE:

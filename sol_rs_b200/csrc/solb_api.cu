@@ -668,7 +668,19 @@ static void fill_frame_consts(FrameConsts &fc, const SolbSceneUniforms *u, uint3
     // gl_LaunchSizeEXT = the extent passed to cmd_trace_rays = the target size (src/ray/sbt.rs:175-177)
     fc.width = w;
     fc.height = h;
+    fc.row_begin = 0;
+    fc.row_end = h;
     fc.frame = u->frame[2];
+}
+
+// SolbTraceParams::tile_row_begin / tile_row_count -> FrameConsts rows (0 rows = the whole image)
+static int apply_tile(solb_ctx *ctx, FrameConsts &fc, const SolbTraceParams *p) {
+    if (p->tile_row_count == 0 && p->tile_row_begin == 0) return SOLB_OK;
+    if (p->tile_row_count == 0 || (uint64_t)p->tile_row_begin + p->tile_row_count > fc.height)
+        return fail(ctx, SOLB_ERR_INVALID, "tile rows outside the target");
+    fc.row_begin = p->tile_row_begin;
+    fc.row_end = p->tile_row_begin + p->tile_row_count;
+    return SOLB_OK;
 }
 
 static int check_trace_args(solb_scene *s, const SolbSceneUniforms *u) {
@@ -746,6 +758,7 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
     fc.spp = params->samples_per_frame;
     fc.max_bounces = params->max_bounces;
     fc.accum_mode = params->accum_mode;
+    if ((rc = apply_tile(ctx, fc, params))) return rc;
     TraceTimer timer(ctx);
     uint32_t n_ev = 0;
     uint32_t schedule = params->schedule;
@@ -817,6 +830,7 @@ SOLB_API int solb_trace_ao(solb_scene *s, const SolbSceneUniforms *u, const Solb
     fc.accum_start = params->accum_start_frame;
     fc.spp = params->samples_per_frame;
     fc.max_bounces = params->max_bounces;
+    if ((rc = apply_tile(ctx, fc, params))) return rc;
     TraceTimer timer(ctx);
     CU(ctx, launch_ao(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->d_blue, ctx->blue_w, ctx->blue_h, (float4 *)image->dev,
                       ctx->d_stats));

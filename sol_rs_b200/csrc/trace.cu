@@ -57,16 +57,19 @@ __device__ __forceinline__ void warp_add_stat(unsigned long long *stats, int slo
 }
 
 // pixel owned by this thread: each warp covers an 8x4 tile so primary rays stay coherent
-__device__ __forceinline__ bool thread_pixel(uint32_t width, uint32_t height, uint32_t &x, uint32_t &y) {
-    const uint32_t tiles_x = (width + 7u) >> 3;
+// The launch covers image rows [fc.row_begin, fc.row_end) (the whole image, or one rank's tile of a tile-split frame,
+// SURVEY 8e): pixel coordinates, RNG seeds and target addresses are always those of the full image.
+__device__ __forceinline__ bool thread_pixel(const FrameConsts &fc, uint32_t &x, uint32_t &y) {
+    const uint32_t tiles_x = (fc.width + 7u) >> 3;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     const uint32_t ty = gwarp / tiles_x, tx = gwarp - ty * tiles_x;
     x = tx * 8u + (lane & 7u);
-    y = ty * 4u + (lane >> 3);
-    return x < width && y < height;
+    y = fc.row_begin + ty * 4u + (lane >> 3);
+    return x < fc.width && y < fc.row_end;
 }
-static uint32_t pixel_grid_blocks(uint32_t width, uint32_t height) {
-    const uint64_t warps = (uint64_t)((width + 7u) >> 3) * ((height + 3u) >> 2);
+static uint32_t region_tiles_y(const FrameConsts &fc) { return (fc.row_end - fc.row_begin + 3u) >> 2; }
+static uint32_t pixel_grid_blocks(const FrameConsts &fc) {
+    const uint64_t warps = (uint64_t)((fc.width + 7u) >> 3) * region_tiles_y(fc);
     return (uint32_t)((warps * 32u + TRACE_BLOCK - 1) / TRACE_BLOCK);
 }
 
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, con
                                                        uint32_t *render, uint2 *ids, float4 *attribs, unsigned long long *stats) {
     SOLB_DECL_STACK();
     uint32_t x, y;
-    const bool active = thread_pixel(fc.width, fc.height, x, y);
+    const bool active = thread_pixel(fc, x, y);
     uint32_t nr = 0, nh = 0;
     if (active) {
         Ray r;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConst
                                                                 uint32_t *render, unsigned long long *stats) {
     SOLB_DECL_STACK();
     uint32_t x, y;
-    const bool active = thread_pixel(fc.width, fc.height, x, y);
+    const bool active = thread_pixel(fc, x, y);
     uint32_t nr = 0, nh = 0, np = 0;
     TraceCounters ctr = { 0, 0 };
     if (active) {
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConst
     }
 }
 
-__device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, uint32_t width, uint32_t height, bool &valid);
+__device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, const FrameConsts &fc, bool &valid);
 
 // Persistent variant of the megakernel (experimental, SOLB_MEGA_PERSISTENT=1): a lane that finishes its pixel's samples
 // resolves it and takes the next pixel from a global counter (8x4-tile order, warp-aggregated batches), so a warp no longer
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega_persistent(const
                 const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
                 if (!has_pixel && rank >= served && rank < served + take) {
                     bool valid;
-                    const uint32_t p = swizzled_pixel(pool_next + (rank - served), fc.width, fc.height, valid);
+                    const uint32_t p = swizzled_pixel(pool_next + (rank - served), fc, valid);
                     if (valid) {  // image edges leave holes in the tile order
                         x = p % fc.width; y = p / fc.width;
                         rng = tea(p, fc.frame);  // pathtrace.rgen:47
@@ -331,13 +334,14 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega_persistent(const
 // Per-pixel path state lives in SoA float4/uint4 arrays (WavefrontState); the RNG state flows from sample to
 // sample inside a pixel exactly like prd.rng does in pathtrace.rgen:47-86.
 
-__device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, uint32_t width, uint32_t height, bool &valid) {
-    // queue slot i -> pixel, in 8x4 tiles (same order as thread_pixel)
+__device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, const FrameConsts &fc, bool &valid) {
+    // queue slot i -> pixel of the launch region, in 8x4 tiles (same order as thread_pixel)
+    const uint32_t width = fc.width;
     const uint32_t tiles_x = (width + 7u) >> 3;
     const uint32_t w = i >> 5, lane = i & 31u;
     const uint32_t ty = w / tiles_x, tx = w - ty * tiles_x;
-    const uint32_t x = tx * 8u + (lane & 7u), y = ty * 4u + (lane >> 3);
-    valid = x < width && y < height;
+    const uint32_t x = tx * 8u + (lane & 7u), y = fc.row_begin + ty * 4u + (lane >> 3);
+    valid = x < width && y < fc.row_end;
     return y * width + x;
 }
 
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, Wavef
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     uint32_t p = 0;
-    if (i < n_slots) p = swizzled_pixel(slot_begin + i, fc.width, fc.height, valid);
+    if (i < n_slots) p = swizzled_pixel(slot_begin + i, fc, valid);
     if (valid) {
         const uint32_t x = p % fc.width, y = p / fc.width;
         uint32_t rng = tea(p, fc.frame);
@@ -865,7 +869,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_ao(const FrameConsts fc, const 
                                                     uint32_t blue_w, uint32_t blue_h, float4 *image, unsigned long long *stats) {
     SOLB_DECL_STACK();
     uint32_t x, y;
-    const bool active = thread_pixel(fc.width, fc.height, x, y);
+    const bool active = thread_pixel(fc, x, y);
     uint32_t nr = 0, nh = 0, np = 0;
     if (active) {
         const uint32_t max_samples = fc.max_bounces;  // ao.rgen:42 (4)
@@ -956,7 +960,7 @@ cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &s
 
 cudaError_t launch_debug(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, uint32_t *render, uint2 *ids,
                          float4 *attribs, unsigned long long *stats) {
-    const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
+    const uint32_t blocks = pixel_grid_blocks(fc);
     if (as.two_level) k_debug<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), render, ids, attribs, stats);
     else k_debug<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, render, ids, attribs, stats);
     return cudaGetLastError();
@@ -974,10 +978,10 @@ cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const flo
 cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                                   const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
                                   bool collect, uint32_t *pixel_counter, int sm_count, const TraceTuning &tune) {
-    const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
+    const uint32_t blocks = pixel_grid_blocks(fc);
     const float4 *il = as.inst_leaves_f4();
     if (pixel_counter && tune.mega_persistent) {
-        const uint32_t n_slots = ((fc.width + 7u) >> 3) * ((fc.height + 3u) >> 2) * 32u;
+        const uint32_t n_slots = ((fc.width + 7u) >> 3) * region_tiles_y(fc) * 32u;
         const uint32_t grid = std::min<uint32_t>(blocks, (uint32_t)(sm_count * tune.mega_ctas_per_sm));
         cudaError_t err = cudaMemsetAsync(pixel_counter, 0, sizeof(uint32_t), st);
         if (err != cudaSuccess) return err;
@@ -1000,7 +1004,7 @@ cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const 
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
                       unsigned long long *stats) {
-    const uint32_t blocks = pixel_grid_blocks(fc.width, fc.height);
+    const uint32_t blocks = pixel_grid_blocks(fc);
     if (as.two_level) k_ao<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), instances, shade, blue, bw, bh, image, stats);
     else k_ao<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, instances, shade, blue, bw, bh, image, stats);
     return cudaGetLastError();
@@ -1021,10 +1025,10 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
                                        const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
                                        unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
                                        uint32_t *n_events_used, const TraceTuning &tune) {
-    const uint32_t n_pixels = fc.width * fc.height;
+    const uint32_t n_pixels = fc.width * (fc.row_end - fc.row_begin);
     if (n_pixels == 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
-    const uint32_t tiles_x = (fc.width + 7u) >> 3, tiles_y = (fc.height + 3u) >> 2;
+    const uint32_t tiles_x = (fc.width + 7u) >> 3, tiles_y = region_tiles_y(fc);
     int n_lanes = (events || !L.stream[1]) ? 1 : tune.overlap;
     if (n_lanes > WF_MAX_PARTS) n_lanes = WF_MAX_PARTS;
     if ((uint32_t)n_lanes > tiles_y) n_lanes = (int)tiles_y;
@@ -1046,8 +1050,8 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
     for (int k = 0; k < n_lanes; k++) {
         const uint32_t row0 = k * rows_per_lane, row1 = (row0 + rows_per_lane < tiles_y) ? row0 + rows_per_lane : tiles_y;
         const uint32_t slot_begin = row0 * tiles_x * 32u, n_slots = (row1 - row0) * tiles_x * 32u;
-        pixel_begin[k] = row0 * 4u * fc.width;
-        pixel_end[k] = (row1 * 4u < fc.height ? row1 * 4u : fc.height) * fc.width;
+        pixel_begin[k] = (fc.row_begin + row0 * 4u) * fc.width;
+        pixel_end[k] = (fc.row_begin + row1 * 4u < fc.row_end ? fc.row_begin + row1 * 4u : fc.row_end) * fc.width;
         if ((err = cudaMemsetAsync(L.ws[k].counters, 0, 4 * sizeof(uint32_t), L.stream[k])) != cudaSuccess) return err;
         k_wf_generate<<<(n_slots + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], slot_begin, n_slots, stats);
         *launches += 1;

@@ -236,12 +236,13 @@ class TraceBindings:
 
     def __init__(self, scene_description, uniforms, accum_target=None, render_target=None, ids_target=None,
                  accumulation_start_frame=0, samples_per_frame=None, max_bounces=None, schedule=N.SCHEDULE_AUTO,
-                 accum_mode=N.ACCUM_MIX, collect_stats=False):
+                 accum_mode=N.ACCUM_MIX, collect_stats=False, tile_rows=None):
         self.scene_description, self.uniforms = scene_description, uniforms
         self.accum_target, self.render_target, self.ids_target = accum_target, render_target, ids_target
         self.accumulation_start_frame = accumulation_start_frame
         self.samples_per_frame, self.max_bounces = samples_per_frame, max_bounces
         self.schedule, self.accum_mode, self.collect_stats = schedule, accum_mode, collect_stats
+        self.tile_rows = tile_rows  # (first_row, n_rows) of the full-size targets: tile split of one frame
 
 
 class ShaderBindingTable:
@@ -270,6 +271,8 @@ class ShaderBindingTable:
         if b.max_bounces is not None:
             p.max_bounces = int(b.max_bounces)
         p.schedule, p.accum_mode, p.collect_stats = int(b.schedule), int(b.accum_mode), int(bool(b.collect_stats))
+        if b.tile_rows is not None:
+            p.tile_row_begin, p.tile_row_count = int(b.tile_rows[0]), int(b.tile_rows[1])
         s = b.scene_description.handle
         h = lambda t: t.handle if t is not None else None
         if self.pipeline.kind == PATHTRACE:

@@ -838,3 +838,44 @@ def test_two_level_edge_cases(sol, ctx):
     hits, _ = empty.trace_rays(rays[:100])
     assert np.all(hits[:, 0] == N.MISS) and empty.accel_info().n_instances == 0
     empty.tlas_regenerate()
+
+
+# ---- full-size properties (BASELINE.json sizes; too large for the oracle, checked through invariants) ------------------
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160)])
+def test_full_size_determinism_and_tile_split(sol, ctx, w, h):
+    """At the bench sizes: (1) a frame is a pure function of (scene, camera, frame index): two renders are bit-identical
+    although queue order and atomics vary; (2) tile split: rendering row tiles of the full-size target one after
+    another gives exactly the undivided frame, for ragged tile heights too; (3) ray / path counts agree."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    sc, sd = _product(sol, ctx, "tunnel")
+    cam = product_camera(sc, "tunnel", w, h)
+    sbt = pathtrace_pipeline(ctx, True)
+    u = scene.scene_uniforms(cam, w, h, 3)
+
+    def render(tiles, schedule=N.SCHEDULE_WAVEFRONT):
+        accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+        rend = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+        ctx.reset_stats()
+        for t in tiles:
+            sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, rend, accumulation_start_frame=3, max_bounces=8, schedule=schedule, tile_rows=t),
+                               (w, h, 1))
+        st = ctx.stats()
+        return accum.readback(), rend.readback(), int(st.rays), int(st.paths)
+
+    a0, r0, rays0, paths0 = render([None])
+    a1, r1, rays1, paths1 = render([None])
+    assert np.array_equal(a0, a1) and np.array_equal(r0, r1) and rays0 == rays1
+    assert paths0 == w * h * 8 and 5.5 < rays0 / paths0 < 7.0
+    third = h // 3 + 1  # ragged: not a multiple of the 4-row pixel tiles
+    tiles = [(0, third), (third, third), (2 * third, h - 2 * third)]
+    a2, r2, rays2, paths2 = render(tiles)
+    assert np.array_equal(a0, a2) and np.array_equal(r0, r2) and rays0 == rays2 and paths0 == paths2
+    if w == 1920:
+        a3, r3, rays3, _ = render(tiles[::-1], N.SCHEDULE_MEGAKERNEL)
+        a4, r4, rays4, _ = render([None], N.SCHEDULE_MEGAKERNEL)
+        assert np.array_equal(a3, a4) and np.array_equal(r3, r4) and rays3 == rays4
+    with pytest.raises(sol.SolbError):
+        render([(h - 2, 5)])
