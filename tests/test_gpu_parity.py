@@ -879,3 +879,37 @@ def test_full_size_determinism_and_tile_split(sol, ctx, w, h):
         assert np.array_equal(a3, a4) and np.array_equal(r3, r4) and rays3 == rays4
     with pytest.raises(sol.SolbError):
         render([(h - 2, 5)])
+
+
+@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("w,h,spp,mb,frame,start", [(1, 1, 8, 32, 0, 0), (3, 5, 8, 32, 0, 0), (9, 7, 1, 32, 7, 7), (37, 21, 3, 0, 2, 0),
+                                                     (64, 33, 8, 1, 0x7FFFFFF0, 0x7FFFFFF0), (130, 70, 16, 4, 1000003, 1000000)])
+def test_ragged_sizes_and_extreme_parameters(sol, ctx, w, h, spp, mb, frame, start, schedule):
+    """image sizes that do not fill the 8x4 pixel tiles, 1 x 1, one sample, bounce cap 0 (every path shades one hit then
+    stops), frame indices near 2^31 (tea seed + alpha = 1 / (frame + 1 - start) arithmetic), a late accumulation start."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    name = "cornell"
+    sc, sd = _product(sol, ctx, name)
+    cam = product_camera(sc, name, w, h)
+    fs, osc = oracle_scene(name)
+    ocamera = oracle_camera(fs, name, w, h)
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    rend = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+    sbt = pathtrace_pipeline(ctx, False)
+    ref = np.zeros((h, w, 4), np.float32)
+    st = oracle.OrcStats()
+    ctx.reset_stats()
+    for f in (frame, frame + 1):
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, rend, accumulation_start_frame=start,
+                                             samples_per_frame=spp, max_bounces=mb, schedule=schedule), (w, h, 1))
+        o_rgba, _ = osc.pathtrace_frame(ocam.scene_uniforms(ocamera, w, h, f), w, h, ref, start, False, spp, mb, st)
+    gs = ctx.stats()
+    assert gs.paths == st.paths == 2 * w * h * spp and abs(int(gs.rays) - int(st.rays)) <= max(2, 0.01 * st.rays)
+    g = accum.readback()
+    d = np.abs(g[..., :3] - ref[..., :3]).max(axis=2)
+    bad = d > 1e-3 * (1.0 + np.abs(ref[..., :3]).max(axis=2))
+    assert bad.sum() <= max(1, 0.03 * w * h), "%d of %d pixels differ" % (bad.sum(), w * h)
+    assert np.all(g[..., 3] == 1.0) and np.all(np.isfinite(g))
+    assert (np.abs(rend.readback().astype(np.int32) - o_rgba.astype(np.int32)).max(axis=2) > 1).sum() <= max(1, 0.03 * w * h)
