@@ -79,10 +79,12 @@ struct AccelStorage {
     float4 *blas_box = nullptr;        // [2 * n_blas] object-space root boxes (lo, hi)
     uint32_t tlas_cap = 0, n_blas = 0, n_tlas_wide = 0, tlas_depth = 0, blas_depth = 0;
     void *d_tlas_info = nullptr, *h_tlas_info = nullptr;  // single-CTA TLAS build: result block (device) + pinned mirror
+    void *d_tlas_dp = nullptr;                              // ... and its optimal-collapse table (32 B per binary node)
     void release() {
         if (d_tlas_info) cudaFree(d_tlas_info);
         if (h_tlas_info) cudaFreeHost(h_tlas_info);
-        d_tlas_info = h_tlas_info = nullptr;
+        if (d_tlas_dp) cudaFree(d_tlas_dp);
+        d_tlas_info = h_tlas_info = d_tlas_dp = nullptr;
         if (nodes) cudaFree(nodes);
         if (tris) cudaFree(tris);
         if (inst_leaves) cudaFree(inst_leaves);
