@@ -546,13 +546,14 @@ __global__ void __launch_bounds__(TL_BLOCK) k_bottom_up_coop(int n, BNode *bn, i
 }
 
 // bottom-up pass of the optimal-collapse dynamic program (DpEntry per binary node); same atomic-flag walk as k_bottom_up
-__global__ void k_bottom_up_dp(int n, const BNode *bn, const int *parent, const int *node_count, uint32_t *flags, DpEntry *dp) {
+__global__ void k_bottom_up_dp(int n, const BNode *bn, const int *parent, const int *node_count, uint32_t *flags, DpEntry *dp,
+                               const DpCost cost) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     {
         const BNode leaf = bn[n - 1 + j];
         DpEntry e;
-        dp_leaf_entry(e, half_area(leaf.lo, leaf.hi));
+        dp_leaf_entry(e, half_area(leaf.lo, leaf.hi), cost);
         dp[n - 1 + j] = e;
     }
     int node = parent[n - 1 + j];
@@ -564,7 +565,7 @@ __global__ void k_bottom_up_dp(int n, const BNode *bn, const int *parent, const 
         const BNode b = bn[node];
         const DpEntry l = dp[b.left], r = dp[b.right];
         DpEntry e;
-        dp_inner_entry(e, l, r, half_area(b.lo, b.hi), node_count[node]);
+        dp_inner_entry(e, l, r, half_area(b.lo, b.hi), node_count[node], cost);
         dp[node] = e;
         node = parent[node];
     }
@@ -796,7 +797,8 @@ __host__ __device__ inline size_t tlas_fast_smem_bytes(uint32_t n) {
 __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n,
                                                                         const float4 *__restrict__ blas_box, uint32_t tlas_cap,
                                                                         Node8 *wide, InstLeaf *inst_leaves, TlasFastInfo *info,
-                                                                        DpEntry *dp /* [2 n - 1] global scratch, or null: greedy collapse */) {
+                                                                        DpEntry *dp /* [2 n - 1] global scratch, or null: greedy collapse */,
+                                                                        const DpCost cost) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_bounds[6];
     __shared__ uint32_t s_counters[3];  // wide nodes, leaf slots, next queue size
@@ -916,7 +918,7 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
             {
                 const BNode &leaf = bn[ni + j];
                 DpEntry e;
-                dp_leaf_entry(e, half_area(leaf.lo, leaf.hi));
+                dp_leaf_entry(e, half_area(leaf.lo, leaf.hi), cost);
                 dp[ni + j] = e;
             }
             uint32_t node = parent[ni + j];
@@ -927,7 +929,7 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
                 const BNode b = bn[node];
                 const DpEntry l = dp[b.left], r = dp[b.right];
                 DpEntry e;
-                dp_inner_entry(e, l, r, half_area(b.lo, b.hi), count[node]);
+                dp_inner_entry(e, l, r, half_area(b.lo, b.hi), count[node], cost);
                 dp[node] = e;
                 node = parent[node];
             }
@@ -1060,7 +1062,9 @@ static cudaError_t tree_refit_optimize(cudaStream_t st, BinaryTree &T, const Bui
     if (opt.dp_collapse) {
         CK(salloc(st, &T.dp, 2 * (size_t)n - 1));
         k_clear_u32<<<nb, 256, 0, st>>>(T.flags, n);
-        k_bottom_up_dp<<<nb, 256, 0, st>>>((int)n, T.bn, T.parent, T.node_count, T.flags, T.dp);
+        DpCost cost;
+        cost.cn = opt.dp_cn; cost.cp = opt.dp_cp; cost.max_leaf = opt.dp_max_leaf;
+        k_bottom_up_dp<<<nb, 256, 0, st>>>((int)n, T.bn, T.parent, T.node_count, T.flags, T.dp, cost);
         *launches += 2;
     }
     CK(cudaGetLastError());
@@ -1221,6 +1225,13 @@ cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorag
     int tlas_passes = 2;
     if (const char *v = getenv("SOLB_TLAS_TREELET_PASSES")) tlas_passes = std::max(0, std::min(8, atoi(v)));
     if (const char *v = getenv("SOLB_TLAS_DP")) opt.dp_collapse = atoi(v) != 0;
+    // TLAS cost model: an instance entry is a whole BLAS walk, not a triangle test
+    opt.dp_cp = 8.0f;
+    opt.dp_max_leaf = 1;
+    if (const char *v = getenv("SOLB_TLAS_CP")) opt.dp_cp = (float)atof(v);
+    if (const char *v = getenv("SOLB_TLAS_MAX_LEAF")) opt.dp_max_leaf = std::max(1, std::min(SOLB_MAX_LEAF_TRIS, atoi(v)));
+    DpCost tlas_cost;
+    tlas_cost.cn = opt.dp_cn; tlas_cost.cp = opt.dp_cp; tlas_cost.max_leaf = opt.dp_max_leaf;
     if (!out.two_level || !out.nodes || n > out.tlas_cap) return cudaErrorInvalidValue;
     out.sah_lbvh = out.sah_final = 0.0f;
     if (n == 0) {
@@ -1239,7 +1250,7 @@ cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorag
         }
         k_tlas_build_small<<<1, TLAS_FAST_THREADS, tlas_fast_smem_bytes(n), st>>>(sv.instances, n, out.blas_box, out.tlas_cap, out.nodes,
                                                                                   out.inst_leaves, (TlasFastInfo *)out.d_tlas_info,
-                                                                                  opt.dp_collapse ? (DpEntry *)out.d_tlas_dp : nullptr);
+                                                                                  opt.dp_collapse ? (DpEntry *)out.d_tlas_dp : nullptr, tlas_cost);
         *launches += 1;
         CK(cudaMemcpyAsync(out.h_tlas_info, out.d_tlas_info, sizeof(TlasFastInfo), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

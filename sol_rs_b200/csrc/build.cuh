@@ -209,12 +209,20 @@ struct DpEntry {
 };
 static_assert(sizeof(DpEntry) == 32, "DpEntry must be 32 bytes");
 
-SOLB_HD void dp_leaf_entry(DpEntry &e, float area) {
-    for (int i = 0; i < 7; i++) e.c[i] = SOLB_DP_CP * area;
+// cost model of one tree: triangles (CP = 1, leaves of up to 3) or, for a TLAS, instances: entering an instance costs a whole
+// BLAS walk, so its CP is much larger and every instance gets a leaf child (and a box test) of its own
+struct DpCost {
+    float cn, cp;
+    int max_leaf;
+};
+SOLB_HD DpCost dp_cost_triangles() { DpCost c; c.cn = SOLB_DP_CN; c.cp = SOLB_DP_CP; c.max_leaf = SOLB_MAX_LEAF_TRIS; return c; }
+
+SOLB_HD void dp_leaf_entry(DpEntry &e, float area, DpCost cost = dp_cost_triangles()) {
+    for (int i = 0; i < 7; i++) e.c[i] = cost.cp * area;
     e.k = 0x80000000u;
 }
 
-SOLB_HD void dp_inner_entry(DpEntry &e, const DpEntry &l, const DpEntry &r, float area, int count) {
+SOLB_HD void dp_inner_entry(DpEntry &e, const DpEntry &l, const DpEntry &r, float area, int count, DpCost cost = dp_cost_triangles()) {
     float dist[9];
     uint32_t kbits = 0;
     for (int j = 2; j <= 8; j++) {
@@ -228,8 +236,8 @@ SOLB_HD void dp_inner_entry(DpEntry &e, const DpEntry &l, const DpEntry &r, floa
         dist[j] = best;
         kbits |= (uint32_t)bk << (3 * (j - 2));
     }
-    const float c_leaf = count <= SOLB_MAX_LEAF_TRIS ? SOLB_DP_CP * area * (float)count : 3.4e38f;
-    const float c_node = dist[8] + SOLB_DP_CN * area;
+    const float c_leaf = count <= cost.max_leaf ? cost.cp * area * (float)count : 3.4e38f;
+    const float c_node = dist[8] + cost.cn * area;
     if (c_leaf <= c_node) kbits |= 0x80000000u;
     e.c[0] = fminf(c_leaf, c_node);
     for (int i = 2; i <= 7; i++) {

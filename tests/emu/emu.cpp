@@ -53,7 +53,8 @@ struct EmuTree {
 
 static int g_emu_dp = 1;  // mirrors BuildOptions::dp_collapse
 
-static void emu_binary_tree(const std::vector<float3> &plo, const std::vector<float3> &phi, int treelet_passes, int gamma, EmuTree &T) {
+static void emu_binary_tree(const std::vector<float3> &plo, const std::vector<float3> &phi, int treelet_passes, int gamma, EmuTree &T,
+                            DpCost cost = dp_cost_triangles()) {
     const uint32_t n = (uint32_t)plo.size();
     float3 clo = f3(3.4e38f, 3.4e38f, 3.4e38f), chi = f3(-3.4e38f, -3.4e38f, -3.4e38f);
     for (uint32_t g = 0; g < n; g++) {
@@ -125,8 +126,8 @@ static void emu_binary_tree(const std::vector<float3> &plo, const std::vector<fl
         for (size_t k = bfs.size(); k-- > 0;) {
             const int node = bfs[k];
             const float a = half_area(bn[node].lo, bn[node].hi);
-            if (node >= ni) dp_leaf_entry(T.dp[node], a);
-            else dp_inner_entry(T.dp[node], T.dp[bn[node].left], T.dp[bn[node].right], a, T.count[node]);
+            if (node >= ni) dp_leaf_entry(T.dp[node], a, cost);
+            else dp_inner_entry(T.dp[node], T.dp[bn[node].left], T.dp[bn[node].right], a, T.count[node], cost);
         }
     }
 }
@@ -276,7 +277,9 @@ static int emu_rebuild_tlas(EmuScene *s, const std::vector<float3> &blo, const s
         return 0;
     }
     EmuTree T;
-    emu_binary_tree(plo, phi, 2, 7, T);
+    DpCost tlas_cost;  // build.cu rebuild_tlas: an instance entry is a whole BLAS walk, every instance gets its own leaf child
+    tlas_cost.cn = 2.0f; tlas_cost.cp = 8.0f; tlas_cost.max_leaf = 1;
+    emu_binary_tree(plo, phi, 2, 7, T, tlas_cost);
     s->sah_lbvh = T.sah_lbvh;
     s->sah_final = T.sah_final;
     std::vector<uint32_t> leaf_prim(n);
