@@ -5,6 +5,7 @@
 #include "build.cuh"
 using namespace solb;
 struct Ent { uint32_t node; float t; };
+static float g_key[8]; static int g_mode = 0;
 // decode child boxes and intersect in f32 (same conservative boxes as intersect_node)
 static int children_hit(const Node8 &n, float3 o, float3 idir, float tmin, float tmax, uint32_t *child_node, float *child_t, uint32_t *leaf_base, uint32_t *leaf_cnt, float *leaf_t, int &n_leaf) {
     const uint32_t *w = (const uint32_t *)&n;
@@ -23,13 +24,18 @@ static int children_hit(const Node8 &n, float3 o, float3 idir, float tmin, float
             t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
         }
         if (t0 > t1) continue;
-        if ((meta & 0x1f) >= 24 && (meta >> 5) == 1) { child_node[ni] = child_base + popc32(imask & ((1u << i) - 1)); child_t[ni] = t0; ni++; }
+        if ((meta & 0x1f) >= 24 && (meta >> 5) == 1) { child_node[ni] = child_base + popc32(imask & ((1u << i) - 1)); child_t[ni] = t0;
+            const float sx = idir.x < 0 ? -1.f : 1.f, sy = idir.y < 0 ? -1.f : 1.f, sz = idir.z < 0 ? -1.f : 1.f;
+            g_key[ni] = g_mode == 7 ? sx * (lo.x + hi.x) + sy * (lo.y + hi.y) + sz * (lo.z + hi.z)            // centre on the octant diagonal
+                      : g_mode == 8 ? sx * (idir.x < 0 ? hi.x : lo.x) + sy * (idir.y < 0 ? hi.y : lo.y) + sz * (idir.z < 0 ? hi.z : lo.z)  // near corner on the diagonal
+                      : 0.f;
+            ni++; }
         else { leaf_base[n_leaf] = tri_base + (meta & 0x1f); leaf_cnt[n_leaf] = (meta >> 5) == 1 ? 1 : ((meta >> 5) == 3 ? 2 : 3); leaf_t[n_leaf] = t0; n_leaf++; }
     }
     return ni;
 }
 extern "C" void order_sim(const Node8 *nodes, const float4 *tris, const float *rays, uint32_t n, int sorted, double *out) {
-    double nn = 0, nt = 0;
+    double nn = 0, nt = 0; g_mode = sorted;
     for (uint32_t r = 0; r < n; r++) {
         const float *p = rays + 8 * (size_t)r;
         const float3 o = f3(p[0], p[1], p[2]), d = f3(p[4], p[5], p[6]);
@@ -51,6 +57,7 @@ extern "C" void order_sim(const Node8 *nodes, const float4 *tris, const float *r
                 if (intersect_tri(o, d, fr, xyz(tp[0]), xyz(tp[1]), xyz(tp[2]), tmin, tmax, t, u, v)) tmax = t; } }
             int io[8]; for (int i = 0; i < ni; i++) io[i] = i;
             if (sorted == 1) std::sort(io, io + ni, [&](int a, int b) { return ct[a] > ct[b]; });   // push far first
+            if (sorted == 7 || sorted == 8) std::sort(io, io + ni, [&](int a, int b) { return g_key[a] > g_key[b]; });  // push far first
             if (sorted == 5 || sorted == 6) {  // nearest child visited first, the rest keep their slot order
                 int best = -1; for (int i = 0; i < ni; i++) if (best < 0 || ct[i] < ct[best]) best = i;
                 if (best >= 0) { int k2 = 0; int tmp[8]; for (int i = 0; i < ni; i++) if (i != best) tmp[k2++] = i; tmp[k2++] = best; for (int i = 0; i < ni; i++) io[i] = tmp[i]; }
