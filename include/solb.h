@@ -133,7 +133,8 @@ typedef struct SolbTraceParams {
     uint32_t tile_row_count;    /* [tile_row_begin, tile_row_begin + tile_row_count) of the full-size targets; 0 = all.
                                    Seeds, pixel coordinates and addresses stay those of the full image, so the union of
                                    the tiles is bit-identical to the undivided frame.                                     */
-    uint32_t _pad;
+    uint32_t tile_row_stride;   /* 0: that one band.  Otherwise the band repeats every tile_row_stride rows down to the
+                                   bottom of the image (interleaved tiles balance uneven images across ranks).            */
 } SolbTraceParams;
 
 typedef struct SolbStats {

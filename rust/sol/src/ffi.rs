@@ -31,7 +31,7 @@ pub struct SolbMeshDesc { pub vertices: *const SolbModelVertex, pub n_vertices: 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct SolbTraceParams { pub accum_start_frame: i32, pub enable_sky: u32, pub samples_per_frame: u32, pub max_bounces: u32,
                              pub schedule: u32, pub accum_mode: u32, pub collect_stats: u32,
-                             pub tile_row_begin: u32, pub tile_row_count: u32, pub _pad: u32 }
+                             pub tile_row_begin: u32, pub tile_row_count: u32, pub tile_row_stride: u32 }
 
 pub const SOLB_FORMAT_RGBA32F: u32 = 0;
 pub const SOLB_FORMAT_RGBA8: u32 = 1;

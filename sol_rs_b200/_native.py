@@ -56,7 +56,7 @@ class TraceParams(ctypes.Structure):
     _fields_ = [("accum_start_frame", ctypes.c_int32), ("enable_sky", ctypes.c_uint32), ("samples_per_frame", ctypes.c_uint32),
                 ("max_bounces", ctypes.c_uint32), ("schedule", ctypes.c_uint32), ("accum_mode", ctypes.c_uint32),
                 ("collect_stats", ctypes.c_uint32), ("tile_row_begin", ctypes.c_uint32), ("tile_row_count", ctypes.c_uint32),
-                ("_pad", ctypes.c_uint32)]
+                ("tile_row_stride", ctypes.c_uint32)]
 
 
 class Stats(ctypes.Structure):

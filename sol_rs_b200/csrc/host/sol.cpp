@@ -316,6 +316,7 @@ void ShaderBindingTable::cmd_trace_rays(const TraceBindings &b, Extent3D extent)
     p.collect_stats = b.overrides.collect_stats;
     p.tile_row_begin = b.overrides.tile_row_begin;
     p.tile_row_count = b.overrides.tile_row_count;
+    p.tile_row_stride = b.overrides.tile_row_stride;
     solb_scene *s = b.scene_description->handle();
     switch (kind_) {
         case PipelineKind::PATHTRACE:

@@ -669,17 +669,24 @@ static void fill_frame_consts(FrameConsts &fc, const SolbSceneUniforms *u, uint3
     fc.width = w;
     fc.height = h;
     fc.row_begin = 0;
-    fc.row_end = h;
+    fc.band_rows = h;
+    fc.band_stride = 0;
+    fc.n_bands = 1;
     fc.frame = u->frame[2];
 }
 
 // SolbTraceParams::tile_row_begin / tile_row_count -> FrameConsts rows (0 rows = the whole image)
 static int apply_tile(solb_ctx *ctx, FrameConsts &fc, const SolbTraceParams *p) {
-    if (p->tile_row_count == 0 && p->tile_row_begin == 0) return SOLB_OK;
-    if (p->tile_row_count == 0 || (uint64_t)p->tile_row_begin + p->tile_row_count > fc.height)
+    if (p->tile_row_count == 0 && p->tile_row_begin == 0 && p->tile_row_stride == 0) return SOLB_OK;
+    if (p->tile_row_count == 0 || p->tile_row_begin >= fc.height ||
+        (p->tile_row_stride == 0 && (uint64_t)p->tile_row_begin + p->tile_row_count > fc.height))
         return fail(ctx, SOLB_ERR_INVALID, "tile rows outside the target");
+    if (p->tile_row_stride != 0 && p->tile_row_stride < p->tile_row_count)
+        return fail(ctx, SOLB_ERR_INVALID, "tile_row_stride smaller than tile_row_count: bands would overlap");
     fc.row_begin = p->tile_row_begin;
-    fc.row_end = p->tile_row_begin + p->tile_row_count;
+    fc.band_rows = p->tile_row_count;
+    fc.band_stride = p->tile_row_stride;
+    fc.n_bands = p->tile_row_stride ? (fc.height - p->tile_row_begin + p->tile_row_stride - 1) / p->tile_row_stride : 1u;
     return SOLB_OK;
 }
 

@@ -58,7 +58,9 @@ struct FrameConsts {
     float3 origin;        // view_inverse * (0,0,0,1), identical for every pixel (pathtrace.rgen:55)
     float tmin, tmax;     // preparePayload: max(1, |origin|) * 1e-3, 1e4 (pathtrace.rgen:35)
     uint32_t width, height, frame;
-    uint32_t row_begin, row_end;  // image rows this launch covers (tile split); whole image: 0, height
+    // image rows this launch covers (tile split): n_bands bands of band_rows rows, band k starting at row
+    // row_begin + k * band_stride, clipped to the image.  Whole image: one band of `height` rows at 0.
+    uint32_t row_begin, band_rows, band_stride, n_bands;
     int32_t accum_start;
     uint32_t enable_sky, spp, max_bounces, accum_mode;
 };

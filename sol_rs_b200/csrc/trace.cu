@@ -57,17 +57,24 @@ __device__ __forceinline__ void warp_add_stat(unsigned long long *stats, int slo
 }
 
 // pixel owned by this thread: each warp covers an 8x4 tile so primary rays stay coherent
-// The launch covers image rows [fc.row_begin, fc.row_end) (the whole image, or one rank's tile of a tile-split frame,
-// SURVEY 8e): pixel coordinates, RNG seeds and target addresses are always those of the full image.
+// The launch covers fc.n_bands bands of image rows (the whole image, or one rank's share of a tile-split frame):
+// pixel coordinates, RNG seeds and target addresses are always those of the full image.  Region-local 8x4 pixel tile
+// (tx, ty) + lane -> pixel.
+__host__ __device__ __forceinline__ uint32_t tiles_per_band(const FrameConsts &fc) { return (fc.band_rows + 3u) >> 2; }
+__device__ __forceinline__ bool region_pixel(const FrameConsts &fc, uint32_t tx, uint32_t ty, uint32_t lane, uint32_t &x, uint32_t &y) {
+    const uint32_t tpb = tiles_per_band(fc);
+    const uint32_t band = ty / tpb, row_in_band = (ty - band * tpb) * 4u + (lane >> 3);
+    x = tx * 8u + (lane & 7u);
+    y = fc.row_begin + band * fc.band_stride + row_in_band;
+    return x < fc.width && band < fc.n_bands && row_in_band < fc.band_rows && y < fc.height;
+}
 __device__ __forceinline__ bool thread_pixel(const FrameConsts &fc, uint32_t &x, uint32_t &y) {
     const uint32_t tiles_x = (fc.width + 7u) >> 3;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     const uint32_t ty = gwarp / tiles_x, tx = gwarp - ty * tiles_x;
-    x = tx * 8u + (lane & 7u);
-    y = fc.row_begin + ty * 4u + (lane >> 3);
-    return x < fc.width && y < fc.row_end;
+    return region_pixel(fc, tx, ty, lane, x, y);
 }
-static uint32_t region_tiles_y(const FrameConsts &fc) { return (fc.row_end - fc.row_begin + 3u) >> 2; }
+static uint32_t region_tiles_y(const FrameConsts &fc) { return tiles_per_band(fc) * fc.n_bands; }
 static uint32_t pixel_grid_blocks(const FrameConsts &fc) {
     const uint64_t warps = (uint64_t)((fc.width + 7u) >> 3) * region_tiles_y(fc);
     return (uint32_t)((warps * 32u + TRACE_BLOCK - 1) / TRACE_BLOCK);
@@ -340,8 +347,8 @@ __device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, const FrameConsts
     const uint32_t tiles_x = (width + 7u) >> 3;
     const uint32_t w = i >> 5, lane = i & 31u;
     const uint32_t ty = w / tiles_x, tx = w - ty * tiles_x;
-    const uint32_t x = tx * 8u + (lane & 7u), y = fc.row_begin + ty * 4u + (lane >> 3);
-    valid = x < width && y < fc.row_end;
+    uint32_t x, y;
+    valid = region_pixel(fc, tx, ty, lane, x, y);
     return y * width + x;
 }
 
@@ -849,9 +856,12 @@ __global__ void __launch_bounds__(256) k_wf_shade(const FrameConsts fc, const De
 }
 
 __global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, WavefrontState ws, float4 *accum, uint32_t *render,
-                                                    uint32_t pixel_begin, uint32_t pixel_end) {
-    const uint32_t p = pixel_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pixel_end) return;
+                                                    uint32_t slot_begin, uint32_t n_slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    bool valid;
+    const uint32_t p = swizzled_pixel(slot_begin + i, fc, valid);
+    if (!valid) return;
     const float4 x4 = ws.pix[p];
     uint32_t rgba;
     const float4 out = resolve_pixel(fc, f3(x4.x, x4.y, x4.z), accum[p], rgba);
@@ -1025,8 +1035,7 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
                                        const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
                                        unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
                                        uint32_t *n_events_used, const TraceTuning &tune) {
-    const uint32_t n_pixels = fc.width * (fc.row_end - fc.row_begin);
-    if (n_pixels == 0) return cudaSuccess;
+    if (fc.width == 0 || fc.band_rows == 0 || fc.n_bands == 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
     const uint32_t tiles_x = (fc.width + 7u) >> 3, tiles_y = region_tiles_y(fc);
     int n_lanes = (events || !L.stream[1]) ? 1 : tune.overlap;
@@ -1039,7 +1048,7 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
     // every pixel needs at least spp rays; at most spp * (max_bounces + 2)
     const uint32_t max_waves = fc.spp * (fc.max_bounces + 2u);
     const uint32_t check_every = (uint32_t)tune.check_every;
-    uint32_t pixel_begin[WF_MAX_PARTS], pixel_end[WF_MAX_PARTS];
+    uint32_t part_slot_begin[WF_MAX_PARTS], part_slots[WF_MAX_PARTS];
     bool live[WF_MAX_PARTS] = { false, false, false, false };
     int qi[WF_MAX_PARTS] = { 0, 0, 0, 0 };
     if (n_lanes > 1) {  // fork: the extra streams start after everything already queued on the ctx stream
@@ -1050,8 +1059,8 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
     for (int k = 0; k < n_lanes; k++) {
         const uint32_t row0 = k * rows_per_lane, row1 = (row0 + rows_per_lane < tiles_y) ? row0 + rows_per_lane : tiles_y;
         const uint32_t slot_begin = row0 * tiles_x * 32u, n_slots = (row1 - row0) * tiles_x * 32u;
-        pixel_begin[k] = (fc.row_begin + row0 * 4u) * fc.width;
-        pixel_end[k] = (fc.row_begin + row1 * 4u < fc.row_end ? fc.row_begin + row1 * 4u : fc.row_end) * fc.width;
+        part_slot_begin[k] = slot_begin;
+        part_slots[k] = n_slots;
         if ((err = cudaMemsetAsync(L.ws[k].counters, 0, 4 * sizeof(uint32_t), L.stream[k])) != cudaSuccess) return err;
         k_wf_generate<<<(n_slots + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], slot_begin, n_slots, stats);
         *launches += 1;
@@ -1104,7 +1113,7 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
         }
     }
     for (int k = 0; k < n_lanes; k++) {
-        k_wf_resolve<<<(pixel_end[k] - pixel_begin[k] + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], accum, render, pixel_begin[k], pixel_end[k]);
+        k_wf_resolve<<<(part_slots[k] + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], accum, render, part_slot_begin[k], part_slots[k]);
         *launches += 1;
     }
     for (int k = 1; k < n_lanes; k++) {  // join

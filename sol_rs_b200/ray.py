@@ -271,8 +271,9 @@ class ShaderBindingTable:
         if b.max_bounces is not None:
             p.max_bounces = int(b.max_bounces)
         p.schedule, p.accum_mode, p.collect_stats = int(b.schedule), int(b.accum_mode), int(bool(b.collect_stats))
-        if b.tile_rows is not None:
+        if b.tile_rows is not None:  # (first_row, rows_per_band[, band_stride])
             p.tile_row_begin, p.tile_row_count = int(b.tile_rows[0]), int(b.tile_rows[1])
+            p.tile_row_stride = int(b.tile_rows[2]) if len(b.tile_rows) > 2 else 0
         s = b.scene_description.handle
         h = lambda t: t.handle if t is not None else None
         if self.pipeline.kind == PATHTRACE:

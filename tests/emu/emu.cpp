@@ -376,7 +376,7 @@ static void fill_fc(FrameConsts &fc, const float *uniforms, uint32_t w, uint32_t
     fc.origin = f3(fc.view_inv[12], fc.view_inv[13], fc.view_inv[14]);
     fc.tmin = fmaxf(1.0f, length(fc.origin)) * 1e-3f;
     fc.tmax = 10000.0f;
-    fc.width = w; fc.height = h; fc.row_begin = 0; fc.row_end = h;
+    fc.width = w; fc.height = h; fc.row_begin = 0; fc.band_rows = h; fc.band_stride = 0; fc.n_bands = 1;
     fc.frame = ((const uint32_t *)uniforms)[98];
 }
 

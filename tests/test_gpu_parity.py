@@ -873,12 +873,20 @@ def test_full_size_determinism_and_tile_split(sol, ctx, w, h):
     tiles = [(0, third), (third, third), (2 * third, h - 2 * third)]
     a2, r2, rays2, paths2 = render(tiles)
     assert np.array_equal(a0, a2) and np.array_equal(r0, r2) and rays0 == rays2 and paths0 == paths2
+    # interleaved bands (tile_row_stride): 3 "ranks" x 4-row bands, and ragged 6-row bands that straddle the 8x4 pixel tiles
+    for band in (4, 6):
+        a5, r5, rays5, paths5 = render([(r * band, band, 3 * band) for r in range(3)])
+        assert np.array_equal(a0, a5) and np.array_equal(r0, r5) and rays0 == rays5 and paths0 == paths5
     if w == 1920:
+        a6, r6, rays6, _ = render([(r * 8, 8, 16) for r in (1, 0)], N.SCHEDULE_MEGAKERNEL)
         a3, r3, rays3, _ = render(tiles[::-1], N.SCHEDULE_MEGAKERNEL)
+        assert np.array_equal(a3, a6) and rays3 == rays6
         a4, r4, rays4, _ = render([None], N.SCHEDULE_MEGAKERNEL)
         assert np.array_equal(a3, a4) and np.array_equal(r3, r4) and rays3 == rays4
     with pytest.raises(sol.SolbError):
         render([(h - 2, 5)])
+    with pytest.raises(sol.SolbError):
+        render([(0, 8, 4)])  # bands would overlap
 
 
 @pytest.mark.parametrize("schedule", [0, 1])
