@@ -164,6 +164,8 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.pool_ctas_per_sm = env_int("SOLB_POOL_CTAS_PER_SM", c->tune.pool_ctas_per_sm, 1, 6);
         c->tune.pool_refill = env_int("SOLB_POOL_REFILL", c->tune.pool_refill, 1, 64);
         c->tune.ctas_per_sm_overlap = env_int("SOLB_CTAS_PER_SM_OVERLAP", c->tune.ctas_per_sm_overlap, 1, 16);
+        c->tune.min_batch = env_int("SOLB_WF_MIN_BATCH", c->tune.min_batch, 32, 128) & ~31;
+        c->tune.min_pixels_per_part = env_int("SOLB_MIN_PIXELS_PER_PART", c->tune.min_pixels_per_part, 1, 1 << 30);
         c->tune.coop_tri = env_int("SOLB_COOP_TRI", c->tune.coop_tri, 0, 1);
         c->tune.coop_block = env_int("SOLB_COOP_BLOCK", c->tune.coop_block, 1, 32);
         c->tune.shade_ctas_per_sm_overlap = env_int("SOLB_SHADE_CTAS", c->tune.shade_ctas_per_sm_overlap, 1, 16);

@@ -382,7 +382,9 @@ __global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, Wavef
 // test one triangle), so the two phases never serialise inside an iteration; triangle groups a lane cannot
 // serve yet are postponed on its stack (after Ylitie et al. 2017).  Lanes whose ray has terminated are
 // refilled from the queue as soon as WF_FETCH_IDLE lanes are idle (dynamic fetch, Aila & Laine 2009); the
-// warp takes rays from the global queue in batches of WF_BATCH to keep the single atomic counter cold.
+// warp takes rays from the global queue in batches of up to WF_BATCH to keep the single atomic counter cold; short queues
+// (late waves, small images, one rank's share of a tile-split frame) use smaller batches so every resident warp gets rays:
+// with a fixed 128 a 86 K-ray wave kept 675 of 2 960 warps busy, four rays deep (tools/tile_time.py).
 constexpr uint32_t WF_BATCH = 128;
 
 #ifndef SOLB_WF_MIN_CTAS
@@ -433,12 +435,14 @@ __global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(cons
             uint32_t served = 0;  // idle lanes (in rank order) already given a slot
             while (served < want && !exhausted) {
                 if (pool_next >= pool_end) {
+                    // recomputed here rather than kept live across the traversal loop
+                    const uint32_t batch = min(WF_BATCH, max((uint32_t)tune.min_batch, (n / (gridDim.x * (TRACE_BLOCK / 32)) + 31u) & ~31u));
                     uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&ws.counters[2], WF_BATCH);
+                    if (lane == 0) base = atomicAdd(&ws.counters[2], batch);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (base >= n) { exhausted = true; break; }
                     pool_next = base;
-                    pool_end = min(base + WF_BATCH, n);
+                    pool_end = min(base + batch, n);
                 }
                 const uint32_t take = min(want - served, pool_end - pool_next);
                 const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
@@ -1040,6 +1044,11 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
     const uint32_t tiles_x = (fc.width + 7u) >> 3, tiles_y = region_tiles_y(fc);
     int n_lanes = (events || !L.stream[1]) ? 1 : tune.overlap;
     if (n_lanes > WF_MAX_PARTS) n_lanes = WF_MAX_PARTS;
+    {   // small launches (a rank's share of a tile-split frame, small images): a part needs enough rays to fill its persistent grid
+        const uint64_t region_pixels = (uint64_t)fc.width * fc.band_rows * fc.n_bands;
+        const int by_size = (int)(region_pixels / (uint64_t)tune.min_pixels_per_part);
+        if (n_lanes > 1 && by_size < n_lanes) n_lanes = by_size < 1 ? 1 : by_size;
+    }
     if ((uint32_t)n_lanes > tiles_y) n_lanes = (int)tiles_y;
     if (n_lanes < 1) n_lanes = 1;
     const uint32_t rows_per_lane = (tiles_y + n_lanes - 1) / n_lanes;

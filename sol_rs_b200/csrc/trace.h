@@ -25,10 +25,12 @@ struct TraceTuning {
     int tri_weight = 1;    // triangle step wins the vote when n_tri * tri_weight >= n_node * node_weight
     int node_weight = 1;
     int ctas_per_sm = 8;   // persistent grid = SMs x this
+    int min_batch = 32;    // smallest ray batch a warp takes from the queue (short queues: rays / resident warps, rounded to 32)
     int check_every = 8;   // host polls the survivor count every this many waves
     int overlap = 3;       // frame parts (1..4) run as independent wave sequences on their own streams, so the drain tail of one
                            // part's persistent trace kernel and its memory-bound shade kernel overlap another part's traversal
     int ctas_per_sm_overlap = 5;  // persistent CTAs per SM and part when overlapping
+    int min_pixels_per_part = 1;  // fewer parts when a part would hold fewer pixels than this (1: always `overlap` parts)
     int coop_tri = 0;      // 1: cooperative triangle step of k_wf_trace (flattened scenes) instead of every lane testing its own
                            // triangles.  Measured slower (3 051 vs 3 300 Mrays/s): dealing the tests out costs ~170 instructions per
                            // round on top of the ~180 of the test, the policy replay only pays off below ~40
