@@ -170,6 +170,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.coop_block = env_int("SOLB_COOP_BLOCK", c->tune.coop_block, 1, 32);
         c->tune.shade_ctas_per_sm_overlap = env_int("SOLB_SHADE_CTAS", c->tune.shade_ctas_per_sm_overlap, 1, 16);
         c->tune.mega_persistent = env_int("SOLB_MEGA_PERSISTENT", c->tune.mega_persistent, 0, 1);
+        c->tune.mega_vote = env_int("SOLB_MEGA_VOTE", c->tune.mega_vote, -1, 1);
         c->tune.mega_ctas_per_sm = env_int("SOLB_MEGA_CTAS_PER_SM", c->tune.mega_ctas_per_sm, 1, 16);
         c->tune.mega_fetch_idle = env_int("SOLB_MEGA_FETCH_IDLE", c->tune.mega_fetch_idle, 1, 32);
     }
@@ -842,7 +843,7 @@ SOLB_API int solb_trace_ao(solb_scene *s, const SolbSceneUniforms *u, const Solb
     if ((rc = apply_tile(ctx, fc, params))) return rc;
     TraceTimer timer(ctx);
     CU(ctx, launch_ao(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->d_blue, ctx->blue_w, ctx->blue_h, (float4 *)image->dev,
-                      ctx->d_stats));
+                      ctx->d_stats, ctx->tune));
     ctx->launches += 1;
     timer.stop();
     return SOLB_OK;
@@ -864,7 +865,7 @@ SOLB_API int solb_trace_debug(solb_scene *s, const SolbSceneUniforms *u, solb_ta
     fill_frame_consts(fc, u, first->width, first->height);
     TraceTimer timer(ctx);
     CU(ctx, launch_debug(ctx->stream, fc, s->accel, render ? (uint32_t *)render->dev : nullptr, ids ? (uint2 *)ids->dev : nullptr,
-                         attribs ? (float4 *)attribs->dev : nullptr, ctx->d_stats));
+                         attribs ? (float4 *)attribs->dev : nullptr, ctx->d_stats, ctx->tune));
     ctx->launches += 1;
     timer.stop();
     return SOLB_OK;
@@ -891,7 +892,7 @@ SOLB_API int solb_trace_rays(solb_scene *s, const float *rays, uint32_t n, uint3
     fr.c = d_t;
     CU(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
     TraceTimer timer(ctx);
-    CU(ctx, launch_trace_rays(ctx->stream, s->accel, d_rays, n, d_hits, d_t, ctx->d_stats));
+    CU(ctx, launch_trace_rays(ctx->stream, s->accel, d_rays, n, d_hits, d_t, ctx->d_stats, ctx->tune));
     ctx->launches += 1;
     timer.stop();
     CU(ctx, cudaMemcpyAsync(hits, d_hits, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));

@@ -48,6 +48,57 @@ __device__ __forceinline__ void trace_any(const uint4 *__restrict__ nodes, const
     else trace_closest<STATS>(nodes, tris, ray, hit, stack, ctr);
 }
 
+// Warp-voted closest hit for the one-pixel-per-lane kernels (megakernel, AO, debug).  trace_closest lets every lane run its
+// own node-step / triangle-loop sequence, so the warp executes the union of all lanes' sequences: in the megakernel's first
+// profile the triangle loop ran 3.7 lanes wide and the node step 10.7 (profiles/r01_ncu_k_pathtrace_mega_b.txt).  Here the
+// whole warp steps together like k_wf_trace does: every iteration a ballot picks the step more lanes are waiting for, lanes
+// waiting for the other kind postpone (node step: pending triangles go on the stack), and lanes whose ray is finished idle
+// until the last one is.  Must be called by all 32 lanes of the warp (has_ray = false for lanes without a ray).  Visiting order
+// per ray differs from trace_closest only in WHEN postponed triangle groups are tested, not in which.
+template <bool STATS, bool TL, class Stack>
+__device__ __forceinline__ void trace_vote(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
+                                           const float4 *__restrict__ inst_leaves, const Ray &ray, bool has_ray, Hit &hit,
+                                           Stack &stack, TraceCounters *ctr) {
+    hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS;
+    hit.t = ray.tmax; hit.u = 0.0f; hit.v = 0.0f;
+    TravRay tr = make_trav_ray(ray.o, ray.d, ray.tmin);
+    float tmax = ray.tmax;
+    uint2 ngroup = has_ray ? SOLB_ROOT_GROUP : make_uint2(0u, 0u);
+    uint2 tgroup = make_uint2(0u, 0u);
+    bool in_blas = false;           // TL only
+    uint32_t cur_inst = SOLB_MISS;  // TL only
+    stack.sp = 0;
+    for (;;) {
+        const bool w_node = (ngroup.y & 0xff000000u) != 0u, w_tri = tgroup.y != 0u;
+        const uint32_t b_node = __ballot_sync(0xffffffffu, w_node), b_tri = __ballot_sync(0xffffffffu, w_tri);
+        // (a lane that has just popped a TLAS sentinel holds nothing but may still have entries on its stack)
+        if ((b_node | b_tri) == 0u && !__any_sync(0xffffffffu, !stack.empty())) break;
+        if (b_tri != 0u && __popc(b_tri) >= __popc(b_node)) {
+            if (w_tri) {
+                if (TL && !in_blas) {
+                    trav_enter_instance(inst_leaves, ray.o, ray.d, tr, ngroup, tgroup, cur_inst, stack);
+                    in_blas = true;
+                } else {
+                    if (trav_tri_step(tris, tr, tmax, tgroup, hit) && TL) hit.inst = cur_inst;
+                    if (STATS) ctr->tris++;
+                }
+            }
+        } else if (w_node) {
+            if (tgroup.y) stack.push(tgroup);  // postpone the pending triangles
+            trav_node_step(nodes, tr, tmax, ngroup, tgroup, stack);
+            if (STATS) ctr->nodes++;
+        }
+        if (!(ngroup.y & 0xff000000u) && !tgroup.y && !stack.empty()) {
+            const uint2 e = stack.pop();
+            if (TL && e.y == 0u) {  // sentinel: back to the TLAS with the world-space ray
+                tr = make_trav_ray(ray.o, ray.d, ray.tmin);
+                in_blas = false;
+            } else if (e.y & 0xff000000u) ngroup = e;
+            else tgroup = e;
+        }
+    }
+}
+
 // stats slots (unsigned long long each)
 enum { ST_RAYS = 0, ST_HITS = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4 };
 
@@ -82,7 +133,7 @@ static uint32_t pixel_grid_blocks(const FrameConsts &fc) {
 
 // ---------------------------------------------------------------------------------------------------
 // 3-ray-debug: debug.rgen:18-37 + debug.rchit:9-13 + debug.rmiss:6-9, plus the ids the parity gate needs
-template <bool TL>
+template <bool TL, bool VOTE>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                        const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
                                                        uint32_t *render, uint2 *ids, float4 *attribs, unsigned long long *stats) {
@@ -90,14 +141,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, con
     uint32_t x, y;
     const bool active = thread_pixel(fc, x, y);
     uint32_t nr = 0, nh = 0;
+    Ray r;
+    r.o = fc.origin;
+    r.d = active ? primary_dir(fc, (float)x + 0.5f, (float)y + 0.5f) : f3(0, 0, 1);  // debug.rgen:20
+    r.tmin = 0.001f;                                                                 // debug.rgen:32-33
+    r.tmax = 1000.0f;
+    Hit h;
+    if (VOTE) trace_vote<false, TL>(nodes, tris, inst_leaves, r, active, h, stack, (TraceCounters *)nullptr);
+    else if (active) trace_any<false, TL>(nodes, tris, inst_leaves, r, h, stack, (TraceCounters *)nullptr);
     if (active) {
-        Ray r;
-        r.o = fc.origin;
-        r.d = primary_dir(fc, (float)x + 0.5f, (float)y + 0.5f);  // debug.rgen:20
-        r.tmin = 0.001f;                                          // debug.rgen:32-33
-        r.tmax = 1000.0f;
-        Hit h;
-        trace_any<false, TL>(nodes, tris, inst_leaves, r, h, stack, (TraceCounters *)nullptr);
         nr = 1;
         float3 hv = r.d;  // debug.rgen:28: payload preset to the direction, the miss shader leaves it
         if (h.inst != SOLB_MISS) { hv = f3(1.0f - h.u - h.v, h.u, h.v); nh = 1; }  // debug.rchit:11-12
@@ -111,7 +163,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_debug(const FrameConsts fc, con
 }
 
 // traceRayEXT for arbitrary rays (tests)
-template <bool TL>
+template <bool TL, bool VOTE>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
                                                             const float4 *__restrict__ inst_leaves, const float4 *__restrict__ rays,
                                                             uint32_t n, uint4 *hits, float *t_out, unsigned long long *stats) {
@@ -119,13 +171,17 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restr
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     TraceCounters ctr = { 0, 0 };
     uint32_t nr = 0;
+    Ray r;
+    r.o = f3(0, 0, 0); r.d = f3(0, 0, 1); r.tmin = 0.0f; r.tmax = 0.0f;
     if (i < n) {
         const float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
-        Ray r;
         r.o = f3(a.x, a.y, a.z); r.tmin = a.w;
         r.d = f3(b.x, b.y, b.z); r.tmax = b.w;
-        Hit h;
-        trace_any<true, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);
+    }
+    Hit h;
+    if (VOTE) trace_vote<true, TL>(nodes, tris, inst_leaves, r, i < n, h, stack, &ctr);
+    else if (i < n) trace_any<true, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);
+    if (i < n) {
         hits[i] = make_uint4(h.inst, h.prim, __float_as_uint(h.u), __float_as_uint(h.v));
         if (t_out) t_out[i] = h.inst != SOLB_MISS ? h.t : 0.0f;
         nr = 1;
@@ -138,7 +194,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restr
 // ---------------------------------------------------------------------------------------------------
 // 5-pathtrace, megakernel schedule: pathtrace.rgen:39-104 with the sample and bounce loops flattened
 // into one loop so a lane that ends a path immediately starts its next sample.
-template <bool STATS, bool TL>
+template <bool STATS, bool TL, bool VOTE>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                                 const float4 *__restrict__ tris,
                                                                 const float4 *__restrict__ inst_leaves,
@@ -150,24 +206,29 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConst
     const bool active = thread_pixel(fc, x, y);
     uint32_t nr = 0, nh = 0, np = 0;
     TraceCounters ctr = { 0, 0 };
-    if (active) {
-        uint32_t rng = tea(x + y * fc.width, fc.frame);  // :47
-        float3 pixel = f3(0, 0, 0);
-        uint32_t sample = 0, depth = 0;
-        float3 thr = f3(1, 1, 1);
-        Ray r;
-        r.tmin = fc.tmin;  // rayRange is set once per sample and never touched by rchit (:35)
-        r.tmax = fc.tmax;
-        {
-            const float jx = next_rand(rng), jy = next_rand(rng);  // :52
-            r.o = fc.origin;
-            r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
-            np++;
-        }
-        while (sample < fc.spp) {
-            Hit h;
+    uint32_t rng = 0, sample = 0, depth = 0;
+    float3 pixel = f3(0, 0, 0), thr = f3(1, 1, 1);
+    Ray r;
+    r.o = fc.origin; r.d = f3(0, 0, 1);
+    r.tmin = fc.tmin;  // rayRange is set once per sample and never touched by rchit (:35)
+    r.tmax = fc.tmax;
+    bool live = active && fc.spp > 0u;
+    if (live) {
+        rng = tea(x + y * fc.width, fc.frame);                 // :47
+        const float jx = next_rand(rng), jy = next_rand(rng);  // :52
+        r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+        np++;
+    }
+    // VOTE: the whole warp stays in the loop until its last pixel is done, so the traversal can step warp-wide
+    while (VOTE ? __any_sync(0xffffffffu, live) : live) {
+        Hit h;
+        if (VOTE) {
+            trace_vote<STATS, TL>(nodes, tris, inst_leaves, r, live, h, stack, &ctr);  // :65-76
+        } else {
             stack.sp = 0;
-            trace_any<STATS, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);  // :65-76
+            trace_any<STATS, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);
+        }
+        if (live) {
             nr++;
             bool end_path;
             if (h.inst != SOLB_MISS) {
@@ -195,9 +256,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConst
                     thr = f3(1, 1, 1);
                     depth = 0;
                     np++;
+                } else {
+                    live = false;
                 }
             }
         }
+    }
+    if (active) {
         const size_t p = (size_t)y * fc.width + x;
         uint32_t rgba;
         const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
@@ -220,7 +285,7 @@ __device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, const FrameConsts
 // waits for its longest pixel (the per-pixel ray count varies 8..72 on the shipped scenes).  Per-pixel arithmetic and RNG
 // streams are unchanged.  Measured 5 % slower than one thread per pixel (TraceTuning::mega_persistent): kept for comparison.
 constexpr uint32_t MEGA_BATCH = 64;
-template <bool STATS, bool TL>
+template <bool STATS, bool TL, bool VOTE>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega_persistent(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                                            const float4 *__restrict__ tris,
                                                                            const float4 *__restrict__ inst_leaves,
@@ -279,10 +344,14 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega_persistent(const
             if (exhausted) break;
             continue;  // every slot of this round was an edge hole: fetch again
         }
-        if (has_pixel) {
-            Hit h;
+        Hit h;
+        if (VOTE) {
+            trace_vote<STATS, TL>(nodes, tris, inst_leaves, r, has_pixel, h, stack, &ctr);  // :65-76
+        } else if (has_pixel) {
             stack.sp = 0;
-            trace_any<STATS, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);  // :65-76
+            trace_any<STATS, TL>(nodes, tris, inst_leaves, r, h, stack, &ctr);
+        }
+        if (has_pixel) {
             nr++;
             bool end_path;
             if (h.inst != SOLB_MISS) {
@@ -875,7 +944,9 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, Wavefr
 
 // ---------------------------------------------------------------------------------------------------
 // 4-ray-ao: ao.rgen:37-83 + ao.rchit:45-88 + ao.rmiss:7-10, one thread per pixel
-template <bool TL>
+// The sample loop (ao.rgen:47-75) and the chained-ray loop (ao.rgen:56-72) are flattened into one loop so that, with VOTE, the
+// whole warp can step its traversals together (trace_vote); per-pixel arithmetic and RNG order are those of the nested loops.
+template <bool TL, bool VOTE>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_ao(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                     const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
                                                     const DeviceInstance *__restrict__ instances,
@@ -885,37 +956,60 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_ao(const FrameConsts fc, const 
     uint32_t x, y;
     const bool active = thread_pixel(fc, x, y);
     uint32_t nr = 0, nh = 0, np = 0;
-    if (active) {
-        const uint32_t max_samples = fc.max_bounces;  // ao.rgen:42 (4)
-        const uint32_t sample_count = fc.spp;         // ao.rgen:43 (4)
-        uint32_t rng = tea(x + y * fc.width, fc.frame);  // ao.rgen:45
-        float3 ao = f3(0, 0, 0);
-        for (uint32_t s = 0; s < sample_count; s++) {
-            const float jx = next_rand(rng), jy = next_rand(rng);  // ao.rgen:49
-            Ray r;
-            r.o = fc.origin;
-            r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
-            r.tmin = fc.tmin;  // preparePayload, ao.rgen:33
-            r.tmax = fc.tmax;
-            float3 hit_value = f3(0, 0, 0);
-            uint32_t depth = 0;
-            np++;
-            for (;;) {
-                Hit h;
-                stack.sp = 0;
-                trace_any<false, TL>(nodes, tris, inst_leaves, r, h, stack, (TraceCounters *)nullptr);
-                nr++;
-                if (h.inst == SOLB_MISS) break;  // ao.rmiss: done = 1
+    const uint32_t max_samples = fc.max_bounces;  // ao.rgen:42 (4)
+    const uint32_t sample_count = fc.spp;         // ao.rgen:43 (4)
+    uint32_t rng = 0, s = 0, depth = 0;
+    float3 ao = f3(0, 0, 0), hit_value = f3(0, 0, 0);
+    Ray r;
+    r.o = fc.origin; r.d = f3(0, 0, 1);
+    r.tmin = fc.tmin;  // preparePayload, ao.rgen:33
+    r.tmax = fc.tmax;
+    bool live = active && sample_count > 0u;
+    if (live) {
+        rng = tea(x + y * fc.width, fc.frame);                 // ao.rgen:45
+        const float jx = next_rand(rng), jy = next_rand(rng);  // ao.rgen:49
+        r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+        np++;
+    }
+    while (VOTE ? __any_sync(0xffffffffu, live) : live) {
+        Hit h;
+        if (VOTE) {
+            trace_vote<false, TL>(nodes, tris, inst_leaves, r, live, h, stack, (TraceCounters *)nullptr);
+        } else {
+            stack.sp = 0;
+            trace_any<false, TL>(nodes, tris, inst_leaves, r, h, stack, (TraceCounters *)nullptr);
+        }
+        if (live) {
+            nr++;
+            bool end_sample = true;  // ao.rmiss: done = 1
+            if (h.inst != SOLB_MISS) {
                 nh++;
                 ao_hit(instances, shade, h.inst, h.gtri, h.u, h.v, x, y, blue, blue_w, blue_h, depth, s, r.o, r.d, rng);
                 r.tmin = 0.001f;  // ao.rchit:83
                 r.tmax = 10.0f;
                 if (depth > 0) hit_value = hit_value + f3(1, 1, 1);  // ao.rchit:84-86
                 depth++;
-                if (depth > max_samples) break;  // ao.rgen:71
+                end_sample = depth > max_samples;  // ao.rgen:71
             }
-            ao = ao + hit_value * (1.0f / (float)max_samples);  // ao.rgen:74
+            if (end_sample) {
+                ao = ao + hit_value * (1.0f / (float)max_samples);  // ao.rgen:74
+                s++;
+                if (s < sample_count) {
+                    const float jx = next_rand(rng), jy = next_rand(rng);  // ao.rgen:49
+                    r.o = fc.origin;
+                    r.d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                    r.tmin = fc.tmin;
+                    r.tmax = fc.tmax;
+                    hit_value = f3(0, 0, 0);
+                    depth = 0;
+                    np++;
+                } else {
+                    live = false;
+                }
+            }
         }
+    }
+    if (active) {
         float3 color = f3(1.0f - ao.x / (float)sample_count, 1.0f - ao.y / (float)sample_count, 1.0f - ao.z / (float)sample_count);
         const size_t p = (size_t)y * fc.width + x;
         const float a = 1.0f / (float)(uint32_t)(fc.frame - (uint32_t)fc.accum_start + 1u);  // ao.rgen:78
@@ -928,7 +1022,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_ao(const FrameConsts fc, const 
     warp_add_stat(stats, ST_PATHS, np);
 }
 
-// sum / count -> accum + display (multi-GPU resolve after the reduce)
 __global__ void __launch_bounds__(256) k_resolve_sum(const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -973,19 +1066,25 @@ cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &s
 }
 
 cudaError_t launch_debug(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, uint32_t *render, uint2 *ids,
-                         float4 *attribs, unsigned long long *stats) {
+                         float4 *attribs, unsigned long long *stats, const TraceTuning &tune) {
     const uint32_t blocks = pixel_grid_blocks(fc);
-    if (as.two_level) k_debug<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), render, ids, attribs, stats);
-    else k_debug<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, render, ids, attribs, stats);
+    const bool vote = tune.mega_vote < 0 ? as.n_wide > 8u : tune.mega_vote != 0;
+#define SOLB_DBG(T, V) k_debug<T, V><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? as.inst_leaves_f4() : nullptr, render, ids, attribs, stats)
+    if (as.two_level) { if (vote) SOLB_DBG(true, true); else SOLB_DBG(true, false); }
+    else { if (vote) SOLB_DBG(false, true); else SOLB_DBG(false, false); }
+#undef SOLB_DBG
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const float4 *rays, uint32_t n, uint4 *hits, float *t_out,
-                              unsigned long long *stats) {
+                              unsigned long long *stats, const TraceTuning &tune) {
     if (n == 0) return cudaSuccess;
     const uint32_t blocks = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
-    if (as.two_level) k_trace_rays<true><<<blocks, TRACE_BLOCK, 0, st>>>(as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), rays, n, hits, t_out, stats);
-    else k_trace_rays<false><<<blocks, TRACE_BLOCK, 0, st>>>(as.nodes_u4(), as.tris_f4(), nullptr, rays, n, hits, t_out, stats);
+    const bool vote = tune.mega_vote < 0 ? as.n_wide > 8u : tune.mega_vote != 0;
+#define SOLB_TR(T, V) k_trace_rays<T, V><<<blocks, TRACE_BLOCK, 0, st>>>(as.nodes_u4(), as.tris_f4(), T ? as.inst_leaves_f4() : nullptr, rays, n, hits, t_out, stats)
+    if (as.two_level) { if (vote) SOLB_TR(true, true); else SOLB_TR(true, false); }
+    else { if (vote) SOLB_TR(false, true); else SOLB_TR(false, false); }
+#undef SOLB_TR
     return cudaGetLastError();
 }
 
@@ -994,33 +1093,38 @@ cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const 
                                   bool collect, uint32_t *pixel_counter, int sm_count, const TraceTuning &tune) {
     const uint32_t blocks = pixel_grid_blocks(fc);
     const float4 *il = as.inst_leaves_f4();
+    const bool vote = tune.mega_vote < 0 ? as.n_wide > 8u : tune.mega_vote != 0;
     if (pixel_counter && tune.mega_persistent) {
         const uint32_t n_slots = ((fc.width + 7u) >> 3) * region_tiles_y(fc) * 32u;
         const uint32_t grid = std::min<uint32_t>(blocks, (uint32_t)(sm_count * tune.mega_ctas_per_sm));
         cudaError_t err = cudaMemsetAsync(pixel_counter, 0, sizeof(uint32_t), st);
         if (err != cudaSuccess) return err;
-#define SOLB_MEGA_P(S, T) k_pathtrace_mega_persistent<S, T><<<grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, accum, render, stats, pixel_counter, n_slots, tune.mega_fetch_idle)
+#define SOLB_MEGA_PV(S, T, V) k_pathtrace_mega_persistent<S, T, V><<<grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, accum, render, stats, pixel_counter, n_slots, tune.mega_fetch_idle)
+#define SOLB_MEGA_P(S, T) do { if (vote) SOLB_MEGA_PV(S, T, true); else SOLB_MEGA_PV(S, T, false); } while (0)
         if (as.two_level) { if (collect) SOLB_MEGA_P(true, true); else SOLB_MEGA_P(false, true); }
         else { if (collect) SOLB_MEGA_P(true, false); else SOLB_MEGA_P(false, false); }
 #undef SOLB_MEGA_P
+#undef SOLB_MEGA_PV
         return cudaGetLastError();
     }
-    if (as.two_level) {
-        if (collect) k_pathtrace_mega<true, true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, instances, shade, accum, render, stats);
-        else k_pathtrace_mega<false, true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, instances, shade, accum, render, stats);
-    } else if (collect)
-        k_pathtrace_mega<true, false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, instances, shade, accum, render, stats);
-    else
-        k_pathtrace_mega<false, false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, instances, shade, accum, render, stats);
+#define SOLB_MEGA(S, T, V) k_pathtrace_mega<S, T, V><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, accum, render, stats)
+#define SOLB_MEGA_V(S, T) do { if (vote) SOLB_MEGA(S, T, true); else SOLB_MEGA(S, T, false); } while (0)
+    if (as.two_level) { if (collect) SOLB_MEGA_V(true, true); else SOLB_MEGA_V(false, true); }
+    else { if (collect) SOLB_MEGA_V(true, false); else SOLB_MEGA_V(false, false); }
+#undef SOLB_MEGA_V
+#undef SOLB_MEGA
     return cudaGetLastError();
 }
 
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
-                      unsigned long long *stats) {
+                      unsigned long long *stats, const TraceTuning &tune) {
     const uint32_t blocks = pixel_grid_blocks(fc);
-    if (as.two_level) k_ao<true><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), as.inst_leaves_f4(), instances, shade, blue, bw, bh, image, stats);
-    else k_ao<false><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, instances, shade, blue, bw, bh, image, stats);
+    const bool vote = tune.mega_vote < 0 ? as.n_wide > 8u : tune.mega_vote != 0;
+#define SOLB_AO(T, V) k_ao<T, V><<<blocks, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? as.inst_leaves_f4() : nullptr, instances, shade, blue, bw, bh, image, stats)
+    if (as.two_level) { if (vote) SOLB_AO(true, true); else SOLB_AO(true, false); }
+    else { if (vote) SOLB_AO(false, true); else SOLB_AO(false, false); }
+#undef SOLB_AO
     return cudaGetLastError();
 }
 

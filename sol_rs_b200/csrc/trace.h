@@ -45,6 +45,10 @@ struct TraceTuning {
                                // Measured slower (cornell 1080p 8 027 vs 8 459 Mrays/s, tunnel 2 236 vs 2 284): the hardware block
                                // scheduler already refills finished warps, only the intra-warp imbalance is left to win and the
                                // refill code costs more than that.  Off by default (SOLB_MEGA_PERSISTENT=1 to compare).
+    int mega_vote = -1;        // megakernel schedule: warp-voted traversal (trace_vote) instead of every lane running its own
+                               // node-step / triangle-loop sequence (trace_closest).  -1 = by hierarchy size: tunnel.gltf
+                               // 2 426 -> 3 050 Mrays/s with the vote, cornell.gltf (3 wide nodes, nothing to diverge on)
+                               // 9 001 -> 8 025 (gpurun_out/mega_vote.log), so the vote is used above 8 wide nodes
     int mega_ctas_per_sm = 6;  // its persistent CTAs per SM (80 registers -> 6 x 128 threads)
     int mega_fetch_idle = 8;   // refill finished lanes once this many are idle
 };
@@ -61,9 +65,9 @@ struct WavefrontLaunch {
 
 cudaError_t launch_build_shade_records(cudaStream_t st, const DeviceSceneView &sv, ShadeRecord *out);
 cudaError_t launch_debug(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, uint32_t *render, uint2 *ids,
-                         float4 *attribs, unsigned long long *stats);
+                         float4 *attribs, unsigned long long *stats, const TraceTuning &tune);
 cudaError_t launch_trace_rays(cudaStream_t st, const AccelStorage &as, const float4 *rays, uint32_t n, uint4 *hits, float *t_out,
-                              unsigned long long *stats);
+                              unsigned long long *stats, const TraceTuning &tune);
 cudaError_t launch_pathtrace_mega(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                                   const ShadeRecord *shade, float4 *accum, uint32_t *render, unsigned long long *stats,
                                   bool collect, uint32_t *pixel_counter, int sm_count, const TraceTuning &tune);
@@ -73,7 +77,7 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
                                        uint32_t *n_events_used, const TraceTuning &tune);
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
-                      unsigned long long *stats);
+                      unsigned long long *stats, const TraceTuning &tune);
 size_t pool_spill_bytes(int sm_count, const TraceTuning &tune);
 cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n);
 

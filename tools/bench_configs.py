@@ -56,13 +56,13 @@ def main():
         return {"ms_per_frame": ms / n, "Mrays_s": st.rays / (ms * 1e-3) / 1e6, "rays_per_frame": st.rays / n,
                 "rays_per_path": st.rays / max(st.paths, 1), "launches_per_frame": st.kernel_launches / n}
 
-    def pathtrace(sd, cam, w, h, sky, mb, frames):
+    def pathtrace(sd, cam, w, h, sky, mb, frames, schedule=N.SCHEDULE_AUTO):
         cam.set_window_size((w, h))
         accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
         render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
         sbt = pt_sbt(sky)
         return timed_frames(lambda f: sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, render,
-                                                                            max_bounces=mb), (w, h, 1)), frames)
+                                                                            max_bounces=mb, schedule=schedule), (w, h, 1)), frames)
 
     for what in args.what:
         if what == "ao":
@@ -110,6 +110,16 @@ def main():
             print(json.dumps({"config": "5-pathtrace tunnel.gltf --sky 1920x1080, 512 frames = 4096 spp, cap 8 (configs[2] in full)",
                               "seconds": dt, "ms_per_frame": 1e3 * dt / 512, "Mrays_s": st.rays / dt / 1e6, "rays": int(st.rays),
                               "mean_rgb": [float(v) for v in accum.readback()[..., :3].mean(axis=(0, 1))]}), flush=True)
+        elif what in ("mega_cornell", "mega_tunnel", "wf_cornell"):
+            # 1080p cap 8 with the schedule forced (SOLB_MEGA_VOTE / SOLB_MEGA_PERSISTENT select the megakernel variant)
+            name = what.split("_")[1]
+            sc = scene.load_scene(ctx, os.path.join(ROOT, "assets/models/%s.gltf" % name))
+            sd = ray.SceneDescription.from_scene(ctx, sc)
+            sched = N.SCHEDULE_WAVEFRONT if what.startswith("wf") else N.SCHEDULE_MEGAKERNEL
+            r = pathtrace(sd, sc.camera, 1920, 1080, name == "tunnel", 8, args.frames, sched)
+            print(json.dumps({"config": "5-pathtrace %s.gltf 1920x1080 cap 8, %s, SOLB_MEGA_VOTE=%s SOLB_MEGA_PERSISTENT=%s" % (
+                name, "wavefront" if what.startswith("wf") else "megakernel", os.environ.get("SOLB_MEGA_VOTE", "default"),
+                os.environ.get("SOLB_MEGA_PERSISTENT", "default")), **r}), flush=True)
         elif what == "cornell512":
             sc = scene.load_scene(ctx, os.path.join(ROOT, "assets/models/cornell.gltf"))
             sd = ray.SceneDescription.from_scene(ctx, sc)
