@@ -132,14 +132,26 @@ SOLB_HD bool intersect_tri(float3 o, float3 d, const RayFrame &fr, float3 p0, fl
 // ---- node test: returns hit mask (bits 31..24 internal children in traversal priority order,
 //      bits 23..0 triangles of the hit leaf children) -------------------------------------------------
 // Dequantisation without I2F (quarter-rate XU pipe; it was the top pipe of the first traversal kernel,
-// profiles/r01_ncu_k_wf_trace_a.txt) and without a separate subtraction: one PRMT drops byte j of w into
-// mantissa bits [15:8] of the float 32768.0, giving m = 32768 + q exactly; the 32768 is folded into the
-// per-node offset, t = m * a + (b - 32768 a).  Folding costs at most |a| / 512 of rounding (a = one
-// quantisation cell in units of t), which the near / far offsets below absorb conservatively.
+// profiles/r01_ncu_k_wf_trace_a.txt) and without a separate subtraction: byte j of w is dropped into the mantissa of the
+// float 32768.0, giving m = 32768 + s q exactly; the 32768 is folded into the per-node offset, t = m * a + (b - 32768 a).
+// Folding costs at most |a| / 512 of rounding (a = one quantisation cell in units of t), which the near / far offsets below
+// absorb conservatively.  Two encodings of the same idea:
+//   PRMT (SOLB_Q2M_PRMT): one byte permute puts q into mantissa bits [15:8]: m = 32768 + q, s = 1.  PRMT runs on the ALU pipe,
+//     which issues one warp-instruction every two cycles; with 48 of them on top of the FMNMX / LOP3 / ISETP of the slab test
+//     the node step was bound by that pipe (~120 ALU instructions = 240 cycles against ~185 issue slots).
+//   IDP.4A (default): dp4a(w, 0xff << 8j, bits(32768.0f)) = bits + 255 q: m = 32768 + q * 255/256, s = 255/256, and the
+//     per-node scale a carries the factor 256/255.  Same instruction count, but IDP.4A issues on the FMA-heavy pipe
+//     (tools/microbench/pipes.cu on B200: PRMT 0.48, IDP.4A 0.48, FFMA 0.89 per clock alone; PRMT + IDP.4A interleaved 0.93 per
+//     clock, i.e. different pipes), so the ALU pipe sheds 40 % of its node-step load.
 #if defined(__CUDACC__)
-// bit pattern of 32768.0f in (non-const) constant memory: opaque to the optimiser, so PRMT takes it as the register /
+// bit pattern of 32768.0f in (non-const) constant memory: opaque to the optimiser, so PRMT / IDP take it as the register /
 // constant operand and the byte selector as an immediate
 __constant__ uint32_t c_q2m_bias = 0x47000000u;
+#endif
+#if defined(SOLB_Q2M_PRMT)
+#define SOLB_Q2M_SCALE 1.0f
+#else
+#define SOLB_Q2M_SCALE 1.00392163f  // 256 / 255 rounded up: m * (a * 256/255) = (32768 * 256/255 + q) * a
 #endif
 SOLB_HD float q2m(uint32_t w, int j) {
 #if defined(__CUDA_ARCH__)
@@ -147,24 +159,35 @@ SOLB_HD float q2m(uint32_t w, int j) {
     // the four selectors in registers (one extra IMAD.U32 per PRMT in the first build)
     uint32_t r;
     const uint32_t k = c_q2m_bias;
+#if defined(SOLB_Q2M_PRMT)
     switch (j) {
         case 0: asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(k)); break;
         case 1: asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(k)); break;
         case 2: asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(w), "r"(k)); break;
         default: asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(k)); break;
     }
-    return __uint_as_float(r);
 #else
+    switch (j) {
+        case 0: asm("dp4a.u32.u32 %0, %1, 0x000000ff, %2;" : "=r"(r) : "r"(w), "r"(k)); break;
+        case 1: asm("dp4a.u32.u32 %0, %1, 0x0000ff00, %2;" : "=r"(r) : "r"(w), "r"(k)); break;
+        case 2: asm("dp4a.u32.u32 %0, %1, 0x00ff0000, %2;" : "=r"(r) : "r"(w), "r"(k)); break;
+        default: asm("dp4a.u32.u32 %0, %1, 0xff000000, %2;" : "=r"(r) : "r"(w), "r"(k)); break;
+    }
+#endif
+    return __uint_as_float(r);
+#elif defined(SOLB_Q2M_PRMT)
     return u2f(0x47000000u | (((w >> (8 * j)) & 0xffu) << 8));
+#else
+    return u2f(0x47000000u + 255u * ((w >> (8 * j)) & 0xffu));
 #endif
 }
 
 SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4,
                                 float3 o, float3 idir, uint32_t oct_inv4, float tmin, float tmax) {
     const uint32_t e = q0.w;
-    const float ax = u2f((e & 0xffu) << 23) * idir.x;
-    const float ay = u2f(((e >> 8) & 0xffu) << 23) * idir.y;
-    const float az = u2f(((e >> 16) & 0xffu) << 23) * idir.z;
+    const float ax = u2f((e & 0xffu) << 23) * idir.x * SOLB_Q2M_SCALE;
+    const float ay = u2f(((e >> 8) & 0xffu) << 23) * idir.y * SOLB_Q2M_SCALE;
+    const float az = u2f(((e >> 16) & 0xffu) << 23) * idir.z * SOLB_Q2M_SCALE;
     const float bx = (u2f(q0.x) - o.x) * idir.x;
     const float by = (u2f(q0.y) - o.y) * idir.y;
     const float bz = (u2f(q0.z) - o.z) * idir.z;

@@ -1179,51 +1179,98 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
         *launches += 1;
         live[k] = true;
     }
-    for (uint32_t wave = 0; wave < max_waves && (live[0] || live[1] || live[2] || live[3]); wave++) {
-        for (int k = 0; k < n_lanes; k++) {
-            if (!live[k]) continue;
-            cudaStream_t st = L.stream[k];
-            if (events) {  // timing mode (single lane): bracket the dominant kernel with an event pair
-                while (events->size() < (size_t)*n_events_used + 2) {
-                    cudaEvent_t e;
-                    if ((err = cudaEventCreate(&e)) != cudaSuccess) return err;
-                    events->push_back(e);
-                }
-                cudaEventRecord((*events)[*n_events_used], st);
+    // Every part advances through its own wave sequence.  The host stays up to tune.max_ahead waves ahead of the last survivor
+    // count it has SEEN for a part (async_poll: a count is copied back every check_every waves and picked up with a non-blocking
+    // event query), so parts never wait for each other on the host and a part on a higher-priority stream can run ahead of the
+    // others: its drain tail then overlaps their full waves instead of their tails.  async_poll = 0 restores the lock-step
+    // schedule (all parts synchronised every check_every waves).
+    uint32_t wave_k[WF_MAX_PARTS] = { 0, 0, 0, 0 }, confirmed[WF_MAX_PARTS] = { 0, 0, 0, 0 }, poll_wave[WF_MAX_PARTS] = { 0, 0, 0, 0 };
+    bool pending[WF_MAX_PARTS] = { false, false, false, false };
+    const bool async_poll = tune.async_poll && !events && L.poll[0];
+    const uint32_t max_ahead = (uint32_t)std::max(tune.max_ahead, tune.check_every);
+    auto launch_wave = [&](int k) {
+        cudaStream_t st = L.stream[k];
+        if (events) {  // timing mode (single lane): bracket the dominant kernel with an event pair
+            while (events->size() < (size_t)*n_events_used + 2) {
+                cudaEvent_t e;
+                if ((err = cudaEventCreate(&e)) != cudaSuccess) return;
+                events->push_back(e);
             }
-            if (as.two_level) {
-                const float4 *il = as.inst_leaves_f4();
-                if (collect) k_wf_trace<true, true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
-                else k_wf_trace<false, true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
-            } else if (tune.pool && L.spill[k]) {
-                const int pool_grid = L.sm_count * tune.pool_ctas_per_sm;
-                if (collect) k_wf_trace_pool<true><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
-                else k_wf_trace_pool<false><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
-            } else if (tune.coop_tri && as.n_tris < (1u << 27)) {  // the dealt item packs the triangle index into 27 bits
-                if (collect) k_wf_trace<true, false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
-                else k_wf_trace<false, false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
-            } else if (collect) k_wf_trace<true, false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
-            else k_wf_trace<false, false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
-            if (events) {
-                cudaEventRecord((*events)[*n_events_used + 1], st);
-                *n_events_used += 2;
-            }
-            if (tune.sort_shade) k_wf_shade<true><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
-            else k_wf_shade<false><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
-            *launches += 2;
-            qi[k] ^= 1;
+            cudaEventRecord((*events)[*n_events_used], st);
         }
-        if (wave + 1 >= fc.spp && ((wave + 1) % check_every) == 0) {
-            // poll the survivor counts so finished halves stop launching empty waves
-            for (int k = 0; k < n_lanes; k++)
-                if (live[k] && (err = cudaMemcpyAsync(&L.host_counts[k], &L.ws[k].counters[qi[k]], sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                                      L.stream[k])) != cudaSuccess) return err;
+        if (as.two_level) {
+            const float4 *il = as.inst_leaves_f4();
+            if (collect) k_wf_trace<true, true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
+            else k_wf_trace<false, true, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), il, L.ws[k], qi[k], stats, tune);
+        } else if (tune.pool && L.spill[k]) {
+            const int pool_grid = L.sm_count * tune.pool_ctas_per_sm;
+            if (collect) k_wf_trace_pool<true><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
+            else k_wf_trace_pool<false><<<pool_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), L.ws[k], qi[k], stats, tune, L.spill[k]);
+        } else if (tune.coop_tri && as.n_tris < (1u << 27)) {  // the dealt item packs the triangle index into 27 bits
+            if (collect) k_wf_trace<true, false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+            else k_wf_trace<false, false, true><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+        } else if (collect) k_wf_trace<true, false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+        else k_wf_trace<false, false, false><<<trace_grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), nullptr, L.ws[k], qi[k], stats, tune);
+        if (events) {
+            cudaEventRecord((*events)[*n_events_used + 1], st);
+            *n_events_used += 2;
+        }
+        if (tune.sort_shade) k_wf_shade<true><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+        else k_wf_shade<false><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+        *launches += 2;
+        qi[k] ^= 1;
+        wave_k[k]++;
+    };
+    if (!async_poll) {
+        for (uint32_t wave = 0; wave < max_waves && (live[0] || live[1] || live[2] || live[3]); wave++) {
             for (int k = 0; k < n_lanes; k++) {
                 if (!live[k]) continue;
-                if ((err = cudaStreamSynchronize(L.stream[k])) != cudaSuccess) return err;
-                if (L.host_counts[k] == 0) live[k] = false;
+                launch_wave(k);
+                if (err != cudaSuccess) return err;
+            }
+            if (wave + 1 >= fc.spp && ((wave + 1) % check_every) == 0) {
+                // poll the survivor counts so finished parts stop launching empty waves
+                for (int k = 0; k < n_lanes; k++)
+                    if (live[k] && (err = cudaMemcpyAsync(&L.host_counts[k], &L.ws[k].counters[qi[k]], sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                                          L.stream[k])) != cudaSuccess) return err;
+                for (int k = 0; k < n_lanes; k++) {
+                    if (!live[k]) continue;
+                    if ((err = cudaStreamSynchronize(L.stream[k])) != cudaSuccess) return err;
+                    if (L.host_counts[k] == 0) live[k] = false;
+                }
             }
         }
+    } else {
+        for (;;) {
+            bool any = false;
+            for (int k = 0; k < n_lanes; k++) {
+                if (!live[k]) continue;
+                if (wave_k[k] >= max_waves) { live[k] = false; continue; }
+                if (pending[k]) {
+                    // too far ahead of the last count seen: wait for the outstanding one
+                    cudaError_t q = (wave_k[k] - confirmed[k] >= max_ahead) ? cudaEventSynchronize(L.poll[k]) : cudaEventQuery(L.poll[k]);
+                    if (q == cudaSuccess) {
+                        pending[k] = false;
+                        confirmed[k] = poll_wave[k];
+                        if (L.host_counts[k] == 0) { live[k] = false; continue; }
+                    } else if (q != cudaErrorNotReady) return q;
+                }
+                any = true;
+                launch_wave(k);
+                if (err != cudaSuccess) return err;
+                if (!pending[k] && wave_k[k] >= fc.spp && wave_k[k] - confirmed[k] >= check_every) {
+                    if ((err = cudaMemcpyAsync(&L.host_counts[k], &L.ws[k].counters[qi[k]], sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                               L.stream[k])) != cudaSuccess) return err;
+                    if ((err = cudaEventRecord(L.poll[k], L.stream[k])) != cudaSuccess) return err;
+                    pending[k] = true;
+                    poll_wave[k] = wave_k[k];
+                }
+            }
+            if (!any) break;
+        }
+        // a count still in flight targets pinned memory: let it land before the next call reuses the slot
+        for (int k = 0; k < n_lanes; k++)
+            if (pending[k] && (err = cudaEventSynchronize(L.poll[k])) != cudaSuccess) return err;
     }
     for (int k = 0; k < n_lanes; k++) {
         k_wf_resolve<<<(part_slots[k] + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], accum, render, part_slot_begin[k], part_slots[k]);

@@ -27,6 +27,11 @@ struct TraceTuning {
     int ctas_per_sm = 8;   // persistent grid = SMs x this
     int min_batch = 32;    // smallest ray batch a warp takes from the queue (short queues: rays / resident warps, rounded to 32)
     int check_every = 8;   // host polls the survivor count every this many waves
+    int async_poll = 1;    // 1: counts are picked up with non-blocking event queries, parts advance independently on the host
+    int max_ahead = 64;    // ... but never more than this many waves beyond the last count seen
+    int part_priority = 0; // 1: the extra part streams get increasing CUDA stream priorities (part k above part k-1) so the parts
+                           // drift apart and one part's drain tail meets the others' full waves.  Measured slower (3 347 ->
+                           // 3 286 Mrays/s, profiles/r01_sweep_async_poll.txt): off
     int overlap = 3;       // frame parts (1..4) run as independent wave sequences on their own streams, so the drain tail of one
                            // part's persistent trace kernel and its memory-bound shade kernel overlap another part's traversal
     int ctas_per_sm_overlap = 5;  // persistent CTAs per SM and part when overlapping
@@ -57,6 +62,7 @@ constexpr int WF_MAX_PARTS = 4;
 struct WavefrontLaunch {
     cudaStream_t stream[WF_MAX_PARTS];   // [0] = the ctx stream; others may be null: no overlap
     cudaEvent_t fork, join[WF_MAX_PARTS];
+    cudaEvent_t poll[WF_MAX_PARTS];      // survivor-count copies in flight (null: blocking polls)
     WavefrontState ws[WF_MAX_PARTS];     // same per-pixel state arrays, separate queues + counters
     uint2 *spill[WF_MAX_PARTS];          // per-part global stack spill of the ray-pool kernel (null: kernel unavailable)
     uint32_t *host_counts;               // pinned, WF_MAX_PARTS entries
