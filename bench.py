@@ -123,10 +123,33 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints its version banner with
+    printf).  Keep a private duplicate of fd 1 for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
@@ -428,7 +451,7 @@ def main():
                 "ms_per_frame": ms_per_step, "reduce_ms": main_run["reduce_ms"],
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": main_run["launches"],
                 "clocks": clock_info, "extra": extra}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
