@@ -37,6 +37,8 @@ struct solb_ctx {
     uint32_t *part_counters[WF_MAX_PARTS] = {};
     cudaStream_t part_stream[WF_MAX_PARTS] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[WF_MAX_PARTS] = {}, ev_poll[WF_MAX_PARTS] = {};
+    cudaStream_t shade_stream[WF_MAX_PARTS] = {};
+    cudaEvent_t ev_ts[WF_MAX_PARTS] = {}, ev_st[WF_MAX_PARTS] = {};
     uint2 *part_spill[WF_MAX_PARTS] = {};  // ray-pool kernel stack spill, one per frame part
     std::vector<cudaEvent_t> ev_pool;  // timing mode: pairs around every dominant-kernel launch
     float trace_kernel_ms_total = 0.0f;
@@ -172,6 +174,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.mega_persistent = env_int("SOLB_MEGA_PERSISTENT", c->tune.mega_persistent, 0, 1);
         c->tune.async_poll = env_int("SOLB_ASYNC_POLL", c->tune.async_poll, 0, 1);
         c->tune.max_ahead = env_int("SOLB_MAX_AHEAD", c->tune.max_ahead, 1, 4096);
+        c->tune.shade_priority = env_int("SOLB_SHADE_PRIORITY", c->tune.shade_priority, 0, 1);
         c->tune.part_priority = env_int("SOLB_PART_PRIORITY", c->tune.part_priority, 0, 1);
         c->tune.mega_vote = env_int("SOLB_MEGA_VOTE", c->tune.mega_vote, -1, 1);
         c->tune.mega_ctas_per_sm = env_int("SOLB_MEGA_CTAS_PER_SM", c->tune.mega_ctas_per_sm, 1, 16);
@@ -217,6 +220,11 @@ static void ctx_release(solb_ctx *ctx) {
         if (ctx->ev_poll[k]) cudaEventDestroy(ctx->ev_poll[k]);
     }
     if (ctx->ev_poll[0]) cudaEventDestroy(ctx->ev_poll[0]);
+    for (int k = 0; k < WF_MAX_PARTS; k++) {
+        if (ctx->shade_stream[k]) cudaStreamDestroy(ctx->shade_stream[k]);
+        if (ctx->ev_ts[k]) cudaEventDestroy(ctx->ev_ts[k]);
+        if (ctx->ev_st[k]) cudaEventDestroy(ctx->ev_st[k]);
+    }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -741,6 +749,14 @@ static int ensure_wavefront(solb_ctx *ctx, uint32_t n_pixels) {
     }
     for (int k = 0; k < WF_MAX_PARTS; k++)
         if (!ctx->ev_poll[k]) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_poll[k], cudaEventDisableTiming));
+    for (int k = 0; k < WF_MAX_PARTS && ctx->tune.shade_priority; k++)
+        if (!ctx->shade_stream[k]) {
+            int prio_lo = 0, prio_hi = 0;
+            CU(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CU(ctx, cudaStreamCreateWithPriority(&ctx->shade_stream[k], cudaStreamNonBlocking, prio_hi));
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_ts[k], cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_st[k], cudaEventDisableTiming));
+        }
     if (!ctx->ev_fork) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     if (ctx->tune.pool)
         for (int k = 0; k < WF_MAX_PARTS; k++) CU(ctx, cudaMalloc((void **)&ctx->part_spill[k], pool_spill_bytes(ctx->sm_count, ctx->tune)));
@@ -806,7 +822,12 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
             L.ws[k].queue[1] = ctx->part_queue[k][1];
             L.ws[k].counters = ctx->part_counters[k];
         }
-        for (int k = 0; k < WF_MAX_PARTS; k++) L.poll[k] = ctx->ev_poll[k];
+        for (int k = 0; k < WF_MAX_PARTS; k++) {
+            L.poll[k] = ctx->ev_poll[k];
+            L.shade_stream[k] = ctx->shade_stream[k];
+            L.ev_ts[k] = ctx->ev_ts[k];
+            L.ev_st[k] = ctx->ev_st[k];
+        }
         L.host_counts = ctx->pinned_count;
         L.sm_count = ctx->sm_count;
         CU(ctx, launch_pathtrace_wavefront(L, fc, s->accel, s->d_inst, s->d_shade, (float4 *)accum->dev,

@@ -1215,8 +1215,19 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
             cudaEventRecord((*events)[*n_events_used + 1], st);
             *n_events_used += 2;
         }
-        if (tune.sort_shade) k_wf_shade<true><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
-        else k_wf_shade<false><<<shade_grid, 256, 0, st>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+        // shade_priority: the short, memory-bound shade kernel runs on a high-priority side stream so its blocks are placed as
+        // soon as any persistent trace CTA of another part retires, instead of queueing behind those parts' pending CTAs
+        cudaStream_t ss = (tune.shade_priority && !events && L.shade_stream[k]) ? L.shade_stream[k] : st;
+        if (ss != st) {
+            cudaEventRecord(L.ev_ts[k], st);
+            cudaStreamWaitEvent(ss, L.ev_ts[k], 0);
+        }
+        if (tune.sort_shade) k_wf_shade<true><<<shade_grid, 256, 0, ss>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+        else k_wf_shade<false><<<shade_grid, 256, 0, ss>>>(fc, instances, shade, L.ws[k], qi[k], stats);
+        if (ss != st) {
+            cudaEventRecord(L.ev_st[k], ss);
+            cudaStreamWaitEvent(st, L.ev_st[k], 0);
+        }
         *launches += 2;
         qi[k] ^= 1;
         wave_k[k]++;

@@ -29,6 +29,8 @@ struct TraceTuning {
     int check_every = 8;   // host polls the survivor count every this many waves
     int async_poll = 1;    // 1: counts are picked up with non-blocking event queries, parts advance independently on the host
     int max_ahead = 64;    // ... but never more than this many waves beyond the last count seen
+    int shade_priority = 0; // 1: shade kernels on high-priority side streams (two event hops per wave): 3 453 -> 3 475 Mrays/s,
+                            // inside run-to-run noise (profiles/r01_sweep_async_poll.txt): off
     int part_priority = 0; // 1: the extra part streams get increasing CUDA stream priorities (part k above part k-1) so the parts
                            // drift apart and one part's drain tail meets the others' full waves.  Measured slower (3 347 ->
                            // 3 286 Mrays/s, profiles/r01_sweep_async_poll.txt): off
@@ -63,6 +65,8 @@ struct WavefrontLaunch {
     cudaStream_t stream[WF_MAX_PARTS];   // [0] = the ctx stream; others may be null: no overlap
     cudaEvent_t fork, join[WF_MAX_PARTS];
     cudaEvent_t poll[WF_MAX_PARTS];      // survivor-count copies in flight (null: blocking polls)
+    cudaStream_t shade_stream[WF_MAX_PARTS];  // high-priority side streams for the shade kernels (null: same stream as the trace)
+    cudaEvent_t ev_ts[WF_MAX_PARTS], ev_st[WF_MAX_PARTS];  // trace -> shade, shade -> trace
     WavefrontState ws[WF_MAX_PARTS];     // same per-pixel state arrays, separate queues + counters
     uint2 *spill[WF_MAX_PARTS];          // per-part global stack spill of the ray-pool kernel (null: kernel unavailable)
     uint32_t *host_counts;               // pinned, WF_MAX_PARTS entries
