@@ -921,3 +921,50 @@ def test_ragged_sizes_and_extreme_parameters(sol, ctx, w, h, spp, mb, frame, sta
     assert bad.sum() <= max(1, 0.03 * w * h), "%d of %d pixels differ" % (bad.sum(), w * h)
     assert np.all(g[..., 3] == 1.0) and np.all(np.isfinite(g))
     assert (np.abs(rend.readback().astype(np.int32) - o_rgba.astype(np.int32)).max(axis=2) > 1).sum() <= max(1, 0.03 * w * h)
+
+
+# ---- session-3 knobs: the scheduling variants must not change a single pixel ------------------------------------
+
+def _render_with_env(sol, env, name, w, h, frames, sky, mb, schedule):
+    """Render through a private context created under `env` (the SOLB_* knobs are read at context creation)."""
+    import os as _os
+
+    saved = {k: _os.environ.get(k) for k in env}
+    _os.environ.update(env)
+    try:
+        c = sol.Context(0)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                _os.environ.pop(k, None)
+            else:
+                _os.environ[k] = v
+    try:
+        return _render_gpu(sol, c, name, w, h, frames, sky, 8, mb, schedule)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("name,w,h,sky,mb", [("tunnel", 320, 180, True, 8), ("tunnel", 200, 120, True, 32), ("cornell", 128, 128, False, 32)])
+def test_async_polls_and_priorities_are_bit_identical(sol, name, w, h, sky, mb):
+    """Lock-step polls, asynchronous polls (parts advancing independently), part / shade stream priorities and the run-ahead
+    bound only change WHEN the waves of a part are enqueued: every variant must produce the same bits."""
+    ref_acc, ref_rgba = _render_with_env(sol, {"SOLB_ASYNC_POLL": "0"}, name, w, h, [0, 1, 2], sky, mb, 0)
+    for env in ({"SOLB_ASYNC_POLL": "1"}, {"SOLB_ASYNC_POLL": "1", "SOLB_MAX_AHEAD": "8", "SOLB_CHECK_EVERY": "4"},
+                {"SOLB_ASYNC_POLL": "1", "SOLB_PART_PRIORITY": "1"}, {"SOLB_ASYNC_POLL": "1", "SOLB_SHADE_PRIORITY": "1"},
+                {"SOLB_ASYNC_POLL": "1", "SOLB_OVERLAP": "4", "SOLB_MIN_PIXELS_PER_PART": "1"}):
+        acc, rgba = _render_with_env(sol, env, name, w, h, [0, 1, 2], sky, mb, 0)
+        np.testing.assert_array_equal(acc, ref_acc, err_msg=str(env))
+        np.testing.assert_array_equal(rgba, ref_rgba, err_msg=str(env))
+
+
+@pytest.mark.parametrize("name,w,h,sky,mb", [("tunnel", 256, 144, True, 8), ("cornell", 128, 128, False, 32), ("Duck", 160, 120, True, 8)])
+def test_voted_traversal_matches_per_thread_traversal(sol, name, w, h, sky, mb):
+    """trace_vote (warp-voted steps, postponed triangle groups) against trace_closest (every lane on its own) in the megakernel:
+    same closest hits, so the same images except decision-flip pixels (the two instantiations are compiled separately, so FMA
+    contraction can differ in the last bit, and the order of equal-t tests differs); same bounds as test_wavefront_equals_megakernel."""
+    a, _ = _render_with_env(sol, {"SOLB_MEGA_VOTE": "0"}, name, w, h, [0, 1], sky, mb, 1)
+    b, _ = _render_with_env(sol, {"SOLB_MEGA_VOTE": "1"}, name, w, h, [0, 1], sky, mb, 1)
+    d = np.abs(a - b)[..., :3]
+    assert (d.max(axis=2) > 1e-4 * (1 + np.abs(b[..., :3]).max(axis=2))).mean() < 0.01
+    assert d.sum() / b[..., :3].sum() < 2e-3
