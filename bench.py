@@ -92,6 +92,8 @@ def cpu_reference_arm(steps, warmup, sample_wh):
     from oracle import gltf_flatten as gf
 
     w, h = sample_wh
+    # all the host threads this process may use, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    oracle.lib().orc_set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     fs = gf.load_scene(os.path.join(ROOT, "assets", "models", "tunnel.gltf"))
     sc = oracle.Scene(fs)
     cam = ocam.Camera.from_view(fs.camera["view"], fs.camera["yfov"], fs.camera["znear"], fs.camera["zfar"])

@@ -772,6 +772,16 @@ ORC_API void orc_ao_frame(const OrcScene *s, const OrcUniforms *u, uint32_t W, u
     if (stats) { stats->rays += n_rays; stats->hits += n_hits; stats->paths += n_paths; }
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1 to every rank: the timed CPU arms ask for the host's threads explicitly */
+ORC_API void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP
