@@ -14,16 +14,23 @@ namespace solb {
 
 // ---- 80-byte node, addressed as 5 uint4 --------------------------------------------------------
 //  q0: px, py, pz (f32 bits), [ex | ey<<8 | ez<<16 | imask<<24]
-//  q1: child_base, tri_base, meta[0..3], meta[4..7]
+//  q1: child_base, tri_base | count0<<28, tmask[0..3], tmask[4..7]
 //  q2: qlo_x[0..3], qlo_x[4..7], qlo_y[0..3], qlo_y[4..7]
 //  q3: qlo_z[0..3], qlo_z[4..7], qhi_x[0..3], qhi_x[4..7]
 //  q4: qhi_y[0..3], qhi_y[4..7], qhi_z[0..3], qhi_z[4..7]
-// meta[i]: 0 = empty; internal child = 0b001_11sss (sss = slot i); leaf = (unary tri count) << 5 | tri offset
+// imask bit i: slot i holds an internal child (children are numbered from child_base in slot order).
+// tmask[i]: 0 for internal and empty slots; for a leaf of 1 or 2 triangles its static contribution to the triangle hit mask,
+//   (unary count = 1 or 3) << (offset inside its group of four slots).  Triangle offsets are cumulative in slot order, so the
+//   leaves of slots 0-3 own triangle bits [0, count0) and those of slots 4-7 the bits from count0 up: a group holds at most
+//   4 x 2 triangles and every contribution fits one byte.  With the eight slab-test results packed as bytes (1 = hit) the
+//   triangle hit mask is two dot products (IDP.4A, FMA-heavy pipe) instead of two field extractions, a variable shift and an OR per
+//   child on the ALU pipe (Ylitie et al.'s meta bytes, used until session 3: 56 of the node step's 237 instructions).
 // child box i = p + q * 2^(e-127) per axis, conservative (floor / ceil).
 struct Node8 {
     uint4 q[5];
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+#define SOLB_TRI_BASE_MASK 0x0fffffffu  // q1.y: triangle base (28 bits) | count0 << 28
 
 // ---- 48-byte triangle: world-space vertices; w lanes carry the ids the hit shaders need ----------
 //  v0.w = gl_InstanceID, v1.w = gl_PrimitiveID, v2.w = global triangle ordinal (index of the shading record)
@@ -32,7 +39,7 @@ struct Tri48 {
 };
 static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
 
-#define SOLB_MAX_LEAF_TRIS 3
+#define SOLB_MAX_LEAF_TRIS 2  // a leaf's mask contribution must fit one byte (above); 3 buys nothing on the shipped scenes
 #define SOLB_SM_STACK 8      // per-lane entries kept in shared memory
 #define SOLB_LOCAL_STACK 56  // spill (local memory)
 // The warp-cooperative kernel may park two entries per level (the siblings' node group and a postponed triangle
@@ -182,8 +189,18 @@ SOLB_HD float q2m(uint32_t w, int j) {
 #endif
 }
 
+// a . b over the four bytes + c (IDP.4A.U8.U8)
+SOLB_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(a, b, c);
+#else
+    for (int k = 0; k < 4; k++) c += ((a >> (8 * k)) & 0xffu) * ((b >> (8 * k)) & 0xffu);
+    return c;
+#endif
+}
+
 SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4,
-                                float3 o, float3 idir, uint32_t oct_inv4, float tmin, float tmax) {
+                                float3 o, float3 idir, uint32_t pow4_lo, uint32_t pow4_hi, float tmin, float tmax) {
     const uint32_t e = q0.w;
     const float ax = u2f((e & 0xffu) << 23) * idir.x * SOLB_Q2M_SCALE;
     const float ay = u2f(((e >> 8) & 0xffu) << 23) * idir.y * SOLB_Q2M_SCALE;
@@ -196,14 +213,9 @@ SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, 
     const float px = fabsf(ax) * 0.00390625f, py = fabsf(ay) * 0.00390625f, pz = fabsf(az) * 0.00390625f;
     const float nbx = cx - px, nby = cy - py, nbz = cz - pz;
     const float fbx = cx + px, fby = cy + py, fbz = cz + pz;
-    uint32_t hitmask = 0;
+    uint32_t hb[2] = { 0u, 0u };  // slab-test results of slots 0-3 / 4-7, one byte each (1 = hit)
 #pragma unroll
     for (int g = 0; g < 2; g++) {
-        const uint32_t meta4 = g ? q1.w : q1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
-        const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
         const uint32_t lox = g ? q2.y : q2.x, loy = g ? q2.w : q2.z, loz = g ? q3.y : q3.x;
         const uint32_t hix = g ? q3.w : q3.z, hiy = g ? q4.y : q4.x, hiz = g ? q4.w : q4.z;
         // near/far planes per axis depend only on the ray's direction signs
@@ -212,20 +224,24 @@ SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, 
         const uint32_t nz = idir.z < 0.0f ? hiz : loz, fz = idir.z < 0.0f ? loz : hiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int s = 8 * j;
             const float t0x = fmaf(q2m(nx, j), ax, nbx), t1x = fmaf(q2m(fx, j), ax, fbx);
             const float t0y = fmaf(q2m(ny, j), ay, nby), t1y = fmaf(q2m(fy, j), ay, fby);
             const float t0z = fmaf(q2m(nz, j), az, nbz), t1z = fmaf(q2m(fz, j), az, fbz);
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-            if (cmin <= cmax) {
-                const uint32_t child_bits = (child_bits4 >> s) & 0xffu;
-                const uint32_t bit_index = (bit_index4 >> s) & 0xffu;
-                hitmask |= child_bits << bit_index;
-            }
+            // (an empty slot decodes to the point box at the node origin; if a ray passes it, its tmask byte and imask bit are 0)
+            if (cmin <= cmax) hb[g] |= 1u << (8 * j);
         }
     }
-    return hitmask;
+    // internal children: slot s -> bit 24 + (s ^ oct_inv), i.e. front-to-back along the ray's octant when popped high bit first;
+    // pow4_lo / pow4_hi = the ray's 1 << (s ^ oct_inv) for s = 0..3 / 4..7, one byte each
+    const uint32_t imask = e >> 24;
+    const uint32_t inner_lo = ((imask & 0xfu) * 0x00204081u) & 0x01010101u;  // imask bits 0-3 spread to bytes
+    const uint32_t inner_hi = ((imask >> 4) * 0x00204081u) & 0x01010101u;
+    const uint32_t inner_hits = dot4_u8(hb[0] & inner_lo, pow4_lo, dot4_u8(hb[1] & inner_hi, pow4_hi, 0u));
+    // triangles: the hit leaves' static contributions (tmask bytes), slots 4-7 shifted past the bits of slots 0-3
+    const uint32_t t_lo = dot4_u8(hb[0], q1.z, 0u), t_hi = dot4_u8(hb[1], q1.w, 0u);
+    return (inner_hits << 24) | t_lo | (t_hi << (q1.y >> 28));
 }
 
 SOLB_HD float safe_rcp_dir(float d) {
@@ -242,17 +258,28 @@ SOLB_HD float safe_rcp_dir(float d) {
 // Per-ray constants of a traversal
 struct TravRay {
     float3 o, d, idir;
-    uint32_t oct_inv4;
+    uint32_t oct_inv;           // 7 - octant: slot ^ oct_inv = traversal priority of a slot
+    uint32_t pow4_lo, pow4_hi;  // byte j = 1 << ((4 g + j) ^ oct_inv) for g = 0 / 1
     RayFrame frame;
     float tmin;
 };
+
+// octant-dependent constants of a direction
+SOLB_HD void set_trav_octant(TravRay &t, float3 d) {
+    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+    t.oct_inv = 7u - oct;
+    // 1 << (j ^ k) for j = 0..3 and the low two bits k of oct_inv, in nibble 0 or 1 of every byte by bit 2 of oct_inv
+    const uint32_t k = t.oct_inv & 3u;
+    const uint32_t p4 = k == 0u ? 0x08040201u : (k == 1u ? 0x04080102u : (k == 2u ? 0x02010804u : 0x01020408u));
+    t.pow4_lo = (t.oct_inv & 4u) ? p4 << 4 : p4;
+    t.pow4_hi = (t.oct_inv & 4u) ? p4 : p4 << 4;
+}
 
 SOLB_HD TravRay make_trav_ray(float3 o, float3 d, float tmin) {
     TravRay t;
     t.o = o; t.d = d; t.tmin = tmin;
     t.idir = f3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
-    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
-    t.oct_inv4 = (7u - oct) * 0x01010101u;
+    set_trav_octant(t, d);
     t.frame = make_ray_frame(d);
     return t;
 }
@@ -269,13 +296,13 @@ SOLB_HD void trav_node_step(const uint4 *__restrict__ nodes, const TravRay &tr, 
     const uint32_t child_base = ngroup.x;
     ngroup.y &= ~(1u << child_bit);
     if (ngroup.y & 0xff000000u) stack.push(ngroup);
-    const uint32_t slot = (uint32_t)(child_bit - 24) ^ (tr.oct_inv4 & 0xffu);
+    const uint32_t slot = (uint32_t)(child_bit - 24) ^ tr.oct_inv;
     const uint32_t rel = (uint32_t)popc32(hits_imask & ~(0xffffffffu << slot));
     const uint4 *np = nodes + (size_t)(child_base + rel) * 5;
     const uint4 q0 = SOLB_LDG4(np + 0), q1 = SOLB_LDG4(np + 1), q2 = SOLB_LDG4(np + 2), q3 = SOLB_LDG4(np + 3), q4 = SOLB_LDG4(np + 4);
-    const uint32_t hm = intersect_node(q0, q1, q2, q3, q4, tr.o, tr.idir, tr.oct_inv4, tr.tmin, tmax);
+    const uint32_t hm = intersect_node(q0, q1, q2, q3, q4, tr.o, tr.idir, tr.pow4_lo, tr.pow4_hi, tr.tmin, tmax);
     ngroup = make_uint2(q1.x, (hm & 0xff000000u) | (q0.w >> 24));
-    tgroup = make_uint2(q1.y, hm & 0x00ffffffu);
+    tgroup = make_uint2(q1.y & SOLB_TRI_BASE_MASK, hm & 0x00ffffffu);
 }
 
 // One triangle step.  Precondition: tgroup.y != 0.  Tests the highest pending triangle of the group.
@@ -441,16 +468,18 @@ SOLB_HD void encode_node8(Node8 &out, float3 lo, float3 hi, uint32_t child_base,
     for (int i = 0; i < 20; i++) w[i] = 0;
     w[0] = f2u(lo.x); w[1] = f2u(lo.y); w[2] = f2u(lo.z);
     uint32_t imask = 0;
+    uint32_t count0 = 0;  // triangle bits owned by the leaves of slots 0-3
+    for (int i = 0; i < 4; i++)
+        if (children[i].valid && !children[i].is_inner) count0 += children[i].tri_count;
     for (int i = 0; i < 8; i++) {
         const ChildRef &c = children[i];
         if (!c.valid) continue;
-        uint32_t meta;
+        uint32_t meta = 0;  // tmask byte
         if (c.is_inner) {
             imask |= 1u << i;
-            meta = (1u << 5) | (24u + (uint32_t)i);
         } else {
-            const uint32_t unary = c.tri_count == 1 ? 1u : (c.tri_count == 2 ? 3u : 7u);
-            meta = (unary << 5) | c.tri_offset;
+            const uint32_t unary = c.tri_count == 1 ? 1u : 3u;  // tri_count <= SOLB_MAX_LEAF_TRIS = 2
+            meta = unary << (c.tri_offset - (i < 4 ? 0u : count0));
         }
         uint32_t q[6];
         const float cl[3] = { c.lo.x, c.lo.y, c.lo.z }, chh[3] = { c.hi.x, c.hi.y, c.hi.z };
@@ -477,8 +506,23 @@ SOLB_HD void encode_node8(Node8 &out, float3 lo, float3 hi, uint32_t child_base,
     }
     w[3] = ex | (ey << 8) | (ez << 16) | (imask << 24);
     w[4] = child_base;
-    w[5] = tri_base;
+    w[5] = (tri_base & SOLB_TRI_BASE_MASK) | (count0 << 28);
     for (int i = 0; i < 5; i++) out.q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+// decode what slot i of a node holds (tests / tools): 0 = empty, 1 = internal child, 2 = leaf with tri_count triangles starting at
+// triangle tri_offset (relative to the node's triangle base)
+SOLB_HD int decode_child_kind(const Node8 &n, int i, uint32_t &tri_offset, uint32_t &tri_count) {
+    const uint32_t *w = (const uint32_t *)&n;
+    tri_offset = tri_count = 0;
+    if ((w[3] >> (24 + i)) & 1u) return 1;
+    const uint32_t tmask = (w[6 + (i >> 2)] >> (8 * (i & 3))) & 0xffu;
+    if (!tmask) return 0;
+    uint32_t first = 0;
+    while (!((tmask >> first) & 1u)) first++;
+    tri_count = (uint32_t)popc32(tmask);
+    tri_offset = first + (i < 4 ? 0u : w[5] >> 28);
+    return 2;
 }
 
 // decode child box i of a node (tests / invariants)

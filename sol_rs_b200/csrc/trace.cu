@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_rays(const uint4 *__restr
 // 5-pathtrace, megakernel schedule: pathtrace.rgen:39-104 with the sample and bounce loops flattened
 // into one loop so a lane that ends a path immediately starts its next sample.
 template <bool STATS, bool TL, bool VOTE>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega(const FrameConsts fc, const uint4 *__restrict__ nodes,
+__global__ void __launch_bounds__(TRACE_BLOCK, (STATS || TL) ? 1 : 6) k_pathtrace_mega(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                                 const float4 *__restrict__ tris,
                                                                 const float4 *__restrict__ inst_leaves,
                                                                 const DeviceInstance *__restrict__ instances,
@@ -286,7 +286,7 @@ __device__ __forceinline__ uint32_t swizzled_pixel(uint32_t i, const FrameConsts
 // streams are unchanged.  Measured 5 % slower than one thread per pixel (TraceTuning::mega_persistent): kept for comparison.
 constexpr uint32_t MEGA_BATCH = 64;
 template <bool STATS, bool TL, bool VOTE>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_pathtrace_mega_persistent(const FrameConsts fc, const uint4 *__restrict__ nodes,
+__global__ void __launch_bounds__(TRACE_BLOCK, (STATS || TL) ? 1 : 6) k_pathtrace_mega_persistent(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                                            const float4 *__restrict__ tris,
                                                                            const float4 *__restrict__ inst_leaves,
                                                                            const DeviceInstance *__restrict__ instances,
@@ -790,8 +790,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace_pool(const FrameConsts
                 }
             } else {
                 tr.idir = f3(safe_rcp_dir(tr.d.x), safe_rcp_dir(tr.d.y), safe_rcp_dir(tr.d.z));
-                const uint32_t oct = (tr.d.x < 0.0f ? 4u : 0u) | (tr.d.y < 0.0f ? 2u : 0u) | (tr.d.z < 0.0f ? 1u : 0u);
-                tr.oct_inv4 = (7u - oct) * 0x01010101u;
+                set_trav_octant(tr, tr.d);
                 if (tgroup.y) stack.push(tgroup);  // postpone the pending triangles
                 trav_node_step(nodes, tr, P.tmax[slot], ngroup, tgroup, stack);
                 if (STATS) ctr.nodes++;

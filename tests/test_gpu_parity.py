@@ -64,22 +64,24 @@ def _walk_accel(nodes, tris):
         max_depth = max(max_depth, depth)
         w = nodes[node]
         imask = int(w[3]) >> 24
-        child_base, tri_base = int(w[4]), int(w[5])
+        child_base, tri_base, count0 = int(w[4]), int(w[5]) & 0x0FFFFFFF, int(w[5]) >> 28
         for i in range(8):
-            meta = (int(w[6 + (i >> 2)]) >> (8 * (i & 3))) & 0xFF
-            if meta == 0:
-                assert not (imask >> i) & 1
+            tmask = (int(w[6 + (i >> 2)]) >> (8 * (i & 3))) & 0xFF  # bvh.cuh: a leaf's contribution to the triangle hit mask
+            inner = (imask >> i) & 1
+            if not inner and tmask == 0:
                 continue
             lo, hi = child_box(node, i)
             if plo is not None:  # child boxes are allowed to poke out of the parent's quantised box only by rounding
                 pass
-            if (meta & 0x1F) >= 24 and (meta >> 5) == 1:
-                assert (imask >> i) & 1 and (meta & 7) == i
+            if inner:
+                assert tmask == 0
                 rel = bin(imask & ((1 << i) - 1)).count("1")
                 stack.append((child_base + rel, lo, hi, depth + 1))
             else:
-                cnt = {1: 1, 3: 2, 7: 3}[meta >> 5]
-                off = meta & 0x1F
+                cnt = bin(tmask).count("1")
+                first = (tmask & -tmask).bit_length() - 1
+                assert cnt in (1, 2) and tmask == ((1 << cnt) - 1) << first, "a leaf owns a run of 1 or 2 triangle bits"
+                off = first + (0 if i < 4 else count0)
                 for k in range(cnt):
                     t = tri_base + off + k
                     seen[t] += 1

@@ -9,11 +9,12 @@ static float g_key[8]; static int g_mode = 0;
 // decode child boxes and intersect in f32 (same conservative boxes as intersect_node)
 static int children_hit(const Node8 &n, float3 o, float3 idir, float tmin, float tmax, uint32_t *child_node, float *child_t, uint32_t *leaf_base, uint32_t *leaf_cnt, float *leaf_t, int &n_leaf) {
     const uint32_t *w = (const uint32_t *)&n;
-    const uint32_t imask = w[3] >> 24, child_base = w[4], tri_base = w[5];
+    const uint32_t imask = w[3] >> 24, child_base = w[4], tri_base = w[5] & SOLB_TRI_BASE_MASK;
     int ni = 0; n_leaf = 0;
     for (int i = 0; i < 8; i++) {
-        const uint32_t meta = (w[6 + (i >> 2)] >> (8 * (i & 3))) & 0xff;
-        if (!meta) continue;
+        uint32_t l_off, l_cnt;
+        const int kind = decode_child_kind(n, i, l_off, l_cnt);
+        if (!kind) continue;
         float3 lo, hi; decode_child_box(n, i, lo, hi);
         float t0 = tmin, t1 = tmax;
         const float lo3[3] = { lo.x, lo.y, lo.z }, hi3[3] = { hi.x, hi.y, hi.z }, o3[3] = { o.x, o.y, o.z }, id3[3] = { idir.x, idir.y, idir.z };
@@ -24,13 +25,13 @@ static int children_hit(const Node8 &n, float3 o, float3 idir, float tmin, float
             t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
         }
         if (t0 > t1) continue;
-        if ((meta & 0x1f) >= 24 && (meta >> 5) == 1) { child_node[ni] = child_base + popc32(imask & ((1u << i) - 1)); child_t[ni] = t0;
+        if (kind == 1) { child_node[ni] = child_base + popc32(imask & ((1u << i) - 1)); child_t[ni] = t0;
             const float sx = idir.x < 0 ? -1.f : 1.f, sy = idir.y < 0 ? -1.f : 1.f, sz = idir.z < 0 ? -1.f : 1.f;
             g_key[ni] = g_mode == 7 ? sx * (lo.x + hi.x) + sy * (lo.y + hi.y) + sz * (lo.z + hi.z)            // centre on the octant diagonal
                       : g_mode == 8 ? sx * (idir.x < 0 ? hi.x : lo.x) + sy * (idir.y < 0 ? hi.y : lo.y) + sz * (idir.z < 0 ? hi.z : lo.z)  // near corner on the diagonal
                       : 0.f;
             ni++; }
-        else { leaf_base[n_leaf] = tri_base + (meta & 0x1f); leaf_cnt[n_leaf] = (meta >> 5) == 1 ? 1 : ((meta >> 5) == 3 ? 2 : 3); leaf_t[n_leaf] = t0; n_leaf++; }
+        else { leaf_base[n_leaf] = tri_base + l_off; leaf_cnt[n_leaf] = l_cnt; leaf_t[n_leaf] = t0; n_leaf++; }
     }
     return ni;
 }
