@@ -115,7 +115,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 4))  # bounded: ~6 s per sample frame on 8 cores
+    steps = max(1, min(args.steps, 8))  # bounded: ~1.6 s per sample frame on 16 host threads, ~6 s on 8
     cb = cpu_reference_arm(steps, min(args.warmup, 1), (CPU_SAMPLE_W, CPU_SAMPLE_H))
     line = {"impl": "reference", "metric": "Mrays/s", "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
@@ -435,7 +435,7 @@ def main():
                                                          "ms_per_step": rc["ms_total"] / min(steps, 6),
                                                          "rays_per_path": rc["rays"] / max(rc["paths"], 1)}
         if not args.no_cpu_baseline and world == 1 and args.workload == "tunnel":
-            cb = cpu_reference_arm(2, 0, (CPU_SAMPLE_W, CPU_SAMPLE_H))
+            cb = cpu_reference_arm(6, 1, (CPU_SAMPLE_W, CPU_SAMPLE_H))  # ~10 s on 16 host threads
             cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
