@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsolb.so")
+# SOLB_LIB_PATH: load an experimental build of the same library instead (A/B runs of compile-time variants)
+LIB_PATH = os.environ.get("SOLB_LIB_PATH") or os.path.join(_HERE, "libsolb.so")
 
 SOLB_OK = 0
 FORMAT_RGBA32F, FORMAT_RGBA8, FORMAT_RG32UI = 0, 1, 2
