@@ -199,6 +199,18 @@ SOLB_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t c) {
 #endif
 }
 
+// Hit mask of a node from the byte-packed slab results (hb_lo / hb_hi: byte j = 1 if slot j / 4 + j passed).
+//   bits 31..24: internal children, slot s -> bit 24 + (s ^ oct_inv), i.e. front-to-back along the ray's octant when popped high
+//                bit first; pow4_lo / pow4_hi = the ray's 1 << (s ^ oct_inv) for s = 0..3 / 4..7, one byte each
+//   bits 23..0 : triangles of the hit leaves = their static contributions (tmask bytes), slots 4-7 shifted past the bits of slots 0-3
+SOLB_HD uint32_t assemble_hit_mask(uint32_t hb_lo, uint32_t hb_hi, uint32_t imask, const uint4 q1, uint32_t pow4_lo, uint32_t pow4_hi) {
+    const uint32_t inner_lo = ((imask & 0xfu) * 0x00204081u) & 0x01010101u;  // imask bits 0-3 spread to bytes
+    const uint32_t inner_hi = ((imask >> 4) * 0x00204081u) & 0x01010101u;
+    const uint32_t inner_hits = dot4_u8(hb_lo & inner_lo, pow4_lo, dot4_u8(hb_hi & inner_hi, pow4_hi, 0u));
+    const uint32_t t_lo = dot4_u8(hb_lo, q1.z, 0u), t_hi = dot4_u8(hb_hi, q1.w, 0u);
+    return (inner_hits << 24) | t_lo | (t_hi << (q1.y >> 28));
+}
+
 SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, const uint4 q3, const uint4 q4,
                                 float3 o, float3 idir, uint32_t pow4_lo, uint32_t pow4_hi, float tmin, float tmax) {
     const uint32_t e = q0.w;
@@ -233,15 +245,7 @@ SOLB_HD uint32_t intersect_node(const uint4 q0, const uint4 q1, const uint4 q2, 
             if (cmin <= cmax) hb[g] |= 1u << (8 * j);
         }
     }
-    // internal children: slot s -> bit 24 + (s ^ oct_inv), i.e. front-to-back along the ray's octant when popped high bit first;
-    // pow4_lo / pow4_hi = the ray's 1 << (s ^ oct_inv) for s = 0..3 / 4..7, one byte each
-    const uint32_t imask = e >> 24;
-    const uint32_t inner_lo = ((imask & 0xfu) * 0x00204081u) & 0x01010101u;  // imask bits 0-3 spread to bytes
-    const uint32_t inner_hi = ((imask >> 4) * 0x00204081u) & 0x01010101u;
-    const uint32_t inner_hits = dot4_u8(hb[0] & inner_lo, pow4_lo, dot4_u8(hb[1] & inner_hi, pow4_hi, 0u));
-    // triangles: the hit leaves' static contributions (tmask bytes), slots 4-7 shifted past the bits of slots 0-3
-    const uint32_t t_lo = dot4_u8(hb[0], q1.z, 0u), t_hi = dot4_u8(hb[1], q1.w, 0u);
-    return (inner_hits << 24) | t_lo | (t_hi << (q1.y >> 28));
+    return assemble_hit_mask(hb[0], hb[1], e >> 24, q1, pow4_lo, pow4_hi);
 }
 
 SOLB_HD float safe_rcp_dir(float d) {

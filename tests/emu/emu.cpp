@@ -455,6 +455,50 @@ void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_
     if (stats) { stats[0] += nrays; stats[1] += nhits; stats[2] += nnodes; stats[3] += ntris; }
 }
 
+// Node encoding self-test: random child sets through encode_node8, random slab results through assemble_hit_mask for all eight
+// octants, against the mask built child by child from the ChildRefs.  Returns the number of mismatches.
+uint32_t emu_mask_selftest(uint32_t seed, uint32_t rounds) {
+    uint32_t bad = 0, rng = seed;
+    auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+    for (uint32_t r = 0; r < rounds; r++) {
+        ChildRef ch[8];
+        uint32_t n_tris = 0;
+        for (int i = 0; i < 8; i++) {
+            const uint32_t kind = rnd() % 4u;  // 0 empty, 1 internal, 2 / 3 leaf
+            ch[i].valid = kind != 0u;
+            ch[i].is_inner = kind == 1u;
+            ch[i].lo = f3(0.1f * i, 0.0f, 0.0f); ch[i].hi = f3(0.1f * i + 0.05f, 1.0f, 1.0f);
+            ch[i].tri_offset = 0; ch[i].tri_count = 0;
+            if (kind >= 2u) { ch[i].tri_count = 1u + rnd() % (uint32_t)SOLB_MAX_LEAF_TRIS; ch[i].tri_offset = n_tris; n_tris += ch[i].tri_count; }
+        }
+        Node8 node;
+        const uint32_t tri_base = rnd() & SOLB_TRI_BASE_MASK;
+        encode_node8(node, f3(0, 0, 0), f3(1, 1, 1), rnd(), tri_base, ch);
+        if ((node.q[1].y & SOLB_TRI_BASE_MASK) != tri_base) bad++;
+        for (int i = 0; i < 8; i++) {  // decode_child_kind must return what was encoded
+            uint32_t off, cnt;
+            const int kind = decode_child_kind(node, i, off, cnt);
+            const int want = !ch[i].valid ? 0 : (ch[i].is_inner ? 1 : 2);
+            if (kind != want || (kind == 2 && (off != ch[i].tri_offset || cnt != ch[i].tri_count))) bad++;
+        }
+        for (uint32_t oct = 0; oct < 8; oct++) {
+            TravRay tr;
+            set_trav_octant(tr, f3(oct & 4u ? -1.0f : 1.0f, oct & 2u ? -1.0f : 1.0f, oct & 1u ? -1.0f : 1.0f));
+            const uint32_t hits = rnd() & 0xffu;
+            uint32_t hb[2] = { 0, 0 }, want = 0;
+            for (int i = 0; i < 8; i++) {
+                if (!((hits >> i) & 1u)) continue;
+                hb[i >> 2] |= 1u << (8 * (i & 3));
+                if (!ch[i].valid) continue;
+                if (ch[i].is_inner) want |= 1u << (24 + ((uint32_t)i ^ tr.oct_inv));
+                else want |= ((1u << ch[i].tri_count) - 1u) << ch[i].tri_offset;
+            }
+            if (assemble_hit_mask(hb[0], hb[1], node.q[0].w >> 24, node.q[1], tr.pow4_lo, tr.pow4_hi) != want) bad++;
+        }
+    }
+    return bad;
+}
+
 uint32_t emu_tea(uint32_t a, uint32_t b) { return tea(a, b); }
 float emu_next_rand(uint32_t *rng) { return next_rand(*rng); }
 

@@ -53,6 +53,8 @@ def lib():
         L.emu_debug.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
         L.emu_pathtrace_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_mask_selftest.restype = ctypes.c_uint32
+        L.emu_mask_selftest.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         L.emu_tea.restype = ctypes.c_uint32
         L.emu_tea.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
         L.emu_next_rand.restype = ctypes.c_float

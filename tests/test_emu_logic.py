@@ -178,3 +178,10 @@ def test_emu_optimal_collapse_beats_greedy():
     assert np.array_equal(res[True][4], res[False][4])  # primary hit ids do not depend on the tree
     d = np.abs(res[True][3] - res[False][3])[..., :3]
     assert (d.max(axis=2) > 1e-3).mean() < 0.01
+
+
+def test_node_hit_mask_table():
+    """bvh.cuh: the per-node triangle-mask bytes, count0 and the per-ray octant bytes reproduce, through four byte dot products, the
+    hit mask built child by child (internal child of slot s -> bit 24 + (s ^ oct_inv), leaf -> its run of triangle bits) for random
+    child sets, random slab results and all eight octants; decode_child_kind returns what encode_node8 was given."""
+    assert emu_lib.lib().emu_mask_selftest(0xB200, 20000) == 0
