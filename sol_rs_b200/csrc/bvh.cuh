@@ -430,7 +430,7 @@ struct ChildRef {
     float3 lo, hi;
     uint32_t is_inner;   // 1: internal child, 0: leaf
     uint32_t tri_offset; // leaf: first triangle relative to tri_base
-    uint32_t tri_count;  // leaf: 1..3
+    uint32_t tri_count;  // leaf: 1..SOLB_MAX_LEAF_TRIS
     uint32_t valid;
 };
 

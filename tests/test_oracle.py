@@ -254,3 +254,24 @@ def test_golden_converged_statistics():
     c = np.load(os.path.join(GOLDEN, "converged_cornell_96x96_4096spp_b32.npz"))
     assert c["accum"].shape == (96, 96, 3) and np.all(np.isfinite(c["accum"]))
     assert 0.01 < int(c["emissive"]) / int(c["paths"]) < 0.06
+
+
+@pytest.mark.parametrize("name,w,h,sky,mb,frame", [("cornell", 12, 12, False, 32, 3), ("tunnel", 16, 9, True, 8, 0), ("Duck", 12, 8, True, 8, 7)])
+def test_oracle_matches_second_glsl_restatement(name, w, h, sky, mb, frame):
+    """oracle.c against tests/glsl_twin.py, a second statement-by-statement reading of pathtrace.rgen / rchit / rmiss and
+    sampling.glsl in numpy float32 (closest hits taken from the oracle's own trace_rays): same number of rays, i.e. the same
+    RNG consumption and the same BRDF branch at every bounce, and the same pixel values to float rounding."""
+    import glsl_twin
+    from helpers import oracle_camera, oracle_scene
+
+    fs, osc = oracle_scene(name)
+    cam = oracle_camera(fs, name, w, h)
+    u = ocam.scene_uniforms(cam, w, h, frame)
+    twin, n_rays = glsl_twin.render_frame(fs, osc, u, w, h, sky, 8, mb)
+    acc = np.zeros((h, w, 4), dtype=np.float32)
+    st = oracle.OrcStats()
+    osc.pathtrace_frame(u, w, h, acc, frame, sky, 8, mb, st)
+    assert n_rays == st.rays
+    d = np.abs(twin[..., :3] - acc[..., :3])
+    assert d.max() <= 2e-4 * (1.0 + np.abs(acc[..., :3]).max())  # libm vs numpy sin / cos, amplified over the bounces
+    assert np.all(acc[..., 3] == 1.0)
