@@ -4,8 +4,8 @@ oracle/oracle.c is the oracle; this file exists to catch TRANSCRIPTION errors in
 (/root/reference/assets/glsl/pathtrace.rgen:39-104, pathtrace.rchit:56-113, pathtrace.rmiss:8-21, sampling.glsl:18-97) restated a
 second time, statement by statement, with none of oracle.c's helper structure.  The closest hit itself (the Vulkan driver's part) is
 taken from oracle.Scene.trace_rays, so what is cross-checked is ray generation, RNG consumption order, hit shading, BRDF sampling,
-sky, the bounce cap and the per-frame mean — everything the reference computes in shader code.  Far too slow for anything but a
-few hundred pixels.
+sky, the bounce cap and the per-frame mean — everything the reference computes in shader code.  render_ao_frame does the same for
+ao.rgen:36-83 / ao.rchit:43-89 / ao.rmiss.  Far too slow for anything but a few hundred pixels.
 """
 import numpy as np
 
@@ -203,5 +203,83 @@ def render_frame(fs, osc, uniforms, w, h, enable_sky, spp, max_bounces):
                 pixel = (pixel + acc).astype(F)
             pixel = (pixel * F(F(1) / F(spp))).astype(F)
             out[y, x, :3] = pixel
+            out[y, x, 3] = 1
+    return out, n_rays
+
+
+def render_ao_frame(fs, osc, uniforms, w, h, blue):
+    """One frame of ao.rgen:36-83 + ao.rchit:43-89 + ao.rmiss into a fresh image (frame == accum_start_frame, a = 1).
+    blue = the blue-noise texture as uploaded (rgba8, [y][x][c])."""
+    u = np.frombuffer(uniforms, dtype=F)
+    view_inv, proj_inv = u[32:48], u[64:80]
+    frame = int(np.frombuffer(uniforms, dtype=np.uint32)[98])
+    verts, indices = np.asarray(fs.vertices, dtype=F), np.asarray(fs.indices)
+    inst_data = []
+    for inst in fs.instances:
+        t = np.asarray(inst["transform"], dtype=F).reshape(16)
+        t_it = np.asarray(gf.mat4_inverse(np.asarray(inst["transform"], dtype=F).reshape(4, 4)).T, dtype=F).reshape(16)
+        inst_data.append((inst, t, t_it))
+    th, tw = blue.shape[0], blue.shape[1]
+    max_samples, sample_count = 4, 4
+    out = np.zeros((h, w, 4), dtype=F)
+    n_rays = 0
+    for y in range(h):
+        for x in range(w):
+            rng = Rng(tea(x + y * w, frame))
+            ao = _v3(0, 0, 0)
+            for s in range(sample_count):
+                jx = rng.next()
+                jy = rng.next()
+                in_uv = np.array([F(F(x) + jx) / F(w), F(F(y) + jy) / F(h)], dtype=F)
+                d = (in_uv * F(2) - F(1)).astype(F)
+                origin = _mat_vec4(view_inv, np.array([0, 0, 0, 1], dtype=F))
+                target = _mat_vec4(proj_inv, np.array([d[0], d[1], 1, 1], dtype=F))
+                tn = _normalize(target[:3])
+                direction = _mat_vec4(view_inv, np.array([tn[0], tn[1], tn[2], 0], dtype=F))
+                ray_o, ray_d = origin[:3].copy(), direction[:3].copy()
+                tmin, tmax = F(max(F(1), _length(origin[:3])) * F(1e-3)), F(10000.0)
+                depth, hit_value = 0, _v3(0, 0, 0)
+                while True:
+                    ray = np.array([[ray_o[0], ray_o[1], ray_o[2], tmin, ray_d[0], ray_d[1], ray_d[2], tmax]], dtype=F)
+                    hits, _t, _ = osc.trace_rays(ray)
+                    n_rays += 1
+                    inst_id, prim = int(hits[0, 0]), int(hits[0, 1])
+                    if inst_id == MISS:
+                        break  # ao.rmiss: done = 1
+                    inst, t, t_it = inst_data[inst_id]
+                    bu, bv = hits[0, 2:4].view(F)
+                    tri = [verts[inst["first_vertex"] + int(indices[inst["first_index"] + 3 * prim + k])] for k in range(3)]
+                    bary = _v3(F(F(F(1) - bu) - bv), bu, bv)
+
+                    def interp(lo):
+                        return ((tri[0][lo:lo + 3] * bary[0]).astype(F) + (tri[1][lo:lo + 3] * bary[1]).astype(F)
+                                + (tri[2][lo:lo + 3] * bary[2]).astype(F)).astype(F)
+
+                    nrm = interp(8)
+                    nrm = _normalize(_mat_vec4(t_it, np.array([nrm[0], nrm[1], nrm[2], 0], dtype=F))[:3])
+                    pos = interp(0)
+                    world = _mat_vec4(t, np.array([pos[0], pos[1], pos[2], 1], dtype=F))[:3]
+                    ray_o_new = (world + ray_d * F(0.00001)).astype(F)
+                    # getBlueRand2(depth + depth * sampleId)
+                    i = depth + depth * s
+                    rx = rng.next()
+                    ry = rng.next()
+                    fx, fy = F(F(x) + F(rx * F(tw))), F(F(y) + F(ry * F(th)))
+                    cx = int(F(fx - F(F(tw) * F(np.floor(F(fx / F(tw)))))))
+                    cy = int(F(fy - F(F(th) * F(np.floor(F(fy / F(th)))))))
+                    texel = blue[cy, cx].astype(F) / F(255.0)
+                    xi = (F(texel[i % 4]), F(texel[(i + 1) % 4]))
+                    hit_norm = (nrm * F(np.sign(_dot(-ray_d, nrm)))).astype(F)
+                    ray_d_new = sample_cosine(hit_norm, xi)
+                    tmin, tmax = F(0.001), F(10.0)
+                    if depth > 0:
+                        hit_value = (hit_value + _v3(1, 1, 1)).astype(F)
+                    depth += 1
+                    ray_o, ray_d = ray_o_new, ray_d_new
+                    if depth > max_samples:
+                        break
+                ao = (ao + hit_value * F(F(1) / F(max_samples))).astype(F)
+            color = (_v3(1, 1, 1) - ao / F(sample_count)).astype(F)
+            out[y, x, :3] = color
             out[y, x, 3] = 1
     return out, n_rays

@@ -275,3 +275,22 @@ def test_oracle_matches_second_glsl_restatement(name, w, h, sky, mb, frame):
     d = np.abs(twin[..., :3] - acc[..., :3])
     assert d.max() <= 2e-4 * (1.0 + np.abs(acc[..., :3]).max())  # libm vs numpy sin / cos, amplified over the bounces
     assert np.all(acc[..., 3] == 1.0)
+
+
+@pytest.mark.parametrize("name,cam_name,w,h,frame", [("Duck", "Duck_ao", 24, 14, 2), ("cornell", "cornell", 12, 12, 0)])
+def test_oracle_ao_matches_second_glsl_restatement(name, cam_name, w, h, frame):
+    """oracle.c's 4-ray-ao frame against tests/glsl_twin.py's reading of ao.rgen / ao.rchit / ao.rmiss (blue-noise lookup, chained
+    cosine-weighted rays in [0.001, 10], hit counting from the second hit on): same rays, same pixels."""
+    import glsl_twin
+    from helpers import load_blue_noise, oracle_camera, oracle_scene
+
+    fs, osc = oracle_scene(name)
+    blue = load_blue_noise()
+    u = ocam.scene_uniforms(oracle_camera(fs, cam_name, w, h), w, h, frame)
+    twin, n_rays = glsl_twin.render_ao_frame(fs, osc, u, w, h, blue)
+    img = np.zeros((h, w, 4), dtype=np.float32)
+    st = oracle.OrcStats()
+    osc.ao_frame(u, w, h, img, blue, frame, st)
+    assert n_rays == st.rays
+    assert np.abs(twin[..., :3] - img[..., :3]).max() <= 1e-6
+    assert 0.0 < img[..., :3].mean() <= 1.0
