@@ -456,8 +456,11 @@ __global__ void __launch_bounds__(256) k_wf_generate(const FrameConsts fc, Wavef
 // with a fixed 128 a 86 K-ray wave kept 675 of 2 960 warps busy, four rays deep (tools/tile_time.py).
 constexpr uint32_t WF_BATCH = 128;
 
+// Resident CTAs per SM the trace kernel is compiled for.  8 (= 64 registers, 12 bytes of spill) for the flattened kernel: with the
+// shorter node step of session 3 it beats the 72-register build (3 507 -> 3 574 Mrays/s, profiles/r01_sweep_regs64.txt; the same
+// experiment on the session-2 kernel had lost 2 %).  The two-level and cooperative variants would spill ~90 bytes at 64: they keep 7.
 #ifndef SOLB_WF_MIN_CTAS
-#define SOLB_WF_MIN_CTAS 7
+#define SOLB_WF_MIN_CTAS 8
 #endif
 // TL: two-level scenes.  A lane is either in the TLAS (its "triangle" groups are instance leaves: the triangle step
 // enters the instance) or inside a BLAS; the sentinel popped at the end of a BLAS walk reloads the world-space ray.
@@ -469,7 +472,7 @@ constexpr uint32_t WF_BATCH = 128;
 // scan, work list, 7 shuffles, ray frame, result gather) costs ~170 instructions per round though, and the replay only wins
 // below ~40: measured 3 051 vs 3 300 Mrays/s, so it stays off (profiles/r01_sweep_coop_tri.txt).
 template <bool STATS, bool TL, bool COOP>
-__global__ void __launch_bounds__(TRACE_BLOCK, SOLB_WF_MIN_CTAS) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
+__global__ void __launch_bounds__(TRACE_BLOCK, (TL || COOP) ? 7 : SOLB_WF_MIN_CTAS) k_wf_trace(const FrameConsts fc, const uint4 *__restrict__ nodes,
                                                           const float4 *__restrict__ tris, const float4 *__restrict__ inst_leaves,
                                                           WavefrontState ws, int qi, unsigned long long *stats, const TraceTuning tune) {
     SOLB_DECL_STACK();
