@@ -970,3 +970,17 @@ def test_voted_traversal_matches_per_thread_traversal(sol, name, w, h, sky, mb):
     d = np.abs(a - b)[..., :3]
     assert (d.max(axis=2) > 1e-4 * (1 + np.abs(b[..., :3]).max(axis=2))).mean() < 0.01
     assert d.sum() / b[..., :3].sum() < 2e-3
+
+
+@pytest.mark.parametrize("env,schedule", [({"SOLB_POOL": "1"}, 0), ({"SOLB_COOP_TRI": "1"}, 0), ({"SOLB_SORT_SHADE": "1"}, 0),
+                                          ({"SOLB_MEGA_PERSISTENT": "1"}, 1), ({"SOLB_MEGA_PERSISTENT": "1", "SOLB_MEGA_VOTE": "1"}, 1)])
+def test_experimental_schedules_still_agree(sol, env, schedule):
+    """The measured-and-switched-off variants (ray-pool kernel, cooperative triangle step, material-sorted shading, persistent
+    megakernel) share the node / triangle steps with the default kernels: after any change to those they must still render the
+    same image, up to decision-flip pixels (separately compiled instantiations, different order of equal-t tests)."""
+    name, w, h = "tunnel", 256, 144
+    ref, _ = _render_with_env(sol, {}, name, w, h, [0, 1], True, 8, schedule)
+    img, _ = _render_with_env(sol, env, name, w, h, [0, 1], True, 8, schedule)
+    d = np.abs(img - ref)[..., :3]
+    assert (d.max(axis=2) > 1e-4 * (1 + np.abs(ref[..., :3]).max(axis=2))).mean() < 0.01, str(env)
+    assert d.sum() / ref[..., :3].sum() < 2e-3, str(env)
