@@ -203,7 +203,8 @@ def main():
     ctx = sol.Context(local_rank, stream.cuda_stream)
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
-    sched = N.SCHEDULE_MEGAKERNEL if args.schedule.startswith("mega") else N.SCHEDULE_WAVEFRONT
+    sched = {"mega": N.SCHEDULE_MEGAKERNEL, "wave": N.SCHEDULE_WAVEFRONT, "warp": N.SCHEDULE_WARPFRONT}[args.schedule[:4]]
+    sched_name = {N.SCHEDULE_MEGAKERNEL: "megakernel", N.SCHEDULE_WAVEFRONT: "wavefront", N.SCHEDULE_WARPFRONT: "warpfront"}[sched]
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def setup(model, sky):
@@ -388,10 +389,12 @@ def main():
                                                  samples_per_frame=SPP, max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
         st2 = ctx.stats()
         ctx.set_timing(False)
-        if sched == N.SCHEDULE_MEGAKERNEL:
-            kernel = "k_pathtrace_mega"
-            # everything happens in one kernel: traversal + shading fetches + accumulation RMW
-            b_ray = 80 * n_node + 48 * n_tri + p_hit * (112 + 176) + 36.0 / (SPP * r_path)
+        if sched in (N.SCHEDULE_MEGAKERNEL, N.SCHEDULE_WARPFRONT):
+            kernel = "k_pathtrace_mega" if sched == N.SCHEDULE_MEGAKERNEL else "k_pt_warpfront"
+            # everything happens in one kernel: traversal + shading fetches + accumulation RMW (+ the path record round trip
+            # of the warp-local wavefront: ray record read, hit record write / read, path state read / write)
+            b_ray = 80 * n_node + 48 * n_tri + p_hit * (112 + 176) + 36.0 / (SPP * r_path) + (
+                (32 + 32 + 80 + 64) if sched == N.SCHEDULE_WARPFRONT else 0)
         else:
             kernel = "k_wf_trace"
             # traversal kernel only: nodes + triangles + ray record read (2 x float4 + queue id) + hit record write
@@ -443,7 +446,7 @@ def main():
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "schedule": "megakernel" if sched else "wavefront", "accel": args.accel, "bvh_build_ms": build_ms,
+                "config": {"workload": workload, "schedule": sched_name, "accel": args.accel, "bvh_build_ms": build_ms,
                            "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * (1 if tiled else world)),
                            "l2": "256 MB buffer written between timed steps (outside the per-step event pairs)",
                            "multi_gpu": ("every frame cut into 8-row bands dealt round-robin to the N ranks, one NCCL all-gather of the accumulation rows per frame inside the timed region"

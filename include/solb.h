@@ -101,8 +101,11 @@ typedef enum SolbTargetFormat {
 typedef enum SolbSchedule {
     SOLB_SCHEDULE_WAVEFRONT = 0, /* queue-based wavefront: persistent trace kernel + shade/compact kernels */
     SOLB_SCHEDULE_MEGAKERNEL = 1,/* one thread per pixel, flattened bounce loop                           */
-    SOLB_SCHEDULE_AUTO = 2       /* megakernel for tiny hierarchies (<= 8 wide nodes: no traversal divergence to
-                                    hide, queue traffic dominates), wavefront otherwise                      */
+    SOLB_SCHEDULE_AUTO = 2,      /* megakernel for tiny hierarchies (<= 8 wide nodes: no traversal divergence to
+                                    hide, queue traffic dominates), warp-local wavefront otherwise           */
+    SOLB_SCHEDULE_WARPFRONT = 3  /* warp-local wavefront: ONE persistent kernel per frame; every warp traces its own pool of
+                                    pixels with the voted traversal and shades its finished rays 32 wide (no global queues,
+                                    no waves, no host polling)                                               */
 } SolbSchedule;
 
 typedef enum SolbAccelMode {

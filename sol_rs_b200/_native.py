@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("SOLB_LIB_PATH") or os.path.join(_HERE, "libsolb.so")
 
 SOLB_OK = 0
 FORMAT_RGBA32F, FORMAT_RGBA8, FORMAT_RG32UI = 0, 1, 2
-SCHEDULE_WAVEFRONT, SCHEDULE_MEGAKERNEL, SCHEDULE_AUTO = 0, 1, 2
+SCHEDULE_WAVEFRONT, SCHEDULE_MEGAKERNEL, SCHEDULE_AUTO, SCHEDULE_WARPFRONT = 0, 1, 2, 3
 ACCUM_MIX, ACCUM_SUM = 0, 1
 ACCEL_FLAT, ACCEL_TWO_LEVEL = 0, 1
 MISS = 0xFFFFFFFF

@@ -32,6 +32,7 @@ struct solb_ctx {
     uint32_t blue_w = 0, blue_h = 0;
     uint32_t *pinned_count = nullptr;
     WavefrontState ws = {};
+    WarpfrontState wl = {};  // warp-local wavefront schedule: slot-indexed path state, sized by the persistent grid
     // queues + counters + streams of the extra frame parts (overlap mode); index 0 unused (= ws / stream)
     uint32_t *part_queue[WF_MAX_PARTS][2] = {};
     uint32_t *part_counters[WF_MAX_PARTS] = {};
@@ -44,6 +45,7 @@ struct solb_ctx {
     float trace_kernel_ms_total = 0.0f;
     uint32_t trace_kernel_launches = 0;
     TraceTuning tune;
+    uint32_t auto_wide_schedule = SOLB_SCHEDULE_WARPFRONT;  // what SOLB_SCHEDULE_AUTO picks above 8 wide nodes (SOLB_AUTO_SCHEDULE)
     int refs = 1;  // the ctx handle itself + every live scene / target: resources are freed when the last one goes
 };
 
@@ -179,6 +181,11 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.mega_vote = env_int("SOLB_MEGA_VOTE", c->tune.mega_vote, -1, 1);
         c->tune.mega_ctas_per_sm = env_int("SOLB_MEGA_CTAS_PER_SM", c->tune.mega_ctas_per_sm, 1, 16);
         c->tune.mega_fetch_idle = env_int("SOLB_MEGA_FETCH_IDLE", c->tune.mega_fetch_idle, 1, 32);
+        c->auto_wide_schedule = env_int("SOLB_AUTO_SCHEDULE", (int)c->auto_wide_schedule, 0, 3) == 0 ? SOLB_SCHEDULE_WAVEFRONT : SOLB_SCHEDULE_WARPFRONT;
+        c->tune.wl_ctas_per_sm = env_int("SOLB_WL_CTAS_PER_SM", c->tune.wl_ctas_per_sm, 1, 16);
+        c->tune.wl_fetch_idle = env_int("SOLB_WL_FETCH_IDLE", c->tune.wl_fetch_idle, 1, 32);
+        c->tune.wl_gen_min = env_int("SOLB_WL_GEN_MIN", c->tune.wl_gen_min, 1, WL_POOL);
+        c->tune.wl_batch = env_int("SOLB_WL_BATCH", c->tune.wl_batch, 32, 1024) & ~31;
     }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
@@ -203,11 +210,18 @@ static void free_wavefront(solb_ctx *c) {
     w = WavefrontState{};
 }
 
+static void free_warpfront(solb_ctx *c) {
+    WarpfrontState &w = c->wl;
+    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.thr); cudaFree(w.pix); cudaFree(w.hit); cudaFree(w.cursor);
+    w = WarpfrontState{};
+}
+
 static void ctx_release(solb_ctx *ctx) {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_wavefront(ctx);
+    free_warpfront(ctx);
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_blue);
     cudaFreeHost(ctx->pinned_count);
@@ -767,6 +781,22 @@ static int ensure_wavefront(solb_ctx *ctx, uint32_t n_pixels) {
     return SOLB_OK;
 }
 
+static int ensure_warpfront(solb_ctx *ctx) {
+    WarpfrontState &w = ctx->wl;
+    const uint32_t n_warps = warpfront_grid_warps(ctx->sm_count, ctx->tune);
+    if (w.n_warps >= n_warps && w.ray_o) return SOLB_OK;
+    free_warpfront(ctx);
+    const size_t n = (size_t)n_warps * WL_POOL;
+    CU(ctx, cudaMalloc((void **)&w.ray_o, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.ray_d, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.thr, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.pix, n * sizeof(float4)));
+    CU(ctx, cudaMalloc((void **)&w.hit, n * sizeof(uint4)));
+    CU(ctx, cudaMalloc((void **)&w.cursor, sizeof(uint32_t)));
+    w.n_warps = n_warps;
+    return SOLB_OK;
+}
+
 struct TraceTimer {
     solb_ctx *c;
     explicit TraceTimer(solb_ctx *ctx) : c(ctx) { if (c->timing) cudaEventRecord(c->ev0, c->stream); }
@@ -801,7 +831,18 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
     TraceTimer timer(ctx);
     uint32_t n_ev = 0;
     uint32_t schedule = params->schedule;
-    if (schedule == SOLB_SCHEDULE_AUTO) schedule = s->accel.n_wide <= 8 ? SOLB_SCHEDULE_MEGAKERNEL : SOLB_SCHEDULE_WAVEFRONT;
+    if (schedule == SOLB_SCHEDULE_AUTO) schedule = s->accel.n_wide <= 8 ? SOLB_SCHEDULE_MEGAKERNEL : ctx->auto_wide_schedule;
+    if (schedule > SOLB_SCHEDULE_WARPFRONT) return fail(ctx, SOLB_ERR_INVALID, "trace: unknown schedule");
+    if (schedule == SOLB_SCHEDULE_WARPFRONT) {
+        if ((rc = ensure_warpfront(ctx))) return rc;
+        CU(ctx, launch_pathtrace_warpfront(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->wl, (float4 *)accum->dev,
+                                           render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0,
+                                           ctx->sm_count, ctx->tune));
+        ctx->launches += 1;
+        timer.stop();
+        if (ctx->timing) { ctx->trace_kernel_ms_total += ctx->last_trace_ms; ctx->trace_kernel_launches += 1; }
+        return SOLB_OK;
+    }
     if (schedule == SOLB_SCHEDULE_MEGAKERNEL) {
         CU(ctx, launch_pathtrace_mega(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, (float4 *)accum->dev,
                                       render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0,

@@ -945,6 +945,250 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, Wavefr
 }
 
 // ---------------------------------------------------------------------------------------------------
+// 5-pathtrace, warp-local wavefront schedule (SOLB_SCHEDULE_WARPFRONT): ONE persistent kernel per frame.
+//
+// The queue-based wavefront above pays for its global queues three times: every one of the ~72 waves of a frame ends in a drain
+// tail (a persistent warp holds ~7 rays per lane and wave, so the last ray of each lane runs in a thinning warp), the shade kernel
+// is a separate memory-bound launch between two traversal launches, and the host has to poll survivor counts to know when to stop.
+// Here every WARP is its own wavefront machine over a pool of WL_POOL pixels it owns:
+//   * its 32 lanes walk one ray each with the voted node / triangle steps of k_wf_trace;
+//   * a finished ray's pixel slot goes on the warp's to-shade list (shared memory, ballot-compacted);
+//   * once 32 slots wait there, the whole warp runs ONE shade step over them - pathtrace.rchit / rmiss / bounce cap / next
+//     sample exactly as k_wf_shade does, 32 lanes wide and converged - and the surviving slots go on the warp's ready list;
+//   * idle lanes take ready slots; a pixel that has finished its samples is resolved into the accumulation / render targets in
+//     the shade step and its slot is refilled with the next pixel of the frame's cursor (8x4 tiles, one atomic per tile).
+// No global queue, no inter-warp communication, no waves: the only drain is the end of the frame.  Path state lives in
+// slot-indexed arrays sized by the grid (36 MB), so it stays in L2.  Per-pixel arithmetic, RNG order and accumulation are those of
+// k_wf_generate / k_wf_shade / k_wf_resolve: the frames are bit-identical to the other schedules'.
+__device__ __forceinline__ void wl_push(uint8_t *list, uint32_t &n, bool flag, uint32_t slot, uint32_t lt_mask) {
+    const uint32_t m = __ballot_sync(0xffffffffu, flag);
+    if (flag) list[n + __popc(m & lt_mask)] = (uint8_t)slot;
+    n += (uint32_t)__popc(m);
+}
+
+template <bool STATS, bool TL>
+__global__ void __launch_bounds__(TRACE_BLOCK, TL ? 7 : SOLB_WF_MIN_CTAS)
+k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
+               const float4 *__restrict__ inst_leaves, const DeviceInstance *__restrict__ instances,
+               const ShadeRecord *__restrict__ shade, const WarpfrontState wl, float4 *accum, uint32_t *render,
+               unsigned long long *stats, const uint32_t n_region_slots, const TraceTuning tune) {
+    SOLB_DECL_STACK();
+    __shared__ uint8_t s_lists[TRACE_BLOCK / 32][3][WL_POOL];
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u, wib = threadIdx.x >> 5;
+    uint8_t *l_ready = s_lists[wib][0], *l_shade = s_lists[wib][1], *l_free = s_lists[wib][2];
+    const uint32_t gwarp = blockIdx.x * (TRACE_BLOCK / 32) + wib;
+    if (gwarp >= wl.n_warps) return;
+    const size_t slot_base = (size_t)gwarp * WL_POOL;
+    uint32_t n_ready = 0, n_shade = 0, n_free = WL_POOL;  // warp-uniform
+    for (uint32_t i = lane; i < (uint32_t)WL_POOL; i += 32u) l_free[i] = (uint8_t)i;
+    __syncwarp();
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform range of frame pixel slots already claimed from the cursor
+    bool exhausted = false;
+    uint32_t nr = 0, nh = 0, np = 0;
+    TraceCounters ctr = { 0, 0 };
+    // per-lane ray state (as k_wf_trace)
+    bool has_ray = false;
+    uint32_t slot = 0;
+    TravRay tr = make_trav_ray(f3(0, 0, 0), f3(0, 0, 1), 0.0f);
+    float tmax = 0.0f;
+    Hit hit;
+    hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f;
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+    bool in_blas = false;
+    uint32_t cur_inst = SOLB_MISS;
+    uint32_t b_ray = 0;
+    for (;;) {
+        const uint32_t n_idle = (uint32_t)__popc(~b_ray);
+        const bool starving = n_ready == 0u && n_idle >= (uint32_t)tune.wl_fetch_idle;
+        // ---- generate: free slots take the next pixels of the frame (k_wf_generate) ----
+        if (!exhausted && n_free > 0u && (n_free >= (uint32_t)tune.wl_gen_min || (starving && n_shade < 32u))) {
+            const uint32_t cnt = min(n_free, 32u);
+            const bool mine = lane < cnt;
+            const uint32_t my_slot = mine ? (uint32_t)l_free[n_free - 1u - lane] : 0u;
+            n_free -= cnt;
+            __syncwarp();
+            // claim cnt frame slots (warp-uniform bookkeeping, like the dynamic fetch of k_wf_trace)
+            uint32_t my_idx = 0xffffffffu, served = 0;
+            while (served < cnt && !exhausted) {
+                if (pool_next >= pool_end) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(wl.cursor, (uint32_t)tune.wl_batch);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= n_region_slots) { exhausted = true; break; }
+                    pool_next = base;
+                    pool_end = min(base + (uint32_t)tune.wl_batch, n_region_slots);
+                }
+                const uint32_t take = min(cnt - served, pool_end - pool_next);
+                if (mine && lane >= served && lane < served + take) my_idx = pool_next + (lane - served);
+                pool_next += take;
+                served += take;
+            }
+            bool valid = false, retry = false;
+            if (my_idx != 0xffffffffu) {
+                const uint32_t p = swizzled_pixel(my_idx, fc, valid);
+                if (valid) {
+                    const uint32_t x = p % fc.width, y = p / fc.width;
+                    uint32_t rng = tea(p, fc.frame);                       // pathtrace.rgen:47
+                    const float jx = next_rand(rng), jy = next_rand(rng);  // :52
+                    const float3 d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                    const size_t gs = slot_base + my_slot;
+                    wl.ray_o[gs] = make_float4(fc.origin.x, fc.origin.y, fc.origin.z, __uint_as_float(p));
+                    wl.ray_d[gs] = make_float4(d.x, d.y, d.z, 0.0f);
+                    wl.thr[gs] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+                    wl.pix[gs] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(rng));
+                    np++;
+                } else {
+                    retry = true;  // a hole of the tile order (image edge): the slot stays free
+                }
+            }
+            wl_push(l_ready, n_ready, valid, my_slot, lt_mask);
+            wl_push(l_free, n_free, retry, my_slot, lt_mask);
+            if (exhausted) n_free = 0u;  // nothing left to start: free slots are retired
+            __syncwarp();
+        }
+        // ---- shade: 32 finished rays, one per lane (k_wf_shade + k_wf_resolve) ----
+        if (n_shade >= 32u || (n_shade > 0u && n_ready == 0u && n_idle >= (uint32_t)tune.wl_fetch_idle)) {
+            const uint32_t cnt = min(n_shade, 32u);
+            const bool mine = lane < cnt;
+            const uint32_t my_slot = mine ? (uint32_t)l_shade[n_shade - 1u - lane] : 0u;
+            n_shade -= cnt;
+            __syncwarp();
+            bool alive = false, freed = false;
+            if (mine) {
+                const size_t gs = slot_base + my_slot;
+                const uint4 h = wl.hit[gs];
+                const float4 t4 = wl.thr[gs], x4 = wl.pix[gs], d4 = wl.ray_d[gs];
+                const uint32_t p = __float_as_uint(wl.ray_o[gs].w);
+                float3 thr = f3(t4.x, t4.y, t4.z), pixel = f3(x4.x, x4.y, x4.z);
+                const uint32_t ds = __float_as_uint(t4.w);
+                uint32_t rng = __float_as_uint(x4.w), depth = ds & 0xffffu, sample = ds >> 16;
+                float3 o = f3(0, 0, 0), d = f3(d4.x, d4.y, d4.z);
+                bool end_path;
+                if (h.x != SOLB_MISS) {
+                    nh++;
+                    float3 hv;
+                    const bool done = shade_hit(instances, shade, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
+                    depth++;
+                    thr = thr * hv;  // pathtrace.rgen:77
+                    end_path = done;
+                    if (!done && depth > fc.max_bounces) { thr = f3(0, 0, 0); end_path = true; }  // :81-84
+                } else {
+                    thr = thr * shade_miss(fc.enable_sky, d);
+                    end_path = true;
+                }
+                alive = true;
+                if (end_path) {
+                    pixel = pixel + thr;  // :86
+                    sample++;
+                    if (sample < fc.spp) {
+                        const uint32_t x = p % fc.width, y = p / fc.width;
+                        const float jx = next_rand(rng), jy = next_rand(rng);
+                        o = fc.origin;
+                        d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                        thr = f3(1, 1, 1);
+                        depth = 0;
+                        np++;
+                    } else {
+                        alive = false;
+                        freed = true;
+                        uint32_t rgba;  // pathtrace.rgen:88-103
+                        const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
+                        accum[p] = out;
+                        if (render) render[p] = rgba;
+                    }
+                }
+                if (alive) {
+                    wl.ray_o[gs] = make_float4(o.x, o.y, o.z, __uint_as_float(p));
+                    wl.ray_d[gs] = make_float4(d.x, d.y, d.z, 0.0f);
+                    wl.thr[gs] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(depth | (sample << 16)));
+                    wl.pix[gs] = make_float4(pixel.x, pixel.y, pixel.z, __uint_as_float(rng));
+                }
+            }
+            wl_push(l_ready, n_ready, alive, my_slot, lt_mask);
+            if (!exhausted) wl_push(l_free, n_free, freed, my_slot, lt_mask);
+            __syncwarp();
+        }
+        // ---- hand ready slots to idle lanes ----
+        if (n_ready > 0u && n_idle >= (uint32_t)tune.wl_fetch_idle) {
+            const uint32_t rank = (uint32_t)__popc(~b_ray & lt_mask);
+            const uint32_t cnt = min(n_ready, n_idle);
+            if (!has_ray && rank < cnt) {
+                slot = (uint32_t)l_ready[n_ready - 1u - rank];
+                const size_t gs = slot_base + slot;
+                const float4 o = wl.ray_o[gs], d = wl.ray_d[gs];
+                tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
+                tmax = fc.tmax;
+                hit.inst = SOLB_MISS; hit.gtri = SOLB_MISS; hit.u = 0.0f; hit.v = 0.0f;
+                ngroup = SOLB_ROOT_GROUP;
+                tgroup = make_uint2(0u, 0u);
+                stack.sp = 0;
+                in_blas = false;
+                has_ray = true;
+                nr++;
+            }
+            n_ready -= cnt;
+            b_ray = __ballot_sync(0xffffffffu, has_ray);
+            __syncwarp();
+        }
+        if (b_ray == 0u) {
+            if (n_ready == 0u && n_shade == 0u && (exhausted || n_free == 0u)) break;
+            continue;
+        }
+        // ---- vote: node step or triangle step (k_wf_trace) ----
+        const bool w_node = has_ray && (ngroup.y & 0xff000000u);
+        const bool w_tri = has_ray && tgroup.y;
+        const uint32_t b_node = __ballot_sync(0xffffffffu, w_node), b_tri = __ballot_sync(0xffffffffu, w_tri);
+        const int nn = __popc(b_node), nt = __popc(b_tri);
+        if (nt > 0 && nt * tune.tri_weight >= nn * tune.node_weight) {
+            if (w_tri) {
+                if (TL && !in_blas) {
+                    trav_enter_instance(inst_leaves, tr.o, tr.d, tr, ngroup, tgroup, cur_inst, stack);
+                    in_blas = true;
+                } else {
+                    if (trav_tri_step(tris, tr, tmax, tgroup, hit) && TL) hit.inst = cur_inst;
+                    if (STATS) ctr.tris++;
+                }
+            }
+        } else if (w_node) {
+            if (tgroup.y) stack.push(tgroup);  // postpone the pending triangles
+            trav_node_step(nodes, tr, tmax, ngroup, tgroup, stack);
+            if (STATS) ctr.nodes++;
+        }
+        // ---- lanes with nothing in hand: pop, or finish the ray ----
+        bool finished = false;
+        if (has_ray && !(ngroup.y & 0xff000000u) && !tgroup.y) {
+            if (stack.empty()) {
+                wl.hit[slot_base + slot] = make_uint4(hit.inst, hit.gtri, __float_as_uint(hit.u), __float_as_uint(hit.v));
+                has_ray = false;
+                finished = true;
+            } else {
+                const uint2 e = stack.pop();
+                if (TL && e.y == 0u) {  // sentinel: back to the TLAS with the world-space ray
+                    const float4 o = wl.ray_o[slot_base + slot], d = wl.ray_d[slot_base + slot];
+                    tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
+                    in_blas = false;
+                } else if (e.y & 0xff000000u) ngroup = e;
+                else tgroup = e;
+            }
+        }
+        const uint32_t b_fin = __ballot_sync(0xffffffffu, finished);
+        if (b_fin) {
+            if (finished) l_shade[n_shade + __popc(b_fin & lt_mask)] = (uint8_t)slot;
+            n_shade += (uint32_t)__popc(b_fin);
+            b_ray &= ~b_fin;
+            __syncwarp();
+        }
+    }
+    warp_add_stat(stats, ST_RAYS, nr);
+    warp_add_stat(stats, ST_HITS, nh);
+    warp_add_stat(stats, ST_PATHS, np);
+    if (STATS) {
+        warp_add_stat(stats, ST_NODES, ctr.nodes);
+        warp_add_stat(stats, ST_TRIS, ctr.tris);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // 4-ray-ao: ao.rgen:37-83 + ao.rchit:45-88 + ao.rmiss:7-10, one thread per pixel
 // The sample loop (ao.rgen:47-75) and the chained-ray loop (ao.rgen:56-72) are flattened into one loop so that, with VOTE, the
 // whole warp can step its traversals together (trace_vote); per-pixel arithmetic and RNG order are those of the nested loops.
@@ -1293,6 +1537,29 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
         if ((err = cudaEventRecord(L.join[k], L.stream[k])) != cudaSuccess) return err;
         if ((err = cudaStreamWaitEvent(L.stream[0], L.join[k], 0)) != cudaSuccess) return err;
     }
+    return cudaGetLastError();
+}
+
+uint32_t warpfront_grid_warps(int sm_count, const TraceTuning &tune) {
+    return (uint32_t)(sm_count * tune.wl_ctas_per_sm * (TRACE_BLOCK / 32));
+}
+
+// One reference frame with the warp-local wavefront schedule: a cursor reset and ONE launch.
+cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
+                                       const ShadeRecord *shade, const WarpfrontState &wl, float4 *accum, uint32_t *render,
+                                       unsigned long long *stats, bool collect, int sm_count, const TraceTuning &tune) {
+    if (fc.width == 0 || fc.band_rows == 0 || fc.n_bands == 0) return cudaSuccess;
+    const uint32_t n_slots = ((fc.width + 7u) >> 3) * region_tiles_y(fc) * 32u;
+    cudaError_t err = cudaMemsetAsync(wl.cursor, 0, sizeof(uint32_t), st);
+    if (err != cudaSuccess) return err;
+    // small regions (a rank's share of a tile-split frame, tiny images): no more warps than 8x4 tiles
+    const uint32_t want_warps = std::min<uint32_t>(std::min(warpfront_grid_warps(sm_count, tune), wl.n_warps), std::max<uint32_t>(1u, n_slots / 32u));
+    const uint32_t grid = (want_warps + TRACE_BLOCK / 32 - 1) / (TRACE_BLOCK / 32);
+    const float4 *il = as.inst_leaves_f4();
+#define SOLB_WLF(S, T) k_pt_warpfront<S, T><<<grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, wl, accum, render, stats, n_slots, tune)
+    if (as.two_level) { if (collect) SOLB_WLF(true, true); else SOLB_WLF(false, true); }
+    else { if (collect) SOLB_WLF(true, false); else SOLB_WLF(false, false); }
+#undef SOLB_WLF
     return cudaGetLastError();
 }
 

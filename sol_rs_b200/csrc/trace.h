@@ -58,6 +58,28 @@ struct TraceTuning {
                                // 9 001 -> 8 025 (gpurun_out/mega_vote.log), so the vote is used above 8 wide nodes
     int mega_ctas_per_sm = 6;  // its persistent CTAs per SM (80 registers -> 6 x 128 threads)
     int mega_fetch_idle = 8;   // refill finished lanes once this many are idle
+    // warp-local wavefront schedule (k_pt_warpfront)
+    int wl_ctas_per_sm = 8;    // persistent CTAs per SM (64 registers -> 8 x 128 threads)
+    int wl_fetch_idle = 8;     // hand ready rays to idle lanes once this many lanes are idle
+    int wl_gen_min = 16;       // start new pixels once this many of a warp's slots are free (or its lanes starve)
+    int wl_batch = 32;         // pixels a warp takes from the frame's cursor per atomic (one 8x4 tile)
+};
+
+// Warp-local wavefront state: every warp of the persistent grid owns WL_POOL pixel slots, indexed warp * WL_POOL + slot.
+// Same per-path record as WavefrontState, but sized by the grid (148 SMs x 8 CTAs x 4 warps x 96 slots x 80 B = 36 MB), not
+// by the image, so it stays L2-resident whatever the resolution.
+#ifndef SOLB_WL_POOL
+#define SOLB_WL_POOL 96
+#endif
+constexpr int WL_POOL = SOLB_WL_POOL;
+struct WarpfrontState {
+    float4 *ray_o;      // xyz origin of the ray in flight, w = bits(pixel id)
+    float4 *ray_d;      // xyz direction
+    float4 *thr;        // xyz throughput, w = bits(depth | sample << 16)
+    float4 *pix;        // xyz sum of finished samples, w = bits(prd.rng)
+    uint4 *hit;         // instance, global triangle, bits(u), bits(v)
+    uint32_t *cursor;   // next pixel slot of the frame (tile order), one counter per launch
+    uint32_t n_warps;   // capacity in warps
 };
 
 constexpr int WF_MAX_PARTS = 4;
@@ -88,6 +110,10 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
 cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
                       unsigned long long *stats, const TraceTuning &tune);
+cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
+                                       const ShadeRecord *shade, const WarpfrontState &wl, float4 *accum, uint32_t *render,
+                                       unsigned long long *stats, bool collect, int sm_count, const TraceTuning &tune);
+uint32_t warpfront_grid_warps(int sm_count, const TraceTuning &tune);
 size_t pool_spill_bytes(int sm_count, const TraceTuning &tune);
 cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n);
 

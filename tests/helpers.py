@@ -185,3 +185,28 @@ def write_instanced_gltf(gltf_path, out_path):
     with open(out_path, "w") as f:
         json.dump(doc, f)
     return out_path
+
+
+def flat_from_product_scene(sc):
+    """gltf_flatten.FlatScene (what the oracle consumes) from a sol_rs_b200.scene.Scene built in memory (synth.make_scene):
+    meshes x sections -> instances in the reference's order (src/ray/mod.rs:78-134), buffers concatenated."""
+    fs = gf.FlatScene()
+    verts, inds = [], []
+    nv, ni = 0, 0
+    for mi, m in enumerate(sc.meshes):
+        secs = []
+        for s_ in m.primitive_sections:
+            secs.append(dict(first_vertex=nv + s_.first_vertex, n_vertices=s_.n_vertices, first_index=ni + s_.first_index,
+                             n_indices=s_.n_indices, material=s_.material_index))
+        t = np.asarray(m.transform, dtype=np.float32).reshape(4, 4)
+        fs.meshes.append(dict(name=m.name, transform=t, sections=secs))
+        verts.append(m.vertices)
+        inds.append(m.indices)
+        nv += m.vertices.shape[0]
+        ni += m.indices.shape[0]
+        for sec in secs:
+            fs.instances.append(dict(mesh=mi, transform=t, **sec))
+    fs.vertices = np.concatenate(verts, axis=0)
+    fs.indices = np.concatenate(inds)
+    fs.materials = np.ascontiguousarray(sc.materials, dtype=np.float32).reshape(-1, 12)
+    return fs

@@ -8,8 +8,8 @@ import pytest
 import oracle
 from oracle import camera as ocam
 
-from helpers import (image_metrics, load_blue_noise, model_path, oracle_camera, oracle_scene, pathtrace_pipeline,
-                     product_camera, simple_pipeline)
+from helpers import (flat_from_product_scene, image_metrics, load_blue_noise, model_path, oracle_camera, oracle_scene,
+                     pathtrace_pipeline, product_camera, simple_pipeline)
 
 pytestmark = pytest.mark.gpu
 
@@ -71,8 +71,14 @@ def _walk_accel(nodes, tris):
             if not inner and tmask == 0:
                 continue
             lo, hi = child_box(node, i)
-            if plo is not None:  # child boxes are allowed to poke out of the parent's quantised box only by rounding
-                pass
+            if plo is not None:
+                # parent's box for this node >= the node's own child boxes: both are conservative roundings of the same true
+                # bounds, so a child box may poke out of the parent's box by at most the node's own quantisation cells
+                cell = np.array([2.0 ** (((int(w[3]) >> (8 * a)) & 0xFF) - 127) for a in range(3)], dtype=np.float64)
+                slack = 2.0 * cell + 1e-6 * (1.0 + np.abs(plo) + np.abs(phi))
+                assert np.all(lo >= plo - slack) and np.all(hi <= phi + slack), \
+                    "child box of node %d slot %d outside its parent's box: %s %s vs %s %s" % (node, i, lo, hi, plo, phi)
+                assert np.all(hi >= lo)
             if inner:
                 assert tmask == 0
                 rel = bin(imask & ((1 << i) - 1)).count("1")
@@ -207,7 +213,7 @@ def _render_oracle(name, w, h, frames, sky, spp, mb, start=0):
     return acc, rgba, st
 
 
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 3])
 @pytest.mark.parametrize("name,w,h,sky,mb", [("cornell", 128, 128, False, 32), ("cornell", 96, 64, False, 4),
                                              ("tunnel", 160, 90, True, 32), ("tunnel", 160, 90, True, 8)])
 def test_pathtrace_frames_vs_oracle(sol, ctx, name, w, h, sky, mb, schedule):
@@ -235,6 +241,30 @@ def test_wavefront_equals_megakernel(sol, ctx):
     # few decision-flip pixels are expected
     assert (d.max(axis=2) > 1e-4 * (1 + np.abs(b[..., :3]).max(axis=2))).mean() < 0.01
     assert d.sum() / b[..., :3].sum() < 2e-3
+
+
+@pytest.mark.parametrize("name,w,h,sky,mb,two_level", [("tunnel", 256, 144, True, 8, False), ("tunnel", 1920, 1080, True, 8, False),
+                                                       ("cornell", 200, 120, False, 32, False), ("Duck", 160, 120, True, 8, True),
+                                                       ("tunnel", 192, 108, True, 8, True)])
+def test_warpfront_equals_wavefront(sol, ctx, name, w, h, sky, mb, two_level):
+    """The warp-local wavefront kernel (schedule 3) runs the per-ray / per-pixel functions of the queue-based wavefront
+    (k_wf_generate / k_wf_trace / k_wf_shade / k_wf_resolve) in a different order only: same rays, same paths, and the same
+    image up to decision-flip pixels (separately compiled instantiations: FMA contraction and the order of equal-t tests)."""
+    ctx.reset_stats()
+    a, ra = _render_gpu(sol, ctx, name, w, h, [0, 1, 2], sky, 8, mb, 0, two_level=two_level)
+    s0 = ctx.stats()
+    ctx.reset_stats()
+    b, rb = _render_gpu(sol, ctx, name, w, h, [0, 1, 2], sky, 8, mb, 3, two_level=two_level)
+    s1 = ctx.stats()
+    assert s0.paths == s1.paths == 3 * 8 * w * h
+    assert abs(int(s0.rays) - int(s1.rays)) <= 1e-4 * int(s0.rays) + 2
+    d = np.abs(a - b)[..., :3]
+    assert (d.max(axis=2) > 1e-4 * (1 + np.abs(b[..., :3]).max(axis=2))).mean() < 0.01
+    assert d.sum() / b[..., :3].sum() < 2e-3
+    assert np.all(b[..., 3] == 1.0) and np.all(np.isfinite(b))
+    # and it is a pure function of its inputs: a second run gives the same bits although slot order and atomics vary
+    c, rc = _render_gpu(sol, ctx, name, w, h, [0, 1, 2], sky, 8, mb, 3, two_level=two_level)
+    assert np.array_equal(b, c) and np.array_equal(rb, rc)
 
 
 def test_accumulation_restart_and_alpha(sol, ctx):
@@ -392,7 +422,7 @@ GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("name,w,h,sky,mb", [("tunnel", 160, 90, True, 8), ("cornell", 96, 96, False, 32)])
-@pytest.mark.parametrize("schedule,two_level", [(0, False), (1, False), (0, True)])
+@pytest.mark.parametrize("schedule,two_level", [(0, False), (1, False), (0, True), (3, False), (3, True)])
 def test_converged_image_vs_golden(sol, ctx, name, w, h, sky, mb, schedule, two_level):
     """512 frames x 8 spp = 4096 spp: mean relative error < 1 % and PSNR > 40 dB (BASELINE.json north_star)."""
     g = np.load(_os.path.join(GOLDEN, "converged_%s_%dx%d_4096spp_b%d.npz" % (name, w, h, mb)))
@@ -623,7 +653,7 @@ def test_two_level_shared_blas_instances(sol, ctx):
     assert flat.n_triangles == 4 * 4212 and flat.n_wide_nodes > 3 * (two.n_wide_nodes - two.n_instances)
 
 
-@pytest.mark.parametrize("schedule", ["wavefront", "megakernel"])
+@pytest.mark.parametrize("schedule", ["wavefront", "megakernel", "warpfront"])
 @pytest.mark.parametrize("name,w,h,sky,mb", [("cornell", 128, 128, False, 32), ("tunnel", 192, 108, True, 8)])
 def test_two_level_pathtrace_matches_oracle(sol, ctx, name, w, h, sky, mb, schedule):
     from sol_rs_b200 import _native as N
@@ -636,7 +666,8 @@ def test_two_level_pathtrace_matches_oracle(sol, ctx, name, w, h, sky, mb, sched
     ctx.reset_stats()
     for f in range(2):
         sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, None, samples_per_frame=8, max_bounces=mb,
-                                             schedule=N.SCHEDULE_WAVEFRONT if schedule == "wavefront" else N.SCHEDULE_MEGAKERNEL,
+                                             schedule={"wavefront": N.SCHEDULE_WAVEFRONT, "megakernel": N.SCHEDULE_MEGAKERNEL,
+                                                       "warpfront": N.SCHEDULE_WARPFRONT}[schedule],
                                              collect_stats=True), (w, h, 1))
     st = ctx.stats()
     o_acc, _, o_st = _render_oracle(name, w, h, range(2), sky, 8, mb)
@@ -882,6 +913,13 @@ def test_full_size_determinism_and_tile_split(sol, ctx, w, h):
     for band in (4, 6):
         a5, r5, rays5, paths5 = render([(r * band, band, 3 * band) for r in range(3)])
         assert np.array_equal(a0, a5) and np.array_equal(r0, r5) and rays0 == rays5 and paths0 == paths5
+    # the warp-local wavefront schedule: deterministic, tile union == undivided frame (contiguous ragged and interleaved bands)
+    a7, r7, rays7, paths7 = render([None], N.SCHEDULE_WARPFRONT)
+    a8, r8, rays8, paths8 = render(tiles, N.SCHEDULE_WARPFRONT)
+    a9, r9, rays9, paths9 = render([(r * 6, 6, 18) for r in (2, 0, 1)], N.SCHEDULE_WARPFRONT)
+    assert np.array_equal(a7, a8) and np.array_equal(r7, r8) and rays7 == rays8 and paths7 == paths8 == paths0
+    assert np.array_equal(a7, a9) and np.array_equal(r7, r9) and rays7 == rays9
+    assert abs(rays7 - rays0) <= 1e-4 * rays0
     if w == 1920:
         a6, r6, rays6, _ = render([(r * 8, 8, 16) for r in (1, 0)], N.SCHEDULE_MEGAKERNEL)
         a3, r3, rays3, _ = render(tiles[::-1], N.SCHEDULE_MEGAKERNEL)
@@ -894,7 +932,7 @@ def test_full_size_determinism_and_tile_split(sol, ctx, w, h):
         render([(0, 8, 4)])  # bands would overlap
 
 
-@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("schedule", [0, 1, 3])
 @pytest.mark.parametrize("w,h,spp,mb,frame,start", [(1, 1, 8, 32, 0, 0), (3, 5, 8, 32, 0, 0), (9, 7, 1, 32, 7, 7), (37, 21, 3, 0, 2, 0),
                                                      (64, 33, 8, 1, 0x7FFFFFF0, 0x7FFFFFF0), (130, 70, 16, 4, 1000003, 1000000)])
 def test_ragged_sizes_and_extreme_parameters(sol, ctx, w, h, spp, mb, frame, start, schedule):
@@ -987,3 +1025,122 @@ def test_experimental_schedules_still_agree(sol, env, schedule):
     d = np.abs(img - ref)[..., :3]
     assert (d.max(axis=2) > 1e-4 * (1 + np.abs(ref[..., :3]).max(axis=2))).mean() < 0.01, str(env)
     assert d.sum() / ref[..., :3].sum() < 2e-3, str(env)
+
+
+# ---- BASELINE.json sizes against the oracle (configs[0] in full; one full 1080p frame of configs[2]) -------------------------
+
+@pytest.mark.parametrize("schedule", [1, 3])
+def test_config0_cornell_512_64spp_cap4_vs_oracle(sol, ctx, schedule):
+    """BASELINE.json configs[0] exactly: cornell.gltf 512 x 512, frames 0..7 (64 accumulated spp), bounce cap 4."""
+    w = h = 512
+    ctx.reset_stats()
+    g_acc, g_rgba = _render_gpu(sol, ctx, "cornell", w, h, range(8), False, 8, 4, schedule)
+    gs = ctx.stats()
+    o_acc, o_rgba, st = _render_oracle("cornell", w, h, range(8), False, 8, 4)
+    assert gs.paths == st.paths == w * h * 64
+    assert abs(int(gs.rays) - int(st.rays)) <= 0.002 * st.rays
+    d = np.abs(g_acc[..., :3] - o_acc[..., :3])
+    # 64 samples per pixel: one decision flip moves a pixel by ~1/64 of a sample's colour, so count pixels that moved at all
+    assert (d.max(axis=2) > 1e-3 * (1.0 + np.abs(o_acc[..., :3]).max(axis=2))).mean() < 0.05
+    mre, psnr = image_metrics(g_acc, o_acc)
+    assert mre < 0.002 and psnr > 50.0, (mre, psnr)
+    assert (np.abs(g_rgba.astype(np.int32) - o_rgba.astype(np.int32)).max(axis=2) > 1).mean() < 0.01
+
+
+@pytest.mark.parametrize("schedule", [0, 3])
+def test_config2_tunnel_1080p_frame_vs_oracle(sol, ctx, schedule):
+    """One full frame of the headline workload (tunnel.gltf --sky 1920 x 1080, 8 spp, bounce cap 8) against the oracle:
+    same path count, same ray count within 0.1 %, per-pixel agreement except decision-flip pixels."""
+    w, h = 1920, 1080
+    ctx.reset_stats()
+    g_acc, g_rgba = _render_gpu(sol, ctx, "tunnel", w, h, [0], True, 8, 8, schedule)
+    gs = ctx.stats()
+    o_acc, o_rgba, st = _render_oracle("tunnel", w, h, [0], True, 8, 8)
+    assert gs.paths == st.paths == w * h * 8
+    assert abs(int(gs.rays) - int(st.rays)) <= 0.001 * st.rays
+    d = np.abs(g_acc[..., :3] - o_acc[..., :3])
+    assert (d.max(axis=2) > 1e-3 * (1.0 + np.abs(o_acc[..., :3]).max(axis=2))).mean() < 0.02
+    mre, _ = image_metrics(g_acc, o_acc)
+    assert mre < 0.01, mre
+    assert (np.abs(g_rgba.astype(np.int32) - o_rgba.astype(np.int32)).max(axis=2) > 1).mean() < 0.02
+
+
+# ---- synthetic instanced scene (BASELINE.json configs[4] at 27 BLAS x 20 000 triangles) -------------------------------------
+
+@pytest.fixture(scope="module")
+def synth27():
+    from sol_rs_b200 import synth
+
+    sc = synth.make_scene(27, 100)
+    fs = flat_from_product_scene(sc)
+    return sc, fs, oracle.Scene(fs)
+
+
+@pytest.mark.parametrize("accel", ["flat", "two_level"])
+def test_synth_scene_rays_and_primary_ids_vs_oracle(sol, ctx, synth27, accel):
+    """sol_rs_b200.synth (the generator of the 20 M-triangle config) at 27 x 20 000 = 540 000 triangles, the deepest hierarchy
+    any test walks: 10^6 incoherent rays and the primary hit ids of its camera, flattened and two-level, against the oracle."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    sc, fs, osc = synth27
+    assert osc.tri_count == 27 * 20000
+    sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=N.ACCEL_TWO_LEVEL if accel == "two_level" else N.ACCEL_FLAT)
+    info = sd.accel_info()
+    assert info.n_triangles == osc.tri_count and info.n_instances == 27
+    rng = np.random.default_rng(5)
+    n = 1_000_000
+    lo, hi = osc.bounds()
+    o = rng.uniform(lo - 1.0, hi + 1.0, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+    g_hits, g_t = sd.trace_rays(rays)
+    o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
+    mism = np.any(g_hits[:, :2] != o_hits[:, :2], axis=1)
+    assert (mism & (flags == 0)).sum() == 0, "%d unlisted rays differ" % (mism & (flags == 0)).sum()
+    assert (flags != 0).mean() < 0.01
+    ok = ~mism & (o_hits[:, 0] != oracle.MISS)
+    assert ok.mean() > 0.2
+    np.testing.assert_allclose(g_t[ok], o_t[ok], rtol=1e-4, atol=5e-4)
+    # primary ids through the debug pipeline with the scene's own camera
+    w, h = 960, 540
+    cam = sc.camera
+    cam.set_window_size((w, h))
+    u = scene.scene_uniforms(cam, w, h, 0)
+    o_rgba, o_ids, o_bt, o_flags = osc.debug(bytes(u), w, h)
+    ids = sol.Image2d(ctx, w, h, N.FORMAT_RG32UI)
+    simple_pipeline(ctx, "debug").cmd_trace_rays(ray.TraceBindings(sd, u, None, None, ids), (w, h, 1))
+    g_ids = ids.readback()
+    mism = np.any(g_ids != o_ids, axis=2)
+    assert (mism & (o_flags == 0)).sum() == 0
+    assert (o_flags != 0).mean() < 0.01 and (o_ids[..., 0] != oracle.MISS).mean() > 0.3
+
+
+@pytest.mark.parametrize("schedule", [0, 1, 3])
+def test_synth_scene_pathtrace_frame_vs_oracle(sol, ctx, synth27, schedule):
+    """One path-traced frame of the synthetic scene (sky on, 8 spp, bounce cap 8: diffuse, rough-metal and emissive materials)."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    sc, fs, osc = synth27
+    w, h = 320, 180
+    sd = ray.SceneDescription.from_scene(ctx, sc)
+    cam = sc.camera
+    cam.set_window_size((w, h))
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    sbt = pathtrace_pipeline(ctx, True)
+    ref = np.zeros((h, w, 4), np.float32)
+    st = oracle.OrcStats()
+    ctx.reset_stats()
+    for f in range(2):
+        u = scene.scene_uniforms(cam, w, h, f)
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, None, samples_per_frame=8, max_bounces=8, schedule=schedule), (w, h, 1))
+        osc.pathtrace_frame(bytes(u), w, h, ref, 0, True, 8, 8, st)
+    gs = ctx.stats()
+    assert gs.paths == st.paths == 2 * 8 * w * h
+    assert abs(int(gs.rays) - int(st.rays)) <= 0.003 * st.rays
+    g = accum.readback()
+    d = np.abs(g[..., :3] - ref[..., :3])
+    assert (d.max(axis=2) > 1e-3 * (1.0 + np.abs(ref[..., :3]).max(axis=2))).mean() < 0.03
+    mre, _ = image_metrics(g, ref)
+    assert mre < 0.02, mre
