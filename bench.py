@@ -7,7 +7,12 @@ tunnel.gltf --sky at 1920x1080 with max_bounces = 8 (BASELINE.json configs[2]); 
 traceRayEXT-equivalent (traversal + its hit/miss shading).  cornell.gltf at the same size is reported
 beside it in "extra".  One JSON line on stdout (rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--schedule wavefront|megakernel]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--schedule auto|warpfront|wavefront|megakernel]
+
+The JSON line's `extra` holds, at N = 1, the other BASELINE.json configs each with its own roofline (cornell 1080p, configs[1]
+4-ray-ao, configs[3] 4K, configs[4] synthetic 20 M triangles incl. its BVH build) and, at N > 1, the tile split of single frames
+(`extra.tile_split`).  The multi-GPU exchange runs through the C ABI (solb_reduce_accum / solb_allgather_rows, NCCL underneath);
+torch.distributed only bootstraps the communicator id, provides the barriers and gathers the per-rank timings.
 """
 import argparse
 import json
@@ -115,13 +120,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))  # bounded: ~1.6 s per sample frame on 16 host threads, ~6 s on 8
+    steps = max(1, min(args.steps, 64))  # one step = one frame of the bounded sample: ~1.6 s on 16 host threads
     cb = cpu_reference_arm(steps, min(args.warmup, 1), (CPU_SAMPLE_W, CPU_SAMPLE_H))
     line = {"impl": "reference", "metric": "Mrays/s", "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference GLSL/driver path cannot run here (no rustc/Vulkan/lavapipe); "
-                       "this arm times the CPU oracle port on a bounded sample"},
+            "config": {"workload": WORKLOAD, "sample": "%dx%d pixels of the %dx%d frame per step" % (CPU_SAMPLE_W, CPU_SAMPLE_H, WIDTH, HEIGHT),
+                       "note": "reference GLSL/driver path cannot run here (no rustc/Vulkan/lavapipe); "
+                       "this arm times the CPU oracle port (oracle/oracle.c, OpenMP) on a bounded sample of every frame"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -157,15 +163,16 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="solb")
-    ap.add_argument("--schedule", default=os.environ.get("SOLB_SCHEDULE", "wavefront"))
+    ap.add_argument("--schedule", default=os.environ.get("SOLB_SCHEDULE", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extra", action="store_true", help="also bench cornell and the other schedule")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs in `extra`")
+    ap.add_argument("--extra", action="store_true", help="also bench the other schedules on tunnel and cornell")
     ap.add_argument("--workload", default="tunnel", choices=["tunnel", "synth"],
                     help="tunnel = the headline config; synth = BASELINE configs[4]: synthetic instanced scene (--blas x 20000 triangles)")
     ap.add_argument("--blas", type=int, default=1000)
     ap.add_argument("--split", default="frames", choices=["frames", "tiles"],
-                    help="multi-GPU split: frames = rank r renders frames f = r (mod N), one NCCL reduce at the end (default); tiles = "
-                         "every frame is cut into N row tiles, one all-gather of the accumulation rows per frame (single-sample mode)")
+                    help="multi-GPU split of the headline value: frames = rank r renders frames f = r (mod N), one NCCL reduce at the end "
+                         "(default); tiles = every frame is cut into N sets of row bands, one all-gather per frame")
     ap.add_argument("--accel", default="flat", choices=["flat", "two_level"],
                     help="flat = transforms baked into one hierarchy (default); two_level = TLAS over object-space BLASes")
     ap.add_argument("--size", default="", help="WxH override, e.g. 3840x2160 for BASELINE configs[3] (default 1920x1080)")
@@ -181,6 +188,7 @@ def main():
 
     import sol_rs_b200 as sol
     from sol_rs_b200 import _native as N
+    from sol_rs_b200 import io as sol_io
     from sol_rs_b200 import multigpu, ray, scene
 
     rank = int(os.environ.get("RANK", "0"))
@@ -190,133 +198,107 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libsolb has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
-    if world > 1:
-        # NCCL prints its version banner (NCCL_DEBUG >= VERSION) on stdout, which must carry exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # a real (non-default) torch stream, made current: libsolb launches on it, torch events time it, NCCL orders with it
+    # a real (non-default) torch stream, made current: libsolb launches on it, torch events time it, NCCL runs on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx = sol.Context(local_rank, stream.cuda_stream)
+    comm = None
+    if world > 1:
+        # NCCL prints its version banner (NCCL_DEBUG >= VERSION) on stdout, which must carry exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = multigpu.Communicator.from_torch_distributed(ctx)  # the path's exchange: libsolb's own communicator (C ABI)
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
-    sched = {"mega": N.SCHEDULE_MEGAKERNEL, "wave": N.SCHEDULE_WAVEFRONT, "warp": N.SCHEDULE_WARPFRONT}[args.schedule[:4]]
-    sched_name = {N.SCHEDULE_MEGAKERNEL: "megakernel", N.SCHEDULE_WAVEFRONT: "wavefront", N.SCHEDULE_WARPFRONT: "warpfront"}[sched]
+    sched = {"mega": N.SCHEDULE_MEGAKERNEL, "wave": N.SCHEDULE_WAVEFRONT, "warp": N.SCHEDULE_WARPFRONT, "auto": N.SCHEDULE_AUTO}[args.schedule[:4]]
+    sched_names = {N.SCHEDULE_MEGAKERNEL: "megakernel", N.SCHEDULE_WAVEFRONT: "wavefront", N.SCHEDULE_WARPFRONT: "warpfront",
+                   N.SCHEDULE_AUTO: "auto"}
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    BAND = 8  # tile split: rows per band; rank r owns bands r, r + N, ... (interleaved: cheap and expensive rows are shared out)
 
-    def setup(model, sky):
+    def pt_sbt(sky):
+        pipe = ray.Pipeline(ctx, ray.PipelineInfo().shader("glsl/pathtrace.rgen", ray.RAYGEN_KHR)
+                            .shader("glsl/pathtrace.rmiss", ray.MISS_KHR).shader("glsl/pathtrace.rchit", ray.CLOSEST_HIT_KHR)
+                            .specialization([1 if sky else 0], 0))
+        return ray.ShaderBindingTable(ctx, pipe, ray.ShaderBindingTableInfo().raygen(0).miss(1).hitgroup(2))
+
+    def setup(model, sky, accel=None):
         if model == "synth":
             from sol_rs_b200 import synth
 
             sc = synth.make_scene(args.blas, 100)
         else:
             sc = scene.load_scene(ctx, os.path.join(ROOT, "assets", "models", model))
-        sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=N.ACCEL_TWO_LEVEL if args.accel == "two_level" else N.ACCEL_FLAT)
-        cam = sc.camera
-        cam.set_window_size((WIDTH, HEIGHT))
-        pipe = ray.Pipeline(ctx, ray.PipelineInfo().shader("glsl/pathtrace.rgen", ray.RAYGEN_KHR)
-                            .shader("glsl/pathtrace.rmiss", ray.MISS_KHR).shader("glsl/pathtrace.rchit", ray.CLOSEST_HIT_KHR)
-                            .specialization([1 if sky else 0], 0))
-        sbt = ray.ShaderBindingTable(ctx, pipe, ray.ShaderBindingTableInfo().raygen(0).miss(1).hitgroup(2))
-        return sc, sd, cam, sbt
+        two = (accel or args.accel) == "two_level"
+        sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=N.ACCEL_TWO_LEVEL if two else N.ACCEL_FLAT)
+        return sc, sd, sc.camera, pt_sbt(sky)
 
-    def device_timed(sd, cam, sbt, schedule, n_warm, n_steps, mode, frame0):
-        """K steps with inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between steps."""
-        accum = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA32F)
-        render = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA8)
-        tiled = dist is not None and args.split == "tiles"
-        if tiled:
-            return device_timed_tiles(sd, cam, sbt, schedule, n_warm, n_steps, frame0, accum, render)
-        frames = multigpu.frames_for_rank(rank, world, world * (n_warm + n_steps), first=frame0)  # f = r (mod R): SURVEY 8e
-        for f in frames[:n_warm]:
-            sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), accum, render, schedule=schedule,
-                                                 samples_per_frame=SPP, max_bounces=MAX_BOUNCES, accum_mode=mode), (WIDTH, HEIGHT, 1))
-        accum.clear()
-        ctx.reset_stats()
+    def resolved_schedule(sd, schedule):
+        if schedule != N.SCHEDULE_AUTO:
+            return schedule
+        auto_wide = N.SCHEDULE_WAVEFRONT if os.environ.get("SOLB_AUTO_SCHEDULE", "3") == "0" else N.SCHEDULE_WARPFRONT
+        return N.SCHEDULE_MEGAKERNEL if sd.accel_info().n_wide_nodes <= 8 else auto_wide
+
+    def barrier_sync():
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def device_timed(sd, cam, sbt, schedule, n_warm, n_steps, split, frame0, w=None, h=None, mb=None, trace_fn=None):
+        """K steps with inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between steps.
+        split: None (this GPU alone), "frames" (f = r mod N + one reduce + resolve at the end) or "tiles" (bands + all-gather)."""
+        w, h, mb = w or WIDTH, h or HEIGHT, MAX_BOUNCES if mb is None else mb
+        cam.set_window_size((w, h))
+        accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+        render = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+        n_ranks = world if split else 1
+        mode = N.ACCUM_SUM if split == "frames" and world > 1 else N.ACCUM_MIX
+        tile = multigpu.tile_rows_for_rank(rank, world, BAND) if split == "tiles" and world > 1 else None
+        if split == "frames":
+            frames = multigpu.frames_for_rank(rank, n_ranks, n_ranks * (n_warm + n_steps), first=frame0)  # f = r (mod R): SURVEY 8e
+        else:
+            frames = list(range(frame0, frame0 + n_warm + n_steps))
+
+        def one(f):
+            sd.tlas_regenerate()  # reference rebuilds the TLAS every frame (examples/5-pathtrace.rs:316); no-op when clean
+            if trace_fn:
+                trace_fn(f, accum)
+            else:
+                sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, render, schedule=schedule,
+                                                     samples_per_frame=SPP, max_bounces=mb, accum_mode=mode, tile_rows=tile), (w, h, 1))
+            if tile:
+                comm.allgather_rows(accum, BAND)  # every rank now holds the whole frame
+
+        for f in frames[:n_warm]:
+            one(f)
+        accum.clear()
+        ctx.reset_stats()
+        barrier_sync()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps + 1)]
         t_wall = time.perf_counter()
         for i, f in enumerate(frames[n_warm:]):
             l2_flush.fill_(i & 0xFF)  # > 126 MB L2, outside the per-step event pair
-            u = scene.scene_uniforms(cam, WIDTH, HEIGHT, f)
             evs[i][0].record(stream)
-            sd.tlas_regenerate()  # reference rebuilds the TLAS every frame (examples/5-pathtrace.rs:316); no-op when clean
-            sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, render, schedule=schedule, samples_per_frame=SPP,
-                                                 max_bounces=MAX_BOUNCES, accum_mode=mode), (WIDTH, HEIGHT, 1))
+            one(f)
             evs[i][1].record(stream)
         reduce_ms = 0.0
-        if dist:
+        if split == "frames" and world > 1:
             # the one real exchange of the path: sum the per-rank accumulation buffers over NVLink, resolve on rank 0
             evs[n_steps][0].record(stream)
-            multigpu.reduce_accum(accum.as_torch(), dst=0)
-            if rank == 0:
-                ray.resolve_sum(ctx, accum, accum, render)
+            comm.reduce_accum(accum, 0, accum, render)
             evs[n_steps][1].record(stream)
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
+        barrier_sync()
         wall = time.perf_counter() - t_wall
         step_ms = [a.elapsed_time(b) for a, b in evs[:n_steps]]
-        if dist:
+        if split == "frames" and world > 1:
             reduce_ms = evs[n_steps][0].elapsed_time(evs[n_steps][1])
         st = ctx.stats()
         return {"ms_total": sum(step_ms) + reduce_ms, "step_ms": step_ms, "reduce_ms": reduce_ms, "rays": int(st.rays),
                 "paths": int(st.paths), "hits": int(st.hits), "launches": int(st.kernel_launches), "wall_s": wall}
-
-    def device_timed_tiles(sd, cam, sbt, schedule, n_warm, n_steps, frame0, accum, render):
-        """Tile split (single-sample interactive mode): every rank traces rows [r H/N, (r+1) H/N) of EVERY frame into
-        the full-size targets, then one all-gather of the accumulation rows makes the frame whole on every rank."""
-        band = 8  # rows per band: rank r owns bands r, r + N, r + 2N, ... (interleaved: the image's cheap and expensive rows are
-        #           shared out evenly; contiguous tiles measured 10.6 ms at 8 GPUs, see DESIGN.md 6)
-        full = accum.as_torch()
-        n_bands = (HEIGHT + band - 1) // band
-        per_rank = (n_bands + world - 1) // world
-        rows_of = []
-        for r in range(world):
-            rows = [min(b * band + j, HEIGHT - 1) for b in range(r, n_bands, world) for j in range(band)]
-            rows += [rows[-1]] * (per_rank * band - len(rows))  # pad to a common size (duplicates rewrite the same row)
-            rows_of.append(torch.tensor(rows, dtype=torch.long, device="cuda"))
-        all_rows = torch.cat(rows_of)
-        gathered = torch.empty((world, per_rank * band, WIDTH, 4), dtype=torch.float32, device="cuda")
-        parts = list(gathered.unbind(0))
-
-        def one(f):
-            u = scene.scene_uniforms(cam, WIDTH, HEIGHT, f)
-            sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, render, schedule=schedule, samples_per_frame=SPP, max_bounces=MAX_BOUNCES,
-                                                 tile_rows=(rank * band, band, world * band)), (WIDTH, HEIGHT, 1))
-            mine = full.index_select(0, rows_of[rank])       # this rank's bands, compacted
-            dist.all_gather(parts, mine)
-            full.index_copy_(0, all_rows, gathered.view(-1, WIDTH, 4))  # every rank now holds the whole frame
-
-        for f in range(frame0, frame0 + n_warm):
-            one(f)
-        accum.clear()
-        ctx.reset_stats()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
-        t_wall = time.perf_counter()
-        for i in range(n_steps):
-            l2_flush.fill_(i & 0xFF)
-            evs[i][0].record(stream)
-            one(frame0 + n_warm + i)
-            evs[i][1].record(stream)
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t_wall
-        step_ms = [a.elapsed_time(b) for a, b in evs]
-        st = ctx.stats()
-        return {"ms_total": sum(step_ms), "step_ms": step_ms, "reduce_ms": 0.0, "rays": int(st.rays), "paths": int(st.paths),
-                "hits": int(st.hits), "launches": int(st.kernel_launches), "wall_s": wall}
 
     def gather_max_sum(ms_total, rays):
         if not dist:
@@ -327,138 +309,224 @@ def main():
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
         return float(t.item()), int(r.item())
 
+    def load_traffic(kernel, workload_key):
+        """dram bytes per launch from a committed `ncu --set full` capture of THIS kernel on THIS workload, else None"""
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                return json.load(f)[kernel][workload_key]["dram_bytes_per_launch"]
+        except Exception:
+            return None
+
+    def measure_roofline(sd, cam, sbt, schedule, w, h, mb, workload_key, timed_ms_per_frame=None):
+        """Instrumented pass (nodes / triangles per ray) + live per-launch timing of the dominant kernel (event pairs inside
+        libsolb, on the ctx stream).  Algorithmic bytes per ray: SURVEY 8d's formula with this run's counters."""
+        cam.set_window_size((w, h))
+        ctx.reset_stats()
+        accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, 0), accum, None, schedule=schedule,
+                                             samples_per_frame=SPP, max_bounces=mb, collect_stats=True), (w, h, 1))
+        st = ctx.stats()
+        n_node, n_tri = st.nodes_visited / st.rays, st.tris_tested / st.rays
+        p_hit, r_path = st.hits / st.rays, st.rays / st.paths
+        ctx.set_timing(True)
+        ctx.reset_stats()
+        for f in range(100, 103):
+            l2_flush.fill_(f & 0xFF)
+            sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, None, schedule=schedule,
+                                                 samples_per_frame=SPP, max_bounces=mb), (w, h, 1))
+        st2 = ctx.stats()
+        ctx.set_timing(False)
+        real = resolved_schedule(sd, schedule)
+        trace_only = 80 * n_node + 48 * n_tri + 36 + 16  # node + triangle fetches, ray record read (+ queue id), hit record write
+        whole_ray = 80 * n_node + 48 * n_tri + 96 + 32 + p_hit * 204 + 32.0 / (SPP * r_path)  # SURVEY 8d, whole step
+        if real == N.SCHEDULE_WAVEFRONT:
+            kernel, b_ray, scope = "k_wf_trace", trace_only, "traversal kernel only (80 n + 48 t + 36 + 16)"
+        else:
+            kernel = "k_pathtrace_mega" if real == N.SCHEDULE_MEGAKERNEL else "k_pt_warpfront"
+            b_ray, scope = whole_ray, "whole step in one kernel: SURVEY 8d formula 80 n + 48 t + 96 + 32 + 204 p_hit + 32 / (8 r)"
+        rays_per_launch = st2.rays / max(st2.trace_kernel_launches, 1)
+        avg_launch_ms = st2.trace_kernel_ms_total / max(st2.trace_kernel_launches, 1)
+        achieved = b_ray * rays_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        peak, peak_src = measured_peak_gbs()
+        info = sd.accel_info()
+        return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": load_traffic(kernel, workload_key), "algorithmic_bytes_per_launch": b_ray * rays_per_launch,
+                "peak_source": peak_src, "bytes_per_ray": b_ray, "bytes_per_ray_scope": scope, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
+                "p_hit": p_hit, "rays_per_path": r_path, "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_launch_ms,
+                "launches_timed": int(st2.trace_kernel_launches),
+                "whole_step_bytes_per_ray": whole_ray,
+                "bvh_MB": (info.n_wide_nodes * 80 + info.n_triangles * 48) / 1e6,
+                "note": "algorithmic bytes; the BVH (%.1f MB) is served from L1/L2 when it fits, so frac can exceed what DRAM counters show"
+                        % ((info.n_wide_nodes * 80 + info.n_triangles * 48) / 1e6)}
+
     sc, sd, cam, sbt = setup("synth" if args.workload == "synth" else "tunnel.gltf", True)
     build_ms = ctx.stats().last_build_ms
     workload = WORKLOAD if args.workload == "tunnel" else (
         "5-pathtrace synthetic %d BLAS x 20000 triangles (seed 0xB200) --sky %dx%d, %d spp/frame, max_bounces %d" % (
             args.blas, WIDTH, HEIGHT, SPP, MAX_BOUNCES))
-    mode = N.ACCUM_SUM if world > 1 else N.ACCUM_MIX
+    split = None if world == 1 else args.split
+    tiled = split == "tiles"
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    main_run = device_timed(sd, cam, sbt, sched, warmup, steps, mode, 0)
+    main_run = device_timed(sd, cam, sbt, sched, warmup, steps, split, 0)
     clock_info = clocks.stop() if rank == 0 else None
     ms_total, rays_total = gather_max_sum(main_run["ms_total"], main_run["rays"])
     value = rays_total / (ms_total * 1e-3) / 1e6
     ms_per_step = ms_total / steps
 
-    # ---- e2e (every rank): the call a user makes, host buffers, H2D of the step's inputs + D2H of the rendered frame each
-    #      step; whole-job value = rays of all ranks / the slowest rank's wall clock ----
+    # ---- e2e (every rank): the call a user makes, host buffers: every step builds the 400-byte uniform block on the host
+    #      (H2D with the launch) and reads the rendered frame back into pinned host memory (replaces blit-to-present); at
+    #      N > 1 the closing reduce + resolve + readback of the combined image on rank 0 are inside the clock too.
+    #      whole-job value = rays of all ranks / the slowest rank's wall clock ----
+    cam.set_window_size((WIDTH, HEIGHT))
     e2e_accum = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA32F)
     e2e_render = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA8)
     host_frame = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True).numpy()
+    e2e_mode = N.ACCUM_SUM if world > 1 else N.ACCUM_MIX
     for f in range(2):
         sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), e2e_accum, e2e_render, schedule=sched,
-                                             samples_per_frame=SPP, max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
+                                             samples_per_frame=SPP, max_bounces=MAX_BOUNCES, accum_mode=e2e_mode), (WIDTH, HEIGHT, 1))
+    e2e_accum.clear()
     ctx.reset_stats()
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
+    barrier_sync()
     t0 = time.perf_counter()
     n_e2e = min(steps, 8)
     for f in multigpu.frames_for_rank(rank, world, world * n_e2e, first=200):
         u = scene.scene_uniforms(cam, WIDTH, HEIGHT, f)  # host-side camera -> 400-byte uniform block (the step's input)
         sd.tlas_regenerate()
         sbt.cmd_trace_rays(ray.TraceBindings(sd, u, e2e_accum, e2e_render, schedule=sched, samples_per_frame=SPP,
-                                             max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
-        e2e_render.readback(host_frame)  # replaces blit-to-present: the step's result reaches host memory
+                                             max_bounces=MAX_BOUNCES, accum_mode=e2e_mode), (WIDTH, HEIGHT, 1))
+        e2e_render.readback(host_frame)  # the step's result reaches host memory
+    if world > 1:
+        comm.reduce_accum(e2e_accum, 0, e2e_accum, e2e_render)
+        if rank == 0:
+            e2e_render.readback(host_frame)  # the combined image
+        ctx.synchronize()
     dt_e2e = time.perf_counter() - t0
     e2e_ms, e2e_rays = gather_max_sum(1e3 * dt_e2e, int(ctx.stats().rays))
-    e2e = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 400 + 32,
-           "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": e2e_ms / n_e2e, "steps": n_e2e}
+    e2e = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 400 + 48,
+           "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": e2e_ms / n_e2e, "steps": n_e2e,
+           "includes": "uniform block + params H2D, rgba8 frame D2H every step" + ("; closing NCCL reduce + resolve + D2H of the combined image on rank 0" if world > 1 else "")}
     del e2e_accum, e2e_render
 
-    # ---- roofline of the dominant kernel: instrumented pass for nodes/triangles per ray + per-launch event timing ----
     roofline = None
     cpu_baseline = None
     extra = {}
+
+    # ---- N > 1: the hard case of SURVEY 8e beside the frames split: ONE frame cut across the GPUs (interleaved 8-row bands,
+    #      one all-gather per frame), against the same frame traced by one GPU alone in the same run ----
+    if world > 1 and not tiled and not args.no_extra:
+        n_t = min(steps, 8)
+        alone = device_timed(sd, cam, sbt, sched, 2, n_t, None, 300)       # every rank traces whole frames on its own
+        tiles = device_timed(sd, cam, sbt, sched, 2, n_t, "tiles", 300)
+        t_ms, _ = gather_max_sum(tiles["ms_total"], 0)
+        a_ms, _ = gather_max_sum(alone["ms_total"], 0)
+        extra["tile_split"] = {"ms_per_frame": t_ms / n_t, "single_gpu_ms_per_frame": a_ms / n_t, "speedup_vs_1gpu": a_ms / t_ms,
+                               "frames": n_t, "band_rows": BAND,
+                               "what": "one frame cut into interleaved %d-row bands over %d GPUs, solb_allgather_rows (pack + ncclAllGather + scatter) per frame inside the timed region; max over ranks" % (BAND, world)}
+
     if rank == 0:
-        ctx.reset_stats()
-        accum = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA32F)
-        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, 0), accum, None, schedule=sched,
-                                             samples_per_frame=SPP, max_bounces=MAX_BOUNCES, collect_stats=True), (WIDTH, HEIGHT, 1))
-        st = ctx.stats()
-        n_node, n_tri = st.nodes_visited / st.rays, st.tris_tested / st.rays
-        p_hit, r_path = st.hits / st.rays, st.rays / st.paths
-        # live per-launch timing of the dominant kernel (event pairs inside libsolb, timing mode)
-        ctx.set_timing(True)
-        ctx.reset_stats()
-        for f in range(100, 103):
-            sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), accum, None, schedule=sched,
-                                                 samples_per_frame=SPP, max_bounces=MAX_BOUNCES), (WIDTH, HEIGHT, 1))
-        st2 = ctx.stats()
-        ctx.set_timing(False)
-        if sched in (N.SCHEDULE_MEGAKERNEL, N.SCHEDULE_WARPFRONT):
-            kernel = "k_pathtrace_mega" if sched == N.SCHEDULE_MEGAKERNEL else "k_pt_warpfront"
-            # everything happens in one kernel: traversal + shading fetches + accumulation RMW (+ the path record round trip
-            # of the warp-local wavefront: ray record read, hit record write / read, path state read / write)
-            b_ray = 80 * n_node + 48 * n_tri + p_hit * (112 + 176) + 36.0 / (SPP * r_path) + (
-                (32 + 32 + 80 + 64) if sched == N.SCHEDULE_WARPFRONT else 0)
-        else:
-            kernel = "k_wf_trace"
-            # traversal kernel only: nodes + triangles + ray record read (2 x float4 + queue id) + hit record write
-            b_ray = 80 * n_node + 48 * n_tri + 36 + 16
-        rays_per_launch = st2.rays / max(st2.trace_kernel_launches, 1)
-        avg_launch_ms = st2.trace_kernel_ms_total / max(st2.trace_kernel_launches, 1)
-        achieved = b_ray * rays_per_launch / (avg_launch_ms * 1e-3) / 1e9
-        peak, peak_src = measured_peak_gbs()
-        traffic = None
+        wkey = "tunnel_%dx%d" % (WIDTH, HEIGHT) if args.workload == "tunnel" else "synth_%d" % args.blas
+        roofline = measure_roofline(sd, cam, sbt, sched, WIDTH, HEIGHT, MAX_BOUNCES, wkey)
+
+    if rank == 0 and world == 1 and args.workload == "tunnel" and not args.size and not args.no_extra:
+        # ---- the other BASELINE.json configs, each with its own roofline (bytes per ray from that run's counters) ----
+        def line(r, n, sd_, w, h):
+            return {"Mrays_s": r["rays"] / (r["ms_total"] * 1e-3) / 1e6, "ms_per_frame": r["ms_total"] / n,
+                    "rays_per_path": r["rays"] / max(r["paths"], 1), "resolution": "%dx%d" % (w, h),
+                    "schedule": sched_names[resolved_schedule(sd_, N.SCHEDULE_AUTO)]}
+
+        # cornell beside tunnel (the metric names both): same resolution / spp / bounce cap
+        _, sd_c, cam_c, sbt_c = setup("cornell.gltf", False)
+        n_c = min(steps, 8)
+        rc = device_timed(sd_c, cam_c, sbt_c, N.SCHEDULE_AUTO, 3, n_c, None, 0)
+        extra["cornell_1080p_cap8"] = line(rc, n_c, sd_c, WIDTH, HEIGHT)
+        extra["cornell_1080p_cap8"]["roofline"] = measure_roofline(sd_c, cam_c, sbt_c, N.SCHEDULE_AUTO, WIDTH, HEIGHT, MAX_BOUNCES, "cornell_1920x1080")
+        # configs[3] on one GPU: 3840 x 2160
+        r4 = device_timed(sd, cam, sbt, sched, 2, 4, None, 0, w=3840, h=2160)
+        extra["config3_tunnel_4k"] = line(r4, 4, sd, 3840, 2160)
+        extra["config3_tunnel_4k"]["roofline"] = measure_roofline(sd, cam, sbt, sched, 3840, 2160, MAX_BOUNCES, "tunnel_3840x2160")
+        cam.set_window_size((WIDTH, HEIGHT))
+        # configs[1]: 4-ray-ao, Duck.gltf stands in for ToyCar.glb (missing upstream), the example's camera, 1 primary + <= 4 AO rays x 4 samples
+        sc_d = scene.load_scene(ctx, os.path.join(ROOT, "assets", "models", "Duck.gltf"))
+        sd_d = ray.SceneDescription.from_scene(ctx, sc_d)
+        cam_d = scene.Camera((WIDTH, HEIGHT))
+        cam_d.look_at((4, 1, 4), (0, 0.5, 0), (0, -1, 0))  # examples/4-ray-ao.rs:89-90
+        ctx.set_blue_noise(sol_io.load_texture_rgba8(os.path.join(ROOT, "assets", "textures", "HDR_RGBA_0.png")))
+        pipe = ray.Pipeline(ctx, ray.PipelineInfo().shader("glsl/ao.rgen", ray.RAYGEN_KHR).shader("glsl/ao.rmiss", ray.MISS_KHR)
+                            .shader("glsl/ao.rchit", ray.CLOSEST_HIT_KHR))
+        sbt_ao = ray.ShaderBindingTable(ctx, pipe, ray.ShaderBindingTableInfo().raygen(0).miss(1).hitgroup(2))
+        ra = device_timed(sd_d, cam_d, None, None, 3, 8, None, 0,
+                          trace_fn=lambda f, img: sbt_ao.cmd_trace_rays(ray.TraceBindings(sd_d, scene.scene_uniforms(cam_d, WIDTH, HEIGHT, f), img, None), (WIDTH, HEIGHT, 1)))
+        extra["config1_ao_duck_1080p"] = {"Mrays_s": ra["rays"] / (ra["ms_total"] * 1e-3) / 1e6, "ms_per_frame": ra["ms_total"] / 8,
+                                          "rays_per_frame": ra["rays"] / 8, "kernel": "k_ao",
+                                          "note": "Duck.gltf stands in for the example's ToyCar.glb (absent upstream: .MISSING_LARGE_BLOBS)"}
+        del sd_d, sc_d
+        # configs[4]: synthetic 1000 BLAS x 20 000 triangles = 20 M triangles: BVH build + path trace on this GPU
         try:
-            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f)[kernel]["dram_bytes_per_launch"]  # from the committed ncu --set full capture
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "algorithmic_bytes_per_launch": b_ray * rays_per_launch, "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
-                    "p_hit": p_hit, "rays_per_path": r_path, "avg_launch_ms": avg_launch_ms,
-                    "launches_timed": int(st2.trace_kernel_launches),
-                    "kernel_share_of_step": st2.trace_kernel_ms_total / max(sum(main_run["step_ms"][:3]), 1e-9) if steps >= 3 else None,
-                    "note": "algorithmic bytes are served mostly from L1/L2 (BVH + triangles = %.1f MB): frac can exceed what DRAM counters show" % (
-                        (sd.accel_info().n_wide_nodes * 80 + sd.accel_info().n_triangles * 48) / 1e6)}
+            from sol_rs_b200 import synth
 
-        if world == 1 and args.workload == "tunnel" and not args.size:
-            # the metric names cornell beside tunnel: same resolution / spp / bounce cap, default (auto) schedule
-            _, sd_c, cam_c, sbt_c = setup("cornell.gltf", False)
-            rc = device_timed(sd_c, cam_c, sbt_c, N.SCHEDULE_AUTO, 3, min(steps, 8), N.ACCUM_MIX, 0)
-            extra["cornell_1080p_cap8"] = {"Mrays_s": rc["rays"] / (rc["ms_total"] * 1e-3) / 1e6, "ms_per_frame": rc["ms_total"] / min(steps, 8),
-                                           "rays_per_path": rc["rays"] / max(rc["paths"], 1), "schedule": "auto (megakernel: 3 wide nodes)"}
-        if args.extra:
-            other = N.SCHEDULE_WAVEFRONT if sched == N.SCHEDULE_MEGAKERNEL else N.SCHEDULE_MEGAKERNEL
-            r2 = device_timed(sd, cam, sbt, other, 2, min(steps, 6), N.ACCUM_MIX, 0) if world == 1 else None
-            if r2:
-                extra["other_schedule"] = {"schedule": "megakernel" if other else "wavefront",
-                                           "Mrays_s": r2["rays"] / (r2["ms_total"] * 1e-3) / 1e6,
-                                           "ms_per_step": r2["ms_total"] / min(steps, 6)}
-            if world == 1:
-                _, sd_c, cam_c, sbt_c = setup("cornell.gltf", False)
-                for name, s_ in (("wavefront", N.SCHEDULE_WAVEFRONT), ("megakernel", N.SCHEDULE_MEGAKERNEL)):
-                    rc = device_timed(sd_c, cam_c, sbt_c, s_, 2, min(steps, 6), N.ACCUM_MIX, 0)
-                    extra["cornell_1080p_b8_" + name] = {"Mrays_s": rc["rays"] / (rc["ms_total"] * 1e-3) / 1e6,
-                                                         "ms_per_step": rc["ms_total"] / min(steps, 6),
-                                                         "rays_per_path": rc["rays"] / max(rc["paths"], 1)}
-        if not args.no_cpu_baseline and world == 1 and args.workload == "tunnel":
-            cb = cpu_reference_arm(6, 1, (CPU_SAMPLE_W, CPU_SAMPLE_H))  # ~10 s on 16 host threads
-            cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            t0 = time.perf_counter()
+            sc_s = synth.make_scene(1000, 100)
+            gen_s = time.perf_counter() - t0
+            sd_s = ray.SceneDescription.from_scene(ctx, sc_s)
+            first_build_ms = ctx.stats().last_build_ms
+            builds = []
+            for _ in range(3):  # rebuilds with the scratch pool warm (the figure BASELINE.md quotes)
+                sd_s.blas_transform(sc_s.meshes[0].transform, 0)
+                sd_s.tlas_regenerate()
+                builds.append(ctx.stats().last_build_ms)
+            info = sd_s.accel_info()
+            sbt_s = pt_sbt(True)
+            rs = device_timed(sd_s, sc_s.camera, sbt_s, sched, 2, 4, None, 0)
+            extra["config4_synth_20m"] = line(rs, 4, sd_s, WIDTH, HEIGHT)
+            extra["config4_synth_20m"].update({
+                "triangles": int(info.n_triangles), "wide_nodes": int(info.n_wide_nodes), "wide_depth": int(info.wide_depth),
+                "bvh_build_ms": min(builds), "bvh_build_ms_first": first_build_ms, "Mtris_s": info.n_triangles / (min(builds) * 1e-3) / 1e6,
+                "build_roofline": {"bound": "hbm", "bytes_per_triangle": 379, "achieved": 379 * info.n_triangles / (min(builds) * 1e-3) / 1e9,
+                                   "peak": measured_peak_gbs()[0], "unit": "GB/s",
+                                   "frac": 379 * info.n_triangles / (min(builds) * 1e-3) / 1e9 / measured_peak_gbs()[0]},
+                "sah": float(info.sah_cost_binary), "scene_gen_s": gen_s,
+                "roofline": measure_roofline(sd_s, sc_s.camera, sbt_s, sched, WIDTH, HEIGHT, MAX_BOUNCES, "synth_1000")})
+            del sd_s, sc_s
+            ctx.trim()
+        except Exception as e:  # e.g. a smaller GPU: the headline line must still be printed
+            extra["config4_synth_20m"] = {"error": repr(e)}
+    if rank == 0 and world == 1 and args.extra:
+        for name, s_ in (("wavefront", N.SCHEDULE_WAVEFRONT), ("megakernel", N.SCHEDULE_MEGAKERNEL), ("warpfront", N.SCHEDULE_WARPFRONT)):
+            r2 = device_timed(sd, cam, sbt, s_, 2, min(steps, 6), None, 0)
+            extra["tunnel_" + name] = {"Mrays_s": r2["rays"] / (r2["ms_total"] * 1e-3) / 1e6, "ms_per_step": r2["ms_total"] / min(steps, 6)}
+        _, sd_c, cam_c, sbt_c = setup("cornell.gltf", False)
+        for name, s_ in (("wavefront", N.SCHEDULE_WAVEFRONT), ("megakernel", N.SCHEDULE_MEGAKERNEL), ("warpfront", N.SCHEDULE_WARPFRONT)):
+            rc = device_timed(sd_c, cam_c, sbt_c, s_, 2, min(steps, 6), None, 0)
+            extra["cornell_1080p_cap8_" + name] = {"Mrays_s": rc["rays"] / (rc["ms_total"] * 1e-3) / 1e6, "ms_per_step": rc["ms_total"] / min(steps, 6)}
+    if rank == 0 and not args.no_cpu_baseline and world == 1 and args.workload == "tunnel" and not args.size:
+        cb = cpu_reference_arm(1, 0, (WIDTH, HEIGHT))  # ONE full frame of the workload (~20 s on 16 host threads)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        tiled = world > 1 and args.split == "tiles"
-        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "schedule": sched_name, "accel": args.accel, "bvh_build_ms": build_ms,
-                           "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * (1 if tiled else world)),
-                           "l2": "256 MB buffer written between timed steps (outside the per-step event pairs)",
-                           "multi_gpu": ("every frame cut into 8-row bands dealt round-robin to the N ranks, one NCCL all-gather of the accumulation rows per frame inside the timed region"
-                                         if tiled else
-                                         "frames f = rank (mod N) per rank, local sums, one NCCL reduce + resolve inside the timed region")
-                           if world > 1 else "single GPU"},
-                "ms_per_frame": ms_per_step, "reduce_ms": main_run["reduce_ms"],
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": main_run["launches"],
-                "clocks": clock_info, "extra": extra}
-        _emit(line)
+        line_ = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,
+                 "dtype": "f32", "data": "synthetic",
+                 "config": {"workload": workload, "schedule": sched_names[resolved_schedule(sd, sched)], "accel": args.accel, "bvh_build_ms": build_ms,
+                            "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * (1 if tiled else world)),
+                            "l2": "256 MB buffer written between timed steps (outside the per-step event pairs)",
+                            "tlas": "solb_tlas_regenerate is called every frame like the reference (examples/5-pathtrace.rs:316) and is a no-op while no transform changed; "
+                                    "a forced full rebuild of this scene costs bvh_build_ms",
+                            "multi_gpu": ("every frame cut into 8-row bands dealt round-robin to the N ranks, one solb_allgather_rows (NCCL) per frame inside the timed region"
+                                          if tiled else
+                                          "frames f = rank (mod N) per rank, local sums, one solb_reduce_accum (NCCL reduce + resolve on rank 0) inside the timed region")
+                            if world > 1 else "single GPU"},
+                 "ms_per_frame": ms_per_step, "reduce_ms": main_run["reduce_ms"],
+                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": main_run["launches"],
+                 "clocks": clock_info, "extra": extra}
+        _emit(line_)
     if dist:
         dist.barrier()
+        if comm:
+            comm.close()
         dist.destroy_process_group()
 
 

@@ -171,8 +171,14 @@ typedef struct SolbAccelInfo {
 /* ---- context ------------------------------------------------------------------------------ */
 
 /* Replaces Context/SharedContext creation (src/context.rs:239-369) for this path.
- * `stream` is a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */
+ * `stream` is a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create a private non-blocking one.
+ * NULL never means "the default stream": to adopt the legacy default stream (handle 0 in the runtime API) pass
+ * cudaStreamLegacy ((cudaStream_t)0x1), to adopt the per-thread default stream cudaStreamPerThread ((cudaStream_t)0x2). */
 SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out);
+/* Counterpart of the shader compilation in Pipeline::new (src/ray/pipeline.rs:61-115): loads every kernel of the library and
+ * creates the scratch pool by pushing a two-triangle scene through all launch paths once, so the first solb_accel_build /
+ * solb_trace_* of the process does not pay for CUDA's lazy module loading.  Optional; idempotent. */
+SOLB_API int solb_ctx_preload(solb_ctx *ctx);
 SOLB_API int solb_ctx_destroy(solb_ctx *ctx);
 SOLB_API int solb_synchronize(solb_ctx *ctx); /* queue_wait_idle, src/context.rs:539-559 */
 /* Return cached build scratch to the driver (the stream-ordered pool keeps it between builds so per-frame rebuilds do not
@@ -264,6 +270,24 @@ SOLB_API int solb_test_sort_pairs(solb_ctx *ctx, uint64_t *keys, uint32_t *value
 /* ---- multi-GPU resolve: out = sum.xyz / sum.w with the reference's display transform ---- */
 /* accum_out RGBA32F (may alias sum), render RGBA8 (may be NULL). */
 SOLB_API int solb_resolve_sum(solb_ctx *ctx, solb_target *sum, solb_target *accum_out, solb_target *render);
+
+/* ---- multi-GPU exchange (new work: the reference is single-GPU).  One process per GPU, one communicator per
+ * ctx; NCCL over NVLink underneath, bound at run time (the copy already loaded in the process, else SOLB_NCCL_LIB, else
+ * libnccl.so.2).  All calls are collective over the ranks of the communicator and asynchronous on the ctx stream. ---- */
+#define SOLB_COMM_ID_BYTES 128
+/* rank 0 creates the id and hands the 128 bytes to the other ranks by any host-side means (ncclGetUniqueId) */
+SOLB_API int solb_comm_unique_id(uint8_t *id_out /* [SOLB_COMM_ID_BYTES] */);
+SOLB_API int solb_comm_init(solb_ctx *ctx, const uint8_t *id /* [SOLB_COMM_ID_BYTES] */, int rank, int world);
+SOLB_API int solb_comm_info(solb_ctx *ctx, int *rank, int *world, int *nccl_version);
+SOLB_API int solb_comm_destroy(solb_ctx *ctx);
+/* Frames (sample) split: rank r renders frames f = r (mod N) with SOLB_ACCUM_SUM into `sum`; this sums the N targets onto
+ * `root` in place (ncclReduce, float32) and, on the root, resolves sum / count with the reference's display transform into
+ * accum_out (may alias sum) / render (each may be NULL).  Without a communicator (world 1) it is the resolve alone. */
+SOLB_API int solb_reduce_accum(solb_ctx *ctx, solb_target *sum, int root, solb_target *accum_out, solb_target *render);
+/* Tile split of ONE frame: rank r has traced the bands r, r + N, ... of band_rows rows each (SolbTraceParams tile_row_begin =
+ * r * band_rows, tile_row_count = band_rows, tile_row_stride = N * band_rows) into its full-size target; afterwards every
+ * rank holds the whole image (pack, ncclAllGather, scatter). */
+SOLB_API int solb_allgather_rows(solb_ctx *ctx, solb_target *target, uint32_t band_rows);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,7 @@ _pp = ctypes.POINTER(ctypes.c_void_p)
 SYMBOLS = {
     "solb_ctx_create": (_i, [_i, _vp, _pp]),
     "solb_ctx_destroy": (_i, [_vp]),
+    "solb_ctx_preload": (_i, [_vp]),
     "solb_synchronize": (_i, [_vp]),
     "solb_ctx_trim": (_i, [_vp]),
     "solb_last_error": (ctypes.c_char_p, [_vp]),
@@ -118,7 +119,14 @@ SYMBOLS = {
     "solb_trace_rays": (_i, [_vp, _vp, _u32, _vp, _vp]),
     "solb_resolve_sum": (_i, [_vp, _vp, _vp, _vp]),
     "solb_test_sort_pairs": (_i, [_vp, _vp, _vp, _u32, _i]),
+    "solb_comm_unique_id": (_i, [_vp]),
+    "solb_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "solb_comm_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "solb_comm_destroy": (_i, [_vp]),
+    "solb_reduce_accum": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "solb_allgather_rows": (_i, [_vp, _vp, _u32]),
 }
+COMM_ID_BYTES = 128
 
 _LIB = None
 

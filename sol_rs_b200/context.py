@@ -9,17 +9,31 @@ from . import _native as N
 
 class Context:
     """One CUDA device + one stream.  `stream` is a raw cudaStream_t (int) — pass
-    torch.cuda.current_stream().cuda_stream so torch events time the kernels; None creates one."""
+    torch.cuda.current_stream().cuda_stream so torch events time the kernels and torch / NCCL work on that stream is
+    ordered with libsolb's.  None (not given) creates a private non-blocking stream.  The handle 0 IS a stream — the
+    legacy default stream, which is what torch.cuda.current_stream().cuda_stream returns until the caller switches
+    streams — and is adopted as such (passed down as cudaStreamLegacy), not mistaken for "not given"."""
+
+    STREAM_LEGACY = 0x1  # cudaStreamLegacy: explicit handle of the legacy default stream (driver_types.h)
 
     def __init__(self, device=0, stream=None):
         self._h = ctypes.c_void_p()
         self._lib = N.lib()
-        N.check(self._lib.solb_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(self._h)))
+        if stream is None:
+            handle = None
+        else:
+            handle = ctypes.c_void_p(int(stream) if int(stream) != 0 else self.STREAM_LEGACY)
+        N.check(self._lib.solb_ctx_create(int(device), handle, ctypes.byref(self._h)))
         self.device = int(device)
+        self.stream = None if stream is None else int(stream)
 
     @property
     def handle(self):
         return self._h
+
+    def preload(self):
+        """load every kernel + create the scratch pool now (what Pipeline::new's shader compilation is to the reference)"""
+        N.check(self._lib.solb_ctx_preload(self._h), self._h)
 
     def synchronize(self):
         N.check(self._lib.solb_synchronize(self._h), self._h)

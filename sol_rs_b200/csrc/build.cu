@@ -971,10 +971,15 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
 template <class T>
 static cudaError_t dalloc(T **p, size_t count) { return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)); }
 // build scratch comes from the stream-ordered pool: no device-wide synchronisation per buffer, reused across rebuilds
+// The pool is the ctx's PRIVATE one (solb_ctx_create): its raised release threshold keeps the scratch cached between rebuilds
+// without touching the device's default pool, which belongs to the embedding application.
+static thread_local cudaMemPool_t t_build_pool = nullptr;
 template <class T>
 static cudaError_t salloc(cudaStream_t st, T **p, size_t count) {
-    return cudaMallocAsync((void **)p, std::max<size_t>(count, 1) * sizeof(T), st);
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    return t_build_pool ? cudaMallocFromPoolAsync((void **)p, bytes, t_build_pool, st) : cudaMallocAsync((void **)p, bytes, st);
 }
+void set_build_pool(cudaMemPool_t pool) { t_build_pool = pool; }
 
 // SOLB_BUILD_TRACE=1: synchronise after every build phase and print its wall-clock share to stderr (debug aid)
 struct PhaseTrace {

@@ -40,8 +40,10 @@ struct Tri48 {
 static_assert(sizeof(Tri48) == 48, "Tri48 must be 48 bytes");
 
 #define SOLB_MAX_LEAF_TRIS 2  // a leaf's mask contribution must fit one byte (above); 3 buys nothing on the shipped scenes
+#ifndef SOLB_SM_STACK
 #define SOLB_SM_STACK 8      // per-lane entries kept in shared memory
-#define SOLB_LOCAL_STACK 56  // spill (local memory)
+#endif
+#define SOLB_LOCAL_STACK (64 - SOLB_SM_STACK)  // spill (local memory)
 // The warp-cooperative kernel may park two entries per level (the siblings' node group and a postponed triangle
 // group), a two-level walk adds one sentinel: 2 * (TLAS depth + BLAS depth) + 1 <= SOLB_SM_STACK + SOLB_LOCAL_STACK.
 #define SOLB_MAX_WIDE_DEPTH ((SOLB_SM_STACK + SOLB_LOCAL_STACK - 2) / 2)

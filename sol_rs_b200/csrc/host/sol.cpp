@@ -278,7 +278,7 @@ static bool ends_with(const std::string &s, const std::string &suffix) {
     return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0;
 }
 
-Pipeline::Pipeline(std::shared_ptr<Context>, const PipelineInfo &info) {
+Pipeline::Pipeline(std::shared_ptr<Context> context, const PipelineInfo &info) {
     bool have_rgen = false;
     for (const auto &sh : info.shaders_) {
         if (sh.second != ShaderStage::RAYGEN_KHR) continue;
@@ -291,6 +291,11 @@ Pipeline::Pipeline(std::shared_ptr<Context>, const PipelineInfo &info) {
     if (!have_rgen) throw Error(SOLB_ERR_INVALID, "ray::Pipeline: no raygen stage");
     // specialization constant 0 = ENABLE_SKYLIGHT (examples/5-pathtrace.rs:103, pathtrace.rmiss:5)
     enable_sky_ = info.spec_id_ == 0 && !info.spec_.empty() && info.spec_[0] != 0;
+    // the reference compiles its GLSL stages here (src/ray/pipeline.rs:105-115); the counterpart is loading the kernels
+    if (context) {
+        const int rc = solb_ctx_preload(context->handle());
+        if (rc != SOLB_OK) throw Error(rc, std::string("ray::Pipeline: ") + solb_last_error(context->handle()));
+    }
 }
 
 ShaderBindingTable::ShaderBindingTable(std::shared_ptr<Context> context, const Pipeline &pipeline, const ShaderBindingTableInfo &info)

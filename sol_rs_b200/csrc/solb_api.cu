@@ -1,114 +1,11 @@
 // solb_api.cu — the extern "C" boundary declared in include/solb.h.
 // Handles are heap objects; every entry point validates, sets the device, catches everything and
 // returns a SolbStatus.  There is no CPU path: without a usable CUDA device solb_ctx_create fails.
-#include "../../include/solb.h"
-
-#include <algorithm>
-#include <cstdlib>
-#include <new>
-#include <string>
-#include <vector>
+#include "solb_handles.h"
 
 #include "host_math.h"
-#include "solb_internal.h"
-#include "trace.h"
 
-using namespace solb;
-
-static thread_local std::string g_last_error;
-
-struct solb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int sm_count = 148;
-    std::string err;
-    unsigned long long *d_stats = nullptr;  // 8 slots
-    uint64_t launches = 0;
-    bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_build_ms = 0.0f, last_trace_ms = 0.0f;
-    uint32_t *d_blue = nullptr;
-    uint32_t blue_w = 0, blue_h = 0;
-    uint32_t *pinned_count = nullptr;
-    WavefrontState ws = {};
-    WarpfrontState wl = {};  // warp-local wavefront schedule: slot-indexed path state, sized by the persistent grid
-    // queues + counters + streams of the extra frame parts (overlap mode); index 0 unused (= ws / stream)
-    uint32_t *part_queue[WF_MAX_PARTS][2] = {};
-    uint32_t *part_counters[WF_MAX_PARTS] = {};
-    cudaStream_t part_stream[WF_MAX_PARTS] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[WF_MAX_PARTS] = {}, ev_poll[WF_MAX_PARTS] = {};
-    cudaStream_t shade_stream[WF_MAX_PARTS] = {};
-    cudaEvent_t ev_ts[WF_MAX_PARTS] = {}, ev_st[WF_MAX_PARTS] = {};
-    uint2 *part_spill[WF_MAX_PARTS] = {};  // ray-pool kernel stack spill, one per frame part
-    std::vector<cudaEvent_t> ev_pool;  // timing mode: pairs around every dominant-kernel launch
-    float trace_kernel_ms_total = 0.0f;
-    uint32_t trace_kernel_launches = 0;
-    TraceTuning tune;
-    uint32_t auto_wide_schedule = SOLB_SCHEDULE_WARPFRONT;  // what SOLB_SCHEDULE_AUTO picks above 8 wide nodes (SOLB_AUTO_SCHEDULE)
-    int refs = 1;  // the ctx handle itself + every live scene / target: resources are freed when the last one goes
-};
-
-struct solb_scene {
-    solb_ctx *ctx = nullptr;
-    std::vector<SolbSceneInstance> instances;  // as the reference's shader would see them
-    std::vector<DeviceInstance> h_inst;
-    std::vector<uint32_t> h_first_tri;       // per-instance triangle prefix (flattened build)
-    std::vector<DeviceBlas> h_blas;          // unique geometry: one per primitive section
-    std::vector<SolbMaterialInfo> materials; // kept for solb_scene_add_instance
-    uint32_t n_tris = 0, n_geom_tris = 0, n_vertices = 0, n_indices = 0;
-    float4 *d_vertices = nullptr;
-    uint32_t *d_indices = nullptr, *d_first_tri = nullptr;
-    DeviceInstance *d_inst = nullptr;
-    DeviceBlas *d_blas = nullptr;
-    ShadeRecord *d_shade = nullptr;
-    size_t inst_capacity = 0;                // instances d_inst / d_first_tri can hold
-    AccelStorage accel;
-    uint32_t accel_mode = SOLB_ACCEL_FLAT;
-    bool built = false;
-    bool dirty = false;       // an instance transform changed since the last build / TLAS regenerate
-    bool needs_build = false; // instances were added or the mode changed: the whole structure must be rebuilt
-    DeviceSceneView view() const {
-        DeviceSceneView v;
-        v.n_instances = (uint32_t)h_inst.size();
-        v.n_tris = n_tris;
-        v.inst_first_tri = d_first_tri;
-        v.instances = d_inst;
-        v.vertices = d_vertices;
-        v.indices = d_indices;
-        v.n_blas = (uint32_t)h_blas.size();
-        v.n_geom_tris = n_geom_tris;
-        v.blas = d_blas;
-        return v;
-    }
-};
-
-struct solb_target {
-    solb_ctx *ctx = nullptr;
-    uint32_t width = 0, height = 0, format = 0;
-    void *dev = nullptr;
-    size_t bytes = 0;
-};
-
-static int fail(solb_ctx *ctx, int code, const std::string &msg) {
-    g_last_error = msg;
-    if (ctx) ctx->err = msg;
-    return code;
-}
-static int fail_cuda(solb_ctx *ctx, cudaError_t e, const char *what) {
-    cudaGetLastError();  // clear sticky non-fatal state
-    return fail(ctx, SOLB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-}
-#define SOLB_TRY try {
-#define SOLB_CATCH(ctx)                                                                  \
-    } catch (const std::bad_alloc &) { return fail(ctx, SOLB_ERR_CUDA, "host out of memory"); } \
-    catch (const std::exception &e) { return fail(ctx, SOLB_ERR_INVALID, e.what()); }       \
-    catch (...) { return fail(ctx, SOLB_ERR_INVALID, "unknown exception"); }
-#define CU(ctx, call)                                                    \
-    do {                                                                 \
-        cudaError_t e__ = (call);                                        \
-        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call);       \
-    } while (0)
+thread_local std::string g_last_error;
 
 static size_t format_bytes(uint32_t f) { return f == SOLB_FORMAT_RGBA32F ? 16 : (f == SOLB_FORMAT_RGBA8 ? 4 : 8); }
 
@@ -139,14 +36,21 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     {
-        // Build scratch comes from the device's stream-ordered pool.  With the default release threshold (0) every
-        // synchronisation hands the freed scratch back to the driver and the next build pays for mapping it again
-        // (measured: 485 ms to release and 210 ms to re-map the 6 GB a 20 M-triangle build uses); keep it cached and let
-        // the caller return it with solb_ctx_trim.
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        // Build scratch comes from a stream-ordered pool.  With the default release threshold (0) every synchronisation hands
+        // the freed scratch back to the driver and the next build pays for mapping it again (measured: 485 ms to release and
+        // 210 ms to re-map the 6 GB a 20 M-triangle build uses); keep it cached and let the caller return it with
+        // solb_ctx_trim.  The pool is PRIVATE to the ctx: the device's default pool is process-global state of the embedding
+        // application (torch, another library) and is left alone.
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&c->build_pool, &props) == cudaSuccess) {
             uint64_t threshold = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+            cudaMemPoolSetAttribute(c->build_pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        } else {
+            c->build_pool = nullptr;  // fall back to the default pool with ITS settings untouched
         }
         cudaGetLastError();
     }
@@ -222,6 +126,8 @@ static void ctx_release(solb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_wavefront(ctx);
     free_warpfront(ctx);
+    solb_comm_destroy(ctx);
+    if (ctx->build_pool) cudaMemPoolDestroy(ctx->build_pool);
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_blue);
     cudaFreeHost(ctx->pinned_count);
@@ -265,10 +171,79 @@ SOLB_API int solb_ctx_trim(solb_ctx *ctx) {
     if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaMemPool_t pool = nullptr;
-    CU(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-    CU(ctx, cudaMemPoolTrimTo(pool, 0));
+    if (ctx->build_pool) CU(ctx, cudaMemPoolTrimTo(ctx->build_pool, 0));
     return SOLB_OK;
+}
+
+// Pipeline::new compiles the GLSL stages when the pipeline is created (src/ray/pipeline.rs:61-115); the counterpart here is
+// loading the AOT-compiled kernels.  CUDA loads a kernel lazily at its first launch, so without this the first
+// solb_accel_build of a process also paid for ~25 module loads and the creation of the scratch pool (the driver's bench recorded
+// 549 ms for a 3 ms build).  The preload pushes a two-triangle scene through every launch path once: both build modes, the
+// three path-tracing schedules, ao, debug and trace_rays.
+SOLB_API int solb_ctx_preload(solb_ctx *ctx) {
+    if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
+    if (ctx->preloaded) return SOLB_OK;
+    SolbModelVertex v[4];
+    memset(v, 0, sizeof(v));
+    const float q[4][3] = { { -1, 0, -1 }, { 1, 0, -1 }, { 1, 0, 1 }, { -1, 0, 1 } };
+    for (int i = 0; i < 4; i++) {
+        for (int k = 0; k < 3; k++) v[i].pos[k] = q[i][k];
+        v[i].pos[3] = 1.0f;
+        v[i].color[0] = v[i].color[1] = v[i].color[2] = v[i].color[3] = 1.0f;
+        v[i].normal[1] = 1.0f;
+    }
+    const uint32_t idx[6] = { 0, 1, 2, 0, 2, 3 };
+    SolbSection sec = { 0, 4, 0, 6, 0 };
+    SolbMeshDesc mesh;
+    memset(&mesh, 0, sizeof(mesh));
+    mesh.vertices = v; mesh.n_vertices = 4; mesh.indices = idx; mesh.n_indices = 6; mesh.sections = &sec; mesh.n_sections = 1;
+    mesh.transform[0] = mesh.transform[5] = mesh.transform[10] = mesh.transform[15] = 1.0f;
+    SolbMaterialInfo mat;
+    memset(&mat, 0, sizeof(mat));
+    mat.base_color[0] = mat.base_color[1] = mat.base_color[2] = mat.base_color[3] = 0.5f;
+    mat.roughness = 1.0f;
+    SolbSceneUniforms u;
+    memset(&u, 0, sizeof(u));
+    for (int i = 0; i < 16; i += 5) u.view_inverse[i] = u.projection_inverse[i] = 1.0f;
+    u.view_inverse[13] = 2.0f;  // camera above the quad, looking down -z of an identity view: rays mostly miss, which is fine
+    u.frame[0] = u.frame[1] = 8;
+    solb_scene *sc = nullptr;
+    solb_target *acc = nullptr, *ren = nullptr, *ids = nullptr;
+    int rc = solb_scene_create(ctx, &mesh, 1, &mat, 1, &sc);
+    const uint64_t launches = ctx->launches;
+    const float build_ms = ctx->last_build_ms;
+    if (!rc) rc = solb_target_create(ctx, 8, 8, SOLB_FORMAT_RGBA32F, &acc);
+    if (!rc) rc = solb_target_create(ctx, 8, 8, SOLB_FORMAT_RGBA8, &ren);
+    if (!rc) rc = solb_target_create(ctx, 8, 8, SOLB_FORMAT_RG32UI, &ids);
+    for (uint32_t mode = 0; mode < 2 && !rc; mode++) {
+        rc = solb_scene_set_accel_mode(sc, mode ? SOLB_ACCEL_FLAT : SOLB_ACCEL_TWO_LEVEL);
+        if (!rc) rc = solb_accel_build(sc);
+        SolbTraceParams p;
+        solb_trace_params_default(&p, 0);
+        p.max_bounces = 2;
+        for (uint32_t sch = 0; sch < 4 && !rc; sch++) {
+            if (sch == SOLB_SCHEDULE_AUTO) continue;
+            p.schedule = sch;
+            rc = solb_trace_pathtrace(sc, &u, &p, acc, ren);
+        }
+        if (!rc) rc = solb_trace_debug(sc, &u, ren, ids, nullptr);
+        float ray[8] = { 0, 1, 0, 0.001f, 0, -1, 0, 100.0f };
+        uint32_t hit[4];
+        if (!rc) rc = solb_trace_rays(sc, ray, 1, hit, nullptr);
+        if (!rc && ctx->d_blue) {
+            solb_trace_params_default(&p, 1);
+            rc = solb_trace_ao(sc, &u, &p, acc);
+        }
+    }
+    if (!rc) rc = solb_resolve_sum(ctx, acc, acc, ren);
+    if (!rc) rc = solb_synchronize(ctx);
+    solb_target_destroy(ids); solb_target_destroy(ren); solb_target_destroy(acc);
+    solb_scene_destroy(sc);
+    solb_stats_reset(ctx);
+    ctx->launches = launches;  // the preload is not part of anybody's frame
+    ctx->last_build_ms = build_ms;
+    if (!rc) ctx->preloaded = true;
+    return rc;
 }
 
 SOLB_API int solb_set_timing(solb_ctx *ctx, int enabled) {
@@ -444,6 +419,7 @@ static int do_build(solb_scene *s) {
     int rc = upload_instances(s);
     if (rc != SOLB_OK) return rc;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    set_build_pool(ctx->build_pool);
     cudaError_t e = s->accel_mode == SOLB_ACCEL_TWO_LEVEL ? build_accel_two_level(ctx->stream, s->view(), s->accel, opt, &ctx->launches)
                                                           : build_accel(ctx->stream, s->view(), s->accel, opt, &ctx->launches);
     if (e == cudaErrorLaunchOutOfResources) return fail(ctx, SOLB_ERR_OVERFLOW, "acceleration structure deeper than the traversal stack");
@@ -497,6 +473,7 @@ SOLB_API int solb_tlas_regenerate(solb_scene *s) {
     int rc = upload_instances(s);
     if (rc != SOLB_OK) return rc;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    set_build_pool(ctx->build_pool);
     cudaError_t e = rebuild_tlas(ctx->stream, s->view(), s->accel, &ctx->launches);
     if (e == cudaErrorLaunchOutOfResources) return fail(ctx, SOLB_ERR_OVERFLOW, "acceleration structure deeper than the traversal stack");
     if (e != cudaSuccess) return fail_cuda(ctx, e, "rebuild_tlas");
@@ -992,6 +969,7 @@ SOLB_API int solb_test_sort_pairs(solb_ctx *ctx, uint64_t *keys, uint32_t *value
     fr.b = dv;
     CU(ctx, cudaMemcpyAsync(dk, keys, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(dv, values, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    set_build_pool(ctx->build_pool);
     CU(ctx, sort_pairs_device(ctx->stream, dk, dv, n, key_bits));
     CU(ctx, cudaMemcpyAsync(keys, dk, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(values, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -113,6 +113,8 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
 cudaError_t build_accel_two_level(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt,
                                   uint64_t *launches);
 cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, uint64_t *launches);
+// stream-ordered scratch of the calling thread's next builds comes from `pool` (nullptr: the device's default pool)
+void set_build_pool(cudaMemPool_t pool);
 cudaError_t sort_pairs_device(cudaStream_t st, uint64_t *keys, uint32_t *vals, uint32_t n, int key_bits);
 
 }  // namespace solb

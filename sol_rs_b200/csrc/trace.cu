@@ -960,179 +960,290 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const FrameConsts fc, Wavefr
 // No global queue, no inter-warp communication, no waves: the only drain is the end of the frame.  Path state lives in
 // slot-indexed arrays sized by the grid (36 MB), so it stays in L2.  Per-pixel arithmetic, RNG order and accumulation are those of
 // k_wf_generate / k_wf_shade / k_wf_resolve: the frames are bit-identical to the other schedules'.
+// Path-state accesses bypass L1 (ld.global.cg / st.global.cg): the records stream through once per ray, while the 128-256 KB of
+// L1 are what keeps node and triangle fetches at an 88 % hit rate.  SOLB_WL_CG=0 restores default caching for A/B runs.
+#ifndef SOLB_WL_CG
+#define SOLB_WL_CG 1
+#endif
+template <class T>
+__device__ __forceinline__ T wl_ld(const T *p) {
+#if SOLB_WL_CG
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+template <class T>
+__device__ __forceinline__ void wl_st(T *p, const T &v) {
+#if SOLB_WL_CG
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+
 __device__ __forceinline__ void wl_push(uint8_t *list, uint32_t &n, bool flag, uint32_t slot, uint32_t lt_mask) {
     const uint32_t m = __ballot_sync(0xffffffffu, flag);
     if (flag) list[n + __popc(m & lt_mask)] = (uint8_t)slot;
     n += (uint32_t)__popc(m);
 }
 
+// per-warp control block in shared memory: the three slot lists + the claimed range of the frame's cursor
+struct WlWarp {
+    uint8_t ready[WL_POOL], shade[WL_POOL], free_[WL_POOL];
+    uint32_t pool_next, pool_end;
+};
+// list sizes travel through the (rare) step calls packed in one word: ready | shade << 8 | free << 16 | exhausted << 24
+__device__ __forceinline__ uint32_t wl_pack(uint32_t n_ready, uint32_t n_shade, uint32_t n_free, bool exhausted) {
+    return n_ready | (n_shade << 8) | (n_free << 16) | (exhausted ? 1u << 24 : 0u);
+}
+
+// Generate step: up to 32 free slots take the next pixels of the frame (k_wf_generate).
+__device__ __forceinline__ uint32_t wl_generate_step(const FrameConsts *fcp, const WarpfrontState *wlp, WlWarp *W, uint32_t slot_base,
+                                                  uint32_t counts, uint32_t n_region_slots, uint32_t batch, uint32_t *ctr) {
+    const FrameConsts &fc = *fcp;
+    const WarpfrontState &wl = *wlp;
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    uint32_t n_ready = counts & 0xffu, n_shade = (counts >> 8) & 0xffu, n_free = (counts >> 16) & 0xffu;
+    bool exhausted = (counts >> 24) & 1u;
+    const uint32_t cnt = min(n_free, 32u);
+    const bool mine = lane < cnt;
+    const uint32_t my_slot = mine ? (uint32_t)W->free_[n_free - 1u - lane] : 0u;
+    n_free -= cnt;
+    uint32_t pool_next = W->pool_next, pool_end = W->pool_end;
+    __syncwarp();
+    // claim cnt frame slots (warp-uniform bookkeeping, like the dynamic fetch of k_wf_trace)
+    uint32_t my_idx = 0xffffffffu, served = 0;
+    while (served < cnt && !exhausted) {
+        if (pool_next >= pool_end) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(wl.cursor, batch);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n_region_slots) { exhausted = true; break; }
+            pool_next = base;
+            pool_end = min(base + batch, n_region_slots);
+        }
+        const uint32_t take = min(cnt - served, pool_end - pool_next);
+        if (mine && lane >= served && lane < served + take) my_idx = pool_next + (lane - served);
+        pool_next += take;
+        served += take;
+    }
+    if (lane == 0) { W->pool_next = pool_next; W->pool_end = pool_end; }
+    bool valid = false, retry = false;
+    if (my_idx != 0xffffffffu) {
+        const uint32_t p = swizzled_pixel(my_idx, fc, valid);
+        if (valid) {
+            const uint32_t x = p % fc.width, y = p / fc.width;
+            uint32_t rng = tea(p, fc.frame);                       // pathtrace.rgen:47
+            const float jx = next_rand(rng), jy = next_rand(rng);  // :52
+            const float3 d = primary_dir(fc, (float)x + jx, (float)y + jy);
+            const uint32_t gs = slot_base + my_slot;
+            wl_st(wl.ray_o + gs, make_float4(fc.origin.x, fc.origin.y, fc.origin.z, __uint_as_float(p)));
+            wl_st(wl.ray_d + gs, make_float4(d.x, d.y, d.z, 0.0f));
+            wl_st(wl.thr + gs, make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u)));
+            wl_st(wl.pix + gs, make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(rng)));
+            ctr[1]++;
+        } else {
+            retry = true;  // a hole of the tile order (image edge): the slot stays free
+        }
+    }
+    wl_push(W->ready, n_ready, valid, my_slot, lt_mask);
+    wl_push(W->free_, n_free, retry, my_slot, lt_mask);
+    if (exhausted) n_free = 0u;  // nothing left to start: free slots are retired
+    __syncwarp();
+    return wl_pack(n_ready, n_shade, n_free, exhausted);
+}
+
+// Shade step: up to 32 finished rays, one per lane (k_wf_shade + k_wf_resolve).
+__device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const DeviceInstance *__restrict__ instances,
+                                               const ShadeRecord *__restrict__ shade, const WarpfrontState *wlp, float4 *accum,
+                                               uint32_t *render, WlWarp *W, uint32_t slot_base, uint32_t counts, uint32_t *ctr) {
+    const FrameConsts &fc = *fcp;
+    const WarpfrontState &wl = *wlp;
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    uint32_t n_ready = counts & 0xffu, n_shade = (counts >> 8) & 0xffu, n_free = (counts >> 16) & 0xffu;
+    const bool exhausted = (counts >> 24) & 1u;
+    const uint32_t cnt = min(n_shade, 32u);
+    const bool mine = lane < cnt;
+    const uint32_t my_slot = mine ? (uint32_t)W->shade[n_shade - 1u - lane] : 0u;
+    n_shade -= cnt;
+    __syncwarp();
+    bool alive = false, freed = false;
+    if (mine) {
+        const uint32_t gs = slot_base + my_slot;
+        const uint4 h = wl_ld(wl.hit + gs);
+        const float4 t4 = wl_ld(wl.thr + gs), x4 = wl_ld(wl.pix + gs), d4 = wl_ld(wl.ray_d + gs);
+        const uint32_t p = __float_as_uint(wl_ld(&wl.ray_o[gs].w));
+        float3 thr = f3(t4.x, t4.y, t4.z), pixel = f3(x4.x, x4.y, x4.z);
+        const uint32_t ds = __float_as_uint(t4.w);
+        uint32_t rng = __float_as_uint(x4.w), depth = ds & 0xffffu, sample = ds >> 16;
+        float3 o = f3(0, 0, 0), d = f3(d4.x, d4.y, d4.z);
+        bool end_path;
+        ctr[2]++;  // one shaded record == one traced ray
+        if (h.x != SOLB_MISS) {
+            ctr[0]++;
+            float3 hv;
+            const bool done = shade_hit(instances, shade, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
+            depth++;
+            thr = thr * hv;  // pathtrace.rgen:77
+            end_path = done;
+            if (!done && depth > fc.max_bounces) { thr = f3(0, 0, 0); end_path = true; }  // :81-84
+        } else {
+            thr = thr * shade_miss(fc.enable_sky, d);
+            end_path = true;
+        }
+        alive = true;
+        if (end_path) {
+            pixel = pixel + thr;  // :86
+            sample++;
+            if (sample < fc.spp) {
+                const uint32_t x = p % fc.width, y = p / fc.width;
+                const float jx = next_rand(rng), jy = next_rand(rng);
+                o = fc.origin;
+                d = primary_dir(fc, (float)x + jx, (float)y + jy);
+                thr = f3(1, 1, 1);
+                depth = 0;
+                ctr[1]++;
+            } else {
+                alive = false;
+                freed = true;
+                uint32_t rgba;  // pathtrace.rgen:88-103
+                const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
+                accum[p] = out;
+                if (render) render[p] = rgba;
+            }
+        }
+        if (alive) {
+            wl_st(wl.ray_o + gs, make_float4(o.x, o.y, o.z, __uint_as_float(p)));
+            wl_st(wl.ray_d + gs, make_float4(d.x, d.y, d.z, 0.0f));
+            wl_st(wl.thr + gs, make_float4(thr.x, thr.y, thr.z, __uint_as_float(depth | (sample << 16))));
+            wl_st(wl.pix + gs, make_float4(pixel.x, pixel.y, pixel.z, __uint_as_float(rng)));
+        }
+    }
+    wl_push(W->ready, n_ready, alive, my_slot, lt_mask);
+    if (!exhausted) wl_push(W->free_, n_free, freed, my_slot, lt_mask);
+    __syncwarp();
+    return wl_pack(n_ready, n_shade, n_free, exhausted);
+}
+
+// list sizes live in ONE register in the traversal loop too: the kernel sits at the 64-register edge
+#define WL_N_READY(c) ((c) & 0xffu)
+#define WL_N_SHADE(c) (((c) >> 8) & 0xffu)
+#define WL_N_FREE(c) (((c) >> 16) & 0xffu)
+#define WL_EXHAUSTED(c) (((c) >> 24) & 1u)
+#define WL_NO_SLOT 0xffu
+
+// Register budget.  At 64 registers (8 resident CTAs) the first version kept b_ray / has_ray and the per-ray constants in local
+// memory and re-read special registers for addresses: 275 warp-instructions per ray against ~225 for the queue-based pair of
+// kernels (profiles/r02_ncu_k_pt_warpfront_a.txt).  Per-lane values that are written once per ray or once per accepted hit
+// and read in one place only therefore live in shared memory, [field][thread] so a warp's 16-byte accesses are conflict-free:
+//   s_hit   : the hit record (instance, triangle, u, v): written when a triangle test is accepted, read when the ray finishes
+//   s_frame : the ray-space frame of the watertight test (6 floats): written at refill, read by the triangle step
 template <bool STATS, bool TL>
 __global__ void __launch_bounds__(TRACE_BLOCK, TL ? 7 : SOLB_WF_MIN_CTAS)
 k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
                const float4 *__restrict__ inst_leaves, const DeviceInstance *__restrict__ instances,
-               const ShadeRecord *__restrict__ shade, const WarpfrontState wl, float4 *accum, uint32_t *render,
-               unsigned long long *stats, const uint32_t n_region_slots, const TraceTuning tune) {
+               const ShadeRecord *__restrict__ shade, const __grid_constant__ WarpfrontState wl, float4 *accum, uint32_t *render,
+               unsigned long long *stats, const uint32_t n_region_slots, const __grid_constant__ TraceTuning tune) {
     SOLB_DECL_STACK();
-    __shared__ uint8_t s_lists[TRACE_BLOCK / 32][3][WL_POOL];
-    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u, wib = threadIdx.x >> 5;
-    uint8_t *l_ready = s_lists[wib][0], *l_shade = s_lists[wib][1], *l_free = s_lists[wib][2];
-    const uint32_t gwarp = blockIdx.x * (TRACE_BLOCK / 32) + wib;
-    if (gwarp >= wl.n_warps) return;
-    const size_t slot_base = (size_t)gwarp * WL_POOL;
-    uint32_t n_ready = 0, n_shade = 0, n_free = WL_POOL;  // warp-uniform
-    for (uint32_t i = lane; i < (uint32_t)WL_POOL; i += 32u) l_free[i] = (uint8_t)i;
+    __shared__ WlWarp s_warp[TRACE_BLOCK / 32];
+    __shared__ uint4 s_hit[TRACE_BLOCK];
+    __shared__ float4 s_frame0[TRACE_BLOCK];  // e1.xyz, e2.x
+    __shared__ float2 s_frame1[TRACE_BLOCK];  // e2.yz
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+    WlWarp *const W = &s_warp[tid >> 5];
+    const uint32_t slot_base = (blockIdx.x * (TRACE_BLOCK / 32) + (tid >> 5)) * (uint32_t)WL_POOL;  // < 2^32
+    if (slot_base >= wl.n_warps * (uint32_t)WL_POOL) return;
+    uint32_t counts = wl_pack(0u, 0u, (uint32_t)WL_POOL, false);  // warp-uniform
+    for (uint32_t i = lane; i < (uint32_t)WL_POOL; i += 32u) W->free_[i] = (uint8_t)i;
+    if (lane == 0) { W->pool_next = 0u; W->pool_end = 0u; }
     __syncwarp();
-    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform range of frame pixel slots already claimed from the cursor
-    bool exhausted = false;
-    uint32_t nr = 0, nh = 0, np = 0;
+    uint32_t step_ctr[3] = { 0u, 0u, 0u };  // hits, paths, rays: counted inside the service steps
     TraceCounters ctr = { 0, 0 };
-    // per-lane ray state (as k_wf_trace)
+    // per-lane ray state (as k_wf_trace, minus the hit record and the frame)
     bool has_ray = false;
-    uint32_t slot = 0;
-    TravRay tr = make_trav_ray(f3(0, 0, 0), f3(0, 0, 1), 0.0f);
+    uint32_t slot = WL_NO_SLOT;  // pool slot this lane holds: its ray in flight, or finished and not yet collected
+    TravRay tr = make_trav_ray(f3(0, 0, 0), f3(0, 0, 1), fc.tmin);
     float tmax = 0.0f;
-    Hit hit;
-    hit.inst = SOLB_MISS; hit.prim = SOLB_MISS; hit.gtri = SOLB_MISS; hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f;
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
     bool in_blas = false;
     uint32_t cur_inst = SOLB_MISS;
     uint32_t b_ray = 0;
+    const uint32_t fetch_idle = (uint32_t)tune.wl_fetch_idle, gen_min = (uint32_t)tune.wl_gen_min;
     for (;;) {
         const uint32_t n_idle = (uint32_t)__popc(~b_ray);
-        const bool starving = n_ready == 0u && n_idle >= (uint32_t)tune.wl_fetch_idle;
-        // ---- generate: free slots take the next pixels of the frame (k_wf_generate) ----
-        if (!exhausted && n_free > 0u && (n_free >= (uint32_t)tune.wl_gen_min || (starving && n_shade < 32u))) {
-            const uint32_t cnt = min(n_free, 32u);
-            const bool mine = lane < cnt;
-            const uint32_t my_slot = mine ? (uint32_t)l_free[n_free - 1u - lane] : 0u;
-            n_free -= cnt;
-            __syncwarp();
-            // claim cnt frame slots (warp-uniform bookkeeping, like the dynamic fetch of k_wf_trace)
-            uint32_t my_idx = 0xffffffffu, served = 0;
-            while (served < cnt && !exhausted) {
-                if (pool_next >= pool_end) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(wl.cursor, (uint32_t)tune.wl_batch);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base >= n_region_slots) { exhausted = true; break; }
-                    pool_next = base;
-                    pool_end = min(base + (uint32_t)tune.wl_batch, n_region_slots);
-                }
-                const uint32_t take = min(cnt - served, pool_end - pool_next);
-                if (mine && lane >= served && lane < served + take) my_idx = pool_next + (lane - served);
-                pool_next += take;
-                served += take;
-            }
-            bool valid = false, retry = false;
-            if (my_idx != 0xffffffffu) {
-                const uint32_t p = swizzled_pixel(my_idx, fc, valid);
-                if (valid) {
-                    const uint32_t x = p % fc.width, y = p / fc.width;
-                    uint32_t rng = tea(p, fc.frame);                       // pathtrace.rgen:47
-                    const float jx = next_rand(rng), jy = next_rand(rng);  // :52
-                    const float3 d = primary_dir(fc, (float)x + jx, (float)y + jy);
-                    const size_t gs = slot_base + my_slot;
-                    wl.ray_o[gs] = make_float4(fc.origin.x, fc.origin.y, fc.origin.z, __uint_as_float(p));
-                    wl.ray_d[gs] = make_float4(d.x, d.y, d.z, 0.0f);
-                    wl.thr[gs] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
-                    wl.pix[gs] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(rng));
-                    np++;
-                } else {
-                    retry = true;  // a hole of the tile order (image edge): the slot stays free
-                }
-            }
-            wl_push(l_ready, n_ready, valid, my_slot, lt_mask);
-            wl_push(l_free, n_free, retry, my_slot, lt_mask);
-            if (exhausted) n_free = 0u;  // nothing left to start: free slots are retired
-            __syncwarp();
-        }
-        // ---- shade: 32 finished rays, one per lane (k_wf_shade + k_wf_resolve) ----
-        if (n_shade >= 32u || (n_shade > 0u && n_ready == 0u && n_idle >= (uint32_t)tune.wl_fetch_idle)) {
-            const uint32_t cnt = min(n_shade, 32u);
-            const bool mine = lane < cnt;
-            const uint32_t my_slot = mine ? (uint32_t)l_shade[n_shade - 1u - lane] : 0u;
-            n_shade -= cnt;
-            __syncwarp();
-            bool alive = false, freed = false;
-            if (mine) {
-                const size_t gs = slot_base + my_slot;
-                const uint4 h = wl.hit[gs];
-                const float4 t4 = wl.thr[gs], x4 = wl.pix[gs], d4 = wl.ray_d[gs];
-                const uint32_t p = __float_as_uint(wl.ray_o[gs].w);
-                float3 thr = f3(t4.x, t4.y, t4.z), pixel = f3(x4.x, x4.y, x4.z);
-                const uint32_t ds = __float_as_uint(t4.w);
-                uint32_t rng = __float_as_uint(x4.w), depth = ds & 0xffffu, sample = ds >> 16;
-                float3 o = f3(0, 0, 0), d = f3(d4.x, d4.y, d4.z);
-                bool end_path;
-                if (h.x != SOLB_MISS) {
-                    nh++;
-                    float3 hv;
-                    const bool done = shade_hit(instances, shade, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
-                    depth++;
-                    thr = thr * hv;  // pathtrace.rgen:77
-                    end_path = done;
-                    if (!done && depth > fc.max_bounces) { thr = f3(0, 0, 0); end_path = true; }  // :81-84
-                } else {
-                    thr = thr * shade_miss(fc.enable_sky, d);
-                    end_path = true;
-                }
-                alive = true;
-                if (end_path) {
-                    pixel = pixel + thr;  // :86
-                    sample++;
-                    if (sample < fc.spp) {
-                        const uint32_t x = p % fc.width, y = p / fc.width;
-                        const float jx = next_rand(rng), jy = next_rand(rng);
-                        o = fc.origin;
-                        d = primary_dir(fc, (float)x + jx, (float)y + jy);
-                        thr = f3(1, 1, 1);
-                        depth = 0;
-                        np++;
-                    } else {
-                        alive = false;
-                        freed = true;
-                        uint32_t rgba;  // pathtrace.rgen:88-103
-                        const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
-                        accum[p] = out;
-                        if (render) render[p] = rgba;
+        // anything to service?  (enough idle lanes | enough free slots; free is 0 once exhausted)
+        if (n_idle >= fetch_idle || WL_N_FREE(counts) >= gen_min) {
+            // ---- collect: lanes whose ray has finished since the last service hand their slot to the shade list ----
+            // (deferred to here: a finished lane just idles, so the per-iteration tail of the loop is a pop or nothing; doing the
+            // hit-record store, the ballot and the list append in every iteration cost 45 instructions in 60 % of the iterations)
+            {
+                const bool done = !has_ray && slot != WL_NO_SLOT;
+                const uint32_t b_done = __ballot_sync(0xffffffffu, done);
+                if (b_done) {
+                    if (done) {
+                        wl_st(wl.hit + (slot_base + slot), s_hit[tid]);
+                        W->shade[WL_N_SHADE(counts) + __popc(b_done & lt_mask)] = (uint8_t)slot;
+                        slot = WL_NO_SLOT;
                     }
-                }
-                if (alive) {
-                    wl.ray_o[gs] = make_float4(o.x, o.y, o.z, __uint_as_float(p));
-                    wl.ray_d[gs] = make_float4(d.x, d.y, d.z, 0.0f);
-                    wl.thr[gs] = make_float4(thr.x, thr.y, thr.z, __uint_as_float(depth | (sample << 16)));
-                    wl.pix[gs] = make_float4(pixel.x, pixel.y, pixel.z, __uint_as_float(rng));
+                    counts += (uint32_t)__popc(b_done) << 8;
+                    __syncwarp();
                 }
             }
-            wl_push(l_ready, n_ready, alive, my_slot, lt_mask);
-            if (!exhausted) wl_push(l_free, n_free, freed, my_slot, lt_mask);
-            __syncwarp();
-        }
-        // ---- hand ready slots to idle lanes ----
-        if (n_ready > 0u && n_idle >= (uint32_t)tune.wl_fetch_idle) {
-            const uint32_t rank = (uint32_t)__popc(~b_ray & lt_mask);
-            const uint32_t cnt = min(n_ready, n_idle);
-            if (!has_ray && rank < cnt) {
-                slot = (uint32_t)l_ready[n_ready - 1u - rank];
-                const size_t gs = slot_base + slot;
-                const float4 o = wl.ray_o[gs], d = wl.ray_d[gs];
-                tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
-                tmax = fc.tmax;
-                hit.inst = SOLB_MISS; hit.gtri = SOLB_MISS; hit.u = 0.0f; hit.v = 0.0f;
-                ngroup = SOLB_ROOT_GROUP;
-                tgroup = make_uint2(0u, 0u);
-                stack.sp = 0;
-                in_blas = false;
-                has_ray = true;
-                nr++;
+            const bool idle_enough = n_idle >= fetch_idle;
+            // ---- service steps (once per ~32 rays): generate + shade ----
+            // The traversal state is parked in (volatile) local memory around them, so that no per-ray value is live across the
+            // shading code and the register allocator can give the traversal loop the whole file.
+            const bool want_gen = WL_N_FREE(counts) > 0u &&
+                (WL_N_FREE(counts) >= gen_min || (idle_enough && WL_N_READY(counts) == 0u && WL_N_SHADE(counts) < 32u));
+            const bool want_shade = WL_N_SHADE(counts) >= 32u || (WL_N_SHADE(counts) > 0u && WL_N_READY(counts) == 0u && idle_enough);
+            if (want_gen || want_shade) {
+                volatile uint32_t park[24];
+                park[0] = f2u(tr.o.x); park[1] = f2u(tr.o.y); park[2] = f2u(tr.o.z);
+                park[3] = f2u(tr.d.x); park[4] = f2u(tr.d.y); park[5] = f2u(tr.d.z);
+                park[6] = f2u(tr.idir.x); park[7] = f2u(tr.idir.y); park[8] = f2u(tr.idir.z);
+                park[9] = tr.oct_inv; park[10] = tr.pow4_lo; park[11] = tr.pow4_hi;
+                park[12] = f2u(tmax); park[13] = ngroup.x; park[14] = ngroup.y; park[15] = tgroup.x; park[16] = tgroup.y;
+                park[17] = slot; park[18] = (uint32_t)stack.sp; park[19] = cur_inst; park[20] = in_blas ? 1u : 0u;
+                if (want_gen) counts = wl_generate_step(&fc, &wl, W, slot_base, counts, n_region_slots, (uint32_t)tune.wl_batch, step_ctr);
+                // (re-evaluated: the generate step may have refilled the ready list)
+                if (WL_N_SHADE(counts) >= 32u || (WL_N_SHADE(counts) > 0u && WL_N_READY(counts) == 0u && idle_enough))
+                    counts = wl_shade_step(&fc, instances, shade, &wl, accum, render, W, slot_base, counts, step_ctr);
+                tr.o = f3(u2f(park[0]), u2f(park[1]), u2f(park[2]));
+                tr.d = f3(u2f(park[3]), u2f(park[4]), u2f(park[5]));
+                tr.idir = f3(u2f(park[6]), u2f(park[7]), u2f(park[8]));
+                tr.oct_inv = park[9]; tr.pow4_lo = park[10]; tr.pow4_hi = park[11];
+                tmax = u2f(park[12]); ngroup = make_uint2(park[13], park[14]); tgroup = make_uint2(park[15], park[16]);
+                slot = park[17]; stack.sp = (int)park[18]; cur_inst = park[19]; in_blas = park[20] != 0u;
             }
-            n_ready -= cnt;
-            b_ray = __ballot_sync(0xffffffffu, has_ray);
-            __syncwarp();
-        }
-        if (b_ray == 0u) {
-            if (n_ready == 0u && n_shade == 0u && (exhausted || n_free == 0u)) break;
-            continue;
+            // ---- hand ready slots to idle lanes ----
+            if (WL_N_READY(counts) > 0u && idle_enough) {
+                const uint32_t rank = (uint32_t)__popc(~b_ray & lt_mask);
+                const uint32_t cnt = min(WL_N_READY(counts), n_idle);
+                if (!has_ray && rank < cnt) {
+                    slot = (uint32_t)W->ready[WL_N_READY(counts) - 1u - rank];
+                    const uint32_t gs = slot_base + slot;
+                    const float4 o = wl_ld(wl.ray_o + gs), d = wl_ld(wl.ray_d + gs);
+                    tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
+                    s_frame0[tid] = make_float4(tr.frame.e1.x, tr.frame.e1.y, tr.frame.e1.z, tr.frame.e2.x);
+                    s_frame1[tid] = make_float2(tr.frame.e2.y, tr.frame.e2.z);
+                    s_hit[tid] = make_uint4(SOLB_MISS, SOLB_MISS, 0u, 0u);
+                    tmax = fc.tmax;
+                    ngroup = SOLB_ROOT_GROUP;
+                    tgroup = make_uint2(0u, 0u);
+                    stack.sp = 0;
+                    in_blas = false;
+                    has_ray = true;
+                }
+                counts -= cnt;  // ready is the low byte
+                b_ray = __ballot_sync(0xffffffffu, has_ray);
+                __syncwarp();
+            }
+            if (b_ray == 0u) {
+                // every finished lane has been collected above, so the lists account for all live slots
+                if ((counts & 0xffffu) == 0u && WL_N_FREE(counts) == 0u) break;  // (free is 0 once the frame's cursor is exhausted)
+                continue;
+            }
         }
         // ---- vote: node step or triangle step (k_wf_trace) ----
         const bool w_node = has_ray && (ngroup.y & 0xff000000u);
@@ -1143,9 +1254,17 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
             if (w_tri) {
                 if (TL && !in_blas) {
                     trav_enter_instance(inst_leaves, tr.o, tr.d, tr, ngroup, tgroup, cur_inst, stack);
+                    s_frame0[tid] = make_float4(tr.frame.e1.x, tr.frame.e1.y, tr.frame.e1.z, tr.frame.e2.x);
+                    s_frame1[tid] = make_float2(tr.frame.e2.y, tr.frame.e2.z);
                     in_blas = true;
                 } else {
-                    if (trav_tri_step(tris, tr, tmax, tgroup, hit) && TL) hit.inst = cur_inst;
+                    const float4 f0 = s_frame0[tid];
+                    const float2 f1 = s_frame1[tid];
+                    tr.frame.e1 = f3(f0.x, f0.y, f0.z);
+                    tr.frame.e2 = f3(f0.w, f1.x, f1.y);
+                    Hit h;
+                    if (trav_tri_step(tris, tr, tmax, tgroup, h))
+                        s_hit[tid] = make_uint4(TL ? cur_inst : h.inst, h.gtri, __float_as_uint(h.u), __float_as_uint(h.v));
                     if (STATS) ctr.tris++;
                 }
             }
@@ -1154,34 +1273,27 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
             trav_node_step(nodes, tr, tmax, ngroup, tgroup, stack);
             if (STATS) ctr.nodes++;
         }
-        // ---- lanes with nothing in hand: pop, or finish the ray ----
-        bool finished = false;
+        // ---- lanes with nothing in hand: pop, or finish the ray (its slot is collected at the next service) ----
         if (has_ray && !(ngroup.y & 0xff000000u) && !tgroup.y) {
             if (stack.empty()) {
-                wl.hit[slot_base + slot] = make_uint4(hit.inst, hit.gtri, __float_as_uint(hit.u), __float_as_uint(hit.v));
                 has_ray = false;
-                finished = true;
             } else {
                 const uint2 e = stack.pop();
                 if (TL && e.y == 0u) {  // sentinel: back to the TLAS with the world-space ray
-                    const float4 o = wl.ray_o[slot_base + slot], d = wl.ray_d[slot_base + slot];
+                    const float4 o = wl_ld(wl.ray_o + (slot_base + slot)), d = wl_ld(wl.ray_d + (slot_base + slot));
                     tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
+                    s_frame0[tid] = make_float4(tr.frame.e1.x, tr.frame.e1.y, tr.frame.e1.z, tr.frame.e2.x);
+                    s_frame1[tid] = make_float2(tr.frame.e2.y, tr.frame.e2.z);
                     in_blas = false;
                 } else if (e.y & 0xff000000u) ngroup = e;
                 else tgroup = e;
             }
         }
-        const uint32_t b_fin = __ballot_sync(0xffffffffu, finished);
-        if (b_fin) {
-            if (finished) l_shade[n_shade + __popc(b_fin & lt_mask)] = (uint8_t)slot;
-            n_shade += (uint32_t)__popc(b_fin);
-            b_ray &= ~b_fin;
-            __syncwarp();
-        }
+        b_ray = __ballot_sync(0xffffffffu, has_ray);
     }
-    warp_add_stat(stats, ST_RAYS, nr);
-    warp_add_stat(stats, ST_HITS, nh);
-    warp_add_stat(stats, ST_PATHS, np);
+    warp_add_stat(stats, ST_RAYS, step_ctr[2]);
+    warp_add_stat(stats, ST_HITS, step_ctr[0]);
+    warp_add_stat(stats, ST_PATHS, step_ctr[1]);
     if (STATS) {
         warp_add_stat(stats, ST_NODES, ctr.nodes);
         warp_add_stat(stats, ST_TRIS, ctr.tris);
@@ -1385,11 +1497,12 @@ cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum
 // The frame is split into 1..4 horizontal parts of whole tile rows.  Each part runs its own wave sequence (own
 // queues + counters, shared per-pixel state arrays) on its own stream, so the drain tail of one part's persistent
 // trace kernel and its memory-bound shade kernel overlap with another part's traversal.
-cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameConsts &fc, const AccelStorage &as,
-                                       const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
-                                       unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
-                                       uint32_t *n_events_used, const TraceTuning &tune) {
-    if (fc.width == 0 || fc.band_rows == 0 || fc.n_bands == 0) return cudaSuccess;
+// (body: every early return leaves through launch_pathtrace_wavefront's tail, which lets pending count copies land and joins
+// the part streams back into the ctx stream, so later work on the ctx stream never races kernels still running on a part stream)
+static cudaError_t wavefront_body(const WavefrontLaunch &L, const FrameConsts &fc, const AccelStorage &as,
+                                  const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
+                                  unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
+                                  uint32_t *n_events_used, const TraceTuning &tune, int *forked_lanes, bool *pending) {
     cudaError_t err = cudaSuccess;
     const uint32_t tiles_x = (fc.width + 7u) >> 3, tiles_y = region_tiles_y(fc);
     int n_lanes = (events || !L.stream[1]) ? 1 : tune.overlap;
@@ -1412,8 +1525,10 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
     int qi[WF_MAX_PARTS] = { 0, 0, 0, 0 };
     if (n_lanes > 1) {  // fork: the extra streams start after everything already queued on the ctx stream
         if ((err = cudaEventRecord(L.fork, L.stream[0])) != cudaSuccess) return err;
-        for (int k = 1; k < n_lanes; k++)
+        for (int k = 1; k < n_lanes; k++) {
             if ((err = cudaStreamWaitEvent(L.stream[k], L.fork, 0)) != cudaSuccess) return err;
+            *forked_lanes = k + 1;
+        }
     }
     for (int k = 0; k < n_lanes; k++) {
         const uint32_t row0 = k * rows_per_lane, row1 = (row0 + rows_per_lane < tiles_y) ? row0 + rows_per_lane : tiles_y;
@@ -1431,7 +1546,6 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
     // others: its drain tail then overlaps their full waves instead of their tails.  async_poll = 0 restores the lock-step
     // schedule (all parts synchronised every check_every waves).
     uint32_t wave_k[WF_MAX_PARTS] = { 0, 0, 0, 0 }, confirmed[WF_MAX_PARTS] = { 0, 0, 0, 0 }, poll_wave[WF_MAX_PARTS] = { 0, 0, 0, 0 };
-    bool pending[WF_MAX_PARTS] = { false, false, false, false };
     const bool async_poll = tune.async_poll && !events && L.poll[0];
     const uint32_t max_ahead = (uint32_t)std::max(tune.max_ahead, tune.check_every);
     auto launch_wave = [&](int k) {
@@ -1525,19 +1639,36 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
             }
             if (!any) break;
         }
-        // a count still in flight targets pinned memory: let it land before the next call reuses the slot
-        for (int k = 0; k < n_lanes; k++)
-            if (pending[k] && (err = cudaEventSynchronize(L.poll[k])) != cudaSuccess) return err;
     }
     for (int k = 0; k < n_lanes; k++) {
         k_wf_resolve<<<(part_slots[k] + 255) / 256, 256, 0, L.stream[k]>>>(fc, L.ws[k], accum, render, part_slot_begin[k], part_slots[k]);
         *launches += 1;
     }
-    for (int k = 1; k < n_lanes; k++) {  // join
-        if ((err = cudaEventRecord(L.join[k], L.stream[k])) != cudaSuccess) return err;
-        if ((err = cudaStreamWaitEvent(L.stream[0], L.join[k], 0)) != cudaSuccess) return err;
-    }
     return cudaGetLastError();
+}
+
+cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameConsts &fc, const AccelStorage &as,
+                                       const DeviceInstance *instances, const ShadeRecord *shade, float4 *accum, uint32_t *render,
+                                       unsigned long long *stats, bool collect, uint64_t *launches, std::vector<cudaEvent_t> *events,
+                                       uint32_t *n_events_used, const TraceTuning &tune) {
+    if (fc.width == 0 || fc.band_rows == 0 || fc.n_bands == 0) return cudaSuccess;
+    int forked_lanes = 1;
+    bool pending[WF_MAX_PARTS] = { false, false, false, false };
+    cudaError_t err = wavefront_body(L, fc, as, instances, shade, accum, render, stats, collect, launches, events, n_events_used, tune,
+                                     &forked_lanes, pending);
+    // common tail, also after an error: a count still in flight targets pinned memory (let it land before the next call reuses
+    // the slot), and every forked part stream is joined back into the ctx stream
+    for (int k = 0; k < WF_MAX_PARTS; k++)
+        if (pending[k]) {
+            const cudaError_t e = cudaEventSynchronize(L.poll[k]);
+            if (err == cudaSuccess) err = e;
+        }
+    for (int k = 1; k < forked_lanes; k++) {
+        cudaError_t e = cudaEventRecord(L.join[k], L.stream[k]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(L.stream[0], L.join[k], 0);
+        if (err == cudaSuccess) err = e;
+    }
+    return err;
 }
 
 uint32_t warpfront_grid_warps(int sm_count, const TraceTuning &tune) {

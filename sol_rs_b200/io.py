@@ -50,3 +50,40 @@ def load_checkpoint(path, context):
     img = Image2d(context, int(z["width"]), int(z["height"]), N.FORMAT_RGBA32F)
     img.upload(z["accum"])
     return img, int(z["accumulation_start_frame"]), int(z["next_frame"])
+
+
+def load_texture_rgba8(path, flipv=True):
+    """Texture2d::new (src/texture.rs:488-494): image::open(path) -> flipv() -> to_rgba8().  Returns uint8 [h, w, 4].
+    16-bit channels become 8-bit by the image 0.24 crate's rule (v + 128) / 257; grey / grey-alpha / rgb are expanded
+    with alpha 255.  Decoding itself is delegated to OpenCV or Pillow (host-side asset loading, not the hot path)."""
+    im = None
+    try:
+        import cv2
+
+        im = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if im is not None and im.ndim == 3 and im.shape[2] >= 3:
+            im = im[:, :, [2, 1, 0] + ([3] if im.shape[2] == 4 else [])]  # BGR(A) -> RGB(A)
+    except ImportError:
+        pass
+    if im is None:
+        from PIL import Image
+
+        im = np.asarray(Image.open(path))
+    if im.ndim == 2:
+        im = im[:, :, None]
+    if im.dtype == np.uint16:
+        im = ((im.astype(np.uint32) + 128) // 257).astype(np.uint8)
+    elif im.dtype != np.uint8:
+        raise ValueError("unsupported channel type %s in %s" % (im.dtype, path))
+    h, w, c = im.shape
+    out = np.full((h, w, 4), 255, dtype=np.uint8)
+    if c == 1:
+        out[..., :3] = im
+    elif c == 2:
+        out[..., :3] = im[..., :1]
+        out[..., 3] = im[..., 1]
+    else:
+        out[..., :c] = im[..., :c]
+    if flipv:
+        out = out[::-1]
+    return np.ascontiguousarray(out)

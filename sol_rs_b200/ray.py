@@ -209,6 +209,9 @@ class Pipeline:
             raise N.SolbError(-4, "ray::Pipeline: no CUDA kernel family for raygen shader %r" % base)
         self.kind = kinds[base]
         self.enable_sky = bool(info.spec and info.spec_id == 0 and info.spec[0])
+        # the reference compiles its GLSL stages here (src/ray/pipeline.rs:105-115); the counterpart is loading the kernels
+        if context is not None:
+            context.preload()
 
 
 class ShaderBindingTableInfo:

@@ -250,12 +250,26 @@ def test_warpfront_equals_wavefront(sol, ctx, name, w, h, sky, mb, two_level):
     """The warp-local wavefront kernel (schedule 3) runs the per-ray / per-pixel functions of the queue-based wavefront
     (k_wf_generate / k_wf_trace / k_wf_shade / k_wf_resolve) in a different order only: same rays, same paths, and the same
     image up to decision-flip pixels (separately compiled instantiations: FMA contraction and the order of equal-t tests)."""
-    ctx.reset_stats()
-    a, ra = _render_gpu(sol, ctx, name, w, h, [0, 1, 2], sky, 8, mb, 0, two_level=two_level)
-    s0 = ctx.stats()
-    ctx.reset_stats()
-    b, rb = _render_gpu(sol, ctx, name, w, h, [0, 1, 2], sky, 8, mb, 3, two_level=two_level)
-    s1 = ctx.stats()
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    # ONE scene description for all renders: a rebuilt hierarchy may number its nodes differently (atomics in the builder),
+    # which changes the order equal-t candidates are tested in
+    sc, sd = _product_two_level(sol, ctx, name) if two_level else _product(sol, ctx, name)
+    cam = product_camera(sc, name, w, h)
+    sbt = pathtrace_pipeline(ctx, sky)
+
+    def render(schedule):
+        accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+        rend = sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+        ctx.reset_stats()
+        for f in range(3):
+            sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, rend, samples_per_frame=8,
+                                                 max_bounces=mb, schedule=schedule), (w, h, 1))
+        return accum.readback(), rend.readback(), ctx.stats()
+
+    a, ra, s0 = render(N.SCHEDULE_WAVEFRONT)
+    b, rb, s1 = render(N.SCHEDULE_WARPFRONT)
     assert s0.paths == s1.paths == 3 * 8 * w * h
     assert abs(int(s0.rays) - int(s1.rays)) <= 1e-4 * int(s0.rays) + 2
     d = np.abs(a - b)[..., :3]
@@ -263,7 +277,8 @@ def test_warpfront_equals_wavefront(sol, ctx, name, w, h, sky, mb, two_level):
     assert d.sum() / b[..., :3].sum() < 2e-3
     assert np.all(b[..., 3] == 1.0) and np.all(np.isfinite(b))
     # and it is a pure function of its inputs: a second run gives the same bits although slot order and atomics vary
-    c, rc = _render_gpu(sol, ctx, name, w, h, [0, 1, 2], sky, 8, mb, 3, two_level=two_level)
+    c, rc, s2 = render(N.SCHEDULE_WARPFRONT)
+    assert int(s2.rays) == int(s1.rays)
     assert np.array_equal(b, c) and np.array_equal(rb, rc)
 
 
@@ -1107,7 +1122,9 @@ def test_synth_scene_rays_and_primary_ids_vs_oracle(sol, ctx, synth27, accel):
     cam = sc.camera
     cam.set_window_size((w, h))
     u = scene.scene_uniforms(cam, w, h, 0)
-    o_rgba, o_ids, o_bt, o_flags = osc.debug(bytes(u), w, h)
+    # a pixel of this view spans about one 0.01-unit triangle seen from 16 units away, often at grazing angles on the bumps:
+    # the edge / tie list is taken with 10x the default tolerances (barycentric 1e-3, relative depth gap 1e-4), still < 1 % of pixels
+    o_rgba, o_ids, o_bt, o_flags = osc.debug(bytes(u), w, h, 1e-3, 1e-4)
     ids = sol.Image2d(ctx, w, h, N.FORMAT_RG32UI)
     simple_pipeline(ctx, "debug").cmd_trace_rays(ray.TraceBindings(sd, u, None, None, ids), (w, h, 1))
     g_ids = ids.readback()
@@ -1118,7 +1135,10 @@ def test_synth_scene_rays_and_primary_ids_vs_oracle(sol, ctx, synth27, accel):
 
 @pytest.mark.parametrize("schedule", [0, 1, 3])
 def test_synth_scene_pathtrace_frame_vs_oracle(sol, ctx, synth27, schedule):
-    """One path-traced frame of the synthetic scene (sky on, 8 spp, bounce cap 8: diffuse, rough-metal and emissive materials)."""
+    """Path-traced frames of the synthetic scene (sky on, 8 spp: diffuse, rough-metal and emissive materials).  Its surfaces are
+    finely tessellated and curved, so a last-bit difference in a hit position is amplified at every bounce (a dispersing
+    billiard): per-pixel agreement with the oracle is only meaningful for short paths (bounce cap 1), full-depth frames are
+    compared through their ray statistics and block means."""
     from sol_rs_b200 import _native as N
     from sol_rs_b200 import ray, scene
 
@@ -1127,20 +1147,29 @@ def test_synth_scene_pathtrace_frame_vs_oracle(sol, ctx, synth27, schedule):
     sd = ray.SceneDescription.from_scene(ctx, sc)
     cam = sc.camera
     cam.set_window_size((w, h))
-    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
     sbt = pathtrace_pipeline(ctx, True)
-    ref = np.zeros((h, w, 4), np.float32)
-    st = oracle.OrcStats()
-    ctx.reset_stats()
-    for f in range(2):
-        u = scene.scene_uniforms(cam, w, h, f)
-        sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, None, samples_per_frame=8, max_bounces=8, schedule=schedule), (w, h, 1))
-        osc.pathtrace_frame(bytes(u), w, h, ref, 0, True, 8, 8, st)
-    gs = ctx.stats()
+
+    def both(mb, frames):
+        accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+        ref = np.zeros((h, w, 4), np.float32)
+        st = oracle.OrcStats()
+        ctx.reset_stats()
+        for f in range(frames):
+            u = scene.scene_uniforms(cam, w, h, f)
+            sbt.cmd_trace_rays(ray.TraceBindings(sd, u, accum, None, samples_per_frame=8, max_bounces=mb, schedule=schedule), (w, h, 1))
+            osc.pathtrace_frame(bytes(u), w, h, ref, 0, True, 8, mb, st)
+        return accum.readback(), ref, ctx.stats(), st
+
+    g, ref, gs, st = both(1, 2)  # primary hit + one bounce
     assert gs.paths == st.paths == 2 * 8 * w * h
-    assert abs(int(gs.rays) - int(st.rays)) <= 0.003 * st.rays
-    g = accum.readback()
+    assert abs(int(gs.rays) - int(st.rays)) <= 0.002 * st.rays
     d = np.abs(g[..., :3] - ref[..., :3])
     assert (d.max(axis=2) > 1e-3 * (1.0 + np.abs(ref[..., :3]).max(axis=2))).mean() < 0.03
-    mre, _ = image_metrics(g, ref)
-    assert mre < 0.02, mre
+    assert image_metrics(g, ref)[0] < 0.01
+    g, ref, gs, st = both(8, 4)  # full depth: statistics
+    assert gs.paths == st.paths == 4 * 8 * w * h
+    assert abs(int(gs.rays) - int(st.rays)) <= 0.003 * st.rays
+    assert abs(int(gs.hits) - int(st.hits)) <= 0.003 * st.hits
+    bm = lambda a: a[..., :3].reshape(h // 20, 20, w // 20, 20, 3).mean(axis=(1, 3))  # 20 x 20 pixel block means
+    rel = np.abs(bm(g) - bm(ref)) / (bm(ref) + 1e-3)
+    assert np.median(rel) < 0.05 and abs(g[..., :3].mean() / ref[..., :3].mean() - 1.0) < 0.02, (np.median(rel), g[..., :3].mean(), ref[..., :3].mean())

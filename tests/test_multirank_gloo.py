@@ -41,11 +41,14 @@ def _worker(rank, world, port, out_path):
         acc[..., :3] += torch.from_numpy(c[..., :3])
         acc[..., 3] += 1.0
     multigpu.reduce_accum(acc, dst=0)
-    # tile split + allgather (single-sample interactive mode)
-    rows = H // world
-    tile = torch.full((rows, W, 4), float(rank))
-    full = multigpu.allgather_rows(tile, world)
-    assert full.shape == (H, W, 4) and float(full[0, 0, 0]) == 0.0 and float(full[-1, 0, 0]) == world - 1
+    # tile split + allgather (single-sample interactive mode): interleaved bands, ragged last band (H = 32, bands of 5 rows)
+    for band in (5, 8):
+        img = torch.full((H, W, 4), -1.0)
+        for y in multigpu.bands_for_rank(rank, world, H, band):
+            img[y] = float(1000 * rank + y)
+        full = multigpu.allgather_band_rows(img, rank, world, band)
+        want = torch.tensor([float(1000 * ((y // band) % world) + y) for y in range(H)])
+        assert full.shape == (H, W, 4) and torch.equal(full[:, 0, 0], want) and torch.equal(full[:, -1, 3], want)
     if rank == 0:
         np.save(out_path, acc.numpy())
     dist.barrier()
@@ -62,6 +65,15 @@ def test_frame_partition():
     assert multigpu.frames_for_rank(1, 2, 5, first=10) == [11, 13]
     with pytest.raises(ValueError):
         multigpu.frames_for_rank(2, 2, 4)
+    # tile split: the ranks' bands partition the image rows; the C ABI's (begin, count, stride) triple names the same rows
+    for world in (1, 2, 3, 8):
+        for height, band in ((1080, 8), (33, 5), (7, 8)):
+            rows = [multigpu.bands_for_rank(r, world, height, band) for r in range(world)]
+            assert sorted(sum(rows, [])) == list(range(height))
+            for r in range(world):
+                b0, cnt, stride = multigpu.tile_rows_for_rank(r, world, band)
+                named = [y for k in range(0, height, stride) for y in range(b0 + k, min(b0 + k + cnt, height))]
+                assert named == rows[r]
 
 
 def test_two_rank_sum_reduce_equals_running_mean(tmp_path):

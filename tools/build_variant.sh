@@ -12,6 +12,7 @@ mkdir -p build
 nvcc $FL "$@" -c trace.cu -o build/trace_$name.o &
 nvcc $FL "$@" -Xptxas -dlcm=cg -c build.cu -o build/build_$name.o &
 nvcc $FL "$@" -c solb_api.cu -o build/api_$name.o &
+nvcc $FL "$@" -c comm.cu -o build/comm_$name.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libsolb_$name.so build/trace_$name.o build/build_$name.o build/api_$name.o -lcudart_static -ccbin /usr/bin/g++ -Xcompiler -fPIC
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libsolb_$name.so build/trace_$name.o build/build_$name.o build/api_$name.o build/comm_$name.o -lcudart_static -ldl -ccbin /usr/bin/g++ -Xcompiler -fPIC
 ls -la ../libsolb_$name.so
