@@ -571,6 +571,177 @@ __global__ void k_bottom_up_dp(int n, const BNode *bn, const int *parent, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// PLOC: parallel locally-ordered clustering (Meister & Bittner 2018; the radius and the single-pass iteration after Benthin
+// et al. 2022, "PLOC++").  Replaces LBVH + refit + treelet restructuring + the bottom-up DP pass for the flattened build: the
+// Morton-sorted leaves are the initial clusters; every iteration each cluster looks PLOC_R clusters to its left and right for
+// the neighbour whose union with it has the smallest area, mutual nearest neighbours are merged into a new binary node, and
+// the cluster array is compacted in place (order preserved).  The array shrinks by 30-45 % per iteration, ~40 iterations at
+// 20 M triangles.  Box, triangle count, SAH cost and the optimal-collapse table of a new node are computed when it is
+// created, so no separate bottom-up pass (a pointer chase with one atomic per node) is needed afterwards.
+// The treelet pass this replaces spent 44.5 of the 62 ms of a 20 M-triangle build at 7.7 of 32 lanes active
+// (profiles/r01_launch_shares_build_20m.txt, r01_ncu_k_bottom_up_coop.txt).
+constexpr int PLOC_CH = 256;  // clusters per block
+#ifndef SOLB_PLOC_R
+#define SOLB_PLOC_R 8
+#endif
+constexpr int PLOC_R = SOLB_PLOC_R;  // search radius
+
+__global__ void k_ploc_init(int n, const uint32_t *__restrict__ sorted_prim, const float4 *__restrict__ prim_lo,
+                            const float4 *__restrict__ prim_hi, BNode *bn, int *parent, int *node_count, float *node_cost, DpEntry *dp,
+                            const DpCost cost, float4 *c_lo, float4 *c_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = sorted_prim[i];
+    const float4 a = prim_lo[g], b = prim_hi[g];
+    BNode leaf;
+    leaf.lo = f3(a.x, a.y, a.z); leaf.hi = f3(b.x, b.y, b.z); leaf.left = -1; leaf.right = -1;
+    const int node = n - 1 + i;
+    bn[node] = leaf;
+    node_count[node] = 1;
+    const float area = half_area(leaf.lo, leaf.hi);
+    node_cost[node] = SOLB_SAH_CT * area;
+    if (dp) {
+        DpEntry e;
+        dp_leaf_entry(e, area, cost);
+        dp[node] = e;
+    }
+    c_lo[i] = make_float4(a.x, a.y, a.z, __int_as_float(node));
+    c_hi[i] = make_float4(b.x, b.y, b.z, __int_as_float(1));
+    if (i == 0) parent[0] = -1;
+}
+
+// One PLOC iteration over n_clusters clusters: nearest neighbours, merges, block-local compaction into tmp (block b's
+// survivors at tmp[b * PLOC_CH ...]) and their number in block_counts[b].
+__global__ void __launch_bounds__(PLOC_CH) k_ploc_merge(int n_prims, int n_clusters, const float4 *__restrict__ in_lo,
+                                                        const float4 *__restrict__ in_hi, float4 *tmp_lo, float4 *tmp_hi,
+                                                        uint32_t *block_counts, uint32_t *node_counter, BNode *bn, int *parent,
+                                                        int *node_count, float *node_cost, DpEntry *dp, const DpCost cost) {
+    constexpr int W = PLOC_CH + 4 * PLOC_R;  // the chunk and 2 R clusters on either side
+    __shared__ float4 s_lo[W], s_hi[W];
+    __shared__ int s_nn[PLOC_CH + 2 * PLOC_R];  // nearest neighbour (global index) of local items R .. R + CH + 2 R - 1
+    __shared__ uint32_t s_warp_valid[PLOC_CH / 32], s_warp_merge[PLOC_CH / 32], s_node_base;
+    const int tid = threadIdx.x;
+    const int g0 = blockIdx.x * PLOC_CH - 2 * PLOC_R;  // global index of local item 0
+    for (int l = tid; l < W; l += PLOC_CH) {
+        const int g = g0 + l;
+        if (g >= 0 && g < n_clusters) { s_lo[l] = in_lo[g]; s_hi[l] = in_hi[g]; }
+    }
+    __syncthreads();
+    // nearest neighbour of the chunk's clusters and of the R clusters on either side (their choice decides mutuality).
+    // Ties go to the smaller index, which is the symmetric order (area, min(i, j), max(i, j)): the globally smallest pair is
+    // always mutual, so every iteration merges at least once.
+    for (int q = tid; q < PLOC_CH + 2 * PLOC_R; q += PLOC_CH) {
+        const int l = PLOC_R + q, g = g0 + l;
+        int best = -1;
+        if (g >= 0 && g < n_clusters) {
+            const float4 lo = s_lo[l], hi = s_hi[l];
+            float best_a = 3.4e38f;
+#pragma unroll
+            for (int d = -PLOC_R; d <= PLOC_R; d++) {
+                if (d == 0) continue;
+                const int gj = g + d;
+                if (gj < 0 || gj >= n_clusters) continue;
+                const float4 lo2 = s_lo[l + d], hi2 = s_hi[l + d];
+                const float ex = fmaxf(hi.x, hi2.x) - fminf(lo.x, lo2.x), ey = fmaxf(hi.y, hi2.y) - fminf(lo.y, lo2.y),
+                            ez = fmaxf(hi.z, hi2.z) - fminf(lo.z, lo2.z);
+                const float a = ex * ey + ey * ez + ez * ex;
+                if (a < best_a) { best_a = a; best = gj; }
+            }
+        }
+        s_nn[q] = best;
+    }
+    __syncthreads();
+    const int l = 2 * PLOC_R + tid, g = g0 + l;  // this thread's cluster
+    const bool have = g < n_clusters;
+    int partner = -1;
+    if (have) {
+        const int j = s_nn[PLOC_R + tid];
+        if (j >= 0 && s_nn[j - g0 - PLOC_R] == g) partner = j;
+    }
+    const bool winner = partner > g;             // the left cluster of a mutual pair creates the node
+    const bool valid = have && !(partner >= 0 && partner < g);  // the right one disappears
+    // ranks inside the block
+    const uint32_t lane = tid & 31, wid = tid >> 5;
+    const uint32_t b_valid = __ballot_sync(0xffffffffu, valid), b_merge = __ballot_sync(0xffffffffu, winner);
+    if (lane == 0) { s_warp_valid[wid] = __popc(b_valid); s_warp_merge[wid] = __popc(b_merge); }
+    __syncthreads();
+    uint32_t valid_before = 0, merge_before = 0, valid_total = 0, merge_total = 0;
+#pragma unroll
+    for (int w = 0; w < PLOC_CH / 32; w++) {
+        if (w < (int)wid) { valid_before += s_warp_valid[w]; merge_before += s_warp_merge[w]; }
+        valid_total += s_warp_valid[w];
+        merge_total += s_warp_merge[w];
+    }
+    if (tid == 0) {
+        s_node_base = merge_total ? atomicAdd(node_counter, merge_total) : 0u;
+        block_counts[blockIdx.x] = valid_total;
+    }
+    __syncthreads();
+    if (!valid) return;
+    float4 lo = s_lo[l], hi = s_hi[l];
+    if (winner) {
+        const float4 lo2 = s_lo[partner - g0], hi2 = s_hi[partner - g0];
+        const int left = __float_as_int(lo.w), right = __float_as_int(lo2.w);
+        const int cnt = __float_as_int(hi.w) + __float_as_int(hi2.w);
+        // internal nodes are numbered from the top down so that the last merge (the root) gets index 0 (Karras numbering)
+        const int node = (n_prims - 2) - (int)(s_node_base + merge_before + __popc(b_merge & ((1u << lane) - 1u)));
+        BNode b;
+        b.lo = f3(fminf(lo.x, lo2.x), fminf(lo.y, lo2.y), fminf(lo.z, lo2.z));
+        b.hi = f3(fmaxf(hi.x, hi2.x), fmaxf(hi.y, hi2.y), fmaxf(hi.z, hi2.z));
+        b.left = left; b.right = right;
+        bn[node] = b;
+        parent[left] = node;
+        parent[right] = node;
+        node_count[node] = cnt;
+        const float area = half_area(b.lo, b.hi);
+        node_cost[node] = leaf_or_internal_cost(area, node_cost[left] + node_cost[right], cnt);
+        if (dp) {
+            const DpEntry dl = dp[left], dr = dp[right];
+            DpEntry e;
+            dp_inner_entry(e, dl, dr, area, cnt, cost);
+            dp[node] = e;
+        }
+        lo = make_float4(b.lo.x, b.lo.y, b.lo.z, __int_as_float(node));
+        hi = make_float4(b.hi.x, b.hi.y, b.hi.z, __int_as_float(cnt));
+    }
+    const uint32_t rank = valid_before + __popc(b_valid & ((1u << lane) - 1u));
+    tmp_lo[(size_t)blockIdx.x * PLOC_CH + rank] = lo;
+    tmp_hi[(size_t)blockIdx.x * PLOC_CH + rank] = hi;
+}
+
+// exclusive scan of the per-block survivor counts (one block); total -> *n_out
+__global__ void __launch_bounds__(1024) k_ploc_scan(const uint32_t *__restrict__ block_counts, uint32_t n_blocks, uint32_t *offsets,
+                                                    uint32_t *n_out) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t tid = threadIdx.x, per = (n_blocks + 1023u) / 1024u;
+    const uint32_t b0 = tid * per, b1 = min(b0 + per, n_blocks);
+    uint32_t sum = 0;
+    for (uint32_t b = b0; b < b1; b++) sum += block_counts[b];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024u; d <<= 1) {  // Hillis-Steele inclusive scan
+        const uint32_t v = tid >= d ? s_part[tid - d] : 0u;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;
+    for (uint32_t b = b0; b < b1; b++) { offsets[b] = run; run += block_counts[b]; }
+    if (tid == 1023u) *n_out = s_part[1023];
+}
+
+// block b's survivors -> their final, order-preserving position
+__global__ void __launch_bounds__(PLOC_CH) k_ploc_scatter(const float4 *__restrict__ tmp_lo, const float4 *__restrict__ tmp_hi,
+                                                          const uint32_t *__restrict__ block_counts, const uint32_t *__restrict__ offsets,
+                                                          float4 *out_lo, float4 *out_hi) {
+    const uint32_t t = threadIdx.x;
+    if (t >= block_counts[blockIdx.x]) return;
+    const size_t src = (size_t)blockIdx.x * PLOC_CH + t, dst = (size_t)offsets[blockIdx.x] + t;
+    out_lo[dst] = tmp_lo[src];
+    out_hi[dst] = tmp_hi[src];
+}
+
 __global__ void k_clear_u32(uint32_t *p, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0;
@@ -774,16 +945,211 @@ __global__ void k_single_inst_root(const float4 *prim_lo, const float4 *prim_hi,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
+// collapse_one for a whole WARP (single-CTA TLAS kernel, optimal-collapse table present).  One thread running collapse_one
+// takes ~45 000 cycles (the slot auction is 8 rounds over 64 pairs, the encoder loops over children x axes with
+// divisions), and the level-synchronous collapse of a 1 000-instance TLAS waited for that five times: 64 % of the kernel
+// (SOLB_TLAS_TRACE).  Here the 32 lanes split the work and write bit-identical nodes:
+//   * children: the DP's expansion runs level by level (every candidate with budget left splits in the same round);
+//   * slot auction: lane = (child i, slot pair), two scores per lane and a warp arg-max per round, ties to the smaller
+//     (child, slot) like the serial loops;
+//   * encoding: lane = (slot, axis): its own exponent requirement (max over slots by shuffle = the serial bump loop), its
+//     two quantised planes with the serial conservative fix-ups, written as bytes straight into the node.
+// Must be called by all 32 lanes with the same item.  dp may live in shared or global memory.
+__device__ __forceinline__ void collapse_one_warp(const BNode *bn, const int *node_count, int n_internal, CollapseItem item, Node8 *wide,
+                                                  uint32_t *wide_count, uint32_t *tri_count, const uint32_t *sorted_prim,
+                                                  CollapseItem *queue_out, uint32_t *queue_out_count, uint32_t *leaf_prim_out,
+                                                  const DpEntry *dp) {
+    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const unsigned FULL = 0xffffffffu;
+    // ---- 1. children of the wide node: lanes 0..7 hold (node, budget) in left-to-right order ----
+    int c_node = -1, c_budget = 0;
+    {
+        const BNode self = bn[item.bnode];
+        const int k = (int)((dp[item.bnode].k >> 18) & 7u);  // distribute(root, 8)
+        if (lane == 0) { c_node = self.left; c_budget = k; }
+        if (lane == 1) { c_node = self.right; c_budget = 8 - k; }
+    }
+    for (;;) {
+        // a candidate splits when it is an internal node that the table gives more than one child slot
+        int split_k = 0, b = c_budget > 7 ? 7 : c_budget, l = -1, r = -1;
+        if (c_node >= 0 && c_node < n_internal && b > 1) {
+            const uint32_t kb = dp[c_node].k;
+            while (b > 1 && ((kb >> (3 * (b - 2))) & 7u) == 0u) b--;
+            if (b > 1) { split_k = (int)((kb >> (3 * (b - 2))) & 7u); l = bn[c_node].left; r = bn[c_node].right; }
+        }
+        const uint32_t m_split = __ballot_sync(FULL, split_k != 0);
+        if (m_split == 0u) break;
+        // new position: every splitting candidate to the left shifts this one right by one
+        const int pos = (int)lane + __popc(m_split & lt_mask);
+        // scatter through shuffles: destination lane d reads from the source whose pos == d (left / stays) or pos + 1 == d (right)
+        int n_node = -1, n_budget = 0;
+        for (int src = 0; src < 8; src++) {
+            const int s_pos = __shfl_sync(FULL, pos, src), s_k = __shfl_sync(FULL, split_k, src);
+            const int s_node = __shfl_sync(FULL, c_node, src), s_l = __shfl_sync(FULL, l, src), s_r = __shfl_sync(FULL, r, src);
+            const int s_b = __shfl_sync(FULL, b, src), s_budget = __shfl_sync(FULL, c_budget, src);
+            if (s_node < 0) continue;
+            if (s_k) {
+                if ((int)lane == s_pos) { n_node = s_l; n_budget = s_k; }
+                if ((int)lane == s_pos + 1) { n_node = s_r; n_budget = s_b - s_k; }
+            } else if ((int)lane == s_pos) { n_node = s_node; n_budget = s_budget; }
+        }
+        c_node = n_node; c_budget = n_budget;
+    }
+    const int n = __popc(__ballot_sync(FULL, c_node >= 0));  // 2..8 children, on lanes 0..n-1
+    // ---- 2. per child (lane i < n): box, count, leaf flag ----
+    const BNode self = bn[item.bnode];
+    const float3 nlo = self.lo, nhi = self.hi;
+    const float3 nc = (nlo + nhi) * 0.5f;
+    float3 clo = f3(0, 0, 0), chi = f3(0, 0, 0), rel = f3(0, 0, 0);
+    int ccount = 0;
+    bool cleaf = false;
+    if ((int)lane < n) {
+        const BNode b = bn[c_node];
+        clo = b.lo; chi = b.hi;
+        rel = (b.lo + b.hi) * 0.5f - nc;
+        ccount = node_count[c_node];
+        cleaf = (dp[c_node].k >> 31) != 0u;
+    }
+    // ---- 3. slot auction: lane = (child i = lane >> 2, slots 2 (lane & 3), 2 (lane & 3) + 1) ----
+    int my_slot = -1;  // lane i < n: the slot of child i
+    {
+        const int ai = (int)(lane >> 2), s0 = 2 * (int)(lane & 3u);
+        const float rx = __shfl_sync(FULL, rel.x, ai), ry = __shfl_sync(FULL, rel.y, ai), rz = __shfl_sync(FULL, rel.z, ai);
+        float v0, v1;
+        {
+            const int sl = s0;
+            v0 = ((sl & 4) ? rx : -rx) + ((sl & 2) ? ry : -ry) + ((sl & 1) ? rz : -rz);
+        }
+        {
+            const int sl = s0 + 1;
+            v1 = ((sl & 4) ? rx : -rx) + ((sl & 2) ? ry : -ry) + ((sl & 1) ? rz : -rz);
+        }
+        uint32_t free_child = (1u << n) - 1u, free_slot = 0xffu;
+        for (int round = 0; round < n; round++) {
+            float best_v = -3.4e38f;
+            int best_idx = 64;  // i * 8 + slot; 64 = none
+            if ((free_child >> ai) & 1u) {
+                if (((free_slot >> s0) & 1u) && v0 > best_v) { best_v = v0; best_idx = ai * 8 + s0; }
+                if (((free_slot >> (s0 + 1)) & 1u) && v1 > best_v) { best_v = v1; best_idx = ai * 8 + s0 + 1; }
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, best_v, off);
+                const int oi = __shfl_xor_sync(FULL, best_idx, off);
+                if (oi < 64 && (best_idx == 64 || ov > best_v || (ov == best_v && oi < best_idx))) { best_v = ov; best_idx = oi; }
+            }
+            const int bi = best_idx >> 3, bs = best_idx & 7;
+            if ((int)lane == bi) my_slot = bs;
+            free_child &= ~(1u << bi);
+            free_slot &= ~(1u << bs);
+        }
+    }
+    // ---- 4. per slot (leader lane = 4 * slot): which child, leaf / inner, triangle offsets in slot order ----
+    const int sl = (int)(lane >> 2), axis = (int)(lane & 3u);
+    int child = -1;  // child index held by slot sl
+    for (int i = 0; i < 8; i++) {
+        const int s_i = __shfl_sync(FULL, my_slot, i);
+        if (i < n && s_i == sl) child = i;
+    }
+    const int src = child >= 0 ? child : 0;
+    const float lo_x = __shfl_sync(FULL, clo.x, src), lo_y = __shfl_sync(FULL, clo.y, src), lo_z = __shfl_sync(FULL, clo.z, src);
+    const float hi_x = __shfl_sync(FULL, chi.x, src), hi_y = __shfl_sync(FULL, chi.y, src), hi_z = __shfl_sync(FULL, chi.z, src);
+    const int s_count = __shfl_sync(FULL, ccount, src), s_node = __shfl_sync(FULL, c_node, src);
+    const bool s_leaf = __shfl_sync(FULL, (int)cleaf, src) != 0;
+    const bool valid = child >= 0, inner = valid && !s_leaf, leaf = valid && s_leaf;
+    const uint32_t m_inner = __ballot_sync(FULL, inner && axis == 0), m_leader = 0x11111111u;
+    uint32_t tri_offset = 0, n_tris = 0, count0 = 0;
+    for (int s2 = 0; s2 < 8; s2++) {
+        const int cnt = __shfl_sync(FULL, leaf ? s_count : 0, 4 * s2);
+        if (s2 < sl) tri_offset += (uint32_t)cnt;
+        if (s2 < 4) count0 += (uint32_t)cnt;
+        n_tris += (uint32_t)cnt;
+    }
+    const uint32_t n_inner = (uint32_t)__popc(m_inner);
+    uint32_t child_base = 0, tri_base = 0, q = 0;
+    if (lane == 0) {
+        child_base = n_inner ? atomicAdd(wide_count, n_inner) : 0u;
+        tri_base = n_tris ? atomicAdd(tri_count, n_tris) : 0u;
+        q = n_inner ? atomicAdd(queue_out_count, n_inner) : 0u;
+    }
+    child_base = __shfl_sync(FULL, child_base, 0);
+    tri_base = __shfl_sync(FULL, tri_base, 0);
+    q = __shfl_sync(FULL, q, 0);
+    // ---- 5. encode (bvh.cuh encode_node8, same arithmetic): lane = (slot, axis) ----
+    uint8_t *node_bytes = (uint8_t *)&wide[item.wnode];
+    uint32_t e_axis = 1u;
+    if (axis < 3) {
+        const float l = axis == 0 ? nlo.x : (axis == 1 ? nlo.y : nlo.z), h = axis == 0 ? nhi.x : (axis == 1 ? nhi.y : nhi.z);
+        const float ch = axis == 0 ? hi_x : (axis == 1 ? hi_y : hi_z);
+        uint32_t e = quant_exponent(h - l);
+        if (valid) {  // the serial loop bumps the exponent until every child fits: the maximum of the per-child requirements
+            for (;;) {
+                const float inv = 1.0f / u2f(e << 23);
+                if (!(ceilf((ch - l) * inv) > 255.0f) || e >= 254u) break;
+                e++;
+            }
+        }
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) e = max(e, __shfl_xor_sync(0x77777777u, e, off));
+        e_axis = e;
+        uint32_t ql_u = 0, qh_u = 0;
+        if (valid) {
+            const float cl = axis == 0 ? lo_x : (axis == 1 ? lo_y : lo_z);
+            const float sc = u2f(e << 23);
+            float ql = floorf((cl - l) / sc), qh = ceilf((ch - l) / sc);
+            ql = fminf(fmaxf(ql, 0.0f), 255.0f);
+            qh = fminf(fmaxf(qh, 0.0f), 255.0f);
+            while (ql > 0.0f && l + ql * sc > cl) ql -= 1.0f;
+            while (qh < 255.0f && l + qh * sc < ch) qh += 1.0f;
+            ql_u = (uint32_t)ql; qh_u = (uint32_t)qh;
+        }
+        node_bytes[32 + 8 * axis + sl] = (uint8_t)ql_u;
+        node_bytes[56 + 8 * axis + sl] = (uint8_t)qh_u;
+    } else {
+        uint32_t meta = 0;  // tmask byte of the slot
+        if (leaf) meta = (s_count == 1 ? 1u : 3u) << (tri_offset - (sl < 4 ? 0u : count0));
+        node_bytes[24 + sl] = (uint8_t)meta;
+    }
+    {
+        const uint32_t ex = __shfl_sync(FULL, e_axis, 0), ey = __shfl_sync(FULL, e_axis, 1), ez = __shfl_sync(FULL, e_axis, 2);
+        uint32_t imask = 0;
+        for (int s2 = 0; s2 < 8; s2++) imask |= ((m_inner >> (4 * s2)) & 1u) << s2;
+        if (lane == 0) {
+            uint32_t *w = (uint32_t *)node_bytes;
+            w[0] = f2u(nlo.x); w[1] = f2u(nlo.y); w[2] = f2u(nlo.z);
+            w[3] = ex | (ey << 8) | (ez << 16) | (imask << 24);
+            w[4] = child_base;
+            w[5] = (tri_base & SOLB_TRI_BASE_MASK) | (count0 << 28);
+        }
+    }
+    // ---- 6. next level's work items / leaf records (slot leaders) ----
+    if (axis == 0 && valid) {
+        if (inner) {
+            CollapseItem it;
+            it.bnode = s_node;
+            it.wnode = child_base + (uint32_t)__popc(m_inner & m_leader & lt_mask);
+            queue_out[q + (uint32_t)__popc(m_inner & m_leader & lt_mask)] = it;
+        } else {
+            int prims[SOLB_MAX_LEAF_TRIS + 1];
+            const int m = gather_leaf_tris(bn, n_internal, s_node, prims);
+            for (int j = 0; j < m; j++) leaf_prim_out[tri_base + tri_offset + (uint32_t)j] = sorted_prim[prims[j]];
+        }
+    }
+}
+
 // Single-CTA TLAS build for up to TLAS_FAST_MAX instances: TLAS::regenerate runs every frame in the reference
 // (examples/5-pathtrace.rs:316), so for the instance counts it is used with (8 ... a few thousand) the whole rebuild is ONE
 // launch working out of shared memory: instance boxes -> Morton keys -> bitonic sort -> Karras links -> atomic-flag refit ->
 // level-synchronous 8-wide collapse -> instance leaf records.  No treelet pass (a plain LBVH over instance boxes).
 constexpr uint32_t TLAS_FAST_MAX = 2048;
-constexpr int TLAS_FAST_THREADS = 256;  // few, fat threads: collapse_one wants registers, everything else is tiny
+constexpr int TLAS_FAST_THREADS = 256;        // serial collapse_one (greedy collapse): few, fat threads, it wants 230 registers
+constexpr int TLAS_FAST_THREADS_COOP = 1024;  // warp-cooperative collapse (optimal-collapse table present): 64 registers
 
 struct TlasFastInfo {
     uint32_t n_wide, depth, leaf_count, pad;
     float lo[4], hi[4];
+    long long t[16];  // clock64() of thread 0 at the phase boundaries (SOLB_TLAS_TRACE=1 prints the shares)
 };
 
 __host__ __device__ inline size_t tlas_fast_smem_bytes(uint32_t n) {
@@ -793,12 +1159,18 @@ __host__ __device__ inline size_t tlas_fast_smem_bytes(uint32_t n) {
     return (size_t)(2 * n) * 32 + (size_t)p2 * 12 + (size_t)(2 * n) * 4 + (size_t)n * 4 + (size_t)(n / 2 + 2) * 16 + (size_t)n * 4 +
            (size_t)(2 * n) * 2 + 64;
 }
+// ... plus the optimal-collapse table (32 B per binary node) when it fits next to the rest: walking it bottom-up from global
+// memory cost 49 000 of the kernel's 430 000 cycles at 1 000 instances
+__host__ __device__ inline size_t tlas_fast_dp_offset(uint32_t n) { return (tlas_fast_smem_bytes(n) + 31) & ~(size_t)31; }
+__host__ __device__ inline size_t tlas_fast_smem_bytes_dp(uint32_t n) { return tlas_fast_dp_offset(n) + (size_t)(2 * n) * sizeof(DpEntry); }
+constexpr size_t TLAS_FAST_SMEM_LIMIT = 227 * 1024;
 
-__global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n,
-                                                                        const float4 *__restrict__ blas_box, uint32_t tlas_cap,
-                                                                        Node8 *wide, InstLeaf *inst_leaves, TlasFastInfo *info,
-                                                                        DpEntry *dp /* [2 n - 1] global scratch, or null: greedy collapse */,
-                                                                        const DpCost cost) {
+template <bool COOP>
+__global__ void __launch_bounds__(COOP ? TLAS_FAST_THREADS_COOP : TLAS_FAST_THREADS)
+k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, const float4 *__restrict__ blas_box, uint32_t tlas_cap,
+                   Node8 *wide, InstLeaf *inst_leaves, TlasFastInfo *info,
+                   DpEntry *dp /* [2 n - 1] global scratch; null: greedy collapse (COOP = false) or table in shared memory */,
+                   const int dp_in_smem, const DpCost cost) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_bounds[6];
     __shared__ uint32_t s_counters[3];  // wide nodes, leaf slots, next queue size
@@ -814,8 +1186,12 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
     CollapseItem *queue_b = queue_a + (n / 2 + 2);
     uint32_t *leaf_prim = (uint32_t *)(queue_b + (n / 2 + 2));
     uint16_t *parent = (uint16_t *)(leaf_prim + n);
+    if (dp_in_smem) dp = (DpEntry *)(smem + tlas_fast_dp_offset(n));
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const int ni = (int)n - 1;
+    int n_stamp = 0;
+#define TLAS_STAMP() do { if (tid == 0 && n_stamp < 16) info->t[n_stamp] = clock64(); n_stamp++; } while (0)
+    TLAS_STAMP();  // 0: start
 
     if (tid < 3) s_bounds[tid] = 0xffffffffu;
     else if (tid < 6) s_bounds[tid] = 0u;
@@ -836,6 +1212,7 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
         }
     }
     __syncthreads();
+    TLAS_STAMP();  // 1: instance boxes
     // 2. Morton keys + bitonic sort of (key, index) in shared memory
     {
         const float3 lo = f3(ordered_to_float(s_bounds[0]), ordered_to_float(s_bounds[1]), ordered_to_float(s_bounds[2]));
@@ -865,10 +1242,11 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
             }
             __syncthreads();
         }
+    TLAS_STAMP();  // 2: keys + sort
     // 3. move the boxes to their sorted leaf slots.  Source bn[idx[i]] (i < n) and destination bn[ni + i] ranges overlap:
     //    stage through registers with a barrier in between (every thread owns at most ceil(n / nt) <= 2 leaves).
     {
-        BNode tmp[(TLAS_FAST_MAX + TLAS_FAST_THREADS - 1) / TLAS_FAST_THREADS];
+        BNode tmp[(TLAS_FAST_MAX + (COOP ? TLAS_FAST_THREADS_COOP : TLAS_FAST_THREADS) - 1) / (COOP ? TLAS_FAST_THREADS_COOP : TLAS_FAST_THREADS)];
         int c = 0;
         for (uint32_t i = tid; i < n; i += nt) tmp[c++] = bn[idx[i]];
         __syncthreads();
@@ -891,6 +1269,7 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
     }
     if (tid == 0) parent[0] = 0xffffu;
     __syncthreads();
+    TLAS_STAMP();  // 3: leaf move + Karras links
     // 5. refit: the second thread to arrive at a node owns it
     for (uint32_t j = tid; j < n; j += nt) {
         uint32_t node = parent[ni + j];
@@ -912,6 +1291,7 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
     //     trace throughput over the greedy collapse, the treelet pass nothing: 618 -> 704 Mrays/s)
     if (dp) {
         __syncthreads();
+        TLAS_STAMP();  // 4: refit
         for (uint32_t i = tid; i < n; i += nt) flags[i] = 0;
         __syncthreads();
         for (uint32_t j = tid; j < n; j += nt) {
@@ -941,17 +1321,24 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
         queue_a[0].bnode = 0; queue_a[0].wnode = 0;
     }
     __syncthreads();
+    TLAS_STAMP();  // 5 (4 without the table): optimal-collapse table
     // 6. level-synchronous collapse
     for (;;) {
         const uint32_t n_items = s_items;
         if (n_items == 0) break;
-        for (uint32_t i = tid; i < n_items; i += nt)
-            collapse_one(bn, count, ni, queue_a[i], wide, &s_counters[0], &s_counters[1], idx, nullptr, nullptr, queue_b, &s_counters[2],
-                         leaf_prim, dp);
+        if (COOP) {
+            for (uint32_t i = tid >> 5; i < n_items; i += nt >> 5)
+                collapse_one_warp(bn, count, ni, queue_a[i], wide, &s_counters[0], &s_counters[1], idx, queue_b, &s_counters[2], leaf_prim, dp);
+        } else {
+            for (uint32_t i = tid; i < n_items; i += nt)
+                collapse_one(bn, count, ni, queue_a[i], wide, &s_counters[0], &s_counters[1], idx, nullptr, nullptr, queue_b, &s_counters[2],
+                             leaf_prim, dp);
+        }
         __syncthreads();
         if (tid == 0) { s_items = s_counters[2]; s_counters[2] = 0; s_depth++; }
         CollapseItem *t = queue_a; queue_a = queue_b; queue_b = t;
         __syncthreads();
+        TLAS_STAMP();  // one per collapse level
     }
     // 7. instance leaf records in TLAS leaf order
     for (uint32_t j = tid; j < n; j += nt) {
@@ -962,7 +1349,10 @@ __global__ void __launch_bounds__(TLAS_FAST_THREADS) k_tlas_build_small(const De
         info->n_wide = s_counters[0]; info->depth = s_depth; info->leaf_count = s_counters[1];
         info->lo[0] = bn[0].lo.x; info->lo[1] = bn[0].lo.y; info->lo[2] = bn[0].lo.z;
         info->hi[0] = bn[0].hi.x; info->hi[1] = bn[0].hi.y; info->hi[2] = bn[0].hi.z;
+        if (n_stamp < 16) info->t[n_stamp] = clock64();  // end
+        for (int k = n_stamp + 1; k < 16; k++) info->t[k] = 0;
     }
+#undef TLAS_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1045,6 +1435,60 @@ static cudaError_t tree_sort_and_link(cudaStream_t st, BinaryTree &T, const floa
     cudaFreeAsync(T.keys_tmp, st); cudaFreeAsync(T.vals_tmp, st); cudaFreeAsync(T.sort_scratch, st);
     T.keys_tmp = nullptr; T.vals_tmp = nullptr; T.sort_scratch = nullptr;
     return cudaGetLastError();
+}
+
+// keys / vals filled: sort, then PLOC over the sorted leaves.  Produces everything tree_sort_and_link + tree_refit_optimize do
+// (binary nodes with boxes, parents, counts, SAH cost, optimal-collapse table), root = node 0.
+static cudaError_t tree_sort_and_ploc(cudaStream_t st, BinaryTree &T, const float4 *prim_lo, const float4 *prim_hi, int key_bits,
+                                      const BuildOptions &opt, uint32_t *h_count /* pinned */, uint64_t *launches, uint32_t *iterations) {
+    cudaError_t err = radix_sort_pairs(st, T.keys, T.vals, T.keys_tmp, T.vals_tmp, T.n, key_bits, T.sort_scratch, launches);
+    if (err != cudaSuccess) return err;
+    const uint32_t n = T.n;
+    float4 *c_lo = nullptr, *c_hi = nullptr, *t_lo = nullptr, *t_hi = nullptr;
+    uint32_t *block_counts = nullptr, *offsets = nullptr, *dev_count = nullptr;
+    const uint32_t max_blocks = (n + PLOC_CH - 1) / PLOC_CH;
+    // the sort's ping-pong buffers and the keys are dead from here on
+    cudaFreeAsync(T.keys_tmp, st); cudaFreeAsync(T.vals_tmp, st); cudaFreeAsync(T.sort_scratch, st); cudaFreeAsync(T.keys, st);
+    T.keys_tmp = nullptr; T.vals_tmp = nullptr; T.sort_scratch = nullptr; T.keys = nullptr;
+    DpCost cost;
+    cost.cn = opt.dp_cn; cost.cp = opt.dp_cp; cost.max_leaf = opt.dp_max_leaf;
+    CK(salloc(st, &c_lo, n));
+    CK(salloc(st, &c_hi, n));
+    CK(salloc(st, &t_lo, (size_t)max_blocks * PLOC_CH));
+    CK(salloc(st, &t_hi, (size_t)max_blocks * PLOC_CH));
+    CK(salloc(st, &block_counts, max_blocks));
+    CK(salloc(st, &offsets, max_blocks));
+    CK(salloc(st, &dev_count, 2));
+    if (opt.dp_collapse) CK(salloc(st, &T.dp, 2 * (size_t)n - 1));
+    CK(cudaMemsetAsync(dev_count, 0, 2 * sizeof(uint32_t), st));  // [0] cluster count after the iteration, [1] nodes created
+    k_ploc_init<<<(n + 255) / 256, 256, 0, st>>>((int)n, T.vals, prim_lo, prim_hi, T.bn, T.parent, T.node_count, T.node_cost, T.dp, cost,
+                                                  c_lo, c_hi);
+    *launches += 1;
+    {
+        uint32_t count = n, iters = 0;
+        while (count > 1) {
+            const uint32_t nb = (count + PLOC_CH - 1) / PLOC_CH;
+            k_ploc_merge<<<nb, PLOC_CH, 0, st>>>((int)n, (int)count, c_lo, c_hi, t_lo, t_hi, block_counts, dev_count + 1, T.bn, T.parent,
+                                                 T.node_count, T.node_cost, T.dp, cost);
+            k_ploc_scan<<<1, 1024, 0, st>>>(block_counts, nb, offsets, dev_count);
+            k_ploc_scatter<<<nb, PLOC_CH, 0, st>>>(t_lo, t_hi, block_counts, offsets, c_lo, c_hi);
+            *launches += 3;
+            CK(cudaMemcpyAsync(h_count, dev_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (*h_count >= count || *h_count == 0) { err = cudaErrorUnknown; goto done; }  // every iteration merges at least one pair
+            count = *h_count;
+            if (++iters > 4096) { err = cudaErrorUnknown; goto done; }
+        }
+        if (iterations) *iterations = iters;
+    }
+    CK(cudaGetLastError());
+done:
+    {
+        void *q[] = { c_lo, c_hi, t_lo, t_hi, block_counts, offsets, dev_count };
+        for (void *x : q)
+            if (x) cudaFreeAsync(x, st);
+    }
+    return err;
 }
 
 // refit (boxes, counts, SAH cost) and treelet restructuring; walks stop at nodes whose parent is -1
@@ -1147,11 +1591,23 @@ cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage
     k_morton<<<nb, 256, 0, st>>>(prim_lo, prim_hi, n, bounds, T.keys, T.vals);
     *launches += 1;
     trace.mark("tree alloc + morton");
-    CK(tree_sort_and_link(st, T, prim_lo, prim_hi, 63, launches));
-    cudaFreeAsync(prim_lo, st); cudaFreeAsync(prim_hi, st); cudaFreeAsync(T.keys, st);  // leaf boxes live in the tree now
-    prim_lo = prim_hi = nullptr; T.keys = nullptr;
-    trace.mark("sort + hierarchy");
-    CK(tree_refit_optimize(st, T, opt, opt.treelet_passes, &out.sah_lbvh, launches));
+    if (opt.ploc) {
+        uint32_t *h_count = nullptr, iters = 0;
+        CK(cudaMallocHost((void **)&h_count, sizeof(uint32_t)));
+        err = tree_sort_and_ploc(st, T, prim_lo, prim_hi, 63, opt, h_count, launches, &iters);
+        cudaFreeHost(h_count);
+        CK(err);
+        cudaFreeAsync(prim_lo, st); cudaFreeAsync(prim_hi, st);  // leaf boxes live in the tree now
+        prim_lo = prim_hi = nullptr;
+        trace.mark("sort + PLOC");
+        CK(cudaMemcpyAsync(&out.sah_lbvh, T.node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));  // (no LBVH stage to compare with)
+    } else {
+        CK(tree_sort_and_link(st, T, prim_lo, prim_hi, 63, launches));
+        cudaFreeAsync(prim_lo, st); cudaFreeAsync(prim_hi, st); cudaFreeAsync(T.keys, st);  // leaf boxes live in the tree now
+        prim_lo = prim_hi = nullptr; T.keys = nullptr;
+        trace.mark("sort + hierarchy");
+        CK(tree_refit_optimize(st, T, opt, opt.treelet_passes, &out.sah_lbvh, launches));
+    }
     CK(cudaMemcpyAsync(&out.sah_final, T.node_cost, sizeof(float), cudaMemcpyDeviceToHost, st));
     {
         BNode root;
@@ -1247,19 +1703,39 @@ cudaError_t rebuild_tlas(cudaStream_t st, const DeviceSceneView &sv, AccelStorag
     }
     if (n >= 2 && n <= TLAS_FAST_MAX && tlas_fast_enabled()) {
         // per device and cheap: set on every call rather than caching a process-wide flag (one process may own several devices)
-        CK(cudaFuncSetAttribute(k_tlas_build_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlas_fast_smem_bytes(TLAS_FAST_MAX)));
         if (!out.d_tlas_info) {
             CK(cudaMalloc(&out.d_tlas_info, sizeof(TlasFastInfo)));
             CK(cudaMallocHost(&out.h_tlas_info, sizeof(TlasFastInfo)));
             CK(cudaMalloc(&out.d_tlas_dp, sizeof(DpEntry) * 2 * (size_t)out.tlas_cap));
         }
-        k_tlas_build_small<<<1, TLAS_FAST_THREADS, tlas_fast_smem_bytes(n), st>>>(sv.instances, n, out.blas_box, out.tlas_cap, out.nodes,
-                                                                                  out.inst_leaves, (TlasFastInfo *)out.d_tlas_info,
-                                                                                  opt.dp_collapse ? (DpEntry *)out.d_tlas_dp : nullptr, tlas_cost);
+        const char *coop_env = getenv("SOLB_TLAS_COOP");
+        const bool coop = opt.dp_collapse && !(coop_env && *coop_env == '0');
+        if (coop) {
+            const bool dp_smem = tlas_fast_smem_bytes_dp(n) <= TLAS_FAST_SMEM_LIMIT;
+            const size_t bytes = dp_smem ? tlas_fast_smem_bytes_dp(n) : tlas_fast_smem_bytes(n);
+            CK(cudaFuncSetAttribute(k_tlas_build_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TLAS_FAST_SMEM_LIMIT));
+            k_tlas_build_small<true><<<1, TLAS_FAST_THREADS_COOP, bytes, st>>>(sv.instances, n, out.blas_box, out.tlas_cap, out.nodes,
+                                                                              out.inst_leaves, (TlasFastInfo *)out.d_tlas_info,
+                                                                              dp_smem ? nullptr : (DpEntry *)out.d_tlas_dp, dp_smem ? 1 : 0,
+                                                                              tlas_cost);
+        } else {
+            CK(cudaFuncSetAttribute(k_tlas_build_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tlas_fast_smem_bytes(TLAS_FAST_MAX)));
+            k_tlas_build_small<false><<<1, TLAS_FAST_THREADS, tlas_fast_smem_bytes(n), st>>>(sv.instances, n, out.blas_box, out.tlas_cap, out.nodes,
+                                                                                            out.inst_leaves, (TlasFastInfo *)out.d_tlas_info,
+                                                                                            opt.dp_collapse ? (DpEntry *)out.d_tlas_dp : nullptr, 0,
+                                                                                            tlas_cost);
+        }
         *launches += 1;
         CK(cudaMemcpyAsync(out.h_tlas_info, out.d_tlas_info, sizeof(TlasFastInfo), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const TlasFastInfo h_info = *(const TlasFastInfo *)out.h_tlas_info;
+        if (const char *v = getenv("SOLB_TLAS_TRACE")) {
+            if (atoi(v)) {
+                fprintf(stderr, "[solb tlas] n = %u, cycles per phase:", n);
+                for (int k = 1; k < 16 && h_info.t[k]; k++) fprintf(stderr, " %lld", h_info.t[k] - h_info.t[k - 1]);
+                fprintf(stderr, "\n");
+            }
+        }
         if (h_info.leaf_count != n || h_info.n_wide > out.tlas_cap) { err = cudaErrorUnknown; goto done; }
         out.n_tlas_wide = h_info.n_wide;
         depth = h_info.depth;

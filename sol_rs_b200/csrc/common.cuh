@@ -108,6 +108,35 @@ SOLB_HD float fast_rsqrt(float x) {
 #endif
 }
 
+// Shading arithmetic (shade.cuh): the GLSL these functions restate runs under Vulkan's precision rules, not IEEE ones
+// (a / b within 2.5 ULP, inversesqrt 2 ULP, sqrt / normalize / pow inherited from those, sin / cos 2^-11 absolute), so on
+// the device they use the hardware approximations (MUFU.RCP / RSQ / SQRT / SIN / COS / LG2 / EX2, all within ~2 ULP or 2^-21
+// absolute) instead of the IEEE sequences with their slow-path calls: ~40 % fewer instructions in the shade step of the
+// persistent kernel and a third less code in its instruction cache.  The host build (tests/emu) keeps libm.
+SOLB_HD float sh_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+SOLB_HD float sh_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+SOLB_HD float sh_pow(float x, float y) {
+#if defined(__CUDA_ARCH__)
+    return __powf(x, y);
+#else
+    return powf(x, y);
+#endif
+}
+
 // ---- float3 helpers ----
 SOLB_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
 SOLB_HD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -120,7 +149,16 @@ SOLB_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z
 SOLB_HD float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 SOLB_HD float length(float3 a) { return sqrtf(dot(a, a)); }
 // GLSL normalize(v) = v / length(v)
-SOLB_HD float3 normalize(float3 a) { float l = length(a); return f3(a.x / l, a.y / l, a.z / l); }
+SOLB_HD float3 normalize(float3 a) {
+#if defined(__CUDA_ARCH__)
+    const float inv = rsqrtf(dot(a, a));
+    return f3(a.x * inv, a.y * inv, a.z * inv);
+#else
+    float l = length(a); return f3(a.x / l, a.y / l, a.z / l);
+#endif
+}
+// IEEE version (v / sqrt(dot)): primary-ray directions, whose hit ids are compared bit for bit with the reference's
+SOLB_HD float3 normalize_ieee(float3 a) { const float l = length(a); return f3(a.x / l, a.y / l, a.z / l); }
 SOLB_HD float3 fmin3(float3 a, float3 b) { return f3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
 SOLB_HD float3 fmax3(float3 a, float3 b) { return f3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 SOLB_HD float3 xyz(float4 a) { return f3(a.x, a.y, a.z); }

@@ -37,9 +37,9 @@ SOLB_HD float fresnel_dielectric(float3 i, float3 m, float eta) {
     const float cosThetaI = fabsf(dot(i, m));
     const float sinThetaOSquared = (eta * eta) * (1.0f - cosThetaI * cosThetaI);
     if (sinThetaOSquared <= 1.0f) {
-        const float cosThetaO = sqrtf(saturate(1.0f - sinThetaOSquared));
-        const float Rs = (cosThetaI - eta * cosThetaO) / (cosThetaI + eta * cosThetaO);
-        const float Rp = (eta * cosThetaI - cosThetaO) / (eta * cosThetaI + cosThetaO);
+        const float cosThetaO = sh_sqrt(saturate(1.0f - sinThetaOSquared));
+        const float Rs = sh_div(cosThetaI - eta * cosThetaO, cosThetaI + eta * cosThetaO);
+        const float Rp = sh_div(eta * cosThetaI - cosThetaO, eta * cosThetaI + cosThetaO);
         result = 0.5f * (Rs * Rs + Rp * Rp);
     }
     return result;
@@ -47,15 +47,15 @@ SOLB_HD float fresnel_dielectric(float3 i, float3 m, float eta) {
 
 // assets/glsl/sampling.glsl:66-84
 SOLB_HD float3 align_to_direction(float3 n, float cosTheta, float phi) {
-    const float sinTheta = sqrtf(saturate(1.0f - cosTheta * cosTheta));
+    const float sinTheta = sh_sqrt(saturate(1.0f - cosTheta * cosTheta));
     const float s = (n.z < 0.0f ? -1.0f : 1.0f);
-    const float a = -1.0f / (s + n.z);
+    const float a = sh_div(-1.0f, s + n.z);
     const float b = n.x * n.y * a;
     const float3 u = f3(1.0f + s * n.x * n.x * a, s * b, -s * n.x);
     const float3 v = f3(b, s + n.y * n.y * a, -n.y);
     float sp, cp;
 #if defined(__CUDA_ARCH__)
-    sincosf(phi, &sp, &cp);
+    __sincosf(phi, &sp, &cp);  // phi in [0, 2 pi]: absolute error ~2^-21 (GLSL allows 2^-11)
 #else
     sp = sinf(phi); cp = cosf(phi);
 #endif
@@ -66,30 +66,31 @@ SOLB_HD float3 align_to_direction(float3 n, float cosTheta, float phi) {
 
 // assets/glsl/sampling.glsl:86-90
 SOLB_HD float3 sample_ggx(float3 n, float xi_x, float xi_y, float alphaSquared) {
-    const float cosTheta = sqrtf(saturate((1.0f - xi_x) / (xi_x * (alphaSquared - 1.0f) + 1.0f)));
+    const float cosTheta = sh_sqrt(saturate(sh_div(1.0f - xi_x, xi_x * (alphaSquared - 1.0f) + 1.0f)));
     return align_to_direction(n, cosTheta, xi_y * SOLB_TWO_PI);
 }
 // assets/glsl/sampling.glsl:92-96
 SOLB_HD float3 sample_cosine(float3 n, float xi_x, float xi_y) {
-    return align_to_direction(n, sqrtf(xi_x), xi_y * SOLB_TWO_PI);
+    return align_to_direction(n, sh_sqrt(xi_x), xi_y * SOLB_TWO_PI);
 }
 // GLSL reflect(I, N) = I - 2 dot(N, I) N
 SOLB_HD float3 reflect(float3 i, float3 n) { return i - n * (2.0f * dot(n, i)); }
 SOLB_HD float3 mix3(float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; }
 SOLB_HD float smoothstep(float e0, float e1, float x) {
-    const float t = saturate((x - e0) / (e1 - e0));
+    const float t = saturate(sh_div(x - e0, e1 - e0));
     return t * t * (3.0f - 2.0f * t);
 }
 
 // Primary ray direction through pixel position (px, py): pathtrace.rgen:52-58, ao.rgen:49-55, debug.rgen:20-26
 SOLB_HD float3 primary_dir(const FrameConsts &fc, float px, float py) {
+    // (IEEE division and normalisation here, unlike the BRDF arithmetic below: the primary-hit parity gate compares ids bit for bit)
     const float ux = px / (float)fc.width, uy = py / (float)fc.height;
     const float dx = ux * 2.0f - 1.0f, dy = uy * 2.0f - 1.0f;
     const float *P = fc.proj_inv;
     // target = projection_inverse * vec4(d.x, d.y, 1, 1)
     const float3 target = f3(P[0] * dx + P[4] * dy + P[8] + P[12], P[1] * dx + P[5] * dy + P[9] + P[13],
                              P[2] * dx + P[6] * dy + P[10] + P[14]);
-    return mat4_mul_dir(fc.view_inv, normalize(target));
+    return mat4_mul_dir(fc.view_inv, normalize_ieee(target));
 }
 
 struct ShadeVerts {
@@ -192,7 +193,7 @@ SOLB_HD bool is_nan_or_inf3(float3 c, bool want_nan) {
 // pathtrace.rgen:88-103.  pixel_sum = sum of the spp sample colours of this frame.
 // Returns the new accumulation value and the packed rgba8 display value.
 SOLB_HD float4 resolve_pixel(const FrameConsts &fc, float3 pixel_sum, float4 old4, uint32_t &rgba8_out) {
-    float3 pixel = pixel_sum * (1.0f / (float)fc.spp);  // :88
+    float3 pixel = pixel_sum * sh_div(1.0f, (float)fc.spp);  // :88
     float4 out;
     if (fc.accum_mode == 1u) {
         // SOLB_ACCUM_SUM (multi-GPU): keep a per-rank sum of frame colours and a frame count;
@@ -201,10 +202,10 @@ SOLB_HD float4 resolve_pixel(const FrameConsts &fc, float3 pixel_sum, float4 old
         float3 add = pixel;
         if (is_nan_or_inf3(pixel, true) || is_nan_or_inf3(pixel, false)) add = old4.w > 0.0f ? old * (1.0f / old4.w) : f3(0, 0, 0);
         out = make_float4(old.x + add.x, old.y + add.y, old.z + add.z, old4.w + 1.0f);
-        const float inv = 1.0f / out.w;
+        const float inv = sh_div(1.0f, out.w);
         pixel = f3(out.x * inv, out.y * inv, out.z * inv);
     } else {
-        const float alpha = 1.0f / (float)(uint32_t)(fc.frame + 1u - (uint32_t)fc.accum_start);  // :89
+        const float alpha = sh_div(1.0f, (float)(uint32_t)(fc.frame + 1u - (uint32_t)fc.accum_start));  // :89
         const float3 old = f3(old4.x, old4.y, old4.z);
         pixel = mix3(old, pixel, alpha);                       // :91
         if (is_nan_or_inf3(pixel, true)) pixel = old;          // :93-95
@@ -212,7 +213,7 @@ SOLB_HD float4 resolve_pixel(const FrameConsts &fc, float3 pixel_sum, float4 old
         out = make_float4(pixel.x, pixel.y, pixel.z, 1.0f);    // :100
     }
     const float g = 1.0f / 2.2f;  // postprocess.glsl:38-41
-    rgba8_out = pack_rgba8(powf(pixel.x, g), powf(pixel.y, g), powf(pixel.z, g), 1.0f);  // :102-103
+    rgba8_out = pack_rgba8(sh_pow(pixel.x, g), sh_pow(pixel.y, g), sh_pow(pixel.z, g), 1.0f);  // :102-103
     return out;
 }
 

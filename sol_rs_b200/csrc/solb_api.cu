@@ -413,6 +413,7 @@ static int do_build(solb_scene *s) {
     if (const char *v = getenv("SOLB_TREELET_COOP")) opt.coop_treelet = atoi(v) != 0;
     if (const char *v = getenv("SOLB_DP_COLLAPSE")) opt.dp_collapse = atoi(v) != 0;
     if (const char *v = getenv("SOLB_TREELET_GAMMA")) opt.treelet_gamma = std::max(3, std::min(1 << 20, atoi(v)));
+    if (const char *v = getenv("SOLB_PLOC")) opt.ploc = atoi(v) != 0;
     // a wide node keeps its triangle (or instance-leaf) base in 28 bits (bvh.cuh: SOLB_TRI_BASE_MASK)
     if (s->n_tris > SOLB_TRI_BASE_MASK || s->h_inst.size() > SOLB_TRI_BASE_MASK)
         return fail(ctx, SOLB_ERR_OVERFLOW, "more than 2^28 - 1 triangles or instances");

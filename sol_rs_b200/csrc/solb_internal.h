@@ -105,6 +105,7 @@ struct BuildOptions {
     int dp_collapse = 1;   // SAH-optimal wide collapse (Ylitie et al. 2017); 0: greedy largest-area-first
     float dp_cn = 2.0f, dp_cp = 1.0f;  // its cost model: 8-wide node visit, primitive test (per unit of box area)
     int dp_max_leaf = SOLB_MAX_LEAF_TRIS;  // ... and the largest leaf it may form
+    int ploc = 0;          // flattened build: PLOC over the Morton-sorted leaves instead of LBVH + treelet restructuring
 };
 
 cudaError_t build_accel(cudaStream_t st, const DeviceSceneView &sv, AccelStorage &out, const BuildOptions &opt, uint64_t *launches);

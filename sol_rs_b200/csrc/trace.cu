@@ -785,6 +785,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_wf_trace_pool(const FrameConsts
                 float tmax = P.tmax[slot];
                 Hit hit;
                 hit.inst = SOLB_MISS;
+                hit.gtri = P.hit_gtri[slot];
                 trav_tri_step(tris, tr, tmax, tgroup, hit);
                 if (STATS) ctr.tris++;
                 if (hit.inst != SOLB_MISS) {
@@ -989,13 +990,26 @@ __device__ __forceinline__ void wl_push(uint8_t *list, uint32_t &n, bool flag, u
 }
 
 // per-warp control block in shared memory: the three slot lists + the claimed range of the frame's cursor
+// Both work lists are FIFO.  With LIFO lists (the first version) a slot at the bottom of the ready stack was only served once
+// everything above it had finished, so the pixels of a pool drifted apart and, once the frame's cursor ran dry, the stale ones
+// were finished one after the other by a handful of lanes: the drain of a warp took several pixel lifetimes.  Served in
+// arrival order all pixels of a pool advance at the same rate and the drain is one pixel lifetime.
+constexpr uint32_t WL_RING = 128;  // ready ring: power of two >= WL_POOL
+static_assert(WL_POOL <= (int)WL_RING && WL_POOL % 32 == 0, "WL_POOL must be a multiple of 32 and fit the ready ring");
 struct WlWarp {
-    uint8_t ready[WL_POOL], shade[WL_POOL], free_[WL_POOL];
+    uint8_t ready[WL_RING];  // ring: entries head .. head + n_ready - 1 (mod WL_RING)
+    uint8_t shade[WL_POOL];  // queue: entries 0 .. n_shade - 1, oldest first
+    uint8_t free_[WL_POOL];  // stack
     uint32_t pool_next, pool_end;
 };
-// list sizes travel through the (rare) step calls packed in one word: ready | shade << 8 | free << 16 | exhausted << 24
-__device__ __forceinline__ uint32_t wl_pack(uint32_t n_ready, uint32_t n_shade, uint32_t n_free, bool exhausted) {
-    return n_ready | (n_shade << 8) | (n_free << 16) | (exhausted ? 1u << 24 : 0u);
+// list state travels in ONE word: n_ready | n_shade << 8 | n_free << 16 | exhausted << 24 | ready head << 25
+__device__ __forceinline__ uint32_t wl_pack(uint32_t n_ready, uint32_t n_shade, uint32_t n_free, bool exhausted, uint32_t head) {
+    return n_ready | (n_shade << 8) | (n_free << 16) | (exhausted ? 1u << 24 : 0u) | (head << 25);
+}
+__device__ __forceinline__ void wl_push_ready(WlWarp *W, uint32_t head, uint32_t &n, bool flag, uint32_t slot, uint32_t lt_mask) {
+    const uint32_t m = __ballot_sync(0xffffffffu, flag);
+    if (flag) W->ready[(head + n + (uint32_t)__popc(m & lt_mask)) & (WL_RING - 1u)] = (uint8_t)slot;
+    n += (uint32_t)__popc(m);
 }
 
 // Generate step: up to 32 free slots take the next pixels of the frame (k_wf_generate).
@@ -1006,6 +1020,7 @@ __device__ __forceinline__ uint32_t wl_generate_step(const FrameConsts *fcp, con
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     uint32_t n_ready = counts & 0xffu, n_shade = (counts >> 8) & 0xffu, n_free = (counts >> 16) & 0xffu;
     bool exhausted = (counts >> 24) & 1u;
+    const uint32_t head = counts >> 25;
     const uint32_t cnt = min(n_free, 32u);
     const bool mine = lane < cnt;
     const uint32_t my_slot = mine ? (uint32_t)W->free_[n_free - 1u - lane] : 0u;
@@ -1047,11 +1062,11 @@ __device__ __forceinline__ uint32_t wl_generate_step(const FrameConsts *fcp, con
             retry = true;  // a hole of the tile order (image edge): the slot stays free
         }
     }
-    wl_push(W->ready, n_ready, valid, my_slot, lt_mask);
+    wl_push_ready(W, head, n_ready, valid, my_slot, lt_mask);
     wl_push(W->free_, n_free, retry, my_slot, lt_mask);
     if (exhausted) n_free = 0u;  // nothing left to start: free slots are retired
     __syncwarp();
-    return wl_pack(n_ready, n_shade, n_free, exhausted);
+    return wl_pack(n_ready, n_shade, n_free, exhausted, head);
 }
 
 // Shade step: up to 32 finished rays, one per lane (k_wf_shade + k_wf_resolve).
@@ -1063,11 +1078,14 @@ __device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const 
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     uint32_t n_ready = counts & 0xffu, n_shade = (counts >> 8) & 0xffu, n_free = (counts >> 16) & 0xffu;
     const bool exhausted = (counts >> 24) & 1u;
+    const uint32_t head = counts >> 25;
     const uint32_t cnt = min(n_shade, 32u);
     const bool mine = lane < cnt;
-    const uint32_t my_slot = mine ? (uint32_t)W->shade[n_shade - 1u - lane] : 0u;
+    const uint32_t my_slot = mine ? (uint32_t)W->shade[lane] : 0u;  // the oldest cnt entries
     n_shade -= cnt;
+    const uint32_t moved = lane < n_shade ? (uint32_t)W->shade[cnt + lane] : 0u;  // at most 31 younger ones move to the front
     __syncwarp();
+    if (lane < n_shade) W->shade[lane] = (uint8_t)moved;
     bool alive = false, freed = false;
     if (mine) {
         const uint32_t gs = slot_base + my_slot;
@@ -1120,10 +1138,10 @@ __device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const 
             wl_st(wl.pix + gs, make_float4(pixel.x, pixel.y, pixel.z, __uint_as_float(rng)));
         }
     }
-    wl_push(W->ready, n_ready, alive, my_slot, lt_mask);
+    wl_push_ready(W, head, n_ready, alive, my_slot, lt_mask);
     if (!exhausted) wl_push(W->free_, n_free, freed, my_slot, lt_mask);
     __syncwarp();
-    return wl_pack(n_ready, n_shade, n_free, exhausted);
+    return wl_pack(n_ready, n_shade, n_free, exhausted, head);
 }
 
 // list sizes live in ONE register in the traversal loop too: the kernel sits at the 64-register edge
@@ -1144,7 +1162,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TL ? 7 : SOLB_WF_MIN_CTAS)
 k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
                const float4 *__restrict__ inst_leaves, const DeviceInstance *__restrict__ instances,
                const ShadeRecord *__restrict__ shade, const __grid_constant__ WarpfrontState wl, float4 *accum, uint32_t *render,
-               unsigned long long *stats, const uint32_t n_region_slots, const __grid_constant__ TraceTuning tune) {
+               unsigned long long *stats, const uint32_t n_region_slots, const uint32_t pool_limit,
+               const __grid_constant__ TraceTuning tune) {
     SOLB_DECL_STACK();
     __shared__ WlWarp s_warp[TRACE_BLOCK / 32];
     __shared__ uint4 s_hit[TRACE_BLOCK];
@@ -1154,8 +1173,10 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
     WlWarp *const W = &s_warp[tid >> 5];
     const uint32_t slot_base = (blockIdx.x * (TRACE_BLOCK / 32) + (tid >> 5)) * (uint32_t)WL_POOL;  // < 2^32
     if (slot_base >= wl.n_warps * (uint32_t)WL_POOL) return;
-    uint32_t counts = wl_pack(0u, 0u, (uint32_t)WL_POOL, false);  // warp-uniform
-    for (uint32_t i = lane; i < (uint32_t)WL_POOL; i += 32u) W->free_[i] = (uint8_t)i;
+    // pool_limit <= WL_POOL slots are used: small regions (a rank's share of a tile-split frame, small images) are shared out
+    // evenly over the warps instead of the first warps claiming WL_POOL pixels each and the rest finding the cursor exhausted
+    uint32_t counts = wl_pack(0u, 0u, pool_limit, false, 0u);  // warp-uniform
+    for (uint32_t i = lane; i < pool_limit; i += 32u) W->free_[i] = (uint8_t)i;
     if (lane == 0) { W->pool_next = 0u; W->pool_end = 0u; }
     __syncwarp();
     uint32_t step_ctr[3] = { 0u, 0u, 0u };  // hits, paths, rays: counted inside the service steps
@@ -1169,7 +1190,7 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
     bool in_blas = false;
     uint32_t cur_inst = SOLB_MISS;
     uint32_t b_ray = 0;
-    const uint32_t fetch_idle = (uint32_t)tune.wl_fetch_idle, gen_min = (uint32_t)tune.wl_gen_min;
+    const uint32_t fetch_idle = (uint32_t)tune.wl_fetch_idle, gen_min = min((uint32_t)tune.wl_gen_min, max(8u, pool_limit - 32u));
     for (;;) {
         const uint32_t n_idle = (uint32_t)__popc(~b_ray);
         // anything to service?  (enough idle lanes | enough free slots; free is 0 once exhausted)
@@ -1221,7 +1242,7 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                 const uint32_t rank = (uint32_t)__popc(~b_ray & lt_mask);
                 const uint32_t cnt = min(WL_N_READY(counts), n_idle);
                 if (!has_ray && rank < cnt) {
-                    slot = (uint32_t)W->ready[WL_N_READY(counts) - 1u - rank];
+                    slot = (uint32_t)W->ready[((counts >> 25) + rank) & (WL_RING - 1u)];  // oldest first
                     const uint32_t gs = slot_base + slot;
                     const float4 o = wl_ld(wl.ray_o + gs), d = wl_ld(wl.ray_d + gs);
                     tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
@@ -1235,7 +1256,7 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                     in_blas = false;
                     has_ray = true;
                 }
-                counts -= cnt;  // ready is the low byte
+                counts = counts - cnt + (cnt << 25);  // n_ready -= cnt (low byte), head += cnt (top 7 bits, wraps mod WL_RING)
                 b_ray = __ballot_sync(0xffffffffu, has_ray);
                 __syncwarp();
             }
@@ -1263,6 +1284,7 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                     tr.frame.e1 = f3(f0.x, f0.y, f0.z);
                     tr.frame.e2 = f3(f0.w, f1.x, f1.y);
                     Hit h;
+                    h.gtri = s_hit[tid].y;  // the hit in hand (tie-break of equal t)
                     if (trav_tri_step(tris, tr, tmax, tgroup, h))
                         s_hit[tid] = make_uint4(TL ? cur_inst : h.inst, h.gtri, __float_as_uint(h.u), __float_as_uint(h.v));
                     if (STATS) ctr.tris++;
@@ -1686,8 +1708,11 @@ cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, c
     // small regions (a rank's share of a tile-split frame, tiny images): no more warps than 8x4 tiles
     const uint32_t want_warps = std::min<uint32_t>(std::min(warpfront_grid_warps(sm_count, tune), wl.n_warps), std::max<uint32_t>(1u, n_slots / 32u));
     const uint32_t grid = (want_warps + TRACE_BLOCK / 32 - 1) / (TRACE_BLOCK / 32);
+    // pixels a warp holds at a time: its even share of the region, between one warp-width and the full pool
+    const uint32_t share = (n_slots + want_warps - 1) / want_warps;
+    const uint32_t pool_limit = std::min<uint32_t>((uint32_t)WL_POOL, std::max<uint32_t>(32u, (share + 7u) & ~7u));
     const float4 *il = as.inst_leaves_f4();
-#define SOLB_WLF(S, T) k_pt_warpfront<S, T><<<grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, wl, accum, render, stats, n_slots, tune)
+#define SOLB_WLF(S, T) k_pt_warpfront<S, T><<<grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, wl, accum, render, stats, n_slots, pool_limit, tune)
     if (as.two_level) { if (collect) SOLB_WLF(true, true); else SOLB_WLF(false, true); }
     else { if (collect) SOLB_WLF(true, false); else SOLB_WLF(false, false); }
 #undef SOLB_WLF

@@ -38,8 +38,19 @@ def tile_rows_for_rank(rank, world, band_rows):
     return (rank * band_rows, band_rows, world * band_rows)
 
 
+def _prefer_host_nccl():
+    """libsolb binds the NCCL copy that is already in the process.  PyTorch bundles its own libnccl.so.2 and resolves it by
+    soname when it is imported, so in a Python process torch must be imported BEFORE libsolb maps the system copy:
+    otherwise torch would later be handed that (possibly older) copy and fail on a missing symbol."""
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
+
+
 def unique_id():
     """ncclGetUniqueId through the C ABI: 128 bytes rank 0 hands to every other rank."""
+    _prefer_host_nccl()
     buf = (ctypes.c_uint8 * N.COMM_ID_BYTES)()
     N.check(N.lib().solb_comm_unique_id(buf))
     return bytes(buf)
@@ -52,6 +63,7 @@ class Communicator:
     def __init__(self, context, comm_id, rank, world):
         if len(comm_id) != N.COMM_ID_BYTES:
             raise ValueError("communicator id must be %d bytes" % N.COMM_ID_BYTES)
+        _prefer_host_nccl()
         self.context, self.rank, self.world = context, int(rank), int(world)
         buf = (ctypes.c_uint8 * N.COMM_ID_BYTES).from_buffer_copy(comm_id)
         N.check(N.lib().solb_comm_init(context.handle, buf, self.rank, self.world), context.handle)

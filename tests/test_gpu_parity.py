@@ -735,8 +735,10 @@ def test_two_level_many_instances_tlas_rebuild_time(sol, ctx):
     sc = scene.load_scene(ctx, model_path("cornell"))
     xf = [trs(rng.uniform(-20, 20, 3), rng.normal(size=3), rng.uniform(0, 6.28), (rng.uniform(0.5, 1.5),) * 3) for _ in range(992)]
     sds = {}
-    for key, mode, fast in (("two", N.ACCEL_TWO_LEVEL, "1"), ("two_general", N.ACCEL_TWO_LEVEL, "0"), ("flat", N.ACCEL_FLAT, "1")):
+    for key, mode, fast in (("two", N.ACCEL_TWO_LEVEL, "1"), ("two_general", N.ACCEL_TWO_LEVEL, "0"), ("flat", N.ACCEL_FLAT, "1"),
+                            ("two_serial", N.ACCEL_TWO_LEVEL, "1")):
         _os.environ["SOLB_TLAS_FAST"] = fast  # "0": the multi-kernel TLAS build (instance counts above the single-CTA limit)
+        _os.environ["SOLB_TLAS_COOP"] = "0" if key == "two_serial" else "1"  # "0": one thread per wide node (collapse_one)
         try:
             sd = ray.SceneDescription.from_scene(ctx, sc, accel_mode=mode)
             for i, t in enumerate(xf):
@@ -744,8 +746,17 @@ def test_two_level_many_instances_tlas_rebuild_time(sol, ctx):
             sd.accel_build()
         finally:
             _os.environ.pop("SOLB_TLAS_FAST", None)
+            _os.environ.pop("SOLB_TLAS_COOP", None)
         sds[key] = sd
     two, flat = sds["two"], sds["flat"]
+    # the warp-cooperative collapse of the single-CTA kernel writes the nodes the one-thread-per-node collapse writes (their
+    # numbering depends on the order the warps claim child ranges): same node count and depth, same TLAS bytes once sorted
+    ia, ib = two.accel_info(), sds["two_serial"].accel_info()
+    assert ia.n_tlas_nodes == ib.n_tlas_nodes and ia.tlas_depth == ib.tlas_depth
+    na, nb_ = two.read_nodes()[:ia.n_tlas_nodes].copy(), sds["two_serial"].read_nodes()[:ib.n_tlas_nodes].copy()
+    na[:, 4:6] = 0  # child base / leaf base: allocation order
+    nb_[:, 4:6] = 0
+    assert sorted(map(bytes, na)) == sorted(map(bytes, nb_))
     assert two.accel_info().n_instances == 1000 and two.accel_info().n_blas == 8 and two.accel_info().n_triangles == 32
     assert flat.accel_info().n_triangles == sum(two.instance_triangles())
     n = 300_000
@@ -756,6 +767,8 @@ def test_two_level_many_instances_tlas_rebuild_time(sol, ctx):
     h1, t1 = flat.trace_rays(rays)
     h3, t3 = sds["two_general"].trace_rays(rays)
     assert np.array_equal(h2, h3) and np.array_equal(t2, t3)  # same BLASes, different TLAS topology: identical hits
+    h6, t6 = sds["two_serial"].trace_rays(rays)
+    assert np.array_equal(h2, h6) and np.array_equal(t2, t6)
     same = np.all(h2[:, :2] == h1[:, :2], axis=1)
     assert same.mean() > 0.9995  # the two builds round differently only on edge / tie rays
     assert (h1[:, 0] != N.MISS).mean() > 0.2
@@ -1173,3 +1186,46 @@ def test_synth_scene_pathtrace_frame_vs_oracle(sol, ctx, synth27, schedule):
     bm = lambda a: a[..., :3].reshape(h // 20, 20, w // 20, 20, 3).mean(axis=(1, 3))  # 20 x 20 pixel block means
     rel = np.abs(bm(g) - bm(ref)) / (bm(ref) + 1e-3)
     assert np.median(rel) < 0.05 and abs(g[..., :3].mean() / ref[..., :3].mean() - 1.0) < 0.02, (np.median(rel), g[..., :3].mean(), ref[..., :3].mean())
+
+
+# ---- PLOC builder (SOLB_PLOC=1): same invariants and the same hits as the LBVH + treelet build ---------------------------------
+
+@pytest.mark.parametrize("name", ["cornell", "Duck", "tunnel", "synth27"])
+def test_ploc_builder_invariants_and_hits(sol, ctx, name, synth27):
+    import os as _os2
+
+    from sol_rs_b200 import ray
+
+    if name == "synth27":
+        sc, fs, osc = synth27
+    else:
+        fs, osc = oracle_scene(name)
+        from sol_rs_b200 import scene
+
+        sc = scene.load_scene(ctx, model_path(name))
+    saved = _os2.environ.get("SOLB_PLOC")
+    _os2.environ["SOLB_PLOC"] = "1"
+    try:
+        sd = ray.SceneDescription.from_scene(ctx, sc)
+    finally:
+        if saved is None:
+            _os2.environ.pop("SOLB_PLOC", None)
+        else:
+            _os2.environ["SOLB_PLOC"] = saved
+    info = sd.accel_info()
+    assert info.n_triangles == osc.tri_count and info.sah_cost_binary > 0
+    if name != "synth27":  # (the Python walk is too slow for 540 000 triangles)
+        seen, n_nodes, depth = _walk_accel(sd.read_nodes(), sd.read_triangles())
+        assert np.all(seen == 1) and n_nodes == info.n_wide_nodes and depth == info.wide_depth
+    ids = sd.read_triangles().view(np.uint32).reshape(-1, 3, 4)[:, :, 3]
+    assert np.array_equal(np.sort(ids[:, 2]), np.arange(osc.tri_count))
+    rng = np.random.default_rng(21)
+    n = 300_000
+    lo, hi = osc.bounds()
+    o = rng.uniform(lo - 0.2 * (hi - lo), hi + 0.2 * (hi - lo), size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    rays = np.concatenate([o, np.full((n, 1), 1e-3), d, np.full((n, 1), 1e4)], axis=1).astype(np.float32)
+    g_hits, g_t = sd.trace_rays(rays)
+    o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
+    mism = np.any(g_hits[:, :2] != o_hits[:, :2], axis=1)
+    assert (mism & (flags == 0)).sum() == 0

@@ -236,3 +236,60 @@ def test_node_graph_instancing_loader(tmp_path):
     got = inst.instances[2]["transform"].astype(np.float64).T @ np.array([0.0, 0.0, 0.0, 1.0])
     np.testing.assert_allclose(got[:3], want[:3], rtol=1e-5, atol=1e-5)
     assert len(scene.load_scene(None, model_path("Duck")).meshes[0].extra_instance_transforms) == 0
+
+
+def test_rust_crate_binds_every_declared_symbol_with_matching_arity():
+    from sol_rs_b200 import _native as N
+
+    """rust/sol is the reference-side binding of include/solb.h (the build image has no rustc, so the crate is checked
+    textually): ffi.rs declares exactly the header's entry points, each with the header's number of parameters; the crate
+    has the modules lib.rs names; the POD mirrors have the header's sizes."""
+    rust = os.path.join(ROOT, "rust", "sol", "src")
+    hdr = open(os.path.join(ROOT, "include", "solb.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"SOLB_API\s+[\w\s\*]+?\b(solb_\w+)\s*\(([^;]*?)\)\s*;", hdr_nc, flags=re.S)}
+    assert len(decl) >= 45
+    ffi = open(os.path.join(rust, "ffi.rs")).read()
+    ffi_nc = re.sub(r"//.*", "", ffi)
+    bound = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (solb_\w+)\s*\(([^)]*)\)", ffi_nc, flags=re.S)}
+    assert set(bound) == set(decl), "ffi.rs and solb.h disagree: %s" % (set(bound) ^ set(decl))
+
+    def arity(params):
+        p = params.strip()
+        return 0 if p in ("", "void") else len([x for x in p.split(",") if x.strip()])
+
+    for name in decl:
+        assert arity(decl[name]) == arity(bound[name]), name
+
+    # struct sizes: add up the fields of the #[repr(C)] mirrors
+    def rust_struct_bytes(name):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, ffi, flags=re.S).group(1)
+        total = 0
+        for ty in re.findall(r"pub \w+: ([^,\n]+),", body):
+            m = re.match(r"\[(\w+); (\d+)\]", ty.strip())
+            base, n = (m.group(1), int(m.group(2))) if m else (ty.strip(), 1)
+            total += {"f32": 4, "u32": 4, "i32": 4, "u64": 8}[base] * n
+        return total
+
+    assert rust_struct_bytes("SolbModelVertex") == 64 and rust_struct_bytes("SolbMaterialInfo") == 48
+    assert rust_struct_bytes("SolbSceneInstance") == 144 and rust_struct_bytes("SolbSceneUniforms") == 400
+    assert rust_struct_bytes("SolbTraceParams") == ctypes.sizeof(N.TraceParams)
+    assert rust_struct_bytes("SolbStats") == ctypes.sizeof(N.Stats) and rust_struct_bytes("SolbAccelInfo") == ctypes.sizeof(N.AccelInfo)
+    # module layout: everything lib.rs declares exists, and the names the reference's examples import are defined
+    lib = open(os.path.join(rust, "lib.rs")).read()
+    mods = set(re.findall(r"^(?:pub )?mod (\w+);", lib, flags=re.M))
+    for mod in mods:
+        assert os.path.exists(os.path.join(rust, mod + ".rs")), mod
+    ray_rs, scene_rs = open(os.path.join(rust, "ray.rs")).read(), open(os.path.join(rust, "scene.rs")).read()
+    for item in ("pub struct SceneDescription", "pub struct PipelineInfo", "pub struct Pipeline", "pub struct ShaderBindingTableInfo",
+                 "pub struct ShaderBindingTable", "pub fn from_scene(", "pub fn from_meshes(", "pub fn blas_transform(",
+                 "pub fn blas_transforms(", "pub fn tlas_regenerate<", "pub fn update(", "pub fn cmd_trace_rays(",
+                 "pub fn new(context: Arc<Context>, pipeline: &Pipeline, info: ShaderBindingTableInfo)"):
+        assert item in ray_rs, item
+    for item in ("pub fn load_scene(", "pub struct Scene", "pub struct Mesh", "pub struct PrimitiveSection", "pub struct Camera",
+                 "pub fn from_view(", "pub fn look_at(", "pub fn set_window_size(", "pub fn view_matrix(", "pub fn perspective_matrix("):
+        assert item in scene_rs, item
+    # every `crate::x` path in the sources names a module of the crate or an item re-exported at its root
+    for f in os.listdir(rust):
+        for m in re.findall(r"crate::(\w+)", open(os.path.join(rust, f)).read()):
+            assert m in mods or m in ("Context", "Image2d", "SceneUniforms"), (f, m)

@@ -294,3 +294,44 @@ def test_oracle_ao_matches_second_glsl_restatement(name, cam_name, w, h, frame):
     assert n_rays == st.rays
     assert np.abs(twin[..., :3] - img[..., :3]).max() <= 1e-6
     assert 0.0 < img[..., :3].mean() <= 1.0
+
+
+# ---- fixtures from the real reference, when somebody has produced them (tools/reference_fixtures/README.md) ------------------
+# The build image cannot run sol-rs (no rustc / Vulkan / lavapipe), so these files do not exist in the repository and the
+# oracle stays "parity unpinned"; on a machine with the toolchain one command writes them and these tests pin the oracle.
+
+def _ref_fixture(name):
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.skip("%s absent: run tools/reference_fixtures/run_reference_lavapipe.sh where sol-rs can run" % name)
+    return np.load(path)
+
+
+def test_reference_fixtures_primary_hit_ids():
+    """3-ray-debug of the reference (id-writing stages) against the oracle's ids, outside the oracle's edge / tie list."""
+    from helpers import oracle_camera, oracle_scene
+
+    ref = _ref_fixture("ref_ids_Duck_900x600.npz")["ids"]
+    fs, osc = oracle_scene("Duck")
+    _, ids, _, flags = osc.debug(ocam.scene_uniforms(oracle_camera(fs, "Duck", 900, 600), 900, 600, 0), 900, 600)
+    mism = np.any(ids != ref, axis=2)
+    assert (mism & (flags == 0)).sum() == 0, "%d unlisted pixels differ from the reference" % (mism & (flags == 0)).sum()
+
+
+@pytest.mark.parametrize("fixture,name,w,h", [("ref_frame_cornell_512x512_f8.npz", "cornell", 512, 512),
+                                              ("ref_frame_tunnel_480x270_f8.npz", "tunnel", 480, 270)])
+def test_reference_fixtures_accumulated_frames(fixture, name, w, h):
+    """5-pathtrace of the reference after N accumulated frames (its own literals: 8 spp, 32 bounces) against the oracle's
+    display image: same RNG streams, so PSNR > 40 dB unless the restatement is wrong."""
+    from helpers import oracle_camera, oracle_scene
+
+    ref = _ref_fixture(fixture)
+    fs, osc = oracle_scene(name)
+    cam = oracle_camera(fs, name, w, h)
+    acc = np.zeros((h, w, 4), dtype=np.float32)
+    rgba = None
+    for f in range(int(ref["frames"])):
+        rgba, _ = osc.pathtrace_frame(ocam.scene_uniforms(cam, w, h, f), w, h, acc, 0, bool(int(ref["sky"])), 8, 32)
+    d = rgba[..., :3].astype(np.float64) - ref["rgba8"][..., :3].astype(np.float64)
+    psnr = 10 * np.log10(255.0 ** 2 / max(np.mean(d ** 2), 1e-12))
+    assert psnr > 40.0, "PSNR %.1f dB against the reference" % psnr
