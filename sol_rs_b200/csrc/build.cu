@@ -1163,7 +1163,7 @@ __host__ __device__ inline size_t tlas_fast_smem_bytes(uint32_t n) {
 // memory cost 49 000 of the kernel's 430 000 cycles at 1 000 instances
 __host__ __device__ inline size_t tlas_fast_dp_offset(uint32_t n) { return (tlas_fast_smem_bytes(n) + 31) & ~(size_t)31; }
 __host__ __device__ inline size_t tlas_fast_smem_bytes_dp(uint32_t n) { return tlas_fast_dp_offset(n) + (size_t)(2 * n) * sizeof(DpEntry); }
-constexpr size_t TLAS_FAST_SMEM_LIMIT = 227 * 1024;
+constexpr size_t TLAS_FAST_SMEM_LIMIT = 227 * 1024 - 512;  // dynamic + the kernel's static shared memory must fit 227 KB
 
 template <bool COOP>
 __global__ void __launch_bounds__(COOP ? TLAS_FAST_THREADS_COOP : TLAS_FAST_THREADS)

@@ -15,28 +15,35 @@ constexpr int TRACE_BLOCK = 128;
 
 // Traversal stack: SOLB_SM_STACK entries per lane in shared memory ([entry][thread] so a warp's
 // accesses are conflict-free), the rest spills to local memory.
+// The shared part is addressed in the shared state space (32-bit address, st.shared / ld.shared): through a generic pointer
+// every push and pop rebuilt the window base from special registers (S2R tid, S2R cga id, MOV, 2 x LEA) - 12 to 17
+// instructions per stack operation, three operations per iteration of the traversal loop
+// (profiles/r02_ncu_k_pt_warpfront_d.txt).
 struct DevStack {
-    uint2 *sm;   // this lane's column in shared memory
-    uint2 *loc;  // spill array (local memory); kept OUTSIDE the struct so sp / sm stay in registers
+    uint32_t sm;  // shared-space byte address of this lane's column; entry e at sm + e * TRACE_BLOCK * 8
+    uint2 *loc;   // spill array (local memory); kept OUTSIDE the struct so sp / sm stay in registers
     int sp;
     __device__ __forceinline__ void push(uint2 v) {
-        if (sp < SOLB_SM_STACK) sm[sp * TRACE_BLOCK] = v;
+        if (sp < SOLB_SM_STACK) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sm + (uint32_t)sp * (TRACE_BLOCK * 8u)), "r"(v.x), "r"(v.y) : "memory");
         else loc[sp - SOLB_SM_STACK] = v;
         sp++;
     }
     __device__ __forceinline__ uint2 pop() {
         sp--;
-        return sp < SOLB_SM_STACK ? sm[sp * TRACE_BLOCK] : loc[sp - SOLB_SM_STACK];
+        uint2 v;
+        if (sp < SOLB_SM_STACK) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sm + (uint32_t)sp * (TRACE_BLOCK * 8u)) : "memory");
+        else v = loc[sp - SOLB_SM_STACK];
+        return v;
     }
     __device__ __forceinline__ bool empty() const { return sp == 0; }
 };
 
-#define SOLB_DECL_STACK()                                        \
-    __shared__ uint2 s_stack[SOLB_SM_STACK * TRACE_BLOCK];       \
-    uint2 stack_spill[SOLB_LOCAL_STACK];                         \
-    DevStack stack;                                              \
-    stack.sm = s_stack + threadIdx.x;                            \
-    stack.loc = stack_spill;                                     \
+#define SOLB_DECL_STACK()                                                      \
+    __shared__ uint2 s_stack[SOLB_SM_STACK * TRACE_BLOCK];                     \
+    uint2 stack_spill[SOLB_LOCAL_STACK];                                       \
+    DevStack stack;                                                            \
+    stack.sm = (uint32_t)__cvta_generic_to_shared(s_stack + threadIdx.x);      \
+    stack.loc = stack_spill;                                                   \
     stack.sp = 0
 
 // flattened (TL = false) or two-level (TL = true) closest hit
@@ -983,6 +990,17 @@ __device__ __forceinline__ void wl_st(T *p, const T &v) {
 #endif
 }
 
+// a new ray of slot gs: origin (+ pixel id), direction and the traversal set-up derived from the direction
+__device__ __forceinline__ void wl_store_ray(const WarpfrontState &wl, uint32_t gs, float3 o, float3 d, uint32_t pixel_id) {
+    const float3 idir = f3(safe_rcp_dir(d.x), safe_rcp_dir(d.y), safe_rcp_dir(d.z));
+    const RayFrame fr = make_ray_frame(d);
+    wl_st(wl.ray_o + gs, make_float4(o.x, o.y, o.z, __uint_as_float(pixel_id)));
+    wl_st(wl.ray_d + gs, make_float4(d.x, d.y, d.z, 0.0f));
+    wl_st(wl.ray_i + gs, make_float4(idir.x, idir.y, idir.z, 0.0f));
+    wl_st(wl.frame0 + gs, make_float4(fr.e1.x, fr.e1.y, fr.e1.z, fr.e2.x));
+    wl_st(wl.frame1 + gs, make_float4(fr.e2.y, fr.e2.z, 0.0f, 0.0f));
+}
+
 __device__ __forceinline__ void wl_push(uint8_t *list, uint32_t &n, bool flag, uint32_t slot, uint32_t lt_mask) {
     const uint32_t m = __ballot_sync(0xffffffffu, flag);
     if (flag) list[n + __popc(m & lt_mask)] = (uint8_t)slot;
@@ -1053,8 +1071,7 @@ __device__ __forceinline__ uint32_t wl_generate_step(const FrameConsts *fcp, con
             const float jx = next_rand(rng), jy = next_rand(rng);  // :52
             const float3 d = primary_dir(fc, (float)x + jx, (float)y + jy);
             const uint32_t gs = slot_base + my_slot;
-            wl_st(wl.ray_o + gs, make_float4(fc.origin.x, fc.origin.y, fc.origin.z, __uint_as_float(p)));
-            wl_st(wl.ray_d + gs, make_float4(d.x, d.y, d.z, 0.0f));
+            wl_store_ray(wl, gs, fc.origin, d, p);
             wl_st(wl.thr + gs, make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u)));
             wl_st(wl.pix + gs, make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(rng)));
             ctr[1]++;
@@ -1132,8 +1149,7 @@ __device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const 
             }
         }
         if (alive) {
-            wl_st(wl.ray_o + gs, make_float4(o.x, o.y, o.z, __uint_as_float(p)));
-            wl_st(wl.ray_d + gs, make_float4(d.x, d.y, d.z, 0.0f));
+            wl_store_ray(wl, gs, o, d, p);
             wl_st(wl.thr + gs, make_float4(thr.x, thr.y, thr.z, __uint_as_float(depth | (sample << 16))));
             wl_st(wl.pix + gs, make_float4(pixel.x, pixel.y, pixel.z, __uint_as_float(rng)));
         }
@@ -1165,6 +1181,9 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                unsigned long long *stats, const uint32_t n_region_slots, const uint32_t pool_limit,
                const __grid_constant__ TraceTuning tune) {
     SOLB_DECL_STACK();
+    // opaque to the optimiser: otherwise ptxas re-derives the column address from tid / the shared window base at every push and
+    // pop (2 x S2R + MOV + LEA + IMAD) instead of keeping the register (k_wf_trace, with less room, is better off re-deriving)
+    asm volatile("" : "+r"(stack.sm));
     __shared__ WlWarp s_warp[TRACE_BLOCK / 32];
     __shared__ uint4 s_hit[TRACE_BLOCK];
     __shared__ float4 s_frame0[TRACE_BLOCK];  // e1.xyz, e2.x
@@ -1181,8 +1200,9 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
     __syncwarp();
     uint32_t step_ctr[3] = { 0u, 0u, 0u };  // hits, paths, rays: counted inside the service steps
     TraceCounters ctr = { 0, 0 };
-    // per-lane ray state (as k_wf_trace, minus the hit record and the frame)
-    bool has_ray = false;
+    // per-lane ray state (as k_wf_trace, minus the hit record and the frame).  A lane holds a ray in flight exactly while it
+    // has a node group or a triangle group in hand or entries on its stack (WL_ACTIVE): no separate flag.
+#define WL_ACTIVE() (((ngroup.y & 0xff000000u) | tgroup.y | (uint32_t)stack.sp) != 0u)
     uint32_t slot = WL_NO_SLOT;  // pool slot this lane holds: its ray in flight, or finished and not yet collected
     TravRay tr = make_trav_ray(f3(0, 0, 0), f3(0, 0, 1), fc.tmin);
     float tmax = 0.0f;
@@ -1199,7 +1219,7 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
             // (deferred to here: a finished lane just idles, so the per-iteration tail of the loop is a pop or nothing; doing the
             // hit-record store, the ballot and the list append in every iteration cost 45 instructions in 60 % of the iterations)
             {
-                const bool done = !has_ray && slot != WL_NO_SLOT;
+                const bool done = !WL_ACTIVE() && slot != WL_NO_SLOT;
                 const uint32_t b_done = __ballot_sync(0xffffffffu, done);
                 if (b_done) {
                     if (done) {
@@ -1241,23 +1261,28 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
             if (WL_N_READY(counts) > 0u && idle_enough) {
                 const uint32_t rank = (uint32_t)__popc(~b_ray & lt_mask);
                 const uint32_t cnt = min(WL_N_READY(counts), n_idle);
-                if (!has_ray && rank < cnt) {
+                if (!WL_ACTIVE() && rank < cnt) {
                     slot = (uint32_t)W->ready[((counts >> 25) + rank) & (WL_RING - 1u)];  // oldest first
                     const uint32_t gs = slot_base + slot;
-                    const float4 o = wl_ld(wl.ray_o + gs), d = wl_ld(wl.ray_d + gs);
-                    tr = make_trav_ray(f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), fc.tmin);
-                    s_frame0[tid] = make_float4(tr.frame.e1.x, tr.frame.e1.y, tr.frame.e1.z, tr.frame.e2.x);
-                    s_frame1[tid] = make_float2(tr.frame.e2.y, tr.frame.e2.z);
+                    const float4 o = wl_ld(wl.ray_o + gs), d = wl_ld(wl.ray_d + gs), id = wl_ld(wl.ray_i + gs);
+                    s_frame0[tid] = wl_ld(wl.frame0 + gs);
+                    {
+                        const float4 f1 = wl_ld(wl.frame1 + gs);
+                        s_frame1[tid] = make_float2(f1.x, f1.y);
+                    }
+                    tr.o = f3(o.x, o.y, o.z);
+                    tr.d = f3(d.x, d.y, d.z);
+                    tr.idir = f3(id.x, id.y, id.z);
+                    set_trav_octant(tr, tr.d);
                     s_hit[tid] = make_uint4(SOLB_MISS, SOLB_MISS, 0u, 0u);
                     tmax = fc.tmax;
                     ngroup = SOLB_ROOT_GROUP;
                     tgroup = make_uint2(0u, 0u);
                     stack.sp = 0;
                     in_blas = false;
-                    has_ray = true;
                 }
                 counts = counts - cnt + (cnt << 25);  // n_ready -= cnt (low byte), head += cnt (top 7 bits, wraps mod WL_RING)
-                b_ray = __ballot_sync(0xffffffffu, has_ray);
+                b_ray = __ballot_sync(0xffffffffu, WL_ACTIVE());
                 __syncwarp();
             }
             if (b_ray == 0u) {
@@ -1267,11 +1292,11 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
             }
         }
         // ---- vote: node step or triangle step (k_wf_trace) ----
-        const bool w_node = has_ray && (ngroup.y & 0xff000000u);
-        const bool w_tri = has_ray && tgroup.y;
+        const bool w_node = (ngroup.y & 0xff000000u) != 0u;
+        const bool w_tri = tgroup.y != 0u;
         const uint32_t b_node = __ballot_sync(0xffffffffu, w_node), b_tri = __ballot_sync(0xffffffffu, w_tri);
         const int nn = __popc(b_node), nt = __popc(b_tri);
-        if (nt > 0 && nt * tune.tri_weight >= nn * tune.node_weight) {
+        if (nt > 0 && nt >= nn) {  // (weights other than 1 : 1 measured slower: profiles/r02_sweep_warpfront_knobs.txt)
             if (w_tri) {
                 if (TL && !in_blas) {
                     trav_enter_instance(inst_leaves, tr.o, tr.d, tr, ngroup, tgroup, cur_inst, stack);
@@ -1296,10 +1321,8 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
             if (STATS) ctr.nodes++;
         }
         // ---- lanes with nothing in hand: pop, or finish the ray (its slot is collected at the next service) ----
-        if (has_ray && !(ngroup.y & 0xff000000u) && !tgroup.y) {
-            if (stack.empty()) {
-                has_ray = false;
-            } else {
+        if (!(ngroup.y & 0xff000000u) && !tgroup.y && !stack.empty()) {
+            {
                 const uint2 e = stack.pop();
                 if (TL && e.y == 0u) {  // sentinel: back to the TLAS with the world-space ray
                     const float4 o = wl_ld(wl.ray_o + (slot_base + slot)), d = wl_ld(wl.ray_d + (slot_base + slot));
@@ -1311,8 +1334,9 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                 else tgroup = e;
             }
         }
-        b_ray = __ballot_sync(0xffffffffu, has_ray);
+        b_ray = __ballot_sync(0xffffffffu, WL_ACTIVE());
     }
+#undef WL_ACTIVE
     warp_add_stat(stats, ST_RAYS, step_ctr[2]);
     warp_add_stat(stats, ST_HITS, step_ctr[0]);
     warp_add_stat(stats, ST_PATHS, step_ctr[1]);

@@ -75,6 +75,11 @@ constexpr int WL_POOL = SOLB_WL_POOL;
 struct WarpfrontState {
     float4 *ray_o;      // xyz origin of the ray in flight, w = bits(pixel id)
     float4 *ray_d;      // xyz direction
+    // traversal set-up of that ray, computed where the ray is born (the shade / generate steps run 32 lanes wide and converged)
+    // instead of by whichever lanes happen to be idle at refill time: make_trav_ray is 91 instructions and ran 17 lanes wide
+    float4 *ray_i;      // xyz reciprocal direction (safe_rcp_dir)
+    float4 *frame0;     // ray-space frame of the watertight test: e1.xyz, e2.x
+    float4 *frame1;     // e2.y, e2.z
     float4 *thr;        // xyz throughput, w = bits(depth | sample << 16)
     float4 *pix;        // xyz sum of finished samples, w = bits(prd.rng)
     uint4 *hit;         // instance, global triangle, bits(u), bits(v)
