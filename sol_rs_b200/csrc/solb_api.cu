@@ -88,6 +88,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->auto_wide_schedule = env_int("SOLB_AUTO_SCHEDULE", (int)c->auto_wide_schedule, 0, 3) == 0 ? SOLB_SCHEDULE_WAVEFRONT : SOLB_SCHEDULE_WARPFRONT;
         c->tune.wl_ctas_per_sm = env_int("SOLB_WL_CTAS_PER_SM", c->tune.wl_ctas_per_sm, 1, 16);
         c->tune.wl_fetch_idle = env_int("SOLB_WL_FETCH_IDLE", c->tune.wl_fetch_idle, 1, 32);
+        c->tune.wl_starve_idle = env_int("SOLB_WL_STARVE_IDLE", c->tune.wl_starve_idle, 1, 32);
         c->tune.wl_gen_min = env_int("SOLB_WL_GEN_MIN", c->tune.wl_gen_min, 1, WL_POOL);
         c->tune.wl_batch = env_int("SOLB_WL_BATCH", c->tune.wl_batch, 32, 1024) & ~31;
     }
@@ -426,6 +427,17 @@ static int do_build(solb_scene *s) {
     if (rc != SOLB_OK) return rc;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     set_build_pool(ctx->build_pool);
+    if (ctx->build_pool && s->n_tris > (1u << 20)) {
+        // Grow the scratch pool in ONE step before a large build: left to the individual allocations the first 20 M-triangle
+        // build of a process spent ~1 s mapping its ~9 GB of scratch piecemeal (bvh_build_ms_first in bench.py's extras).
+        uint64_t reserved = 0;
+        const uint64_t want = (uint64_t)s->n_tris * 480ull;
+        if (cudaMemPoolGetAttribute(ctx->build_pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess && reserved < want) {
+            void *grow = nullptr;
+            if (cudaMallocFromPoolAsync(&grow, want, ctx->build_pool, ctx->stream) == cudaSuccess) cudaFreeAsync(grow, ctx->stream);
+            cudaGetLastError();
+        }
+    }
     cudaError_t e = s->accel_mode == SOLB_ACCEL_TWO_LEVEL ? build_accel_two_level(ctx->stream, s->view(), s->accel, opt, &ctx->launches)
                                                           : build_accel(ctx->stream, s->view(), s->accel, opt, &ctx->launches);
     if (e == cudaErrorLaunchOutOfResources) return fail(ctx, SOLB_ERR_OVERFLOW, "acceleration structure deeper than the traversal stack");

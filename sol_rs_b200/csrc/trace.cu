@@ -1232,12 +1232,15 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                 }
             }
             const bool idle_enough = n_idle >= fetch_idle;
+            // a partial shade / generate step (fewer than 32 slots) only when the warp is really short of rays: these steps cost
+            // ~600 instructions whatever their width
+            const bool starving = n_idle >= (uint32_t)tune.wl_starve_idle;
             // ---- service steps (once per ~32 rays): generate + shade ----
             // The traversal state is parked in (volatile) local memory around them, so that no per-ray value is live across the
             // shading code and the register allocator can give the traversal loop the whole file.
             const bool want_gen = WL_N_FREE(counts) > 0u &&
-                (WL_N_FREE(counts) >= gen_min || (idle_enough && WL_N_READY(counts) == 0u && WL_N_SHADE(counts) < 32u));
-            const bool want_shade = WL_N_SHADE(counts) >= 32u || (WL_N_SHADE(counts) > 0u && WL_N_READY(counts) == 0u && idle_enough);
+                (WL_N_FREE(counts) >= gen_min || (starving && WL_N_READY(counts) == 0u && WL_N_SHADE(counts) < 32u));
+            const bool want_shade = WL_N_SHADE(counts) >= 32u || (WL_N_SHADE(counts) > 0u && WL_N_READY(counts) == 0u && starving);
             if (want_gen || want_shade) {
                 volatile uint32_t park[24];
                 park[0] = f2u(tr.o.x); park[1] = f2u(tr.o.y); park[2] = f2u(tr.o.z);
@@ -1248,7 +1251,7 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                 park[17] = slot; park[18] = (uint32_t)stack.sp; park[19] = cur_inst; park[20] = in_blas ? 1u : 0u;
                 if (want_gen) counts = wl_generate_step(&fc, &wl, W, slot_base, counts, n_region_slots, (uint32_t)tune.wl_batch, step_ctr);
                 // (re-evaluated: the generate step may have refilled the ready list)
-                if (WL_N_SHADE(counts) >= 32u || (WL_N_SHADE(counts) > 0u && WL_N_READY(counts) == 0u && idle_enough))
+                if (WL_N_SHADE(counts) >= 32u || (WL_N_SHADE(counts) > 0u && WL_N_READY(counts) == 0u && starving))
                     counts = wl_shade_step(&fc, instances, shade, &wl, accum, render, W, slot_base, counts, step_ctr);
                 tr.o = f3(u2f(park[0]), u2f(park[1]), u2f(park[2]));
                 tr.d = f3(u2f(park[3]), u2f(park[4]), u2f(park[5]));
@@ -1729,8 +1732,11 @@ cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, c
     const uint32_t n_slots = ((fc.width + 7u) >> 3) * region_tiles_y(fc) * 32u;
     cudaError_t err = cudaMemsetAsync(wl.cursor, 0, sizeof(uint32_t), st);
     if (err != cudaSuccess) return err;
-    // small regions (a rank's share of a tile-split frame, tiny images): no more warps than 8x4 tiles
-    const uint32_t want_warps = std::min<uint32_t>(std::min(warpfront_grid_warps(sm_count, tune), wl.n_warps), std::max<uint32_t>(1u, n_slots / 32u));
+    // small regions (a rank's share of a tile-split frame, tiny images): fewer warps rather than smaller pools.  A warp needs
+    // ~72 slots to keep 32 lanes tracing while 32 finished rays wait for a full-width shade step; with every resident warp
+    // holding 56 pixels (1/8 of a 1080p frame over 8 CTAs per SM) the shade steps ran partial and the share took 6.2 ms, with
+    // 6 CTAs per SM (72 slots each) 4.9 ms (tools/tile_time.py, profiles/r02_tile_split.txt).
+    const uint32_t want_warps = std::min<uint32_t>(std::min(warpfront_grid_warps(sm_count, tune), wl.n_warps), std::max<uint32_t>(1u, n_slots / 72u));
     const uint32_t grid = (want_warps + TRACE_BLOCK / 32 - 1) / (TRACE_BLOCK / 32);
     // pixels a warp holds at a time: its even share of the region, between one warp-width and the full pool
     const uint32_t share = (n_slots + want_warps - 1) / want_warps;

@@ -61,6 +61,7 @@ struct TraceTuning {
     // warp-local wavefront schedule (k_pt_warpfront)
     int wl_ctas_per_sm = 8;    // persistent CTAs per SM (64 registers -> 8 x 128 threads)
     int wl_fetch_idle = 16;    // hand ready rays to idle lanes once this many lanes are idle (8: 3 556, 12: 3 618, 16: 3 645 Mrays/s)
+    int wl_starve_idle = 16;   // partial (< 32 slots) shade / generate steps only once this many lanes are idle and nothing is ready
     int wl_gen_min = 32;       // start new pixels once this many of a warp's slots are free (or its lanes starve): a full-width generate step
     int wl_batch = 32;         // pixels a warp takes from the frame's cursor per atomic (one 8x4 tile)
 };

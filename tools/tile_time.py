@@ -10,6 +10,7 @@ import sol_rs_b200 as sol  # noqa: E402
 from sol_rs_b200 import _native as N, ray, scene  # noqa: E402
 
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+SCHED = {"wavefront": N.SCHEDULE_WAVEFRONT, "warpfront": N.SCHEDULE_WARPFRONT, "megakernel": N.SCHEDULE_MEGAKERNEL}[sys.argv[2] if len(sys.argv) > 2 else "warpfront"]
 W, H = 1920, 1080
 ctx = sol.Context(0)
 sc = scene.load_scene(ctx, os.path.join(ROOT, "assets", "models", "tunnel.gltf"))
@@ -23,14 +24,14 @@ accum, render = sol.Image2d(ctx, W, H, N.FORMAT_RGBA32F), sol.Image2d(ctx, W, H,
 for rank in (0, world // 2):
     tile = (rank * 8, 8, world * 8) if world > 1 else None
     for f in range(3):
-        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, W, H, f), accum, render, max_bounces=8, schedule=N.SCHEDULE_WAVEFRONT,
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, W, H, f), accum, render, max_bounces=8, schedule=SCHED,
                                              tile_rows=tile), (W, H, 1))
     ctx.synchronize()
     ctx.reset_stats()
     t0 = time.perf_counter()
     n = 10
     for f in range(3, 3 + n):
-        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, W, H, f), accum, render, max_bounces=8, schedule=N.SCHEDULE_WAVEFRONT,
+        sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, W, H, f), accum, render, max_bounces=8, schedule=SCHED,
                                              tile_rows=tile), (W, H, 1))
     ctx.synchronize()
     dt = (time.perf_counter() - t0) / n
