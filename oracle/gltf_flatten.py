@@ -20,6 +20,7 @@ compare the two.  Nothing in the product imports this module.
 import base64
 import json
 import os
+import urllib.parse
 
 import numpy as np
 
@@ -65,7 +66,7 @@ class Gltf:
             elif uri.startswith("data:"):
                 data = base64.b64decode(uri.split(",", 1)[1])
             else:
-                with open(os.path.join(base, uri), "rb") as f:
+                with open(os.path.join(base, urllib.parse.unquote(uri)), "rb") as f:
                     data = f.read()
             self.buffers.append(data[: b["byteLength"]])
 
@@ -73,10 +74,12 @@ class Gltf:
         """Accessor -> ndarray [count, ncomp] in its stored component type (no sparse support:
         no shipped asset uses it)."""
         acc = self.doc["accessors"][idx]
-        view = self.doc["bufferViews"][acc["bufferView"]]
         dt = np.dtype(_COMPONENT[acc["componentType"]])
         nc = _NCOMP[acc["type"]]
         count = acc["count"]
+        if "bufferView" not in acc:  # an accessor without bufferView is all zeros (glTF 2.0 5.1.1)
+            return np.zeros((count, nc), dtype=dt), acc
+        view = self.doc["bufferViews"][acc["bufferView"]]
         start = view.get("byteOffset", 0) + acc.get("byteOffset", 0)
         stride = view.get("byteStride", 0) or dt.itemsize * nc
         strided = np.ndarray(shape=(count, nc), dtype=dt, buffer=self.buffers[view["buffer"]], offset=start,
@@ -92,6 +95,10 @@ def _normalized_to_f32(arr):
         return (arr.astype(F32) / F32(255.0)).astype(F32)
     if arr.dtype == np.uint16:
         return (arr.astype(F32) / F32(65535.0)).astype(F32)
+    if arr.dtype == np.int8:  # signed normalised (KHR_mesh_quantization): max(v / 127, -1)
+        return np.maximum(arr.astype(F32) / F32(127.0), F32(-1.0)).astype(F32)
+    if arr.dtype == np.int16:
+        return np.maximum(arr.astype(F32) / F32(32767.0), F32(-1.0)).astype(F32)
     raise ValueError("unsupported normalized type %s" % arr.dtype)
 
 
@@ -307,6 +314,7 @@ def load_scene(path, instancing=False):
                 v[:, 8:12] = [0.0, 1.0, 0.0, 1.0]  # normal default (0,1,0), w = 1: mod.rs:184,190
                 if "NORMAL" in attrs:
                     nrm, _ = g.accessor(attrs["NORMAL"])
+                    nrm = _normalized_to_f32(nrm)
                     k = min(n, nrm.shape[0])
                     v[:k, 8:11] = nrm[:k]
                 if "TEXCOORD_0" in attrs:

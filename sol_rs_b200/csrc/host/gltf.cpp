@@ -18,6 +18,7 @@
 
 #include "json.hpp"
 #include "sol.hpp"
+#include <algorithm>
 
 namespace sol {
 namespace scene {
@@ -61,10 +62,23 @@ struct Doc {
 };
 
 struct AccessorView {
-    const uint8_t *base = nullptr;
+    const uint8_t *base = nullptr;  // null: an accessor without bufferView = all zeros (glTF 2.0 5.1.1)
     size_t count = 0, stride = 0;
     int component = 0, ncomp = 0;
 };
+
+// RFC 3986 percent-decoding of a relative buffer URI ("my%20mesh.bin")
+std::string uri_decode(const std::string &s) {
+    auto hex = [](char c) { return c >= '0' && c <= '9' ? c - '0' : (c >= 'a' && c <= 'f' ? c - 'a' + 10 : (c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1)); };
+    std::string out;
+    for (size_t i = 0; i < s.size(); i++) {
+        if (s[i] == '%' && i + 2 < s.size() + 0 && hex(s[i + 1]) >= 0 && hex(s[i + 2]) >= 0) {
+            out.push_back((char)(hex(s[i + 1]) * 16 + hex(s[i + 2])));
+            i += 2;
+        } else out.push_back(s[i]);
+    }
+    return out;
+}
 
 int comp_size(int c) { return (c == 5120 || c == 5121) ? 1 : ((c == 5122 || c == 5123) ? 2 : 4); }
 int type_ncomp(const std::string &t) {
@@ -78,10 +92,15 @@ int type_ncomp(const std::string &t) {
 AccessorView accessor(const Doc &d, size_t index) {
     const json::Value &acc = d.root["accessors"][index];
     if (acc.has("sparse")) throw Error(SOLB_ERR_UNSUPPORTED, "load_scene: sparse accessors are not supported");
-    const json::Value &view = d.root["bufferViews"][(size_t)acc["bufferView"].integer(0)];
     AccessorView a;
     a.component = (int)acc["componentType"].integer(0);
     a.ncomp = type_ncomp(acc["type"].string());
+    if (!acc.has("bufferView")) {  // zero-filled accessor: no storage to point at
+        a.count = (size_t)acc["count"].integer(0);
+        a.stride = (size_t)comp_size(a.component) * a.ncomp;
+        return a;
+    }
+    const json::Value &view = d.root["bufferViews"][(size_t)acc["bufferView"].integer(0)];
     a.count = (size_t)acc["count"].integer(0);
     const size_t elem = (size_t)comp_size(a.component) * a.ncomp;
     const size_t bs = (size_t)view["byteStride"].integer(0);
@@ -94,15 +113,20 @@ AccessorView accessor(const Doc &d, size_t index) {
 }
 
 float read_f32(const AccessorView &a, size_t i, int c) {  // into_f32 / into_rgba_f32 casts
+    if (!a.base) return 0.0f;
     const uint8_t *p = a.base + i * a.stride + (size_t)c * comp_size(a.component);
     switch (a.component) {
         case 5126: { float f; std::memcpy(&f, p, 4); return f; }
         case 5121: return (float)p[0] / 255.0f;
         case 5123: { uint16_t v; std::memcpy(&v, p, 2); return (float)v / 65535.0f; }
+        // signed normalised components (KHR_mesh_quantization normals / texture coordinates): max(v / 127, -1), max(v / 32767, -1)
+        case 5120: return std::max((float)(int8_t)p[0] / 127.0f, -1.0f);
+        case 5122: { int16_t v; std::memcpy(&v, p, 2); return std::max((float)v / 32767.0f, -1.0f); }
         default: throw Error(SOLB_ERR_UNSUPPORTED, "load_scene: unsupported float attribute component type");
     }
 }
 uint32_t read_u32(const AccessorView &a, size_t i) {  // into_u32
+    if (!a.base) return 0u;
     const uint8_t *p = a.base + i * a.stride;
     switch (a.component) {
         case 5121: return p[0];
@@ -239,7 +263,7 @@ Scene load_scene(std::shared_ptr<Context>, const std::string &filepath) {
             if (comma == std::string::npos) throw Error(SOLB_ERR_INVALID, "load_scene: malformed data URI");
             data = base64_decode(uri, comma + 1);
         } else {
-            data = read_file(dir + "/" + uri, true);
+            data = read_file(dir + "/" + uri_decode(uri), true);
         }
         const size_t want = (size_t)buffers[i]["byteLength"].integer(0);
         if (data.size() < want) throw Error(SOLB_ERR_INVALID, "load_scene: buffer shorter than byteLength");

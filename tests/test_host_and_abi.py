@@ -293,3 +293,37 @@ def test_rust_crate_binds_every_declared_symbol_with_matching_arity():
     for f in os.listdir(rust):
         for m in re.findall(r"crate::(\w+)", open(os.path.join(rust, f)).read()):
             assert m in mods or m in ("Context", "Image2d", "SceneUniforms"), (f, m)
+
+
+def test_loaders_handle_snorm_zero_filled_and_percent_encoded_uris(tmp_path):
+    """Valid glTF the shipped assets do not exercise: normalised signed BYTE normals, an accessor without
+    bufferView (= zeros), a percent-encoded buffer URI.  The C++ loader and the oracle's loader must agree byte for byte."""
+    import json
+    import struct
+
+    from sol_rs_b200 import scene
+
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    nrm = np.array([[0, 0, 127, 0], [0, 127, 0, 0], [-128, 0, 0, 0]], dtype=np.int8)  # VEC3 of BYTE, stride 4
+    idx = np.array([0, 1, 2], dtype=np.uint16)
+    blob = pos.tobytes() + nrm.tobytes() + idx.tobytes() + b"\x00\x00"
+    (tmp_path / "my mesh.bin").write_bytes(blob)
+    doc = {"asset": {"version": "2.0"}, "buffers": [{"uri": "my%20mesh.bin", "byteLength": len(blob)}],
+           "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 12, "byteStride": 4},
+                           {"buffer": 0, "byteOffset": 48, "byteLength": 6}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3", "min": [0, 0, 0], "max": [1, 1, 0]},
+                         {"bufferView": 1, "componentType": 5120, "normalized": True, "count": 3, "type": "VEC3"},
+                         {"bufferView": 2, "componentType": 5123, "count": 3, "type": "SCALAR"},
+                         {"componentType": 5126, "count": 3, "type": "VEC2"}],  # no bufferView: zero-filled texture coordinates
+           "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.5, 0.5, 0.5, 1.0]}}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1, "TEXCOORD_0": 3}, "indices": 2, "material": 0}]}],
+           "nodes": [{"mesh": 0}], "scenes": [{"nodes": [0]}], "scene": 0}
+    path = tmp_path / "edge.gltf"
+    path.write_text(json.dumps(doc))
+    s = scene.load_scene(None, str(path))
+    fs = gf.load_scene(str(path))
+    v = s.meshes[0].vertices
+    assert np.array_equal(v, fs.vertices) and np.array_equal(s.meshes[0].indices, fs.indices)
+    np.testing.assert_array_equal(v[:, 8:11], np.array([[0, 0, 1], [0, 1, 0], [-1, 0, 0]], dtype=np.float32))  # -128 clamps to -1
+    assert np.all(v[:, 12:14] == 0.0) and np.array_equal(v[:, 0:3], pos)
+    assert struct.calcsize("f") == 4
