@@ -389,7 +389,11 @@ def main():
     cam.set_window_size((WIDTH, HEIGHT))
     e2e_accum = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA32F)
     e2e_render = sol.Image2d(ctx, WIDTH, HEIGHT, N.FORMAT_RGBA8)
-    host_frame = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, pin_memory=True).numpy()
+    # two frames in flight, like the reference's render loop (one fence + one present image per swapchain image,
+    # src/renderer.rs:72-81, 188): frame f's read-back overlaps frame f+1's tracing, and a slot's host buffer is reused only
+    # after its fence has been waited for
+    host_frames = [ctx.host_alloc((HEIGHT, WIDTH, 4), np.uint8) for _ in range(2)]
+    fences = [ctx.fence() for _ in range(2)]
     e2e_mode = N.ACCUM_SUM if world > 1 else N.ACCUM_MIX
     for f in range(2):
         sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, WIDTH, HEIGHT, f), e2e_accum, e2e_render, schedule=sched,
@@ -399,23 +403,28 @@ def main():
     barrier_sync()
     t0 = time.perf_counter()
     n_e2e = min(steps, 8)
-    for f in multigpu.frames_for_rank(rank, world, world * n_e2e, first=200):
+    for i, f in enumerate(multigpu.frames_for_rank(rank, world, world * n_e2e, first=200)):
+        fences[i & 1].wait()  # wait_for_and_reset_fence: the frame that last used this slot has reached host memory
         u = scene.scene_uniforms(cam, WIDTH, HEIGHT, f)  # host-side camera -> 400-byte uniform block (the step's input)
         sd.tlas_regenerate()
         sbt.cmd_trace_rays(ray.TraceBindings(sd, u, e2e_accum, e2e_render, schedule=sched, samples_per_frame=SPP,
                                              max_bounces=MAX_BOUNCES, accum_mode=e2e_mode), (WIDTH, HEIGHT, 1))
-        e2e_render.readback(host_frame)  # the step's result reaches host memory
+        e2e_render.readback_async(host_frames[i & 1])  # the step's result -> host memory (replaces blit + present)
+        fences[i & 1].signal()
     if world > 1:
         comm.reduce_accum(e2e_accum, 0, e2e_accum, e2e_render)
         if rank == 0:
-            e2e_render.readback(host_frame)  # the combined image
-        ctx.synchronize()
+            e2e_render.readback(host_frames[0])  # the combined image
+    for fence in fences:
+        fence.wait()
+    ctx.synchronize()
     dt_e2e = time.perf_counter() - t0
     e2e_ms, e2e_rays = gather_max_sum(1e3 * dt_e2e, int(ctx.stats().rays))
     e2e = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 400 + 48,
            "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": e2e_ms / n_e2e, "steps": n_e2e,
-           "includes": "uniform block + params H2D, rgba8 frame D2H every step" + ("; closing NCCL reduce + resolve + D2H of the combined image on rank 0" if world > 1 else "")}
-    del e2e_accum, e2e_render
+           "frames_in_flight": 2,
+           "includes": "uniform block + params H2D, rgba8 frame D2H into page-locked memory every step (2 frames in flight, per-slot fences)" + ("; closing NCCL reduce + resolve + D2H of the combined image on rank 0" if world > 1 else "")}
+    del e2e_accum, e2e_render, host_frames, fences
 
     roofline = None
     cpu_baseline = None

@@ -47,6 +47,7 @@ typedef enum SolbStatus {
 typedef struct solb_ctx solb_ctx;       /* replaces sol::Context for this path: src/context.rs        */
 typedef struct solb_scene solb_scene;   /* replaces ray::SceneDescription (+BLAS/TLAS): src/ray/mod.rs */
 typedef struct solb_target solb_target; /* replaces sol::Image2d storage targets: src/texture.rs:36-96 */
+typedef struct solb_fence solb_fence;   /* replaces AppFrameData::in_flight_fence: src/renderer.rs:8      */
 
 /* ---- POD data contracts (identical bytes to the reference) ------------- */
 
@@ -181,6 +182,19 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out);
 SOLB_API int solb_ctx_preload(solb_ctx *ctx);
 SOLB_API int solb_ctx_destroy(solb_ctx *ctx);
 SOLB_API int solb_synchronize(solb_ctx *ctx); /* queue_wait_idle, src/context.rs:539-559 */
+/* Frames in flight.  Replaces the per-frame fence of the reference's render loop: vkCreateFence(SIGNALED) per swapchain image
+ * (src/renderer.rs:72-81), queue_submit(..., in_flight_fence) (src/renderer.rs:310-317) and wait_for_and_reset_fence at the
+ * start of the frame that reuses the slot (src/renderer.rs:123-131, 188).  A new fence is signalled; solb_fence_signal
+ * re-arms it to complete when everything enqueued on the context so far (traces, resolves, asynchronous readbacks) has
+ * finished; solb_fence_wait blocks the calling thread until then. */
+SOLB_API int solb_fence_create(solb_ctx *ctx, solb_fence **out);
+SOLB_API int solb_fence_signal(solb_fence *fence);
+SOLB_API int solb_fence_wait(solb_fence *fence);
+SOLB_API int solb_fence_destroy(solb_fence *fence);
+/* Page-locked host memory for uploads / read-backs (the reference's CpuToGpu / GpuToCpu staging buffers,
+ * src/buffer.rs:76-83). */
+SOLB_API int solb_host_alloc(solb_ctx *ctx, size_t bytes, void **out);
+SOLB_API int solb_host_free(solb_ctx *ctx, void *ptr);
 /* Return cached build scratch to the driver (the stream-ordered pool keeps it between builds so per-frame rebuilds do not
  * re-map memory; cf. the reference's gpu-allocator blocks, src/context.rs:229). Synchronises. */
 SOLB_API int solb_ctx_trim(solb_ctx *ctx);
@@ -239,6 +253,11 @@ SOLB_API int solb_target_clear(solb_target *t);
 /* Replaces cmd_blit_to(present image) (examples/5-pathtrace.rs:360-361): D2H of the whole image. Synchronises. */
 SOLB_API int solb_target_readback(solb_target *t, void *host, size_t bytes);
 SOLB_API int solb_target_upload(solb_target *t, const void *host, size_t bytes);
+/* The same copy without the wait, for a render loop with frames in flight (the reference's blit is a queued command too,
+ * examples/5-pathtrace.rs:360-361 inside the frame's command buffer): enqueued after the frames traced so far; `host` must
+ * stay valid, and is complete, once a fence signalled after this call has been waited for (or after solb_synchronize).
+ * The copy overlaps the next frame's tracing when `host` is page-locked (solb_host_alloc). */
+SOLB_API int solb_target_readback_async(solb_target *t, void *host, size_t bytes);
 SOLB_API int solb_target_device_ptr(solb_target *t, void **out); /* for torch.distributed / NCCL plumbing */
 SOLB_API int solb_target_info(solb_target *t, uint32_t *width, uint32_t *height, uint32_t *format);
 

@@ -75,6 +75,69 @@ impl Context {
     }
 }
 
+/// Per-frame fence of a render loop with frames in flight (AppFrameData::in_flight_fence, src/renderer.rs:8): created
+/// signalled; `signal` after the frame's work is enqueued (queue_submit(.., fence), src/renderer.rs:310-317), `wait` before
+/// the slot is reused (wait_for_and_reset_fence, src/renderer.rs:123-131).
+pub struct Fence {
+    context: Arc<Context>,
+    raw: *mut solb_fence,
+}
+
+impl Fence {
+    pub fn new(context: Arc<Context>) -> Fence {
+        let mut raw = std::ptr::null_mut();
+        context.check(unsafe { solb_fence_create(context.raw, &mut raw) });
+        Fence { context, raw }
+    }
+
+    pub fn signal(&self) {
+        self.context.check(unsafe { solb_fence_signal(self.raw) });
+    }
+
+    pub fn wait(&self) {
+        self.context.check(unsafe { solb_fence_wait(self.raw) });
+    }
+}
+
+impl Drop for Fence {
+    fn drop(&mut self) {
+        unsafe {
+            solb_fence_destroy(self.raw);
+        }
+    }
+}
+
+/// Page-locked host bytes for uploads and read-backs (the reference's CpuToGpu / GpuToCpu buffers, src/buffer.rs:76-83).
+pub struct HostBuffer {
+    context: Arc<Context>,
+    ptr: *mut u8,
+    len: usize,
+}
+
+impl HostBuffer {
+    pub fn new(context: Arc<Context>, len: usize) -> HostBuffer {
+        let mut p: *mut c_void = std::ptr::null_mut();
+        context.check(unsafe { solb_host_alloc(context.raw, len, &mut p) });
+        HostBuffer { context, ptr: p as *mut u8, len }
+    }
+
+    pub fn as_slice(&self) -> &[u8] {
+        unsafe { std::slice::from_raw_parts(self.ptr, self.len) }
+    }
+
+    pub fn as_mut_slice(&mut self) -> &mut [u8] {
+        unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) }
+    }
+}
+
+impl Drop for HostBuffer {
+    fn drop(&mut self) {
+        unsafe {
+            solb_host_free(self.context.raw, self.ptr as *mut c_void);
+        }
+    }
+}
+
 impl Drop for Context {
     fn drop(&mut self) {
         unsafe {

@@ -15,6 +15,10 @@ pub struct solb_scene {
 pub struct solb_target {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct solb_fence {
+    _private: [u8; 0],
+}
 
 /// identical bytes to sol::scene::ModelVertex (src/scene/mesh.rs:9-14), 64 B
 #[repr(C)]
@@ -145,6 +149,12 @@ extern "C" {
     pub fn solb_ctx_preload(ctx: *mut solb_ctx) -> c_int;
     pub fn solb_ctx_destroy(ctx: *mut solb_ctx) -> c_int;
     pub fn solb_synchronize(ctx: *mut solb_ctx) -> c_int;
+    pub fn solb_fence_create(ctx: *mut solb_ctx, out: *mut *mut solb_fence) -> c_int;
+    pub fn solb_fence_signal(fence: *mut solb_fence) -> c_int;
+    pub fn solb_fence_wait(fence: *mut solb_fence) -> c_int;
+    pub fn solb_fence_destroy(fence: *mut solb_fence) -> c_int;
+    pub fn solb_host_alloc(ctx: *mut solb_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn solb_host_free(ctx: *mut solb_ctx, ptr: *mut c_void) -> c_int;
     pub fn solb_ctx_trim(ctx: *mut solb_ctx) -> c_int;
     pub fn solb_last_error(ctx: *mut solb_ctx) -> *const c_char;
     pub fn solb_version() -> u32;
@@ -173,6 +183,7 @@ extern "C" {
     pub fn solb_target_destroy(t: *mut solb_target) -> c_int;
     pub fn solb_target_clear(t: *mut solb_target) -> c_int;
     pub fn solb_target_readback(t: *mut solb_target, host: *mut c_void, bytes: usize) -> c_int;
+    pub fn solb_target_readback_async(t: *mut solb_target, host: *mut c_void, bytes: usize) -> c_int;
     pub fn solb_target_upload(t: *mut solb_target, host: *const c_void, bytes: usize) -> c_int;
     pub fn solb_target_device_ptr(t: *mut solb_target, out: *mut *mut c_void) -> c_int;
     pub fn solb_target_info(t: *mut solb_target, width: *mut u32, height: *mut u32, format: *mut u32) -> c_int;

@@ -72,6 +72,14 @@ impl Image2d {
         self.context.check(unsafe { solb_target_readback(self.raw, host.as_mut_ptr() as *mut c_void, host.len()) });
     }
 
+    /// The same copy enqueued without the wait: `host` is complete once a `Fence` signalled after this call has been waited
+    /// for (frames in flight; the reference's blit is a queued command as well).
+    pub fn readback_async(&self, host: &mut crate::HostBuffer) {
+        let bytes = host.as_mut_slice();
+        assert_eq!(bytes.len(), self.size_bytes());
+        self.context.check(unsafe { solb_target_readback_async(self.raw, bytes.as_mut_ptr() as *mut c_void, bytes.len()) });
+    }
+
     pub fn upload(&self, host: &[u8]) {
         assert_eq!(host.len(), self.size_bytes());
         self.context.check(unsafe { solb_target_upload(self.raw, host.as_ptr() as *const c_void, host.len()) });

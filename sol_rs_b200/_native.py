@@ -84,6 +84,12 @@ SYMBOLS = {
     "solb_ctx_destroy": (_i, [_vp]),
     "solb_ctx_preload": (_i, [_vp]),
     "solb_synchronize": (_i, [_vp]),
+    "solb_fence_create": (_i, [_vp, _pp]),
+    "solb_fence_signal": (_i, [_vp]),
+    "solb_fence_wait": (_i, [_vp]),
+    "solb_fence_destroy": (_i, [_vp]),
+    "solb_host_alloc": (_i, [_vp, ctypes.c_size_t, _pp]),
+    "solb_host_free": (_i, [_vp, _vp]),
     "solb_ctx_trim": (_i, [_vp]),
     "solb_last_error": (ctypes.c_char_p, [_vp]),
     "solb_version": (_u32, []),
@@ -108,6 +114,7 @@ SYMBOLS = {
     "solb_target_destroy": (_i, [_vp]),
     "solb_target_clear": (_i, [_vp]),
     "solb_target_readback": (_i, [_vp, _vp, ctypes.c_size_t]),
+    "solb_target_readback_async": (_i, [_vp, _vp, ctypes.c_size_t]),
     "solb_target_upload": (_i, [_vp, _vp, ctypes.c_size_t]),
     "solb_target_device_ptr": (_i, [_vp, _pp]),
     "solb_target_info": (_i, [_vp, ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),

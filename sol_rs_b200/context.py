@@ -38,6 +38,14 @@ class Context:
     def synchronize(self):
         N.check(self._lib.solb_synchronize(self._h), self._h)
 
+    def fence(self):
+        """a frame-in-flight fence (AppFrameData::in_flight_fence, src/renderer.rs:8), created signalled"""
+        return Fence(self)
+
+    def host_alloc(self, shape, dtype=np.uint8):
+        """page-locked host array for uploads / read-backs (solb_host_alloc); freed with the returned array"""
+        return _PinnedArray.make(self, shape, dtype)
+
     def trim(self):
         """hand the cached build scratch back to the driver (solb_ctx_trim)"""
         N.check(self._lib.solb_ctx_trim(self._h), self._h)
@@ -71,6 +79,60 @@ class Context:
             pass
 
 
+class Fence:
+    """solb_fence_*: signal() after a frame's work has been enqueued, wait() before reusing that frame slot's host buffers
+    (queue_submit(.., in_flight_fence) / wait_for_and_reset_fence, src/renderer.rs:310-317, 123-131)."""
+
+    def __init__(self, context):
+        self.context = context
+        self._lib = N.lib()
+        self._h = ctypes.c_void_p()
+        N.check(self._lib.solb_fence_create(context.handle, ctypes.byref(self._h)), context.handle)
+
+    def signal(self):
+        N.check(self._lib.solb_fence_signal(self._h), self.context.handle)
+
+    def wait(self):
+        N.check(self._lib.solb_fence_wait(self._h), self.context.handle)
+
+    def close(self):
+        if self._h:
+            self._lib.solb_fence_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _PinnedArray:
+    """owner of one solb_host_alloc block; numpy views keep it alive through .base"""
+
+    def __init__(self, context, nbytes):
+        self.context = context
+        self._lib = N.lib()
+        self.ptr = ctypes.c_void_p()
+        N.check(self._lib.solb_host_alloc(context.handle, int(nbytes), ctypes.byref(self.ptr)), context.handle)
+        self.nbytes = int(nbytes)
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr.value, False), "version": 3}
+
+    @classmethod
+    def make(cls, context, shape, dtype):
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        owner = cls(context, max(n, 1))
+        return np.asarray(owner)[:n].view(dt).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr and self.context.handle:
+                self._lib.solb_host_free(self.context.handle, self.ptr)
+        except Exception:
+            pass
+
+
 _NP = {N.FORMAT_RGBA32F: (np.float32, 4), N.FORMAT_RGBA8: (np.uint8, 4), N.FORMAT_RG32UI: (np.uint32, 2)}
 
 
@@ -98,6 +160,13 @@ class Image2d:
             out = np.empty((self.height, self.width, nc), dtype=dt)
         assert out.flags.c_contiguous and out.nbytes == self.nbytes
         N.check(self._lib.solb_target_readback(self._h, out.ctypes.data_as(ctypes.c_void_p), out.nbytes), self.context.handle)
+        return out
+
+    def readback_async(self, out):
+        """the same copy enqueued without the wait (solb_target_readback_async): `out` is complete after a Fence signalled
+        later has been waited for, or after Context.synchronize(); give it page-locked memory (Context.host_alloc)"""
+        assert out.flags.c_contiguous and out.nbytes == self.nbytes
+        N.check(self._lib.solb_target_readback_async(self._h, out.ctypes.data_as(ctypes.c_void_p), out.nbytes), self.context.handle)
         return out
 
     def upload(self, arr):

@@ -91,6 +91,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.wl_starve_idle = env_int("SOLB_WL_STARVE_IDLE", c->tune.wl_starve_idle, 1, 32);
         c->tune.wl_gen_min = env_int("SOLB_WL_GEN_MIN", c->tune.wl_gen_min, 1, WL_POOL);
         c->tune.wl_batch = env_int("SOLB_WL_BATCH", c->tune.wl_batch, 32, 1024) & ~31;
+        c->tune.wl_frames_in_flight = env_int("SOLB_WL_FRAMES_IN_FLIGHT", c->tune.wl_frames_in_flight, 1, 2);
     }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
@@ -116,10 +117,32 @@ static void free_wavefront(solb_ctx *c) {
 }
 
 static void free_warpfront(solb_ctx *c) {
-    WarpfrontState &w = c->wl;
-    cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.ray_i); cudaFree(w.frame0); cudaFree(w.frame1);
-    cudaFree(w.thr); cudaFree(w.pix); cudaFree(w.hit); cudaFree(w.cursor);
-    w = WarpfrontState{};
+    for (int k = 0; k < 2; k++) {
+        if (c->frame_stream[k]) cudaStreamSynchronize(c->frame_stream[k]);
+        WarpfrontState &w = c->wl[k];
+        cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.ray_i); cudaFree(w.frame0); cudaFree(w.frame1);
+        cudaFree(w.thr); cudaFree(w.pix); cudaFree(w.hit); cudaFree(w.cursor);
+        w = WarpfrontState{};
+        cudaFree(c->frame_sum[k]);
+        c->frame_sum[k] = nullptr;
+        c->frame_sum_pixels[k] = 0;
+        if (c->frame_stream[k]) cudaStreamDestroy(c->frame_stream[k]);
+        c->frame_stream[k] = nullptr;
+        cudaEvent_t *evs[] = { &c->ev_trace_done[k], &c->ev_resolve_done[k], &c->ev_k0[k], &c->ev_k1[k] };
+        for (cudaEvent_t *e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+        c->have_resolve_done[k] = false;
+    }
+    if (c->ev_side_barrier) cudaEventDestroy(c->ev_side_barrier);
+    if (c->ev_serial) cudaEventDestroy(c->ev_serial);
+    c->ev_side_barrier = c->ev_serial = nullptr;
+    c->have_side_barrier = false;
+}
+
+// Work just enqueued on the ctx stream that later frames (launched on the side streams) must see: scene uploads, builds,
+// TLAS regenerates, stats resets.
+static void mark_side_barrier(solb_ctx *c) {
+    if (!c->ev_side_barrier && cudaEventCreateWithFlags(&c->ev_side_barrier, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaEventRecord(c->ev_side_barrier, c->stream) == cudaSuccess) c->have_side_barrier = true;
 }
 
 static void ctx_release(solb_ctx *ctx) {
@@ -166,6 +189,60 @@ SOLB_API int solb_synchronize(solb_ctx *ctx) {
     if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_fence_create(solb_ctx *ctx, solb_fence **out) {
+    if (!ctx || !out) return fail(ctx, SOLB_ERR_INVALID, "null argument");
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaEvent_t ev = nullptr;
+    CU(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    solb_fence *f = new solb_fence();
+    f->ctx = ctx;
+    f->ev = ev;
+    *out = f;
+    return SOLB_OK;
+    SOLB_CATCH(ctx)
+}
+
+SOLB_API int solb_fence_signal(solb_fence *f) {
+    if (!f) return fail(nullptr, SOLB_ERR_INVALID, "null fence");
+    CU(f->ctx, cudaSetDevice(f->ctx->device));
+    CU(f->ctx, cudaEventRecord(f->ev, f->ctx->stream));  // every frame's resolve is on this stream, after its kernel
+    f->armed = true;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_fence_wait(solb_fence *f) {
+    if (!f) return fail(nullptr, SOLB_ERR_INVALID, "null fence");
+    if (!f->armed) return SOLB_OK;
+    CU(f->ctx, cudaSetDevice(f->ctx->device));
+    CU(f->ctx, cudaEventSynchronize(f->ev));
+    f->armed = false;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_fence_destroy(solb_fence *f) {
+    if (!f) return SOLB_OK;
+    cudaSetDevice(f->ctx->device);
+    if (f->ev) cudaEventDestroy(f->ev);
+    delete f;
+    return SOLB_OK;
+}
+
+SOLB_API int solb_host_alloc(solb_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out || !bytes) return fail(ctx, SOLB_ERR_INVALID, "null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return SOLB_OK;
+}
+
+SOLB_API int solb_host_free(solb_ctx *ctx, void *ptr) {
+    if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
+    if (!ptr) return SOLB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaFreeHost(ptr));
     return SOLB_OK;
 }
 
@@ -273,6 +350,7 @@ SOLB_API int solb_stats_reset(solb_ctx *ctx) {
     if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    mark_side_barrier(ctx);  // frames launched on the side streams from now on count into the cleared counters
     ctx->launches = 0;
     ctx->trace_kernel_ms_total = 0.0f;
     ctx->trace_kernel_launches = 0;
@@ -648,6 +726,14 @@ SOLB_API int solb_target_readback(solb_target *t, void *host, size_t bytes) {
     return SOLB_OK;
 }
 
+SOLB_API int solb_target_readback_async(solb_target *t, void *host, size_t bytes) {
+    if (!t || !host) return fail(t ? t->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
+    if (bytes != t->bytes) return fail(t->ctx, SOLB_ERR_INVALID, "readback size must equal width*height*texel size");
+    CU(t->ctx, cudaSetDevice(t->ctx->device));
+    CU(t->ctx, cudaMemcpyAsync(host, t->dev, bytes, cudaMemcpyDeviceToHost, t->ctx->stream));
+    return SOLB_OK;
+}
+
 SOLB_API int solb_target_upload(solb_target *t, const void *host, size_t bytes) {
     if (!t || !host) return fail(t ? t->ctx : nullptr, SOLB_ERR_INVALID, "null argument");
     if (bytes != t->bytes) return fail(t->ctx, SOLB_ERR_INVALID, "upload size must equal width*height*texel size");
@@ -776,22 +862,44 @@ static int ensure_wavefront(solb_ctx *ctx, uint32_t n_pixels) {
     return SOLB_OK;
 }
 
-static int ensure_warpfront(solb_ctx *ctx) {
-    WarpfrontState &w = ctx->wl;
+static int ensure_warpfront(solb_ctx *ctx, int k, size_t n_pixels) {
+    WarpfrontState &w = ctx->wl[k];
     const uint32_t n_warps = warpfront_grid_warps(ctx->sm_count, ctx->tune);
-    if (w.n_warps >= n_warps && w.ray_o) return SOLB_OK;
-    free_warpfront(ctx);
-    const size_t n = (size_t)n_warps * WL_POOL;
-    CU(ctx, cudaMalloc((void **)&w.ray_o, n * sizeof(float4)));
-    CU(ctx, cudaMalloc((void **)&w.ray_d, n * sizeof(float4)));
-    CU(ctx, cudaMalloc((void **)&w.ray_i, n * sizeof(float4)));
-    CU(ctx, cudaMalloc((void **)&w.frame0, n * sizeof(float4)));
-    CU(ctx, cudaMalloc((void **)&w.frame1, n * sizeof(float4)));
-    CU(ctx, cudaMalloc((void **)&w.thr, n * sizeof(float4)));
-    CU(ctx, cudaMalloc((void **)&w.pix, n * sizeof(float4)));
-    CU(ctx, cudaMalloc((void **)&w.hit, n * sizeof(uint4)));
-    CU(ctx, cudaMalloc((void **)&w.cursor, sizeof(uint32_t)));
-    w.n_warps = n_warps;
+    if (!ctx->frame_stream[k]) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->frame_stream[k], cudaStreamNonBlocking));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_trace_done[k], cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_resolve_done[k], cudaEventDisableTiming));
+        CU(ctx, cudaEventCreate(&ctx->ev_k0[k]));
+        CU(ctx, cudaEventCreate(&ctx->ev_k1[k]));
+    }
+    if (!ctx->ev_serial) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_serial, cudaEventDisableTiming));
+    if (!(w.n_warps >= n_warps && w.ray_o)) {
+        CU(ctx, cudaStreamSynchronize(ctx->frame_stream[k]));
+        cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.ray_i); cudaFree(w.frame0); cudaFree(w.frame1);
+        cudaFree(w.thr); cudaFree(w.pix); cudaFree(w.hit); cudaFree(w.cursor);
+        w = WarpfrontState{};
+        const size_t n = (size_t)n_warps * WL_POOL;
+        CU(ctx, cudaMalloc((void **)&w.ray_o, n * sizeof(float4)));
+        CU(ctx, cudaMalloc((void **)&w.ray_d, n * sizeof(float4)));
+        CU(ctx, cudaMalloc((void **)&w.ray_i, n * sizeof(float4)));
+        CU(ctx, cudaMalloc((void **)&w.frame0, n * sizeof(float4)));
+        CU(ctx, cudaMalloc((void **)&w.frame1, n * sizeof(float4)));
+        CU(ctx, cudaMalloc((void **)&w.thr, n * sizeof(float4)));
+        CU(ctx, cudaMalloc((void **)&w.pix, n * sizeof(float4)));
+        CU(ctx, cudaMalloc((void **)&w.hit, n * sizeof(uint4)));
+        CU(ctx, cudaMalloc((void **)&w.cursor, sizeof(uint32_t)));
+        w.n_warps = n_warps;
+    }
+    if (ctx->frame_sum_pixels[k] < n_pixels) {
+        // (the previous users of this buffer, a kernel on the side stream and a resolve on the ctx stream, must be done)
+        CU(ctx, cudaStreamSynchronize(ctx->frame_stream[k]));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->frame_sum[k]);
+        ctx->frame_sum[k] = nullptr;
+        ctx->frame_sum_pixels[k] = 0;
+        CU(ctx, cudaMalloc((void **)&ctx->frame_sum[k], n_pixels * sizeof(float4)));
+        ctx->frame_sum_pixels[k] = n_pixels;
+    }
     return SOLB_OK;
 }
 
@@ -832,13 +940,37 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
     if (schedule == SOLB_SCHEDULE_AUTO) schedule = s->accel.n_wide <= 8 ? SOLB_SCHEDULE_MEGAKERNEL : ctx->auto_wide_schedule;
     if (schedule > SOLB_SCHEDULE_WARPFRONT) return fail(ctx, SOLB_ERR_INVALID, "trace: unknown schedule");
     if (schedule == SOLB_SCHEDULE_WARPFRONT) {
-        if ((rc = ensure_warpfront(ctx))) return rc;
-        CU(ctx, launch_pathtrace_warpfront(ctx->stream, fc, s->accel, s->d_inst, s->d_shade, ctx->wl, (float4 *)accum->dev,
-                                           render ? (uint32_t *)render->dev : nullptr, ctx->d_stats, params->collect_stats != 0,
-                                           ctx->sm_count, ctx->tune));
-        ctx->launches += 1;
+        // The kernel runs on a side stream and writes only its own path state and the frame's per-pixel sums; the resolve into
+        // the targets follows on the ctx stream.  The two frame slots alternate, so the kernel of this frame may start while
+        // the previous frame's kernel drains (its last pixels are chains of ~50 rays each: ~9 % of a 1080p frame with the SMs
+        // emptying), and everything later on the ctx stream is ordered after this frame's resolve as before.
+        const int k = (int)(ctx->frame_slot ^= 1u);
+        if ((rc = ensure_warpfront(ctx, k, (size_t)fc.width * fc.height))) return rc;
+        cudaStream_t side = ctx->frame_stream[k];
+        const bool serial = ctx->timing || ctx->tune.wl_frames_in_flight < 2;
+        if (serial) {  // after everything already on the ctx stream (incl. the previous frame's resolve)
+            CU(ctx, cudaEventRecord(ctx->ev_serial, ctx->stream));
+            CU(ctx, cudaStreamWaitEvent(side, ctx->ev_serial, 0));
+        } else {
+            if (ctx->have_side_barrier) CU(ctx, cudaStreamWaitEvent(side, ctx->ev_side_barrier, 0));  // scene / stats changes
+            if (ctx->have_resolve_done[k]) CU(ctx, cudaStreamWaitEvent(side, ctx->ev_resolve_done[k], 0));  // frame_sum[k] consumed
+        }
+        if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev_k0[k], side));
+        CU(ctx, launch_pathtrace_warpfront(side, fc, s->accel, s->d_inst, s->d_shade, ctx->wl[k], ctx->frame_sum[k], ctx->d_stats,
+                                           params->collect_stats != 0, ctx->sm_count, ctx->tune));
+        if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev_k1[k], side));
+        CU(ctx, cudaEventRecord(ctx->ev_trace_done[k], side));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_trace_done[k], 0));
+        CU(ctx, launch_warpfront_resolve(ctx->stream, fc, ctx->frame_sum[k], (float4 *)accum->dev, render ? (uint32_t *)render->dev : nullptr));
+        CU(ctx, cudaEventRecord(ctx->ev_resolve_done[k], ctx->stream));
+        ctx->have_resolve_done[k] = true;
+        ctx->launches += 2;
         timer.stop();
-        if (ctx->timing) { ctx->trace_kernel_ms_total += ctx->last_trace_ms; ctx->trace_kernel_launches += 1; }
+        if (ctx->timing) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ctx->ev_k0[k], ctx->ev_k1[k]) == cudaSuccess) ctx->trace_kernel_ms_total += ms;
+            ctx->trace_kernel_launches += 1;
+        }
         return SOLB_OK;
     }
     if (schedule == SOLB_SCHEDULE_MEGAKERNEL) {

@@ -32,7 +32,17 @@ struct solb_ctx {
     uint32_t blue_w = 0, blue_h = 0;
     uint32_t *pinned_count = nullptr;
     WavefrontState ws = {};
-    WarpfrontState wl = {};  // warp-local wavefront schedule: slot-indexed path state, sized by the persistent grid
+    // warp-local wavefront schedule: slot-indexed path state sized by the persistent grid, and the per-pixel frame sums the
+    // kernel hands to the resolve; two of each plus two side streams, so that the kernel of frame f + 1 can start while frame
+    // f drains (the resolves into the targets stay in order on the ctx stream)
+    WarpfrontState wl[2] = {};
+    float4 *frame_sum[2] = {};
+    size_t frame_sum_pixels[2] = {};
+    cudaStream_t frame_stream[2] = {};
+    cudaEvent_t ev_trace_done[2] = {}, ev_resolve_done[2] = {}, ev_side_barrier = nullptr, ev_serial = nullptr;
+    cudaEvent_t ev_k0[2] = {}, ev_k1[2] = {};  // timing mode: around the kernel on its side stream
+    bool have_resolve_done[2] = { false, false }, have_side_barrier = false;
+    uint32_t frame_slot = 0;
     // queues + counters + streams of the extra frame parts (overlap mode); index 0 unused (= ws / stream)
     uint32_t *part_queue[WF_MAX_PARTS][2] = {};
     uint32_t *part_counters[WF_MAX_PARTS] = {};
@@ -93,6 +103,12 @@ struct solb_target {
     uint32_t width = 0, height = 0, format = 0;
     void *dev = nullptr;
     size_t bytes = 0;
+};
+
+struct solb_fence {
+    solb_ctx *ctx = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool armed = false;  // false: created signalled, nothing to wait for
 };
 
 static inline int fail(solb_ctx *ctx, int code, const std::string &msg) {

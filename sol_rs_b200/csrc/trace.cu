@@ -12,6 +12,15 @@
 namespace solb {
 
 constexpr int TRACE_BLOCK = 128;
+// threads per CTA of the warp-local wavefront kernel.  Its warps never talk to each other, so the CTA is only the unit in
+// which the SM hands out and takes back warp slots: with frames in flight a CTA of the next frame starts when ALL warps of a
+// CTA of the draining frame have finished.  One warp per CTA: 4 516 Mrays/s on the headline against 4 415 with two and 4 403 with
+// four warps per CTA, and 4 221 against 4 148 without frames in flight (profiles/r02_frames_in_flight.txt).
+#ifndef SOLB_WL_BLOCK
+#define SOLB_WL_BLOCK 32
+#endif
+constexpr int WL_BLOCK = SOLB_WL_BLOCK;
+static_assert(WL_BLOCK % 32 == 0 && WL_BLOCK >= 32 && WL_BLOCK <= TRACE_BLOCK && TRACE_BLOCK % WL_BLOCK == 0, "SOLB_WL_BLOCK");
 
 // Traversal stack: SOLB_SM_STACK entries per lane in shared memory ([entry][thread] so a warp's
 // accesses are conflict-free), the rest spills to local memory.
@@ -19,29 +28,32 @@ constexpr int TRACE_BLOCK = 128;
 // every push and pop rebuilt the window base from special registers (S2R tid, S2R cga id, MOV, 2 x LEA) - 12 to 17
 // instructions per stack operation, three operations per iteration of the traversal loop
 // (profiles/r02_ncu_k_pt_warpfront_d.txt).
-struct DevStack {
-    uint32_t sm;  // shared-space byte address of this lane's column; entry e at sm + e * TRACE_BLOCK * 8
+template <int BLOCK>
+struct DevStackT {
+    uint32_t sm;  // shared-space byte address of this lane's column; entry e at sm + e * BLOCK * 8
     uint2 *loc;   // spill array (local memory); kept OUTSIDE the struct so sp / sm stay in registers
     int sp;
     __device__ __forceinline__ void push(uint2 v) {
-        if (sp < SOLB_SM_STACK) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sm + (uint32_t)sp * (TRACE_BLOCK * 8u)), "r"(v.x), "r"(v.y) : "memory");
+        if (sp < SOLB_SM_STACK) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sm + (uint32_t)sp * (BLOCK * 8u)), "r"(v.x), "r"(v.y) : "memory");
         else loc[sp - SOLB_SM_STACK] = v;
         sp++;
     }
     __device__ __forceinline__ uint2 pop() {
         sp--;
         uint2 v;
-        if (sp < SOLB_SM_STACK) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sm + (uint32_t)sp * (TRACE_BLOCK * 8u)) : "memory");
+        if (sp < SOLB_SM_STACK) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sm + (uint32_t)sp * (BLOCK * 8u)) : "memory");
         else v = loc[sp - SOLB_SM_STACK];
         return v;
     }
     __device__ __forceinline__ bool empty() const { return sp == 0; }
 };
+using DevStack = DevStackT<TRACE_BLOCK>;
 
-#define SOLB_DECL_STACK()                                                      \
-    __shared__ uint2 s_stack[SOLB_SM_STACK * TRACE_BLOCK];                     \
+#define SOLB_DECL_STACK() SOLB_DECL_STACK_N(TRACE_BLOCK)
+#define SOLB_DECL_STACK_N(BLOCK)                                               \
+    __shared__ uint2 s_stack[SOLB_SM_STACK * (BLOCK)];                         \
     uint2 stack_spill[SOLB_LOCAL_STACK];                                       \
-    DevStack stack;                                                            \
+    DevStackT<(BLOCK)> stack;                                                  \
     stack.sm = (uint32_t)__cvta_generic_to_shared(s_stack + threadIdx.x);      \
     stack.loc = stack_spill;                                                   \
     stack.sp = 0
@@ -1088,8 +1100,8 @@ __device__ __forceinline__ uint32_t wl_generate_step(const FrameConsts *fcp, con
 
 // Shade step: up to 32 finished rays, one per lane (k_wf_shade + k_wf_resolve).
 __device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const DeviceInstance *__restrict__ instances,
-                                               const ShadeRecord *__restrict__ shade, const WarpfrontState *wlp, float4 *accum,
-                                               uint32_t *render, WlWarp *W, uint32_t slot_base, uint32_t counts, uint32_t *ctr) {
+                                               const ShadeRecord *__restrict__ shade, const WarpfrontState *wlp, float4 *frame_sum,
+                                               WlWarp *W, uint32_t slot_base, uint32_t counts, uint32_t *ctr) {
     const FrameConsts &fc = *fcp;
     const WarpfrontState &wl = *wlp;
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
@@ -1142,10 +1154,9 @@ __device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const 
             } else {
                 alive = false;
                 freed = true;
-                uint32_t rgba;  // pathtrace.rgen:88-103
-                const float4 out = resolve_pixel(fc, pixel, accum[p], rgba);
-                accum[p] = out;
-                if (render) render[p] = rgba;
+                // the sum of the pixel's samples; pathtrace.rgen:88-103 (mean, running mix, gamma) runs in k_wf_resolve on the ctx
+                // stream, so that this kernel touches neither target and consecutive frames can overlap (launch wrapper)
+                wl_st(frame_sum + p, make_float4(pixel.x, pixel.y, pixel.z, __uint_as_float(rng)));
             }
         }
         if (alive) {
@@ -1174,23 +1185,23 @@ __device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const 
 //   s_hit   : the hit record (instance, triangle, u, v): written when a triangle test is accepted, read when the ray finishes
 //   s_frame : the ray-space frame of the watertight test (6 floats): written at refill, read by the triangle step
 template <bool STATS, bool TL>
-__global__ void __launch_bounds__(TRACE_BLOCK, TL ? 7 : SOLB_WF_MIN_CTAS)
+__global__ void __launch_bounds__(WL_BLOCK, (TL ? 7 : SOLB_WF_MIN_CTAS) * (TRACE_BLOCK / WL_BLOCK))
 k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
                const float4 *__restrict__ inst_leaves, const DeviceInstance *__restrict__ instances,
-               const ShadeRecord *__restrict__ shade, const __grid_constant__ WarpfrontState wl, float4 *accum, uint32_t *render,
+               const ShadeRecord *__restrict__ shade, const __grid_constant__ WarpfrontState wl, float4 *frame_sum,
                unsigned long long *stats, const uint32_t n_region_slots, const uint32_t pool_limit,
                const __grid_constant__ TraceTuning tune) {
-    SOLB_DECL_STACK();
+    SOLB_DECL_STACK_N(WL_BLOCK);
     // opaque to the optimiser: otherwise ptxas re-derives the column address from tid / the shared window base at every push and
     // pop (2 x S2R + MOV + LEA + IMAD) instead of keeping the register (k_wf_trace, with less room, is better off re-deriving)
     asm volatile("" : "+r"(stack.sm));
-    __shared__ WlWarp s_warp[TRACE_BLOCK / 32];
-    __shared__ uint4 s_hit[TRACE_BLOCK];
-    __shared__ float4 s_frame0[TRACE_BLOCK];  // e1.xyz, e2.x
-    __shared__ float2 s_frame1[TRACE_BLOCK];  // e2.yz
+    __shared__ WlWarp s_warp[WL_BLOCK / 32];
+    __shared__ uint4 s_hit[WL_BLOCK];
+    __shared__ float4 s_frame0[WL_BLOCK];  // e1.xyz, e2.x
+    __shared__ float2 s_frame1[WL_BLOCK];  // e2.yz
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
     WlWarp *const W = &s_warp[tid >> 5];
-    const uint32_t slot_base = (blockIdx.x * (TRACE_BLOCK / 32) + (tid >> 5)) * (uint32_t)WL_POOL;  // < 2^32
+    const uint32_t slot_base = (blockIdx.x * (WL_BLOCK / 32) + (tid >> 5)) * (uint32_t)WL_POOL;  // < 2^32
     if (slot_base >= wl.n_warps * (uint32_t)WL_POOL) return;
     // pool_limit <= WL_POOL slots are used: small regions (a rank's share of a tile-split frame, small images) are shared out
     // evenly over the warps instead of the first warps claiming WL_POOL pixels each and the rest finding the cursor exhausted
@@ -1252,7 +1263,7 @@ k_pt_warpfront(const __grid_constant__ FrameConsts fc, const uint4 *__restrict__
                 if (want_gen) counts = wl_generate_step(&fc, &wl, W, slot_base, counts, n_region_slots, (uint32_t)tune.wl_batch, step_ctr);
                 // (re-evaluated: the generate step may have refilled the ready list)
                 if (WL_N_SHADE(counts) >= 32u || (WL_N_SHADE(counts) > 0u && WL_N_READY(counts) == 0u && starving))
-                    counts = wl_shade_step(&fc, instances, shade, &wl, accum, render, W, slot_base, counts, step_ctr);
+                    counts = wl_shade_step(&fc, instances, shade, &wl, frame_sum, W, slot_base, counts, step_ctr);
                 tr.o = f3(u2f(park[0]), u2f(park[1]), u2f(park[2]));
                 tr.d = f3(u2f(park[3]), u2f(park[4]), u2f(park[5]));
                 tr.idir = f3(u2f(park[6]), u2f(park[7]), u2f(park[8]));
@@ -1724,9 +1735,10 @@ uint32_t warpfront_grid_warps(int sm_count, const TraceTuning &tune) {
     return (uint32_t)(sm_count * tune.wl_ctas_per_sm * (TRACE_BLOCK / 32));
 }
 
-// One reference frame with the warp-local wavefront schedule: a cursor reset and ONE launch.
+// One reference frame with the warp-local wavefront schedule: a cursor reset and ONE launch on `st` (a side stream of the ctx:
+// the kernel writes only its own path state and frame_sum, the per-pixel sums of the frame's samples) ...
 cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
-                                       const ShadeRecord *shade, const WarpfrontState &wl, float4 *accum, uint32_t *render,
+                                       const ShadeRecord *shade, const WarpfrontState &wl, float4 *frame_sum,
                                        unsigned long long *stats, bool collect, int sm_count, const TraceTuning &tune) {
     if (fc.width == 0 || fc.band_rows == 0 || fc.n_bands == 0) return cudaSuccess;
     const uint32_t n_slots = ((fc.width + 7u) >> 3) * region_tiles_y(fc) * 32u;
@@ -1737,15 +1749,25 @@ cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, c
     // holding 56 pixels (1/8 of a 1080p frame over 8 CTAs per SM) the shade steps ran partial and the share took 6.2 ms, with
     // 6 CTAs per SM (72 slots each) 4.9 ms (tools/tile_time.py, profiles/r02_tile_split.txt).
     const uint32_t want_warps = std::min<uint32_t>(std::min(warpfront_grid_warps(sm_count, tune), wl.n_warps), std::max<uint32_t>(1u, n_slots / 72u));
-    const uint32_t grid = (want_warps + TRACE_BLOCK / 32 - 1) / (TRACE_BLOCK / 32);
+    const uint32_t grid = (want_warps + WL_BLOCK / 32 - 1) / (WL_BLOCK / 32);
     // pixels a warp holds at a time: its even share of the region, between one warp-width and the full pool
     const uint32_t share = (n_slots + want_warps - 1) / want_warps;
     const uint32_t pool_limit = std::min<uint32_t>((uint32_t)WL_POOL, std::max<uint32_t>(32u, (share + 7u) & ~7u));
     const float4 *il = as.inst_leaves_f4();
-#define SOLB_WLF(S, T) k_pt_warpfront<S, T><<<grid, TRACE_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, wl, accum, render, stats, n_slots, pool_limit, tune)
+#define SOLB_WLF(S, T) k_pt_warpfront<S, T><<<grid, WL_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, wl, frame_sum, stats, n_slots, pool_limit, tune)
     if (as.two_level) { if (collect) SOLB_WLF(true, true); else SOLB_WLF(false, true); }
     else { if (collect) SOLB_WLF(true, false); else SOLB_WLF(false, false); }
 #undef SOLB_WLF
+    return cudaGetLastError();
+}
+
+// ... and its resolve on the ctx stream: pathtrace.rgen:88-103 per pixel of the launch region (k_wf_resolve reads pix[p].xyz).
+cudaError_t launch_warpfront_resolve(cudaStream_t st, const FrameConsts &fc, float4 *frame_sum, float4 *accum, uint32_t *render) {
+    if (fc.width == 0 || fc.band_rows == 0 || fc.n_bands == 0) return cudaSuccess;
+    const uint32_t n_slots = ((fc.width + 7u) >> 3) * region_tiles_y(fc) * 32u;
+    WavefrontState ws = {};
+    ws.pix = frame_sum;
+    k_wf_resolve<<<(n_slots + 255) / 256, 256, 0, st>>>(fc, ws, accum, render, 0u, n_slots);
     return cudaGetLastError();
 }
 

@@ -63,6 +63,8 @@ struct TraceTuning {
     int wl_fetch_idle = 16;    // hand ready rays to idle lanes once this many lanes are idle (8: 3 556, 12: 3 618, 16: 3 645 Mrays/s)
     int wl_starve_idle = 16;   // partial (< 32 slots) shade / generate steps only once this many lanes are idle and nothing is ready
     int wl_gen_min = 32;       // start new pixels once this many of a warp's slots are free (or its lanes starve): a full-width generate step
+    int wl_frames_in_flight = 2;  // 2: the kernel of frame f + 1 starts while frame f drains (they share nothing: each writes its
+                                  // own path state and frame sums, the resolves into the targets run in order on the ctx stream); 1: serial
     int wl_batch = 32;         // pixels a warp takes from the frame's cursor per atomic (one 8x4 tile)
 };
 
@@ -117,8 +119,9 @@ cudaError_t launch_ao(cudaStream_t st, const FrameConsts &fc, const AccelStorage
                       const ShadeRecord *shade, const uint32_t *blue, uint32_t bw, uint32_t bh, float4 *image,
                       unsigned long long *stats, const TraceTuning &tune);
 cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, const AccelStorage &as, const DeviceInstance *instances,
-                                       const ShadeRecord *shade, const WarpfrontState &wl, float4 *accum, uint32_t *render,
+                                       const ShadeRecord *shade, const WarpfrontState &wl, float4 *frame_sum,
                                        unsigned long long *stats, bool collect, int sm_count, const TraceTuning &tune);
+cudaError_t launch_warpfront_resolve(cudaStream_t st, const FrameConsts &fc, float4 *frame_sum, float4 *accum, uint32_t *render);
 uint32_t warpfront_grid_warps(int sm_count, const TraceTuning &tune);
 size_t pool_spill_bytes(int sm_count, const TraceTuning &tune);
 cudaError_t launch_resolve_sum(cudaStream_t st, const float4 *sum, float4 *accum_out, uint32_t *render, uint32_t n);

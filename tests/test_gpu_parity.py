@@ -1229,3 +1229,47 @@ def test_ploc_builder_invariants_and_hits(sol, ctx, name, synth27):
     o_hits, o_t, flags = osc.trace_rays(rays, classify=True)
     mism = np.any(g_hits[:, :2] != o_hits[:, :2], axis=1)
     assert (mism & (flags == 0)).sum() == 0
+
+
+def test_frames_in_flight_fences_and_async_readback(sol, ctx):
+    """A render loop with two frames in flight (src/renderer.rs:72-81, 123-131, 188, 310-317 per-slot fences; the blit of
+    examples/5-pathtrace.rs:360-361 as a queued copy): every frame's asynchronous read-back, collected after its fence, holds
+    exactly what the blocking read-back of the same frame holds in a loop that waits after every frame."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    w, h, frames = 640, 360, 6
+    sc, sd = _product(sol, ctx, "tunnel")
+    cam = product_camera(sc, "tunnel", w, h)
+    sbt = pathtrace_pipeline(ctx, True)
+
+    def bindings(accum, rend, f):
+        return ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, rend, samples_per_frame=4, max_bounces=8,
+                                 schedule=N.SCHEDULE_WARPFRONT)
+
+    accum, rend = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F), sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+    blocking = []
+    for f in range(frames):
+        sbt.cmd_trace_rays(bindings(accum, rend, f), (w, h, 1))
+        blocking.append(rend.readback().copy())
+    assert any(not np.array_equal(blocking[0], b) for b in blocking[1:])
+
+    accum2, rend2 = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F), sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+    slots = [ctx.host_alloc((h, w, 4), np.uint8) for _ in range(2)]
+    fences = [ctx.fence() for _ in range(2)]
+    fences[0].wait()  # a new fence is signalled: nothing to wait for
+    got = []
+    for f in range(frames):
+        k = f & 1
+        if f >= 2:
+            fences[k].wait()
+            got.append(slots[k].copy())  # frame f-2, complete once its fence has been waited for
+        sbt.cmd_trace_rays(bindings(accum2, rend2, f), (w, h, 1))
+        rend2.readback_async(slots[k])
+        fences[k].signal()
+    for f in range(frames - 2, frames):
+        fences[f & 1].wait()
+        got.append(slots[f & 1].copy())
+    for f in range(frames):
+        assert np.array_equal(got[f], blocking[f]), f
+    assert np.array_equal(accum.readback(), accum2.readback())

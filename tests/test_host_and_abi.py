@@ -292,7 +292,7 @@ def test_rust_crate_binds_every_declared_symbol_with_matching_arity():
     # every `crate::x` path in the sources names a module of the crate or an item re-exported at its root
     for f in os.listdir(rust):
         for m in re.findall(r"crate::(\w+)", open(os.path.join(rust, f)).read()):
-            assert m in mods or m in ("Context", "Image2d", "SceneUniforms"), (f, m)
+            assert m in mods or m in ("Context", "Image2d", "SceneUniforms", "HostBuffer", "Fence"), (f, m)
 
 
 def test_loaders_handle_snorm_zero_filled_and_percent_encoded_uris(tmp_path):
