@@ -250,7 +250,9 @@ def main():
         torch.cuda.synchronize()
 
     def device_timed(sd, cam, sbt, schedule, n_warm, n_steps, split, frame0, w=None, h=None, mb=None, trace_fn=None):
-        """K steps with inputs resident in HBM; per-step CUDA events on the launching stream; L2 flushed between steps.
+        """K steps with inputs resident in HBM; CUDA events on the launching stream; L2 flushed between steps.  The clock is
+        ONE interval from before the first step to after the last (steps overlap when the schedule keeps frames in flight, so
+        per-step intervals would leave the work done during the flushes uncounted); the flushes are inside it.
         split: None (this GPU alone), "frames" (f = r mod N + one reduce + resolve at the end) or "tiles" (bands + all-gather)."""
         w, h, mb = w or WIDTH, h or HEIGHT, MAX_BOUNCES if mb is None else mb
         cam.set_window_size((w, h))
@@ -272,7 +274,8 @@ def main():
                 sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, render, schedule=schedule,
                                                      samples_per_frame=SPP, max_bounces=mb, accum_mode=mode, tile_rows=tile), (w, h, 1))
             if tile:
-                comm.allgather_rows(accum, BAND)  # every rank now holds the whole frame
+                comm.allgather_rows(render, BAND)  # every rank now holds the whole displayable frame (what the reference presents);
+                # the float accumulation stays distributed, every rank owning its bands, and is gathered once at the end
 
         for f in frames[:n_warm]:
             one(f)
@@ -282,11 +285,14 @@ def main():
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps + 1)]
         t_wall = time.perf_counter()
         for i, f in enumerate(frames[n_warm:]):
-            l2_flush.fill_(i & 0xFF)  # > 126 MB L2, outside the per-step event pair
+            l2_flush.fill_(i & 0xFF)  # > 126 MB L2
             evs[i][0].record(stream)
             one(f)
             evs[i][1].record(stream)
         reduce_ms = 0.0
+        if tile:
+            comm.allgather_rows(accum, BAND)
+            evs[n_steps - 1][1].record(stream)  # (re-recorded: the closing gather of the accumulation is inside the clock)
         if split == "frames" and world > 1:
             # the one real exchange of the path: sum the per-rank accumulation buffers over NVLink, resolve on rank 0
             evs[n_steps][0].record(stream)
@@ -295,10 +301,12 @@ def main():
         barrier_sync()
         wall = time.perf_counter() - t_wall
         step_ms = [a.elapsed_time(b) for a, b in evs[:n_steps]]
+        last = evs[n_steps - 1][1]
         if split == "frames" and world > 1:
             reduce_ms = evs[n_steps][0].elapsed_time(evs[n_steps][1])
+            last = evs[n_steps][1]
         st = ctx.stats()
-        return {"ms_total": sum(step_ms) + reduce_ms, "step_ms": step_ms, "reduce_ms": reduce_ms, "rays": int(st.rays),
+        return {"ms_total": evs[0][0].elapsed_time(last), "step_ms": step_ms, "reduce_ms": reduce_ms, "rays": int(st.rays),
                 "paths": int(st.paths), "hits": int(st.hits), "launches": int(st.kernel_launches), "wall_s": wall}
 
     def gather_max_sum(ms_total, rays):
@@ -433,14 +441,14 @@ def main():
     # ---- N > 1: the hard case of SURVEY 8e beside the frames split: ONE frame cut across the GPUs (interleaved 8-row bands,
     #      one all-gather per frame), against the same frame traced by one GPU alone in the same run ----
     if world > 1 and not tiled and not args.no_extra:
-        n_t = min(steps, 8)
+        n_t = 32  # short frames: enough of them that the fill and drain of the frame pipeline are a small part of the clock
         alone = device_timed(sd, cam, sbt, sched, 2, n_t, None, 300)       # every rank traces whole frames on its own
         tiles = device_timed(sd, cam, sbt, sched, 2, n_t, "tiles", 300)
         t_ms, _ = gather_max_sum(tiles["ms_total"], 0)
         a_ms, _ = gather_max_sum(alone["ms_total"], 0)
         extra["tile_split"] = {"ms_per_frame": t_ms / n_t, "single_gpu_ms_per_frame": a_ms / n_t, "speedup_vs_1gpu": a_ms / t_ms,
                                "frames": n_t, "band_rows": BAND,
-                               "what": "one frame cut into interleaved %d-row bands over %d GPUs, solb_allgather_rows (pack + ncclAllGather + scatter) per frame inside the timed region; max over ranks" % (BAND, world)}
+                               "what": "one frame cut into interleaved %d-row bands over %d GPUs, solb_allgather_rows (pack + ncclAllGather + scatter) of the rgba8 frame per frame and of the float accumulation once at the end, all inside the timed region; max over ranks" % (BAND, world)}
 
     if rank == 0:
         wkey = "tunnel_%dx%d" % (WIDTH, HEIGHT) if args.workload == "tunnel" else "synth_%d" % args.blas
@@ -527,10 +535,11 @@ def main():
                  "dtype": "f32", "data": "synthetic",
                  "config": {"workload": workload, "schedule": sched_names[resolved_schedule(sd, sched)], "accel": args.accel, "bvh_build_ms": build_ms, "bvh_rebuild_ms": min(rebuilds),
                             "frames_per_rank": steps, "rays_per_frame": rays_total / (steps * (1 if tiled else world)),
-                            "l2": "256 MB buffer written between timed steps (outside the per-step event pairs)",
+                            "l2": "256 MB buffer written between timed steps; the clock is one CUDA-event interval over all K steps, flushes included",
+                            "frames_in_flight": int(os.environ.get("SOLB_WL_FRAMES_IN_FLIGHT", 3)) if sched_names[resolved_schedule(sd, sched)] == "warpfront" else 1,
                             "tlas": "solb_tlas_regenerate is called every frame like the reference (examples/5-pathtrace.rs:316) and is a no-op while no transform changed; "
                                     "a forced full rebuild of this scene costs bvh_build_ms",
-                            "multi_gpu": ("every frame cut into 8-row bands dealt round-robin to the N ranks, one solb_allgather_rows (NCCL) per frame inside the timed region"
+                            "multi_gpu": ("every frame cut into 8-row bands dealt round-robin to the N ranks, one solb_allgather_rows (NCCL) of the rgba8 frame per frame + one of the accumulation at the end, inside the timed region"
                                           if tiled else
                                           "frames f = rank (mod N) per rank, local sums, one solb_reduce_accum (NCCL reduce + resolve on rank 0) inside the timed region")
                             if world > 1 else "single GPU"},

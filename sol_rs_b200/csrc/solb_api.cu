@@ -91,7 +91,9 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.wl_starve_idle = env_int("SOLB_WL_STARVE_IDLE", c->tune.wl_starve_idle, 1, 32);
         c->tune.wl_gen_min = env_int("SOLB_WL_GEN_MIN", c->tune.wl_gen_min, 1, WL_POOL);
         c->tune.wl_batch = env_int("SOLB_WL_BATCH", c->tune.wl_batch, 32, 1024) & ~31;
-        c->tune.wl_frames_in_flight = env_int("SOLB_WL_FRAMES_IN_FLIGHT", c->tune.wl_frames_in_flight, 1, 2);
+        c->tune.wl_warps_per_sm = env_int("SOLB_WL_WARPS_PER_SM", c->tune.wl_warps_per_sm, 0, 64);
+        c->use_hi_stream = env_int("SOLB_HI_STREAM", 1, 0, 1);
+        c->tune.wl_frames_in_flight = env_int("SOLB_WL_FRAMES_IN_FLIGHT", c->tune.wl_frames_in_flight, 1, WL_MAX_FRAMES);
     }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
@@ -117,7 +119,7 @@ static void free_wavefront(solb_ctx *c) {
 }
 
 static void free_warpfront(solb_ctx *c) {
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < WL_MAX_FRAMES; k++) {
         if (c->frame_stream[k]) cudaStreamSynchronize(c->frame_stream[k]);
         WarpfrontState &w = c->wl[k];
         cudaFree(w.ray_o); cudaFree(w.ray_d); cudaFree(w.ray_i); cudaFree(w.frame0); cudaFree(w.frame1);
@@ -132,6 +134,10 @@ static void free_warpfront(solb_ctx *c) {
         for (cudaEvent_t *e : evs) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
         c->have_resolve_done[k] = false;
     }
+    if (c->hi_stream) { cudaStreamSynchronize(c->hi_stream); cudaStreamDestroy(c->hi_stream); c->hi_stream = nullptr; }
+    if (c->ev_hi_in) cudaEventDestroy(c->ev_hi_in);
+    if (c->ev_hi_out) cudaEventDestroy(c->ev_hi_out);
+    c->ev_hi_in = c->ev_hi_out = nullptr;
     if (c->ev_side_barrier) cudaEventDestroy(c->ev_side_barrier);
     if (c->ev_serial) cudaEventDestroy(c->ev_serial);
     c->ev_side_barrier = c->ev_serial = nullptr;
@@ -944,7 +950,7 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
         // the targets follows on the ctx stream.  The two frame slots alternate, so the kernel of this frame may start while
         // the previous frame's kernel drains (its last pixels are chains of ~50 rays each: ~9 % of a 1080p frame with the SMs
         // emptying), and everything later on the ctx stream is ordered after this frame's resolve as before.
-        const int k = (int)(ctx->frame_slot ^= 1u);
+        const int k = (int)(ctx->frame_slot = (ctx->frame_slot + 1u) % (uint32_t)std::max(ctx->tune.wl_frames_in_flight, 1));
         if ((rc = ensure_warpfront(ctx, k, (size_t)fc.width * fc.height))) return rc;
         cudaStream_t side = ctx->frame_stream[k];
         const bool serial = ctx->timing || ctx->tune.wl_frames_in_flight < 2;
@@ -960,9 +966,12 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
                                            params->collect_stats != 0, ctx->sm_count, ctx->tune));
         if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev_k1[k], side));
         CU(ctx, cudaEventRecord(ctx->ev_trace_done[k], side));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_trace_done[k], 0));
-        CU(ctx, launch_warpfront_resolve(ctx->stream, fc, ctx->frame_sum[k], (float4 *)accum->dev, render ? (uint32_t *)render->dev : nullptr));
-        CU(ctx, cudaEventRecord(ctx->ev_resolve_done[k], ctx->stream));
+        cudaStream_t rs;
+        CU(ctx, hi_begin(ctx, &rs));
+        CU(ctx, cudaStreamWaitEvent(rs, ctx->ev_trace_done[k], 0));
+        CU(ctx, launch_warpfront_resolve(rs, fc, ctx->frame_sum[k], (float4 *)accum->dev, render ? (uint32_t *)render->dev : nullptr));
+        CU(ctx, cudaEventRecord(ctx->ev_resolve_done[k], rs));
+        CU(ctx, hi_end(ctx));
         ctx->have_resolve_done[k] = true;
         ctx->launches += 2;
         timer.stop();

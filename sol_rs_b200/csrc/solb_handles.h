@@ -35,14 +35,19 @@ struct solb_ctx {
     // warp-local wavefront schedule: slot-indexed path state sized by the persistent grid, and the per-pixel frame sums the
     // kernel hands to the resolve; two of each plus two side streams, so that the kernel of frame f + 1 can start while frame
     // f drains (the resolves into the targets stay in order on the ctx stream)
-    WarpfrontState wl[2] = {};
-    float4 *frame_sum[2] = {};
-    size_t frame_sum_pixels[2] = {};
-    cudaStream_t frame_stream[2] = {};
-    cudaEvent_t ev_trace_done[2] = {}, ev_resolve_done[2] = {}, ev_side_barrier = nullptr, ev_serial = nullptr;
-    cudaEvent_t ev_k0[2] = {}, ev_k1[2] = {};  // timing mode: around the kernel on its side stream
-    bool have_resolve_done[2] = { false, false }, have_side_barrier = false;
+    WarpfrontState wl[WL_MAX_FRAMES] = {};
+    float4 *frame_sum[WL_MAX_FRAMES] = {};
+    size_t frame_sum_pixels[WL_MAX_FRAMES] = {};
+    cudaStream_t frame_stream[WL_MAX_FRAMES] = {};
+    cudaEvent_t ev_trace_done[WL_MAX_FRAMES] = {}, ev_resolve_done[WL_MAX_FRAMES] = {}, ev_side_barrier = nullptr, ev_serial = nullptr;
+    cudaEvent_t ev_k0[WL_MAX_FRAMES] = {}, ev_k1[WL_MAX_FRAMES] = {};  // timing mode: around the kernel on its side stream
+    bool have_resolve_done[WL_MAX_FRAMES] = {}, have_side_barrier = false;
     uint32_t frame_slot = 0;
+    // greatest-priority stream for the short kernels that follow a frame (resolve, band pack / all-gather / scatter): the
+    // persistent trace kernels of the frames in flight fill every SM, and a kernel of their priority waits for a whole drain
+    cudaStream_t hi_stream = nullptr;
+    cudaEvent_t ev_hi_in = nullptr, ev_hi_out = nullptr;
+    int use_hi_stream = 1;
     // queues + counters + streams of the extra frame parts (overlap mode); index 0 unused (= ws / stream)
     uint32_t *part_queue[WF_MAX_PARTS][2] = {};
     uint32_t *part_counters[WF_MAX_PARTS] = {};
@@ -61,6 +66,18 @@ struct solb_ctx {
     int comm_rank = 0, comm_world = 1;
     void *comm_stage = nullptr;
     size_t comm_stage_bytes = 0;
+    // peer-to-peer band exchange (comm.cu): every rank's staging block is mapped into every other rank (CUDA IPC), a rank
+    // stores its bands straight into its peers' blocks over NVLink and raises a flag there
+    static constexpr int P2P_MAX_RANKS = 16;
+    static constexpr size_t P2P_HEADER_BYTES = 4096;  // flags[P2P_MAX_RANKS] at the start of the block, data behind
+    int p2p_state = 0;             // 0: not tried yet, 1: in use, -1: unavailable (NCCL all-gather instead)
+    void *p2p_block = nullptr;     // this rank's block: header + 2 x world x chunk (double-buffered by frame parity)
+    size_t p2p_chunk_bytes = 0;
+    void *p2p_peer[P2P_MAX_RANKS] = {};
+    unsigned long long *p2p_counter = nullptr;
+    uint32_t p2p_seq = 0;
+    unsigned long long p2p_ctas = 0;  // CTAs of all pushes so far (what p2p_counter reaches when the latest push is complete)
+    int *p2p_err_host = nullptr, *p2p_err_dev = nullptr;  // mapped page-locked: a wait that timed out
     int refs = 1;  // the ctx handle itself + every live scene / target: resources are freed when the last one goes
 };
 
@@ -104,6 +121,31 @@ struct solb_target {
     void *dev = nullptr;
     size_t bytes = 0;
 };
+
+// hi_begin: *out = the stream to launch on, ordered after everything enqueued on the ctx stream so far; hi_end: the ctx stream
+// continues after what was launched in between.  (use_hi_stream = 0: the ctx stream itself.)
+static inline cudaError_t hi_begin(solb_ctx *c, cudaStream_t *out) {
+    *out = c->stream;
+    if (!c->use_hi_stream) return cudaSuccess;
+    cudaError_t e;
+    if (!c->hi_stream) {
+        int least = 0, greatest = 0;
+        if ((e = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithPriority(&c->hi_stream, cudaStreamNonBlocking, greatest)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&c->ev_hi_in, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&c->ev_hi_out, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if ((e = cudaEventRecord(c->ev_hi_in, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(c->hi_stream, c->ev_hi_in, 0)) != cudaSuccess) return e;
+    *out = c->hi_stream;
+    return cudaSuccess;
+}
+static inline cudaError_t hi_end(solb_ctx *c) {
+    if (!c->use_hi_stream || !c->hi_stream) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaEventRecord(c->ev_hi_out, c->hi_stream)) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(c->stream, c->ev_hi_out, 0);
+}
 
 struct solb_fence {
     solb_ctx *ctx = nullptr;

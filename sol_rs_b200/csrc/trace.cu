@@ -1732,7 +1732,7 @@ cudaError_t launch_pathtrace_wavefront(const WavefrontLaunch &L, const FrameCons
 }
 
 uint32_t warpfront_grid_warps(int sm_count, const TraceTuning &tune) {
-    return (uint32_t)(sm_count * tune.wl_ctas_per_sm * (TRACE_BLOCK / 32));
+    return (uint32_t)(sm_count * (tune.wl_warps_per_sm > 0 ? tune.wl_warps_per_sm : tune.wl_ctas_per_sm * (TRACE_BLOCK / 32)));
 }
 
 // One reference frame with the warp-local wavefront schedule: a cursor reset and ONE launch on `st` (a side stream of the ctx:

@@ -59,12 +59,15 @@ struct TraceTuning {
     int mega_ctas_per_sm = 6;  // its persistent CTAs per SM (80 registers -> 6 x 128 threads)
     int mega_fetch_idle = 8;   // refill finished lanes once this many are idle
     // warp-local wavefront schedule (k_pt_warpfront)
-    int wl_ctas_per_sm = 8;    // persistent CTAs per SM (64 registers -> 8 x 128 threads)
+    int wl_ctas_per_sm = 8;    // persistent warps per SM in units of four (64 registers -> 8 x 128 threads)
+    int wl_warps_per_sm = 0;   // > 0: persistent warps per SM, overrides wl_ctas_per_sm (one warp per CTA since round 2)
     int wl_fetch_idle = 16;    // hand ready rays to idle lanes once this many lanes are idle (8: 3 556, 12: 3 618, 16: 3 645 Mrays/s)
     int wl_starve_idle = 16;   // partial (< 32 slots) shade / generate steps only once this many lanes are idle and nothing is ready
     int wl_gen_min = 32;       // start new pixels once this many of a warp's slots are free (or its lanes starve): a full-width generate step
-    int wl_frames_in_flight = 2;  // 2: the kernel of frame f + 1 starts while frame f drains (they share nothing: each writes its
-                                  // own path state and frame sums, the resolves into the targets run in order on the ctx stream); 1: serial
+    int wl_frames_in_flight = 3;  // > 1: the kernel of frame f + 1 starts while frame f drains (they share nothing: each writes its
+                                  // own path state and frame sums, the resolves into the targets run in order on the ctx stream); 1: serial.
+                                  // Full 1080p frames: 2 and 3 give the same 4 484 Mrays/s; a rank's 1/8 share of a tile-split frame
+                                  // takes 4.70 / 3.43 / 3.32 ms with 1 / 2 / 3 (profiles/r02_frames_in_flight.txt)
     int wl_batch = 32;         // pixels a warp takes from the frame's cursor per atomic (one 8x4 tile)
 };
 
@@ -75,6 +78,7 @@ struct TraceTuning {
 #define SOLB_WL_POOL 96
 #endif
 constexpr int WL_POOL = SOLB_WL_POOL;
+constexpr int WL_MAX_FRAMES = 3;  // frame slots a ctx keeps (path state + frame sums + side stream each)
 struct WarpfrontState {
     float4 *ray_o;      // xyz origin of the ray in flight, w = bits(pixel id)
     float4 *ray_d;      // xyz direction

@@ -64,7 +64,8 @@ def test_world_one_reduce_is_the_resolve_and_gather_is_a_noop():
     ctx.close()
 
 
-def _rank_main(rank, world, id_path, out_dir):
+def _rank_main(rank, world, id_path, out_dir, p2p):
+    os.environ["SOLB_P2P"] = "1" if p2p else "0"  # read once per process by libsolb
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import time
@@ -102,15 +103,35 @@ def _rank_main(rank, world, id_path, out_dir):
             _frame(sol, ctx, sd, cam, sbt, f, a, tile=multigpu.tile_rows_for_rank(rank, world, band))
             comm.allgather_rows(a, band)
         tiles[band] = a.readback()
+    # the way bench.py's tile split runs: many frames in flight, the rgba8 frame gathered after every frame (each read back
+    # without waiting, two host slots), the float accumulation - every rank owns its bands of it - gathered once at the end
+    a, rend = sol.Image2d(ctx, W, H, N.FORMAT_RGBA32F), sol.Image2d(ctx, W, H, N.FORMAT_RGBA8)
+    slots, fences, shown = [ctx.host_alloc((H, W, 4), np.uint8) for _ in range(2)], [ctx.fence() for _ in range(2)], []
+    for f in range(8):
+        fences[f & 1].wait()
+        if f >= 2:
+            shown.append(slots[f & 1].copy())
+        _frame(sol, ctx, sd, cam, sbt, f, a, rend, tile=multigpu.tile_rows_for_rank(rank, world, 8))
+        comm.allgather_rows(rend, 8)
+        rend.readback_async(slots[f & 1])
+        fences[f & 1].signal()
+    for f in (6, 7):
+        fences[f & 1].wait()
+        shown.append(slots[f & 1].copy())
+    comm.allgather_rows(a, 8)
+    extra = dict(t8=tiles[8], t10=tiles[10], shown=np.stack(shown), loop_accum=a.readback())
     if rank == 0:
-        np.savez(os.path.join(out_dir, "rank0.npz"), accum=s.readback(), render=r.readback(), t8=tiles[8], t10=tiles[10])
+        np.savez(os.path.join(out_dir, "rank0.npz"), accum=s.readback(), render=r.readback(), **extra)
     else:
-        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), t8=tiles[8], t10=tiles[10])
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **extra)
     comm.close()
     ctx.close()
 
 
-def test_two_ranks_reduce_and_band_gather(tmp_path):
+@pytest.mark.parametrize("p2p", [True, False], ids=["peer_stores", "nccl_allgather"])
+def test_two_ranks_reduce_and_band_gather(tmp_path, p2p):
+    """p2p: the band exchange as 64-thread CTAs storing into the peers' IPC-mapped staging blocks (default), or as pack +
+    ncclAllGather + scatter (SOLB_P2P=0, and what a rank falls back to when a peer's block cannot be mapped)."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -121,7 +142,7 @@ def test_two_ranks_reduce_and_band_gather(tmp_path):
     from sol_rs_b200 import _native as N
     from sol_rs_b200 import ray
 
-    mp.spawn(_rank_main, args=(2, str(tmp_path / "nccl_id"), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_rank_main, args=(2, str(tmp_path / "nccl_id"), str(tmp_path), p2p), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     # single-GPU references
     ctx = sol.Context(0)
@@ -140,4 +161,11 @@ def test_two_ranks_reduce_and_band_gather(tmp_path):
     want = full.readback()
     for key in ("t8", "t10"):  # the tile split is bit-identical to the undivided frames, on every rank
         assert np.array_equal(r0[key], want) and np.array_equal(r1[key], want), key
+    full, rend = sol.Image2d(ctx, W, H, N.FORMAT_RGBA32F), sol.Image2d(ctx, W, H, N.FORMAT_RGBA8)
+    for f in range(8):
+        _frame(sol, ctx, sd, cam, sbt, f, full, rend)
+        shown = rend.readback()
+        assert np.array_equal(r0["shown"][f], shown) and np.array_equal(r1["shown"][f], shown), f
+    want = full.readback()
+    assert np.array_equal(r0["loop_accum"], want) and np.array_equal(r1["loop_accum"], want)
     ctx.close()
