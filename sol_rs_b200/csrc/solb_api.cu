@@ -92,7 +92,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.wl_gen_min = env_int("SOLB_WL_GEN_MIN", c->tune.wl_gen_min, 1, WL_POOL);
         c->tune.wl_batch = env_int("SOLB_WL_BATCH", c->tune.wl_batch, 32, 1024) & ~31;
         c->tune.wl_warps_per_sm = env_int("SOLB_WL_WARPS_PER_SM", c->tune.wl_warps_per_sm, 0, 64);
-        c->use_hi_stream = env_int("SOLB_HI_STREAM", 1, 0, 1);
+        c->use_hi_stream = env_int("SOLB_HI_STREAM", c->use_hi_stream, 0, 1);
         c->tune.wl_frames_in_flight = env_int("SOLB_WL_FRAMES_IN_FLIGHT", c->tune.wl_frames_in_flight, 1, WL_MAX_FRAMES);
     }
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));

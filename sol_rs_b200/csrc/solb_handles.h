@@ -47,7 +47,7 @@ struct solb_ctx {
     // persistent trace kernels of the frames in flight fill every SM, and a kernel of their priority waits for a whole drain
     cudaStream_t hi_stream = nullptr;
     cudaEvent_t ev_hi_in = nullptr, ev_hi_out = nullptr;
-    int use_hi_stream = 1;
+    int use_hi_stream = 0;  // SOLB_HI_STREAM=1: measured neutral with the peer-store exchange, slower with the NCCL one (profiles/r02_tile_split.txt)
     // queues + counters + streams of the extra frame parts (overlap mode); index 0 unused (= ws / stream)
     uint32_t *part_queue[WF_MAX_PARTS][2] = {};
     uint32_t *part_counters[WF_MAX_PARTS] = {};

@@ -71,6 +71,7 @@ struct AccelStorage {
     float4 *inst_leaves_f4() const { return (float4 *)inst_leaves; }
     Node8 *nodes = nullptr;
     Tri48 *tris = nullptr;
+    size_t nodes_cap = 0, tris_cap = 0;  // elements allocated (flattened builds: a rebuild reuses arrays that are large enough)
     uint32_t n_wide = 0, n_tris = 0, depth = 0, n_binary = 0;
     float sah_lbvh = 0.0f, sah_final = 0.0f;
     float lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
@@ -92,6 +93,7 @@ struct AccelStorage {
         if (inst_leaves) cudaFree(inst_leaves);
         if (blas_box) cudaFree(blas_box);
         nodes = nullptr; tris = nullptr; inst_leaves = nullptr; blas_box = nullptr;
+        nodes_cap = tris_cap = 0;
         n_wide = n_tris = depth = n_binary = 0;
         two_level = false;
         tlas_cap = n_blas = n_tlas_wide = tlas_depth = blas_depth = 0;
