@@ -410,7 +410,7 @@ def main():
     ctx.reset_stats()
     barrier_sync()
     t0 = time.perf_counter()
-    n_e2e = min(steps, 8)
+    n_e2e = steps
     for i, f in enumerate(multigpu.frames_for_rank(rank, world, world * n_e2e, first=200)):
         fences[i & 1].wait()  # wait_for_and_reset_fence: the frame that last used this slot has reached host memory
         u = scene.scene_uniforms(cam, WIDTH, HEIGHT, f)  # host-side camera -> 400-byte uniform block (the step's input)
@@ -448,7 +448,14 @@ def main():
         a_ms, _ = gather_max_sum(alone["ms_total"], 0)
         extra["tile_split"] = {"ms_per_frame": t_ms / n_t, "single_gpu_ms_per_frame": a_ms / n_t, "speedup_vs_1gpu": a_ms / t_ms,
                                "frames": n_t, "band_rows": BAND,
-                               "what": "one frame cut into interleaved %d-row bands over %d GPUs, solb_allgather_rows (pack + ncclAllGather + scatter) of the rgba8 frame per frame and of the float accumulation once at the end, all inside the timed region; max over ranks" % (BAND, world)}
+                               "what": "one frame cut into interleaved %d-row bands over %d GPUs, solb_allgather_rows (peer stores into the IPC-mapped staging of every rank over NVLink, flags, scatter; ncclAllGather when the peers cannot be mapped) of the rgba8 frame per frame and of the float accumulation once at the end, all inside the timed region; max over ranks" % (BAND, world)}
+        # configs[3] (3840 x 2160) with the frames split at this N: frames f = rank (mod N), one reduce + resolve at the end
+        n_4k = 4
+        r4 = device_timed(sd, cam, sbt, sched, 2, n_4k, "frames", 400, w=3840, h=2160)
+        k_ms, k_rays = gather_max_sum(r4["ms_total"], r4["rays"])
+        extra["config3_tunnel_4k"] = {"Mrays_s": k_rays / (k_ms * 1e-3) / 1e6, "ms_per_frame_per_gpu": (k_ms - r4["reduce_ms"]) / n_4k,
+                                      "reduce_ms": r4["reduce_ms"], "frames_per_rank": n_4k, "resolution": "3840x2160", "n_gpus": world}
+        cam.set_window_size((WIDTH, HEIGHT))
 
     if rank == 0:
         wkey = "tunnel_%dx%d" % (WIDTH, HEIGHT) if args.workload == "tunnel" else "synth_%d" % args.blas
@@ -529,6 +536,11 @@ def main():
         cb = cpu_reference_arm(1, 0, (WIDTH, HEIGHT))  # ONE full frame of the workload (~20 s on 16 host threads)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    if rank == 0 and roofline:
+        # the same algorithmic bytes over the steady-state step of the timed region (frames in flight overlap one frame's drain
+        # with the next frame's start; `achieved` / `frac` above are from launches timed one at a time)
+        roofline["achieved_in_timed_region"] = roofline["bytes_per_ray"] * (rays_total / world) / (ms_total * 1e-3) / 1e9
+        roofline["frac_in_timed_region"] = roofline["achieved_in_timed_region"] / roofline["peak"]
     if rank == 0:
         line_ = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                  "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiled else "weak", "vs_baseline": None,

@@ -61,7 +61,8 @@ struct TraceTuning {
     // warp-local wavefront schedule (k_pt_warpfront)
     int wl_ctas_per_sm = 8;    // persistent warps per SM in units of four (64 registers -> 8 x 128 threads)
     int wl_warps_per_sm = 0;   // > 0: persistent warps per SM, overrides wl_ctas_per_sm (one warp per CTA since round 2)
-    int wl_fetch_idle = 16;    // hand ready rays to idle lanes once this many lanes are idle (8: 3 556, 12: 3 618, 16: 3 645 Mrays/s)
+    int wl_fetch_idle = 20;    // hand ready rays to idle lanes once this many lanes are idle (round-2 final build, frames in flight:
+                               // 16: 4 508, 20: 4 539, 24: 4 470 Mrays/s, profiles/r02_sweep_warpfront_knobs.txt)
     int wl_starve_idle = 16;   // partial (< 32 slots) shade / generate steps only once this many lanes are idle and nothing is ready
     int wl_gen_min = 32;       // start new pixels once this many of a warp's slots are free (or its lanes starve): a full-width generate step
     int wl_frames_in_flight = 3;  // > 1: the kernel of frame f + 1 starts while frame f drains (they share nothing: each writes its
