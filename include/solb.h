@@ -12,6 +12,10 @@
  *     the reference's unwrap()/expect() behaviour (src/scene/mod.rs:140, src/ray/pipeline.rs:105).
  *   - one ctx = one CUDA device + one stream; a ctx is not thread-safe (the reference is
  *     single-threaded: src/lib.rs:174).  Multi-GPU = one ctx per device / process.
+ *   - everything is ORDERED as if enqueued on that one stream.  Internally the path tracer's frame kernels run on side
+ *     streams of the ctx so that consecutive frames overlap (frames in flight, like the reference's per-swapchain-image
+ *     command buffers); their resolves into the targets, and every other call, stay in order on the ctx stream, so work
+ *     the caller enqueues on that stream after a call sees its result.
  *   - host pointers passed in are copied during the call and never retained
  *     (reference: Buffer::from_data copies, src/buffer.rs:186-206).
  *   - matrices are column-major float[16] exactly as glam::Mat4 lays them out.
@@ -266,7 +270,9 @@ SOLB_API int solb_target_info(solb_target *t, uint32_t *width, uint32_t *height,
 
 SOLB_API void solb_trace_params_default(SolbTraceParams *p, int pipeline /* 0 pathtrace, 1 ao */);
 
-/* 5-pathtrace: assets/glsl/pathtrace.{rgen,rchit,rmiss}.  accum RGBA32F in/out, render RGBA8 out (may be NULL). */
+/* 5-pathtrace: assets/glsl/pathtrace.{rgen,rchit,rmiss}.  accum RGBA32F in/out, render RGBA8 out (may be NULL).
+ * Asynchronous: returns once the frame is enqueued (up to three frames of one ctx are in flight; the targets are written
+ * in frame order on the ctx stream).  Read results with solb_target_readback (blocks) or readback_async + a fence. */
 SOLB_API int solb_trace_pathtrace(solb_scene *scene, const SolbSceneUniforms *uniforms, const SolbTraceParams *params,
                                   solb_target *accum, solb_target *render);
 /* 4-ray-ao: assets/glsl/ao.{rgen,rchit,rmiss}.  image RGBA32F in/out; blue_noise = host rgba8[w*h],
@@ -292,7 +298,10 @@ SOLB_API int solb_resolve_sum(solb_ctx *ctx, solb_target *sum, solb_target *accu
 
 /* ---- multi-GPU exchange (new work: the reference is single-GPU).  One process per GPU, one communicator per
  * ctx; NCCL over NVLink underneath, bound at run time (the copy already loaded in the process, else SOLB_NCCL_LIB, else
- * libnccl.so.2).  All calls are collective over the ranks of the communicator and asynchronous on the ctx stream. ---- */
+ * libnccl.so.2).  All calls are collective over the ranks of the communicator and asynchronous on the ctx stream.
+ * solb_allgather_rows moves the bands with peer stores into CUDA-IPC-mapped staging blocks (one process per GPU on one
+ * node) and falls back, on every rank together, to ncclAllGather when a peer's block cannot be mapped; SOLB_P2P=0 forces
+ * the latter. ---- */
 #define SOLB_COMM_ID_BYTES 128
 /* rank 0 creates the id and hands the 128 bytes to the other ranks by any host-side means (ncclGetUniqueId) */
 SOLB_API int solb_comm_unique_id(uint8_t *id_out /* [SOLB_COMM_ID_BYTES] */);
