@@ -217,6 +217,24 @@ SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32
                                const SolbMaterialInfo *materials, uint32_t n_materials, solb_scene **out);
 SOLB_API int solb_scene_destroy(solb_scene *scene);
 
+/* Base-colour textures (an extension: the reference reserves SceneInstance::texture_offset, src/ray/mod.rs:20 and
+ * assets/glsl/pathtrace.rchit:31, and samples nothing).  textures[t].rgba8 = width x height x 4 bytes, rows top first (glTF
+ * image order: uv (0, 0) is the top-left corner), copied during the call; srgb != 0 decodes the colour channels with the sRGB
+ * transfer function (what glTF prescribes for baseColorTexture).  material_texture[m] = texture of material m or
+ * SOLB_NO_TEXTURE.  Afterwards every instance's texture_offset is the texture of its material (solb_scene_get_instances shows
+ * it) and 5-pathtrace multiplies the albedo (base_color x vertex colour, pathtrace.rchit:99,109) by a bilinear sample at the
+ * interpolated ModelVertex::uv.  n_textures = 0 unbinds: the reference's shading, bit for bit.  Synchronises. */
+#define SOLB_NO_TEXTURE 0xffffffffu
+typedef struct SolbTextureDesc {
+    const uint8_t *rgba8;
+    uint32_t width, height;
+    uint32_t wrap_s, wrap_t; /* glTF sampler codes: 10497 REPEAT (also 0), 33071 CLAMP_TO_EDGE, 33648 MIRRORED_REPEAT */
+    uint32_t srgb;
+    uint32_t _pad;
+} SolbTextureDesc;
+SOLB_API int solb_scene_set_textures(solb_scene *scene, const SolbTextureDesc *textures, uint32_t n_textures,
+                                     const uint32_t *material_texture, uint32_t n_materials);
+
 /* Replaces BLAS::new per section + TLAS::new (src/ray/acceleration.rs:136-239,344-400): GPU build of
  * the acceleration structure (Morton LBVH -> treelet SAH -> 8-wide compressed nodes). */
 SOLB_API int solb_accel_build(solb_scene *scene);

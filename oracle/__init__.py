@@ -123,6 +123,31 @@ class Scene:
         self.handle = lib().orc_scene_create(n, arr, _ptr(self.vertices), self.vertices.shape[0],
                                              _ptr(self.indices), self.indices.shape[0])
 
+    def set_textures(self, textures, material_textures):
+        """EXTENSION shared with the product, not reference behaviour: textures = [(rgba8 [h, w, 4] rows top first,
+        wrap_s, wrap_t)], material_textures = per material an index or None; instance i samples the texture of its material."""
+        n = len(textures)
+        imgs = [np.ascontiguousarray(t[0], dtype=np.uint8) for t in textures]
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in imgs])
+        w = np.array([a.shape[1] for a in imgs], dtype=np.uint32)
+        h = np.array([a.shape[0] for a in imgs], dtype=np.uint32)
+        ws = np.array([t[1] for t in textures], dtype=np.uint32)
+        wt = np.array([t[2] for t in textures], dtype=np.uint32)
+        it = np.array([0xFFFFFFFF if material_textures[inst["material"]] is None else material_textures[inst["material"]]
+                       for inst in self.flat.instances], dtype=np.uint32)
+        L = lib()
+        L.orc_scene_set_textures.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.orc_scene_set_textures(self.handle, n, ptrs, _ptr(w), _ptr(h), _ptr(ws), _ptr(wt), 1, _ptr(it))
+        self.instance_textures = it
+
+    def sample_texture(self, t, u, v):
+        out = np.zeros(3, dtype=np.float32)
+        L = lib()
+        L.orc_sample_texture.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]
+        L.orc_sample_texture(self.handle, int(t), float(u), float(v), _ptr(out))
+        return out
+
     def __del__(self):
         if getattr(self, "handle", None):
             lib().orc_scene_destroy(self.handle)

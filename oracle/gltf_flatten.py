@@ -250,6 +250,122 @@ class FlatScene:
         self.instances = []  # dicts: mesh, first_vertex, n_vertices, first_index, n_indices, material, transform
         self.meshes = []  # dicts: name, transform, sections
         self.camera = None  # dict(view=[4,4], yfov, znear, zfar) or None
+        # EXTENSION shared with the product (the reference loads no images): base-colour textures of the
+        # materials, (rgba8 [h, w, 4] rows top first, wrap_s, wrap_t), and per material an index into them or None
+        self.textures = []
+        self.material_textures = []
+
+
+def decode_png(data):
+    """PNG -> uint8 [h, w, 4]: 8 / 16-bit grey, rgb, palette (8-bit), grey-alpha, rgba; non-interlaced.  zlib does the inflate;
+    16-bit samples -> 8-bit by (v + 128) // 257 (the image 0.24 crate's to_rgba8 rule)."""
+    import struct
+    import zlib
+
+    assert data[:8] == b"\x89PNG\r\n\x1a\n", "not a PNG"
+    off, idat, plte, trns, hdr = 8, b"", b"", b"", None
+    while off + 12 <= len(data):
+        n, tag = struct.unpack_from(">I4s", data, off)
+        body = data[off + 8: off + 8 + n]
+        if tag == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body[:13])
+        elif tag == b"PLTE":
+            plte = body
+        elif tag == b"tRNS":
+            trns = body
+        elif tag == b"IDAT":
+            idat += body
+        elif tag == b"IEND":
+            break
+        off += 12 + n
+    w, h, depth, ctype, _, _, interlace = hdr
+    assert interlace == 0 and (depth == 8 or (depth == 16 and ctype != 3))
+    ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+    bpp = ch * depth // 8
+    stride = w * bpp
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8)[: (stride + 1) * h].reshape(h, stride + 1)
+    rows = np.zeros((h, stride), dtype=np.uint8)
+    prev = np.zeros(stride, dtype=np.int32)
+    for y in range(h):
+        f, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
+        if f == 0:
+            cur = line
+        elif f == 2:
+            cur = (line + prev) & 255
+        else:  # filters that look left: byte-serial
+            cur = np.zeros(stride, dtype=np.int32)
+            for i in range(stride):
+                a = cur[i - bpp] if i >= bpp else 0
+                b = prev[i]
+                c = prev[i - bpp] if i >= bpp else 0
+                if f == 1:
+                    p = a
+                elif f == 3:
+                    p = (a + b) >> 1
+                else:
+                    q = a + b - c
+                    pa, pb, pc = abs(q - a), abs(q - b), abs(q - c)
+                    p = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                cur[i] = (line[i] + p) & 255
+        rows[y] = cur
+        prev = cur
+    if depth == 16:
+        v = rows.reshape(h, w, ch, 2).astype(np.uint32)
+        s8 = (((v[..., 0] << 8) | v[..., 1]) + 128) // 257
+    else:
+        s8 = rows.reshape(h, w, ch).astype(np.uint32)
+    out = np.full((h, w, 4), 255, dtype=np.uint8)
+    if ctype == 0:
+        out[..., :3] = s8[..., :1]
+    elif ctype == 2:
+        out[..., :3] = s8
+    elif ctype == 4:
+        out[..., :3] = s8[..., :1]
+        out[..., 3] = s8[..., 1]
+    elif ctype == 6:
+        out[...] = s8
+    else:
+        pal = np.frombuffer(plte, dtype=np.uint8).reshape(-1, 3)
+        out[..., :3] = pal[s8[..., 0]]
+        alpha = np.full(256, 255, dtype=np.uint8)
+        alpha[: len(trns)] = np.frombuffer(trns, dtype=np.uint8)
+        out[..., 3] = alpha[s8[..., 0]]
+    return out
+
+
+def _load_textures(g, fs):
+    doc = g.doc
+    base = os.path.dirname(os.path.abspath(g.path))
+    slot = {}
+    for mat in doc.get("materials", []):
+        ref = mat.get("pbrMetallicRoughness", {}).get("baseColorTexture")
+        bound = None
+        if ref is not None and ref.get("texCoord", 0) == 0 and 0 <= ref.get("index", 0) < len(doc.get("textures", [])):
+            ti = ref.get("index", 0)
+            if ti not in slot:
+                slot[ti] = None
+                try:
+                    tex = doc["textures"][ti]
+                    img = doc["images"][tex["source"]]
+                    if "uri" in img:
+                        uri = img["uri"]
+                        if uri.startswith("data:"):
+                            data = base64.b64decode(uri.split(",", 1)[1])
+                        else:
+                            with open(os.path.join(base, urllib.parse.unquote(uri)), "rb") as f:
+                                data = f.read()
+                    else:
+                        view = doc["bufferViews"][img["bufferView"]]
+                        o = view.get("byteOffset", 0)
+                        data = bytes(g.buffers[view["buffer"]][o: o + view["byteLength"]])
+                    rgba = decode_png(data)
+                    smp = doc.get("samplers", [])[tex["sampler"]] if "sampler" in tex else {}
+                    slot[ti] = len(fs.textures)
+                    fs.textures.append((rgba, smp.get("wrapS", 10497), smp.get("wrapT", 10497)))
+                except Exception:
+                    pass  # not a PNG / missing file: the material stays untextured
+            bound = slot[ti]
+        fs.material_textures.append(bound)
 
 
 def _other_node_transforms(doc, mesh_index, first_node):
@@ -291,6 +407,7 @@ def load_scene(path, instancing=False):
              pbr.get("metallicFactor", 1.0), pbr.get("roughnessFactor", 1.0), 0.0, 0.0]
         )
     fs.materials = np.array(mats, dtype=F32).reshape(-1, 12)
+    _load_textures(g, fs)
     verts, inds = [], []
     nv_total, ni_total = 0, 0
     for mi, mesh in enumerate(doc.get("meshes", [])):

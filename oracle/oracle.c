@@ -166,7 +166,18 @@ typedef struct {
     OrcNode *nodes;
     uint32_t n_nodes;
     double scale;         /* max |coordinate| of the world-space scene: sizes the interval-end tolerance */
+    /* Base-colour textures: an EXTENSION shared with the product, not reference behaviour - the reference
+     * reserves SceneInstance::texture_offset (src/ray/mod.rs:20, pathtrace.rchit:31) and samples nothing.  Unbound
+     * (n_tex == 0): the shaders above, untouched. */
+    uint32_t n_tex;
+    struct OrcTexture *tex;
+    uint32_t *inst_tex;   /* per instance: texture index or 0xffffffff */
 } OrcScene;
+
+typedef struct OrcTexture {
+    uint32_t width, height, wrap_s, wrap_t; /* glTF sampler codes: 10497 repeat, 33071 clamp, 33648 mirrored repeat */
+    float *texels;                          /* linear-light rgba, rows top first */
+} OrcTexture;
 
 static void bvh_bounds(const OrcTri *t, double lo[3], double hi[3])
 {
@@ -277,9 +288,82 @@ ORC_API OrcScene *orc_scene_create(uint32_t n_inst, const OrcInstance *inst,
     return s;
 }
 
+static void orc_free_textures(OrcScene *s)
+{
+    for (uint32_t t = 0; t < s->n_tex; t++) free(s->tex[t].texels);
+    free(s->tex); free(s->inst_tex);
+    s->tex = NULL; s->inst_tex = NULL; s->n_tex = 0;
+}
+
+/* rgba8[t]: width x height x 4 bytes, rows top first; colour channels sRGB-decoded (IEC 61966-2-1) when srgb != 0.
+ * inst_tex[i]: texture of instance i (the reference's reserved texture_offset) or 0xffffffff. */
+ORC_API void orc_scene_set_textures(OrcScene *s, uint32_t n_tex, const uint8_t *const *rgba8, const uint32_t *width,
+                                    const uint32_t *height, const uint32_t *wrap_s, const uint32_t *wrap_t, int srgb,
+                                    const uint32_t *inst_tex)
+{
+    orc_free_textures(s);
+    if (!n_tex) return;
+    float lut[256];
+    for (int i = 0; i < 256; i++) {
+        const float x = (float)i / 255.0f;
+        lut[i] = x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
+    }
+    s->n_tex = n_tex;
+    s->tex = (OrcTexture *)calloc(n_tex, sizeof(OrcTexture));
+    for (uint32_t t = 0; t < n_tex; t++) {
+        OrcTexture *d = &s->tex[t];
+        d->width = width[t]; d->height = height[t];
+        d->wrap_s = wrap_s[t] ? wrap_s[t] : 10497u; d->wrap_t = wrap_t[t] ? wrap_t[t] : 10497u;
+        const size_t n = (size_t)width[t] * height[t];
+        d->texels = (float *)malloc(sizeof(float) * 4 * n);
+        for (size_t i = 0; i < n; i++) {
+            for (int c = 0; c < 3; c++) d->texels[4 * i + c] = srgb ? lut[rgba8[t][4 * i + c]] : (float)rgba8[t][4 * i + c] / 255.0f;
+            d->texels[4 * i + 3] = (float)rgba8[t][4 * i + 3] / 255.0f;
+        }
+    }
+    s->inst_tex = (uint32_t *)malloc(sizeof(uint32_t) * (s->n_inst ? s->n_inst : 1));
+    memcpy(s->inst_tex, inst_tex, sizeof(uint32_t) * s->n_inst);
+}
+
+static int tex_wrap(int i, int n, uint32_t mode)
+{
+    if (mode == 33071u) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    if (mode == 33648u) {
+        int m = i % (2 * n);
+        if (m < 0) m += 2 * n;
+        return m < n ? m : 2 * n - 1 - m;
+    }
+    int m = i % n;
+    return m < 0 ? m + n : m;
+}
+
+/* bilinear, texel centres at (i + 0.5) / n, lerp as fma(b - a, t, a); non-finite coordinates sample (0, 0) */
+static void sample_texture(const OrcTexture *td, float u, float v, float out[3])
+{
+    if (!(fabsf(u) < 1e9f)) u = 0.0f;
+    if (!(fabsf(v) < 1e9f)) v = 0.0f;
+    const float x = fmaf(u, (float)td->width, -0.5f), y = fmaf(v, (float)td->height, -0.5f);
+    const float x0 = floorf(x), y0 = floorf(y);
+    const float fx = x - x0, fy = y - y0;
+    const int ix0 = tex_wrap((int)x0, (int)td->width, td->wrap_s), ix1 = tex_wrap((int)x0 + 1, (int)td->width, td->wrap_s);
+    const int iy0 = tex_wrap((int)y0, (int)td->height, td->wrap_t), iy1 = tex_wrap((int)y0 + 1, (int)td->height, td->wrap_t);
+    const float *t00 = td->texels + 4 * ((size_t)iy0 * td->width + ix0), *t10 = td->texels + 4 * ((size_t)iy0 * td->width + ix1);
+    const float *t01 = td->texels + 4 * ((size_t)iy1 * td->width + ix0), *t11 = td->texels + 4 * ((size_t)iy1 * td->width + ix1);
+    for (int c = 0; c < 3; c++) {
+        const float top = fmaf(t10[c] - t00[c], fx, t00[c]), bot = fmaf(t11[c] - t01[c], fx, t01[c]);
+        out[c] = fmaf(bot - top, fy, top);
+    }
+}
+
+ORC_API void orc_sample_texture(const OrcScene *s, uint32_t t, float u, float v, float out[3])
+{
+    sample_texture(&s->tex[t], u, v, out);
+}
+
 ORC_API void orc_scene_destroy(OrcScene *s)
 {
     if (!s) return;
+    orc_free_textures(s);
     free(s->inst); free(s->vertices); free(s->indices); free(s->tris); free(s->nodes); free(s);
 }
 
@@ -558,6 +642,12 @@ static void pathtrace_rchit(const OrcScene *s, const OrcHit *h, v3 worldRayDir, 
         worldPos = V3(r[0], r[1], r[2]);
     }
     v3 vertex_color = mix3(v0 + 4, v1 + 4, v2 + 4, bx, by, bz); /* :88 */
+    if (s->n_tex && s->inst_tex[h->inst] < s->n_tex) { /* extension: albedo x base-colour texture at the interpolated uv */
+        const float u = v0[12] * bx + v1[12] * by + v2[12] * bz, v = v0[13] * bx + v1[13] * by + v2[13] * bz; /* uv @ float 12 */
+        float tc[3];
+        sample_texture(&s->tex[s->inst_tex[h->inst]], u, v, tc);
+        vertex_color = V3(vertex_color.x * tc[0], vertex_color.y * tc[1], vertex_color.z * tc[2]);
+    }
     v3 wI = v3_normalize(worldRayDir); /* :90 */
     v3 nO = v3_scale(normal, signf(v3_dot(normal, V3(-wI.x, -wI.y, -wI.z)))); /* :91 */
     float alphaSquared = mat[9] * mat[9]; /* :92 */

@@ -73,6 +73,18 @@ pub struct SolbSection {
     pub n_indices: u32,
     pub material_index: u32,
 }
+pub const SOLB_NO_TEXTURE: u32 = 0xffff_ffff;
+/// base-colour texture handed to solb_scene_set_textures: rgba8 rows top first
+#[repr(C)]
+pub struct SolbTextureDesc {
+    pub rgba8: *const u8,
+    pub width: u32,
+    pub height: u32,
+    pub wrap_s: u32,
+    pub wrap_t: u32,
+    pub srgb: u32,
+    pub _pad: u32,
+}
 #[repr(C)]
 pub struct SolbMeshDesc {
     pub vertices: *const SolbModelVertex,
@@ -169,6 +181,8 @@ extern "C" {
     pub fn solb_instance_set_transform(scene: *mut solb_scene, index: u32, transform: *const f32) -> c_int;
     pub fn solb_scene_update(scene: *mut solb_scene) -> c_int;
     pub fn solb_tlas_regenerate(scene: *mut solb_scene) -> c_int;
+    pub fn solb_scene_set_textures(scene: *mut solb_scene, textures: *const SolbTextureDesc, n_textures: u32, material_texture: *const u32,
+                                   n_materials: u32) -> c_int;
     pub fn solb_scene_add_instance(scene: *mut solb_scene, source_instance: u32, transform: *const f32, material_index: u32,
                                    out_index: *mut u32) -> c_int;
     pub fn solb_scene_set_accel_mode(scene: *mut solb_scene, mode: u32) -> c_int;

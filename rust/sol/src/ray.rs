@@ -160,6 +160,19 @@ impl SceneDescription {
         id
     }
 
+    /// Beyond the reference: bind base-colour textures (rgba8 rows top first, sRGB colour) and, per material, its
+    /// texture (`None`: untextured).  Every instance's `texture_offset` (src/ray/mod.rs:20) becomes the texture of its material.
+    pub fn set_textures(&mut self, textures: &[crate::scene::Texture], material_textures: &[Option<u32>]) {
+        let descs: Vec<SolbTextureDesc> = textures
+            .iter()
+            .map(|t| SolbTextureDesc { rgba8: t.rgba8.as_ptr(), width: t.width, height: t.height, wrap_s: t.wrap_s, wrap_t: t.wrap_t, srgb: 1, _pad: 0 })
+            .collect();
+        let mt: Vec<u32> = material_textures.iter().map(|t| t.unwrap_or(SOLB_NO_TEXTURE)).collect();
+        self.context.check(unsafe {
+            solb_scene_set_textures(self.raw, descs.as_ptr(), descs.len() as u32, mt.as_ptr(), mt.len() as u32)
+        });
+    }
+
     pub fn set_accel_mode(&mut self, mode: AccelMode) {
         let m = if mode == AccelMode::TwoLevel { SOLB_ACCEL_TWO_LEVEL } else { SOLB_ACCEL_FLAT };
         self.context.check(unsafe { solb_scene_set_accel_mode(self.raw, m) });

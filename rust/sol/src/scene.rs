@@ -70,11 +70,32 @@ pub struct Mesh {
     pub extra_instance_transforms: Vec<Mat4>,
 }
 
-/// src/scene/mod.rs:99-104
+/// Base-colour texture of a material (beyond the reference): rgba8 rows top first + the sampler's wrap modes
+/// (glTF codes, 10497 = REPEAT).
+pub struct Texture {
+    pub width: u32,
+    pub height: u32,
+    pub rgba8: Vec<u8>,
+    pub wrap_s: u32,
+    pub wrap_t: u32,
+}
+
+/// src/scene/mod.rs:99-104 (+ `textures` / `material_textures`, beyond the reference: bound with
+/// `SceneDescription::set_textures`; nothing samples them otherwise)
 pub struct Scene {
     pub meshes: Vec<Mesh>,
     pub materials: Vec<MaterialInfo>,
     pub camera: Option<Camera>,
+    pub textures: Vec<Texture>,
+    pub material_textures: Vec<Option<u32>>,
+}
+
+fn wrap_code(w: gltf::texture::WrappingMode) -> u32 {
+    match w {
+        gltf::texture::WrappingMode::ClampToEdge => 33071,
+        gltf::texture::WrappingMode::MirroredRepeat => 33648,
+        gltf::texture::WrappingMode::Repeat => 10497,
+    }
 }
 
 fn local_matrix(node: &gltf::Node) -> Mat4 {
@@ -136,7 +157,7 @@ fn other_instance_transforms(doc: &gltf::Document, mesh_index: usize, first_node
 
 /// src/scene/mod.rs:138-295.  `context` is accepted for source compatibility (the reference uploads here).
 pub fn load_scene(_context: Arc<Context>, filepath: &PathBuf) -> Scene {
-    let (doc, buffers, _images) = gltf::import(filepath).unwrap();
+    let (doc, buffers, images) = gltf::import(filepath).unwrap();
 
     // materials with the gltf crate's defaults (base 1,1,1,1; metallic 1; roughness 1; emissive 0)
     let materials: Vec<MaterialInfo> = doc
@@ -215,7 +236,41 @@ pub fn load_scene(_context: Arc<Context>, filepath: &PathBuf) -> Scene {
             }
         }
     }
-    Scene { meshes, materials, camera }
+    // base-colour textures (texture-coordinate set 0 only), one entry per glTF texture in use
+    let mut textures: Vec<Texture> = Vec::new();
+    let mut slot: Vec<Option<u32>> = vec![None; doc.textures().count()];
+    let mut material_textures: Vec<Option<u32>> = Vec::new();
+    for m in doc.materials() {
+        let mut bound = None;
+        if let Some(info) = m.pbr_metallic_roughness().base_color_texture() {
+            if info.tex_coord() == 0 {
+                let tex = info.texture();
+                if slot[tex.index()].is_none() {
+                    let data = &images[tex.source().index()];
+                    let rgba8 = match data.format {
+                        gltf::image::Format::R8G8B8A8 => Some(data.pixels.clone()),
+                        gltf::image::Format::R8G8B8 => Some(data.pixels.chunks(3).flat_map(|p| [p[0], p[1], p[2], 255]).collect()),
+                        gltf::image::Format::R8 => Some(data.pixels.iter().flat_map(|&v| [v, v, v, 255]).collect()),
+                        gltf::image::Format::R8G8 => Some(data.pixels.chunks(2).flat_map(|p| [p[0], p[0], p[0], p[1]]).collect()),
+                        _ => None,
+                    };
+                    if let Some(rgba8) = rgba8 {
+                        slot[tex.index()] = Some(textures.len() as u32);
+                        textures.push(Texture {
+                            width: data.width,
+                            height: data.height,
+                            rgba8,
+                            wrap_s: wrap_code(tex.sampler().wrap_s()),
+                            wrap_t: wrap_code(tex.sampler().wrap_t()),
+                        });
+                    }
+                }
+                bound = slot[tex.index()];
+            }
+        }
+        material_textures.push(bound);
+    }
+    Scene { meshes, materials, camera, textures, material_textures }
 }
 
 /// src/scene/camera.rs:34-127 (matrices only)

@@ -53,6 +53,14 @@ class MeshDesc(ctypes.Structure):
                 ("transform", ctypes.c_float * 16)]
 
 
+class TextureDesc(ctypes.Structure):
+    _fields_ = [("rgba8", ctypes.c_void_p), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("wrap_s", ctypes.c_uint32),
+                ("wrap_t", ctypes.c_uint32), ("srgb", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
+
+
+NO_TEXTURE = 0xFFFFFFFF
+
+
 class TraceParams(ctypes.Structure):
     _fields_ = [("accum_start_frame", ctypes.c_int32), ("enable_sky", ctypes.c_uint32), ("samples_per_frame", ctypes.c_uint32),
                 ("max_bounces", ctypes.c_uint32), ("schedule", ctypes.c_uint32), ("accum_mode", ctypes.c_uint32),
@@ -102,6 +110,7 @@ SYMBOLS = {
     "solb_instance_set_transform": (_i, [_vp, _u32, ctypes.POINTER(ctypes.c_float)]),
     "solb_scene_update": (_i, [_vp]),
     "solb_tlas_regenerate": (_i, [_vp]),
+    "solb_scene_set_textures": (_i, [_vp, ctypes.POINTER(TextureDesc), _u32, ctypes.POINTER(_u32), _u32]),
     "solb_scene_add_instance": (_i, [_vp, _u32, ctypes.POINTER(ctypes.c_float), _u32, ctypes.POINTER(_u32)]),
     "solb_scene_set_accel_mode": (_i, [_vp, _u32]),
     "solb_scene_instance_count": (_i, [_vp, ctypes.POINTER(_u32)]),

@@ -11,7 +11,9 @@
 // The `gltf` crate (1.0.0, Cargo.lock:518-519) behaviour it relies on is restated: material
 // defaults, Node::transform().matrix() for decomposed TRS, accessor readers into_u32 / into_f32 /
 // into_rgba_f32.  .glb containers are accepted (JSON + BIN chunks).  Unsupported (no shipped asset uses them): sparse
-// accessors, Draco, textures (the reference loads none on this path: texture_offset is reserved, src/ray/mod.rs:20).
+// accessors, Draco.  Beyond the reference: the materials' base-colour textures are decoded (PNG) into
+// Scene::textures / material_textures; the reference loads none on this path (texture_offset is reserved, src/ray/mod.rs:20),
+// and nothing changes for a caller that does not bind them.
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -282,6 +284,57 @@ Scene load_scene(std::shared_ptr<Context>, const std::string &filepath) {
         m.metallic = (float)pbr["metallicFactor"].number(1.0);
         m.roughness = (float)pbr["roughnessFactor"].number(1.0);
         scene.materials.push_back(m);
+    }
+    // base-colour textures: material -> texture -> (image, sampler).  One Scene::textures entry per glTF texture in use.
+    {
+        const json::Value &textures = d.root["textures"], &images = d.root["images"], &samplers = d.root["samplers"];
+        std::vector<uint32_t> slot(textures.size(), SOLB_NO_TEXTURE - 1u);  // SOLB_NO_TEXTURE - 1: not tried yet
+        scene.material_textures.assign(mats.size(), SOLB_NO_TEXTURE);
+        for (size_t i = 0; i < mats.size(); i++) {
+            const json::Value &pbr = mats[i]["pbrMetallicRoughness"];
+            if (!pbr.has("baseColorTexture")) continue;
+            const json::Value &ref = pbr["baseColorTexture"];
+            const size_t ti = (size_t)ref["index"].integer(0);
+            if (ti >= textures.size() || ref["texCoord"].integer(0) != 0) continue;
+            if (slot[ti] == SOLB_NO_TEXTURE - 1u) {
+                slot[ti] = SOLB_NO_TEXTURE;
+                try {
+                    const json::Value &tex = textures[ti];
+                    if (!tex.has("source")) throw Error(SOLB_ERR_UNSUPPORTED, "texture without source");
+                    const json::Value &img = images[(size_t)tex["source"].integer(0)];
+                    std::string bytes;
+                    if (img.has("uri")) {
+                        const std::string uri = img["uri"].string();
+                        if (uri.compare(0, 5, "data:") == 0) {
+                            const size_t comma = uri.find(',');
+                            if (comma == std::string::npos) throw Error(SOLB_ERR_INVALID, "malformed data URI");
+                            bytes = base64_decode(uri, comma + 1);
+                        } else bytes = read_file(dir + "/" + uri_decode(uri), true);
+                    } else {
+                        const json::Value &view = d.root["bufferViews"][(size_t)img["bufferView"].integer(0)];
+                        const std::string &buf = d.buffers.at((size_t)view["buffer"].integer(0));
+                        const size_t off = (size_t)view["byteOffset"].integer(0), len = (size_t)view["byteLength"].integer(0);
+                        if (off + len > buf.size()) throw Error(SOLB_ERR_INVALID, "image bufferView outside its buffer");
+                        bytes = buf.substr(off, len);
+                    }
+                    const image::Rgba8 im = image::decode_png((const uint8_t *)bytes.data(), bytes.size());
+                    Texture t;
+                    t.width = im.width;
+                    t.height = im.height;
+                    t.rgba8 = im.pixels;
+                    if (tex.has("sampler")) {
+                        const json::Value &smp = samplers[(size_t)tex["sampler"].integer(0)];
+                        t.wrap_s = (uint32_t)smp["wrapS"].integer(10497);
+                        t.wrap_t = (uint32_t)smp["wrapT"].integer(10497);
+                    }
+                    slot[ti] = (uint32_t)scene.textures.size();
+                    scene.textures.push_back(std::move(t));
+                } catch (const std::exception &) {
+                    // not a PNG / missing file / broken stream: the material stays untextured, as it is for the reference
+                }
+            }
+            scene.material_textures[i] = slot[ti];
+        }
     }
 
     const json::Value &meshes = d.root["meshes"];

@@ -33,6 +33,28 @@ SOLH_API uint32_t solh_scene_material_count(const scene::Scene *s) { return (uin
 SOLH_API const void *solh_scene_materials(const scene::Scene *s) { return s->materials.data(); }
 SOLH_API int solh_scene_has_camera(const scene::Scene *s) { return s->camera.has_value(); }
 
+SOLH_API uint32_t solh_scene_texture_count(const scene::Scene *s) { return (uint32_t)s->textures.size(); }
+// out4 = { width, height, wrap_s, wrap_t }; returns the rgba8 pixels (rows top first), valid until solh_scene_free
+SOLH_API const uint8_t *solh_scene_texture(const scene::Scene *s, uint32_t i, uint32_t *out4) {
+    if (i >= s->textures.size()) return nullptr;
+    const scene::Texture &t = s->textures[i];
+    out4[0] = t.width; out4[1] = t.height; out4[2] = t.wrap_s; out4[3] = t.wrap_t;
+    return t.rgba8.data();
+}
+SOLH_API const uint32_t *solh_scene_material_textures(const scene::Scene *s) { return s->material_textures.data(); }
+// decode_png for tests: returns 0 and fills w / h; pixels into out when capacity suffices
+SOLH_API int solh_decode_png(const uint8_t *data, size_t n, uint32_t *w, uint32_t *h, uint8_t *out, size_t capacity, char *err, size_t errlen) {
+    try {
+        const image::Rgba8 im = image::decode_png(data, n);
+        *w = im.width; *h = im.height;
+        if (out && capacity >= im.pixels.size()) std::memcpy(out, im.pixels.data(), im.pixels.size());
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, e.what());
+        return -1;
+    }
+}
+
 SOLH_API int solh_mesh_info(const scene::Scene *s, uint32_t i, SolhMeshInfo *out) {
     if (i >= s->meshes.size()) return -1;
     const scene::Mesh &m = s->meshes[i];

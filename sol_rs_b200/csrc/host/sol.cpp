@@ -254,6 +254,16 @@ uint32_t SceneDescription::add_instance(size_t source_instance, const Mat4 &tran
     ctx_->check(solb_scene_add_instance(h_, (uint32_t)source_instance, transform.data(), material_index, &id));
     return id;
 }
+void SceneDescription::set_textures(const std::vector<scene::Texture> &textures, const std::vector<uint32_t> &material_textures) {
+    std::vector<SolbTextureDesc> descs(textures.size());
+    for (size_t i = 0; i < textures.size(); i++) {
+        if (textures[i].rgba8.size() != (size_t)textures[i].width * textures[i].height * 4)
+            throw Error(SOLB_ERR_INVALID, "set_textures: texture size does not match its pixels");
+        descs[i] = SolbTextureDesc{ textures[i].rgba8.data(), textures[i].width, textures[i].height, textures[i].wrap_s, textures[i].wrap_t,
+                                    1u /* glTF base colour is sRGB-encoded */, 0u };
+    }
+    ctx_->check(solb_scene_set_textures(h_, descs.data(), (uint32_t)descs.size(), material_textures.data(), (uint32_t)material_textures.size()));
+}
 void SceneDescription::set_accel_mode(SolbAccelMode mode) { ctx_->check(solb_scene_set_accel_mode(h_, (uint32_t)mode)); }
 void SceneDescription::accel_build() { ctx_->check(solb_accel_build(h_)); }
 void SceneDescription::tlas_regenerate() { ctx_->check(solb_tlas_regenerate(h_)); }

@@ -30,6 +30,15 @@ struct Error : std::runtime_error {
     Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
 
+namespace image {
+struct Rgba8 {
+    uint32_t width = 0, height = 0;
+    std::vector<uint8_t> pixels;  // rows top first
+};
+bool is_png(const uint8_t *data, size_t n);
+Rgba8 decode_png(const uint8_t *data, size_t n);  // host/png.cpp; throws sol::Error
+}  // namespace image
+
 using Mat4 = std::array<float, 16>;  // column-major like glam::Mat4
 struct Vec3 { float x, y, z; };
 struct Vec2 { float x, y; };
@@ -136,10 +145,23 @@ private:
     Vec2 window_size_{ 1920.0f, 1080.0f };
 };
 
+// Base-colour texture of a glTF material (beyond the reference, whose load_scene reads no images): decoded
+// rgba8, rows top first, with the sampler's wrap modes (glTF codes; 10497 = REPEAT is the default).
+struct Texture {
+    uint32_t width = 0, height = 0;
+    std::vector<uint8_t> rgba8;
+    uint32_t wrap_s = 10497, wrap_t = 10497;
+};
+
 struct Scene {  // src/scene/mod.rs:99-104
     std::vector<Mesh> meshes;
     std::vector<MaterialInfo> materials;
     std::optional<Camera> camera;
+    // beyond the reference: the base-colour textures the materials name (PNG images only; a material whose image cannot be
+    // decoded, or that uses a texture-coordinate set other than 0, stays untextured) and, per material, its texture or
+    // SOLB_NO_TEXTURE.  SceneDescription::set_textures(scene) binds them; nothing samples them otherwise.
+    std::vector<Texture> textures;
+    std::vector<uint32_t> material_textures;
 };
 
 // src/scene/mod.rs:138-295.  Throws sol::Error where the reference unwrap()s (missing file, bad glTF).
@@ -175,6 +197,10 @@ public:
     // Beyond the reference (its TODO at src/ray/mod.rs:122): one more instance of the BLAS `source_instance` uses; returns the
     // new gl_InstanceID.  accel_mode SOLB_ACCEL_TWO_LEVEL keeps BLASes shared and lets tlas_regenerate rebuild the TLAS only.
     uint32_t add_instance(size_t source_instance, const Mat4 &transform, uint32_t material_index);
+    // Beyond the reference: bind the scene's base-colour textures (solb_scene_set_textures); every instance's
+    // texture_offset (src/ray/mod.rs:20) becomes the texture of its material.  An empty list unbinds.
+    void set_textures(const std::vector<scene::Texture> &textures, const std::vector<uint32_t> &material_textures);
+    void set_textures(const scene::Scene &scene) { set_textures(scene.textures, scene.material_textures); }
     void set_accel_mode(SolbAccelMode mode);
     void accel_build();
     void tlas_regenerate();  // the reference takes the command buffer; launches are stream-ordered here

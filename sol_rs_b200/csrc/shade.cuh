@@ -118,10 +118,60 @@ SOLB_HD void unpack_shade_record(const float4 *q, ShadeVerts &sv) {
 
 SOLB_HD float3 bary_mix(const float3 *v, float bx, float by, float bz) { return v[0] * bx + v[1] * by + v[2] * bz; }
 
+// ---- base-colour texture (extension; the CPU checker restates it operation for operation) ----
+SOLB_HD int tex_wrap(int i, int n, uint32_t mode) {
+    if (mode == 33071u) return i < 0 ? 0 : (i >= n ? n - 1 : i);  // CLAMP_TO_EDGE
+    if (mode == 33648u) {                                          // MIRRORED_REPEAT
+        int m = i % (2 * n);
+        if (m < 0) m += 2 * n;
+        return m < n ? m : 2 * n - 1 - m;
+    }
+    int m = i % n;  // REPEAT (glTF default)
+    return m < 0 ? m + n : m;
+}
+SOLB_HD float3 tex_lerp3(float3 a, float3 b, float t) {
+    return f3(fmaf(b.x - a.x, t, a.x), fmaf(b.y - a.y, t, a.y), fmaf(b.z - a.z, t, a.z));
+}
+SOLB_HD float3 tex_fetch(const TexDesc &td, int x, int y) {
+#if defined(__CUDA_ARCH__)
+    const float4 t = __ldg(td.texels + (size_t)y * td.width + (size_t)x);
+#else
+    const float4 t = td.texels[(size_t)y * td.width + (size_t)x];
+#endif
+    return f3(t.x, t.y, t.z);
+}
+// bilinear, texel centres at (i + 0.5) / n; non-finite coordinates sample (0, 0)
+SOLB_HD float3 sample_texture(const TexDesc &td, float u, float v) {
+    if (!(fabsf(u) < 1e9f)) u = 0.0f;
+    if (!(fabsf(v) < 1e9f)) v = 0.0f;
+    const float x = fmaf(u, (float)td.width, -0.5f), y = fmaf(v, (float)td.height, -0.5f);
+    const float x0 = floorf(x), y0 = floorf(y);
+    const float fx = x - x0, fy = y - y0;
+    const int ix0 = tex_wrap((int)x0, (int)td.width, td.wrap_s), ix1 = tex_wrap((int)x0 + 1, (int)td.width, td.wrap_s);
+    const int iy0 = tex_wrap((int)y0, (int)td.height, td.wrap_t), iy1 = tex_wrap((int)y0 + 1, (int)td.height, td.wrap_t);
+    const float3 top = tex_lerp3(tex_fetch(td, ix0, iy0), tex_fetch(td, ix1, iy0), fx);
+    const float3 bot = tex_lerp3(tex_fetch(td, ix0, iy1), tex_fetch(td, ix1, iy1), fx);
+    return tex_lerp3(top, bot, fy);
+}
+// the instance's texture at the hit: uv through indices[] / vertices[] as pathtrace.rchit:61-67 fetches its vertices
+SOLB_HD float3 instance_texture(const TexBinding &tb, const DeviceInstance &in, uint32_t prim, float bx, float by, float bz) {
+    const uint32_t t1 = f2u(in.mat[10]);
+    if (t1 == 0u || t1 > tb.n_tex) return f3(1.0f, 1.0f, 1.0f);
+    const uint32_t *ip = tb.indices + in.first_index + 3u * prim;
+    float2 uv[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float4 q = tb.vertices[(size_t)(in.first_vertex + ip[k]) * 4 + 3];
+        uv[k] = make_float2(q.x, q.y);
+    }
+    const float u = uv[0].x * bx + uv[1].x * by + uv[2].x * bz, v = uv[0].y * bx + uv[1].y * by + uv[2].y * bz;
+    return sample_texture(tb.tex[t1 - 1u], u, v);
+}
+
 // assets/glsl/pathtrace.rchit:56-113.  Returns true when the path terminates (prd.done = 1).
 // inout: origin/dir (ray that hit, replaced by the bounce ray), rng.  out: hit_value.
-SOLB_HD bool shade_hit(const DeviceInstance *__restrict__ instances, const ShadeRecord *__restrict__ shade, uint32_t inst,
-                       uint32_t gtri, float u, float v, float3 &origin, float3 &dir, uint32_t &rng, float3 &hit_value) {
+SOLB_HD bool shade_hit(const DeviceInstance *__restrict__ instances, const ShadeRecord *__restrict__ shade, const TexBinding &texb,
+                       uint32_t inst, uint32_t gtri, float u, float v, float3 &origin, float3 &dir, uint32_t &rng, float3 &hit_value) {
     const DeviceInstance &in = instances[inst];
     const float *mat = in.mat;
     if (mat[4] >= 1.0f || mat[5] >= 1.0f || mat[6] >= 1.0f) {  // :71-76 emissive terminates, no RNG draw
@@ -135,7 +185,8 @@ SOLB_HD bool shade_hit(const DeviceInstance *__restrict__ instances, const Shade
     normal = normalize(mat4_mul_dir(in.transform_it, normal));  // :82
     float3 world_pos = bary_mix(sv.p, bx, by, bz);   // :84
     world_pos = mat4_mul_point(in.transform, world_pos);        // :86
-    const float3 vertex_color = bary_mix(sv.c, bx, by, bz);     // :88
+    float3 vertex_color = bary_mix(sv.c, bx, by, bz);           // :88
+    if (texb.n_tex) vertex_color = vertex_color * instance_texture(texb, in, gtri - in.shade_first_tri, bx, by, bz);  // (extension)
     const float3 wI = normalize(dir);                           // :90
     const float3 nO = normal * signf_glsl(dot(normal, -wI));    // :91
     const float alphaSquared = mat[9] * mat[9];                 // :92

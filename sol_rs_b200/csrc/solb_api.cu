@@ -427,6 +427,7 @@ SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32
             memcpy(di.transform, si.transform, sizeof(di.transform));
             memcpy(di.transform_it, si.transform_it, sizeof(di.transform_it));
             memcpy(di.mat, &materials[sec.material_index], sizeof(di.mat));  // materials[gl_InstanceID]
+            di.mat[10] = 0.0f;  // MaterialInfo::padding1: libsolb's texture slot (solb_scene_set_textures)
             s->h_inst.push_back(di);
             s->n_tris += sec.n_indices / 3;
             s->h_first_tri.push_back(s->n_tris);
@@ -458,9 +459,18 @@ SOLB_API int solb_scene_create(solb_ctx *ctx, const SolbMeshDesc *meshes, uint32
     SOLB_CATCH(ctx)
 }
 
+static void free_textures(solb_scene *s) {
+    for (float4 *t : s->d_texels) cudaFree(t);
+    s->d_texels.clear();
+    cudaFree(s->d_tex);
+    s->d_tex = nullptr;
+    s->n_tex = 0;
+}
+
 SOLB_API int solb_scene_destroy(solb_scene *s) {
     if (!s) return SOLB_OK;
     if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
+    free_textures(s);
     cudaFree(s->d_vertices); cudaFree(s->d_indices); cudaFree(s->d_first_tri); cudaFree(s->d_inst); cudaFree(s->d_blas);
     cudaFree(s->d_shade);
     s->accel.release();
@@ -486,6 +496,71 @@ static int upload_instances(solb_scene *s) {
     if (ni) CU(ctx, cudaMemcpyAsync(s->d_inst, s->h_inst.data(), ni * sizeof(DeviceInstance), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SOLB_OK;
+}
+
+// sRGB electro-optical transfer function (IEC 61966-2-1), the decode glTF prescribes for base-colour textures
+static float srgb_to_linear(uint8_t c) {
+    const float x = (float)c / 255.0f;
+    return x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
+}
+
+SOLB_API int solb_scene_set_textures(solb_scene *s, const SolbTextureDesc *textures, uint32_t n_textures, const uint32_t *material_texture,
+                                     uint32_t n_materials) {
+    if (!s) return fail(nullptr, SOLB_ERR_INVALID, "null scene");
+    solb_ctx *ctx = s->ctx;
+    if (n_textures && !textures) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_set_textures: null texture array");
+    if (n_materials != s->materials.size()) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_set_textures: one texture index per material of the scene");
+    if (n_materials && !material_texture) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_set_textures: null material_texture");
+    for (uint32_t t = 0; t < n_textures; t++) {
+        const SolbTextureDesc &d = textures[t];
+        if (!d.rgba8 || d.width == 0 || d.height == 0 || d.width > 32768u || d.height > 32768u) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_set_textures: bad texture");
+        for (uint32_t wmode : { d.wrap_s, d.wrap_t })
+            if (wmode != 0u && wmode != 10497u && wmode != 33071u && wmode != 33648u) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_set_textures: unknown wrap mode");
+    }
+    for (uint32_t m = 0; m < n_materials; m++)
+        if (material_texture[m] != SOLB_NO_TEXTURE && material_texture[m] >= n_textures) return fail(ctx, SOLB_ERR_INVALID, "solb_scene_set_textures: texture index out of range");
+    SOLB_TRY
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // frames in flight may still sample the textures being replaced
+    free_textures(s);
+    float lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = srgb_to_linear((uint8_t)i);
+    std::vector<TexDesc> descs(n_textures);
+    std::vector<float> texels;
+    for (uint32_t t = 0; t < n_textures; t++) {
+        const SolbTextureDesc &d = textures[t];
+        const size_t n = (size_t)d.width * d.height;
+        texels.resize(n * 4);
+        for (size_t i = 0; i < n; i++) {
+            for (int c = 0; c < 3; c++) texels[4 * i + c] = d.srgb ? lut[d.rgba8[4 * i + c]] : (float)d.rgba8[4 * i + c] / 255.0f;
+            texels[4 * i + 3] = (float)d.rgba8[4 * i + 3] / 255.0f;
+        }
+        float4 *dev = nullptr;
+        CU(ctx, cudaMalloc((void **)&dev, n * sizeof(float4)));
+        s->d_texels.push_back(dev);
+        CU(ctx, cudaMemcpy(dev, texels.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+        descs[t].texels = dev;
+        descs[t].width = d.width;
+        descs[t].height = d.height;
+        descs[t].wrap_s = d.wrap_s ? d.wrap_s : 10497u;
+        descs[t].wrap_t = d.wrap_t ? d.wrap_t : 10497u;
+    }
+    if (n_textures) {
+        CU(ctx, cudaMalloc((void **)&s->d_tex, n_textures * sizeof(TexDesc)));
+        CU(ctx, cudaMemcpy(s->d_tex, descs.data(), n_textures * sizeof(TexDesc), cudaMemcpyHostToDevice));
+    }
+    s->n_tex = n_textures;
+    s->material_texture.assign(material_texture, material_texture + n_materials);
+    // SceneInstance::texture_offset (src/ray/mod.rs:20) finally means something: the texture of the instance's material
+    for (size_t i = 0; i < s->h_inst.size(); i++) {
+        const uint32_t m = s->h_inst[i].material;
+        const uint32_t tex = (n_textures && m < n_materials) ? material_texture[m] : SOLB_NO_TEXTURE;
+        s->instances[i].texture_offset = n_textures ? tex : 0u;  // no textures bound: the reference's default 0
+        const uint32_t t1 = tex == SOLB_NO_TEXTURE ? 0u : tex + 1u;
+        memcpy(&s->h_inst[i].mat[10], &t1, sizeof(t1));
+    }
+    return upload_instances(s);
+    SOLB_CATCH(ctx)
 }
 
 static int do_build(solb_scene *s) {
@@ -607,6 +682,12 @@ SOLB_API int solb_scene_add_instance(solb_scene *s, uint32_t source_instance, co
     memcpy(di.transform, si.transform, sizeof(di.transform));
     memcpy(di.transform_it, si.transform_it, sizeof(di.transform_it));
     memcpy(di.mat, &s->materials[material_index], sizeof(di.mat));
+    di.mat[10] = 0.0f;
+    if (material_index < s->material_texture.size() && s->material_texture[material_index] < s->n_tex) {
+        si.texture_offset = s->material_texture[material_index];
+        const uint32_t t1 = si.texture_offset + 1u;
+        memcpy(&di.mat[10], &t1, sizeof(t1));
+    } else if (s->n_tex) si.texture_offset = SOLB_NO_TEXTURE;
     s->instances.push_back(si);
     s->h_inst.push_back(di);
     s->n_tris += di.n_indices / 3;
@@ -934,6 +1015,7 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
     CU(ctx, cudaSetDevice(ctx->device));
     FrameConsts fc;
     fill_frame_consts(fc, u, accum->width, accum->height);
+    fc.texb = s->texb();
     fc.accum_start = params->accum_start_frame;
     fc.enable_sky = params->enable_sky;
     fc.spp = params->samples_per_frame;

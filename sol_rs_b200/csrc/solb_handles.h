@@ -94,6 +94,19 @@ struct solb_scene {
     DeviceInstance *d_inst = nullptr;
     DeviceBlas *d_blas = nullptr;
     ShadeRecord *d_shade = nullptr;
+    // base-colour textures (solb_scene_set_textures): linear float4 texels, one allocation per texture
+    std::vector<float4 *> d_texels;
+    TexDesc *d_tex = nullptr;
+    uint32_t n_tex = 0;
+    std::vector<uint32_t> material_texture;  // texture index per material (SOLB_NO_TEXTURE: none)
+    TexBinding texb() const {
+        TexBinding b;
+        b.tex = d_tex;
+        b.vertices = d_vertices;
+        b.indices = d_indices;
+        b.n_tex = n_tex;
+        return b;
+    }
     size_t inst_capacity = 0;                // instances d_inst / d_first_tri can hold
     AccelStorage accel;
     uint32_t accel_mode = SOLB_ACCEL_FLAT;

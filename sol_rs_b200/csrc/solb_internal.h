@@ -26,7 +26,8 @@ struct DeviceInstance {
     uint32_t shade_first_tri;  // DeviceBlas.first_tri of that geometry
     float transform[16];    // SceneInstance.transform (column-major)
     float transform_it[16]; // SceneInstance.transform_it = inverse().transpose()
-    float mat[12];          // MaterialInfo of materials[gl_InstanceID]: base @0, emissive @4, metallic @8, roughness @9
+    float mat[12];          // MaterialInfo of materials[gl_InstanceID]: base @0, emissive @4, metallic @8, roughness @9;
+                            // @10 (MaterialInfo::padding1) carries bits(texture index + 1), 0 = untextured (solb_scene_set_textures)
 };
 static_assert(sizeof(DeviceInstance) == 200, "DeviceInstance layout is mirrored by tests/emu_lib.py");
 
@@ -49,6 +50,24 @@ struct ShadeRecord {
 };
 static_assert(sizeof(ShadeRecord) == 112, "ShadeRecord must be 112 bytes");
 
+// Base-colour textures.  The reference reserves SceneInstance::texture_offset (src/ray/mod.rs:20,
+// pathtrace.rchit:31) and never reads it; solb_scene_set_textures gives it a meaning: the instance's albedo is multiplied by
+// a bilinear sample of texture `texture_offset` at the interpolated ModelVertex::uv.  Texels are linear-light float4 (sRGB
+// decoded on upload), rows top first (glTF: uv (0, 0) = top-left texel corner).  No textures bound (n_tex = 0): the
+// reference's shading, bit for bit.
+struct TexDesc {
+    const float4 *texels;
+    uint32_t width, height;
+    uint32_t wrap_s, wrap_t;  // glTF sampler codes: 10497 repeat, 33071 clamp to edge, 33648 mirrored repeat
+};
+static_assert(sizeof(TexDesc) == 24, "TexDesc");
+struct TexBinding {
+    const TexDesc *tex = nullptr;
+    const float4 *vertices = nullptr;    // ModelVertex array (4 x float4: pos, color, normal, uv), as the closest-hit shader reads it
+    const uint32_t *indices = nullptr;   // section-relative indices
+    uint32_t n_tex = 0, pad = 0;
+};
+
 // Per-launch constants: the parts of SceneUniforms the RT stages read (view_inverse,
 // projection_inverse, frame.z: pathtrace.rgen:13-21) + push constant + specialization constant +
 // the shader literals exposed as parameters (SolbTraceParams).
@@ -63,6 +82,7 @@ struct FrameConsts {
     uint32_t row_begin, band_rows, band_stride, n_bands;
     int32_t accum_start;
     uint32_t enable_sky, spp, max_bounces, accum_mode;
+    TexBinding texb;      // base-colour textures of the scene (n_tex = 0: none)
 };
 
 struct AccelStorage {

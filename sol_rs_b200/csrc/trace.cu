@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, (STATS || TL) ? 1 : 6) k_pathtrac
             if (h.inst != SOLB_MISS) {
                 nh++;
                 float3 hv;
-                const bool done = shade_hit(instances, shade, h.inst, h.gtri, h.u, h.v, r.o, r.d, rng, hv);
+                const bool done = shade_hit(instances, shade, fc.texb, h.inst, h.gtri, h.u, h.v, r.o, r.d, rng, hv);
                 depth++;
                 thr = thr * hv;  // :77
                 end_path = done;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, (STATS || TL) ? 1 : 6) k_pathtrac
             if (h.inst != SOLB_MISS) {
                 nh++;
                 float3 hv;
-                const bool done = shade_hit(instances, shade, h.inst, h.gtri, h.u, h.v, r.o, r.d, rng, hv);
+                const bool done = shade_hit(instances, shade, fc.texb, h.inst, h.gtri, h.u, h.v, r.o, r.d, rng, hv);
                 depth++;
                 thr = thr * hv;  // :77
                 end_path = done;
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const FrameConsts fc, const De
             if (h.x != SOLB_MISS) {
                 nh++;
                 float3 hv;
-                const bool done = shade_hit(instances, shade, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
+                const bool done = shade_hit(instances, shade, fc.texb, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
                 depth++;
                 thr = thr * hv;
                 end_path = done;
@@ -1130,7 +1130,7 @@ __device__ __forceinline__ uint32_t wl_shade_step(const FrameConsts *fcp, const 
         if (h.x != SOLB_MISS) {
             ctr[0]++;
             float3 hv;
-            const bool done = shade_hit(instances, shade, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
+            const bool done = shade_hit(instances, shade, fc.texb, h.x, h.y, __uint_as_float(h.z), __uint_as_float(h.w), o, d, rng, hv);
             depth++;
             thr = thr * hv;  // pathtrace.rgen:77
             end_path = done;

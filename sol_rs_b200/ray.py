@@ -23,10 +23,13 @@ class SceneDescription:
         self._lib = N.lib()
 
     @classmethod
-    def from_scene(cls, context, scene, accel_mode=N.ACCEL_FLAT, instancing=False):
+    def from_scene(cls, context, scene, accel_mode=N.ACCEL_FLAT, instancing=False, textures=False):
         """src/ray/mod.rs:50-57.  instancing=True (beyond the reference): every further glTF node that references
-        a mesh becomes one more instance of that mesh's BLASes (instance ids continue the running count)."""
+        a mesh becomes one more instance of that mesh's BLASes (instance ids continue the running count).  textures=True
+        (beyond the reference): bind the scene's base-colour textures (set_textures)."""
         sd = cls.from_meshes(context, scene.meshes, [m.transform for m in scene.meshes], scene.materials, accel_mode)
+        if textures and getattr(scene, "textures", None):
+            sd.set_textures(scene.textures, scene.material_textures)
         if instancing:
             first, added = 0, False
             for m in scene.meshes:
@@ -91,6 +94,20 @@ class SceneDescription:
         N.check(self._lib.solb_scene_add_instance(self._h, int(source_instance), t.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
                                                   int(material_index), ctypes.byref(out)), self.context.handle)
         return out.value
+
+    def set_textures(self, textures, material_textures):
+        """solb_scene_set_textures: textures = scene.Texture list (rgba8 rows top first, sRGB-encoded colour), material_textures
+        = per material a texture index or None.  Every instance's texture_offset (src/ray/mod.rs:20) becomes the texture of its
+        material and 5-pathtrace multiplies the albedo by a bilinear sample at the hit's uv.  An empty list unbinds."""
+        descs = (N.TextureDesc * max(len(textures), 1))()
+        keep = []
+        for i, t in enumerate(textures):
+            a = np.ascontiguousarray(t.rgba8, dtype=np.uint8)
+            keep.append(a)
+            descs[i] = N.TextureDesc(a.ctypes.data, a.shape[1], a.shape[0], int(t.wrap_s), int(t.wrap_t), 1, 0)
+        mt = np.array([N.NO_TEXTURE if t is None else int(t) for t in material_textures], dtype=np.uint32)
+        N.check(self._lib.solb_scene_set_textures(self._h, descs, len(textures), mt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(mt)),
+                self.context.handle)
 
     def set_accel_mode(self, mode):
         N.check(self._lib.solb_scene_set_accel_mode(self._h, int(mode)), self.context.handle)

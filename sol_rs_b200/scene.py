@@ -38,6 +38,13 @@ def hostlib():
         H.solh_scene_materials.restype = vp
         H.solh_scene_materials.argtypes = [vp]
         H.solh_scene_has_camera.argtypes = [vp]
+        H.solh_scene_texture_count.restype = u32
+        H.solh_scene_texture_count.argtypes = [vp]
+        H.solh_scene_texture.restype = vp
+        H.solh_scene_texture.argtypes = [vp, u32, ctypes.POINTER(u32)]
+        H.solh_scene_material_textures.restype = vp
+        H.solh_scene_material_textures.argtypes = [vp]
+        H.solh_decode_png.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(u32), ctypes.POINTER(u32), vp, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
         H.solh_mesh_info.argtypes = [vp, u32, ctypes.POINTER(_MeshInfo)]
         H.solh_mesh_sections.argtypes = [vp, u32, ctypes.POINTER(N.Section)]
         H.solh_mesh_extra_instance_count.restype = u32
@@ -141,13 +148,38 @@ def scene_uniforms(camera, width, height, frame):
     return u
 
 
-class Scene:
-    """src/scene/mod.rs:99-104"""
+class Texture:
+    """Base-colour texture of a glTF material (the reference's load_scene reads no images): rgba8 [h, w, 4], rows
+    top first, with the sampler's wrap modes (glTF codes, 10497 = REPEAT)."""
 
-    def __init__(self, meshes, materials, camera=None):
+    def __init__(self, rgba8, wrap_s=10497, wrap_t=10497):
+        self.rgba8 = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        assert self.rgba8.ndim == 3 and self.rgba8.shape[2] == 4
+        self.wrap_s, self.wrap_t = int(wrap_s), int(wrap_t)
+
+
+class Scene:
+    """src/scene/mod.rs:99-104 (+ textures / material_textures, beyond the reference: bound with
+    SceneDescription.set_textures or from_scene(..., textures=True); nothing samples them otherwise)"""
+
+    def __init__(self, meshes, materials, camera=None, textures=(), material_textures=None):
         self.meshes = list(meshes)
         self.materials = np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 12)  # MaterialInfo rows
         self.camera = camera
+        self.textures = list(textures)
+        self.material_textures = [None] * len(self.materials) if material_textures is None else list(material_textures)
+
+
+def decode_png(data):
+    """sol::image::decode_png (csrc/host/png.cpp) -> uint8 [h, w, 4]"""
+    H = hostlib()
+    buf = (ctypes.c_uint8 * len(data)).from_buffer_copy(data)
+    w, h, err = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.create_string_buffer(256)
+    if H.solh_decode_png(buf, len(data), ctypes.byref(w), ctypes.byref(h), None, 0, err, len(err)) != 0:
+        raise N.SolbError(-1, err.value.decode("utf-8", "replace"))
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+    H.solh_decode_png(buf, len(data), ctypes.byref(w), ctypes.byref(h), out.ctypes.data_as(ctypes.c_void_p), out.nbytes, err, len(err))
+    return out
 
 
 def load_scene(context, filepath):
@@ -182,6 +214,13 @@ def load_scene(context, filepath):
         mats = np.ctypeslib.as_array(ctypes.cast(H.solh_scene_materials(h), ctypes.POINTER(ctypes.c_float)),
                                      shape=(nm, 12)).copy() if nm else np.zeros((0, 12), np.float32)
         cam = Camera(_handle=H.solh_camera_from_scene(h)) if H.solh_scene_has_camera(h) else None
-        return Scene(meshes, mats, cam)
+        textures = []
+        for i in range(H.solh_scene_texture_count(h)):
+            info = (ctypes.c_uint32 * 4)()
+            px = H.solh_scene_texture(h, i, info)
+            rgba = np.ctypeslib.as_array(ctypes.cast(px, ctypes.POINTER(ctypes.c_uint8)), shape=(info[1], info[0], 4)).copy()
+            textures.append(Texture(rgba, info[2], info[3]))
+        mt = np.ctypeslib.as_array(ctypes.cast(H.solh_scene_material_textures(h), ctypes.POINTER(ctypes.c_uint32)), shape=(nm,)).copy() if nm else []
+        return Scene(meshes, mats, cam, textures, [None if int(t) == N.NO_TEXTURE else int(t) for t in mt])
     finally:
         H.solh_scene_free(h)

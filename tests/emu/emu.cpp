@@ -429,7 +429,7 @@ void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_
                 if (hit.inst != SOLB_MISS) {
                     nhits++;
                     float3 hv;
-                    const bool done = shade_hit(s->inst.data(), s->shade.data(), hit.inst, hit.gtri, hit.u, hit.v, r.o, r.d, rng, hv);
+                    const bool done = shade_hit(s->inst.data(), s->shade.data(), fc.texb, hit.inst, hit.gtri, hit.u, hit.v, r.o, r.d, rng, hv);
                     depth++;
                     thr = thr * hv;
                     end_path = done;

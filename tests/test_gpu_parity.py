@@ -1273,3 +1273,94 @@ def test_frames_in_flight_fences_and_async_readback(sol, ctx):
     for f in range(frames):
         assert np.array_equal(got[f], blocking[f]), f
     assert np.array_equal(accum.readback(), accum2.readback())
+
+
+# ---- base-colour textures (an extension shared with the oracle, the reference samples none) ------------------
+
+@pytest.mark.parametrize("schedule", [0, 1, 3])
+def test_textured_duck_vs_oracle(sol, ctx, schedule):
+    """Duck.gltf with DuckCM.png bound (solb_scene_set_textures): frames agree with the oracle carrying the same extension;
+    texture_offset (src/ray/mod.rs:20) reports the material's texture; unbinding restores the untextured frame bit for bit."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    w, h, mb = 160, 120, 8
+    sc = scene.load_scene(ctx, model_path("Duck"))
+    assert len(sc.textures) == 1 and sc.material_textures == [0] and sc.textures[0].rgba8.shape == (512, 512, 4)
+    sd = ray.SceneDescription.from_scene(ctx, sc)
+    cam = product_camera(sc, "Duck", w, h)
+    sbt = pathtrace_pipeline(ctx, True)
+
+    def render():
+        accum, rend = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F), sol.Image2d(ctx, w, h, N.FORMAT_RGBA8)
+        for f in range(2):
+            sbt.cmd_trace_rays(ray.TraceBindings(sd, scene.scene_uniforms(cam, w, h, f), accum, rend, samples_per_frame=8, max_bounces=mb,
+                                                 schedule=schedule), (w, h, 1))
+        return accum.readback(), rend.readback()
+
+    plain, _ = render()
+    assert all(i.texture_offset == 0 for i in sd.instances())  # nothing bound: the reference's default
+    sd.set_textures(sc.textures, sc.material_textures)
+    assert [i.texture_offset for i in sd.instances()] == [0] * len(sd.instances())
+    g_acc, g_rgba = render()
+    fs, osc = oracle_scene("Duck")
+    assert np.array_equal(fs.textures[0][0], sc.textures[0].rgba8) and fs.material_textures == [0]
+    osc.set_textures(fs.textures, fs.material_textures)
+    ocm = oracle_camera(fs, "Duck", w, h)
+    o_acc = np.zeros((h, w, 4), dtype=np.float32)
+    for f in range(2):
+        o_rgba, _ = osc.pathtrace_frame(ocam.scene_uniforms(ocm, w, h, f), w, h, o_acc, 0, True, 8, mb, oracle.OrcStats())
+    d = np.abs(g_acc[..., :3] - o_acc[..., :3])
+    assert (d.max(axis=2) > 1e-3 * (1.0 + np.abs(o_acc[..., :3]).max(axis=2))).mean() < 0.02
+    assert image_metrics(g_acc, o_acc)[0] < 0.01
+    assert (np.abs(g_rgba.astype(np.int32) - o_rgba.astype(np.int32)).max(axis=2) > 1).mean() < 0.02
+    # the texture did something (the duck is yellow, not white), on the duck's pixels only
+    changed = np.abs(g_acc[..., :3] - plain[..., :3]).max(axis=2) > 1e-3
+    assert 0.05 < changed.mean() < 0.9
+    assert g_acc[changed][:, 2].mean() < 0.7 * plain[changed][:, 2].mean()
+    sd.set_textures([], [None] * len(sc.material_textures))
+    again, _ = render()
+    assert np.array_equal(again, plain)
+
+
+@pytest.mark.parametrize("wrap", [10497, 33071, 33648])
+def test_texture_sampling_and_wrap_modes_vs_oracle(sol, ctx, wrap):
+    """A quad whose uv run from -1.3 to 2.4 under a 5 x 3 random texture: bilinear taps, texel-centre convention, the three glTF
+    wrap modes and the sRGB decode, against the oracle's restatement (primary hit x sky: one bounce)."""
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import ray, scene
+
+    w, h = 192, 128
+    rng = np.random.default_rng(wrap)
+    tex = rng.integers(0, 256, size=(3, 5, 4), dtype=np.uint8)
+    v = np.zeros((4, 16), dtype=np.float32)
+    for k, (x, y) in enumerate([(-1, -1), (1, -1), (1, 1), (-1, 1)]):
+        v[k, 0:4] = (x, y, 0, 1)
+        v[k, 4:8] = (1, 1, 1, 1)
+        v[k, 8:12] = (0, 0, 1, 1)
+        v[k, 12:14] = (-1.3 + 3.7 * (x + 1) / 2, -0.8 + 2.9 * (y + 1) / 2)
+    mesh = scene.Mesh("quad", v, np.array([0, 1, 2, 0, 2, 3], dtype=np.uint32), np.eye(4, dtype=np.float32).reshape(16),
+                      [scene.PrimitiveSection(0, 0, 4, 0, 6, 0)])
+    mats = np.array([[1, 1, 1, 1, 0, 0, 0, 0, 0.0, 1.0, 0, 0]], dtype=np.float32)
+    sc = scene.Scene([mesh], mats, None, [scene.Texture(tex, wrap, wrap)], [0])
+    sd = ray.SceneDescription.from_scene(ctx, sc, textures=True)
+    cam = scene.Camera((w, h))
+    cam.look_at((0.3, 0.2, 3.0), (0, 0, 0), (0, -1, 0))
+    accum = sol.Image2d(ctx, w, h, N.FORMAT_RGBA32F)
+    u = scene.scene_uniforms(cam, w, h, 0)
+    pathtrace_pipeline(ctx, True).cmd_trace_rays(ray.TraceBindings(sd, u, accum, None, samples_per_frame=8, max_bounces=1), (w, h, 1))
+    g = accum.readback()
+    fs = flat_from_product_scene(sc)
+    osc = oracle.Scene(fs)
+    osc.set_textures([(tex, wrap, wrap)], [0])
+    ref = np.zeros((h, w, 4), dtype=np.float32)
+    osc.pathtrace_frame(bytes(u), w, h, ref, 0, True, 8, 1, oracle.OrcStats())
+    d = np.abs(g[..., :3] - ref[..., :3])
+    assert (d.max(axis=2) > 1e-4 * (1.0 + np.abs(ref[..., :3]).max(axis=2))).mean() < 0.005
+    assert image_metrics(g, ref)[0] < 1e-3
+    # and the oracle's sampler is what the header says: texel centres at (i + 0.5) / n, sRGB decode, wrap
+    lin = lambda c: np.where(c / 255.0 <= 0.04045, c / 255.0 / 12.92, ((c / 255.0 + 0.055) / 1.055) ** 2.4)
+    np.testing.assert_allclose(osc.sample_texture(0, 1.5 / 5, 2.5 / 3), lin(tex[2, 1, :3].astype(np.float64)), rtol=1e-5, atol=1e-6)
+    edge = osc.sample_texture(0, 1.0, 0.5 / 3)  # u = 1: between the last and (repeat) the first / (clamp, mirror) the last texel
+    want = 0.5 * (lin(tex[0, 4, :3].astype(np.float64)) + lin(tex[0, 0 if wrap == 10497 else 4, :3].astype(np.float64)))
+    np.testing.assert_allclose(edge, want, rtol=1e-5, atol=1e-6)

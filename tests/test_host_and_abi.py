@@ -327,3 +327,133 @@ def test_loaders_handle_snorm_zero_filled_and_percent_encoded_uris(tmp_path):
     np.testing.assert_array_equal(v[:, 8:11], np.array([[0, 0, 1], [0, 1, 0], [-1, 0, 0]], dtype=np.float32))  # -128 clamps to -1
     assert np.all(v[:, 12:14] == 0.0) and np.array_equal(v[:, 0:3], pos)
     assert struct.calcsize("f") == 4
+
+
+def _encode_png(img, ctype, depth, filt, level, palette=None, trns=None):
+    """minimal PNG writer for the decoder tests: img [h, w, channels] of uint8 / uint16 samples, one filter type for all rows"""
+    import struct
+    import zlib
+
+    h, w, ch = img.shape
+    raw = img.astype(">u2").tobytes() if depth == 16 else img.astype(np.uint8).tobytes()
+    bpp = ch * depth // 8
+    stride = w * bpp
+    rows = np.frombuffer(raw, dtype=np.uint8).reshape(h, stride).astype(np.int32)
+    out = bytearray()
+    prev = np.zeros(stride, dtype=np.int32)
+    for y in range(h):
+        cur = rows[y]
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]]) if stride > bpp else np.zeros(stride, np.int32)
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]]) if stride > bpp else np.zeros(stride, np.int32)
+        if filt == 0:
+            pred = np.zeros(stride, np.int32)
+        elif filt == 1:
+            pred = a
+        elif filt == 2:
+            pred = prev
+        elif filt == 3:
+            pred = (a + prev) >> 1
+        else:
+            p = a + prev - c
+            pa, pb, pc = np.abs(p - a), np.abs(p - prev), np.abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+        out.append(filt)
+        out += ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if palette is not None:
+        png += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    if trns is not None:
+        png += chunk(b"tRNS", trns.astype(np.uint8).tobytes())
+    comp = zlib.compress(bytes(out), level)
+    half = len(comp) // 2
+    return png + chunk(b"IDAT", comp[:half]) + chunk(b"IDAT", comp[half:]) + chunk(b"IEND", b"")
+
+
+def test_png_decoder_all_colour_types_filters_and_block_types():
+    """sol::image::decode_png (csrc/host/png.cpp: own inflate) against the oracle loader's decoder (Python zlib) and against the
+    pixels that went in: every colour type at 8 and 16 bits, every row filter, stored / fixed / dynamic deflate blocks, IDAT
+    split over two chunks; plus the two PNGs the repo ships."""
+    from oracle import gltf_flatten as gf
+    from sol_rs_b200 import _native as N
+    from sol_rs_b200 import scene
+
+    rng = np.random.default_rng(3)
+    w, h = 13, 7
+    n = 0
+    for ctype, ch in ((0, 1), (2, 3), (3, 1), (4, 2), (6, 4)):
+        for depth in ((8,) if ctype == 3 else (8, 16)):
+            for filt in range(5):
+                for level in (0, 1, 9):
+                    smooth = (np.add.outer(np.arange(h) * 9, np.arange(w) * 5)[..., None] + np.arange(ch) * 40) % (1 << depth)
+                    img = smooth if level == 9 else rng.integers(0, 1 << depth, size=(h, w, ch))
+                    pal = rng.integers(0, 256, size=(256, 3)) if ctype == 3 else None
+                    trns = rng.integers(0, 256, size=(200,)) if ctype == 3 else None
+                    if ctype == 3:
+                        img = img % 256
+                    data = _encode_png(img, ctype, depth, filt, level, pal, trns)
+                    got = scene.decode_png(data)
+                    assert np.array_equal(got, gf.decode_png(data)), (ctype, depth, filt, level)
+                    s8 = ((img.astype(np.uint32) + 128) // 257 if depth == 16 else img).astype(np.uint8)
+                    want = np.full((h, w, 4), 255, dtype=np.uint8)
+                    if ctype == 0:
+                        want[..., :3] = s8[..., :1]
+                    elif ctype == 2:
+                        want[..., :3] = s8
+                    elif ctype == 4:
+                        want[..., :3], want[..., 3] = s8[..., :1], s8[..., 1]
+                    elif ctype == 6:
+                        want[...] = s8
+                    else:
+                        want[..., :3] = pal[s8[..., 0]]
+                        want[..., 3] = np.concatenate([trns, np.full(56, 255)])[s8[..., 0]]
+                    assert np.array_equal(got, want), (ctype, depth, filt, level)
+                    n += 1
+    assert n == 135
+    for f in (os.path.join(ROOT, "assets", "models", "DuckCM.png"), os.path.join(ROOT, "assets", "textures", "HDR_RGBA_0.png")):
+        data = open(f, "rb").read()
+        assert np.array_equal(scene.decode_png(data), gf.decode_png(data))
+    with pytest.raises(N.SolbError):
+        scene.decode_png(b"\x89PNG\r\n\x1a\n" + b"\x00" * 40)
+    with pytest.raises(N.SolbError):
+        scene.decode_png(data[: len(data) // 2])
+
+
+def test_loaders_agree_on_base_colour_textures(tmp_path):
+    """Duck.gltf names DuckCM.png as its material's baseColorTexture: both loaders decode the same pixels, wrap modes and
+    material -> texture table; a material whose image is missing or not a PNG simply stays untextured (the reference loads no
+    images at all); scenes without textures report none."""
+    import json
+    import shutil
+
+    from oracle import gltf_flatten as gf
+    from sol_rs_b200 import scene
+
+    duck = os.path.join(ROOT, "assets", "models", "Duck.gltf")
+    sc, fs = scene.load_scene(None, duck), gf.load_scene(duck)
+    assert len(sc.textures) == len(fs.textures) == 1 and sc.material_textures == fs.material_textures == [0]
+    assert np.array_equal(sc.textures[0].rgba8, fs.textures[0][0]) and (sc.textures[0].wrap_s, sc.textures[0].wrap_t) == fs.textures[0][1:]
+    assert sc.textures[0].rgba8.shape == (512, 512, 4) and sc.textures[0].rgba8[..., 3].min() == 255
+    for name in ("cornell", "tunnel"):
+        p = os.path.join(ROOT, "assets", "models", name + ".gltf")
+        a, b = scene.load_scene(None, p), gf.load_scene(p)
+        assert a.textures == [] and b.textures == [] and all(t is None for t in a.material_textures + b.material_textures)
+    # clamp / mirror samplers, an embedded (data URI) image, a second material sharing the texture, one with a broken image
+    doc = json.load(open(duck))
+    import base64
+    doc["images"] = [{"uri": "data:image/png;base64," + base64.b64encode(open(os.path.join(ROOT, "assets", "models", "DuckCM.png"), "rb").read()).decode()},
+                     {"uri": "missing.png"}]
+    doc["samplers"] = [{"wrapS": 33071, "wrapT": 33648}]
+    doc["textures"] = [{"sampler": 0, "source": 0}, {"source": 1}]
+    doc["materials"] = [doc["materials"][0], {"pbrMetallicRoughness": {"baseColorTexture": {"index": 1}}},
+                        {"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}, {"pbrMetallicRoughness": {"baseColorTexture": {"index": 0, "texCoord": 1}}}]
+    shutil.copy(os.path.join(ROOT, "assets", "models", "Duck0.bin"), tmp_path / "Duck0.bin")
+    json.dump(doc, open(tmp_path / "d.gltf", "w"))
+    a, b = scene.load_scene(None, str(tmp_path / "d.gltf")), gf.load_scene(str(tmp_path / "d.gltf"))
+    assert a.material_textures == b.material_textures == [0, None, 0, None]
+    assert len(a.textures) == len(b.textures) == 1 and np.array_equal(a.textures[0].rgba8, b.textures[0][0])
+    assert (a.textures[0].wrap_s, a.textures[0].wrap_t) == b.textures[0][1:] == (33071, 33648)
