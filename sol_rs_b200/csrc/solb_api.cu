@@ -91,6 +91,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->tune.wl_starve_idle = env_int("SOLB_WL_STARVE_IDLE", c->tune.wl_starve_idle, 1, 32);
         c->tune.wl_gen_min = env_int("SOLB_WL_GEN_MIN", c->tune.wl_gen_min, 1, WL_POOL);
         c->tune.wl_batch = env_int("SOLB_WL_BATCH", c->tune.wl_batch, 32, 1024) & ~31;
+        c->tune.wl_region_slots_per_warp = env_int("SOLB_WL_REGION_SLOTS", c->tune.wl_region_slots_per_warp, 32, 4096);
         c->tune.wl_warps_per_sm = env_int("SOLB_WL_WARPS_PER_SM", c->tune.wl_warps_per_sm, 0, 64);
         c->use_hi_stream = env_int("SOLB_HI_STREAM", c->use_hi_stream, 0, 1);
         c->tune.wl_frames_in_flight = env_int("SOLB_WL_FRAMES_IN_FLIGHT", c->tune.wl_frames_in_flight, 1, WL_MAX_FRAMES);
@@ -195,6 +196,7 @@ SOLB_API int solb_synchronize(solb_ctx *ctx) {
     if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->p2p_err_host && *ctx->p2p_err_host) return fail(ctx, SOLB_ERR_CUDA, "a peer did not deliver its bands within 20 s (solb_allgather_rows)");
     return SOLB_OK;
 }
 

@@ -1748,7 +1748,7 @@ cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, c
     // ~72 slots to keep 32 lanes tracing while 32 finished rays wait for a full-width shade step; with every resident warp
     // holding 56 pixels (1/8 of a 1080p frame over 8 CTAs per SM) the shade steps ran partial and the share took 6.2 ms, with
     // 6 CTAs per SM (72 slots each) 4.9 ms (tools/tile_time.py, profiles/r02_tile_split.txt).
-    const uint32_t want_warps = std::min<uint32_t>(std::min(warpfront_grid_warps(sm_count, tune), wl.n_warps), std::max<uint32_t>(1u, n_slots / 72u));
+    const uint32_t want_warps = std::min<uint32_t>(std::min(warpfront_grid_warps(sm_count, tune), wl.n_warps), std::max<uint32_t>(1u, n_slots / (uint32_t)std::max(tune.wl_region_slots_per_warp, 32)));
     const uint32_t grid = (want_warps + WL_BLOCK / 32 - 1) / (WL_BLOCK / 32);
     // pixels a warp holds at a time: its even share of the region, between one warp-width and the full pool
     const uint32_t share = (n_slots + want_warps - 1) / want_warps;

@@ -60,6 +60,7 @@ struct TraceTuning {
     int mega_fetch_idle = 8;   // refill finished lanes once this many are idle
     // warp-local wavefront schedule (k_pt_warpfront)
     int wl_ctas_per_sm = 8;    // persistent warps per SM in units of four (64 registers -> 8 x 128 threads)
+    int wl_region_slots_per_warp = 72;  // small regions: launch n_slots / this many warps (see launch_pathtrace_warpfront)
     int wl_warps_per_sm = 0;   // > 0: persistent warps per SM, overrides wl_ctas_per_sm (one warp per CTA since round 2)
     int wl_fetch_idle = 20;    // hand ready rays to idle lanes once this many lanes are idle (round-2 final build, frames in flight:
                                // 16: 4 508, 20: 4 539, 24: 4 470 Mrays/s, profiles/r02_sweep_warpfront_knobs.txt)
