@@ -4,7 +4,7 @@
 //!   cargo run --release --example pathtrace_offscreen -- assets/models/tunnel.gltf --sky 64 out.png
 use sol::glam::{uvec3, vec2};
 use sol::ray::{self, TraceBindings};
-use sol::{scene, Context, Image2d, ImageFormat, ImageInfo, SceneUniforms};
+use sol::{scene, Context, Fence, HostBuffer, Image2d, ImageFormat, ImageInfo, SceneUniforms};
 use std::path::PathBuf;
 
 fn main() {
@@ -34,17 +34,27 @@ fn main() {
     );
     let sbt = ray::ShaderBindingTable::new(context.clone(), pipeline.handle(), ray::ShaderBindingTableInfo::default().raygen(0).miss(1).hitgroup(2));
 
-    // render(): examples/5-pathtrace.rs:294-369, once per frame
+    // render(): examples/5-pathtrace.rs:294-369, once per frame.  Two frames in flight like the reference's renderer (one fence
+    // per swapchain image, src/renderer.rs:72-81, 188): frame f's blit (here: the copy into a page-locked host buffer)
+    // overlaps frame f + 1's tracing, and a slot's buffer is touched again only after its fence.
+    let fences = [Fence::new(context.clone()), Fence::new(context.clone())];
+    let mut present = [HostBuffer::new(context.clone(), render_target.size_bytes()), HostBuffer::new(context.clone(), render_target.size_bytes())];
     for frame in 0..frames {
+        let slot = (frame & 1) as usize;
+        fences[slot].wait(); // wait_for_and_reset_fence
         let uniforms = SceneUniforms::from(&camera, uvec3(width, height, frame));
         scene_description.tlas_regenerate(());
         let mut bindings = TraceBindings::new(&scene_description, &uniforms);
         bindings.accum_target = Some(&accum_target);
         bindings.render_target = Some(&render_target);
         sbt.cmd_trace_rays(&bindings, (width, height, 1));
+        render_target.readback_async(&mut present[slot]); // replaces cmd_blit_to(present image)
+        fences[slot].signal(); // queue_submit(.., in_flight_fence)
     }
-    let mut pixels = vec![0u8; render_target.size_bytes()];
-    render_target.readback(&mut pixels); // replaces cmd_blit_to(present image)
+    let last = ((frames.max(1) - 1) & 1) as usize;
+    fences[0].wait();
+    fences[1].wait();
+    let pixels = present[last].as_slice().to_vec();
     let stats = context.stats();
     println!("{} frames, {} rays, {} kernel launches", frames, stats.rays, stats.kernel_launches);
     image::save_buffer(&out, &pixels, width, height, image::ColorType::Rgba8).unwrap();
