@@ -28,6 +28,67 @@ def write_png(path, rgba8):
         f.write(chunk(b"IEND", b""))
 
 
+def write_exr(path, rgba32f, channels="RGB"):
+    """float32 [h, w, >= len(channels)] -> OpenEXR 2 scan-line file, uncompressed, 32-bit float channels (the accumulation
+    target keeps linear radiance: SURVEY 8f item 2 names EXR for it).  No external dependency: magic, version 2, the eight
+    required attributes, the scan-line offset table, then per line (y, byte count, channels in alphabetical order)."""
+    a = np.ascontiguousarray(rgba32f, dtype=np.float32)
+    assert a.ndim == 3 and a.shape[2] >= len(channels)
+    h, w = a.shape[:2]
+    names = sorted(channels)  # the file stores channels alphabetically
+    src = {c: "RGBA".index(c) for c in names}
+
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+
+    chlist = b"".join(c.encode() + b"\0" + struct.pack("<iBxxxii", 2, 0, 1, 1) for c in names) + b"\0"  # 2 = FLOAT
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    header = (struct.pack("<ii", 20000630, 2) + attr("channels", "chlist", chlist) + attr("compression", "compression", b"\0")
+              + attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0")
+              + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + attr("screenWindowCenter", "v2f", struct.pack("<ff", 0.0, 0.0))
+              + attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+    line_bytes = len(names) * w * 4
+    first = len(header) + 8 * h
+    with open(path, "wb") as f:
+        f.write(header)
+        f.write(struct.pack("<%dq" % h, *[first + y * (8 + line_bytes) for y in range(h)]))
+        for y in range(h):
+            f.write(struct.pack("<ii", y, line_bytes))
+            for c in names:
+                f.write(a[y, :, src[c]].astype("<f4").tobytes())
+
+
+def read_exr(path):
+    """the files write_exr makes (uncompressed float scan lines) -> (float32 [h, w, n], channel names); for tests / resuming"""
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<i", raw, 0)[0] == 20000630
+    off, attrs = 8, {}
+    while raw[off] != 0:
+        e = raw.index(b"\0", off)
+        name = raw[off:e].decode()
+        e2 = raw.index(b"\0", e + 1)
+        n = struct.unpack_from("<i", raw, e2 + 1)[0]
+        attrs[name] = raw[e2 + 5: e2 + 5 + n]
+        off = e2 + 5 + n
+    off += 1
+    x0, y0, x1, y1 = struct.unpack("<iiii", attrs["dataWindow"])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    assert attrs["compression"] == b"\0"
+    names, p = [], 0
+    ch = attrs["channels"]
+    while ch[p] != 0:
+        e = ch.index(b"\0", p)
+        names.append(ch[p:e].decode())
+        assert struct.unpack_from("<i", ch, e + 1)[0] == 2
+        p = e + 17
+    offs = struct.unpack_from("<%dq" % h, raw, off)
+    out = np.zeros((h, w, len(names)), dtype=np.float32)
+    for y in range(h):
+        yy, nb = struct.unpack_from("<ii", raw, offs[y])
+        out[yy - y0] = np.frombuffer(raw, dtype="<f4", count=len(names) * w, offset=offs[y] + 8).reshape(len(names), w).T
+    return out, names
+
+
 def write_ppm(path, rgba8):
     a = np.ascontiguousarray(rgba8, dtype=np.uint8)
     with open(path, "wb") as f:

@@ -457,3 +457,26 @@ def test_loaders_agree_on_base_colour_textures(tmp_path):
     assert a.material_textures == b.material_textures == [0, None, 0, None]
     assert len(a.textures) == len(b.textures) == 1 and np.array_equal(a.textures[0].rgba8, b.textures[0][0])
     assert (a.textures[0].wrap_s, a.textures[0].wrap_t) == b.textures[0][1:] == (33071, 33648)
+
+
+def test_exr_writer_round_trip_and_independent_reader(tmp_path):
+    """sol_rs_b200.io.write_exr (EXR dump of the float accumulation target): bit-exact round trip through the
+    module's own reader and, where OpenCV was built with OpenEXR, through an independent decoder."""
+    from sol_rs_b200 import io as sio
+
+    a = np.random.default_rng(7).normal(scale=50.0, size=(9, 17, 4)).astype(np.float32)
+    a[0, 0, :3] = (0.0, np.float32(1e-30), np.float32(6.5e4))
+    for channels in ("RGB", "RGBA"):
+        p = str(tmp_path / ("t_%s.exr" % channels))
+        sio.write_exr(p, a, channels)
+        b, names = sio.read_exr(p)
+        assert names == sorted(channels)
+        assert np.array_equal(b, a[..., ["RGBA".index(c) for c in names]])
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    try:
+        import cv2
+    except ImportError:
+        return
+    im = cv2.imread(str(tmp_path / "t_RGB.exr"), cv2.IMREAD_UNCHANGED)
+    if im is not None:  # (None: this OpenCV build has no OpenEXR codec)
+        assert np.array_equal(im, a[..., [2, 1, 0]])
