@@ -88,6 +88,7 @@ SOLB_API int solb_ctx_create(int device, void *stream, solb_ctx **out) {
         c->auto_wide_schedule = env_int("SOLB_AUTO_SCHEDULE", (int)c->auto_wide_schedule, 0, 3) == 0 ? SOLB_SCHEDULE_WAVEFRONT : SOLB_SCHEDULE_WARPFRONT;
         c->tune.wl_ctas_per_sm = env_int("SOLB_WL_CTAS_PER_SM", c->tune.wl_ctas_per_sm, 1, 16);
         c->tune.wl_fetch_idle = env_int("SOLB_WL_FETCH_IDLE", c->tune.wl_fetch_idle, 1, 32);
+        c->tune.wl_fetch_idle_large = env_int("SOLB_WL_FETCH_IDLE_LARGE", c->tune.wl_fetch_idle_large, 1, 32);
         c->tune.wl_starve_idle = env_int("SOLB_WL_STARVE_IDLE", c->tune.wl_starve_idle, 1, 32);
         c->tune.wl_gen_min = env_int("SOLB_WL_GEN_MIN", c->tune.wl_gen_min, 1, WL_POOL);
         c->tune.wl_batch = env_int("SOLB_WL_BATCH", c->tune.wl_batch, 32, 1024) & ~31;

@@ -1754,7 +1754,9 @@ cudaError_t launch_pathtrace_warpfront(cudaStream_t st, const FrameConsts &fc, c
     const uint32_t share = (n_slots + want_warps - 1) / want_warps;
     const uint32_t pool_limit = std::min<uint32_t>((uint32_t)WL_POOL, std::max<uint32_t>(32u, (share + 7u) & ~7u));
     const float4 *il = as.inst_leaves_f4();
-#define SOLB_WLF(S, T) k_pt_warpfront<S, T><<<grid, WL_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, wl, frame_sum, stats, n_slots, pool_limit, tune)
+    TraceTuning tn = tune;
+    if ((size_t)as.n_wide * sizeof(Node8) + (size_t)as.n_tris * sizeof(Tri48) > ((size_t)64 << 20)) tn.wl_fetch_idle = tune.wl_fetch_idle_large;
+#define SOLB_WLF(S, T) k_pt_warpfront<S, T><<<grid, WL_BLOCK, 0, st>>>(fc, as.nodes_u4(), as.tris_f4(), T ? il : nullptr, instances, shade, wl, frame_sum, stats, n_slots, pool_limit, tn)
     if (as.two_level) { if (collect) SOLB_WLF(true, true); else SOLB_WLF(false, true); }
     else { if (collect) SOLB_WLF(true, false); else SOLB_WLF(false, false); }
 #undef SOLB_WLF

@@ -64,6 +64,9 @@ struct TraceTuning {
     int wl_warps_per_sm = 0;   // > 0: persistent warps per SM, overrides wl_ctas_per_sm (one warp per CTA since round 2)
     int wl_fetch_idle = 20;    // hand ready rays to idle lanes once this many lanes are idle (round-2 final build, frames in flight:
                                // 16: 4 508, 20: 4 539, 24: 4 470 Mrays/s, profiles/r02_sweep_warpfront_knobs.txt)
+    int wl_fetch_idle_large = 8;  // ... when the hierarchy does not fit the caches (> 64 MB of nodes + triangles): the traversal waits on
+                                  // memory, not on issue slots, and more rays in flight win: 20 M-triangle scene 1 557 (20) / 1 583 (12) /
+                                  // 1 605 (8) Mrays/s, profiles/r02_sweep_warpfront_knobs.txt
     int wl_starve_idle = 16;   // partial (< 32 slots) shade / generate steps only once this many lanes are idle and nothing is ready
     int wl_gen_min = 32;       // start new pixels once this many of a warp's slots are free (or its lanes starve): a full-width generate step
     int wl_frames_in_flight = 3;  // > 1: the kernel of frame f + 1 starts while frame f drains (they share nothing: each writes its
