@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(32) k_p2p_wait(const uint32_t *flags, uint32_t
         while ((int32_t)(*(volatile const uint32_t *)(flags + r) - seq) < 0) {
             __nanosleep(200);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) { *(volatile int *)err = 1; break; }  // 20 s: a peer died; reported by the next call
+            if (t1 - t0 > 600000000000ull) { *(volatile int *)err = 1; break; }  // 10 min: a peer died; reported by the next call
         }
     }
     __threadfence_system();
@@ -340,7 +340,7 @@ SOLB_API int solb_allgather_rows(solb_ctx *ctx, solb_target *target, uint32_t ba
     const uint32_t bands_per_rank = (n_bands + world - 1) / world;
     const size_t chunk_bytes = (size_t)bands_per_rank * band_rows * row_bytes;
     const uint32_t row_elems = (uint32_t)(row_bytes / 16);
-    if (ctx->p2p_err_host && *ctx->p2p_err_host) return fail(ctx, SOLB_ERR_CUDA, "solb_allgather_rows: a peer did not deliver its bands within 20 s");
+    if (ctx->p2p_err_host && *ctx->p2p_err_host) return fail(ctx, SOLB_ERR_CUDA, "solb_allgather_rows: a peer did not deliver its bands within 10 min");
     static const bool want_p2p = !(getenv("SOLB_P2P") && atoi(getenv("SOLB_P2P")) == 0);
     if (want_p2p && (ctx->p2p_state == 0 || (ctx->p2p_state == 1 && ctx->p2p_chunk_bytes < chunk_bytes))) {
         // sized for 16-byte texels at once: the rgba8 frame and the float accumulation of one image alternate through one block

@@ -197,7 +197,7 @@ SOLB_API int solb_synchronize(solb_ctx *ctx) {
     if (!ctx) return fail(nullptr, SOLB_ERR_INVALID, "null ctx");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->p2p_err_host && *ctx->p2p_err_host) return fail(ctx, SOLB_ERR_CUDA, "a peer did not deliver its bands within 20 s (solb_allgather_rows)");
+    if (ctx->p2p_err_host && *ctx->p2p_err_host) return fail(ctx, SOLB_ERR_CUDA, "a peer did not deliver its bands within 10 min (solb_allgather_rows)");
     return SOLB_OK;
 }
 
