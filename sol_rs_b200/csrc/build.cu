@@ -959,7 +959,7 @@ __global__ void k_single_inst_root(const float4 *prim_lo, const float4 *prim_hi,
 __device__ __forceinline__ void collapse_one_warp(const BNode *bn, const int *node_count, int n_internal, CollapseItem item, Node8 *wide,
                                                   uint32_t *wide_count, uint32_t *tri_count, const uint32_t *sorted_prim,
                                                   CollapseItem *queue_out, uint32_t *queue_out_count, uint32_t *leaf_prim_out,
-                                                  const DpEntry *dp) {
+                                                  const DpEntry *dp, int2 *scratch /* 8 entries of shared memory owned by this warp */) {
     const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
     const unsigned FULL = 0xffffffffu;
     // ---- 1. children of the wide node: lanes 0..7 hold (node, budget) in left-to-right order ----
@@ -980,21 +980,20 @@ __device__ __forceinline__ void collapse_one_warp(const BNode *bn, const int *no
         }
         const uint32_t m_split = __ballot_sync(FULL, split_k != 0);
         if (m_split == 0u) break;
-        // new position: every splitting candidate to the left shifts this one right by one
+        // new position: every splitting candidate to the left shifts this one right by one.  The candidates (at most 8, on
+        // lanes 0..7) write themselves - or their two halves - to the warp's scratch row and every lane reads its new one back:
+        // two stores and a load per round where a shuffle scatter took 56 shuffles (the expansion was 40 % of a call).
+        const uint32_t m_have = __ballot_sync(FULL, c_node >= 0);
         const int pos = (int)lane + __popc(m_split & lt_mask);
-        // scatter through shuffles: destination lane d reads from the source whose pos == d (left / stays) or pos + 1 == d (right)
-        int n_node = -1, n_budget = 0;
-        for (int src = 0; src < 8; src++) {
-            const int s_pos = __shfl_sync(FULL, pos, src), s_k = __shfl_sync(FULL, split_k, src);
-            const int s_node = __shfl_sync(FULL, c_node, src), s_l = __shfl_sync(FULL, l, src), s_r = __shfl_sync(FULL, r, src);
-            const int s_b = __shfl_sync(FULL, b, src), s_budget = __shfl_sync(FULL, c_budget, src);
-            if (s_node < 0) continue;
-            if (s_k) {
-                if ((int)lane == s_pos) { n_node = s_l; n_budget = s_k; }
-                if ((int)lane == s_pos + 1) { n_node = s_r; n_budget = s_b - s_k; }
-            } else if ((int)lane == s_pos) { n_node = s_node; n_budget = s_budget; }
+        if (c_node >= 0) {
+            if (split_k) { scratch[pos] = make_int2(l, split_k); scratch[pos + 1] = make_int2(r, b - split_k); }
+            else scratch[pos] = make_int2(c_node, c_budget);
         }
-        c_node = n_node; c_budget = n_budget;
+        __syncwarp();
+        const int n_now = __popc(m_have) + __popc(m_split);
+        const int2 mine = (int)lane < n_now ? scratch[lane] : make_int2(-1, 0);
+        c_node = mine.x; c_budget = mine.y;
+        __syncwarp();
     }
     const int n = __popc(__ballot_sync(FULL, c_node >= 0));  // 2..8 children, on lanes 0..n-1
     // ---- 2. per child (lane i < n): box, count, leaf flag ----
@@ -1140,6 +1139,23 @@ __device__ __forceinline__ void collapse_one_warp(const BNode *bn, const int *no
     }
 }
 
+// blas id + transform of instance i through 8-byte loads: the 200-byte records are 8-byte aligned, and 17 scalar loads at a
+// 200-byte stride cost the single SM of the TLAS kernel one L1 transaction per lane each (the box and leaf-record phases were
+// bound by that)
+__device__ __forceinline__ uint32_t load_instance_placement(const DeviceInstance *instances, uint32_t i, float t[16]) {
+    static_assert(sizeof(DeviceInstance) % 8 == 0 && offsetof(DeviceInstance, blas) == 16 && offsetof(DeviceInstance, transform) == 24,
+                  "DeviceInstance layout");
+    const uint2 *p = (const uint2 *)((const char *)(instances + i) + 16);
+    const uint2 head = __ldg(p);  // blas, shade_first_tri
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint2 v = __ldg(p + 1 + k);
+        t[2 * k] = __uint_as_float(v.x);
+        t[2 * k + 1] = __uint_as_float(v.y);
+    }
+    return head.x;
+}
+
 // Single-CTA TLAS build for up to TLAS_FAST_MAX instances: TLAS::regenerate runs every frame in the reference
 // (examples/5-pathtrace.rs:316), so for the instance counts it is used with (8 ... a few thousand) the whole rebuild is ONE
 // launch working out of shared memory: instance boxes -> Morton keys -> bitonic sort -> Karras links -> atomic-flag refit ->
@@ -1165,7 +1181,7 @@ __host__ __device__ inline size_t tlas_fast_smem_bytes(uint32_t n) {
 // memory cost 49 000 of the kernel's 430 000 cycles at 1 000 instances
 __host__ __device__ inline size_t tlas_fast_dp_offset(uint32_t n) { return (tlas_fast_smem_bytes(n) + 31) & ~(size_t)31; }
 __host__ __device__ inline size_t tlas_fast_smem_bytes_dp(uint32_t n) { return tlas_fast_dp_offset(n) + (size_t)(2 * n) * sizeof(DpEntry); }
-constexpr size_t TLAS_FAST_SMEM_LIMIT = 227 * 1024 - 512;  // dynamic + the kernel's static shared memory must fit 227 KB
+constexpr size_t TLAS_FAST_SMEM_LIMIT = 227 * 1024 - 512 - 2048;  // dynamic + the kernel's static shared memory (incl. 2 KB of warp scratch rows) must fit 227 KB
 
 template <bool COOP>
 __global__ void __launch_bounds__(COOP ? TLAS_FAST_THREADS_COOP : TLAS_FAST_THREADS)
@@ -1177,6 +1193,7 @@ k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, con
     __shared__ uint32_t s_bounds[6];
     __shared__ uint32_t s_counters[3];  // wide nodes, leaf slots, next queue size
     __shared__ uint32_t s_items, s_depth;
+    __shared__ int2 s_expand[COOP ? TLAS_FAST_THREADS_COOP / 32 : 1][8];  // collapse_one_warp: a scratch row per warp
     uint32_t p2 = 2;
     while (p2 < n) p2 <<= 1;
     BNode *bn = (BNode *)smem;
@@ -1202,10 +1219,11 @@ k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, con
     {
         uint32_t bmin[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, bmax[3] = { 0u, 0u, 0u };
         for (uint32_t i = tid; i < n; i += nt) {
-            const DeviceInstance &di = instances[i];
-            const float4 a = blas_box[2 * di.blas], b = blas_box[2 * di.blas + 1];
+            float xf[16];
+            const uint32_t blas = load_instance_placement(instances, i, xf);
+            const float4 a = blas_box[2 * blas], b = blas_box[2 * blas + 1];
             float3 lo, hi;
-            transform_box(di.transform, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), lo, hi);
+            transform_box(xf, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), lo, hi);
             BNode leaf;
             leaf.lo = lo; leaf.hi = hi; leaf.left = -1; leaf.right = -1;
             bn[i] = leaf;  // temporary position; moved to bn[ni + sorted position] after the sort
@@ -1233,10 +1251,13 @@ k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, con
         const float3 inv = f3(ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f);
         for (uint32_t i = tid; i < p2; i += nt) {
             if (i < n) {
+                // the top 53 bits of the 63-bit code (17.6 bits per axis) with the instance index below them: unique keys, so the
+                // sort moves ONE 8-byte word per element and ties need no second array (instances whose codes agree that far
+                // are ordered by index, as equal codes were before)
                 const BNode &b = bn[i];
-                keys[i] = morton63((b.lo + b.hi) * 0.5f, lo, inv);
+                static_assert(TLAS_FAST_MAX <= 2048, "11 index bits");
+                keys[i] = ((morton63((b.lo + b.hi) * 0.5f, lo, inv) >> 10) << 11) | (uint64_t)i;
             } else keys[i] = ~0ull;  // padding sorts last
-            idx[i] = i;
         }
     }
     __syncthreads();
@@ -1246,10 +1267,8 @@ k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, con
                 const uint32_t l = i ^ j;
                 if (l > i) {
                     const uint64_t ka = keys[i], kb = keys[l];
-                    const uint32_t ia = idx[i], ib = idx[l];
-                    const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
                     const bool up = (i & k) == 0;
-                    if (a_gt_b == up) { keys[i] = kb; keys[l] = ka; idx[i] = ib; idx[l] = ia; }
+                    if ((ka > kb) == up) { keys[i] = kb; keys[l] = ka; }
                 }
             }
             // partners closer than 32 sit in the same warp's 32 consecutive elements: between two such stages a warp barrier is
@@ -1257,6 +1276,8 @@ k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, con
             const uint32_t next_j = j > 1 ? (j >> 1) : k;
             if (j >= 32u || next_j >= 32u || (k == p2 && j == 1u)) __syncthreads(); else __syncwarp();
         }
+    for (uint32_t i = tid; i < p2; i += nt) idx[i] = (uint32_t)(keys[i] & 2047u);
+    __syncthreads();
     TLAS_STAMP();  // 2: keys + sort
     // 3. move the boxes to their sorted leaf slots.  Source bn[idx[i]] (i < n) and destination bn[ni + i] ranges overlap:
     //    stage through registers with a barrier in between (every thread owns at most ceil(n / nt) <= 2 leaves).
@@ -1343,7 +1364,8 @@ k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, con
         if (n_items == 0) break;
         if (COOP) {
             for (uint32_t i = tid >> 5; i < n_items; i += nt >> 5)
-                collapse_one_warp(bn, count, ni, queue_a[i], wide, &s_counters[0], &s_counters[1], idx, queue_b, &s_counters[2], leaf_prim, dp);
+                collapse_one_warp(bn, count, ni, queue_a[i], wide, &s_counters[0], &s_counters[1], idx, queue_b, &s_counters[2], leaf_prim, dp,
+                                  s_expand[tid >> 5]);
         } else {
             for (uint32_t i = tid; i < n_items; i += nt)
                 collapse_one(bn, count, ni, queue_a[i], wide, &s_counters[0], &s_counters[1], idx, nullptr, nullptr, queue_b, &s_counters[2],
@@ -1358,7 +1380,9 @@ k_tlas_build_small(const DeviceInstance *__restrict__ instances, uint32_t n, con
     // 7. instance leaf records in TLAS leaf order
     for (uint32_t j = tid; j < n; j += nt) {
         const uint32_t i = leaf_prim[j];
-        inst_leaves[j] = make_inst_leaf(instances[i].transform, tlas_cap + instances[i].blas, i);
+        float xf[16];
+        const uint32_t blas = load_instance_placement(instances, i, xf);
+        inst_leaves[j] = make_inst_leaf(xf, tlas_cap + blas, i);
     }
     if (tid == 0) {
         info->n_wide = s_counters[0]; info->depth = s_depth; info->leaf_count = s_counters[1];
