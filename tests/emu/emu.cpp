@@ -34,6 +34,8 @@ struct EmuScene {
     std::vector<Node8> nodes;
     std::vector<Tri48> tris;
     std::vector<InstLeaf> inst_leaves;
+    std::vector<std::vector<float4>> texels;  // base-colour textures (linear light), as solb_scene_set_textures uploads them
+    std::vector<TexDesc> tex;
     bool two_level = false;
     uint32_t n_tris = 0, n_geom_tris = 0, depth = 0, tlas_depth = 0;
     float sah_lbvh = 0, sah_final = 0;
@@ -400,6 +402,31 @@ void emu_debug(EmuScene *s, const float *uniforms, uint32_t w, uint32_t h, uint3
         }
 }
 
+// mirrors solb_scene_set_textures: inst_tex[i] = texture of instance i or 0xffffffff
+void emu_scene_set_textures(EmuScene *s, uint32_t n_tex, const uint8_t *const *rgba8, const uint32_t *width, const uint32_t *height,
+                            const uint32_t *wrap_s, const uint32_t *wrap_t, const uint32_t *inst_tex) {
+    float lut[256];
+    for (int i = 0; i < 256; i++) {
+        const float x = (float)i / 255.0f;
+        lut[i] = x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
+    }
+    s->texels.assign(n_tex, {});
+    s->tex.assign(n_tex, TexDesc{});
+    for (uint32_t t = 0; t < n_tex; t++) {
+        const size_t n = (size_t)width[t] * height[t];
+        s->texels[t].resize(n);
+        for (size_t i = 0; i < n; i++)
+            s->texels[t][i] = make_float4(lut[rgba8[t][4 * i]], lut[rgba8[t][4 * i + 1]], lut[rgba8[t][4 * i + 2]], (float)rgba8[t][4 * i + 3] / 255.0f);
+        s->tex[t].texels = s->texels[t].data();
+        s->tex[t].width = width[t]; s->tex[t].height = height[t];
+        s->tex[t].wrap_s = wrap_s[t] ? wrap_s[t] : 10497u; s->tex[t].wrap_t = wrap_t[t] ? wrap_t[t] : 10497u;
+    }
+    for (size_t i = 0; i < s->inst.size(); i++) {
+        const uint32_t t1 = (n_tex && inst_tex[i] < n_tex) ? inst_tex[i] + 1u : 0u;
+        memcpy(&s->inst[i].mat[10], &t1, sizeof(t1));
+    }
+}
+
 // mirrors k_pathtrace_mega
 void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_t h, int accum_start, int enable_sky, int spp,
                          int max_bounces, int accum_mode, float *accum, uint32_t *render, uint64_t *stats) {
@@ -407,6 +434,7 @@ void emu_pathtrace_frame(EmuScene *s, const float *uniforms, uint32_t w, uint32_
     fill_fc(fc, uniforms, w, h);
     fc.accum_start = accum_start; fc.enable_sky = (uint32_t)enable_sky; fc.spp = (uint32_t)spp; fc.max_bounces = (uint32_t)max_bounces;
     fc.accum_mode = (uint32_t)accum_mode;
+    fc.texb.tex = s->tex.data(); fc.texb.vertices = s->vertices.data(); fc.texb.indices = s->indices.data(); fc.texb.n_tex = (uint32_t)s->tex.size();
     uint64_t nrays = 0, nhits = 0, nnodes = 0, ntris = 0;
 #pragma omp parallel for schedule(dynamic, 2) reduction(+ : nrays, nhits, nnodes, ntris)
     for (int64_t y = 0; y < (int64_t)h; y++)

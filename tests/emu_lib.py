@@ -97,6 +97,21 @@ class EmuScene:
         rc = (lib().emu_build_two_level if self.two_level else lib().emu_build)(self.h, self.passes, self.gamma)
         assert rc == 0, "emu_build: triangle / instance count mismatch"
 
+    def set_textures(self, textures, material_textures, flat):
+        """textures = [(rgba8 [h, w, 4] rows top first, wrap_s, wrap_t)], material_textures = per material an index or None"""
+        n = len(textures)
+        imgs = [np.ascontiguousarray(t[0], dtype=np.uint8) for t in textures]
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in imgs])
+        w = np.array([a.shape[1] for a in imgs], dtype=np.uint32)
+        h = np.array([a.shape[0] for a in imgs], dtype=np.uint32)
+        ws = np.array([t[1] for t in textures], dtype=np.uint32)
+        wt = np.array([t[2] for t in textures], dtype=np.uint32)
+        it = np.array([0xFFFFFFFF if material_textures[i["material"]] is None else material_textures[i["material"]] for i in flat.instances],
+                      dtype=np.uint32)
+        L = lib()
+        L.emu_scene_set_textures.argtypes = [ctypes.c_void_p, ctypes.c_uint32] + [ctypes.c_void_p] * 6
+        L.emu_scene_set_textures(self.h, n, ptrs, _p(w), _p(h), _p(ws), _p(wt), _p(it))
+
     def set_transform(self, index, transform):
         t = np.ascontiguousarray(transform, dtype=np.float32).reshape(4, 4)
         tit = np.ascontiguousarray(gf.mat4_inverse(t).T, dtype=np.float32)

@@ -66,6 +66,30 @@ def test_emu_pathtrace_frame(name, w, h, sky, mb):
     assert d.sum() / a[..., :3].sum() < 0.01
 
 
+def test_emu_textured_duck_frame():
+    """shade.cuh's base-colour texture path (an extension shared with the oracle) on the CPU tier: the device
+    code compiled for the host, Duck.gltf with DuckCM.png, against the oracle carrying the same extension."""
+    fs, osc = oracle_scene("Duck")
+    assert len(fs.textures) == 1 and fs.material_textures == [0]
+    es = emu_lib.EmuScene(fs, 2)
+    osc.set_textures(fs.textures, fs.material_textures)
+    es.set_textures(fs.textures, fs.material_textures, fs)
+    w, h = 96, 72
+    cam = oracle_camera(fs, "Duck", w, h)
+    a, b, plain = (np.zeros((h, w, 4), np.float32) for _ in range(3))
+    for f in range(2):
+        u = ocam.scene_uniforms(cam, w, h, f)
+        osc.pathtrace_frame(u, w, h, a, 0, True, 8, 4, oracle.OrcStats())
+        es.pathtrace_frame(u, w, h, b, 0, True, 8, 4)
+    d = np.abs(a - b)[..., :3]
+    assert (d.max(axis=2) > 1e-3 * (1 + a[..., :3].max(axis=2))).mean() < 0.02
+    assert d.sum() / a[..., :3].sum() < 0.01
+    es.set_textures([], fs.material_textures, fs)
+    for f in range(2):
+        es.pathtrace_frame(ocam.scene_uniforms(cam, w, h, f), w, h, plain, 0, True, 8, 4)
+    assert np.abs(plain - b)[..., :3].max(axis=2).mean() > 1e-3  # the texture did something
+
+
 def test_emu_rng_bit_exact():
     L = emu_lib.lib()
     import ctypes
