@@ -1,6 +1,6 @@
 // pathtrace_offscreen.cpp — examples/5-pathtrace.rs of the reference without the window: the same setup() /
 // render() call sequence through the C++ host mirror (sol.hpp), frames read back instead of presented.
-//   pathtrace_offscreen --model models/cornell.gltf [--sky] [--frames 8] [--size 512x512] [--bounces 32]
+//   pathtrace_offscreen --model models/cornell.gltf [--sky] [--frames 8] [--size 512x512] [--bounces 32] [--textures]
 //                       [--debug] [--two-level] [--out frame.ppm]
 // Prints one line: frames, ms/frame, Mrays/s, and an FNV-1a checksum of the final rgba8 frame.
 #include <chrono>
@@ -16,12 +16,13 @@ using namespace sol;
 
 int main(int argc, char **argv) {
     std::string model, out;
-    bool enable_sky = false, debug = false, two_level = false;
+    bool enable_sky = false, debug = false, two_level = false, textures = false;
     uint32_t frames = 8, w = 1280, h = 720, bounces = 0;  // 1280x720: examples/5-pathtrace.rs:374
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--model" && i + 1 < argc) model = argv[++i];       // examples/5-pathtrace.rs:120-125
         else if (a == "--sky") enable_sky = true;                     // :220
+        else if (a == "--textures") textures = true;                  // beyond the reference: bind the base-colour textures
         else if (a == "--debug") debug = true;
         else if (a == "--two-level") two_level = true;  // TLAS over object-space BLASes instead of the flattened hierarchy
         else if (a == "--frames" && i + 1 < argc) frames = (uint32_t)atoi(argv[++i]);
@@ -37,6 +38,7 @@ int main(int argc, char **argv) {
         if (!path) path = model;
         scene::Scene scene = scene::load_scene(context, *path);
         ray::SceneDescription scene_description = ray::SceneDescription::from_scene(context, scene);
+        if (textures) scene_description.set_textures(scene);
         if (two_level) {
             scene_description.set_accel_mode(SOLB_ACCEL_TWO_LEVEL);
             scene_description.accel_build();
