@@ -952,7 +952,20 @@ static int ensure_wavefront(solb_ctx *ctx, uint32_t n_pixels) {
     return SOLB_OK;
 }
 
-static int ensure_warpfront(solb_ctx *ctx, int k, size_t n_pixels) {
+static int ensure_warpfront_slot(solb_ctx *ctx, int k, size_t n_pixels);
+
+// Every frame slot in use is sized by the first frame that needs it (not slot k by the k-th frame): allocation and the
+// synchronisation it needs then fall into the first frame of a size - a warm-up frame - instead of the first three.
+static int ensure_warpfront(solb_ctx *ctx, size_t n_pixels) {
+    const int n_slots = std::max(1, std::min(ctx->tune.wl_frames_in_flight, (int)WL_MAX_FRAMES));
+    for (int k = 0; k < n_slots; k++) {
+        const int rc = ensure_warpfront_slot(ctx, k, n_pixels);
+        if (rc != SOLB_OK) return rc;
+    }
+    return SOLB_OK;
+}
+
+static int ensure_warpfront_slot(solb_ctx *ctx, int k, size_t n_pixels) {
     WarpfrontState &w = ctx->wl[k];
     const uint32_t n_warps = warpfront_grid_warps(ctx->sm_count, ctx->tune);
     if (!ctx->frame_stream[k]) {
@@ -1036,7 +1049,7 @@ SOLB_API int solb_trace_pathtrace(solb_scene *s, const SolbSceneUniforms *u, con
         // the previous frame's kernel drains (its last pixels are chains of ~50 rays each: ~9 % of a 1080p frame with the SMs
         // emptying), and everything later on the ctx stream is ordered after this frame's resolve as before.
         const int k = (int)(ctx->frame_slot = (ctx->frame_slot + 1u) % (uint32_t)std::max(ctx->tune.wl_frames_in_flight, 1));
-        if ((rc = ensure_warpfront(ctx, k, (size_t)fc.width * fc.height))) return rc;
+        if ((rc = ensure_warpfront(ctx, (size_t)fc.width * fc.height))) return rc;
         cudaStream_t side = ctx->frame_stream[k];
         const bool serial = ctx->timing || ctx->tune.wl_frames_in_flight < 2;
         if (serial) {  // after everything already on the ctx stream (incl. the previous frame's resolve)
